@@ -1,0 +1,135 @@
+// Shared device/host plumbing for libeth3d_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/eth3d_b200.h"
+
+namespace b2 {
+
+// ---- error plumbing -------------------------------------------------------------------------------------------
+inline std::string& last_error_ref() { static thread_local std::string e; return e; }
+inline int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+#define B2_CUDA(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess)                                                                              \
+      return ::b2::set_error(B2_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,          \
+                             cudaGetErrorString(_e));                                                   \
+  } while (0)
+#define B2_TRY(expr) do { int _rc = (expr); if (_rc != B2_OK) return _rc; } while (0)
+
+// ---- grow-only device buffer ----------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return B2_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;   // slack so small growth does not re-allocate
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return set_error(B2_ERR_ALLOC, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    cap = want;
+    return B2_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return B2_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e != cudaSuccess) return set_error(B2_ERR_ALLOC, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    cap = bytes;
+    return B2_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ---- device selection: fail loudly, no CPU fallback ------------------------------------------------------------
+inline int select_device(int requested, int* out_dev, int* out_sms) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return set_error(B2_ERR_NO_DEVICE, "no CUDA device available (%s); libeth3d_b200 has no CPU fallback",
+                     e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  int dev = requested;
+  if (dev < 0) { B2_CUDA(cudaGetDevice(&dev)); }
+  if (dev >= count) return set_error(B2_ERR_ARG, "device %d out of range (%d devices)", dev, count);
+  cudaDeviceProp prop;
+  B2_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return set_error(B2_ERR_NO_DEVICE, "device %d (%s) is sm_%d%d; this library is built for sm_100a only", dev,
+                     prop.name, prop.major, prop.minor);
+  B2_CUDA(cudaSetDevice(dev));
+  *out_dev = dev;
+  *out_sms = prop.multiProcessorCount;
+  return B2_OK;
+}
+
+// ---- fp32 arithmetic without FMA contraction (bit-parity with the CPU evaluation order) -------------------------
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+// Eigen 3-term reduction order a0 + (a1 + a2).
+__device__ __forceinline__ float sum3(float a, float b, float c) { return fadd(a, fadd(b, c)); }
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+  return sum3(fmul(ax, bx), fmul(ay, by), fmul(az, bz));
+}
+
+// Column-major 4x4 rigid transform applied the way pcl::transformPointCloudWithNormals does (PCL 1.10 SSE path):
+//   point : x*c0 + (y*c1 + (z*c2 + c3))      normal: x*c0 + (y*c1 + z*c2)
+struct Mat4 { float m[16]; };
+__device__ __forceinline__ float3 xform_point(const Mat4& T, float x, float y, float z) {
+  float3 o;
+  o.x = fadd(fmul(x, T.m[0]), fadd(fmul(y, T.m[4]), fadd(fmul(z, T.m[8]), T.m[12])));
+  o.y = fadd(fmul(x, T.m[1]), fadd(fmul(y, T.m[5]), fadd(fmul(z, T.m[9]), T.m[13])));
+  o.z = fadd(fmul(x, T.m[2]), fadd(fmul(y, T.m[6]), fadd(fmul(z, T.m[10]), T.m[14])));
+  return o;
+}
+__device__ __forceinline__ float3 xform_normal(const Mat4& T, float x, float y, float z) {
+  float3 o;
+  o.x = fadd(fmul(x, T.m[0]), fadd(fmul(y, T.m[4]), fmul(z, T.m[8])));
+  o.y = fadd(fmul(x, T.m[1]), fadd(fmul(y, T.m[5]), fmul(z, T.m[9])));
+  o.z = fadd(fmul(x, T.m[2]), fadd(fmul(y, T.m[6]), fmul(z, T.m[10])));
+  return o;
+}
+
+// ---- uniform grid over the union bounding box ------------------------------------------------------------------
+struct GridParams {
+  double ox, oy, oz;   // origin (bbox min)
+  double inv;          // 1 / cell size
+  int nx, ny, nz;      // cells per axis (each < 2^21)
+};
+__host__ __device__ __forceinline__ int cell_of(float v, double o, double inv) {
+  return (int)floor(((double)v - o) * inv);
+}
+__host__ __device__ __forceinline__ unsigned long long cell_key(const GridParams& g, int cx, int cy, int cz) {
+  return ((unsigned long long)cz * (unsigned long long)g.ny + (unsigned long long)cy) * (unsigned long long)g.nx +
+         (unsigned long long)cx;
+}
+
+struct HashEntry { unsigned long long key; unsigned int begin, end; };   // 16 B: one LDG.128 per probe
+static constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+__host__ __device__ __forceinline__ unsigned int hash_slot(unsigned long long key, int log2size) {
+  return (unsigned int)((key * 0x9E3779B97F4A7C15ull) >> (64 - log2size));
+}
+
+}  // namespace b2

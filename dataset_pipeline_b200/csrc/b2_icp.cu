@@ -1,0 +1,671 @@
+// Host side of Path A behind the C ABI (include/eth3d_b200.h): owns device memory, builds the spatial index,
+// schedules the pair-directions, runs the LM loop of PointToPlaneICPImpl::compute on top of the streaming kernels.
+//
+// Reference seams replaced (see the header for the signatures):
+//   PointToPlaneICP::AddPointCloud  /root/reference/src/icp/icp_point_to_plane.cc:109-135
+//   PointToPlaneICP::Run            :137-163        AlignMeshes :169-342
+//   PointToPlaneICPImpl::compute    /root/reference/src/icp/icp_point_to_plane_impl.h:115-293
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <memory>
+#include <vector>
+
+#include "b2_common.cuh"
+#include "b2_hostmath.h"
+#include "b2_icp_kernels.cuh"
+
+namespace b2 {
+
+struct Cloud {
+  size_t n = 0;
+  bool is_fixed = false;
+  DevBuf local_xyz, local_nrm;          // packed float3 (cloud frame; global frame for the fixed cloud)
+  float T[16];                          // global_T_cloud, column-major
+  float bmin[3], bmax[3];               // AABB of the global-frame cloud (this outer iteration)
+  DevBuf keys_in, keys_out, idx_in, perm, s_xyz, s_nrm, table;
+  int log2size = 0;
+  unsigned int ncells = 0;
+};
+
+struct Direction {
+  int src = 0, tgt = 0;                 // impl cloud indices
+  bool local = false;                   // searched / accumulated on this rank
+  DevBuf match, d2, flags, offs;
+  unsigned long long count = 0, rec_begin = 0;
+};
+
+static inline Mat4 mat4_of(const float T[16]) { Mat4 m; std::memcpy(m.m, T, sizeof(m.m)); return m; }
+static inline unsigned int div_up(size_t a, size_t b) { return (unsigned int)((a + b - 1) / b); }
+
+}  // namespace b2
+
+using namespace b2;
+
+struct b2_icp {
+  b2_icp_config cfg;
+  int device = 0, sms = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::vector<std::unique_ptr<Cloud>> movable;
+  std::unique_ptr<Cloud> fixed;         // concatenated global-frame fixed cloud (may be null)
+  std::vector<std::unique_ptr<Direction>> dirs;   // pool, reused across outer iterations
+  int ndirs = 0;
+  // scratch
+  DevBuf bbox_partial, cub_tmp, cell_counts, rec_a, rec_b, rec_c, segs_dev, poses_dev, partials, segsum, eq_dev, scatter_m, scatter_d;
+  PinnedBuf pin_bbox, pin_counts, pin_eq, pin_poses, pin_segs, pin_misc;
+  // last outer iteration
+  b2_icp_stats stats;
+  std::vector<int32_t> tries;
+  std::vector<double> H0, b0;
+  double cost0 = 0;
+  std::vector<Segment> segs_host;       // local non-empty segments
+  std::vector<int> seg_dir;             // segs_host[k] -> dirs index
+  unsigned long long total_records = 0;
+  int grid_acc = 0;
+  unsigned long long per_cta = 0;
+  int launches = 0;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> acc_events;
+};
+
+namespace b2 {
+
+static int num_impl_clouds(const b2_icp* h) { return (int)h->movable.size() + (h->fixed ? 1 : 0); }
+static Cloud* impl_cloud(b2_icp* h, int idx) {
+  if (h->fixed) return idx == 0 ? h->fixed.get() : h->movable[idx - 1].get();
+  return h->movable[idx].get();
+}
+static int impl_index_of_movable(const b2_icp* h, int m) { return h->fixed ? m + 1 : m; }
+
+static int upload_cloud(b2_icp* h, Cloud* c, const float* xyz, const float* nrm, size_t n, size_t stride_bytes, bool from_device) {
+  c->n = n;
+  B2_TRY(c->local_xyz.ensure(std::max<size_t>(n, 1) * 12));
+  B2_TRY(c->local_nrm.ensure(std::max<size_t>(n, 1) * 12));
+  if (n == 0) return B2_OK;
+  if (from_device) {
+    B2_CUDA(cudaMemcpyAsync(c->local_xyz.p, xyz, n * 12, cudaMemcpyDeviceToDevice, h->stream));
+    B2_CUDA(cudaMemcpyAsync(c->local_nrm.p, nrm, n * 12, cudaMemcpyDeviceToDevice, h->stream));
+  } else if (stride_bytes == 12) {
+    B2_CUDA(cudaMemcpyAsync(c->local_xyz.p, xyz, n * 12, cudaMemcpyHostToDevice, h->stream));
+    B2_CUDA(cudaMemcpyAsync(c->local_nrm.p, nrm, n * 12, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    B2_CUDA(cudaMemcpy2DAsync(c->local_xyz.p, 12, xyz, stride_bytes, 12, n, cudaMemcpyHostToDevice, h->stream));
+    B2_CUDA(cudaMemcpy2DAsync(c->local_nrm.p, 12, nrm, stride_bytes, 12, n, cudaMemcpyHostToDevice, h->stream));
+  }
+  B2_CUDA(cudaStreamSynchronize(h->stream));   // the caller may free / reuse its buffers after return
+  return B2_OK;
+}
+
+// Sort one cloud into the grid and build its occupied-cell table (K1b, K1c, K2). Two-phase so that all clouds share
+// one host sync for the cell counts.
+static int index_cloud_phase1(b2_icp* h, Cloud* c, const GridParams& g, int key_bits, int slot) {
+  const size_t n = c->n;
+  if (n == 0) { c->ncells = 0; return B2_OK; }
+  B2_TRY(c->keys_in.ensure(n * 8)); B2_TRY(c->keys_out.ensure(n * 8));
+  B2_TRY(c->idx_in.ensure(n * 4)); B2_TRY(c->perm.ensure(n * 4));
+  B2_TRY(c->s_xyz.ensure(n * 16)); B2_TRY(c->s_nrm.ensure(n * 16));
+  const Mat4 T = mat4_of(c->T);
+  k_keys<<<div_up(n, 256), 256, 0, h->stream>>>(c->local_xyz.as<float>(), n, T, g, c->keys_in.as<unsigned long long>(),
+                                                c->idx_in.as<unsigned int>());
+  ++h->launches;
+  size_t tmp = 0;
+  B2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->keys_in.as<unsigned long long>(), c->keys_out.as<unsigned long long>(),
+                                          c->idx_in.as<unsigned int>(), c->perm.as<unsigned int>(), (long long)n, 0, key_bits, h->stream));
+  B2_TRY(h->cub_tmp.ensure(tmp));
+  B2_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, c->keys_in.as<unsigned long long>(), c->keys_out.as<unsigned long long>(),
+                                          c->idx_in.as<unsigned int>(), c->perm.as<unsigned int>(), (long long)n, 0, key_bits, h->stream));
+  k_apply<<<div_up(n, 256), 256, 0, h->stream>>>(c->local_xyz.as<float>(), c->local_nrm.as<float>(), n, T, c->perm.as<unsigned int>(),
+                                                 c->s_xyz.as<float4>(), c->s_nrm.as<float4>());
+  k_count_cells<<<div_up(n, 256), 256, 0, h->stream>>>(c->keys_out.as<unsigned long long>(), n, h->cell_counts.as<unsigned int>() + slot);
+  h->launches += 2;
+  return B2_OK;
+}
+static int index_cloud_phase2(b2_icp* h, Cloud* c) {
+  const size_t n = c->n;
+  if (n == 0) return B2_OK;
+  int lg = 4;
+  while ((1ull << lg) < 2ull * c->ncells) ++lg;
+  c->log2size = lg;
+  B2_TRY(c->table.ensure(sizeof(HashEntry) << lg));
+  B2_CUDA(cudaMemsetAsync(c->table.p, 0xFF, sizeof(HashEntry) << lg, h->stream));
+  k_hash_insert<<<div_up(n, 256), 256, 0, h->stream>>>(c->keys_out.as<unsigned long long>(), n, c->table.as<HashEntry>(), lg);
+  k_hash_ends<<<div_up(n, 256), 256, 0, h->stream>>>(c->keys_out.as<unsigned long long>(), n, c->table.as<HashEntry>(), lg);
+  h->launches += 2;
+  return B2_OK;
+}
+
+static bool boxes_intersect(const Cloud* a, const Cloud* b) {
+  // Eigen::AlignedBox::intersection(...).isEmpty(): empty iff (min > max) on any axis (icp_point_to_plane.cc:214-215).
+  for (int d = 0; d < 3; ++d) if (std::max(a->bmin[d], b->bmin[d]) > std::min(a->bmax[d], b->bmax[d])) return false;
+  return true;
+}
+
+static Direction* next_direction(b2_icp* h) {
+  if (h->ndirs == (int)h->dirs.size()) h->dirs.emplace_back(new Direction());
+  return h->dirs[h->ndirs++].get();
+}
+
+static int compute_grid(b2_icp* h, float max_dist, GridParams* g, int* key_bits) {
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  const int nc = num_impl_clouds(h);
+  for (int i = 0; i < nc; ++i) {
+    const Cloud* c = impl_cloud(h, i);
+    if (c->n == 0) continue;
+    for (int d = 0; d < 3; ++d) { mn[d] = std::min(mn[d], c->bmin[d]); mx[d] = std::max(mx[d], c->bmax[d]); }
+  }
+  if (!(mn[0] <= mx[0])) { mn[0] = mn[1] = mn[2] = 0.f; mx[0] = mx[1] = mx[2] = 0.f; }
+  for (int d = 0; d < 3; ++d)
+    if (!std::isfinite(mn[d]) || !std::isfinite(mx[d]))
+      return set_error(B2_ERR_ARG, "non-finite point coordinates (clouds must be dense, as the reference's is_dense path assumes)");
+  // cell >= d*(1+1e-4): any target with fp32 d2 < fl(d*d) lies in the 27-neighbourhood of the query's cell.
+  double cell = (double)max_dist * 1.0001;
+  if (!(cell > 0.0)) cell = 1e-30;
+  const double ext = std::max({(double)mx[0] - mn[0], (double)mx[1] - mn[1], (double)mx[2] - mn[2]});
+  cell = std::max(cell, ext / 2097000.0);    // keep every axis below 2^21 cells
+  g->ox = mn[0]; g->oy = mn[1]; g->oz = mn[2];
+  g->inv = 1.0 / cell;
+  g->nx = cell_of(mx[0], g->ox, g->inv) + 1;
+  g->ny = cell_of(mx[1], g->oy, g->inv) + 1;
+  g->nz = cell_of(mx[2], g->oz, g->inv) + 1;
+  const unsigned long long maxkey = cell_key(*g, g->nx - 1, g->ny - 1, g->nz - 1);
+  int bits = 1;
+  while (bits < 64 && (maxkey >> bits) != 0ull) ++bits;
+  *key_bits = bits;
+  return B2_OK;
+}
+
+// One streaming pass (K5 + K6) at the given increments; returns [H|b|cost|extras] in h->pin_eq (host) after the
+// optional cross-rank reduction.
+static int run_pass(b2_icp* h, const std::vector<Pose>& poses, bool with_h, int nv) {
+  const int nc = (int)poses.size();
+  CloudPose* pp = h->pin_poses.as<CloudPose>();
+  for (int i = 0; i < nc; ++i) { quat_matrix(poses[i].q, pp[i].R); for (int k = 0; k < 3; ++k) pp[i].t[k] = poses[i].t[k]; }
+  B2_CUDA(cudaMemcpyAsync(h->poses_dev.p, pp, sizeof(CloudPose) * nc, cudaMemcpyHostToDevice, h->stream));
+  const int nseg = (int)h->segs_host.size();
+  const size_t eq_count = (size_t)nv * nv + nv + 3;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->total_records > 0) {
+    B2_CUDA(cudaEventCreate(&e0)); B2_CUDA(cudaEventCreate(&e1));
+    B2_CUDA(cudaEventRecord(e0, h->stream));
+    if (with_h)
+      k_accumulate<true><<<h->grid_acc, kAccThreads, 0, h->stream>>>(h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>(),
+                                                                    h->segs_dev.as<Segment>(), nseg, h->poses_dev.as<CloudPose>(),
+                                                                    h->total_records, h->per_cta, h->partials.as<double>());
+    else
+      k_accumulate<false><<<h->grid_acc, kAccThreads, 0, h->stream>>>(h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>(),
+                                                                     h->segs_dev.as<Segment>(), nseg, h->poses_dev.as<CloudPose>(),
+                                                                     h->total_records, h->per_cta, h->partials.as<double>());
+    B2_CUDA(cudaEventRecord(e1, h->stream));
+    h->acc_events.emplace_back(e0, e1);
+    ++h->launches;
+  }
+  double local_pairs = (double)nseg, local_corr = (double)h->total_records;
+  if (with_h)
+    k_finalize<true><<<1, 1024, 0, h->stream>>>(h->partials.as<double>(), h->segs_dev.as<Segment>(), nseg, h->grid_acc, h->per_cta, nv,
+                                                h->segsum.as<double>(), h->eq_dev.as<double>(), local_pairs, local_corr);
+  else
+    k_finalize<false><<<1, 1024, 0, h->stream>>>(h->partials.as<double>(), h->segs_dev.as<Segment>(), nseg, h->grid_acc, h->per_cta, nv,
+                                                 h->segsum.as<double>(), h->eq_dev.as<double>(), local_pairs, local_corr);
+  ++h->launches;
+  B2_CUDA(cudaGetLastError());
+  if (h->cfg.world_size > 1) {
+    // Data-parallel exchange: ONE sum-allreduce of the packed normal equations per pass (NCCL over NVLink on the host side).
+    double* buf = h->eq_dev.as<double>();
+    size_t off = 0, cnt = eq_count;
+    if (!with_h) { off = (size_t)nv * nv + nv; cnt = 3; }
+    if (h->cfg.allreduce(h->cfg.allreduce_user, buf + off, cnt, (void*)h->stream) != 0)
+      return set_error(B2_ERR_COMM, "allreduce hook failed");
+  }
+  B2_CUDA(cudaMemcpyAsync(h->pin_eq.p, h->eq_dev.p, eq_count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  ++h->stats.passes;
+  return B2_OK;
+}
+
+static float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+// AlignMeshes (icp_point_to_plane.cc:169-342).
+static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* converged, bool search_only = false, bool gate = true) {
+  h->launches = 0;
+  std::memset(&h->stats, 0, sizeof(h->stats));
+  h->tries.clear();
+  for (auto& pr : h->acc_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  h->acc_events.clear();
+  const int nc = num_impl_clouds(h);
+  const int nmov = (int)h->movable.size();
+  const int nv = 6 * (nc - 1);
+  B2_CUDA(cudaEventRecord(h->ev[0], h->stream));
+
+  // ---- K1a: bounding boxes of the global-frame clouds ----
+  const int bb_blocks = h->sms * 2;
+  B2_TRY(h->bbox_partial.ensure((size_t)nc * bb_blocks * 6 * sizeof(float)));
+  B2_TRY(h->pin_bbox.ensure((size_t)nc * bb_blocks * 6 * sizeof(float)));
+  for (int i = 0; i < nc; ++i) {
+    Cloud* c = impl_cloud(h, i);
+    if (c->n == 0) continue;
+    k_bbox<<<bb_blocks, 256, 0, h->stream>>>(c->local_xyz.as<float>(), c->n, mat4_of(c->T), h->bbox_partial.as<float>() + (size_t)i * bb_blocks * 6);
+    ++h->launches;
+  }
+  B2_CUDA(cudaMemcpyAsync(h->pin_bbox.p, h->bbox_partial.p, (size_t)nc * bb_blocks * 6 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < nc; ++i) {
+    Cloud* c = impl_cloud(h, i);
+    for (int d = 0; d < 3; ++d) { c->bmin[d] = INFINITY; c->bmax[d] = -INFINITY; }
+    if (c->n == 0) continue;
+    const float* p = h->pin_bbox.as<float>() + (size_t)i * bb_blocks * 6;
+    for (int b = 0; b < bb_blocks; ++b)
+      for (int d = 0; d < 3; ++d) { c->bmin[d] = std::min(c->bmin[d], p[b * 6 + d]); c->bmax[d] = std::max(c->bmax[d], p[b * 6 + 3 + d]); }
+  }
+
+  // ---- K1b/K1c/K2: common grid, cell sort, occupied-cell tables ----
+  GridParams g; int key_bits = 0;
+  B2_TRY(compute_grid(h, max_dist, &g, &key_bits));
+  B2_TRY(h->cell_counts.ensure(sizeof(unsigned int) * nc));
+  B2_TRY(h->pin_counts.ensure(sizeof(unsigned long long) * (size_t)std::max(nc, 4 * nmov * nmov + 4 * nmov + 4)));
+  B2_CUDA(cudaMemsetAsync(h->cell_counts.p, 0, sizeof(unsigned int) * nc, h->stream));
+  for (int i = 0; i < nc; ++i) B2_TRY(index_cloud_phase1(h, impl_cloud(h, i), g, key_bits, i));
+  B2_CUDA(cudaMemcpyAsync(h->pin_counts.p, h->cell_counts.p, sizeof(unsigned int) * nc, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < nc; ++i) { impl_cloud(h, i)->ncells = h->pin_counts.as<unsigned int>()[i]; B2_TRY(index_cloud_phase2(h, impl_cloud(h, i))); }
+  B2_CUDA(cudaEventRecord(h->ev[1], h->stream));
+
+  // ---- pair scheduling in ik order (icp_point_to_plane.cc:208-309) ----
+  h->ndirs = 0;
+  const int fixed_idx = h->fixed ? 0 : -1;
+  for (int i = 0; i < nmov; ++i) {
+    for (int k = 0; k < nmov; ++k) {
+      Cloud* A = h->movable[i].get(); Cloud* B = h->movable[k].get();
+      if (i != k && (!gate || boxes_intersect(A, B))) {
+        Direction* d = next_direction(h); d->src = impl_index_of_movable(h, i); d->tgt = impl_index_of_movable(h, k);
+      }
+      if (i == k && h->fixed && boxes_intersect(h->fixed.get(), A)) {
+        Direction* d = next_direction(h); d->src = impl_index_of_movable(h, i); d->tgt = fixed_idx;
+        Direction* e = next_direction(h); e->src = fixed_idx; e->tgt = impl_index_of_movable(h, i);
+      }
+    }
+  }
+  const int world = std::max(1, h->cfg.world_size), rank = h->cfg.rank;
+  const float r2 = (float)((double)max_dist * (double)max_dist);
+
+  // ---- K3 + compaction offsets ----
+  unsigned long long* counts = h->pin_counts.as<unsigned long long>();
+  B2_TRY(h->pin_misc.ensure(sizeof(unsigned int) * 2 * (size_t)std::max(1, h->ndirs)));
+  unsigned int* tails = h->pin_misc.as<unsigned int>();
+  for (int k = 0; k < h->ndirs; ++k) {
+    Direction* d = h->dirs[k].get();
+    d->local = (k % world) == rank;
+    d->count = 0;
+    if (!d->local) continue;
+    Cloud* S = impl_cloud(h, d->src); Cloud* T = impl_cloud(h, d->tgt);
+    const size_t ns = S->n;
+    tails[2 * k] = tails[2 * k + 1] = 0;
+    if (ns == 0 || T->n == 0) continue;
+    B2_TRY(d->match.ensure(ns * 4)); B2_TRY(d->d2.ensure(ns * 4)); B2_TRY(d->flags.ensure(ns * 4)); B2_TRY(d->offs.ensure(ns * 4));
+    k_nn_radius1<<<div_up(ns, 256), 256, 0, h->stream>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->table.as<HashEntry>(),
+                                                         T->log2size, g, r2, d->match.as<int>(), d->d2.as<float>(), d->flags.as<unsigned int>());
+    ++h->launches;
+    size_t tmp = 0;
+    B2_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d->flags.as<unsigned int>(), d->offs.as<unsigned int>(), (long long)ns, h->stream));
+    B2_TRY(h->cub_tmp.ensure(tmp));
+    B2_CUDA(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tmp, d->flags.as<unsigned int>(), d->offs.as<unsigned int>(), (long long)ns, h->stream));
+    B2_CUDA(cudaMemcpyAsync(&tails[2 * k], d->offs.as<unsigned int>() + (ns - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaMemcpyAsync(&tails[2 * k + 1], d->flags.as<unsigned int>() + (ns - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  B2_CUDA(cudaEventRecord(h->ev[2], h->stream));
+  (void)counts;
+
+  // ---- K4: pack local non-empty sets into one record array ----
+  h->segs_host.clear(); h->seg_dir.clear();
+  unsigned long long total = 0;
+  for (int k = 0; k < h->ndirs; ++k) {
+    Direction* d = h->dirs[k].get();
+    if (!d->local) continue;
+    d->count = (unsigned long long)tails[2 * k] + tails[2 * k + 1];
+    d->rec_begin = total;
+    if (d->count == 0) continue;   // empty sets are not registered (icp_point_to_plane.cc:240)
+    h->segs_host.push_back(Segment{total, total + d->count, d->src, d->tgt});
+    h->seg_dir.push_back(k);
+    total += d->count;
+  }
+  h->total_records = total;
+  const int nseg = (int)h->segs_host.size();
+  if (search_only) { *converged = false; h->stats.kernel_launches = h->launches; return B2_OK; }
+  B2_TRY(h->rec_a.ensure(std::max<unsigned long long>(total, 1) * 16)); B2_TRY(h->rec_b.ensure(std::max<unsigned long long>(total, 1) * 16));
+  B2_TRY(h->rec_c.ensure(std::max<unsigned long long>(total, 1) * 16));
+  for (int s = 0; s < nseg; ++s) {
+    Direction* d = h->dirs[h->seg_dir[s]].get();
+    Cloud* S = impl_cloud(h, d->src); Cloud* T = impl_cloud(h, d->tgt);
+    k_pack<<<div_up(S->n, 256), 256, 0, h->stream>>>(S->s_xyz.as<float4>(), S->s_nrm.as<float4>(), S->n, T->s_xyz.as<float4>(),
+                                                     T->s_nrm.as<float4>(), d->match.as<int>(), d->offs.as<unsigned int>(), d->rec_begin,
+                                                     h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>());
+    ++h->launches;
+  }
+  B2_TRY(h->segs_dev.ensure(sizeof(Segment) * std::max(1, nseg)));
+  B2_TRY(h->pin_segs.ensure(sizeof(Segment) * std::max(1, nseg)));
+  if (nseg) {
+    std::memcpy(h->pin_segs.p, h->segs_host.data(), sizeof(Segment) * nseg);
+    B2_CUDA(cudaMemcpyAsync(h->segs_dev.p, h->pin_segs.p, sizeof(Segment) * nseg, cudaMemcpyHostToDevice, h->stream));
+  }
+  B2_CUDA(cudaEventRecord(h->ev[3], h->stream));
+  if (print) {
+    for (int k = 0; k < h->ndirs; ++k) {
+      Direction* d = h->dirs[k].get();
+      if (d->local) printf("  found correspondences from %d to %d: %llu\n", d->src, d->tgt, d->count);
+    }
+  }
+
+  // ---- streaming-pass geometry ----
+  h->grid_acc = h->sms * 2;
+  unsigned long long per = (total + h->grid_acc - 1) / (unsigned long long)h->grid_acc;
+  per = std::max<unsigned long long>(kAccThreads, (per + kAccThreads - 1) / kAccThreads * kAccThreads);
+  h->per_cta = per;
+  const size_t eq_count = (size_t)nv * nv + nv + 3;
+  B2_TRY(h->partials.ensure(sizeof(double) * kAccVals * (size_t)std::max(1, nseg) * h->grid_acc));
+  B2_TRY(h->segsum.ensure(sizeof(double) * kAccVals * std::max(1, nseg)));
+  B2_TRY(h->eq_dev.ensure(sizeof(double) * eq_count));
+  B2_TRY(h->pin_eq.ensure(sizeof(double) * eq_count));
+  B2_TRY(h->poses_dev.ensure(sizeof(CloudPose) * nc));
+  B2_TRY(h->pin_poses.ensure(sizeof(CloudPose) * nc));
+
+  // ---- compute() (icp_point_to_plane_impl.h:115-293): LM over the fixed correspondence sets ----
+  std::vector<Pose> poses(nc), trial(nc);
+  std::vector<double> H((size_t)nv * nv), b(nv), Ht, bt, x(nv), HL;
+  const double* eq = h->pin_eq.as<double>();
+  B2_TRY(run_pass(h, poses, true, nv));
+  std::copy(eq, eq + (size_t)nv * nv, H.begin()); std::copy(eq + (size_t)nv * nv, eq + (size_t)nv * nv + nv, b.begin());
+  double cost = eq[(size_t)nv * nv + nv];
+  h->stats.num_pairs = (int)std::llround(eq[(size_t)nv * nv + nv + 1]);
+  h->stats.num_correspondences = (uint64_t)std::llround(eq[(size_t)nv * nv + nv + 2]);
+  h->stats.local_correspondences = total;
+  h->stats.num_variables = nv;
+  h->stats.first_cost = cost;
+  h->H0 = H; h->b0 = b; h->cost0 = cost;
+  double lambda = 0.1;
+  const int max_inner = h->cfg.inner_max_iterations > 0 ? h->cfg.inner_max_iterations : 150;
+  for (int it = 0; it < max_inner; ++it) {
+    ++h->stats.inner_iterations;
+    bool applied = false;
+    int ntries = 0;
+    for (int lm = 0; lm < 10; ++lm) {
+      ++ntries;
+      HL = H;
+      for (int i = 0; i < nv; ++i) HL[(size_t)i * nv + i] += lambda;
+      if (nv > 0) sym_solve(HL, nv, b.data(), x.data());
+      trial = poses;
+      for (int ci = 1; ci < nc; ++ci) {
+        double neg[6];
+        for (int k = 0; k < 6; ++k) neg[k] = -x[6 * (ci - 1) + k];
+        trial[ci] = pose_mul(pose_exp(neg), poses[ci]);
+      }
+      // Speculative fused pass: cost at the trial poses AND the normal equations there; if the try is accepted they are
+      // exactly what the next iteration of compute() would recompute (same poses, same arithmetic).
+      B2_TRY(run_pass(h, trial, true, nv));
+      ++h->stats.lm_tries_total;
+      const double new_cost = eq[(size_t)nv * nv + nv];
+      if (new_cost < cost) {
+        poses = trial;
+        std::copy(eq, eq + (size_t)nv * nv, H.begin()); std::copy(eq + (size_t)nv * nv, eq + (size_t)nv * nv + nv, b.begin());
+        cost = new_cost;
+        lambda = 0.5f * lambda;
+        applied = true;
+        break;
+      } else {
+        lambda = 2.f * lambda;
+      }
+    }
+    h->tries.push_back(ntries);
+    if (!applied) break;
+  }
+  h->stats.last_cost = cost;
+  h->stats.final_lambda = lambda;
+  B2_CUDA(cudaEventRecord(h->ev[4], h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+
+  // ---- pose composition + convergence (icp_point_to_plane.cc:320-341) ----
+  *converged = true;
+  for (int m = 0; m < nmov; ++m) {
+    Cloud* c = h->movable[m].get();
+    float U[16], N[16];
+    affine_from_pose(poses[impl_index_of_movable(h, m)], U);
+    affine_mul(U, c->T, N);
+    const float dx = c->T[12] - N[12], dy = c->T[13] - N[13], dz = c->T[14] - N[14];
+    const float movement = std::sqrt(dx * dx + (dy * dy + dz * dz));
+    if (movement > thr) *converged = false;
+    if (print) printf("  %d moved by %g\n", impl_index_of_movable(h, m), movement);
+    std::memcpy(c->T, N, sizeof(N));
+  }
+  h->stats.kernel_launches = h->launches;
+  h->stats.ms_index = elapsed(h->ev[0], h->ev[1]);
+  h->stats.ms_search = elapsed(h->ev[1], h->ev[2]);
+  h->stats.ms_pack = elapsed(h->ev[2], h->ev[3]);
+  h->stats.ms_inner = elapsed(h->ev[3], h->ev[4]);
+  h->stats.ms_total = elapsed(h->ev[0], h->ev[4]);
+  double acc = 0; for (auto& pr : h->acc_events) acc += elapsed(pr.first, pr.second);
+  h->stats.ms_accum_kernel_avg = h->acc_events.empty() ? 0.f : (float)(acc / h->acc_events.size());
+  return B2_OK;
+}
+
+}  // namespace b2
+
+extern "C" {
+
+const char* b2_last_error(void) { return last_error_ref().c_str(); }
+int b2_abi_version(void) { return B2_ABI_VERSION; }
+
+int b2_device_info(int* device, char* name, size_t name_cap, int* sm_count, int* cc_major, int* cc_minor) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return set_error(B2_ERR_NO_DEVICE, "no CUDA device available; libeth3d_b200 has no CPU fallback");
+  int dev = 0; B2_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p; B2_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (device) *device = dev;
+  if (name && name_cap) { std::strncpy(name, p.name, name_cap - 1); name[name_cap - 1] = 0; }
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return B2_OK;
+}
+
+void b2_icp_default_config(b2_icp_config* cfg) {
+  if (!cfg) return;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->device = -1; cfg->inner_max_iterations = 150; cfg->world_size = 1;
+}
+
+int b2_icp_create(const b2_icp_config* cfg, b2_icp** out) {
+  if (!out) return set_error(B2_ERR_ARG, "out is null");
+  *out = nullptr;
+  b2_icp_config c; b2_icp_default_config(&c);
+  if (cfg) c = *cfg;
+  if (c.world_size < 1) c.world_size = 1;
+  if (c.world_size > 1 && !c.allreduce) return set_error(B2_ERR_ARG, "world_size > 1 needs an allreduce hook");
+  if (c.rank < 0 || c.rank >= c.world_size) return set_error(B2_ERR_ARG, "rank %d out of range", c.rank);
+  std::unique_ptr<b2_icp> h(new b2_icp());
+  h->cfg = c;
+  B2_TRY(select_device(c.device, &h->device, &h->sms));
+  if (c.stream) { h->stream = (cudaStream_t)c.stream; }
+  else { B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  for (auto& e : h->ev) B2_CUDA(cudaEventCreate(&e));
+  std::memset(&h->stats, 0, sizeof(h->stats));
+  *out = h.release();
+  return B2_OK;
+}
+
+int b2_icp_destroy(b2_icp* h) {
+  if (!h) return B2_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  auto free_cloud = [](Cloud* c) {
+    if (!c) return;
+    for (DevBuf* b : {&c->local_xyz, &c->local_nrm, &c->keys_in, &c->keys_out, &c->idx_in, &c->perm, &c->s_xyz, &c->s_nrm, &c->table}) b->release();
+  };
+  for (auto& c : h->movable) free_cloud(c.get());
+  free_cloud(h->fixed.get());
+  for (auto& d : h->dirs) for (DevBuf* b : {&d->match, &d->d2, &d->flags, &d->offs}) b->release();
+  for (DevBuf* b : {&h->bbox_partial, &h->cub_tmp, &h->cell_counts, &h->rec_a, &h->rec_b, &h->rec_c, &h->segs_dev, &h->poses_dev, &h->partials,
+                    &h->segsum, &h->eq_dev, &h->scatter_m, &h->scatter_d}) b->release();
+  for (PinnedBuf* b : {&h->pin_bbox, &h->pin_counts, &h->pin_eq, &h->pin_poses, &h->pin_segs, &h->pin_misc}) b->release();
+  for (auto& pr : h->acc_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return B2_OK;
+}
+
+static int add_cloud_impl(b2_icp* h, const float* xyz, const float* nrm, size_t n, size_t stride, const float T[16], int fixed, int* out_id,
+                          bool from_device) {
+  if (!h || !T || (n > 0 && (!xyz || !nrm))) return set_error(B2_ERR_ARG, "null argument");
+  if (!from_device && stride < 12) return set_error(B2_ERR_ARG, "stride_bytes must be >= 12");
+  if (n >= (1ull << 31)) return set_error(B2_ERR_ARG, "clouds above 2^31 points are not supported (pcl::Correspondence indices are int)");
+  B2_CUDA(cudaSetDevice(h->device));
+  if (fixed) {
+    // icp_point_to_plane.cc:112-127: transform to the global frame, concatenate, return -1.
+    Cloud tmp;
+    B2_TRY(upload_cloud(h, &tmp, xyz, nrm, n, stride, from_device));
+    if (!h->fixed) { h->fixed.reset(new Cloud()); h->fixed->is_fixed = true; const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}; std::memcpy(h->fixed->T, I, sizeof(I)); }
+    Cloud* f = h->fixed.get();
+    const size_t old = f->n, tot = old + n;
+    DevBuf nx, nn;
+    B2_TRY(nx.ensure(std::max<size_t>(tot, 1) * 12)); B2_TRY(nn.ensure(std::max<size_t>(tot, 1) * 12));
+    if (old) {
+      B2_CUDA(cudaMemcpyAsync(nx.p, f->local_xyz.p, old * 12, cudaMemcpyDeviceToDevice, h->stream));
+      B2_CUDA(cudaMemcpyAsync(nn.p, f->local_nrm.p, old * 12, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (n) k_transform<<<div_up(n, 256), 256, 0, h->stream>>>(tmp.local_xyz.as<float>(), tmp.local_nrm.as<float>(), n, mat4_of(T),
+                                                             nx.as<float>() + 3 * old, nn.as<float>() + 3 * old);
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    f->local_xyz.release(); f->local_nrm.release();
+    f->local_xyz = nx; f->local_nrm = nn; f->n = tot;
+    tmp.local_xyz.release(); tmp.local_nrm.release();
+    if (out_id) *out_id = -1;
+    return B2_OK;
+  }
+  std::unique_ptr<Cloud> c(new Cloud());
+  std::memcpy(c->T, T, sizeof(float) * 16);
+  B2_TRY(upload_cloud(h, c.get(), xyz, nrm, n, stride, from_device));
+  h->movable.push_back(std::move(c));
+  if (out_id) *out_id = (int)h->movable.size() - 1;
+  return B2_OK;
+}
+
+int b2_icp_add_cloud(b2_icp* h, const float* xyz, const float* normals, size_t n, size_t stride_bytes, const float T[16], int fixed, int* out_id) {
+  return add_cloud_impl(h, xyz, normals, n, stride_bytes, T, fixed, out_id, false);
+}
+int b2_icp_add_cloud_dev(b2_icp* h, const float* xyz_dev, const float* normals_dev, size_t n, const float T[16], int fixed, int* out_id) {
+  return add_cloud_impl(h, xyz_dev, normals_dev, n, 12, T, fixed, out_id, true);
+}
+
+int b2_icp_run(b2_icp* h, float max_dist, int initial_iteration, int max_iters, float thr, int print, int* converged) {
+  if (!h || !converged) return set_error(B2_ERR_ARG, "null argument");
+  *converged = 0;
+  if (h->movable.empty()) return set_error(B2_ERR_STATE, "Run() without any movable cloud (reference: CHECK(!clouds_.empty()))");
+  B2_CUDA(cudaSetDevice(h->device));
+  for (int i = initial_iteration; i < initial_iteration + max_iters; ++i) {
+    if (print) printf("-- Alignment iteration %d --\n", i);
+    bool conv = false;
+    B2_TRY(align_once(h, max_dist, thr, print, &conv));
+    if (conv) {
+      if (print) printf("Convergence is assumed as the maximum movement is less than the threshold.\n");
+      *converged = 1;
+      return B2_OK;
+    }
+  }
+  return B2_OK;
+}
+
+int b2_icp_get_pose(b2_icp* h, int id, float T[16]) {
+  if (!h || !T || id < 0 || id >= (int)h->movable.size()) return set_error(B2_ERR_ARG, "bad cloud id %d", id);
+  std::memcpy(T, h->movable[id]->T, sizeof(float) * 16);
+  return B2_OK;
+}
+int b2_icp_set_pose(b2_icp* h, int id, const float T[16]) {
+  if (!h || !T || id < 0 || id >= (int)h->movable.size()) return set_error(B2_ERR_ARG, "bad cloud id %d", id);
+  std::memcpy(h->movable[id]->T, T, sizeof(float) * 16);
+  return B2_OK;
+}
+
+int b2_icp_last_stats(b2_icp* h, b2_icp_stats* out) {
+  if (!h || !out) return set_error(B2_ERR_ARG, "null argument");
+  *out = h->stats;
+  return B2_OK;
+}
+int b2_icp_get_lm_tries(b2_icp* h, int32_t* tries, int cap, int* count) {
+  if (!h || !count) return set_error(B2_ERR_ARG, "null argument");
+  *count = (int)h->tries.size();
+  for (int i = 0; i < std::min(cap, *count); ++i) tries[i] = h->tries[i];
+  return B2_OK;
+}
+int b2_icp_get_pair_info(b2_icp* h, int k, int* src, int* tgt, uint64_t* count) {
+  if (!h || k < 0 || k >= (int)h->segs_host.size()) return set_error(B2_ERR_ARG, "bad pair index %d", k);
+  if (src) *src = h->segs_host[k].src;
+  if (tgt) *tgt = h->segs_host[k].tgt;
+  if (count) *count = h->segs_host[k].end - h->segs_host[k].begin;
+  return B2_OK;
+}
+
+int b2_icp_get_pair_correspondences(b2_icp* h, int k, int32_t* iq, int32_t* im, float* dist) {
+  if (!h || k < 0 || k >= (int)h->segs_host.size() || !iq || !im || !dist) return set_error(B2_ERR_ARG, "bad argument");
+  B2_CUDA(cudaSetDevice(h->device));
+  Direction* d = h->dirs[h->seg_dir[k]].get();
+  Cloud* S = impl_cloud(h, d->src); Cloud* T = impl_cloud(h, d->tgt);
+  const size_t ns = S->n;
+  B2_TRY(h->scatter_m.ensure(ns * 4)); B2_TRY(h->scatter_d.ensure(ns * 4));
+  k_scatter_matches<<<div_up(ns, 256), 256, 0, h->stream>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), d->match.as<int>(), d->d2.as<float>(),
+                                                           h->scatter_m.as<int>(), h->scatter_d.as<float>());
+  std::vector<int> m(ns); std::vector<float> dd(ns);
+  B2_CUDA(cudaMemcpyAsync(m.data(), h->scatter_m.p, ns * 4, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaMemcpyAsync(dd.data(), h->scatter_d.p, ns * 4, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  size_t o = 0;
+  for (size_t i = 0; i < ns; ++i) if (m[i] >= 0) { iq[o] = (int32_t)i; im[o] = m[i]; dist[o] = dd[i]; ++o; }
+  return B2_OK;
+}
+
+int b2_icp_get_normal_equations(b2_icp* h, double* H, double* b, double* cost, int* nv) {
+  if (!h) return set_error(B2_ERR_ARG, "null argument");
+  const int n = (int)h->b0.size();
+  if (nv) *nv = n;
+  if (H) std::copy(h->H0.begin(), h->H0.end(), H);
+  if (b) std::copy(h->b0.begin(), h->b0.end(), b);
+  if (cost) *cost = h->cost0;
+  return B2_OK;
+}
+
+int b2_find_correspondences(const float* src_xyz, size_t n_src, const float* tgt_xyz, size_t n_tgt, float max_dist, int32_t* iq, int32_t* im,
+                            float* dist, uint64_t* count) {
+  if (!count || (n_src && (!src_xyz || !iq || !im || !dist)) || (n_tgt && !tgt_xyz)) return set_error(B2_ERR_ARG, "null argument");
+  *count = 0;
+  b2_icp_config cfg; b2_icp_default_config(&cfg);
+  b2_icp* h = nullptr;
+  B2_TRY(b2_icp_create(&cfg, &h));
+  int rc = B2_OK;
+  do {
+    const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    Cloud S, T;
+    std::memcpy(S.T, I, sizeof(I)); std::memcpy(T.T, I, sizeof(I));
+    // normals are irrelevant for the search: reuse xyz as a stand-in
+    if ((rc = upload_cloud(h, &S, src_xyz, src_xyz, n_src, 12, false)) != B2_OK) break;
+    if ((rc = upload_cloud(h, &T, tgt_xyz, tgt_xyz, n_tgt, 12, false)) != B2_OK) break;
+    h->movable.emplace_back(new Cloud(S)); h->movable.emplace_back(new Cloud(T));
+    S = Cloud(); T = Cloud();
+    if (n_src == 0 || n_tgt == 0) break;
+    // run only the index + search part of an outer iteration
+    bool conv;
+    if ((rc = align_once(h, max_dist, 0.f, 0, &conv, /*search_only=*/true, /*gate=*/false)) != B2_OK) break;
+    for (int k = 0; k < (int)h->segs_host.size(); ++k) {
+      if (h->segs_host[k].src == 0 && h->segs_host[k].tgt == 1) {
+        *count = h->segs_host[k].end - h->segs_host[k].begin;
+        rc = b2_icp_get_pair_correspondences(h, k, iq, im, dist);
+      }
+    }
+  } while (false);
+  b2_icp_destroy(h);
+  return rc;
+}
+
+}  // extern "C"

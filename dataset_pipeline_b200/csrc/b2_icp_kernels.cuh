@@ -1,0 +1,426 @@
+// Device kernels of Path A (multi-scan point-to-plane ICP) for sm_100a.
+//
+//   K1  k_bbox / k_keys / k_apply   transform to the global frame + AABB + cell keys + sorted SoA copies
+//                                   (replaces pcl::transformPointCloudWithNormals + bbox loops, icp_point_to_plane.cc:189-205)
+//   K2  k_count_cells / k_hash_*    occupied-cell hash over the cell-sorted target (replaces the per-pair kd-tree build, :46-51)
+//   K3  k_nn_radius1                nearest target within radius per source point (replaces radiusSearch loop, :63-102)
+//   K4  k_pack                      48 B packed correspondence records (p_s,n_s,p_t,n_t), three float4 planes
+//   K5  k_accumulate                one streaming pass: cost + 6x6 S + 6-vector g per correspondence set, fp64
+//                                   (replaces compute() loops, icp_point_to_plane_impl.h:129-211 and :240-266)
+//   K6  k_finalize                  fixed-order reduction of the per-CTA partials + assembly of the normal equations
+//                                   with the reference's upper-triangle quirk (impl.h:82-113 + :226)
+// All of these are HBM / gather bound integer+fp32+fp64 streaming work: no tensor cores.
+#pragma once
+#include "b2_common.cuh"
+
+namespace b2 {
+
+static constexpr int kAccThreads = 256;
+static constexpr int kAccVals = 28;   // 21 (upper S) + 6 (g) + 1 (cost)
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1a: AABB of the transformed cloud. One partial (6 floats) per block; the host finishes the reduction.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bbox(const float* __restrict__ xyz, size_t n, Mat4 T, float* __restrict__ partial) {
+  float mnx = INFINITY, mny = INFINITY, mnz = INFINITY, mxx = -INFINITY, mxy = -INFINITY, mxz = -INFINITY;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float3 p = xform_point(T, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    mnx = fminf(mnx, p.x); mny = fminf(mny, p.y); mnz = fminf(mnz, p.z);
+    mxx = fmaxf(mxx, p.x); mxy = fmaxf(mxy, p.y); mxz = fmaxf(mxz, p.z);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o)); mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
+  }
+  __shared__ float s[8][6];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s[w][0] = mnx; s[w][1] = mny; s[w][2] = mnz; s[w][3] = mxx; s[w][4] = mxy; s[w][5] = mxz; }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float v = s[0][threadIdx.x];
+    for (int i = 1; i < 8; ++i) v = threadIdx.x < 3 ? fminf(v, s[i][threadIdx.x]) : fmaxf(v, s[i][threadIdx.x]);
+    partial[blockIdx.x * 6 + threadIdx.x] = v;
+  }
+}
+
+// K1b: cell key of every transformed point (+ identity permutation).
+__global__ void __launch_bounds__(256) k_keys(const float* __restrict__ xyz, size_t n, Mat4 T, GridParams g,
+                                              unsigned long long* __restrict__ keys, unsigned int* __restrict__ idx) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float3 p = xform_point(T, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+  keys[i] = cell_key(g, cell_of(p.x, g.ox, g.inv), cell_of(p.y, g.oy, g.inv), cell_of(p.z, g.oz, g.inv));
+  idx[i] = (unsigned int)i;
+}
+
+// K1c: cell-sorted global-frame copies: s_xyz[j] = (p, bits(original index)), s_nrm[j] = (n, 0).
+__global__ void __launch_bounds__(256) k_apply(const float* __restrict__ xyz, const float* __restrict__ nrm, size_t n, Mat4 T,
+                                               const unsigned int* __restrict__ perm, float4* __restrict__ s_xyz,
+                                               float4* __restrict__ s_nrm) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const unsigned int i = perm[j];
+  const float3 p = xform_point(T, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]);
+  s_xyz[j] = make_float4(p.x, p.y, p.z, __uint_as_float(i));
+  if (nrm) {
+    const float3 q = xform_normal(T, nrm[3 * (size_t)i], nrm[3 * (size_t)i + 1], nrm[3 * (size_t)i + 2]);
+    s_nrm[j] = make_float4(q.x, q.y, q.z, 0.f);
+  }
+}
+
+// Plain transform into packed float3 arrays (fixed-cloud concatenation, icp_point_to_plane.cc:118-126).
+__global__ void __launch_bounds__(256) k_transform(const float* __restrict__ xyz, const float* __restrict__ nrm, size_t n, Mat4 T,
+                                                   float* __restrict__ oxyz, float* __restrict__ onrm) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float3 p = xform_point(T, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+  oxyz[3 * i] = p.x; oxyz[3 * i + 1] = p.y; oxyz[3 * i + 2] = p.z;
+  const float3 q = xform_normal(T, nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]);
+  onrm[3 * i] = q.x; onrm[3 * i + 1] = q.y; onrm[3 * i + 2] = q.z;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2: occupied-cell hash table over the sorted keys. Entry = {key, begin, end} (16 B, one LDG.128 per probe).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_count_cells(const unsigned long long* __restrict__ keys, size_t n, unsigned int* __restrict__ count) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool head = j < n && (j == 0 || keys[j] != keys[j - 1]);
+  const unsigned int m = __ballot_sync(0xffffffffu, head);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned int)__popc(m));
+}
+
+__global__ void __launch_bounds__(256) k_hash_insert(const unsigned long long* __restrict__ keys, size_t n, HashEntry* __restrict__ table,
+                                                     int log2size) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const unsigned long long key = keys[j];
+  if (j != 0 && keys[j - 1] == key) return;
+  const unsigned int mask = (1u << log2size) - 1u;
+  unsigned int s = hash_slot(key, log2size);
+  while (true) {
+    const unsigned long long prev = atomicCAS(&table[s].key, kEmptyKey, key);
+    if (prev == kEmptyKey) { table[s].begin = (unsigned int)j; return; }
+    s = (s + 1) & mask;
+  }
+}
+
+__device__ __forceinline__ bool hash_find(const HashEntry* __restrict__ table, int log2size, unsigned long long key,
+                                          unsigned int* begin, unsigned int* end) {
+  const unsigned int mask = (1u << log2size) - 1u;
+  unsigned int s = hash_slot(key, log2size);
+  while (true) {
+    const uint4 e = __ldg(reinterpret_cast<const uint4*>(table + s));
+    const unsigned long long k = ((unsigned long long)e.y << 32) | e.x;
+    if (k == key) { *begin = e.z; *end = e.w; return true; }
+    if (k == kEmptyKey) return false;
+    s = (s + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_hash_ends(const unsigned long long* __restrict__ keys, size_t n, HashEntry* __restrict__ table,
+                                                   int log2size) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const unsigned long long key = keys[j];
+  if (j + 1 != n && keys[j + 1] == key) return;
+  const unsigned int mask = (1u << log2size) - 1u;
+  unsigned int s = hash_slot(key, log2size);
+  while (table[s].key != key) s = (s + 1) & mask;
+  table[s].end = (unsigned int)(j + 1);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3: nearest target within radius (strict d2 < r2), lowest ORIGINAL target index on exact ties.
+// d2 = ((dx*dx)+(dy*dy))+(dz*dz) in fp32 without contraction (FLANN L2_Simple order).
+// One thread per cell-sorted source point: neighbouring threads share cells, so the 27 probes and the candidate
+// rows are served from L1/L2. Output at the sorted source position.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_nn_radius1(const float4* __restrict__ src, size_t ns, const float4* __restrict__ tgt,
+                                                    const HashEntry* __restrict__ table, int log2size, GridParams g, float r2,
+                                                    int* __restrict__ match_pos, float* __restrict__ match_d2,
+                                                    unsigned int* __restrict__ flags) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ns) return;
+  const float4 q = src[j];
+  const int cx = cell_of(q.x, g.ox, g.inv), cy = cell_of(q.y, g.oy, g.inv), cz = cell_of(q.z, g.oz, g.inv);
+  float best = r2;
+  int best_pos = -1;
+  unsigned int best_idx = 0xFFFFFFFFu;
+#pragma unroll 1
+  for (int dz = -1; dz <= 1; ++dz) {
+    const int z = cz + dz;
+    if (z < 0 || z >= g.nz) continue;
+#pragma unroll 1
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = cy + dy;
+      if (y < 0 || y >= g.ny) continue;
+#pragma unroll 1
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = cx + dx;
+        if (x < 0 || x >= g.nx) continue;
+        unsigned int b, e;
+        if (!hash_find(table, log2size, cell_key(g, x, y, z), &b, &e)) continue;
+        for (unsigned int p = b; p < e; ++p) {
+          const float4 t = __ldg(tgt + p);
+          const float ddx = fsub(q.x, t.x), ddy = fsub(q.y, t.y), ddz = fsub(q.z, t.z);
+          const float d2 = fadd(fadd(fmul(ddx, ddx), fmul(ddy, ddy)), fmul(ddz, ddz));
+          const unsigned int ti = __float_as_uint(t.w);
+          if (d2 < best || (d2 == best && best_pos >= 0 && ti < best_idx)) { best = d2; best_pos = (int)p; best_idx = ti; }
+        }
+      }
+    }
+  }
+  match_pos[j] = best_pos;
+  match_d2[j] = best;
+  flags[j] = best_pos >= 0 ? 1u : 0u;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K4: packed correspondence records, three float4 planes (48 B / correspondence, fully coalesced in K5):
+//   A = (ps.x, ps.y, ps.z, ns.x)  B = (ns.y, ns.z, pt.x, pt.y)  C = (pt.z, nt.x, nt.y, nt.z)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack(const float4* __restrict__ s_xyz_src, const float4* __restrict__ s_nrm_src, size_t ns,
+                                              const float4* __restrict__ s_xyz_tgt, const float4* __restrict__ s_nrm_tgt,
+                                              const int* __restrict__ match_pos, const unsigned int* __restrict__ offs,
+                                              unsigned long long base, float4* __restrict__ ra, float4* __restrict__ rb,
+                                              float4* __restrict__ rc) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ns) return;
+  const int p = match_pos[j];
+  if (p < 0) return;
+  const float4 ps = s_xyz_src[j], nsr = s_nrm_src[j];
+  const float4 pt = __ldg(s_xyz_tgt + p), nt = __ldg(s_nrm_tgt + p);
+  const unsigned long long o = base + offs[j];
+  ra[o] = make_float4(ps.x, ps.y, ps.z, nsr.x);
+  rb[o] = make_float4(nsr.y, nsr.z, pt.x, pt.y);
+  rc[o] = make_float4(pt.z, nt.x, nt.y, nt.z);
+}
+
+// Correspondence list in the caller's (original) indexing, scattered to the original query index.
+__global__ void __launch_bounds__(256) k_scatter_matches(const float4* __restrict__ s_xyz_src, size_t ns, const float4* __restrict__ s_xyz_tgt,
+                                                         const int* __restrict__ match_pos, const float* __restrict__ match_d2,
+                                                         int* __restrict__ out_match, float* __restrict__ out_d2) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ns) return;
+  const unsigned int qi = __float_as_uint(s_xyz_src[j].w);
+  const int p = match_pos[j];
+  out_match[qi] = p >= 0 ? (int)__float_as_uint(__ldg(s_xyz_tgt + p).w) : -1;
+  out_d2[qi] = match_d2[j];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K5: one streaming pass over the packed records.
+// The record array is the concatenation of the correspondence sets ("segments"); CTA b owns the contiguous range
+// [b*per_cta, (b+1)*per_cta) and flushes a 28-double partial per segment it touches: a fixed partition and a fixed
+// reduction tree, so the result (and therefore every LM accept/reject decision) is reproducible run to run.
+// Per record (fp32, evaluation order of icp_point_to_plane_impl.h:146-204, no FMA contraction):
+//   ps = Rs*ps0 + ts, ns = Rs*ns0, pt = Rt*pt0 + tt, nt = Rt*nt0
+//   r1 = ns.(pt-ps)   j1 = [ns ; pt x ns]        (d r1 / d target pose; d/d source pose = -j1)
+//   r2 = nt.(ps-pt)   j2 = [nt ; ps x nt]        (d r2 / d source pose; d/d target pose = -j2)
+// accumulated in fp64 (products of fp32-valued doubles are exact):  S += j1 j1^T + j2 j2^T,  g += r1 j1 - r2 j2,
+// cost += r1*r1 + r2*r2 (fp32 squares, as the reference).
+// ------------------------------------------------------------------------------------------------------------------
+struct CloudPose { float R[9]; float t[3]; };      // increment of one impl cloud (row-major R)
+struct Segment { unsigned long long begin, end; int src, tgt; };   // records [begin,end), impl cloud indices
+
+__device__ __forceinline__ void load_pose(const CloudPose* __restrict__ P, int i, float R[9], float t[3]) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) R[k] = __ldg(&P[i].R[k]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) t[k] = __ldg(&P[i].t[k]);
+}
+
+__device__ __forceinline__ void accumulate_record(const float4 a, const float4 b, const float4 c, const float Rs[9], const float ts[3],
+                                                  const float Rt[9], const float tt[3], double acc[kAccVals]) {
+  const float psx = fadd(sum3(fmul(Rs[0], a.x), fmul(Rs[1], a.y), fmul(Rs[2], a.z)), ts[0]);
+  const float psy = fadd(sum3(fmul(Rs[3], a.x), fmul(Rs[4], a.y), fmul(Rs[5], a.z)), ts[1]);
+  const float psz = fadd(sum3(fmul(Rs[6], a.x), fmul(Rs[7], a.y), fmul(Rs[8], a.z)), ts[2]);
+  const float nsx = sum3(fmul(Rs[0], a.w), fmul(Rs[1], b.x), fmul(Rs[2], b.y));
+  const float nsy = sum3(fmul(Rs[3], a.w), fmul(Rs[4], b.x), fmul(Rs[5], b.y));
+  const float nsz = sum3(fmul(Rs[6], a.w), fmul(Rs[7], b.x), fmul(Rs[8], b.y));
+  const float ptx = fadd(sum3(fmul(Rt[0], b.z), fmul(Rt[1], b.w), fmul(Rt[2], c.x)), tt[0]);
+  const float pty = fadd(sum3(fmul(Rt[3], b.z), fmul(Rt[4], b.w), fmul(Rt[5], c.x)), tt[1]);
+  const float ptz = fadd(sum3(fmul(Rt[6], b.z), fmul(Rt[7], b.w), fmul(Rt[8], c.x)), tt[2]);
+  const float ntx = sum3(fmul(Rt[0], c.y), fmul(Rt[1], c.z), fmul(Rt[2], c.w));
+  const float nty = sum3(fmul(Rt[3], c.y), fmul(Rt[4], c.z), fmul(Rt[5], c.w));
+  const float ntz = sum3(fmul(Rt[6], c.y), fmul(Rt[7], c.z), fmul(Rt[8], c.w));
+
+  const float r1 = dot3(nsx, nsy, nsz, fsub(ptx, psx), fsub(pty, psy), fsub(ptz, psz));
+  const float r2 = dot3(ntx, nty, ntz, fsub(psx, ptx), fsub(psy, pty), fsub(psz, ptz));
+  float j1[6], j2[6];
+  j1[0] = nsx; j1[1] = nsy; j1[2] = nsz;
+  j1[3] = fadd(fmul(-nsy, ptz), fmul(nsz, pty));
+  j1[4] = fsub(fmul(nsx, ptz), fmul(nsz, ptx));
+  j1[5] = fadd(fmul(-nsx, pty), fmul(nsy, ptx));
+  j2[0] = ntx; j2[1] = nty; j2[2] = ntz;
+  j2[3] = fadd(fmul(-nty, psz), fmul(ntz, psy));
+  j2[4] = fsub(fmul(ntx, psz), fmul(ntz, psx));
+  j2[5] = fadd(fmul(-ntx, psy), fmul(nty, psx));
+
+  double d1[6], d2[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { d1[i] = (double)j1[i]; d2[i] = (double)j2[i]; }
+  const double dr1 = (double)r1, dr2 = -(double)r2;
+  int k = 0;
+#pragma unroll
+  for (int cidx = 0; cidx < 6; ++cidx)
+#pragma unroll
+    for (int r = 0; r <= cidx; ++r) { acc[k] = fma(d1[r], d1[cidx], acc[k]); acc[k] = fma(d2[r], d2[cidx], acc[k]); ++k; }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { acc[21 + i] = fma(dr1, d1[i], acc[21 + i]); acc[21 + i] = fma(dr2, d2[i], acc[21 + i]); }
+  acc[27] += (double)fmul(r1, r1);
+  acc[27] += (double)fmul(r2, r2);
+}
+
+__device__ __forceinline__ void cost_record(const float4 a, const float4 b, const float4 c, const float Rs[9], const float ts[3],
+                                            const float Rt[9], const float tt[3], double* cost) {
+  const float psx = fadd(sum3(fmul(Rs[0], a.x), fmul(Rs[1], a.y), fmul(Rs[2], a.z)), ts[0]);
+  const float psy = fadd(sum3(fmul(Rs[3], a.x), fmul(Rs[4], a.y), fmul(Rs[5], a.z)), ts[1]);
+  const float psz = fadd(sum3(fmul(Rs[6], a.x), fmul(Rs[7], a.y), fmul(Rs[8], a.z)), ts[2]);
+  const float nsx = sum3(fmul(Rs[0], a.w), fmul(Rs[1], b.x), fmul(Rs[2], b.y));
+  const float nsy = sum3(fmul(Rs[3], a.w), fmul(Rs[4], b.x), fmul(Rs[5], b.y));
+  const float nsz = sum3(fmul(Rs[6], a.w), fmul(Rs[7], b.x), fmul(Rs[8], b.y));
+  const float ptx = fadd(sum3(fmul(Rt[0], b.z), fmul(Rt[1], b.w), fmul(Rt[2], c.x)), tt[0]);
+  const float pty = fadd(sum3(fmul(Rt[3], b.z), fmul(Rt[4], b.w), fmul(Rt[5], c.x)), tt[1]);
+  const float ptz = fadd(sum3(fmul(Rt[6], b.z), fmul(Rt[7], b.w), fmul(Rt[8], c.x)), tt[2]);
+  const float ntx = sum3(fmul(Rt[0], c.y), fmul(Rt[1], c.z), fmul(Rt[2], c.w));
+  const float nty = sum3(fmul(Rt[3], c.y), fmul(Rt[4], c.z), fmul(Rt[5], c.w));
+  const float ntz = sum3(fmul(Rt[6], c.y), fmul(Rt[7], c.z), fmul(Rt[8], c.w));
+  const float r1 = dot3(nsx, nsy, nsz, fsub(ptx, psx), fsub(pty, psy), fsub(ptz, psz));
+  const float r2 = dot3(ntx, nty, ntz, fsub(psx, ptx), fsub(psy, pty), fsub(psz, ptz));
+  *cost += (double)fmul(r1, r1);
+  *cost += (double)fmul(r2, r2);
+}
+
+// Block-wide fixed-tree reduction of NV doubles per thread; result valid in threads [0,NV) of the block.
+template <int NV>
+__device__ __forceinline__ void block_reduce(double acc[NV], double (*smem)[NV], double* out_first_nv_threads) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    acc[k] = v;
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();   // smem may still be read from a previous flush
+  if (l == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) smem[w][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double v = smem[0][threadIdx.x];
+    for (int i = 1; i < kAccThreads / 32; ++i) v += smem[i][threadIdx.x];
+    *out_first_nv_threads = v;
+  }
+}
+
+template <bool WITH_H>
+__global__ void __launch_bounds__(kAccThreads, 2)
+k_accumulate(const float4* __restrict__ ra, const float4* __restrict__ rb, const float4* __restrict__ rc,
+             const Segment* __restrict__ segs, int nseg, const CloudPose* __restrict__ poses, unsigned long long total,
+             unsigned long long per_cta, double* __restrict__ partials /* [nseg][gridDim.x][kAccVals] */) {
+  constexpr int NV = WITH_H ? kAccVals : 1;
+  __shared__ double smem[kAccThreads / 32][NV];
+  unsigned long long r0 = (unsigned long long)blockIdx.x * per_cta;
+  const unsigned long long r1 = min(total, r0 + per_cta);
+  if (r0 >= r1) return;
+  // first segment whose end is beyond r0 (segments are sorted, non-overlapping, possibly empty)
+  int lo = 0, hi = nseg - 1;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (segs[mid].end > r0) hi = mid; else lo = mid + 1; }
+  int seg = lo;
+  while (r0 < r1) {
+    const Segment sg = segs[seg];
+    const unsigned long long e = min(r1, sg.end);
+    if (e <= r0) { ++seg; continue; }
+    float Rs[9], ts[3], Rt[9], tt[3];
+    load_pose(poses, sg.src, Rs, ts);
+    load_pose(poses, sg.tgt, Rt, tt);
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    unsigned long long r = r0 + threadIdx.x;
+    // two records in flight per thread: 6 independent LDG.128 before the math
+    for (; r + kAccThreads < e; r += 2 * kAccThreads) {
+      const float4 a0 = __ldcs(ra + r), b0 = __ldcs(rb + r), c0 = __ldcs(rc + r);
+      const float4 a1 = __ldcs(ra + r + kAccThreads), b1 = __ldcs(rb + r + kAccThreads), c1 = __ldcs(rc + r + kAccThreads);
+      if (WITH_H) { accumulate_record(a0, b0, c0, Rs, ts, Rt, tt, acc); accumulate_record(a1, b1, c1, Rs, ts, Rt, tt, acc); }
+      else { cost_record(a0, b0, c0, Rs, ts, Rt, tt, &acc[0]); cost_record(a1, b1, c1, Rs, ts, Rt, tt, &acc[0]); }
+    }
+    if (r < e) {
+      const float4 a0 = __ldcs(ra + r), b0 = __ldcs(rb + r), c0 = __ldcs(rc + r);
+      if (WITH_H) accumulate_record(a0, b0, c0, Rs, ts, Rt, tt, acc);
+      else cost_record(a0, b0, c0, Rs, ts, Rt, tt, &acc[0]);
+    }
+    double out;
+    block_reduce<NV>(acc, smem, &out);
+    if (threadIdx.x < NV) {
+      const int slot = WITH_H ? threadIdx.x : (kAccVals - 1);
+      partials[((size_t)seg * gridDim.x + blockIdx.x) * kAccVals + slot] = out;
+    }
+    r0 = e;
+    ++seg;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K6: per-segment sums in ascending CTA order, then the normal equations [H (nv*nv, col-major, symmetric) | b | cost].
+// Assembly follows Accumulate (impl.h:82-113) with w = 1 and the solver's Upper view (impl.h:226):
+//   H(src,src) += S, H(tgt,tgt) += S, H(src,tgt) += -S only when that block lies in the upper triangle (src var < tgt var),
+//   b(src) -= g, b(tgt) += g; impl cloud 0 has no variables.
+// Single block; every sum runs in a fixed order.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool WITH_H>
+__global__ void __launch_bounds__(1024) k_finalize(const double* __restrict__ partials, const Segment* __restrict__ segs, int nseg,
+                                                   int grid_acc, unsigned long long per_cta, int nv, double* __restrict__ segsum,
+                                                   double* __restrict__ eq, double extra0, double extra1) {
+  for (int w = threadIdx.x; w < nseg * kAccVals; w += blockDim.x) {
+    const int s = w / kAccVals, k = w % kAccVals;
+    double v = 0.0;
+    if ((WITH_H || k == kAccVals - 1) && segs[s].end > segs[s].begin) {
+      const int b0 = (int)(segs[s].begin / per_cta), b1 = (int)((segs[s].end - 1) / per_cta);
+      for (int b = b0; b <= b1; ++b) v += partials[((size_t)s * grid_acc + b) * kAccVals + k];
+    }
+    segsum[w] = v;
+  }
+  __syncthreads();
+  const int nh = nv * nv;
+  if (WITH_H) {
+    for (int w = threadIdx.x; w < nh; w += blockDim.x) {
+      const int r = w % nv, c = w / nv;          // column-major
+      const int rr = r <= c ? r : c, cc = r <= c ? c : r;   // mirror the upper triangle
+      const int vr = rr / 6, vc = cc / 6, ir = rr % 6, ic = cc % 6;
+      const int lo6 = ir <= ic ? ir : ic, hi6 = ir <= ic ? ic : ir;
+      const int sidx = hi6 * (hi6 + 1) / 2 + lo6;           // packed upper index of S
+      double v = 0.0;
+      for (int s = 0; s < nseg; ++s) {
+        const int sv = segs[s].src - 1, tv = segs[s].tgt - 1;   // variable block index, -1 = fixed
+        const double S = segsum[s * kAccVals + sidx];
+        if (vr == vc) { if (sv == vr) v += S; if (tv == vr) v += S; }
+        else if (sv == vr && tv == vc) v -= S;
+      }
+      eq[w] = v;
+    }
+    for (int w = threadIdx.x; w < nv; w += blockDim.x) {
+      const int vb = w / 6, i = w % 6;
+      double v = 0.0;
+      for (int s = 0; s < nseg; ++s) {
+        const double g = segsum[s * kAccVals + 21 + i];
+        if (segs[s].tgt - 1 == vb) v += g;
+        if (segs[s].src - 1 == vb) v -= g;
+      }
+      eq[nh + w] = v;
+    }
+  }
+  if (threadIdx.x == 0) {
+    double c = 0.0;
+    for (int s = 0; s < nseg; ++s) c += segsum[s * kAccVals + kAccVals - 1];
+    eq[nh + nv] = c;
+    eq[nh + nv + 1] = extra0;
+    eq[nh + nv + 2] = extra1;
+  }
+}
+
+}  // namespace b2

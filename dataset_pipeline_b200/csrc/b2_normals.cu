@@ -1,0 +1,380 @@
+// Path A — kNN two-pass normal estimation on sm_100a (kernel K7), behind b2_normals_estimate().
+//
+// Replaces pcl::NormalEstimationTwoPassOMP::computeFeature (/root/reference/src/geometry/two_pass_normal_3d_omp.hpp:47-119):
+//   per point: k nearest neighbours incl. itself (kd-tree nearestKSearch, sorted) ->
+//   computeMeanAndCovarianceMatrixTwoPass (/root/reference/src/geometry/two_pass_centroid.hpp:155-259, fp32 sequential sums in
+//   neighbour order) -> smallest eigenvector of the 3x3 covariance (pcl::eigen33 closed form) -> curvature ->
+//   flipNormalTowardsViewpoint; NaN when fewer than 3 neighbours (two_pass_normal_3d.h:100-105).
+//
+// Spatial index: the points are sorted by a 63-bit Morton code; consecutive runs of 8 sorted points are the leaves of an
+// IMPLICIT binary BVH (node i of level l covers leaves [i*2^l, (i+1)*2^l); no pointers, 24 B AABB per node). One thread per
+// sorted query walks it near-child-first with a k-best list in shared memory. The kNN is exact with the tie-break
+// (squared distance, original index) ascending; the AABB lower bound is evaluated with the same fp32 operations as the
+// point distance, so pruning can never drop a neighbour (rounding is monotone).
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "b2_common.cuh"
+
+namespace b2 {
+
+static constexpr int kLeaf = 8;
+static constexpr int kKnnThreads = 128;
+
+struct Aabb { float lo[3], hi[3]; };
+
+__global__ void __launch_bounds__(256) kn_bbox(const float* __restrict__ xyz, size_t n, float* __restrict__ partial) {
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    for (int d = 0; d < 3; ++d) { const float v = xyz[3 * i + d]; mn[d] = fminf(mn[d], v); mx[d] = fmaxf(mx[d], v); }
+  for (int o = 16; o > 0; o >>= 1)
+    for (int d = 0; d < 3; ++d) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o)); mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+  __shared__ float s[8][6];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) for (int d = 0; d < 3; ++d) { s[w][d] = mn[d]; s[w][3 + d] = mx[d]; }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float v = s[0][threadIdx.x];
+    for (int i = 1; i < 8; ++i) v = threadIdx.x < 3 ? fminf(v, s[i][threadIdx.x]) : fmaxf(v, s[i][threadIdx.x]);
+    partial[blockIdx.x * 6 + threadIdx.x] = v;
+  }
+}
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long v) {
+  v &= 0x1FFFFFull;
+  v = (v | (v << 32)) & 0x1F00000000FFFFull;
+  v = (v | (v << 16)) & 0x1F0000FF0000FFull;
+  v = (v | (v << 8)) & 0x100F00F00F00F00Full;
+  v = (v | (v << 4)) & 0x10C30C30C30C30C3ull;
+  v = (v | (v << 2)) & 0x1249249249249249ull;
+  return v;
+}
+
+__global__ void __launch_bounds__(256) kn_morton(const float* __restrict__ xyz, size_t n, float ox, float oy, float oz, float scale,
+                                                 unsigned long long* __restrict__ keys, unsigned int* __restrict__ idx) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float m = 2097151.f;
+  const unsigned int x = (unsigned int)fminf(fmaxf((xyz[3 * i] - ox) * scale, 0.f), m);
+  const unsigned int y = (unsigned int)fminf(fmaxf((xyz[3 * i + 1] - oy) * scale, 0.f), m);
+  const unsigned int z = (unsigned int)fminf(fmaxf((xyz[3 * i + 2] - oz) * scale, 0.f), m);
+  keys[i] = spread21(x) | (spread21(y) << 1) | (spread21(z) << 2);
+  idx[i] = (unsigned int)i;
+}
+
+__global__ void __launch_bounds__(256) kn_gather(const float* __restrict__ xyz, size_t n, const unsigned int* __restrict__ perm,
+                                                 float4* __restrict__ s_xyz) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const unsigned int i = perm[j];
+  s_xyz[j] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], __uint_as_float(i));
+}
+
+__global__ void __launch_bounds__(256) kn_leaf_aabb(const float4* __restrict__ s_xyz, size_t n, unsigned int nleaf, Aabb* __restrict__ nodes) {
+  const unsigned int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nleaf) return;
+  Aabb b; for (int d = 0; d < 3; ++d) { b.lo[d] = INFINITY; b.hi[d] = -INFINITY; }
+  const size_t e = min(n, (size_t)(l + 1) * kLeaf);
+  for (size_t p = (size_t)l * kLeaf; p < e; ++p) {
+    const float4 v = s_xyz[p];
+    b.lo[0] = fminf(b.lo[0], v.x); b.lo[1] = fminf(b.lo[1], v.y); b.lo[2] = fminf(b.lo[2], v.z);
+    b.hi[0] = fmaxf(b.hi[0], v.x); b.hi[1] = fmaxf(b.hi[1], v.y); b.hi[2] = fmaxf(b.hi[2], v.z);
+  }
+  nodes[l] = b;
+}
+
+__global__ void __launch_bounds__(256) kn_merge_level(const Aabb* __restrict__ child, unsigned int nchild, Aabb* __restrict__ parent,
+                                                      unsigned int nparent) {
+  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nparent) return;
+  Aabb b = child[2 * i];
+  if (2 * i + 1 < nchild) {
+    const Aabb c = child[2 * i + 1];
+    for (int d = 0; d < 3; ++d) { b.lo[d] = fminf(b.lo[d], c.lo[d]); b.hi[d] = fmaxf(b.hi[d], c.hi[d]); }
+  }
+  parent[i] = b;
+}
+
+static constexpr int kMaxLevels = 32;
+struct BvhLevels { unsigned int offset[kMaxLevels]; unsigned int count[kMaxLevels]; int nlevels; };
+
+__device__ __forceinline__ float dist2_pt(const float4& q, const float4& t) {
+  const float dx = fsub(q.x, t.x), dy = fsub(q.y, t.y), dz = fsub(q.z, t.z);
+  return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+}
+__device__ __forceinline__ float dist2_box(const float4& q, const Aabb& b) {
+  const float dx = fmaxf(fmaxf(fsub(b.lo[0], q.x), fsub(q.x, b.hi[0])), 0.f);
+  const float dy = fmaxf(fmaxf(fsub(b.lo[1], q.y), fsub(q.y, b.hi[1])), 0.f);
+  const float dz = fmaxf(fmaxf(fsub(b.lo[2], q.z), fsub(q.z, b.hi[2])), 0.f);
+  return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+}
+
+// k-best list of one thread in shared memory, element e of thread t at [e * kKnnThreads + t] (conflict-free).
+struct KBest {
+  float* d2; unsigned int* pos; int k; int count; int worst; float worst_d2;
+  __device__ __forceinline__ float& D(int e) { return d2[e * kKnnThreads]; }
+  __device__ __forceinline__ unsigned int& P(int e) { return pos[e * kKnnThreads]; }
+};
+
+// (d2, original index) strict "less" with the index fetched lazily.
+__device__ __forceinline__ bool less_than(float da, unsigned int ia, float db, unsigned int posb, const float4* __restrict__ s) {
+  if (da != db) return da < db;
+  return ia < __float_as_uint(__ldg(&s[posb].w));
+}
+
+__device__ __forceinline__ void kbest_rescan(KBest& h, const float4* __restrict__ s) {
+  int w = 0; float wd = h.D(0);
+  for (int e = 1; e < h.count; ++e) {
+    const float d = h.D(e);
+    if (d > wd || (d == wd && __float_as_uint(__ldg(&s[h.P(e)].w)) > __float_as_uint(__ldg(&s[h.P(w)].w)))) { w = e; wd = d; }
+  }
+  h.worst = w; h.worst_d2 = wd;
+}
+
+__device__ __forceinline__ void kbest_offer(KBest& h, float d, unsigned int p, unsigned int idx, const float4* __restrict__ s) {
+  if (h.count < h.k) {
+    h.D(h.count) = d; h.P(h.count) = p; ++h.count;
+    if (h.count == h.k) kbest_rescan(h, s);
+    return;
+  }
+  if (!less_than(d, idx, h.worst_d2, h.P(h.worst), s)) return;
+  h.D(h.worst) = d; h.P(h.worst) = p;
+  kbest_rescan(h, s);
+}
+
+__device__ __forceinline__ void scan_leaf(KBest& h, const float4& q, unsigned int leaf, size_t n, const float4* __restrict__ s) {
+  const size_t b = (size_t)leaf * kLeaf, e = min(n, b + kLeaf);
+  for (size_t p = b; p < e; ++p) {
+    const float4 t = __ldg(&s[p]);
+    const float d = dist2_pt(q, t);
+    if (h.count < h.k || d <= h.worst_d2) kbest_offer(h, d, (unsigned int)p, __float_as_uint(t.w), s);
+  }
+}
+
+// ---- closed-form smallest eigenpair of a symmetric 3x3 (pcl::eigen33 / computeRoots, fp32) ----
+__device__ __forceinline__ void roots2(float b, float c, float r[3]) {
+  r[0] = 0.f;
+  float d = b * b - 4.f * c;
+  if (d < 0.f) d = 0.f;
+  const float sd = sqrtf(d);
+  r[2] = 0.5f * (b + sd);
+  r[1] = 0.5f * (b - sd);
+}
+__device__ __forceinline__ void swapf(float& a, float& b) { const float t = a; a = b; b = t; }
+__device__ void compute_roots(const float m[9], float r[3]) {
+  const float c0 = m[0] * m[4] * m[8] + 2.f * m[1] * m[2] * m[5] - m[0] * m[5] * m[5] - m[4] * m[2] * m[2] - m[8] * m[1] * m[1];
+  const float c1 = m[0] * m[4] - m[1] * m[1] + m[0] * m[8] - m[2] * m[2] + m[4] * m[8] - m[5] * m[5];
+  const float c2 = m[0] + m[4] + m[8];
+  if (fabsf(c0) < 1.1920929e-07f) { roots2(c2, c1, r); return; }
+  const float s_inv3 = 1.0f / 3.0f;
+  const float s_sqrt3 = sqrtf(3.0f);
+  const float c2_over_3 = c2 * s_inv3;
+  float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+  if (a_over_3 > 0.f) a_over_3 = 0.f;
+  const float half_b = 0.5f * (c0 + c2_over_3 * (2.f * c2_over_3 * c2_over_3 - c1));
+  float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+  if (q > 0.f) q = 0.f;
+  const float rho = sqrtf(-a_over_3);
+  const float theta = atan2f(sqrtf(-q), half_b) * s_inv3;
+  const float ct = cosf(theta), st = sinf(theta);
+  r[0] = c2_over_3 + 2.f * rho * ct;
+  r[1] = c2_over_3 - rho * (ct + s_sqrt3 * st);
+  r[2] = c2_over_3 - rho * (ct - s_sqrt3 * st);
+  if (r[0] >= r[1]) swapf(r[0], r[1]);
+  if (r[1] >= r[2]) { swapf(r[1], r[2]); if (r[0] >= r[1]) swapf(r[0], r[1]); }
+  if (r[0] <= 0.f) roots2(c2, c1, r);
+}
+__device__ __forceinline__ void cross3(const float* a, const float* b, float* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+__global__ void __launch_bounds__(kKnnThreads)
+kn_knn_normals(const float4* __restrict__ s_xyz, size_t n, const Aabb* __restrict__ nodes, BvhLevels lv, int k, float vpx, float vpy, float vpz,
+               float4* __restrict__ out, int* __restrict__ out_idx, unsigned int* __restrict__ nan_count) {
+  extern __shared__ unsigned char smem_raw[];
+  float* sm_d2 = reinterpret_cast<float*>(smem_raw);
+  unsigned int* sm_pos = reinterpret_cast<unsigned int*>(smem_raw + sizeof(float) * (size_t)k * kKnnThreads);
+  const size_t j = (size_t)blockIdx.x * kKnnThreads + threadIdx.x;
+  if (j >= n) return;
+  const float4 q = s_xyz[j];
+  KBest h{sm_d2 + threadIdx.x, sm_pos + threadIdx.x, k, 0, 0, INFINITY};
+
+  // seed with the query's own leaf and its two neighbours in Morton order
+  const unsigned int nleaf = lv.count[0];
+  const unsigned int own = (unsigned int)(j / kLeaf);
+  const unsigned int l0 = own > 0 ? own - 1 : 0, l1 = min(nleaf - 1, own + 1);
+  for (unsigned int l = l0; l <= l1; ++l) scan_leaf(h, q, l, n, s_xyz);
+
+  // near-first depth-first walk from the root; entries are (level << 27 | index)
+  unsigned int stack[kMaxLevels + 2];
+  int sp = 0;
+  stack[sp++] = ((unsigned int)(lv.nlevels - 1) << 27);
+  while (sp > 0) {
+    const unsigned int e = stack[--sp];
+    const int level = (int)(e >> 27);
+    const unsigned int i = e & 0x7FFFFFFu;
+    if (h.count == h.k && dist2_box(q, nodes[lv.offset[level] + i]) > h.worst_d2) continue;
+    if (level == 0) {
+      if (i < l0 || i > l1) scan_leaf(h, q, i, n, s_xyz);
+      continue;
+    }
+    const unsigned int c0 = 2 * i, c1 = 2 * i + 1;
+    const unsigned int nchild = lv.count[level - 1];
+    if (c1 >= nchild) { stack[sp++] = ((unsigned int)(level - 1) << 27) | c0; continue; }
+    const float d0 = dist2_box(q, nodes[lv.offset[level - 1] + c0]);
+    const float d1 = dist2_box(q, nodes[lv.offset[level - 1] + c1]);
+    const bool full = h.count == h.k;
+    const bool v0 = !full || d0 <= h.worst_d2, v1 = !full || d1 <= h.worst_d2;
+    if (d0 <= d1) {
+      if (v1) stack[sp++] = ((unsigned int)(level - 1) << 27) | c1;
+      if (v0) stack[sp++] = ((unsigned int)(level - 1) << 27) | c0;
+    } else {
+      if (v0) stack[sp++] = ((unsigned int)(level - 1) << 27) | c0;
+      if (v1) stack[sp++] = ((unsigned int)(level - 1) << 27) | c1;
+    }
+  }
+
+  // sort the list by (d2, original index): neighbour order defines the fp32 summation order
+  const int cnt = h.count;
+  for (int a = 1; a < cnt; ++a) {
+    const float d = h.D(a); const unsigned int p = h.P(a);
+    const unsigned int pi = __float_as_uint(__ldg(&s_xyz[p].w));
+    int b = a - 1;
+    while (b >= 0 && less_than(d, pi, h.D(b), h.P(b), s_xyz)) { h.D(b + 1) = h.D(b); h.P(b + 1) = h.P(b); --b; }
+    h.D(b + 1) = d; h.P(b + 1) = p;
+  }
+  const unsigned int qi = __float_as_uint(q.w);
+  if (out_idx) {
+    for (int a = 0; a < k; ++a) out_idx[(size_t)qi * k + a] = a < cnt ? (int)__float_as_uint(__ldg(&s_xyz[h.P(a)].w)) : -1;
+  }
+  const float nanv = __int_as_float(0x7fc00000);
+  if (cnt < 3) { out[qi] = make_float4(nanv, nanv, nanv, nanv); atomicAdd(nan_count, 1u); return; }
+
+  // two-pass mean / covariance, fp32, sequential in neighbour order, no contraction (two_pass_centroid.hpp:164-258)
+  float a6 = 0.f, a7 = 0.f, a8 = 0.f;
+  for (int a = 0; a < cnt; ++a) { const float4 p = __ldg(&s_xyz[h.P(a)]); a6 = fadd(a6, p.x); a7 = fadd(a7, p.y); a8 = fadd(a8, p.z); }
+  const float fn = (float)cnt;
+  a6 = a6 / fn; a7 = a7 / fn; a8 = a8 / fn;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
+  for (int a = 0; a < cnt; ++a) {
+    const float4 p = __ldg(&s_xyz[h.P(a)]);
+    const float dx = fsub(p.x, a6), dy = fsub(p.y, a7), dz = fsub(p.z, a8);
+    a0 = fadd(a0, fmul(dx, dx)); a1 = fadd(a1, fmul(dx, dy)); a2 = fadd(a2, fmul(dx, dz));
+    a3 = fadd(a3, fmul(dy, dy)); a4 = fadd(a4, fmul(dy, dz)); a5 = fadd(a5, fmul(dz, dz));
+  }
+  float cov[9];
+  cov[0] = a0 / fn; cov[1] = a1 / fn; cov[2] = a2 / fn; cov[4] = a3 / fn; cov[5] = a4 / fn; cov[8] = a5 / fn;
+  cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+
+  // pcl::eigen33: scale, closed-form roots, eigenvector from the largest cross product of rows of (A - l0 I)
+  float scale = 0.f;
+  for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(cov[i]));
+  if (scale <= 1.17549435e-38f) scale = 1.f;
+  float sc[9];
+  for (int i = 0; i < 9; ++i) sc[i] = cov[i] / scale;
+  float r[3];
+  compute_roots(sc, r);
+  const float ev = r[0] * scale;
+  sc[0] -= r[0]; sc[4] -= r[0]; sc[8] -= r[0];
+  float v1[3], v2[3], v3[3];
+  cross3(sc, sc + 3, v1); cross3(sc, sc + 6, v2); cross3(sc + 3, sc + 6, v3);
+  const float n1 = v1[0] * v1[0] + (v1[1] * v1[1] + v1[2] * v1[2]);
+  const float n2 = v2[0] * v2[0] + (v2[1] * v2[1] + v2[2] * v2[2]);
+  const float n3 = v3[0] * v3[0] + (v3[1] * v3[1] + v3[2] * v3[2]);
+  const float* v; float len;
+  if (n1 >= n2 && n1 >= n3) { v = v1; len = n1; } else if (n2 >= n1 && n2 >= n3) { v = v2; len = n2; } else { v = v3; len = n3; }
+  const float inv = sqrtf(len);
+  float nx = v[0] / inv, ny = v[1] / inv, nz = v[2] / inv;
+  const float eig_sum = cov[0] + cov[4] + cov[8];
+  const float curv = eig_sum != 0.f ? fabsf(ev / eig_sum) : 0.f;
+  // flipNormalTowardsViewpoint
+  const float wx = vpx - q.x, wy = vpy - q.y, wz = vpz - q.z;
+  if ((wx * nx + wy * ny + wz * nz) < 0.f) { nx *= -1.f; ny *= -1.f; nz *= -1.f; }
+  out[qi] = make_float4(nx, ny, nz, curv);
+}
+
+static inline unsigned int div_up_u(size_t a, size_t b) { return (unsigned int)((a + b - 1) / b); }
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_normals_estimate(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3], float* out_nxyz_curv,
+                                   int32_t* out_knn_idx, int* is_dense) {
+  if ((n && (!xyz || !out_nxyz_curv)) || !viewpoint) return set_error(B2_ERR_ARG, "null argument");
+  if (stride_bytes < 12) return set_error(B2_ERR_ARG, "stride_bytes must be >= 12");
+  if (k < 1 || k > 128) return set_error(B2_ERR_ARG, "k must be in [1,128]");
+  if (n >= (1ull << 30)) return set_error(B2_ERR_ARG, "clouds above 2^30 points are not supported");
+  if (is_dense) *is_dense = 1;
+  if (n == 0) return B2_OK;
+  int dev = 0, sms = 0;
+  B2_TRY(select_device(-1, &dev, &sms));
+  cudaStream_t st; B2_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  DevBuf d_xyz, d_part, d_keys, d_keys2, d_idx, d_perm, d_sxyz, d_nodes, d_tmp, d_out, d_oidx, d_nan;
+  PinnedBuf p_part;
+  int rc = B2_OK;
+  auto body = [&]() -> int {
+    B2_TRY(d_xyz.ensure(n * 12));
+    if (stride_bytes == 12) B2_CUDA(cudaMemcpyAsync(d_xyz.p, xyz, n * 12, cudaMemcpyHostToDevice, st));
+    else B2_CUDA(cudaMemcpy2DAsync(d_xyz.p, 12, xyz, stride_bytes, 12, n, cudaMemcpyHostToDevice, st));
+    const int bb = sms * 2;
+    B2_TRY(d_part.ensure(sizeof(float) * 6 * bb)); B2_TRY(p_part.ensure(sizeof(float) * 6 * bb));
+    kn_bbox<<<bb, 256, 0, st>>>(d_xyz.as<float>(), n, d_part.as<float>());
+    B2_CUDA(cudaMemcpyAsync(p_part.p, d_part.p, sizeof(float) * 6 * bb, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int b = 0; b < bb; ++b) for (int d = 0; d < 3; ++d) {
+      mn[d] = std::min(mn[d], p_part.as<float>()[6 * b + d]); mx[d] = std::max(mx[d], p_part.as<float>()[6 * b + 3 + d]);
+    }
+    for (int d = 0; d < 3; ++d) if (!std::isfinite(mn[d]) || !std::isfinite(mx[d])) return set_error(B2_ERR_ARG, "non-finite coordinates (dense clouds only)");
+    const float ext = std::max({mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2], 1e-30f});
+    const float scale = 2097151.f / ext;
+    B2_TRY(d_keys.ensure(n * 8)); B2_TRY(d_keys2.ensure(n * 8)); B2_TRY(d_idx.ensure(n * 4)); B2_TRY(d_perm.ensure(n * 4));
+    B2_TRY(d_sxyz.ensure(n * 16));
+    kn_morton<<<div_up_u(n, 256), 256, 0, st>>>(d_xyz.as<float>(), n, mn[0], mn[1], mn[2], scale, d_keys.as<unsigned long long>(), d_idx.as<unsigned int>());
+    size_t tmp = 0;
+    B2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_keys.as<unsigned long long>(), d_keys2.as<unsigned long long>(), d_idx.as<unsigned int>(),
+                                            d_perm.as<unsigned int>(), (long long)n, 0, 63, st));
+    B2_TRY(d_tmp.ensure(tmp));
+    B2_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp, d_keys.as<unsigned long long>(), d_keys2.as<unsigned long long>(), d_idx.as<unsigned int>(),
+                                            d_perm.as<unsigned int>(), (long long)n, 0, 63, st));
+    kn_gather<<<div_up_u(n, 256), 256, 0, st>>>(d_xyz.as<float>(), n, d_perm.as<unsigned int>(), d_sxyz.as<float4>());
+    // implicit BVH levels
+    BvhLevels lv; std::memset(&lv, 0, sizeof(lv));
+    unsigned int cnt = div_up_u(n, kLeaf), off = 0; int L = 0;
+    while (true) { lv.offset[L] = off; lv.count[L] = cnt; off += cnt; ++L; if (cnt == 1) break; cnt = (cnt + 1) / 2; }
+    lv.nlevels = L;
+    B2_TRY(d_nodes.ensure(sizeof(Aabb) * (size_t)off));
+    kn_leaf_aabb<<<div_up_u(lv.count[0], 256), 256, 0, st>>>(d_sxyz.as<float4>(), n, lv.count[0], d_nodes.as<Aabb>());
+    for (int l = 1; l < L; ++l)
+      kn_merge_level<<<div_up_u(lv.count[l], 256), 256, 0, st>>>(d_nodes.as<Aabb>() + lv.offset[l - 1], lv.count[l - 1],
+                                                                 d_nodes.as<Aabb>() + lv.offset[l], lv.count[l]);
+    B2_TRY(d_out.ensure(n * 16));
+    if (out_knn_idx) B2_TRY(d_oidx.ensure(n * (size_t)k * 4));
+    B2_TRY(d_nan.ensure(4));
+    B2_CUDA(cudaMemsetAsync(d_nan.p, 0, 4, st));
+    const size_t smem = (size_t)k * kKnnThreads * 8;
+    B2_CUDA(cudaFuncSetAttribute(kn_knn_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kn_knn_normals<<<div_up_u(n, kKnnThreads), kKnnThreads, smem, st>>>(d_sxyz.as<float4>(), n, d_nodes.as<Aabb>(), lv, k, viewpoint[0], viewpoint[1],
+                                                                       viewpoint[2], d_out.as<float4>(), out_knn_idx ? d_oidx.as<int>() : nullptr,
+                                                                       d_nan.as<unsigned int>());
+    B2_CUDA(cudaGetLastError());
+    unsigned int nans = 0;
+    B2_CUDA(cudaMemcpyAsync(out_nxyz_curv, d_out.p, n * 16, cudaMemcpyDeviceToHost, st));
+    if (out_knn_idx) B2_CUDA(cudaMemcpyAsync(out_knn_idx, d_oidx.p, n * (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(&nans, d_nan.p, 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (is_dense) *is_dense = nans == 0;
+    return B2_OK;
+  };
+  rc = body();
+  for (DevBuf* b : {&d_xyz, &d_part, &d_keys, &d_keys2, &d_idx, &d_perm, &d_sxyz, &d_nodes, &d_tmp, &d_out, &d_oidx, &d_nan}) b->release();
+  p_part.release();
+  cudaStreamDestroy(st);
+  return rc;
+}

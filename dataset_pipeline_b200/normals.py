@@ -1,0 +1,50 @@
+"""Host-side mirror of pcl::NormalEstimationTwoPassOMP (/root/reference/src/geometry/two_pass_normal_3d_omp.h:53-99) as the
+tools drive it (icp_scan_aligner.cc:323-330, normal_estimator.cc:177-194): setInputCloud / setKSearch / setViewPoint / compute."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class NormalEstimationTwoPassOMP:
+    def __init__(self):
+        self._xyz = None
+        self._k = 0
+        self._vp = np.zeros(3, np.float32)
+        self.is_dense = True
+
+    def setInputCloud(self, xyz):
+        self._xyz = np.ascontiguousarray(xyz, np.float32)
+        if self._xyz.ndim != 2 or self._xyz.shape[1] != 3:
+            raise ValueError("expected (n,3) float32")
+
+    def setSearchMethod(self, tree=None):   # the spatial index is internal (implicit BVH on the GPU)
+        pass
+
+    def setKSearch(self, k):
+        self._k = int(k)
+
+    def setViewPoint(self, x, y, z):
+        self._vp = np.array([x, y, z], np.float32)
+
+    def compute(self, return_indices=False):
+        """Returns (n,4) float32: normal_x, normal_y, normal_z, curvature (NaN rows where < 3 neighbours)."""
+        if self._xyz is None or self._k <= 0:
+            raise _lib.B2Error(2, "setInputCloud and setKSearch must be called first")
+        n = self._xyz.shape[0]
+        out = np.zeros((n, 4), np.float32)
+        idx = np.zeros((n, self._k), np.int32) if return_indices else None
+        dense = C.c_int32(1)
+        fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        _lib.check(_lib.lib().b2_normals_estimate(self._xyz.ctypes.data, n, 12, self._k, self._vp.ctypes.data_as(fp),
+                                                  out.ctypes.data_as(fp), idx.ctypes.data_as(ip) if return_indices else None,
+                                                  C.byref(dense)))
+        self.is_dense = bool(dense.value)
+        return (out, idx) if return_indices else out
+
+
+def estimate_normals(xyz, k, viewpoint=(0.0, 0.0, 0.0), return_indices=False):
+    ne = NormalEstimationTwoPassOMP()
+    ne.setInputCloud(xyz); ne.setKSearch(k); ne.setViewPoint(*viewpoint)
+    return ne.compute(return_indices)

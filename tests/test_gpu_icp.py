@@ -1,0 +1,212 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+Bar: correspondence lists bit-exact; normal equations and poses within 1e-5 relative Frobenius."""
+import math
+
+import numpy as np
+import pytest
+
+from tests.golden import ref_test_inputs as rti
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def rel_fro(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64) - np.asarray(b, np.float64)) / max(np.linalg.norm(np.asarray(b, np.float64)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def b2():
+    import dataset_pipeline_b200 as b2
+    return b2
+
+
+@pytest.fixture(scope="module")
+def room3():
+    from dataset_pipeline_b200 import synth
+    return synth.room_scans(3, 300, 120)      # 3 x 36k points
+
+
+def test_find_correspondences_bit_exact(b2, oracle):
+    rng = np.random.default_rng(3)
+    tgt = rng.uniform(-1, 1, (40000, 3)).astype(np.float32)
+    src = rng.uniform(-1.05, 1.05, (30000, 3)).astype(np.float32)
+    tgt[100:110] = tgt[50:60]            # exact duplicates: lowest-index tie-break
+    src[:10] = tgt[50:60]
+    for d in (0.01, 0.03, 0.1):
+        qa, ma, da = b2.find_correspondences(src, tgt, d)
+        qb, mb, db = oracle.find_correspondences(src, tgt, d, use_kdtree=True)
+        assert np.array_equal(qa, qb)
+        assert np.array_equal(ma, mb)
+        assert np.array_equal(da, db)
+    assert set(ma[:10].tolist()) <= set(range(50, 60))
+
+
+def test_find_correspondences_edge_cases(b2, oracle):
+    e = np.zeros((0, 3), np.float32)
+    p = np.random.default_rng(0).uniform(0, 1, (100, 3)).astype(np.float32)
+    assert len(b2.find_correspondences(e, p, 0.1)[0]) == 0
+    assert len(b2.find_correspondences(p, e, 0.1)[0]) == 0
+    assert len(b2.find_correspondences(p, p + 10.0, 0.1)[0]) == 0
+    # boxes that do not intersect but lie within d of each other still match (no bbox gate in FindCorrespondencesFast)
+    a = np.array([[0, 0, 0]], np.float32); b = np.array([[0.05, 0, 0]], np.float32)
+    assert len(b2.find_correspondences(a, b, 0.1)[0]) == 1
+    # strict radius
+    t = np.array([[0.5, 0, 0]], np.float32)
+    assert len(b2.find_correspondences(a, t, 0.5)[0]) == 0
+    assert len(b2.find_correspondences(a, t, float(np.nextafter(np.float32(0.5), np.float32(1))))[0]) == 1
+    # far-from-origin coordinates (large cell indices)
+    big = (p * 50 + 4000).astype(np.float32)
+    qa, ma, da = b2.find_correspondences(big, big[::-1].copy(), 0.5)
+    qb, mb, db = oracle.find_correspondences(big, big[::-1].copy(), 0.5)
+    assert np.array_equal(qa, qb) and np.array_equal(ma, mb) and np.array_equal(da, db)
+
+
+def _setup_pair(b2, oracle, clouds, poses, fixed_first=False, inner=150):
+    g = b2.PointToPlaneICP(keep_correspondences=True, inner_max_iterations=inner)
+    o = oracle.PointToPlaneICP(use_kdtree=True, inner_max_iterations=inner)
+    ids = []
+    for k, ((xyz, nrm), T) in enumerate(zip(clouds, poses)):
+        fx = fixed_first and k == 0
+        ig = g.AddPointCloud(xyz, nrm, T, fx); io = o.AddPointCloud(xyz, nrm, T, fx)
+        assert ig == io
+        if not fx:
+            ids.append(ig)
+    return g, o, ids
+
+
+def _check_iteration(g, o, ids):
+    pg, po = g.pairs(), o.pairs()
+    assert [(s, t) for s, t, *_ in pg] == [(s, t) for s, t, *_ in po]
+    for (s, t, q1, m1, d1), (_, _, q2, m2, d2) in zip(pg, po):
+        assert np.array_equal(q1, q2), "query indices differ for pair %d->%d" % (s, t)
+        assert np.array_equal(m1, m2), "match indices differ for pair %d->%d" % (s, t)
+        assert np.array_equal(d1, d2), "squared distances differ for pair %d->%d" % (s, t)
+    Hg, bg, cg = g.normal_equations()
+    Ho, bo = o.normal_equations()
+    so = o.stats(); sg = g.stats()
+    assert sg["num_correspondences"] == so["num_correspondences"]
+    assert sg["num_pairs"] == so["num_pairs"]
+    if Ho.size:
+        assert rel_fro(Hg, Ho) <= TOL
+        assert rel_fro(bg, bo) <= TOL
+    assert abs(cg - so["first_cost"]) <= 1e-9 * max(1.0, abs(so["first_cost"]))
+    for i in ids:
+        assert rel_fro(g.GetResultGlobalTCloud(i), o.GetResultGlobalTCloud(i)) <= TOL
+    return sg, so
+
+
+def test_room_one_outer_iteration(b2, oracle, room3):
+    clouds, poses, _ = room3
+    g, o, ids = _setup_pair(b2, oracle, clouds, poses)
+    g.Run(0.05, 0, 1, 1e-10, False); o.Run(0.05, 0, 1, 1e-10, False)
+    sg, so = _check_iteration(g, o, ids)
+    assert sg["num_correspondences"] > 20000
+    # same LM accept/reject sequence on this scene
+    assert np.array_equal(g.tries(), o.tries())
+    assert abs(sg["last_cost"] - so["last_cost"]) <= 1e-6 * so["last_cost"]
+
+
+def test_room_trajectory_with_pose_resync(b2, oracle, room3):
+    """10 outer iterations; before each one both sides are given the oracle's poses, so every iteration is compared
+    on identical inputs (correspondences bit-exact, pose update within 1e-5)."""
+    clouds, poses, _ = room3
+    g, o, ids = _setup_pair(b2, oracle, clouds, poses)
+    for it in range(10):
+        for i in ids:
+            g.SetGlobalTCloud(i, o.GetResultGlobalTCloud(i))
+        g.Run(0.05, it, 1, 1e-10, False); o.Run(0.05, it, 1, 1e-10, False)
+        _check_iteration(g, o, ids)
+
+
+def test_room_free_running_converges_like_oracle(b2, oracle, room3):
+    clouds, poses, gts = room3
+    g, o, ids = _setup_pair(b2, oracle, clouds, poses)
+    g.Run(0.05, 0, 15, 1e-10, False); o.Run(0.05, 0, 15, 1e-10, False)
+    for i in ids:
+        assert rel_fro(g.GetResultGlobalTCloud(i), o.GetResultGlobalTCloud(i)) <= 1e-4
+
+
+def test_fixed_cloud_both_directions(b2, oracle, room3):
+    clouds, poses, _ = room3
+    g, o, ids = _setup_pair(b2, oracle, clouds, poses, fixed_first=True)
+    g.Run(0.05, 0, 1, 1e-10, False); o.Run(0.05, 0, 1, 1e-10, False)
+    sg, _ = _check_iteration(g, o, ids)
+    assert sg["num_variables"] == 12
+    assert (1, 0) in [(s, t) for s, t, *_ in g.pairs()] and (0, 1) in [(s, t) for s, t, *_ in g.pairs()]
+
+
+def test_ref_identical_cloud_alignment_gpu(b2, oracle):
+    """The reference's own test (test_icp.cc:39-109) through the C ABI."""
+    pts, nrm, poses = rti.identical_cloud_alignment_inputs()
+    icp = b2.PointToPlaneICP()
+    ids = [icp.AddPointCloud(pts, nrm, T, False) for T in poses]
+    assert ids == list(range(20))
+    icp.Run(float(np.float32(0.15) * np.float32(math.sqrt(3))), 0, 100, 1e-7, False)
+    T0 = icp.GetResultGlobalTCloud(ids[0])
+    for i in ids[1:]:
+        assert np.abs(T0[:3, :] - icp.GetResultGlobalTCloud(i)[:3, :]).max() <= 1e-5
+
+
+def test_ref_plane_with_single_point_gpu(b2):
+    """The reference's own test (test_icp.cc:111-172) through the C ABI: rank-deficient planar case."""
+    pts, nrm, poses = rti.plane_with_single_point_inputs()
+    icp = b2.PointToPlaneICP()
+    a = icp.AddPointCloud(pts, nrm, poses[0], False); b = icp.AddPointCloud(pts, nrm, poses[1], False)
+    icp.Run(1.5, 0, 100, 1e-7, False)
+    assert np.abs(icp.GetResultGlobalTCloud(a)[:3, :] - icp.GetResultGlobalTCloud(b)[:3, :]).max() <= 1e-5
+
+
+def test_config1_relief_scans(b2, oracle):
+    """BASELINE config 1: 2 x 50k scans, -d 0.01, 10 iterations, pose-resynced per iteration."""
+    from dataset_pipeline_b200 import synth
+    clouds, poses = synth.relief_scans()
+    g, o, ids = _setup_pair(b2, oracle, clouds, poses)
+    for it in range(10):
+        for i in ids:
+            g.SetGlobalTCloud(i, o.GetResultGlobalTCloud(i))
+        g.Run(0.01, it, 1, 1e-10, False); o.Run(0.01, it, 1, 1e-10, False)
+        _check_iteration(g, o, ids)
+
+
+def test_pointnormal_strided_input(b2, oracle, room3):
+    clouds, poses, _ = room3
+    xyz, nrm = clouds[0]
+    pn = np.zeros((len(xyz), 12), np.float32)
+    pn[:, 0:3] = xyz; pn[:, 4:7] = nrm
+    g1 = b2.PointToPlaneICP(); g2 = b2.PointToPlaneICP()
+    for g in (g1, g2):
+        if g is g1:
+            g.AddPointNormalArray(pn, poses[0]); g.AddPointCloud(clouds[1][0], clouds[1][1], poses[1])
+        else:
+            g.AddPointCloud(xyz, nrm, poses[0]); g.AddPointCloud(clouds[1][0], clouds[1][1], poses[1])
+        g.Run(0.05, 0, 1, 1e-10, False)
+    assert np.array_equal(g1.GetResultGlobalTCloud(1), g2.GetResultGlobalTCloud(1))
+
+
+def test_error_paths(b2):
+    from dataset_pipeline_b200._lib import B2Error
+    icp = b2.PointToPlaneICP()
+    with pytest.raises(B2Error):
+        icp.Run(0.1, 0, 1, 1e-6, False)          # reference: CHECK(!clouds_.empty())
+    with pytest.raises(B2Error):
+        icp.GetResultGlobalTCloud(3)
+    # single movable cloud, no fixed: zero variables, nothing moves, converges immediately
+    p = np.random.default_rng(0).uniform(0, 1, (100, 3)).astype(np.float32)
+    icp.AddPointCloud(p, p, np.eye(4, dtype=np.float32))
+    assert icp.Run(0.1, 0, 3, 1e-6, False) is True
+    assert np.array_equal(icp.GetResultGlobalTCloud(0), np.eye(4, dtype=np.float32))
+
+
+def test_deterministic_repeat(b2, room3):
+    clouds, poses, _ = room3
+    res = []
+    for _ in range(2):
+        g = b2.PointToPlaneICP()
+        for (xyz, nrm), T in zip(clouds, poses):
+            g.AddPointCloud(xyz, nrm, T)
+        g.Run(0.05, 0, 3, 1e-10, False)
+        res.append([g.GetResultGlobalTCloud(i) for i in range(3)] + [g.stats()["last_cost"]])
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
