@@ -47,7 +47,7 @@ EXPORTS = [
     "b2_last_error", "b2_abi_version", "b2_device_info", "b2_icp_default_config", "b2_icp_create", "b2_icp_destroy",
     "b2_icp_add_cloud", "b2_icp_add_cloud_dev", "b2_icp_run", "b2_icp_get_pose", "b2_icp_set_pose", "b2_icp_last_stats",
     "b2_icp_get_lm_tries", "b2_icp_get_pair_info", "b2_icp_get_pair_correspondences", "b2_icp_get_normal_equations",
-    "b2_find_correspondences", "b2_normals_estimate",
+    "b2_find_correspondences", "b2_normals_estimate", "b2_icp_plan_directions",
 ]
 
 
@@ -77,6 +77,7 @@ def lib():
     L.b2_icp_get_pair_info.argtypes = [vp, C.c_int, ip, ip, C.POINTER(C.c_uint64)]
     L.b2_icp_get_pair_correspondences.argtypes = [vp, C.c_int, ip, ip, fp]
     L.b2_icp_get_normal_equations.argtypes = [vp, dp, dp, dp, ip]
+    L.b2_icp_plan_directions.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, C.c_int, ip]
     L.b2_find_correspondences.argtypes = [fp, C.c_size_t, fp, C.c_size_t, C.c_float, ip, ip, fp, C.POINTER(C.c_uint64)]
     L.b2_normals_estimate.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_int, fp, fp, ip, ip]
     _lib = L

@@ -161,8 +161,9 @@ static int compute_grid(b2_icp* h, float max_dist, GridParams* g, int* key_bits)
   for (int d = 0; d < 3; ++d)
     if (!std::isfinite(mn[d]) || !std::isfinite(mx[d]))
       return set_error(B2_ERR_ARG, "non-finite point coordinates (clouds must be dense, as the reference's is_dense path assumes)");
-  // cell >= d*(1+1e-4): any target with fp32 d2 < fl(d*d) lies in the 27-neighbourhood of the query's cell.
-  double cell = (double)max_dist * 1.0001;
+  // cell >= 2d*(1+1e-4): any target with fp32 d2 < fl(d*d) lies in the 2x2x2 block of cells on the query's side of its cell
+  // (k_nn_radius1): the face on the far side is >= cell/2 > d away.
+  double cell = (double)max_dist * 2.0002;
   if (!(cell > 0.0)) cell = 1e-30;
   const double ext = std::max({(double)mx[0] - mn[0], (double)mx[1] - mn[1], (double)mx[2] - mn[2]});
   cell = std::max(cell, ext / 2097000.0);    // keep every axis below 2^21 cells
@@ -273,22 +274,20 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   for (int i = 0; i < nc; ++i) { impl_cloud(h, i)->ncells = h->pin_counts.as<unsigned int>()[i]; B2_TRY(index_cloud_phase2(h, impl_cloud(h, i))); }
   B2_CUDA(cudaEventRecord(h->ev[1], h->stream));
 
-  // ---- pair scheduling in ik order (icp_point_to_plane.cc:208-309) ----
+  // ---- pair scheduling in ik order (icp_point_to_plane.cc:208-309); ownership from the shared planner ----
   h->ndirs = 0;
-  const int fixed_idx = h->fixed ? 0 : -1;
-  for (int i = 0; i < nmov; ++i) {
-    for (int k = 0; k < nmov; ++k) {
-      Cloud* A = h->movable[i].get(); Cloud* B = h->movable[k].get();
-      if (i != k && (!gate || boxes_intersect(A, B))) {
-        Direction* d = next_direction(h); d->src = impl_index_of_movable(h, i); d->tgt = impl_index_of_movable(h, k);
-      }
-      if (i == k && h->fixed && boxes_intersect(h->fixed.get(), A)) {
-        Direction* d = next_direction(h); d->src = impl_index_of_movable(h, i); d->tgt = fixed_idx;
-        Direction* e = next_direction(h); e->src = fixed_idx; e->tgt = impl_index_of_movable(h, i);
+  const int world = std::max(1, h->cfg.world_size), rank = h->cfg.rank;
+  {
+    const int cap = nmov * nmov + 2 * nmov + 1;
+    std::vector<int32_t> ps(cap), pt(cap), po(cap);
+    int cnt = 0;
+    B2_TRY(b2_icp_plan_directions(nmov, h->fixed ? 1 : 0, world, ps.data(), pt.data(), po.data(), cap, &cnt));
+    for (int k = 0; k < cnt; ++k) {
+      if (!gate || boxes_intersect(impl_cloud(h, ps[k]), impl_cloud(h, pt[k]))) {
+        Direction* d = next_direction(h); d->src = ps[k]; d->tgt = pt[k]; d->local = po[k] == rank;
       }
     }
   }
-  const int world = std::max(1, h->cfg.world_size), rank = h->cfg.rank;
   const float r2 = (float)((double)max_dist * (double)max_dist);
 
   // ---- K3 + compaction offsets ----
@@ -297,7 +296,6 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   unsigned int* tails = h->pin_misc.as<unsigned int>();
   for (int k = 0; k < h->ndirs; ++k) {
     Direction* d = h->dirs[k].get();
-    d->local = (k % world) == rank;
     d->count = 0;
     if (!d->local) continue;
     Cloud* S = impl_cloud(h, d->src); Cloud* T = impl_cloud(h, d->tgt);
@@ -453,6 +451,24 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
 }  // namespace b2
 
 extern "C" {
+
+int b2_icp_plan_directions(int n_movable, int has_fixed, int world_size, int32_t* src_impl, int32_t* tgt_impl, int32_t* owner, int cap,
+                           int* count) {
+  if (!count || n_movable < 0 || world_size < 1) return set_error(B2_ERR_ARG, "bad argument");
+  int n = 0;
+  auto emit = [&](int s, int t) {
+    if (n < cap) { if (src_impl) src_impl[n] = s; if (tgt_impl) tgt_impl[n] = t; if (owner) owner[n] = n % world_size; }
+    ++n;
+  };
+  const int off = has_fixed ? 1 : 0;   // impl index 0 is the fixed cloud when there is one
+  for (int i = 0; i < n_movable; ++i)
+    for (int k = 0; k < n_movable; ++k) {
+      if (i != k) emit(i + off, k + off);
+      else if (has_fixed) { emit(i + off, 0); emit(0, i + off); }
+    }
+  *count = n;
+  return n <= cap ? B2_OK : set_error(B2_ERR_ARG, "capacity %d too small for %d directions", cap, n);
+}
 
 const char* b2_last_error(void) { return last_error_ref().c_str(); }
 int b2_abi_version(void) { return B2_ABI_VERSION; }

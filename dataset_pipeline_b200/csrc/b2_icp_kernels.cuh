@@ -133,9 +133,34 @@ __global__ void __launch_bounds__(256) k_hash_ends(const unsigned long long* __r
 // ------------------------------------------------------------------------------------------------------------------
 // K3: nearest target within radius (strict d2 < r2), lowest ORIGINAL target index on exact ties.
 // d2 = ((dx*dx)+(dy*dy))+(dz*dz) in fp32 without contraction (FLANN L2_Simple order).
-// One thread per cell-sorted source point: neighbouring threads share cells, so the 27 probes and the candidate
-// rows are served from L1/L2. Output at the sorted source position.
+// Grid cells are >= 2d wide, so every target within d of a query lies in the 2x2x2 block of cells on the query's side of
+// its own cell (per axis: the neighbour across the NEARER face; the farther face is >= cell/2 >= d away). One thread per
+// cell-sorted source point: the 8 table probes are issued together (independent LDG.128), the query's own cell is scanned
+// first and the other seven are skipped when their nearest face is already farther than the best match.
+// Neighbouring threads share cells, so probes and candidate rows are served from L1/L2. Output at the sorted source position.
 // ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void scan_cell(const float4* __restrict__ tgt, unsigned int b, unsigned int e, const float4& q, float& best,
+                                          int& best_pos, unsigned int& best_idx) {
+  unsigned int p = b;
+  for (; p + 1 < e; p += 2) {   // two candidates in flight
+    const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + p + 1);
+    const float ax = fsub(q.x, t0.x), ay = fsub(q.y, t0.y), az = fsub(q.z, t0.z);
+    const float bx = fsub(q.x, t1.x), by = fsub(q.y, t1.y), bz = fsub(q.z, t1.z);
+    const float d0 = fadd(fadd(fmul(ax, ax), fmul(ay, ay)), fmul(az, az));
+    const float d1 = fadd(fadd(fmul(bx, bx), fmul(by, by)), fmul(bz, bz));
+    const unsigned int i0 = __float_as_uint(t0.w), i1 = __float_as_uint(t1.w);
+    if (d0 < best || (d0 == best && best_pos >= 0 && i0 < best_idx)) { best = d0; best_pos = (int)p; best_idx = i0; }
+    if (d1 < best || (d1 == best && best_pos >= 0 && i1 < best_idx)) { best = d1; best_pos = (int)p + 1; best_idx = i1; }
+  }
+  if (p < e) {
+    const float4 t0 = __ldg(tgt + p);
+    const float ax = fsub(q.x, t0.x), ay = fsub(q.y, t0.y), az = fsub(q.z, t0.z);
+    const float d0 = fadd(fadd(fmul(ax, ax), fmul(ay, ay)), fmul(az, az));
+    const unsigned int i0 = __float_as_uint(t0.w);
+    if (d0 < best || (d0 == best && best_pos >= 0 && i0 < best_idx)) { best = d0; best_pos = (int)p; best_idx = i0; }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_nn_radius1(const float4* __restrict__ src, size_t ns, const float4* __restrict__ tgt,
                                                     const HashEntry* __restrict__ table, int log2size, GridParams g, float r2,
                                                     int* __restrict__ match_pos, float* __restrict__ match_d2,
@@ -143,33 +168,46 @@ __global__ void __launch_bounds__(256) k_nn_radius1(const float4* __restrict__ s
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= ns) return;
   const float4 q = src[j];
-  const int cx = cell_of(q.x, g.ox, g.inv), cy = cell_of(q.y, g.oy, g.inv), cz = cell_of(q.z, g.oz, g.inv);
+  const double fx = ((double)q.x - g.ox) * g.inv, fy = ((double)q.y - g.oy) * g.inv, fz = ((double)q.z - g.oz) * g.inv;
+  const int cx = (int)floor(fx), cy = (int)floor(fy), cz = (int)floor(fz);
+  const double rx = fx - cx, ry = fy - cy, rz = fz - cz;               // position inside the cell, [0,1)
+  const int sx = rx < 0.5 ? -1 : 1, sy = ry < 0.5 ? -1 : 1, sz = rz < 0.5 ? -1 : 1;
+  // distance to the nearer face per axis, shrunk so that fp32 rounding of d2 can never beat the bound
+  const double cell = 1.0 / g.inv;
+  const float ex = (float)((rx < 0.5 ? rx : 1.0 - rx) * cell * 0.9999);
+  const float ey = (float)((ry < 0.5 ? ry : 1.0 - ry) * cell * 0.9999);
+  const float ez = (float)((rz < 0.5 ? rz : 1.0 - rz) * cell * 0.9999);
+  const float ex2 = ex * ex * 0.9999f, ey2 = ey * ey * 0.9999f, ez2 = ez * ez * 0.9999f;
+
+  // 8 probes up front: bit0 = x neighbour, bit1 = y, bit2 = z
+  unsigned int cb[8], ce[8];
+  const unsigned int mask = (1u << log2size) - 1u;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int x = cx + ((c & 1) ? sx : 0), y = cy + ((c & 2) ? sy : 0), z = cz + ((c & 4) ? sz : 0);
+    cb[c] = 0; ce[c] = 0;
+    if (x < 0 || x >= g.nx || y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+    const unsigned long long key = cell_key(g, x, y, z);
+    unsigned int s = hash_slot(key, log2size);
+    uint4 e = __ldg(reinterpret_cast<const uint4*>(table + s));
+    unsigned long long k = ((unsigned long long)e.y << 32) | e.x;
+    while (k != key && k != kEmptyKey) {      // linear probing (rare at load factor <= 0.5)
+      s = (s + 1) & mask;
+      e = __ldg(reinterpret_cast<const uint4*>(table + s));
+      k = ((unsigned long long)e.y << 32) | e.x;
+    }
+    if (k == key) { cb[c] = e.z; ce[c] = e.w; }
+  }
   float best = r2;
   int best_pos = -1;
   unsigned int best_idx = 0xFFFFFFFFu;
-#pragma unroll 1
-  for (int dz = -1; dz <= 1; ++dz) {
-    const int z = cz + dz;
-    if (z < 0 || z >= g.nz) continue;
-#pragma unroll 1
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int y = cy + dy;
-      if (y < 0 || y >= g.ny) continue;
-#pragma unroll 1
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int x = cx + dx;
-        if (x < 0 || x >= g.nx) continue;
-        unsigned int b, e;
-        if (!hash_find(table, log2size, cell_key(g, x, y, z), &b, &e)) continue;
-        for (unsigned int p = b; p < e; ++p) {
-          const float4 t = __ldg(tgt + p);
-          const float ddx = fsub(q.x, t.x), ddy = fsub(q.y, t.y), ddz = fsub(q.z, t.z);
-          const float d2 = fadd(fadd(fmul(ddx, ddx), fmul(ddy, ddy)), fmul(ddz, ddz));
-          const unsigned int ti = __float_as_uint(t.w);
-          if (d2 < best || (d2 == best && best_pos >= 0 && ti < best_idx)) { best = d2; best_pos = (int)p; best_idx = ti; }
-        }
-      }
-    }
+  scan_cell(tgt, cb[0], ce[0], q, best, best_pos, best_idx);
+#pragma unroll
+  for (int c = 1; c < 8; ++c) {
+    if (cb[c] == ce[c]) continue;
+    const float lb = ((c & 1) ? ex2 : 0.f) + ((c & 2) ? ey2 : 0.f) + ((c & 4) ? ez2 : 0.f);
+    if (lb > best) continue;
+    scan_cell(tgt, cb[c], ce[c], q, best, best_pos, best_idx);
   }
   match_pos[j] = best_pos;
   match_d2[j] = best;

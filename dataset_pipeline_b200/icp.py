@@ -152,3 +152,12 @@ def find_correspondences(src_xyz, tgt_xyz, max_correspondence_distance):
     c = C.c_uint64(0)
     _lib.check(_lib.lib().b2_find_correspondences(_f(src), n, _f(tgt), tgt.shape[0], max_correspondence_distance, _i(q), _i(m), _f(d2), C.byref(c)))
     return q[:c.value].copy(), m[:c.value].copy(), d2[:c.value].copy()
+
+
+def plan_directions(n_movable, has_fixed=False, world_size=1):
+    """[(src_impl_index, tgt_impl_index, owner_rank)] in the reference's ik order (host-only call, no GPU needed)."""
+    cap = n_movable * n_movable + 2 * n_movable + 1
+    s = np.zeros(cap, np.int32); t = np.zeros(cap, np.int32); o = np.zeros(cap, np.int32)
+    c = C.c_int32(0)
+    _lib.check(_lib.lib().b2_icp_plan_directions(n_movable, int(has_fixed), world_size, _i(s), _i(t), _i(o), cap, C.byref(c)))
+    return [(int(s[k]), int(t[k]), int(o[k])) for k in range(c.value)]

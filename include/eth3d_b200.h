@@ -114,6 +114,12 @@ int b2_icp_get_pair_correspondences(b2_icp* h, int k, int32_t* index_query, int3
  * H: nv*nv doubles column-major, b: nv doubles. */
 int b2_icp_get_normal_equations(b2_icp* h, double* H, double* b, double* cost, int* nv);
 
+/* Pure host function (no device needed): the pair-directions AlignMeshes searches for n_movable clouds (+ the fixed cloud), in
+ * the reference's ik order (icp_point_to_plane.cc:208-309, before the bbox gate), as impl-cloud indices (0 = fixed cloud if any),
+ * and the rank that owns each under the round-robin sharding used by b2_icp_run. *count receives the number of directions. */
+int b2_icp_plan_directions(int n_movable, int has_fixed, int world_size, int32_t* src_impl, int32_t* tgt_impl, int32_t* owner,
+                           int cap, int* count);
+
 /* Stand-alone correspondence search = FindCorrespondencesFast (icp_point_to_plane.cc:42-105) on two point sets that
  * are already in a common frame. Outputs sized for n_src; *count receives the number of correspondences. */
 int b2_find_correspondences(const float* src_xyz, size_t n_src, const float* tgt_xyz, size_t n_tgt,

@@ -30,7 +30,8 @@ class IcpStats(C.Structure):
     _fields_ = [("inner_iterations", C.c_int32), ("lm_tries_total", C.c_int32), ("num_pairs", C.c_int32),
                 ("num_variables", C.c_int32), ("num_correspondences", C.c_uint64),
                 ("first_cost", C.c_double), ("last_cost", C.c_double), ("final_lambda", C.c_double),
-                ("t_transform", C.c_double), ("t_search", C.c_double), ("t_inner", C.c_double)]
+                ("t_transform", C.c_double), ("t_search", C.c_double), ("t_inner", C.c_double),
+                ("t_acc", C.c_double), ("t_cost", C.c_double)]
 
 
 def lib():
@@ -44,6 +45,7 @@ def lib():
     L.orc_icp_create.restype = C.c_void_p
     L.orc_icp_destroy.argtypes = [C.c_void_p]
     L.orc_icp_set_options.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.orc_icp_set_query_stride.argtypes = [C.c_void_p, C.c_size_t]
     L.orc_icp_add_cloud.argtypes = [C.c_void_p, fp, fp, C.c_size_t, fp, C.c_int]
     L.orc_icp_run.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_float, ip]
     L.orc_icp_get_pose.argtypes = [C.c_void_p, C.c_int, fp]
@@ -56,6 +58,7 @@ def lib():
     L.orc_transform_cloud.argtypes = [fp, fp, C.c_size_t, fp, fp, fp]
     L.orc_find_correspondences.argtypes = [fp, C.c_size_t, fp, C.c_size_t, C.c_float, C.c_int, ip, ip, fp]
     L.orc_find_correspondences.restype = C.c_uint64
+    L.orc_time_search.argtypes = [fp, C.c_size_t, fp, C.c_size_t, C.c_float, dp, dp, C.POINTER(C.c_uint64)]
     L.orc_se3_exp_left_mul.argtypes = [dp, fp, fp, fp, fp]
     L.orc_ldlt_solve_upper.argtypes = [dp, C.c_int, dp, dp]
     L.orc_normals_knn.argtypes = [fp, C.c_size_t, C.c_int, fp, fp, ip]
@@ -99,6 +102,9 @@ class PointToPlaneICP:
         if getattr(self, "_h", None):
             lib().orc_icp_destroy(self._h)
             self._h = None
+
+    def set_query_stride(self, stride):
+        lib().orc_icp_set_query_stride(self._h, int(stride))
 
     def AddPointCloud(self, xyz, normals, global_T_cloud, fixed=False):
         xyz, normals = _c32(xyz), _c32(normals)
@@ -167,6 +173,14 @@ def find_correspondences(src_xyz, tgt_xyz, max_dist, use_kdtree=True):
     q = np.zeros(n, np.int32); m = np.zeros(n, np.int32); d2 = np.zeros(n, np.float32)
     c = lib().orc_find_correspondences(_f(src_xyz), n, _f(tgt_xyz), tgt_xyz.shape[0], max_dist, int(use_kdtree), _i(q), _i(m), _f(d2))
     return q[:c].copy(), m[:c].copy(), d2[:c].copy()
+
+
+def time_search(src_xyz, tgt_xyz, max_dist):
+    """(t_build, t_query, matched): single-thread kd-tree build on tgt + nearest-within-radius for every src point."""
+    src_xyz, tgt_xyz = _c32(src_xyz), _c32(tgt_xyz)
+    tb, tq, m = C.c_double(), C.c_double(), C.c_uint64()
+    lib().orc_time_search(_f(src_xyz), src_xyz.shape[0], _f(tgt_xyz), tgt_xyz.shape[0], max_dist, C.byref(tb), C.byref(tq), C.byref(m))
+    return tb.value, tq.value, m.value
 
 
 def se3_exp_left_mul(x, q, t):

@@ -50,14 +50,15 @@ struct Corr { int q, m; float d2; };
 
 // FindCorrespondencesFast (icp_point_to_plane.cc:42-105): tree on target, nearest within radius per source point,
 // output in ascending source index.
+// query_stride > 1 is a SAMPLING knob for the bounded CPU-baseline timing only (bench.py): every stride-th source point.
 static void find_correspondences(const float* src, size_t ns, const float* tgt, size_t nt, float max_dist,
-                                 bool use_kdtree, std::vector<Corr>* out) {
+                                 bool use_kdtree, std::vector<Corr>* out, size_t query_stride = 1) {
   out->clear();
   const float r2 = (float)((double)max_dist * (double)max_dist);
   if (use_kdtree) {
     KdTree tree;
     tree.build(tgt, nt, 3, 15);
-    for (size_t i = 0; i < ns; ++i) {
+    for (size_t i = 0; i < ns; i += query_stride) {
       float d2;
       const int m = tree.nearest_within(src + 3 * i, r2, &d2);
       if (m >= 0) out->push_back(Corr{(int)i, m, d2});
@@ -83,6 +84,7 @@ struct InnerStats {
   double first_cost = 0, last_cost = 0, final_lambda = 0;
   std::vector<int> tries_per_iteration;  // tries used in each inner iteration (10 & not applied => abort)
   std::vector<double> H0, b0;            // normal equations of the first inner iteration (full matrix as written)
+  double t_acc = 0, t_cost = 0;          // wall seconds in accumulate passes / cost passes
 };
 
 static inline void rigid(const float R[9], const V3f& t, const float* p, V3f* out) {
@@ -164,6 +166,7 @@ static void inner_compute(std::vector<ImplCloud>* clouds_io, const std::vector<C
   for (int iteration = 0; iteration < max_iterations; ++iteration) {
     std::vector<double> H((size_t)nv * nv, 0.0), b(nv, 0.0);
     double cost = 0.0;
+    const double ta0 = omp_get_wtime();
     for (const CorrSet& cs : sets) {
       const int sv = 6 * (cs.src - 1), tv = 6 * (cs.tgt - 1);
       const ImplCloud& S = clouds[cs.src]; const ImplCloud& T = clouds[cs.tgt];
@@ -180,6 +183,7 @@ static void inner_compute(std::vector<ImplCloud>* clouds_io, const std::vector<C
         accumulate((double)r2, sv, j2s, tv, j2t, &H, &b, nv);
       }
     }
+    st->t_acc += omp_get_wtime() - ta0;
     st->inner_iterations++;
     if (iteration == 0) { st->first_cost = cost; st->H0 = H; st->b0 = b; }
     st->last_cost = cost;
@@ -198,7 +202,9 @@ static void inner_compute(std::vector<ImplCloud>* clouds_io, const std::vector<C
         for (int k = 0; k < 6; ++k) neg[k] = -x[6 * (ci - 1) + k];
         upd[ci].T = se3_mul(se3d_exp_cast_float(neg), clouds[ci].T);
       }
+      const double tc0 = omp_get_wtime();
       const double new_cost = cost_pass(upd, sets);
+      st->t_cost += omp_get_wtime() - tc0;
       st->lm_tries_total++;
       if (new_cost < cost) {
         clouds = upd;
@@ -245,6 +251,7 @@ struct orc_icp {
   std::vector<float> fixed_xyz, fixed_nrm;
   bool use_kdtree = true;
   int inner_max_iterations = 150;
+  size_t query_stride = 1;
   // last AlignMeshes
   std::vector<CorrSet> last_sets;
   InnerStats last_stats;
@@ -281,15 +288,15 @@ static bool align_meshes(orc_icp* h, float max_dist, float thr) {
     MovCloud& A = h->clouds[i]; MovCloud& B = h->clouds[k];
     if (i != k && boxes_intersect(A.bmin, A.bmax, B.bmin, B.bmax)) {
       CorrSet cs; cs.src = A.cloud_index; cs.tgt = B.cloud_index;
-      find_correspondences(A.gxyz.data(), A.gxyz.size() / 3, B.gxyz.data(), B.gxyz.size() / 3, max_dist, h->use_kdtree, &cs.corr);
+      find_correspondences(A.gxyz.data(), A.gxyz.size() / 3, B.gxyz.data(), B.gxyz.size() / 3, max_dist, h->use_kdtree, &cs.corr, h->query_stride);
       if (!cs.corr.empty()) { slots[2 * (size_t)ik] = std::move(cs); used[2 * (size_t)ik] = 1; }
     }
     if (i == k && h->has_fixed && boxes_intersect(fmin, fmax, A.bmin, A.bmax)) {
       CorrSet cs; cs.src = A.cloud_index; cs.tgt = fixed_vertex;
-      find_correspondences(A.gxyz.data(), A.gxyz.size() / 3, h->fixed_xyz.data(), h->fixed_xyz.size() / 3, max_dist, h->use_kdtree, &cs.corr);
+      find_correspondences(A.gxyz.data(), A.gxyz.size() / 3, h->fixed_xyz.data(), h->fixed_xyz.size() / 3, max_dist, h->use_kdtree, &cs.corr, h->query_stride);
       if (!cs.corr.empty()) { slots[2 * (size_t)ik] = std::move(cs); used[2 * (size_t)ik] = 1; }
       CorrSet cs2; cs2.src = fixed_vertex; cs2.tgt = A.cloud_index;
-      find_correspondences(h->fixed_xyz.data(), h->fixed_xyz.size() / 3, A.gxyz.data(), A.gxyz.size() / 3, max_dist, h->use_kdtree, &cs2.corr);
+      find_correspondences(h->fixed_xyz.data(), h->fixed_xyz.size() / 3, A.gxyz.data(), A.gxyz.size() / 3, max_dist, h->use_kdtree, &cs2.corr, h->query_stride);
       if (!cs2.corr.empty()) { slots[2 * (size_t)ik + 1] = std::move(cs2); used[2 * (size_t)ik + 1] = 1; }
     }
   }
@@ -324,6 +331,7 @@ void orc_icp_set_options(orc_icp* h, int use_kdtree, int inner_max_iterations) {
   h->use_kdtree = use_kdtree != 0;
   if (inner_max_iterations > 0) h->inner_max_iterations = inner_max_iterations;
 }
+void orc_icp_set_query_stride(orc_icp* h, size_t stride) { h->query_stride = stride ? stride : 1; }
 
 int orc_icp_add_cloud(orc_icp* h, const float* xyz, const float* nrm, size_t n, const float T_colmajor[16], int fixed) {
   Affine3f T; std::memcpy(T.m, T_colmajor, sizeof(T.m));
@@ -373,6 +381,7 @@ void orc_icp_last_stats(orc_icp* h, orc_icp_stats* s) {
   s->num_correspondences = (uint64_t)tot;
   s->num_variables = 6 * ((int)h->clouds.size() + (h->has_fixed ? 1 : 0) - 1);
   s->t_transform = h->t_transform; s->t_search = h->t_search; s->t_inner = h->t_inner;
+  s->t_acc = h->last_stats.t_acc; s->t_cost = h->last_stats.t_cost;
 }
 int orc_icp_last_tries(orc_icp* h, int* tries, int cap) {
   const int n = (int)h->last_stats.tries_per_iteration.size();
@@ -412,6 +421,19 @@ uint64_t orc_find_correspondences(const float* src, size_t ns, const float* tgt,
   find_correspondences(src, ns, tgt, nt, max_dist, use_kdtree != 0, &v);
   for (size_t i = 0; i < v.size(); ++i) { q[i] = v[i].q; m[i] = v[i].m; d2[i] = v[i].d2; }
   return v.size();
+}
+
+// Timing probe for the CPU baseline: kd-tree build on the target + nearest-within-radius for the given queries, one thread.
+void orc_time_search(const float* src, size_t ns, const float* tgt, size_t nt, float max_dist, double* t_build, double* t_query,
+                     uint64_t* matched) {
+  const float r2 = (float)((double)max_dist * (double)max_dist);
+  double t0 = omp_get_wtime();
+  KdTree tree; tree.build(tgt, nt, 3, 15);
+  double t1 = omp_get_wtime();
+  uint64_t m = 0;
+  for (size_t i = 0; i < ns; ++i) { float d2; if (tree.nearest_within(src + 3 * i, r2, &d2) >= 0) ++m; }
+  double t2 = omp_get_wtime();
+  *t_build = t1 - t0; *t_query = t2 - t1; *matched = m;
 }
 
 void orc_se3_exp_left_mul(const double x[6], const float q_in[4], const float t_in[3], float q_out[4], float t_out[3]) {

@@ -1,0 +1,100 @@
+"""N>1 host-side logic on CPU (gloo, world_size 2): the pair-direction sharding of the C ABI planner covers every direction
+exactly once, and summing the per-rank partial normal equations with an allreduce reproduces the single-rank system.
+The per-rank partials are computed with the oracle's pieces (test infrastructure); the planner is the product's."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _partial_system(pairs, clouds_g, nv, owner_of, rank):
+    """Normal equations from the pair-directions owned by `rank` (same algebra as k_finalize / impl.h:82-113 + :226)."""
+    H = np.zeros((nv, nv)); b = np.zeros(nv); cost = 0.0
+    for (s, t, q, m, _), owner in zip(pairs, owner_of):
+        if owner != rank:
+            continue
+        ps, ns = clouds_g[s]; pt, nt = clouds_g[t]
+        ps, ns, pt, nt = (a.astype(np.float64) for a in (ps[q], ns[q], pt[m], nt[m]))
+        r1 = (ns * (pt - ps)).sum(1); r2 = (nt * (ps - pt)).sum(1)
+        j1 = np.concatenate([ns, np.cross(pt, ns)], 1)          # d r1 / d target
+        j2 = np.concatenate([nt, np.cross(ps, nt)], 1)          # d r2 / d source
+        S = j1.T @ j1 + j2.T @ j2
+        g = j1.T @ r1 - j2.T @ r2
+        sv, tv = 6 * (s - 1), 6 * (t - 1)
+        if sv >= 0:
+            H[sv:sv + 6, sv:sv + 6] += S; b[sv:sv + 6] -= g
+        if tv >= 0:
+            H[tv:tv + 6, tv:tv + 6] += S; b[tv:tv + 6] += g
+        if sv >= 0 and tv >= 0 and sv < tv:
+            H[sv:sv + 6, tv:tv + 6] -= S; H[tv:tv + 6, sv:sv + 6] -= S
+        cost += float((r1 * r1).sum() + (r2 * r2).sum())
+    return H, b, cost
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dataset_pipeline_b200 import synth
+    from dataset_pipeline_b200.icp import plan_directions
+    from oracle import oracle as orc
+    clouds, poses, _ = synth.room_scans(3, 160, 64)
+    o = orc.PointToPlaneICP(use_kdtree=True, inner_max_iterations=1)
+    for (xyz, nrm), T in zip(clouds, poses):
+        o.AddPointCloud(xyz, nrm, T)
+    o.Run(0.08, 0, 1, 1e-10, False)
+    pairs = o.pairs()
+    plan = plan_directions(3, False, world)
+    owner = {(s, t): w for s, t, w in plan}
+    owner_of = [owner[(s, t)] for s, t, *_ in pairs]
+    clouds_g = [orc.transform_cloud(xyz, nrm, T) for (xyz, nrm), T in zip(clouds, poses)]
+    nv = 12
+    H, b, cost = _partial_system(pairs, clouds_g, nv, owner_of, rank)
+    buf = torch.from_numpy(np.concatenate([H.ravel(order="F"), b, [cost, sum(1 for w in owner_of if w == rank), 0.0]]))
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)      # the ONE exchange of the data path: [H | b | cost | counters]
+    if rank == 0:
+        Ho, bo = o.normal_equations()
+        tot = buf.numpy()
+        ret["H_err"] = float(np.linalg.norm(tot[:nv * nv].reshape(nv, nv, order="F") - Ho) / np.linalg.norm(Ho))
+        ret["b_err"] = float(np.linalg.norm(tot[nv * nv:nv * nv + nv] - bo) / np.linalg.norm(bo))
+        ret["cost_err"] = abs(tot[nv * nv + nv] - o.stats()["first_cost"]) / o.stats()["first_cost"]
+        ret["pairs"] = int(round(tot[nv * nv + nv + 1]))
+        ret["expected_pairs"] = len(pairs)
+    dist.destroy_process_group()
+
+
+def test_direction_plan_partitions_all_directions():
+    from dataset_pipeline_b200.icp import plan_directions
+    for n, fixed in ((2, False), (8, False), (3, True), (1, True)):
+        full = plan_directions(n, fixed, 1)
+        assert len(full) == n * (n - 1) + (2 * n if fixed else 0)
+        assert len(set((s, t) for s, t, _ in full)) == len(full)
+        for world in (2, 4, 8):
+            plan = plan_directions(n, fixed, world)
+            assert [(s, t) for s, t, _ in plan] == [(s, t) for s, t, _ in full]      # same ik order on every rank
+            owners = [w for *_, w in plan]
+            assert all(0 <= w < world for w in owners)
+            counts = np.bincount(owners, minlength=world)
+            assert counts.max() - counts.min() <= 1                                  # balanced round-robin
+    # 8 scans: the reference's 56 ordered pair-directions
+    assert len(plan_directions(8, False, 8)) == 56
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_allreduce_reproduces_single_rank_system(oracle):
+    ctx = mp.get_context("spawn")
+    mgr = ctx.Manager(); ret = mgr.dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(240) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert ret["pairs"] == ret["expected_pairs"]
+    assert ret["H_err"] < 1e-5 and ret["b_err"] < 1e-5 and ret["cost_err"] < 1e-9
