@@ -126,6 +126,30 @@ __host__ __device__ __forceinline__ unsigned long long cell_key(const GridParams
          (unsigned long long)cx;
 }
 
+// Sort key = (cell key << kFineBits) | 15-bit Morton code of the position inside the cell: points of one cell stay contiguous
+// (the hash table is keyed by key >> kFineBits) and are ordered along a space-filling curve, so the per-32 / per-1024 point
+// chunk boxes of dense cells are compact and prune well.
+static constexpr int kFineBits = 15;
+__host__ __device__ __forceinline__ unsigned int spread5(unsigned int v) {   // 5 bits -> every third bit
+  v &= 31u;
+  return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8);
+}
+__host__ __device__ __forceinline__ unsigned int fine_code(double rx, double ry, double rz) {   // r* in [0,1)
+  const int x = min(31, max(0, (int)(rx * 32.0))), y = min(31, max(0, (int)(ry * 32.0))), z = min(31, max(0, (int)(rz * 32.0)));
+  return spread5((unsigned)x) | (spread5((unsigned)y) << 1) | (spread5((unsigned)z) << 2);
+}
+
+struct Aabb { float lo[3], hi[3]; };
+static constexpr int kChunk1 = 32, kChunk2 = 1024;     // points per level-1 / level-2 chunk box
+// Lower bound of the fp32 squared distance from q to any point in the box, evaluated with the SAME operations as the point
+// distance (rounding is monotone), so pruning with `bound > best` can never drop a candidate.
+__device__ __forceinline__ float dist2_box(float qx, float qy, float qz, const Aabb& b) {
+  const float dx = fmaxf(fmaxf(fsub(b.lo[0], qx), fsub(qx, b.hi[0])), 0.f);
+  const float dy = fmaxf(fmaxf(fsub(b.lo[1], qy), fsub(qy, b.hi[1])), 0.f);
+  const float dz = fmaxf(fmaxf(fsub(b.lo[2], qz), fsub(qz, b.hi[2])), 0.f);
+  return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+}
+
 struct HashEntry { unsigned long long key; unsigned int begin, end; };   // 16 B: one LDG.128 per probe
 static constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 __host__ __device__ __forceinline__ unsigned int hash_slot(unsigned long long key, int log2size) {

@@ -26,7 +26,7 @@ struct Cloud {
   DevBuf local_xyz, local_nrm;          // packed float3 (cloud frame; global frame for the fixed cloud)
   float T[16];                          // global_T_cloud, column-major
   float bmin[3], bmax[3];               // AABB of the global-frame cloud (this outer iteration)
-  DevBuf keys_in, keys_out, idx_in, perm, s_xyz, s_nrm, table;
+  DevBuf keys_in, keys_out, idx_in, perm, s_xyz, s_nrm, table, box1, box2;
   int log2size = 0;
   unsigned int ncells = 0;
 };
@@ -121,7 +121,11 @@ static int index_cloud_phase1(b2_icp* h, Cloud* c, const GridParams& g, int key_
   k_apply<<<div_up(n, 256), 256, 0, h->stream>>>(c->local_xyz.as<float>(), c->local_nrm.as<float>(), n, T, c->perm.as<unsigned int>(),
                                                  c->s_xyz.as<float4>(), c->s_nrm.as<float4>());
   k_count_cells<<<div_up(n, 256), 256, 0, h->stream>>>(c->keys_out.as<unsigned long long>(), n, h->cell_counts.as<unsigned int>() + slot);
-  h->launches += 2;
+  const unsigned int nb1 = div_up(n, kChunk1), nb2 = div_up(nb1, 32);
+  B2_TRY(c->box1.ensure(sizeof(Aabb) * nb1)); B2_TRY(c->box2.ensure(sizeof(Aabb) * nb2));
+  k_chunk_boxes1<<<div_up((size_t)nb1 * 32, 256), 256, 0, h->stream>>>(c->s_xyz.as<float4>(), n, c->box1.as<Aabb>(), nb1);
+  k_chunk_boxes2<<<div_up((size_t)nb2 * 32, 256), 256, 0, h->stream>>>(c->box1.as<Aabb>(), nb1, c->box2.as<Aabb>(), nb2);
+  h->launches += 4;
   return B2_OK;
 }
 static int index_cloud_phase2(b2_icp* h, Cloud* c) {
@@ -172,10 +176,15 @@ static int compute_grid(b2_icp* h, float max_dist, GridParams* g, int* key_bits)
   g->nx = cell_of(mx[0], g->ox, g->inv) + 1;
   g->ny = cell_of(mx[1], g->oy, g->inv) + 1;
   g->nz = cell_of(mx[2], g->oz, g->inv) + 1;
+  // keep the cell key below 2^47 so that (key << kFineBits) fits 63 bits: enlarge the cells of enormous sparse scenes
+  while ((double)g->nx * (double)g->ny * (double)g->nz >= 140737488355328.0) {
+    cell *= 2.0; g->inv = 1.0 / cell;
+    g->nx = cell_of(mx[0], g->ox, g->inv) + 1; g->ny = cell_of(mx[1], g->oy, g->inv) + 1; g->nz = cell_of(mx[2], g->oz, g->inv) + 1;
+  }
   const unsigned long long maxkey = cell_key(*g, g->nx - 1, g->ny - 1, g->nz - 1);
   int bits = 1;
   while (bits < 64 && (maxkey >> bits) != 0ull) ++bits;
-  *key_bits = bits;
+  *key_bits = bits + kFineBits;
   return B2_OK;
 }
 
@@ -303,7 +312,8 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
     tails[2 * k] = tails[2 * k + 1] = 0;
     if (ns == 0 || T->n == 0) continue;
     B2_TRY(d->match.ensure(ns * 4)); B2_TRY(d->d2.ensure(ns * 4)); B2_TRY(d->flags.ensure(ns * 4)); B2_TRY(d->offs.ensure(ns * 4));
-    k_nn_radius1<<<div_up(ns, 256), 256, 0, h->stream>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->table.as<HashEntry>(),
+    k_nn_radius1<<<div_up(ns, 128), 128, 0, h->stream>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(), T->box2.as<Aabb>(),
+                                                         T->table.as<HashEntry>(),
                                                          T->log2size, g, r2, d->match.as<int>(), d->d2.as<float>(), d->flags.as<unsigned int>());
     ++h->launches;
     size_t tmp = 0;
@@ -518,7 +528,7 @@ int b2_icp_destroy(b2_icp* h) {
   cudaStreamSynchronize(h->stream);
   auto free_cloud = [](Cloud* c) {
     if (!c) return;
-    for (DevBuf* b : {&c->local_xyz, &c->local_nrm, &c->keys_in, &c->keys_out, &c->idx_in, &c->perm, &c->s_xyz, &c->s_nrm, &c->table}) b->release();
+    for (DevBuf* b : {&c->local_xyz, &c->local_nrm, &c->keys_in, &c->keys_out, &c->idx_in, &c->perm, &c->s_xyz, &c->s_nrm, &c->table, &c->box1, &c->box2}) b->release();
   };
   for (auto& c : h->movable) free_cloud(c.get());
   free_cloud(h->fixed.get());

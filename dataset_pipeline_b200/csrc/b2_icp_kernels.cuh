@@ -50,7 +50,9 @@ __global__ void __launch_bounds__(256) k_keys(const float* __restrict__ xyz, siz
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float3 p = xform_point(T, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
-  keys[i] = cell_key(g, cell_of(p.x, g.ox, g.inv), cell_of(p.y, g.oy, g.inv), cell_of(p.z, g.oz, g.inv));
+  const double fx = ((double)p.x - g.ox) * g.inv, fy = ((double)p.y - g.oy) * g.inv, fz = ((double)p.z - g.oz) * g.inv;
+  const int cx = (int)floor(fx), cy = (int)floor(fy), cz = (int)floor(fz);
+  keys[i] = (cell_key(g, cx, cy, cz) << kFineBits) | fine_code(fx - cx, fy - cy, fz - cz);
   idx[i] = (unsigned int)i;
 }
 
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(256) k_transform(const float* __restrict__ xyz
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_count_cells(const unsigned long long* __restrict__ keys, size_t n, unsigned int* __restrict__ count) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool head = j < n && (j == 0 || keys[j] != keys[j - 1]);
+  const bool head = j < n && (j == 0 || (keys[j] >> kFineBits) != (keys[j - 1] >> kFineBits));
   const unsigned int m = __ballot_sync(0xffffffffu, head);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned int)__popc(m));
 }
@@ -94,8 +96,8 @@ __global__ void __launch_bounds__(256) k_hash_insert(const unsigned long long* _
                                                      int log2size) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const unsigned long long key = keys[j];
-  if (j != 0 && keys[j - 1] == key) return;
+  const unsigned long long key = keys[j] >> kFineBits;
+  if (j != 0 && (keys[j - 1] >> kFineBits) == key) return;
   const unsigned int mask = (1u << log2size) - 1u;
   unsigned int s = hash_slot(key, log2size);
   while (true) {
@@ -122,8 +124,8 @@ __global__ void __launch_bounds__(256) k_hash_ends(const unsigned long long* __r
                                                    int log2size) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const unsigned long long key = keys[j];
-  if (j + 1 != n && keys[j + 1] == key) return;
+  const unsigned long long key = keys[j] >> kFineBits;
+  if (j + 1 != n && (keys[j + 1] >> kFineBits) == key) return;
   const unsigned int mask = (1u << log2size) - 1u;
   unsigned int s = hash_slot(key, log2size);
   while (table[s].key != key) s = (s + 1) & mask;
@@ -139,8 +141,38 @@ __global__ void __launch_bounds__(256) k_hash_ends(const unsigned long long* __r
 // first and the other seven are skipped when their nearest face is already farther than the best match.
 // Neighbouring threads share cells, so probes and candidate rows are served from L1/L2. Output at the sorted source position.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void scan_cell(const float4* __restrict__ tgt, unsigned int b, unsigned int e, const float4& q, float& best,
-                                          int& best_pos, unsigned int& best_idx) {
+// Chunk boxes over the cell-sorted points: level 1 = 32 consecutive points (one warp each), level 2 = 32 level-1 boxes.
+__global__ void __launch_bounds__(256) k_chunk_boxes1(const float4* __restrict__ s_xyz, size_t n, Aabb* __restrict__ box1, unsigned int nbox1) {
+  const unsigned int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= nbox1) return;
+  const size_t p = (size_t)c * kChunk1 + lane;
+  float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+  if (p < n) { const float4 v = s_xyz[p]; lx = hx = v.x; ly = hy = v.y; lz = hz = v.z; }
+  for (int o = 16; o > 0; o >>= 1) {
+    lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o));
+    lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+    hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+  }
+  if (lane == 0) { Aabb b; b.lo[0] = lx; b.lo[1] = ly; b.lo[2] = lz; b.hi[0] = hx; b.hi[1] = hy; b.hi[2] = hz; box1[c] = b; }
+}
+__global__ void __launch_bounds__(256) k_chunk_boxes2(const Aabb* __restrict__ box1, unsigned int nbox1, Aabb* __restrict__ box2, unsigned int nbox2) {
+  const unsigned int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= nbox2) return;
+  const unsigned int i = c * 32 + lane;
+  float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+  if (i < nbox1) { const Aabb v = box1[i]; lx = v.lo[0]; ly = v.lo[1]; lz = v.lo[2]; hx = v.hi[0]; hy = v.hi[1]; hz = v.hi[2]; }
+  for (int o = 16; o > 0; o >>= 1) {
+    lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o));
+    lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+    hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+  }
+  if (lane == 0) { Aabb b; b.lo[0] = lx; b.lo[1] = ly; b.lo[2] = lz; b.hi[0] = hx; b.hi[1] = hy; b.hi[2] = hz; box2[c] = b; }
+}
+
+__device__ __forceinline__ void scan_range(const float4* __restrict__ tgt, unsigned int b, unsigned int e, const float4& q, float& best,
+                                           int& best_pos, unsigned int& best_idx) {
   unsigned int p = b;
   for (; p + 1 < e; p += 2) {   // two candidates in flight
     const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + p + 1);
@@ -161,7 +193,24 @@ __device__ __forceinline__ void scan_cell(const float4* __restrict__ tgt, unsign
   }
 }
 
-__global__ void __launch_bounds__(256) k_nn_radius1(const float4* __restrict__ src, size_t ns, const float4* __restrict__ tgt,
+// One cell's candidates [b,e). Small cells are scanned directly; dense cells (scanner-zenith clusters reach 10^4..10^5 points in
+// one cell) go through the chunk boxes so the work per query stays bounded and the warps stay balanced.
+__device__ __forceinline__ void scan_cell(const float4* __restrict__ tgt, const Aabb* __restrict__ box1, const Aabb* __restrict__ box2,
+                                          unsigned int b, unsigned int e, const float4& q, float& best, int& best_pos, unsigned int& best_idx) {
+  if (e - b <= 48u) { scan_range(tgt, b, e, q, best, best_pos, best_idx); return; }
+  const unsigned int last = e - 1;
+  for (unsigned int c2 = b / kChunk2; c2 <= last / kChunk2; ++c2) {
+    if (e - b > 2u * kChunk2 && dist2_box(q.x, q.y, q.z, box2[c2]) > best) continue;
+    const unsigned int c1b = max(b / kChunk1, c2 * 32u), c1e = min(last / kChunk1, c2 * 32u + 31u);
+    for (unsigned int c1 = c1b; c1 <= c1e; ++c1) {
+      if (dist2_box(q.x, q.y, q.z, box1[c1]) > best) continue;
+      scan_range(tgt, max(b, c1 * kChunk1), min(e, (c1 + 1u) * kChunk1), q, best, best_pos, best_idx);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_nn_radius1(const float4* __restrict__ src, size_t ns, const float4* __restrict__ tgt,
+                                                    const Aabb* __restrict__ box1, const Aabb* __restrict__ box2,
                                                     const HashEntry* __restrict__ table, int log2size, GridParams g, float r2,
                                                     int* __restrict__ match_pos, float* __restrict__ match_d2,
                                                     unsigned int* __restrict__ flags) {
@@ -201,13 +250,13 @@ __global__ void __launch_bounds__(256) k_nn_radius1(const float4* __restrict__ s
   float best = r2;
   int best_pos = -1;
   unsigned int best_idx = 0xFFFFFFFFu;
-  scan_cell(tgt, cb[0], ce[0], q, best, best_pos, best_idx);
+  scan_cell(tgt, box1, box2, cb[0], ce[0], q, best, best_pos, best_idx);
 #pragma unroll
   for (int c = 1; c < 8; ++c) {
     if (cb[c] == ce[c]) continue;
     const float lb = ((c & 1) ? ex2 : 0.f) + ((c & 2) ? ey2 : 0.f) + ((c & 4) ? ez2 : 0.f);
     if (lb > best) continue;
-    scan_cell(tgt, cb[c], ce[c], q, best, best_pos, best_idx);
+    scan_cell(tgt, box1, box2, cb[c], ce[c], q, best, best_pos, best_idx);
   }
   match_pos[j] = best_pos;
   match_d2[j] = best;

@@ -24,7 +24,6 @@ namespace b2 {
 static constexpr int kLeaf = 8;
 static constexpr int kKnnThreads = 128;
 
-struct Aabb { float lo[3], hi[3]; };
 
 __global__ void __launch_bounds__(256) kn_bbox(const float* __restrict__ xyz, size_t n, float* __restrict__ partial) {
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -107,12 +106,7 @@ __device__ __forceinline__ float dist2_pt(const float4& q, const float4& t) {
   const float dx = fsub(q.x, t.x), dy = fsub(q.y, t.y), dz = fsub(q.z, t.z);
   return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
 }
-__device__ __forceinline__ float dist2_box(const float4& q, const Aabb& b) {
-  const float dx = fmaxf(fmaxf(fsub(b.lo[0], q.x), fsub(q.x, b.hi[0])), 0.f);
-  const float dy = fmaxf(fmaxf(fsub(b.lo[1], q.y), fsub(q.y, b.hi[1])), 0.f);
-  const float dz = fmaxf(fmaxf(fsub(b.lo[2], q.z), fsub(q.z, b.hi[2])), 0.f);
-  return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
-}
+__device__ __forceinline__ float dist2_box(const float4& q, const Aabb& b) { return dist2_box(q.x, q.y, q.z, b); }
 
 // k-best list of one thread in shared memory, element e of thread t at [e * kKnnThreads + t] (conflict-free).
 struct KBest {

@@ -205,3 +205,210 @@ def normals_knn(xyz, k, viewpoint=(0.0, 0.0, 0.0), return_indices=False):
     idx = np.zeros((n, k), np.int32) if return_indices else None
     lib().orc_normals_knn(_f(xyz), n, k, _f(vp), _f(out), _i(idx) if return_indices else None)
     return (out, idx) if return_indices else out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Path B (orc_reg.cc)
+# ---------------------------------------------------------------------------------------------------------------------
+class RegParams(C.Structure):
+    _fields_ = [("point_neighbor_count", C.c_int32), ("fixed_residuals_weight", C.c_float), ("variable_residuals_weight", C.c_float),
+                ("robust_weighting_type", C.c_int32), ("robust_weighting_parameter", C.c_float),
+                ("maximum_valid_intensity", C.c_float), ("occlusion_depth_threshold", C.c_float),
+                ("min_occlusion_check_image_scale", C.c_int32), ("max_initial_image_area_in_pixels", C.c_int32),
+                ("splat_radius", C.c_float), ("image_scale_count_override", C.c_int32)]
+
+
+_reg_bound = False
+
+
+def _bind_reg():
+    global _reg_bound
+    L = lib()
+    if _reg_bound:
+        return L
+    fp, ip, dp, vp = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_void_p
+    u8, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
+    L.orc_reg_default_params.argtypes = [C.POINTER(RegParams)]
+    L.orc_reg_create.argtypes = [C.POINTER(RegParams)]; L.orc_reg_create.restype = vp
+    L.orc_reg_destroy.argtypes = [vp]
+    L.orc_reg_add_intrinsics.argtypes = [vp, C.c_int, C.c_int, fp]
+    L.orc_reg_add_image.argtypes = [vp, C.c_int, u8, u8, fp]
+    L.orc_reg_initialize.argtypes = [vp]
+    L.orc_reg_add_point_scale.argtypes = [vp, fp, C.c_size_t, C.c_float, u64p, fp]
+    L.orc_reg_set_splat_points.argtypes = [vp, fp, C.c_size_t]
+    L.orc_reg_set_depth_map.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp]
+    L.orc_reg_set_image_scale.argtypes = [vp, C.c_int]
+    L.orc_reg_image_scale_count.argtypes = [vp]
+    L.orc_reg_num_variables.argtypes = [vp]
+    L.orc_reg_render_depth.argtypes = [vp, C.c_int, ip, ip, fp]
+    L.orc_reg_create_observations.argtypes = [vp, C.c_int]
+    L.orc_reg_num_observations.argtypes = [vp, C.c_int, C.c_int]; L.orc_reg_num_observations.restype = C.c_uint64
+    L.orc_reg_get_observations.argtypes = [vp, C.c_int, C.c_int, u64p, fp, fp, fp, u8]
+    L.orc_reg_color_update.argtypes = [vp]
+    L.orc_reg_get_descriptors.argtypes = [vp, C.c_int, fp, fp, ip]
+    L.orc_reg_cost.argtypes = [vp, dp]; L.orc_reg_cost.restype = C.c_double
+    L.orc_reg_accumulate.argtypes = [vp, dp, dp, dp]; L.orc_reg_accumulate.restype = C.c_double
+    L.orc_reg_get_state.argtypes = [vp, fp, fp]
+    L.orc_reg_set_state.argtypes = [vp, fp, fp]
+    L.orc_reg_cost_for_delta.argtypes = [vp, dp]; L.orc_reg_cost_for_delta.restype = C.c_double
+    L.orc_reg_apply.argtypes = [vp, fp, fp, ip]
+    L.orc_reg_run_on_current_scale.argtypes = [vp, C.c_int, C.c_float, C.c_int, dp, ip]
+    L.orc_reg_point_jacobians.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, fp, fp, fp]
+    L.orc_interp_bilinear.argtypes = [u8, C.c_int, C.c_int, C.c_float, C.c_float, fp, fp, fp]
+    L.orc_interp_trilinear.argtypes = [u8, C.c_int, C.c_int, u8, C.c_float, C.c_float, C.c_float, fp, fp, fp, fp]
+    L.orc_robust.argtypes = [C.c_int, C.c_float, C.c_float, C.c_int]; L.orc_robust.restype = C.c_float
+    L.orc_image_pyramid_level.argtypes = [u8, C.c_int, C.c_int, u8]
+    _reg_bound = True
+    return L
+
+
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def reg_default_params(**kw):
+    p = RegParams()
+    _bind_reg().orc_reg_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class Registration:
+    """Oracle of the Path B problem + optimizer pieces (opt::Problem / VisibilityEstimator / IntrinsicsAndPoseOptimizer /
+    CostCalculator / ColorOptimizer / Optimizer), pinhole cameras."""
+
+    def __init__(self, params=None):
+        L = _bind_reg()
+        self.params = params or reg_default_params()
+        self._h = C.c_void_p(L.orc_reg_create(C.byref(self.params)))
+        self.K = self.params.point_neighbor_count
+        self.n_intr = 0; self.n_img = 0; self.scale_sizes = []
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_reg_destroy(self._h); self._h = None
+
+    def add_intrinsics(self, w, h, params):
+        p = _c32(params); self.n_intr += 1
+        return lib().orc_reg_add_intrinsics(self._h, w, h, _f(p))
+
+    def add_image(self, intr_id, gray, mask, image_T_global):
+        g = np.ascontiguousarray(gray, np.uint8); T = _c32(image_T_global)
+        m = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
+        self.n_img += 1
+        return lib().orc_reg_add_image(self._h, intr_id, _u8(g), _u8(m) if m is not None else None, _f(T))
+
+    def initialize(self):
+        r = lib().orc_reg_initialize(self._h)
+        if r < 0:
+            raise ValueError("odd pyramid parent size")
+        return r
+
+    def add_point_scale(self, xyz, radius, neighbors, colors):
+        xyz = _c32(xyz); nb = np.ascontiguousarray(neighbors, np.uint64); col = _c32(colors)
+        self.scale_sizes.append(xyz.shape[0])
+        return lib().orc_reg_add_point_scale(self._h, _f(xyz), xyz.shape[0], radius, nb.ctypes.data_as(C.POINTER(C.c_uint64)), _f(col))
+
+    def set_splat_points(self, xyz):
+        xyz = _c32(xyz); lib().orc_reg_set_splat_points(self._h, _f(xyz), xyz.shape[0])
+
+    def set_depth_map(self, image, depth):
+        d = _c32(depth); lib().orc_reg_set_depth_map(self._h, image, d.shape[1], d.shape[0], _f(d))
+
+    def set_image_scale(self, s):
+        lib().orc_reg_set_image_scale(self._h, s)
+
+    def image_scale_count(self):
+        return lib().orc_reg_image_scale_count(self._h)
+
+    def num_variables(self):
+        return lib().orc_reg_num_variables(self._h)
+
+    def render_depth(self, image):
+        w, h = C.c_int(), C.c_int()
+        lib().orc_reg_render_depth(self._h, image, C.byref(w), C.byref(h), None)
+        out = np.zeros((h.value, w.value), np.float32)
+        s = lib().orc_reg_render_depth(self._h, image, C.byref(w), C.byref(h), _f(out))
+        return out, s
+
+    def create_observations(self, border=1):
+        lib().orc_reg_create_observations(self._h, border)
+
+    def observations(self, image, ps):
+        n = lib().orc_reg_num_observations(self._h, image, ps)
+        idx = np.zeros(n, np.uint64); x = np.zeros(n, np.float32); y = np.zeros(n, np.float32); s = np.zeros(n, np.float32); nb = np.zeros(n, np.uint8)
+        lib().orc_reg_get_observations(self._h, image, ps, idx.ctypes.data_as(C.POINTER(C.c_uint64)), _f(x), _f(y), _f(s), _u8(nb))
+        return idx, x, y, s, nb
+
+    def color_update(self):
+        lib().orc_reg_color_update(self._h)
+
+    def descriptors(self, ps):
+        n = self.scale_sizes[ps]
+        f = np.zeros(n * self.K, np.float32); v = np.zeros(n * self.K, np.float32); c = np.zeros(n, np.int32)
+        lib().orc_reg_get_descriptors(self._h, ps, _f(f), _f(v), _i(c))
+        return f, v, c
+
+    def cost(self):
+        s = np.zeros(6, np.float64)
+        return lib().orc_reg_cost(self._h, _d(s)), s
+
+    def accumulate(self):
+        nv = self.num_variables()
+        H = np.zeros((nv, nv), np.float64, order="F"); b = np.zeros(nv); s = np.zeros(6)
+        c = lib().orc_reg_accumulate(self._h, _d(H), _d(b), _d(s))
+        return np.asarray(H), b, s, c
+
+    def get_state(self):
+        ip = np.zeros((self.n_intr, 4), np.float32); po = np.zeros((self.n_img, 7), np.float32)
+        lib().orc_reg_get_state(self._h, _f(ip), _f(po))
+        return ip, po
+
+    def set_state(self, intr_params, poses):
+        ip = _c32(intr_params); po = _c32(poses)
+        lib().orc_reg_set_state(self._h, _f(ip), _f(po))
+
+    def cost_for_delta(self, delta):
+        d = np.ascontiguousarray(delta, np.float64)
+        return lib().orc_reg_cost_for_delta(self._h, _d(d))
+
+    def apply(self, lam):
+        l = C.c_float(lam); mc = C.c_float(0); ap = C.c_int(0)
+        tries = lib().orc_reg_apply(self._h, C.byref(l), C.byref(mc), C.byref(ap))
+        return bool(ap.value), l.value, mc.value, tries
+
+    def run_on_current_scale(self, max_it, max_change_thr, no_opt_thr):
+        oc = C.c_double(0); cv = C.c_int(0)
+        it = lib().orc_reg_run_on_current_scale(self._h, max_it, max_change_thr, no_opt_thr, C.byref(oc), C.byref(cv))
+        return it, oc.value, bool(cv.value)
+
+    def point_jacobians(self, image, ps, obs_index):
+        I = C.c_float(0); jk = np.zeros(4, np.float32); jp = np.zeros(6, np.float32)
+        lib().orc_reg_point_jacobians(self._h, image, ps, obs_index, C.byref(I), _f(jk), _f(jp))
+        return I.value, jk, jp
+
+
+def interp_bilinear(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    v, dx, dy = C.c_float(), C.c_float(), C.c_float()
+    ok = _bind_reg().orc_interp_bilinear(_u8(img), img.shape[1], img.shape[0], x, y, C.byref(v), C.byref(dx), C.byref(dy))
+    return ok, v.value, dx.value, dy.value
+
+
+def interp_trilinear(img0, img1, x, y, z):
+    img0 = np.ascontiguousarray(img0, np.uint8); img1 = np.ascontiguousarray(img1, np.uint8)
+    v, dx, dy, dz = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+    _bind_reg().orc_interp_trilinear(_u8(img0), img0.shape[1], img0.shape[0], _u8(img1), x, y, z, C.byref(v), C.byref(dx), C.byref(dy), C.byref(dz))
+    return v.value, dx.value, dy.value, dz.value
+
+
+def robust(type_, p, r, weight=False):
+    return _bind_reg().orc_robust(type_, p, r, int(weight))
+
+
+def image_pyramid_level(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros((img.shape[0] // 2, img.shape[1] // 2), np.uint8)
+    _bind_reg().orc_image_pyramid_level(_u8(img), img.shape[1], img.shape[0], _u8(out))
+    return out

@@ -53,6 +53,50 @@ int orc_ldlt_solve_upper(const double* A_colmajor, int n, const double* b, doubl
 int orc_normals_knn(const float* xyz, size_t n, int k, const float viewpoint[3], float* out_nxyz_curv /* n x 4 */,
                     int* out_knn_idx /* n x k or NULL */);
 
+/* ---- Path B: photometric image<->scan alignment (orc_reg.cc), pinhole cameras, no rigs, no depth residuals ---- */
+typedef struct orc_reg orc_reg;
+typedef struct orc_reg_params {   /* mirror of opt::Parameters (src/opt/parameters.h:40-67) restricted to what Path B reads */
+  int32_t point_neighbor_count;
+  float fixed_residuals_weight, variable_residuals_weight;
+  int32_t robust_weighting_type;        /* 0 none, 1 huber, 2 tukey */
+  float robust_weighting_parameter;
+  float maximum_valid_intensity, occlusion_depth_threshold;
+  int32_t min_occlusion_check_image_scale, max_initial_image_area_in_pixels;
+  float splat_radius;
+  int32_t image_scale_count_override;   /* >0: force Problem::image_scale_count_ (tests do this through friend helpers) */
+} orc_reg_params;
+void orc_reg_default_params(orc_reg_params*);
+orc_reg* orc_reg_create(const orc_reg_params*);
+void orc_reg_destroy(orc_reg*);
+int orc_reg_add_intrinsics(orc_reg*, int w, int h, const float fx_fy_cx_cy[4]);
+/* image_T_global as Sophus::SE3f::data(): qx qy qz qw tx ty tz */
+int orc_reg_add_image(orc_reg*, int intrinsics_id, const uint8_t* gray, const uint8_t* mask_or_null, const float image_T_global[7]);
+int orc_reg_initialize(orc_reg*);
+int orc_reg_add_point_scale(orc_reg*, const float* xyz, size_t n, float radius, const uint64_t* neighbor_indices, const float* colors);
+void orc_reg_set_splat_points(orc_reg*, const float* xyz, size_t n);
+int orc_reg_set_depth_map(orc_reg*, int image, int w, int h, const float* depth);
+void orc_reg_set_image_scale(orc_reg*, int image_scale);
+int orc_reg_image_scale_count(orc_reg*);
+int orc_reg_num_variables(orc_reg*);
+int orc_reg_render_depth(orc_reg*, int image, int* w, int* h, float* out_or_null);
+void orc_reg_create_observations(orc_reg*, int border);
+uint64_t orc_reg_num_observations(orc_reg*, int image, int point_scale);
+void orc_reg_get_observations(orc_reg*, int image, int point_scale, uint64_t* idx, float* x, float* y, float* s, uint8_t* nbrs_observed);
+void orc_reg_color_update(orc_reg*);
+void orc_reg_get_descriptors(orc_reg*, int point_scale, float* fixed, float* variable, int* counts);
+double orc_reg_cost(orc_reg*, double sums[6]);
+double orc_reg_accumulate(orc_reg*, double* H_colmajor, double* b, double sums[6]);
+void orc_reg_get_state(orc_reg*, float* intr_params, float* poses);
+void orc_reg_set_state(orc_reg*, const float* intr_params, const float* poses);
+double orc_reg_cost_for_delta(orc_reg*, const double* delta);
+int orc_reg_apply(orc_reg*, float* lambda, float* max_change, int* applied);
+int orc_reg_run_on_current_scale(orc_reg*, int max_it, float max_change_thr, int no_opt_thr, double* optimum_cost, int* converged);
+void orc_reg_point_jacobians(orc_reg*, int image, int point_scale, uint64_t obs_index, float* intensity, float jK[4], float jP[6]);
+int orc_interp_bilinear(const uint8_t* img, int w, int h, float x, float y, float* v, float* dx, float* dy);
+void orc_interp_trilinear(const uint8_t* img0, int w0, int h0, const uint8_t* img1, float x, float y, float z, float* v, float* dx, float* dy, float* dz);
+float orc_robust(int type, float p, float r, int weight);
+void orc_image_pyramid_level(const uint8_t* src, int w, int h, uint8_t* dst);
+
 #ifdef __cplusplus
 }
 #endif

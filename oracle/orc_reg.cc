@@ -1,0 +1,725 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. Not part of the product path (see orc_math.h header).
+//
+// CPU restatement of the reference's dense photometric image<->scan alignment (Path B), pinhole cameras, no rigs,
+// depth residuals off (the reference default, parameters.h:54):
+//   interpolation        /root/reference/src/opt/interpolate_bilinear.h:36-74, interpolate_trilinear.h:44-87
+//   robust weighting     /root/reference/src/opt/robust_weighting.h:61-106
+//   camera (pinhole)     /root/reference/src/camera/camera_base.cc:81-85, camera_base_impl.h:70-89,135-137,155-164,333-408,
+//                        camera_pinhole.h:40-86
+//   pyramids             /root/reference/src/opt/image.cc:106-154, intrinsics.cc:45-79, intrinsics.h:61-86, problem.cc:478-494
+//   splat depth map      /root/reference/src/opt/occlusion_geometry.cc:404-464 (and the all-inf map :271-281)
+//   visibility           /root/reference/src/opt/visibility_estimator.cc:61-91,140-168,199-256,258-295,366-532
+//   intensity+Jacobians  /root/reference/src/opt/intrinsics_and_pose_optimizer.cc:933-1147
+//   accumulate           /root/reference/src/opt/intrinsics_and_pose_optimizer.cc:624-930,1220-1296
+//   LM step              /root/reference/src/opt/intrinsics_and_pose_optimizer.cc:48-259,385-473,475-558
+//   cost                 /root/reference/src/opt/cost_calculator.cc:44-271, problem.cc:602-631
+//   colour update        /root/reference/src/opt/color_optimizer.cc:40-123
+//   outer loop           /root/reference/src/opt/optimizer.cc:49-190
+// Pinned by the reference's own tests ported in tests/test_oracle_reg.py: test_interpolation.cc:39-185 (exact values),
+// test_intrinsics_and_pose_optimizer.cc:101-336 (analytic Jacobians vs finite differences).
+// Unpinned / defined here: iteration order over images (the reference iterates unordered_maps: here ascending image id, which
+// also fixes the variable layout [intrinsics | image poses]); cv::resize INTER_AREA for even sizes = (a+b+c+d+2)>>2 (verified
+// against Python cv2 4.13 in SURVEY.md §7) — odd parent sizes are rejected.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <vector>
+
+#include "orc_api.h"
+#include "orc_math.h"
+
+namespace orc {
+
+struct Pinhole {   // one pyramid level of camera::PinholeCamera
+  int w, h;
+  float fx, fy, cx, cy, fx_inv, fy_inv, cx_inv, cy_inv;
+  void set(int w_, int h_, float fx_, float fy_, float cx_, float cy_) {
+    w = w_; h = h_; fx = fx_; fy = fy_; cx = cx_; cy = cy_;
+    fx_inv = (float)(1.0 / fx); fy_inv = (float)(1.0 / fy);                 // camera_base.cc:83
+    cx_inv = (float)(-1.0 * cx / fx); cy_inv = (float)(-1.0 * cy / fy);
+  }
+  Pinhole scaled_half() const {                                            // camera_base_impl.h:70-89, factor 0.5
+    const float f = 0.5f;
+    Pinhole s;
+    s.set((int)(f * w + 0.5f), (int)(f * h + 0.5f), fx * f, fy * f, f * (cx + 0.5f) - 0.5f, f * (cy + 0.5f) - 0.5f);
+    return s;
+  }
+  // NormalizedToImage (camera_base_impl.h:155-164): pinhole has no cutoff; inf r2 -> inf.
+  void project(float nx, float ny, float* ix, float* iy) const {
+    const float r2 = nx * nx + ny * ny;
+    if (std::isinf(r2)) { *ix = nx * std::numeric_limits<float>::infinity(); *iy = ny * std::numeric_limits<float>::infinity(); return; }
+    *ix = fx * nx + cx; *iy = fy * ny + cy;
+  }
+  // ImageDerivativeByWorld (camera_base_impl.h:333-360): f.asDiagonal() * [I/z | -n/z]
+  void d_by_world(const V3f& p, float d[6]) const {
+    const float nx = p.x / p.z, ny = p.y / p.z;
+    const float z_inv = 1.f / p.z;
+    d[0] = fx * (1.f * z_inv); d[1] = fx * (0.f * z_inv); d[2] = fx * (-1.f * nx * z_inv);
+    d[3] = fy * (0.f * z_inv); d[4] = fy * (1.f * z_inv); d[5] = fy * (-1.f * ny * z_inv);
+  }
+  // ImageDerivativeByIntrinsics (camera_base_impl.h:369-408), 2x4: [x 0 1 0; 0 y 0 1]
+  void d_by_intrinsics(const V3f& p, float d[8]) const {
+    d[0] = p.x / p.z; d[1] = 0.f; d[2] = 1.f; d[3] = 0.f;
+    d[4] = 0.f; d[5] = p.y / p.z; d[6] = 0.f; d[7] = 1.f;
+  }
+};
+
+struct Img8 { int w = 0, h = 0; std::vector<uint8_t> d; uint8_t at(int y, int x) const { return d[(size_t)y * w + x]; } };
+struct ImgF { int w = 0, h = 0; std::vector<float> d; float at(int y, int x) const { return d[(size_t)y * w + x]; } };
+
+// interpolate_bilinear.h:36-74
+static inline float bilinear(const Img8& im, float x, float y, int ix, int iy) {
+  const float fx = x - ix, fx_inv = 1.f - fx, fy = y - iy, fy_inv = 1.f - fy;
+  return fy_inv * (fx_inv * im.at(iy, ix) + fx * im.at(iy, ix + 1)) + fy * (fx_inv * im.at(iy + 1, ix) + fx * im.at(iy + 1, ix + 1));
+}
+static inline void bilinear_d(const Img8& im, float x, float y, int ix, int iy, float* v, float* dx, float* dy) {
+  const uint8_t tl = im.at(iy, ix), tr = im.at(iy, ix + 1), bl = im.at(iy + 1, ix), br = im.at(iy + 1, ix + 1);
+  const float fx = x - ix, fx_inv = 1.f - fx, fy = y - iy, fy_inv = 1.f - fy;
+  const float top = fx_inv * tl + fx * tr, bottom = fx_inv * bl + fx * br;
+  *v = fy_inv * top + fy * bottom;
+  *dx = fy * (br - bl) + fy_inv * (tr - tl);
+  *dy = bottom - top;
+}
+// interpolate_trilinear.h:44-87
+static inline void trilinear(const Img8& i0, const Img8& i1, float x0, float y0, float z, float* v) {
+  const float v0 = bilinear(i0, x0, y0, (int)x0, (int)y0);
+  const float x1 = 2 * (x0 + 0.5f) - 0.5f, y1 = 2 * (y0 + 0.5f) - 0.5f;
+  const float v1 = bilinear(i1, x1, y1, (int)x1, (int)y1);
+  *v = (1 - z) * v0 + z * v1;
+}
+static inline void trilinear_d(const Img8& i0, const Img8& i1, float x0, float y0, float z, float* v, float* dx, float* dy, float* dz) {
+  float v0, d0x, d0y, v1, d1x, d1y;
+  bilinear_d(i0, x0, y0, (int)x0, (int)y0, &v0, &d0x, &d0y);
+  const float x1 = 2 * (x0 + 0.5f) - 0.5f, y1 = 2 * (y0 + 0.5f) - 0.5f;
+  bilinear_d(i1, x1, y1, (int)x1, (int)y1, &v1, &d1x, &d1y);
+  *v = (1 - z) * v0 + z * v1;
+  *dx = (1 - z) * d0x + z * 2 * d1x;
+  *dy = (1 - z) * d0y + z * 2 * d1y;
+  *dz = v1 - v0;
+}
+
+// robust_weighting.h:61-106
+struct Robust {
+  int type = 1; float p = 0.f;   // 0 none, 1 huber, 2 tukey
+  float residual(float r) const {
+    if (type == 1) { const float a = std::fabs(r); return a < p ? 0.5f * r * r : p * (a - 0.5f * p); }
+    if (type == 2) {
+      const float a = std::fabs(r);
+      if (a < p) { const float q = r / p; const float t = 1.f - q * q; return (1 / 6.f) * p * p * (1 - t * t * t); }
+      return (1 / 6.f) * p * p;
+    }
+    return 0.5f * r * r;
+  }
+  float weight(float r) const {
+    if (type == 1) { const float a = std::fabs(r); return a < p ? 1.f : p / a; }
+    if (type == 2) { const float a = std::fabs(r); if (a < p) { const float q = r / p; const float t = 1.f - q * q; return t * t; } return 0.f; }
+    return 1.f;
+  }
+};
+
+struct Observation { uint64_t point_index; float x, y, scale; };   // point_observation.h:97-116
+static inline int smaller_scale(const Observation& o) { return (int)o.scale + 1; }
+static inline int larger_scale(const Observation& o) { return (int)o.scale; }
+
+struct Intrinsics {
+  std::vector<Pinhole> models;   // index 0 = original resolution
+  int min_image_scale = -1;
+  const Pinhole& model(int image_scale) const { return models[std::max(0, image_scale - min_image_scale)]; }
+  int best_available(int image_scale) const { return std::min<int>(min_image_scale + (int)models.size() - 1, std::max<int>(min_image_scale, image_scale)); }
+  void build_pyramid() { for (size_t i = 1; i < models.size(); ++i) models[i] = models[i - 1].scaled_half(); }
+};
+
+struct Image {
+  int intrinsics_id = 0;
+  SE3f image_T_global;
+  std::vector<Img8> image, mask;   // pyramids (mask levels may be empty)
+  ImgF given_depth; bool has_given_depth = false;
+};
+
+struct ScalePoints {
+  std::vector<float> xyz; float radius = 0;
+  std::vector<uint64_t> nbr;              // n * K
+  std::vector<float> fixed_desc, var_desc; std::vector<int> obs_count;
+  size_t n() const { return xyz.size() / 3; }
+};
+
+struct State { std::vector<Intrinsics> intr; std::vector<Image> images; };
+
+}  // namespace orc
+
+using namespace orc;
+
+struct orc_reg {
+  orc_reg_params prm;
+  Robust robust;
+  State st;
+  std::vector<ScalePoints> pts;
+  std::vector<float> splat_xyz; bool has_splats = false;
+  int image_scale_count = 0, current_image_scale = 0;
+  // observations: [image][point_scale]
+  std::vector<std::vector<std::vector<Observation>>> obs;
+  std::vector<std::vector<std::vector<uint8_t>>> nbr_obs;
+  double last_sums[6] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace orc {
+
+static int K(const orc_reg* h) { return h->prm.point_neighbor_count; }
+
+// ---- pyramids ----
+static bool build_image_pyramid(std::vector<Img8>& pyr) {   // image.cc:106-131, even parents only
+  for (size_t i = 1; i < pyr.size(); ++i) {
+    const Img8& s = pyr[i - 1];
+    Img8& d = pyr[i];
+    d.w = (int)(0.5 * s.w); d.h = (int)(0.5 * s.h);
+    if ((s.w & 1) || (s.h & 1)) return false;
+    d.d.resize((size_t)d.w * d.h);
+    for (int y = 0; y < d.h; ++y) for (int x = 0; x < d.w; ++x)
+      d.d[(size_t)y * d.w + x] = (uint8_t)((s.at(2 * y, 2 * x) + s.at(2 * y, 2 * x + 1) + s.at(2 * y + 1, 2 * x) + s.at(2 * y + 1, 2 * x + 1) + 2) >> 2);
+  }
+  return true;
+}
+static void build_mask_pyramid(std::vector<Img8>& pyr) {    // image.cc:133-154
+  for (size_t i = 1; i < pyr.size(); ++i) {
+    const Img8& s = pyr[i - 1];
+    Img8& d = pyr[i];
+    d.h = (int)(0.5 * s.h); d.w = (int)(0.5 * s.w);
+    d.d.resize((size_t)d.w * d.h);
+    for (int y = 0; y < d.h; ++y) for (int x = 0; x < d.w; ++x)
+      d.d[(size_t)y * d.w + x] = s.at(2 * y, 2 * x) | s.at(2 * y, 2 * x + 1) | s.at(2 * y + 1, 2 * x) | s.at(2 * y + 1, 2 * x + 1);
+  }
+}
+
+// ---- occlusion depth map (occlusion_geometry.cc:185-282: splats, given, or all-inf) ----
+static ImgF render_depth(const orc_reg* h, const Intrinsics& intr, const Image& im, int image_scale) {
+  const Pinhole& cam = intr.model(image_scale);
+  ImgF out; out.w = cam.w; out.h = cam.h; out.d.assign((size_t)cam.w * cam.h, std::numeric_limits<float>::infinity());
+  if (im.has_given_depth) return im.given_depth;
+  if (!h->has_splats) return out;
+  float R[9]; quat_to_matrix(im.image_T_global.q, R);
+  const M3f& M = *reinterpret_cast<const M3f*>(R);
+  const float max_splat_radius = 10;
+  for (size_t i = 0; i < h->splat_xyz.size() / 3; ++i) {
+    const V3f v = mul(M, V3f{h->splat_xyz[3 * i], h->splat_xyz[3 * i + 1], h->splat_xyz[3 * i + 2]});
+    const V3f pp{v.x + im.image_T_global.t.x, v.y + im.image_T_global.t.y, v.z + im.image_T_global.t.z};
+    if (!(pp.z > 0.f)) continue;
+    float px, py; cam.project(pp.x / pp.z, pp.y / pp.z, &px, &py);
+    float d[6]; cam.d_by_world(pp, d);
+    float rx = std::sqrt(sum3(d[0] * d[0], d[1] * d[1], d[2] * d[2])) * h->prm.splat_radius;
+    float ry = std::sqrt(sum3(d[3] * d[3], d[4] * d[4], d[5] * d[5])) * h->prm.splat_radius;
+    rx = std::min(rx, max_splat_radius); ry = std::min(ry, max_splat_radius);
+    const int ix = px + 0.5f, iy = py + 0.5f;
+    const int min_x = std::max(0, int(ix - rx + 0.5)), min_y = std::max(0, int(iy - ry + 0.5));
+    const int end_x = std::min(cam.w, int(ix + rx + 1.5)), end_y = std::min(cam.h, int(iy + ry + 1.5));
+    if (min_y < end_y && min_x < end_x)
+      for (int y = min_y; y < end_y; ++y) for (int x = min_x; x < end_x; ++x)
+        if (out.d[(size_t)y * out.w + x] > pp.z) out.d[(size_t)y * out.w + x] = pp.z;
+  }
+  return out;
+}
+
+// ---- CreateObservationIfScaleFits (visibility_estimator.cc:405-532) ----
+static void create_observation_if_scale_fits(const orc_reg* h, const Intrinsics& intr, const Image& im, const Pinhole& cam, int image_scale,
+                                             uint64_t point_index, const V3f& pp, float point_radius, float ixx, float ixy, int border,
+                                             bool check_masks, std::vector<Observation>* out) {
+  const V3f ppr{pp.x + point_radius, pp.y + 0, pp.z + 0};
+  float rx, ry; cam.project(ppr.x / ppr.z, ppr.y / ppr.z, &rx, &ry);
+  const float dx = rx - ixx, dy = ry - ixy;
+  const float radius_pixels = std::sqrt(dx * dx + dy * dy);
+  const float observation_scale = image_scale + log2((double)(2 * radius_pixels));   // ::log2(double); float-vs-double overload UNPINNED (differs by <= 1 ulp)
+  if (observation_scale >= std::max(intr.min_image_scale, h->current_image_scale) &&
+      static_cast<int>(observation_scale) < h->image_scale_count - 1) {
+    const int small = static_cast<int>(observation_scale) + 1;
+    const Pinhole& ic = intr.model(small);
+    const float nx = cam.fx_inv * ixx + cam.cx_inv, ny = cam.fy_inv * ixy + cam.cy_inv;
+    const float jx = ic.fx * nx + ic.cx, jy = ic.fy * ny + ic.cy;
+    const int ix = jx + 0.5f, iy = jy + 0.5f;
+    if (jx + 0.5f >= border && jy + 0.5f >= border && ix >= border && iy >= border && ix < ic.w - border && iy < ic.h - border) {
+      if (check_masks) {
+        const int level = small - intr.min_image_scale;
+        if (level < (int)im.mask.size() && !im.mask[level].d.empty() && im.mask[level].at(iy, ix) != 0) return;
+        if (im.image[level].at(iy, ix) > h->prm.maximum_valid_intensity) return;
+      }
+      out->push_back(Observation{point_index, jx, jy, observation_scale});
+    }
+  }
+}
+
+static void rigid_pp(const float R[9], const V3f& t, const float* p, V3f* out) {
+  const M3f& M = *reinterpret_cast<const M3f*>(R);
+  const V3f v = mul(M, V3f{p[0], p[1], p[2]});
+  *out = {v.x + t.x, v.y + t.y, v.z + t.z};
+}
+
+// AppendObservationsForImage (visibility_estimator.cc:61-91 + 258-295) or, with `lists`, the indexed variant (:140-168, 366-403).
+static void append_observations(const orc_reg* h, const Image& im, const Intrinsics& intr, int border,
+                                const std::vector<std::vector<uint64_t>>* lists, std::vector<std::vector<Observation>>* out) {
+  const int best = intr.best_available(std::max(h->prm.min_occlusion_check_image_scale, h->current_image_scale));
+  const Pinhole& cam = intr.model(best);
+  ImgF depth;
+  if (!lists) depth = render_depth(h, intr, im, best);
+  float R[9]; quat_to_matrix(im.image_T_global.q, R);
+  out->assign(h->pts.size(), {});
+  bool had_many = false;
+  for (int ps = (int)h->pts.size() - 1; ps >= 0; --ps) {
+    const ScalePoints& P = h->pts[ps];
+    std::vector<Observation>& o = (*out)[ps];
+    const size_t count = lists ? (*lists)[ps].size() : P.n();
+    for (size_t i = 0; i < count; ++i) {
+      const uint64_t pi = lists ? (*lists)[ps][i] : i;
+      V3f pp; rigid_pp(R, im.image_T_global.t, &P.xyz[3 * pi], &pp);
+      if (pp.z > 0.f) {
+        float ixx, ixy; cam.project(pp.x / pp.z, pp.y / pp.z, &ixx, &ixy);
+        const int ix = ixx + 0.5f, iy = ixy + 0.5f;
+        if (ix >= 0 && iy >= 0 && ix < cam.w && iy < cam.h &&
+            (lists || depth.d[(size_t)iy * depth.w + ix] + h->prm.occlusion_depth_threshold >= pp.z))
+          create_observation_if_scale_fits(h, intr, im, cam, best, pi, pp, P.radius, ixx, ixy, border, !lists, &o);
+      }
+    }
+    if (o.size() > 100) had_many = true;                 // kManyObservationsCount (visibility_estimator.cc:44,75-90)
+    else if (o.size() == 0 && had_many) break;
+  }
+}
+
+// DetermineIfAllNeighborsAreObserved (visibility_estimator.cc:199-256)
+static void neighbors_observed(const orc_reg* h, int ps, const std::vector<Observation>& o, std::vector<uint8_t>* out) {
+  const ScalePoints& P = h->pts[ps];
+  std::vector<bool> seen(P.n(), false);
+  for (const Observation& ob : o) seen[ob.point_index] = true;
+  out->resize(o.size());
+  for (size_t i = 0; i < o.size(); ++i) {
+    bool all = true;
+    for (int k = 0; k < K(h); ++k) if (!seen[P.nbr[o[i].point_index * K(h) + k]]) { all = false; break; }
+    (*out)[i] = all;
+  }
+}
+
+// ComputePointIntensityAndJacobians (intrinsics_and_pose_optimizer.cc:933-1147), non-rig, no depth residual.
+static void point_intensity_and_jacobians(const orc_reg* h, const Intrinsics& intr, const Image& im, const float R[9], float point_radius,
+                                          const float* point, const Observation& ob, float* intensity, float jK[4], float jP[6]) {
+  const Pinhole& cam = intr.model(0);
+  V3f tp; rigid_pp(R, im.image_T_global.t, point, &tp);
+  float ji[3];
+  const Img8& i0 = im.image[smaller_scale(ob) - intr.min_image_scale];
+  const Img8& i1 = im.image[larger_scale(ob) - intr.min_image_scale];
+  trilinear_d(i0, i1, ob.x, ob.y, 1 - (ob.scale - static_cast<int>(ob.scale)), intensity, &ji[0], &ji[1], &ji[2]);
+  ji[2] = -1 * ji[2];
+  const float scale_factor = (float)pow(2, intr.min_image_scale - smaller_scale(ob));
+  const float inv_scale_factor = 1.f / scale_factor;
+  ji[0] *= scale_factor; ji[1] *= scale_factor;
+  const float mx = inv_scale_factor * (ob.x + 0.5f) - 0.5f, my = inv_scale_factor * (ob.y + 0.5f) - 0.5f;
+  const V3f tpo{tp.x + point_radius, tp.y, tp.z};
+  float ox, oy; cam.project(tpo.x / tpo.z, tpo.y / tpo.z, &ox, &oy);
+  const float rdx = ox - mx, rdy = oy - my;
+  const float denom = std::max(1e-6f, 0.693147180559945f * (rdx * rdx + rdy * rdy));
+  float jpi[12], jpoi[8];   // 3x4 row-major, 2x4
+  cam.d_by_intrinsics(tp, jpi); cam.d_by_intrinsics(tpo, jpoi);
+  for (int i = 0; i < 4; ++i) jpi[8 + i] = ((jpoi[i] - jpi[i]) * rdx + (jpoi[4 + i] - jpi[4 + i]) * rdy) / denom;
+  for (int i = 0; i < 4; ++i) jK[i] = sum3(ji[0] * jpi[i], ji[1] * jpi[4 + i], ji[2] * jpi[8 + i]);
+  float jpp[9], jpop[6];    // 3x3 row-major, 2x3
+  cam.d_by_world(tp, jpp); cam.d_by_world(tpo, jpop);
+  for (int i = 0; i < 3; ++i) jpp[6 + i] = ((jpop[i] - jpp[i]) * rdx + (jpop[3 + i] - jpp[3 + i]) * rdy) / denom;
+  float a[3];
+  for (int i = 0; i < 3; ++i) a[i] = sum3(ji[0] * jpp[i], ji[1] * jpp[3 + i], ji[2] * jpp[6 + i]);
+  // [I | -[p]x] rows: (1,0,0,0,z,-y), (0,1,0,-z,0,x), (0,0,1,y,-x,0)
+  const float C[18] = {1, 0, 0, 0, tp.z, -1 * tp.y, 0, 1, 0, -1 * tp.z, 0, tp.x, 0, 0, 1, tp.y, -1 * tp.x, 0};
+  for (int c = 0; c < 6; ++c) jP[c] = sum3(a[0] * C[c], a[1] * C[6 + c], a[2] * C[12 + c]);
+}
+
+struct Sums { double fixed_sum = 0, var_sum = 0; uint64_t nf = 0, nv = 0; };
+
+// Problem::ComputeCost (problem.cc:602-631), depth weight 0.
+static double compute_cost(const orc_reg* h, const Sums& s) {
+  const bool uf = h->prm.fixed_residuals_weight > 0, uv = h->prm.variable_residuals_weight > 0;
+  double r = 0;
+  if (uf && s.nf > 0) r += h->prm.fixed_residuals_weight * s.fixed_sum / s.nf;
+  if (uv && s.nv > 0) r += h->prm.variable_residuals_weight * s.var_sum / s.nv;
+  if ((!uf && !uv) || (s.nf == 0 && s.nv == 0)) r = std::numeric_limits<float>::infinity();
+  return r;
+}
+
+// cost_calculator.cc:102-271
+static void accumulate_residuals(const orc_reg* h, const Intrinsics& intr, const Image& im, int ps, const std::vector<Observation>& o,
+                                 const std::vector<uint8_t>& nb, Sums* s) {
+  const ScalePoints& P = h->pts[ps];
+  std::vector<float> inten(P.n(), -1.f);
+  for (const Observation& ob : o)
+    trilinear(im.image[smaller_scale(ob) - intr.min_image_scale], im.image[larger_scale(ob) - intr.min_image_scale], ob.x, ob.y,
+              1 - (ob.scale - static_cast<int>(ob.scale)), &inten[ob.point_index]);
+  auto residual = [&](uint64_t pi, const std::vector<float>& desc) {
+    float pr = 0.f;
+    for (int k = 0; k < K(h); ++k) {
+      const float c = (inten[P.nbr[pi * K(h) + k]] - inten[pi]) - desc[pi * K(h) + k];
+      pr += c * c;
+    }
+    return h->robust.residual(sqrtf(pr));
+  };
+  for (size_t i = 0; i < o.size(); ++i) {
+    if (!nb[i]) continue;
+    if (h->prm.fixed_residuals_weight > 0) { s->fixed_sum += residual(o[i].point_index, P.fixed_desc); ++s->nf; }
+    if (h->prm.variable_residuals_weight > 0 && P.obs_count[o[i].point_index] >= 2) { s->var_sum += residual(o[i].point_index, P.var_desc); ++s->nv; }
+  }
+}
+
+// AccumulateOnHAndB (intrinsics_and_pose_optimizer.cc:1220-1296): fp32 products cast to double, upper triangles + full cross block.
+static void accumulate_on_H_b(float w, float res, int iv, int pv, const float jK[4], const float jP[6], std::vector<double>* H, std::vector<double>* b, int nv) {
+  if (w == 0) return;
+  auto Hh = [&](int r, int c) -> double& { return (*H)[(size_t)c * nv + r]; };
+  for (int c = 0; c < 4; ++c) for (int r = 0; r <= c; ++r) Hh(iv + r, iv + c) += (double)(w * jK[r] * jK[c]);
+  for (int r = 0; r < 4; ++r) for (int c = 0; c < 6; ++c) Hh(iv + r, pv + c) += (double)(w * jK[r] * jP[c]);
+  for (int c = 0; c < 6; ++c) for (int r = 0; r <= c; ++r) Hh(pv + r, pv + c) += (double)(w * jP[r] * jP[c]);
+  const float wr = w * res;
+  for (int i = 0; i < 4; ++i) (*b)[iv + i] += (double)(wr * jK[i]);
+  for (int i = 0; i < 6; ++i) (*b)[pv + i] += (double)(wr * jP[i]);
+}
+
+// AccumulateHAndBAndResidualsForObservations (intrinsics_and_pose_optimizer.cc:624-837) + ...ForColorObservation (:840-930)
+static void accumulate_H_b(const orc_reg* h, const Intrinsics& intr, const Image& im, int ps, const std::vector<Observation>& o,
+                           const std::vector<uint8_t>& nb, int iv, int pv, Sums* s, std::vector<double>* H, std::vector<double>* b, int nv) {
+  const ScalePoints& P = h->pts[ps];
+  float R[9]; quat_to_matrix(im.image_T_global.q, R);
+  std::vector<float> inten(o.size()), jK(4 * o.size()), jP(6 * o.size());
+  std::vector<int64_t> jac_of_point(P.n(), -1);
+  for (size_t i = 0; i < o.size(); ++i) {
+    point_intensity_and_jacobians(h, intr, im, R, P.radius, &P.xyz[3 * o[i].point_index], o[i], &inten[i], &jK[4 * i], &jP[6 * i]);
+    jac_of_point[o[i].point_index] = (int64_t)i;
+  }
+  if (h->prm.fixed_residuals_weight == 0 && h->prm.variable_residuals_weight == 0) return;
+  std::vector<float> comp(K(h));
+  auto color_obs = [&](uint64_t pi, size_t oj, const std::vector<float>& desc, float static_w, double* sum, uint64_t* cnt) {
+    float pr = 0.f;
+    for (int k = 0; k < K(h); ++k) {
+      const size_t nj = (size_t)jac_of_point[P.nbr[pi * K(h) + k]];
+      const float c = (inten[nj] - inten[oj]) - desc[pi * K(h) + k];
+      comp[k] = c; pr += c * c;
+    }
+    pr = sqrtf(pr);
+    ++(*cnt);
+    (*sum) += h->robust.residual(pr);
+    const float w = static_w * h->robust.weight(pr);
+    if (w != 0) {
+      for (int k = 0; k < K(h); ++k) {
+        const size_t nj = (size_t)jac_of_point[P.nbr[pi * K(h) + k]];
+        float dK[4], dP[6];
+        for (int i = 0; i < 4; ++i) dK[i] = jK[4 * nj + i] - jK[4 * oj + i];
+        for (int i = 0; i < 6; ++i) dP[i] = jP[6 * nj + i] - jP[6 * oj + i];
+        accumulate_on_H_b(w, comp[k], iv, pv, dK, dP, H, b, nv);
+      }
+    }
+  };
+  for (size_t i = 0; i < o.size(); ++i) {
+    if (!nb[i]) continue;
+    const uint64_t pi = o[i].point_index;
+    if (h->prm.fixed_residuals_weight > 0) color_obs(pi, i, P.fixed_desc, h->prm.fixed_residuals_weight, &s->fixed_sum, &s->nf);
+    if (h->prm.variable_residuals_weight > 0 && P.obs_count[pi] >= 2) color_obs(pi, i, P.var_desc, h->prm.variable_residuals_weight, &s->var_sum, &s->nv);
+  }
+}
+
+static int num_variables(const orc_reg* h) { return 4 * (int)h->st.intr.size() + 6 * (int)h->st.images.size(); }
+static int intr_var(const orc_reg*, int id) { return 4 * id; }
+static int pose_var(const orc_reg* h, int image_id) { return 4 * (int)h->st.intr.size() + 6 * image_id; }
+
+static void accumulate_all(const orc_reg* h, std::vector<double>* H, std::vector<double>* b, Sums* s) {
+  const int nv = num_variables(h);
+  H->assign((size_t)nv * nv, 0.0); b->assign(nv, 0.0);
+  for (size_t im = 0; im < h->st.images.size(); ++im)
+    for (size_t ps = 0; ps < h->pts.size(); ++ps)
+      accumulate_H_b(h, h->st.intr[h->st.images[im].intrinsics_id], h->st.images[im], (int)ps, h->obs[im][ps], h->nbr_obs[im][ps],
+                     intr_var(h, h->st.images[im].intrinsics_id), pose_var(h, (int)im), s, H, b, nv);
+}
+
+// CreateDeltaState (intrinsics_and_pose_optimizer.cc:475-558): params += delta (fp32 += double), pose <- exp(delta).cast<float>() * pose.
+static State delta_state(const orc_reg* h, const std::vector<double>& delta) {
+  State n = h->st;
+  for (size_t i = 0; i < n.intr.size(); ++i) {
+    Pinhole& m = n.intr[i].models[0];
+    float p[4] = {m.fx, m.fy, m.cx, m.cy};
+    for (int k = 0; k < 4; ++k) p[k] += delta[intr_var(h, (int)i) + k];
+    m.set(m.w, m.h, p[0], p[1], p[2], p[3]);
+    n.intr[i].build_pyramid();
+  }
+  for (size_t i = 0; i < n.images.size(); ++i) {
+    double d[6]; for (int k = 0; k < 6; ++k) d[k] = delta[pose_var(h, (int)i) + k];
+    n.images[i].image_T_global = se3_mul(se3d_exp_cast_float(d), h->st.images[i].image_T_global);
+  }
+  return n;
+}
+
+// ComputeResidualForState (intrinsics_and_pose_optimizer.cc:385-440) with frozen visibility lists.
+static double residual_for_state(orc_reg* h, const State& s, const std::vector<std::vector<std::vector<uint64_t>>>& lists) {
+  Sums sums;
+  const State saved = h->st;
+  h->st = s;   // descriptors / counts / points are not part of the state
+  for (size_t im = 0; im < s.images.size(); ++im) {
+    std::vector<std::vector<Observation>> o;
+    append_observations(h, s.images[im], s.intr[s.images[im].intrinsics_id], 1, &lists[im], &o);
+    for (size_t ps = 0; ps < h->pts.size(); ++ps) {
+      std::vector<uint8_t> nb; neighbors_observed(h, (int)ps, o[ps], &nb);
+      accumulate_residuals(h, s.intr[s.images[im].intrinsics_id], s.images[im], (int)ps, o[ps], nb, &sums);
+    }
+  }
+  h->st = saved;
+  return compute_cost(h, sums);
+}
+
+}  // namespace orc
+
+extern "C" {
+
+void orc_reg_default_params(orc_reg_params* p) {
+  p->point_neighbor_count = 5; p->fixed_residuals_weight = 1.f; p->variable_residuals_weight = 1.f;
+  p->robust_weighting_type = 1; p->robust_weighting_parameter = (float)(30 * sqrt(5) / sqrt(2));
+  p->maximum_valid_intensity = 252; p->occlusion_depth_threshold = 0.01f; p->min_occlusion_check_image_scale = 0;
+  p->max_initial_image_area_in_pixels = 200 * 160; p->splat_radius = 0.03f; p->image_scale_count_override = 0;
+}
+orc_reg* orc_reg_create(const orc_reg_params* p) {
+  orc_reg* h = new orc_reg(); h->prm = *p; h->robust.type = p->robust_weighting_type; h->robust.p = p->robust_weighting_parameter; return h;
+}
+void orc_reg_destroy(orc_reg* h) { delete h; }
+
+int orc_reg_add_intrinsics(orc_reg* h, int w, int hh, const float p[4]) {
+  Intrinsics in; in.models.resize(1); in.models[0].set(w, hh, p[0], p[1], p[2], p[3]);
+  h->st.intr.push_back(in); return (int)h->st.intr.size() - 1;
+}
+int orc_reg_add_image(orc_reg* h, int intr_id, const uint8_t* gray, const uint8_t* mask, const float T[7]) {
+  Image im; im.intrinsics_id = intr_id;
+  im.image_T_global.q = {T[0], T[1], T[2], T[3]}; im.image_T_global.t = {T[4], T[5], T[6]};
+  const Pinhole& c = h->st.intr[intr_id].models[0];
+  im.image.resize(1); im.image[0].w = c.w; im.image[0].h = c.h; im.image[0].d.assign(gray, gray + (size_t)c.w * c.h);
+  if (mask) { im.mask.resize(1); im.mask[0].w = c.w; im.mask[0].h = c.h; im.mask[0].d.assign(mask, mask + (size_t)c.w * c.h); }
+  h->st.images.push_back(std::move(im)); return (int)h->st.images.size() - 1;
+}
+// Problem::InitializeImages (problem.cc:478-494) + pyramids. Returns image_scale_count, or -1 on odd pyramid parents.
+int orc_reg_initialize(orc_reg* h) {
+  int count = 1;
+  auto scale_count = [&](const Intrinsics& in) {
+    const int px = in.models[0].w * in.models[0].h;
+    const double af = px * 1.0 / h->prm.max_initial_image_area_in_pixels;
+    return std::max<int>(2, 1 + (int)std::ceil(log(af) / log(4)));
+  };
+  for (const Intrinsics& in : h->st.intr) count = std::max(count, scale_count(in));
+  if (h->prm.image_scale_count_override > 0) count = h->prm.image_scale_count_override;
+  h->image_scale_count = count;
+  for (Intrinsics& in : h->st.intr) {
+    const int c = h->prm.image_scale_count_override > 0 ? count : scale_count(in);
+    in.min_image_scale = count - c;
+    in.models.resize(count - in.min_image_scale);
+    in.build_pyramid();
+  }
+  for (Image& im : h->st.images) {
+    const size_t levels = h->st.intr[im.intrinsics_id].models.size();
+    im.image.resize(levels);
+    if (!build_image_pyramid(im.image)) return -1;
+    if (!im.mask.empty()) { im.mask.resize(levels); build_mask_pyramid(im.mask); }
+  }
+  return count;
+}
+// One point scale: xyz n*3, radius, neighbour indices n*K, grey colours n (fixed descriptors d = c_nbr - c_ctr, problem.cc:550-572).
+int orc_reg_add_point_scale(orc_reg* h, const float* xyz, size_t n, float radius, const uint64_t* nbr, const float* colors) {
+  ScalePoints P; P.xyz.assign(xyz, xyz + 3 * n); P.radius = radius; P.nbr.assign(nbr, nbr + n * K(h));
+  P.fixed_desc.assign(n * K(h), 0.f); P.var_desc.assign(n * K(h), 0.f); P.obs_count.assign(n, 0);
+  if (h->prm.fixed_residuals_weight > 0)
+    for (size_t i = 0; i < n; ++i) {
+      for (int k = 0; k < K(h); ++k) P.fixed_desc[i * K(h) + k] = colors[P.nbr[i * K(h) + k]] - colors[i];
+      P.obs_count[i] = 99999;
+    }
+  h->pts.push_back(std::move(P)); return (int)h->pts.size() - 1;
+}
+void orc_reg_set_splat_points(orc_reg* h, const float* xyz, size_t n) { h->splat_xyz.assign(xyz, xyz + 3 * n); h->has_splats = n > 0; }
+int orc_reg_set_depth_map(orc_reg* h, int image, int w, int hh, const float* d) {
+  Image& im = h->st.images[image]; im.given_depth.w = w; im.given_depth.h = hh; im.given_depth.d.assign(d, d + (size_t)w * hh); im.has_given_depth = true; return 0;
+}
+void orc_reg_set_image_scale(orc_reg* h, int s) { h->current_image_scale = s; }
+int orc_reg_image_scale_count(orc_reg* h) { return h->image_scale_count; }
+int orc_reg_num_variables(orc_reg* h) { return num_variables(h); }
+
+int orc_reg_render_depth(orc_reg* h, int image, int* w, int* hh, float* out) {
+  const Image& im = h->st.images[image]; const Intrinsics& in = h->st.intr[im.intrinsics_id];
+  const int best = in.best_available(std::max(h->prm.min_occlusion_check_image_scale, h->current_image_scale));
+  const ImgF d = render_depth(h, in, im, best);
+  *w = d.w; *hh = d.h;
+  if (out) std::memcpy(out, d.d.data(), d.d.size() * sizeof(float));
+  return best;
+}
+
+// CreateObservationsForAllImages + DetermineIfAllNeighborsAreObserved (optimizer.cc:123-128)
+void orc_reg_create_observations(orc_reg* h, int border) {
+  h->obs.assign(h->st.images.size(), {}); h->nbr_obs.assign(h->st.images.size(), {});
+  for (size_t im = 0; im < h->st.images.size(); ++im) {
+    append_observations(h, h->st.images[im], h->st.intr[h->st.images[im].intrinsics_id], border, nullptr, &h->obs[im]);
+    h->nbr_obs[im].resize(h->pts.size());
+    for (size_t ps = 0; ps < h->pts.size(); ++ps) neighbors_observed(h, (int)ps, h->obs[im][ps], &h->nbr_obs[im][ps]);
+  }
+}
+uint64_t orc_reg_num_observations(orc_reg* h, int image, int ps) { return h->obs[image][ps].size(); }
+void orc_reg_get_observations(orc_reg* h, int image, int ps, uint64_t* idx, float* x, float* y, float* s, uint8_t* nb) {
+  const auto& o = h->obs[image][ps];
+  for (size_t i = 0; i < o.size(); ++i) { idx[i] = o[i].point_index; x[i] = o[i].x; y[i] = o[i].y; s[i] = o[i].scale; if (nb) nb[i] = h->nbr_obs[image][ps][i]; }
+}
+
+// ColorOptimizer::Apply (color_optimizer.cc:40-123); images in ascending id.
+void orc_reg_color_update(orc_reg* h) {
+  for (size_t ps = 0; ps < h->pts.size(); ++ps) {
+    ScalePoints& P = h->pts[ps];
+    std::fill(P.obs_count.begin(), P.obs_count.end(), 0);
+    std::fill(P.var_desc.begin(), P.var_desc.end(), 0.f);
+    for (size_t im = 0; im < h->st.images.size(); ++im) {
+      const Image& I = h->st.images[im]; const Intrinsics& in = h->st.intr[I.intrinsics_id];
+      const auto& o = h->obs[im][ps];
+      std::vector<float> inten(P.n(), -1);
+      for (const Observation& ob : o)
+        trilinear(I.image[smaller_scale(ob) - in.min_image_scale], I.image[larger_scale(ob) - in.min_image_scale], ob.x, ob.y,
+                  1 - (ob.scale - static_cast<int>(ob.scale)), &inten[ob.point_index]);
+      for (size_t i = 0; i < o.size(); ++i) if (h->nbr_obs[im][ps][i]) {
+        const uint64_t pi = o[i].point_index;
+        P.obs_count[pi] += 1;
+        for (int k = 0; k < K(h); ++k) P.var_desc[pi * K(h) + k] += inten[P.nbr[pi * K(h) + k]] - inten[pi];
+      }
+    }
+    for (size_t i = 0; i < P.n(); ++i) if (P.obs_count[i] > 1) for (int k = 0; k < K(h); ++k) P.var_desc[i * K(h) + k] /= P.obs_count[i];
+  }
+}
+void orc_reg_get_descriptors(orc_reg* h, int ps, float* fixed, float* variable, int* counts) {
+  const ScalePoints& P = h->pts[ps];
+  if (fixed) std::memcpy(fixed, P.fixed_desc.data(), P.fixed_desc.size() * 4);
+  if (variable) std::memcpy(variable, P.var_desc.data(), P.var_desc.size() * 4);
+  if (counts) std::memcpy(counts, P.obs_count.data(), P.obs_count.size() * 4);
+}
+
+// CostCalculator::ComputeCost (cost_calculator.cc:44-100). sums = [fixed_sum, n_fixed, var_sum, n_var, 0, 0]
+double orc_reg_cost(orc_reg* h, double sums[6]) {
+  Sums s;
+  for (size_t im = 0; im < h->st.images.size(); ++im)
+    for (size_t ps = 0; ps < h->pts.size(); ++ps)
+      accumulate_residuals(h, h->st.intr[h->st.images[im].intrinsics_id], h->st.images[im], (int)ps, h->obs[im][ps], h->nbr_obs[im][ps], &s);
+  if (sums) { sums[0] = s.fixed_sum; sums[1] = (double)s.nf; sums[2] = s.var_sum; sums[3] = (double)s.nv; sums[4] = sums[5] = 0; }
+  if (s.nf == 0 && s.nv == 0) return std::numeric_limits<double>::infinity();
+  return compute_cost(h, s);
+}
+
+// H (nv*nv col-major, the UPPER triangle the solver reads, mirrored), b, sums; returns the cost ("initial residual").
+double orc_reg_accumulate(orc_reg* h, double* H, double* b, double sums[6]) {
+  std::vector<double> Hv, bv; Sums s;
+  accumulate_all(h, &Hv, &bv, &s);
+  const int nv = num_variables(h);
+  if (H) for (int c = 0; c < nv; ++c) for (int r = 0; r < nv; ++r) H[(size_t)c * nv + r] = r <= c ? Hv[(size_t)c * nv + r] : Hv[(size_t)r * nv + c];
+  if (b) std::memcpy(b, bv.data(), sizeof(double) * nv);
+  if (sums) { sums[0] = s.fixed_sum; sums[1] = (double)s.nf; sums[2] = s.var_sum; sums[3] = (double)s.nv; sums[4] = sums[5] = 0; }
+  return compute_cost(h, s);
+}
+
+void orc_reg_get_state(orc_reg* h, float* intr_params, float* poses) {
+  for (size_t i = 0; i < h->st.intr.size(); ++i) { const Pinhole& m = h->st.intr[i].models[0]; float* p = intr_params + 4 * i; p[0] = m.fx; p[1] = m.fy; p[2] = m.cx; p[3] = m.cy; }
+  for (size_t i = 0; i < h->st.images.size(); ++i) {
+    const SE3f& T = h->st.images[i].image_T_global; float* p = poses + 7 * i;
+    p[0] = T.q.x; p[1] = T.q.y; p[2] = T.q.z; p[3] = T.q.w; p[4] = T.t.x; p[5] = T.t.y; p[6] = T.t.z;
+  }
+}
+void orc_reg_set_state(orc_reg* h, const float* intr_params, const float* poses) {
+  for (size_t i = 0; i < h->st.intr.size(); ++i) { Pinhole& m = h->st.intr[i].models[0]; const float* p = intr_params + 4 * i; m.set(m.w, m.h, p[0], p[1], p[2], p[3]); h->st.intr[i].build_pyramid(); }
+  for (size_t i = 0; i < h->st.images.size(); ++i) {
+    SE3f& T = h->st.images[i].image_T_global; const float* p = poses + 7 * i;
+    T.q = {p[0], p[1], p[2], p[3]}; T.t = {p[4], p[5], p[6]};
+  }
+}
+
+// Cost of the state (current state + delta) with the CURRENT observations' visibility lists frozen (what each LM try evaluates).
+double orc_reg_cost_for_delta(orc_reg* h, const double* delta) {
+  std::vector<std::vector<std::vector<uint64_t>>> lists(h->st.images.size());
+  for (size_t im = 0; im < h->st.images.size(); ++im) {
+    lists[im].resize(h->pts.size());
+    for (size_t ps = 0; ps < h->pts.size(); ++ps) for (const Observation& ob : h->obs[im][ps]) lists[im][ps].push_back(ob.point_index);
+  }
+  std::vector<double> d(delta, delta + num_variables(h));
+  return residual_for_state(h, delta_state(h, d), lists);
+}
+
+// IntrinsicsAndPoseOptimizer::Apply (intrinsics_and_pose_optimizer.cc:48-259). Returns the number of LM tries used.
+int orc_reg_apply(orc_reg* h, float* lambda, float* max_change, int* applied) {
+  std::vector<double> H, b; Sums s;
+  accumulate_all(h, &H, &b, &s);
+  const int nv = num_variables(h);
+  const double initial = compute_cost(h, s);
+  std::vector<std::vector<std::vector<uint64_t>>> lists(h->st.images.size());
+  for (size_t im = 0; im < h->st.images.size(); ++im) {
+    lists[im].resize(h->pts.size());
+    for (size_t ps = 0; ps < h->pts.size(); ++ps) for (const Observation& ob : h->obs[im][ps]) lists[im][ps].push_back(ob.point_index);
+  }
+  *applied = 0;
+  int tries = 0;
+  for (int lm = 0; lm < 10; ++lm) {
+    ++tries;
+    std::vector<double> HL = H;
+    for (int i = 0; i < nv; ++i) HL[(size_t)i * nv + i] *= (1 + (*lambda));
+    std::vector<double> x; ldlt_solve_upper(HL, nv, b, &x);
+    std::vector<double> neg(nv); for (int i = 0; i < nv; ++i) neg[i] = -1 * x[i];
+    const State ns = delta_state(h, neg);
+    const double nr = residual_for_state(h, ns, lists);
+    if (nr < initial || lm == 9) {
+      double mx = -std::numeric_limits<double>::infinity(); for (double v : x) mx = std::max(mx, v);   // signed maxCoeff (:245)
+      *max_change = (float)mx;
+      h->st = ns;
+      *lambda = 0.5f * (*lambda);
+      *applied = 1;
+      break;
+    } else {
+      *lambda = 2.f * (*lambda);
+    }
+  }
+  return tries;
+}
+
+// Optimizer::RunOnCurrentScale (optimizer.cc:49-182). Returns iterations executed; *converged set.
+int orc_reg_run_on_current_scale(orc_reg* h, int max_it, float max_change_thr, int no_opt_thr, double* optimum_cost, int* converged) {
+  h->current_image_scale = std::min(h->current_image_scale, h->image_scale_count - 1 - 1);   // max_image_scale() - 1
+  float lambda = 64.0f;
+  int without = 0, it_done = 0;
+  *optimum_cost = std::numeric_limits<double>::infinity();
+  *converged = 0;
+  State best = h->st;
+  for (int it = 0; it < max_it; ++it) {
+    ++it_done;
+    int applied = 1; float max_change = std::numeric_limits<float>::infinity();
+    if (it > 0) { applied = 0; max_change = 0; orc_reg_apply(h, &lambda, &max_change, &applied); }
+    orc_reg_create_observations(h, 1);
+    if (h->prm.variable_residuals_weight > 0) orc_reg_color_update(h);
+    const double cost = orc_reg_cost(h, nullptr);
+    if (cost < *optimum_cost) { *optimum_cost = cost; without = 0; best = h->st; } else { ++without; }
+    if (!applied || max_change < max_change_thr || without >= no_opt_thr) { *converged = 1; break; }
+  }
+  h->st = best;
+  return it_done;
+}
+
+// Unit hooks for the reference's own unit tests.
+void orc_reg_point_jacobians(orc_reg* h, int image, int ps, uint64_t obs_index, float* intensity, float jK[4], float jP[6]) {
+  const Image& im = h->st.images[image]; const Intrinsics& in = h->st.intr[im.intrinsics_id];
+  float R[9]; quat_to_matrix(im.image_T_global.q, R);
+  const Observation& ob = h->obs[image][ps][obs_index];
+  point_intensity_and_jacobians(h, in, im, R, h->pts[ps].radius, &h->pts[ps].xyz[3 * ob.point_index], ob, intensity, jK, jP);
+}
+int orc_interp_bilinear(const uint8_t* img, int w, int hh, float x, float y, float* v, float* dx, float* dy) {
+  Img8 im; im.w = w; im.h = hh; im.d.assign(img, img + (size_t)w * hh);
+  const int ix = (int)x, iy = (int)y;
+  if (x < 0.f || y < 0.f || ix >= w - 1 || iy >= hh - 1) return 0;     // interpolate_bilinear.h:79-112
+  float a, b, c; bilinear_d(im, x, y, ix, iy, &a, &b, &c);
+  const float plain = bilinear(im, x, y, ix, iy);
+  if (v) *v = plain; if (dx) *dx = b; if (dy) *dy = c;
+  return a == plain ? 1 : 2;
+}
+void orc_interp_trilinear(const uint8_t* img0, int w0, int h0, const uint8_t* img1, float x, float y, float z, float* v, float* dx, float* dy, float* dz) {
+  Img8 a, b; a.w = w0; a.h = h0; a.d.assign(img0, img0 + (size_t)w0 * h0); b.w = 2 * w0; b.h = 2 * h0; b.d.assign(img1, img1 + (size_t)4 * w0 * h0);
+  float pv; trilinear(a, b, x, y, z, &pv);
+  trilinear_d(a, b, x, y, z, v, dx, dy, dz);
+  if (pv != *v) *v = std::numeric_limits<float>::quiet_NaN();
+}
+float orc_robust(int type, float p, float r, int weight) { Robust R; R.type = type; R.p = p; return weight ? R.weight(r) : R.residual(r); }
+void orc_image_pyramid_level(const uint8_t* src, int w, int hh, uint8_t* dst) {
+  std::vector<Img8> p(2); p[0].w = w; p[0].h = hh; p[0].d.assign(src, src + (size_t)w * hh);
+  build_image_pyramid(p); std::memcpy(dst, p[1].d.data(), p[1].d.size());
+}
+
+}  // extern "C"

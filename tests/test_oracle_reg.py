@@ -1,0 +1,125 @@
+"""Path B oracle pinned on the reference's own unit tests (CPU only):
+  /root/reference/src/opt/test/test_interpolation.cc:39-185                       exact interpolation values / derivatives
+  /root/reference/src/opt/test/test_intrinsics_and_pose_optimizer.cc:101-336      analytic Jacobians vs finite differences
+plus the image pyramid against OpenCV's INTER_AREA (cv2 is importable in this container)."""
+import math
+
+import numpy as np
+import pytest
+
+EPS = 1e-5
+CE = 1e-6
+
+
+def test_ref_interpolation_bilinear(oracle):
+    img = np.array([[1, 2], [3, 4]], np.uint8)
+    B = oracle.interp_bilinear
+    assert B(img, 0, 0)[0] and abs(B(img, 0, 0)[1] - 1) < EPS
+    assert abs(B(img, 1 - CE, 0)[1] - 2) < EPS
+    assert abs(B(img, 0, 1 - CE)[1] - 3) < EPS
+    assert abs(B(img, 1 - CE, 1 - CE)[1] - 4) < EPS
+    assert abs(B(img, 0.5, 0)[1] - 1.5) < EPS and abs(B(img, 0, 0.5)[1] - 2.0) < EPS
+    ok, v, dx, dy = B(img, 0, 0)
+    assert abs(v - 1) < EPS and abs(dx - 1) < EPS and abs(dy - 2) < EPS
+    ok, v, dx, dy = B(img, 1 - CE, 0)
+    assert abs(v - 2) < EPS and abs(dx - 1) < EPS and abs(dy - 2) < EPS
+    # out-of-range accesses are rejected (interpolate_bilinear.h:79-112)
+    assert B(img, -0.1, 0)[0] == 0 and B(img, 1.0, 0)[0] == 0 and B(img, 0, 1.0)[0] == 0
+
+
+def test_ref_interpolation_trilinear(oracle):
+    i0 = np.array([[1, 2], [3, 4]], np.uint8)
+    i1 = (np.arange(4)[None, :] + 4 * np.arange(4)[:, None]).astype(np.uint8)
+    T = oracle.interp_trilinear
+    assert abs(T(i0, i1, 0, 0, 0)[0] - 1) < EPS and abs(T(i0, i1, 1 - CE, 0, 0)[0] - 2) < EPS
+    assert abs(T(i0, i1, 0, 1 - CE, 0)[0] - 3) < EPS and abs(T(i0, i1, 1 - CE, 1 - CE, 0)[0] - 4) < EPS
+    assert abs(T(i0, i1, 0.25, 0.25, 1)[0] - i1[1, 1]) < EPS and abs(T(i0, i1, 0.75, 0.25, 1)[0] - i1[1, 2]) < EPS
+    assert abs(T(i0, i1, 0.25, 0.75, 1)[0] - i1[2, 1]) < EPS and abs(T(i0, i1, 0.75, 0.75, 1)[0] - i1[2, 2]) < EPS
+    assert abs(T(i0, i1, 0.5, 0, 0)[0] - 1.5) < EPS and abs(T(i0, i1, 0, 0.5, 0)[0] - 2.0) < EPS
+    assert abs(T(i0, i1, 0.5, 0.25, 1)[0] - 0.5 * (5 + 6)) < EPS and abs(T(i0, i1, 0.25, 0.5, 1)[0] - 0.5 * (5 + 9)) < EPS
+    q = 0.25 * (0 + 1 + 4 + 5)
+    assert abs(T(i0, i1, 0, 0, 0.5)[0] - (0.5 * 1 + 0.5 * q)) < EPS
+    v, dx, dy, dz = T(i0, i1, 0, 0, 0)
+    assert abs(v - 1) < EPS and abs(dx - 1) < EPS and abs(dy - 2) < EPS and abs(dz - (q - 1)) < EPS
+    v, dx, dy, dz = T(i0, i1, 1 - CE, 0, 0)
+    q2 = 0.25 * (2 + 3 + 6 + 7)
+    assert abs(v - 2) < EPS and abs(dx - 1) < EPS and abs(dy - 2) < EPS and abs(dz - (q2 - 2)) < EPS
+
+
+def test_robust_weighting(oracle):
+    k = 30 * math.sqrt(5) / math.sqrt(2)
+    for r in (0.0, 1.0, 47.0, 48.0, 100.0):
+        hub = 0.5 * r * r if abs(r) < k else k * (abs(r) - 0.5 * k)
+        assert abs(oracle.robust(1, k, r) - hub) < 1e-3 * max(1, hub)
+        assert abs(oracle.robust(1, k, r, True) - (1.0 if abs(r) < k else k / abs(r))) < 1e-6
+    assert oracle.robust(2, 30, 31.0, True) == 0.0 and abs(oracle.robust(2, 30, 0.0, True) - 1.0) < 1e-6
+    assert abs(oracle.robust(0, 0, 3.0) - 4.5) < 1e-6
+
+
+def test_image_pyramid_matches_opencv_inter_area(oracle):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for (h, w) in ((30, 40), (240, 320), (64, 2)):
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        ref = cv2.resize(img, (int(0.5 * w), int(0.5 * h)), fx=0.5, fy=0.5, interpolation=cv2.INTER_AREA)
+        assert np.array_equal(oracle.image_pyramid_level(img), ref)
+
+
+# ---- test_intrinsics_and_pose_optimizer.cc:101-336 -------------------------------------------------------------------
+def _from_two_vectors(a, b):
+    """Eigen::Quaternionf::FromTwoVectors -> (x,y,z,w)."""
+    v0 = a / np.linalg.norm(a); v1 = b / np.linalg.norm(b)
+    c = float(v0 @ v1)
+    axis = np.cross(v0, v1)
+    s = math.sqrt((1 + c) * 2)
+    return np.array([axis[0] / s, axis[1] / s, axis[2] / s, s * 0.5])
+
+
+def _quat_R(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _make_problem(oracle, intr_params, image_T_global, point, radius):
+    p = oracle.reg_default_params(point_neighbor_count=2, robust_weighting_type=2, robust_weighting_parameter=30.0,
+                                  max_initial_image_area_in_pixels=80 * 60, image_scale_count_override=2)
+    r = oracle.Registration(p)
+    r.add_intrinsics(40, 30, intr_params)
+    yy, xx = np.mgrid[0:30, 0:40]
+    r.add_image(0, ((1 * xx + 3 * yy) % 256).astype(np.uint8), None, image_T_global)
+    assert r.initialize() == 2
+    r.add_point_scale(point[None, :], radius, np.zeros((1, 2), np.uint64), np.zeros(1, np.float32))
+    r.set_splat_points(point[None, :])
+    r.set_image_scale(0)
+    r.create_observations(0)
+    idx, x, y, s, nb = r.observations(0, 0)
+    assert len(idx) == 1
+    return r
+
+
+def test_ref_point_intensity_and_jacobians_fd(oracle):
+    q = _from_two_vectors(np.array([0.1, 0.3, 0.785]), np.array([0.4375, 0.2458, 0.2724]))
+    q = q / np.linalg.norm(q)
+    t = np.array([0.89763, 0.789346, 0.21398])
+    R = _quat_R(q)
+    qi = np.array([-q[0], -q[1], -q[2], q[3]]); ti = -(R.T @ t)
+    image_T_global = np.concatenate([qi, ti]).astype(np.float32)
+    base_intr = np.array([40, 30, 20, 15], np.float32)
+    radius = 0.036
+    for local in ((0.1, 0.23, 2.0), (0.4, 0.67, 2.1), (0.0, 0.0, 1.9)):
+        point = (R @ np.array(local) + t).astype(np.float32)
+        r = _make_problem(oracle, base_intr, image_T_global, point, radius)
+        I0, jK, jP = r.point_jacobians(0, 0, 0)
+        for c in range(4):                                             # intrinsics, delta = 1
+            ip = base_intr.copy(); ip[c] += 1
+            r2 = _make_problem(oracle, ip, image_T_global, point, radius)
+            I1, _, _ = r2.point_jacobians(0, 0, 0)
+            assert abs(1.0 * jK[c] - (I1 - I0)) < 1e-3, ("intrinsics", c)
+        for c in range(6):                                             # pose
+            d = np.zeros(6); d[c] = 2 * radius if c < 2 else 0.002
+            qo, to = oracle.se3_exp_left_mul(d, image_T_global[:4], image_T_global[4:])
+            r2 = _make_problem(oracle, base_intr, np.concatenate([qo, to]), point, radius)
+            I1, _, _ = r2.point_jacobians(0, 0, 0)
+            assert abs(d[c] * jP[c] - (I1 - I0)) < 1e-3, ("pose", c)
