@@ -339,11 +339,27 @@ def run_b200(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_accumulate<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": traffic,
-                "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "algorithmic_bytes_per_launch": 48.0 * recs, "avg_launch_ms": acc_ms}
+    src = "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
     mean = lambda k: float(np.mean([s[k] for s in step_stats]))
+    roof_acc = {"bound": "hbm", "kernel": "k_accumulate<true> (K5, 48 B/correspondence/pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": src,
+                "algorithmic_bytes_per_launch": 48.0 * recs, "avg_launch_ms": acc_ms,
+                "share_of_step": mean("passes") * acc_ms / (ms / args.steps)}
+    nn_ms = mean("ms_search_kernel_avg"); nn_launches = max(1.0, mean("search_launches"))
+    nn_bytes = mean("search_algorithmic_bytes") / nn_launches
+    nn_ach = (nn_bytes / (nn_ms * 1e-3)) / 1e9 if nn_ms > 0 else 0.0
+    nn_traffic = None
+    tp = os.path.join(ROOT, "profiles", "search_traffic.json")
+    if os.path.exists(tp):
+        try:
+            nn_traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            nn_traffic = None
+    roof_nn = {"bound": "hbm", "kernel": "k_nn_radius1 (K3, 12Q+8Qm+12T B/pair-direction; gather/L2-latency bound in practice)", "achieved": nn_ach,
+               "peak": peak, "unit": "GB/s", "frac": nn_ach / peak if peak else None, "traffic": nn_traffic, "peak_source": src,
+               "algorithmic_bytes_per_launch": nn_bytes, "avg_launch_ms": nn_ms, "share_of_step": nn_launches * nn_ms / (ms / args.steps)}
+    # the dominant kernel of the step is the one the roofline key describes; the other is kept alongside
+    roofline, roofline2 = (roof_nn, roof_acc) if roof_nn["share_of_step"] >= roof_acc["share_of_step"] else (roof_acc, roof_nn)
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f32 residuals/Jacobians, f64 accumulation", "data": "synthetic",
@@ -355,7 +371,7 @@ def run_b200(args):
                       "ms_breakdown": {"index": mean("ms_index"), "search": mean("ms_search"), "pack": mean("ms_pack"), "inner": mean("ms_inner")},
                       "input_generation_s": t_gen},
            "gpu_launches": int(sum(s["kernel_launches"] for s in step_stats)),
-           "clocks": clocks, "roofline": roofline}
+           "clocks": clocks, "roofline": roofline, "roofline_second_kernel": roofline2}
     if e2e:
         out["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

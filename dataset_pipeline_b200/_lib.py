@@ -26,7 +26,8 @@ class IcpStats(C.Structure):
                 ("first_cost", C.c_double), ("last_cost", C.c_double), ("final_lambda", C.c_double),
                 ("passes", C.c_int32), ("kernel_launches", C.c_int32),
                 ("ms_index", C.c_float), ("ms_search", C.c_float), ("ms_pack", C.c_float), ("ms_inner", C.c_float),
-                ("ms_total", C.c_float), ("ms_accum_kernel_avg", C.c_float)]
+                ("ms_total", C.c_float), ("ms_accum_kernel_avg", C.c_float), ("ms_search_kernel_avg", C.c_float),
+                ("search_launches", C.c_int32), ("search_algorithmic_bytes", C.c_uint64)]
 
 
 class B2Error(RuntimeError):
@@ -44,10 +45,51 @@ def build(force=False):
 
 # every symbol include/eth3d_b200.h declares
 EXPORTS = [
-    "b2_last_error", "b2_abi_version", "b2_device_info", "b2_icp_default_config", "b2_icp_create", "b2_icp_destroy",
-    "b2_icp_add_cloud", "b2_icp_add_cloud_dev", "b2_icp_run", "b2_icp_get_pose", "b2_icp_set_pose", "b2_icp_last_stats",
-    "b2_icp_get_lm_tries", "b2_icp_get_pair_info", "b2_icp_get_pair_correspondences", "b2_icp_get_normal_equations",
-    "b2_find_correspondences", "b2_normals_estimate", "b2_icp_plan_directions",
+    "b2_abi_version",
+    "b2_device_info",
+    "b2_find_correspondences",
+    "b2_icp_add_cloud",
+    "b2_icp_add_cloud_dev",
+    "b2_icp_create",
+    "b2_icp_default_config",
+    "b2_icp_destroy",
+    "b2_icp_get_lm_tries",
+    "b2_icp_get_normal_equations",
+    "b2_icp_get_pair_correspondences",
+    "b2_icp_get_pair_info",
+    "b2_icp_get_pose",
+    "b2_icp_last_stats",
+    "b2_icp_plan_directions",
+    "b2_icp_run",
+    "b2_icp_set_pose",
+    "b2_last_error",
+    "b2_normals_estimate",
+    "b2_reg_accumulate",
+    "b2_reg_add_image",
+    "b2_reg_add_intrinsics",
+    "b2_reg_add_point_scale",
+    "b2_reg_apply",
+    "b2_reg_color_update",
+    "b2_reg_cost",
+    "b2_reg_cost_for_delta",
+    "b2_reg_create",
+    "b2_reg_create_observations",
+    "b2_reg_default_params",
+    "b2_reg_destroy",
+    "b2_reg_get_descriptors",
+    "b2_reg_get_observations",
+    "b2_reg_get_point_jacobians",
+    "b2_reg_get_state",
+    "b2_reg_initialize",
+    "b2_reg_last_stats",
+    "b2_reg_num_observations",
+    "b2_reg_num_variables",
+    "b2_reg_render_depth",
+    "b2_reg_run_on_current_scale",
+    "b2_reg_set_depth_map",
+    "b2_reg_set_image_scale",
+    "b2_reg_set_splat_points",
+    "b2_reg_set_state",
 ]
 
 

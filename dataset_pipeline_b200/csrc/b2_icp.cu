@@ -69,7 +69,7 @@ struct b2_icp {
   unsigned long long per_cta = 0;
   int launches = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> acc_events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> acc_events, nn_events;
 };
 
 namespace b2 {
@@ -245,6 +245,8 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   h->tries.clear();
   for (auto& pr : h->acc_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   h->acc_events.clear();
+  for (auto& pr : h->nn_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  h->nn_events.clear();
   const int nc = num_impl_clouds(h);
   const int nmov = (int)h->movable.size();
   const int nv = 6 * (nc - 1);
@@ -312,9 +314,15 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
     tails[2 * k] = tails[2 * k + 1] = 0;
     if (ns == 0 || T->n == 0) continue;
     B2_TRY(d->match.ensure(ns * 4)); B2_TRY(d->d2.ensure(ns * 4)); B2_TRY(d->flags.ensure(ns * 4)); B2_TRY(d->offs.ensure(ns * 4));
+    cudaEvent_t n0 = nullptr, n1 = nullptr;
+    B2_CUDA(cudaEventCreate(&n0)); B2_CUDA(cudaEventCreate(&n1));
+    B2_CUDA(cudaEventRecord(n0, h->stream));
     k_nn_radius1<<<div_up(ns, 128), 128, 0, h->stream>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(), T->box2.as<Aabb>(),
                                                          T->table.as<HashEntry>(),
                                                          T->log2size, g, r2, d->match.as<int>(), d->d2.as<float>(), d->flags.as<unsigned int>());
+    B2_CUDA(cudaEventRecord(n1, h->stream));
+    h->nn_events.emplace_back(n0, n1);
+    h->stats.search_algorithmic_bytes += 12ull * ns + 12ull * T->n;
     ++h->launches;
     size_t tmp = 0;
     B2_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d->flags.as<unsigned int>(), d->offs.as<unsigned int>(), (long long)ns, h->stream));
@@ -334,6 +342,7 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
     Direction* d = h->dirs[k].get();
     if (!d->local) continue;
     d->count = (unsigned long long)tails[2 * k] + tails[2 * k + 1];
+    h->stats.search_algorithmic_bytes += 8ull * d->count;
     d->rec_begin = total;
     if (d->count == 0) continue;   // empty sets are not registered (icp_point_to_plane.cc:240)
     h->segs_host.push_back(Segment{total, total + d->count, d->src, d->tgt});
@@ -455,6 +464,9 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   h->stats.ms_total = elapsed(h->ev[0], h->ev[4]);
   double acc = 0; for (auto& pr : h->acc_events) acc += elapsed(pr.first, pr.second);
   h->stats.ms_accum_kernel_avg = h->acc_events.empty() ? 0.f : (float)(acc / h->acc_events.size());
+  double nn = 0; for (auto& pr : h->nn_events) nn += elapsed(pr.first, pr.second);
+  h->stats.ms_search_kernel_avg = h->nn_events.empty() ? 0.f : (float)(nn / h->nn_events.size());
+  h->stats.search_launches = (int)h->nn_events.size();
   return B2_OK;
 }
 
@@ -537,6 +549,7 @@ int b2_icp_destroy(b2_icp* h) {
                     &h->segsum, &h->eq_dev, &h->scatter_m, &h->scatter_d}) b->release();
   for (PinnedBuf* b : {&h->pin_bbox, &h->pin_counts, &h->pin_eq, &h->pin_poses, &h->pin_segs, &h->pin_misc}) b->release();
   for (auto& pr : h->acc_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (auto& pr : h->nn_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;

@@ -1,0 +1,797 @@
+// Host side of Path B behind the C ABI (include/eth3d_b200.h, b2_reg_*): owns the problem state in HBM (image / mask / intrinsics
+// pyramids, multi-resolution points, descriptors, per-(image, point-scale) observation sets) and runs the optimizer loop of
+// the reference on top of the kernels in b2_reg_kernels.cuh.
+//
+// Reference seams replaced:
+//   Problem::InitializeImages / LoadImages pyramids            /root/reference/src/opt/problem.cc:478-503, image.cc:106-154, intrinsics.cc:45-79
+//   OcclusionGeometry::RenderDepthMap (splats / none)          /root/reference/src/opt/occlusion_geometry.cc:185-282,404-464
+//   VisibilityEstimator::CreateObservationsForAllImages        /root/reference/src/opt/visibility_estimator.cc:49-91
+//   IntrinsicsAndPoseOptimizer::Apply / ComputeResidualForState /root/reference/src/opt/intrinsics_and_pose_optimizer.cc:48-259,385-440
+//   CostCalculator::ComputeCost, ColorOptimizer::Apply         /root/reference/src/opt/cost_calculator.cc:44-100, color_optimizer.cc:40-123
+//   Optimizer::RunOnCurrentScale                               /root/reference/src/opt/optimizer.cc:49-182
+// Images are visited in ascending id (the reference iterates unordered_maps); per-image fp64 partial sums are combined on the
+// host in that fixed order, so results are reproducible run to run.
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <limits>
+#include <memory>
+#include <vector>
+
+#include "b2_common.cuh"
+#include "b2_hostmath.h"
+#include "b2_reg_kernels.cuh"
+
+namespace b2 {
+
+static void cam_set(Cam* c, int w, int h, float fx, float fy, float cx, float cy) {
+  c->w = w; c->h = h; c->fx = fx; c->fy = fy; c->cx = cx; c->cy = cy;
+  c->fx_inv = (float)(1.0 / fx); c->fy_inv = (float)(1.0 / fy);            // camera_base.cc:83
+  c->cx_inv = (float)(-1.0 * cx / fx); c->cy_inv = (float)(-1.0 * cy / fy);
+}
+static Cam cam_half(const Cam& s) {                                          // CameraBaseImpl::ScaledBy(0.5), camera_base_impl.h:70-89
+  const float f = 0.5f;
+  Cam d; cam_set(&d, (int)(f * s.w + 0.5f), (int)(f * s.h + 0.5f), s.fx * f, s.fy * f, f * (s.cx + 0.5f) - 0.5f, f * (s.cy + 0.5f) - 0.5f);
+  return d;
+}
+
+struct IntrinsicsB {
+  std::vector<Cam> models;   // [0] = original resolution
+  int min_image_scale = -1;
+  const Cam& model(int image_scale) const { return models[std::max(0, image_scale - min_image_scale)]; }
+  int best_available(int image_scale) const { return std::min<int>(min_image_scale + (int)models.size() - 1, std::max<int>(min_image_scale, image_scale)); }
+  void build_pyramid() { for (size_t i = 1; i < models.size(); ++i) models[i] = cam_half(models[i - 1]); }
+};
+
+struct ImageB {
+  int intrinsics_id = 0;
+  Pose pose;                               // image_T_global
+  std::vector<DevBuf> img, mask;           // pyramids in HBM (mask empty = none)
+  std::vector<int> lw, lh;                 // level sizes (image pyramid: truncating halving)
+  bool has_mask = false;
+  DevBuf given_depth; int gd_w = 0, gd_h = 0; bool has_given_depth = false;
+};
+
+struct ScaleB {
+  size_t n = 0; float radius = 0.f;
+  DevBuf xyz, nbr, fixed_desc, var_desc, obs_count;
+};
+
+struct ObsSet {       // observations of one (image, point scale)
+  size_t count = 0;
+  DevBuf idx, x, y, s, nb, inten, jK, jP, slot;   // slot: per POINT (n), -1 = unobserved
+};
+
+struct StateB { std::vector<IntrinsicsB> intr; std::vector<Pose> poses; };
+
+static inline unsigned int divup(size_t a, size_t b) { return (unsigned int)((a + b - 1) / b); }
+
+}  // namespace b2
+
+using namespace b2;
+
+struct b2_reg {
+  b2_reg_params prm;
+  int device = 0, sms = 148;
+  cudaStream_t stream = nullptr;
+  std::vector<IntrinsicsB> intr;
+  std::vector<ImageB> images;
+  std::vector<ScaleB> pts;
+  DevBuf splats; size_t nsplats = 0;
+  int image_scale_count = 0, current_image_scale = 0;
+  bool initialized = false;
+  std::vector<std::vector<ObsSet>> obs;      // [image][scale]
+  std::vector<ObsSet> trial;                 // scratch sets for trial states, [scale]
+  // scratch
+  DevBuf flags, offs, cx, cy, cs, cub_tmp, depth, partials, results;
+  PinnedBuf pin;
+  b2_reg_stats stats;
+  int launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evj0 = nullptr, evj1 = nullptr, eva0 = nullptr, eva1 = nullptr;
+};
+
+namespace b2 {
+
+static int K(const b2_reg* h) { return h->prm.point_neighbor_count; }
+static int nvars(const b2_reg* h) { return 4 * (int)h->intr.size() + 6 * (int)h->images.size(); }
+static int intr_var(const b2_reg*, int id) { return 4 * id; }
+static int pose_var(const b2_reg* h, int im) { return 4 * (int)h->intr.size() + 6 * im; }
+
+static Pose3 pose3_of(const Pose& p) { Pose3 o; quat_matrix(p.q, o.R); for (int k = 0; k < 3; ++k) o.t[k] = p.t[k]; return o; }
+
+static Levels levels_of(const b2_reg* h, const ImageB& im, const IntrinsicsB& in) {
+  Levels L; std::memset(&L, 0, sizeof(L));
+  L.nlevels = (int)in.models.size(); L.min_image_scale = in.min_image_scale;
+  for (int l = 0; l < L.nlevels; ++l) {
+    L.cam[l] = in.models[l];
+    L.img[l] = im.img[l].as<unsigned char>();
+    L.mask[l] = im.has_mask ? im.mask[l].as<unsigned char>() : nullptr;
+  }
+  (void)h;
+  return L;
+}
+
+static void begin_call(b2_reg* h) { h->launches = 0; cudaEventRecord(h->ev0, h->stream); }
+static void end_call(b2_reg* h) {
+  cudaEventRecord(h->ev1, h->stream); cudaEventSynchronize(h->ev1);
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats.ms_last_call = ms; h->stats.kernel_launches = h->launches;
+}
+
+// RenderDepthMap at `image_scale`: caller-supplied map, splats, or nullptr (= all-inf map, occlusion_geometry.cc:271-281: the
+// test `inf + thr >= z` always passes, so the kernel simply skips the tap).
+static int render_depth(b2_reg* h, const ImageB& im, const IntrinsicsB& in, const Pose& pose, int image_scale, const float** out) {
+  const Cam& cam = in.model(image_scale);
+  if (im.has_given_depth) {
+    if (im.gd_w != cam.w || im.gd_h != cam.h)
+      return set_error(B2_ERR_ARG, "given depth map is %dx%d but the occlusion-check scale %d is %dx%d", im.gd_w, im.gd_h, image_scale, cam.w, cam.h);
+    *out = im.given_depth.as<float>(); return B2_OK;
+  }
+  if (h->nsplats == 0) { *out = nullptr; return B2_OK; }
+  const size_t px = (size_t)cam.w * cam.h;
+  B2_TRY(h->depth.ensure(px * 4));
+  kr_fill_u32<<<divup(px, 256), 256, 0, h->stream>>>(h->depth.as<unsigned int>(), px, 0x7f800000u);
+  kr_splat_depth<<<divup(h->nsplats, 256), 256, 0, h->stream>>>(h->splats.as<float>(), h->nsplats, pose3_of(pose), cam, h->prm.splat_radius,
+                                                                h->depth.as<unsigned int>());
+  h->launches += 2;
+  *out = h->depth.as<float>();
+  return B2_OK;
+}
+
+static int ensure_obs_set(ObsSet* o, size_t cap, size_t npoints, bool with_jac) {
+  cap = std::max<size_t>(cap, 1);
+  B2_TRY(o->idx.ensure(cap * 4)); B2_TRY(o->x.ensure(cap * 4)); B2_TRY(o->y.ensure(cap * 4)); B2_TRY(o->s.ensure(cap * 4));
+  B2_TRY(o->nb.ensure(cap)); B2_TRY(o->inten.ensure(cap * 4));
+  if (with_jac) { B2_TRY(o->jK.ensure(cap * 16)); B2_TRY(o->jP.ensure(cap * 24)); }
+  B2_TRY(o->slot.ensure(std::max<size_t>(npoints, 1) * 4));
+  return B2_OK;
+}
+
+// AppendObservationsForImage (visibility_estimator.cc:61-91) or, with `lists`, AppendObservationsForIndexedPointsVisibleInImage
+// (:140-168): observation sets for every point scale of one image under `state`, plus DetermineIfAllNeighborsAreObserved.
+static int observations_for_image(b2_reg* h, const StateB& st, int im_id, int border, const std::vector<ObsSet>* lists, std::vector<ObsSet>* out) {
+  const ImageB& im = h->images[im_id];
+  const IntrinsicsB& in = st.intr[im.intrinsics_id];
+  const Pose& pose = st.poses[im_id];
+  const int best = in.best_available(std::max(h->prm.min_occlusion_check_image_scale, h->current_image_scale));
+  const float* depth = nullptr;
+  if (!lists) B2_TRY(render_depth(h, im, in, pose, best, &depth));
+  Levels L = levels_of(h, im, in);
+  for (int l = 0; l < L.nlevels; ++l) L.cam[l] = in.models[l];
+  out->resize(h->pts.size());
+  bool had_many = false, stopped = false;
+  for (int ps = (int)h->pts.size() - 1; ps >= 0; --ps) {
+    const ScaleB& P = h->pts[ps];
+    ObsSet& o = (*out)[ps];
+    const size_t cand = lists ? (*lists)[ps].count : P.n;
+    B2_TRY(ensure_obs_set(&o, cand, P.n, !lists));
+    B2_CUDA(cudaMemsetAsync(o.slot.p, 0xFF, std::max<size_t>(P.n, 1) * 4, h->stream));
+    o.count = 0;
+    if (stopped || cand == 0) continue;
+    B2_TRY(h->flags.ensure(cand * 4)); B2_TRY(h->offs.ensure(cand * 4));
+    B2_TRY(h->cx.ensure(cand * 4)); B2_TRY(h->cy.ensure(cand * 4)); B2_TRY(h->cs.ensure(cand * 4));
+    VisParams V;
+    V.P = pose3_of(pose); V.cam = in.model(best); V.image_scale = best; V.depth = lists ? nullptr : depth;
+    V.occlusion_threshold = h->prm.occlusion_depth_threshold; V.point_radius = P.radius; V.max_valid_intensity = h->prm.maximum_valid_intensity;
+    V.border = border; V.check_masks = lists ? 0 : 1; V.current_image_scale = h->current_image_scale; V.image_scale_count = h->image_scale_count;
+    const unsigned int* list = lists ? (*lists)[ps].idx.as<unsigned int>() : nullptr;
+    kr_visibility<<<divup(cand, 256), 256, 0, h->stream>>>(P.xyz.as<float>(), list, cand, V, L, h->flags.as<unsigned int>(), h->cx.as<float>(),
+                                                           h->cy.as<float>(), h->cs.as<float>());
+    size_t tmp = 0;
+    B2_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, h->flags.as<unsigned int>(), h->offs.as<unsigned int>(), (long long)cand, h->stream));
+    B2_TRY(h->cub_tmp.ensure(tmp));
+    B2_CUDA(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tmp, h->flags.as<unsigned int>(), h->offs.as<unsigned int>(), (long long)cand, h->stream));
+    unsigned int* tail = h->pin.as<unsigned int>();
+    B2_CUDA(cudaMemcpyAsync(&tail[0], h->offs.as<unsigned int>() + (cand - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaMemcpyAsync(&tail[1], h->flags.as<unsigned int>() + (cand - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+    kr_compact<<<divup(cand, 256), 256, 0, h->stream>>>(h->flags.as<unsigned int>(), h->offs.as<unsigned int>(), list, cand, h->cx.as<float>(),
+                                                        h->cy.as<float>(), h->cs.as<float>(), o.idx.as<unsigned int>(), o.x.as<float>(),
+                                                        o.y.as<float>(), o.s.as<float>(), o.slot.as<int>());
+    h->launches += 2;
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    o.count = (size_t)tail[0] + tail[1];
+    if (o.count > 0) {
+      kr_neighbors_observed<<<divup(o.count, 256), 256, 0, h->stream>>>(o.idx.as<unsigned int>(), o.count, P.nbr.as<unsigned int>(), K(h),
+                                                                       o.slot.as<int>(), o.nb.as<unsigned char>());
+      ++h->launches;
+    }
+    if (o.count > 100) had_many = true;                    // kManyObservationsCount (visibility_estimator.cc:44,75-90)
+    else if (o.count == 0 && had_many) stopped = true;
+  }
+  B2_CUDA(cudaGetLastError());
+  return B2_OK;
+}
+
+static ResidualArgs residual_args(const b2_reg* h, int ps, const ObsSet& o) {
+  const ScaleB& P = h->pts[ps];
+  ResidualArgs A;
+  A.count = o.count; A.idx = o.idx.as<unsigned int>(); A.nb = o.nb.as<unsigned char>(); A.nbr = P.nbr.as<unsigned int>(); A.K = K(h);
+  A.slot = o.slot.as<int>(); A.inten = o.inten.as<float>(); A.fixed_desc = P.fixed_desc.as<float>(); A.var_desc = P.var_desc.as<float>();
+  A.obs_count = P.obs_count.as<int>(); A.robust.type = h->prm.robust_weighting_type; A.robust.p = h->prm.robust_weighting_parameter;
+  A.fixed_w = h->prm.fixed_residuals_weight; A.var_w = h->prm.variable_residuals_weight;
+  return A;
+}
+
+struct Sums { double fixed_sum = 0, var_sum = 0, nf = 0, nv = 0; };
+
+// Problem::ComputeCost (problem.cc:602-631), depth weight 0.
+static double compute_cost(const b2_reg* h, const Sums& s) {
+  const bool uf = h->prm.fixed_residuals_weight > 0, uv = h->prm.variable_residuals_weight > 0;
+  double r = 0;
+  if (uf && s.nf > 0) r += h->prm.fixed_residuals_weight * s.fixed_sum / s.nf;
+  if (uv && s.nv > 0) r += h->prm.variable_residuals_weight * s.var_sum / s.nv;
+  if ((!uf && !uv) || (s.nf == 0 && s.nv == 0)) r = std::numeric_limits<float>::infinity();
+  return r;
+}
+
+// Residual sums of ONE image over its observation sets (kr_intensity + kr_residual_sums per point scale, one readback), added to *acc.
+static int residual_sums_image(b2_reg* h, const StateB& st, int im, std::vector<ObsSet>& sets, Sums* acc) {
+  const int grid = h->sms * 2;
+  const size_t S = h->pts.size();
+  B2_TRY(h->partials.ensure(sizeof(double) * 4 * grid));
+  B2_TRY(h->results.ensure(sizeof(double) * 4 * std::max<size_t>(S, 1)));
+  B2_TRY(h->pin.ensure(std::max<size_t>(sizeof(double) * 4 * S, 64)));
+  B2_CUDA(cudaMemsetAsync(h->results.p, 0, sizeof(double) * 4 * std::max<size_t>(S, 1), h->stream));
+  const Levels L = levels_of(h, h->images[im], st.intr[h->images[im].intrinsics_id]);
+  bool any = false;
+  for (size_t ps = 0; ps < S; ++ps) {
+    ObsSet& o = sets[ps];
+    if (o.count == 0) continue;
+    any = true;
+    kr_intensity<<<divup(o.count, 256), 256, 0, h->stream>>>(o.count, o.x.as<float>(), o.y.as<float>(), o.s.as<float>(), L, o.inten.as<float>());
+    kr_residual_sums<<<grid, 256, 0, h->stream>>>(residual_args(h, (int)ps, o), h->partials.as<double>());
+    kr_reduce_partials<<<1, 128, 0, h->stream>>>(h->partials.as<double>(), grid, 4, h->results.as<double>() + 4 * ps);
+    h->launches += 3;
+  }
+  if (!any) return B2_OK;
+  B2_CUDA(cudaMemcpyAsync(h->pin.p, h->results.p, sizeof(double) * 4 * S, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  B2_CUDA(cudaGetLastError());
+  const double* r = h->pin.as<double>();
+  for (size_t k = 0; k < S; ++k) { acc->fixed_sum += r[4 * k]; acc->nf += r[4 * k + 1]; acc->var_sum += r[4 * k + 2]; acc->nv += r[4 * k + 3]; }
+  return B2_OK;
+}
+
+static StateB current_state(const b2_reg* h) {
+  StateB s; s.intr = h->intr;
+  for (const ImageB& im : h->images) s.poses.push_back(im.pose);
+  return s;
+}
+static void set_current_state(b2_reg* h, const StateB& s) {
+  h->intr = s.intr;
+  for (size_t i = 0; i < h->images.size(); ++i) h->images[i].pose = s.poses[i];
+}
+
+// CreateDeltaState (intrinsics_and_pose_optimizer.cc:475-558).
+static StateB delta_state(const b2_reg* h, const StateB& base, const double* delta) {
+  StateB n = base;
+  for (size_t i = 0; i < n.intr.size(); ++i) {
+    Cam& m = n.intr[i].models[0];
+    float p[4] = {m.fx, m.fy, m.cx, m.cy};
+    for (int k = 0; k < 4; ++k) p[k] += delta[intr_var(h, (int)i) + k];      // float += double (intrinsics.cc:72-74)
+    cam_set(&m, m.w, m.h, p[0], p[1], p[2], p[3]);
+    n.intr[i].build_pyramid();
+  }
+  for (size_t i = 0; i < n.poses.size(); ++i) n.poses[i] = pose_mul(pose_exp(delta + pose_var(h, (int)i)), base.poses[i]);   // image.cc:161
+  return n;
+}
+
+// ComputeResidualForState with frozen visibility lists (intrinsics_and_pose_optimizer.cc:385-440).
+static int residual_for_state(b2_reg* h, const StateB& st, double* cost) {
+  Sums total;
+  for (size_t im = 0; im < h->images.size(); ++im) {
+    B2_TRY(observations_for_image(h, st, (int)im, 1, &h->obs[im], &h->trial));
+    B2_TRY(residual_sums_image(h, st, (int)im, h->trial, &total));
+  }
+  *cost = compute_cost(h, total);
+  return B2_OK;
+}
+
+// AccumulateHAndBAndResidualsForObservations over all images and point scales (intrinsics_and_pose_optimizer.cc:102-185).
+static int accumulate_all(b2_reg* h, std::vector<double>* H, std::vector<double>* b, Sums* sums) {
+  const int nv = nvars(h);
+  const int grid = h->sms * 2;
+  const size_t S = h->pts.size(), NI = h->images.size();
+  H->assign((size_t)nv * nv, 0.0); b->assign(nv, 0.0);
+  B2_TRY(h->partials.ensure(sizeof(double) * kAccB * grid));
+  B2_TRY(h->results.ensure(sizeof(double) * kAccB * NI * S));
+  B2_TRY(h->pin.ensure(std::max<size_t>(sizeof(double) * kAccB * NI * S, 64)));
+  B2_CUDA(cudaMemsetAsync(h->results.p, 0, sizeof(double) * kAccB * NI * S, h->stream));
+  const StateB st = current_state(h);
+  uint64_t evals = 0;
+  float ms_j = 0.f, ms_a = 0.f;
+  for (size_t im = 0; im < NI; ++im) {
+    const ImageB& I = h->images[im];
+    const Levels L = levels_of(h, I, st.intr[I.intrinsics_id]);
+    const Pose3 P3 = pose3_of(I.pose);
+    for (size_t ps = 0; ps < S; ++ps) {
+      ObsSet& o = h->obs[im][ps];
+      if (o.count == 0) continue;
+      evals += o.count;
+      cudaEventRecord(h->evj0, h->stream);
+      kr_jacobians<<<divup(o.count, 256), 256, 0, h->stream>>>(o.count, o.idx.as<unsigned int>(), o.x.as<float>(), o.y.as<float>(), o.s.as<float>(),
+                                                              h->pts[ps].xyz.as<float>(), P3, h->pts[ps].radius, L, o.inten.as<float>(),
+                                                              o.jK.as<float>(), o.jP.as<float>());
+      cudaEventRecord(h->evj1, h->stream);
+      cudaEventRecord(h->eva0, h->stream);
+      kr_accumulate<<<grid, 128, 0, h->stream>>>(residual_args(h, (int)ps, o), o.jK.as<float>(), o.jP.as<float>(), h->partials.as<double>());
+      cudaEventRecord(h->eva1, h->stream);
+      kr_reduce_partials<<<1, 128, 0, h->stream>>>(h->partials.as<double>(), grid, kAccB, h->results.as<double>() + kAccB * (im * S + ps));
+      h->launches += 3;
+      cudaEventSynchronize(h->eva1);
+      float a = 0, c = 0; cudaEventElapsedTime(&a, h->evj0, h->evj1); cudaEventElapsedTime(&c, h->eva0, h->eva1);
+      ms_j += a; ms_a += c;
+    }
+  }
+  B2_CUDA(cudaMemcpyAsync(h->pin.p, h->results.p, sizeof(double) * kAccB * NI * S, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  B2_CUDA(cudaGetLastError());
+  const double* r = h->pin.as<double>();
+  *sums = Sums();
+  for (size_t im = 0; im < NI; ++im) {
+    const int iv = intr_var(h, h->images[im].intrinsics_id), pv = pose_var(h, (int)im);
+    auto g = [&](int l) { return l < kNI ? iv + l : pv + (l - kNI); };
+    for (size_t ps = 0; ps < S; ++ps) {
+      const double* v = r + kAccB * (im * S + ps);
+      int e = 0;
+      for (int c = 0; c < kNV; ++c) for (int rr = 0; rr <= c; ++rr) { (*H)[(size_t)g(c) * nv + g(rr)] += v[e]; ++e; }
+      for (int k = 0; k < kNV; ++k) (*b)[g(k)] += v[kNH + k];
+      sums->fixed_sum += v[kNH + kNV]; sums->nf += v[kNH + kNV + 1]; sums->var_sum += v[kNH + kNV + 2]; sums->nv += v[kNH + kNV + 3];
+    }
+  }
+  for (int c = 0; c < nv; ++c) for (int rr = 0; rr < c; ++rr) (*H)[(size_t)rr * nv + c] = (*H)[(size_t)c * nv + rr];   // mirror the Upper view
+  h->stats.residual_evaluations = evals; h->stats.ms_jacobian_kernel = ms_j; h->stats.ms_accumulate_kernel = ms_a;
+  return B2_OK;
+}
+
+static int create_observations(b2_reg* h, int border) {
+  const StateB st = current_state(h);
+  h->obs.resize(h->images.size());
+  uint64_t total = 0;
+  for (size_t im = 0; im < h->images.size(); ++im) {
+    B2_TRY(observations_for_image(h, st, (int)im, border, nullptr, &h->obs[im]));
+    for (const ObsSet& o : h->obs[im]) total += o.count;
+  }
+  h->stats.observations = total;
+  return B2_OK;
+}
+
+static int color_update(b2_reg* h) {
+  const StateB st = current_state(h);
+  for (size_t ps = 0; ps < h->pts.size(); ++ps) {
+    ScaleB& P = h->pts[ps];
+    if (P.n == 0) continue;
+    B2_CUDA(cudaMemsetAsync(P.obs_count.p, 0, P.n * 4, h->stream));
+    B2_CUDA(cudaMemsetAsync(P.var_desc.p, 0, P.n * K(h) * 4, h->stream));
+    for (size_t im = 0; im < h->images.size(); ++im) {
+      ObsSet& o = h->obs[im][ps];
+      if (o.count == 0) continue;
+      const Levels L = levels_of(h, h->images[im], st.intr[h->images[im].intrinsics_id]);
+      kr_intensity<<<divup(o.count, 256), 256, 0, h->stream>>>(o.count, o.x.as<float>(), o.y.as<float>(), o.s.as<float>(), L, o.inten.as<float>());
+      kr_color_accumulate<<<divup(o.count, 256), 256, 0, h->stream>>>(o.count, o.idx.as<unsigned int>(), o.nb.as<unsigned char>(), P.nbr.as<unsigned int>(),
+                                                                     K(h), o.slot.as<int>(), o.inten.as<float>(), P.var_desc.as<float>(), P.obs_count.as<int>());
+      h->launches += 2;
+    }
+    kr_color_mean<<<divup(P.n, 256), 256, 0, h->stream>>>(P.n, K(h), P.var_desc.as<float>(), P.obs_count.as<int>());
+    ++h->launches;
+  }
+  B2_CUDA(cudaGetLastError());
+  return B2_OK;
+}
+
+static int current_cost(b2_reg* h, double* cost, Sums* s) {
+  const StateB st = current_state(h);
+  *s = Sums();
+  for (size_t im = 0; im < h->images.size(); ++im) B2_TRY(residual_sums_image(h, st, (int)im, h->obs[im], s));
+  if (s->nf == 0 && s->nv == 0) { *cost = std::numeric_limits<double>::infinity(); return B2_OK; }   // cost_calculator.cc:88-93
+  *cost = compute_cost(h, *s);
+  return B2_OK;
+}
+
+// IntrinsicsAndPoseOptimizer::Apply (intrinsics_and_pose_optimizer.cc:48-259).
+static int apply_lm(b2_reg* h, float* lambda, float* max_change, int* applied, int* tries_out) {
+  std::vector<double> H, b; Sums s;
+  B2_TRY(accumulate_all(h, &H, &b, &s));
+  const int nv = nvars(h);
+  const double initial = compute_cost(h, s);
+  const StateB base = current_state(h);
+  *applied = 0;
+  int tries = 0;
+  std::vector<double> x(nv), neg(nv);
+  for (int lm = 0; lm < 10; ++lm) {
+    ++tries;
+    std::vector<double> HL = H;
+    for (int i = 0; i < nv; ++i) HL[(size_t)i * nv + i] *= (1 + (*lambda));
+    sym_solve(HL, nv, b.data(), x.data());
+    for (int i = 0; i < nv; ++i) neg[i] = -1 * x[i];
+    const StateB ns = delta_state(h, base, neg.data());
+    double nr = 0;
+    B2_TRY(residual_for_state(h, ns, &nr));
+    if (nr < initial || lm == 9) {      // kAlwaysApplyLastUpdate (:199,239-240)
+      double mx = -std::numeric_limits<double>::infinity();
+      for (double v : x) mx = std::max(mx, v);
+      *max_change = (float)mx;         // signed maxCoeff (:245)
+      set_current_state(h, ns);
+      *lambda = 0.5f * (*lambda);
+      *applied = 1;
+      break;
+    } else {
+      *lambda = 2.f * (*lambda);
+    }
+  }
+  if (tries_out) *tries_out = tries;
+  return B2_OK;
+}
+
+}  // namespace b2
+
+#define REG_ENTER(h)                                                            \
+  if (!(h)) return set_error(B2_ERR_ARG, "null handle");                         \
+  B2_CUDA(cudaSetDevice((h)->device));
+
+extern "C" {
+
+void b2_reg_default_params(b2_reg_params* p) {
+  if (!p) return;
+  p->point_neighbor_count = 5; p->fixed_residuals_weight = 1.f; p->variable_residuals_weight = 1.f;
+  p->robust_weighting_type = 1; p->robust_weighting_parameter = (float)(30 * std::sqrt(5.0) / std::sqrt(2.0));
+  p->maximum_valid_intensity = 252; p->occlusion_depth_threshold = 0.01f; p->min_occlusion_check_image_scale = 0;
+  p->max_initial_image_area_in_pixels = 200 * 160; p->splat_radius = 0.03f; p->image_scale_count_override = 0; p->device = -1;
+}
+
+int b2_reg_create(const b2_reg_params* p, b2_reg** out) {
+  if (!out) return set_error(B2_ERR_ARG, "out is null");
+  *out = nullptr;
+  std::unique_ptr<b2_reg> h(new b2_reg());
+  if (p) h->prm = *p; else b2_reg_default_params(&h->prm);
+  if (h->prm.point_neighbor_count < 1 || h->prm.point_neighbor_count > kMaxNbr) return set_error(B2_ERR_ARG, "point_neighbor_count must be in [1,%d]", kMaxNbr);
+  B2_TRY(select_device(h->prm.device, &h->device, &h->sms));
+  B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&h->ev0, &h->ev1, &h->evj0, &h->evj1, &h->eva0, &h->eva1}) B2_CUDA(cudaEventCreate(e));
+  B2_TRY(h->pin.ensure(4096));
+  std::memset(&h->stats, 0, sizeof(h->stats));
+  *out = h.release();
+  return B2_OK;
+}
+
+int b2_reg_destroy(b2_reg* h) {
+  if (!h) return B2_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  auto free_set = [](ObsSet& o) { for (DevBuf* b : {&o.idx, &o.x, &o.y, &o.s, &o.nb, &o.inten, &o.jK, &o.jP, &o.slot}) b->release(); };
+  for (auto& v : h->obs) for (auto& o : v) free_set(o);
+  for (auto& o : h->trial) free_set(o);
+  for (auto& im : h->images) { for (auto& b : im.img) b.release(); for (auto& b : im.mask) b.release(); im.given_depth.release(); }
+  for (auto& P : h->pts) for (DevBuf* b : {&P.xyz, &P.nbr, &P.fixed_desc, &P.var_desc, &P.obs_count}) b->release();
+  for (DevBuf* b : {&h->splats, &h->flags, &h->offs, &h->cx, &h->cy, &h->cs, &h->cub_tmp, &h->depth, &h->partials, &h->results}) b->release();
+  h->pin.release();
+  for (cudaEvent_t e : {h->ev0, h->ev1, h->evj0, h->evj1, h->eva0, h->eva1}) if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return B2_OK;
+}
+
+int b2_reg_add_intrinsics(b2_reg* h, int camera_model, int width, int height, const float* params, int num_params, int* out_id) {
+  REG_ENTER(h);
+  if (camera_model != 0) return set_error(B2_ERR_ARG, "camera model %d not supported by this ABI version (0 = PINHOLE only)", camera_model);
+  if (!params || num_params != 4 || width < 2 || height < 2) return set_error(B2_ERR_ARG, "PINHOLE needs 4 parameters and a size >= 2x2");
+  if (h->initialized) return set_error(B2_ERR_STATE, "add_intrinsics after initialize");
+  IntrinsicsB in; in.models.resize(1); cam_set(&in.models[0], width, height, params[0], params[1], params[2], params[3]);
+  h->intr.push_back(in);
+  if (out_id) *out_id = (int)h->intr.size() - 1;
+  return B2_OK;
+}
+
+int b2_reg_add_image(b2_reg* h, int intrinsics_id, const uint8_t* gray, const uint8_t* mask, const float T[7], int* out_id) {
+  REG_ENTER(h);
+  if (intrinsics_id < 0 || intrinsics_id >= (int)h->intr.size() || !gray || !T) return set_error(B2_ERR_ARG, "bad argument");
+  if (h->initialized) return set_error(B2_ERR_STATE, "add_image after initialize");
+  ImageB im; im.intrinsics_id = intrinsics_id;
+  for (int k = 0; k < 4; ++k) im.pose.q[k] = T[k];
+  for (int k = 0; k < 3; ++k) im.pose.t[k] = T[4 + k];
+  const Cam& c = h->intr[intrinsics_id].models[0];
+  const size_t px = (size_t)c.w * c.h;
+  im.img.resize(1); B2_TRY(im.img[0].ensure(px));
+  B2_CUDA(cudaMemcpyAsync(im.img[0].p, gray, px, cudaMemcpyHostToDevice, h->stream));
+  if (mask) { im.has_mask = true; im.mask.resize(1); B2_TRY(im.mask[0].ensure(px)); B2_CUDA(cudaMemcpyAsync(im.mask[0].p, mask, px, cudaMemcpyHostToDevice, h->stream)); }
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  h->images.push_back(std::move(im));
+  if (out_id) *out_id = (int)h->images.size() - 1;
+  return B2_OK;
+}
+
+int b2_reg_initialize(b2_reg* h, int* image_scale_count) {
+  REG_ENTER(h);
+  if (h->intr.empty() || h->images.empty()) return set_error(B2_ERR_STATE, "initialize needs at least one intrinsics and one image");
+  auto scale_count = [&](const IntrinsicsB& in) {                       // Intrinsics::ComputeImageScaleCount (intrinsics.h:82-86)
+    const int px = in.models[0].w * in.models[0].h;
+    const double af = px * 1.0 / h->prm.max_initial_image_area_in_pixels;
+    return std::max<int>(2, 1 + (int)std::ceil(std::log(af) / std::log(4)));
+  };
+  int count = 1;
+  for (const IntrinsicsB& in : h->intr) count = std::max(count, scale_count(in));
+  if (h->prm.image_scale_count_override > 0) count = h->prm.image_scale_count_override;
+  if (count > kMaxLevels) return set_error(B2_ERR_ARG, "more than %d image scales", kMaxLevels);
+  h->image_scale_count = count;
+  for (IntrinsicsB& in : h->intr) {
+    const int c = h->prm.image_scale_count_override > 0 ? count : scale_count(in);
+    in.min_image_scale = count - c;
+    in.models.resize(count - in.min_image_scale);
+    in.build_pyramid();
+  }
+  begin_call(h);
+  for (ImageB& im : h->images) {
+    const IntrinsicsB& in = h->intr[im.intrinsics_id];
+    const size_t levels = in.models.size();
+    im.img.resize(levels); if (im.has_mask) im.mask.resize(levels);
+    im.lw.assign(levels, 0); im.lh.assign(levels, 0);
+    im.lw[0] = in.models[0].w; im.lh[0] = in.models[0].h;
+    for (size_t l = 1; l < levels; ++l) {
+      if ((im.lw[l - 1] & 1) || (im.lh[l - 1] & 1))
+        return set_error(B2_ERR_ARG, "pyramid level %zu has odd size %dx%d: cv::resize INTER_AREA is only reproduced for even sizes (use sizes divisible by 2^(levels-1))",
+                         l - 1, im.lw[l - 1], im.lh[l - 1]);
+      im.lw[l] = (int)(0.5 * im.lw[l - 1]); im.lh[l] = (int)(0.5 * im.lh[l - 1]);
+      if (im.lw[l] != in.models[l].w || im.lh[l] != in.models[l].h)
+        return set_error(B2_ERR_ARG, "image pyramid level %zu (%dx%d) and camera pyramid (%dx%d) disagree", l, im.lw[l], im.lh[l], in.models[l].w, in.models[l].h);
+      const size_t px = (size_t)im.lw[l] * im.lh[l];
+      B2_TRY(im.img[l].ensure(px));
+      dim3 g(divup(im.lw[l], 256), im.lh[l]);
+      kr_pyr_down<<<g, 256, 0, h->stream>>>(im.img[l - 1].as<unsigned char>(), im.lw[l - 1], im.img[l].as<unsigned char>(), im.lw[l], im.lh[l], 0);
+      ++h->launches;
+      if (im.has_mask) {
+        B2_TRY(im.mask[l].ensure(px));
+        kr_pyr_down<<<g, 256, 0, h->stream>>>(im.mask[l - 1].as<unsigned char>(), im.lw[l - 1], im.mask[l].as<unsigned char>(), im.lw[l], im.lh[l], 1);
+        ++h->launches;
+      }
+    }
+  }
+  B2_CUDA(cudaGetLastError());
+  end_call(h);
+  h->initialized = true;
+  if (image_scale_count) *image_scale_count = count;
+  return B2_OK;
+}
+
+int b2_reg_add_point_scale(b2_reg* h, const float* xyz, size_t n, float radius, const uint64_t* nbr, const float* colors, int* out_scale) {
+  REG_ENTER(h);
+  if (n && (!xyz || !nbr || !colors)) return set_error(B2_ERR_ARG, "null argument");
+  if (n >= (1ull << 31)) return set_error(B2_ERR_ARG, "point scales above 2^31 points are not supported");
+  const int k = K(h);
+  ScaleB P; P.n = n; P.radius = radius;
+  const size_t m = std::max<size_t>(n, 1);
+  B2_TRY(P.xyz.ensure(m * 12)); B2_TRY(P.nbr.ensure(m * k * 4)); B2_TRY(P.fixed_desc.ensure(m * k * 4)); B2_TRY(P.var_desc.ensure(m * k * 4));
+  B2_TRY(P.obs_count.ensure(m * 4));
+  if (n) {
+    std::vector<unsigned int> nb32(n * k);
+    for (size_t i = 0; i < n * k; ++i) { if (nbr[i] >= n) return set_error(B2_ERR_ARG, "neighbour index out of range"); nb32[i] = (unsigned int)nbr[i]; }
+    DevBuf col; B2_TRY(col.ensure(n * 4));
+    B2_CUDA(cudaMemcpyAsync(P.xyz.p, xyz, n * 12, cudaMemcpyHostToDevice, h->stream));
+    B2_CUDA(cudaMemcpyAsync(P.nbr.p, nb32.data(), n * k * 4, cudaMemcpyHostToDevice, h->stream));
+    B2_CUDA(cudaMemcpyAsync(col.p, colors, n * 4, cudaMemcpyHostToDevice, h->stream));
+    B2_CUDA(cudaMemsetAsync(P.fixed_desc.p, 0, n * k * 4, h->stream));
+    B2_CUDA(cudaMemsetAsync(P.var_desc.p, 0, n * k * 4, h->stream));
+    B2_CUDA(cudaMemsetAsync(P.obs_count.p, 0, n * 4, h->stream));
+    if (h->prm.fixed_residuals_weight > 0)
+      kr_fixed_descriptors<<<divup(n, 256), 256, 0, h->stream>>>(n, k, P.nbr.as<unsigned int>(), col.as<float>(), P.fixed_desc.as<float>(), P.obs_count.as<int>());
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    col.release();
+  }
+  h->pts.push_back(P);
+  if (out_scale) *out_scale = (int)h->pts.size() - 1;
+  return B2_OK;
+}
+
+int b2_reg_set_splat_points(b2_reg* h, const float* xyz, size_t n) {
+  REG_ENTER(h);
+  h->nsplats = n;
+  if (n) { if (!xyz) return set_error(B2_ERR_ARG, "null"); B2_TRY(h->splats.ensure(n * 12)); B2_CUDA(cudaMemcpy(h->splats.p, xyz, n * 12, cudaMemcpyHostToDevice)); }
+  return B2_OK;
+}
+
+int b2_reg_set_depth_map(b2_reg* h, int image_id, int width, int height, const float* depth) {
+  REG_ENTER(h);
+  if (image_id < 0 || image_id >= (int)h->images.size() || !depth || width < 1 || height < 1) return set_error(B2_ERR_ARG, "bad argument");
+  ImageB& im = h->images[image_id];
+  B2_TRY(im.given_depth.ensure((size_t)width * height * 4));
+  B2_CUDA(cudaMemcpy(im.given_depth.p, depth, (size_t)width * height * 4, cudaMemcpyHostToDevice));
+  im.gd_w = width; im.gd_h = height; im.has_given_depth = true;
+  return B2_OK;
+}
+
+int b2_reg_set_image_scale(b2_reg* h, int s) { REG_ENTER(h); h->current_image_scale = s; return B2_OK; }
+int b2_reg_num_variables(b2_reg* h, int* nv) { REG_ENTER(h); if (nv) *nv = nvars(h); return B2_OK; }
+
+int b2_reg_render_depth(b2_reg* h, int image_id, int* width, int* height, int* image_scale, float* out) {
+  REG_ENTER(h);
+  if (!h->initialized) return set_error(B2_ERR_STATE, "not initialized");
+  if (image_id < 0 || image_id >= (int)h->images.size()) return set_error(B2_ERR_ARG, "bad image id");
+  const ImageB& im = h->images[image_id]; const IntrinsicsB& in = h->intr[im.intrinsics_id];
+  const int best = in.best_available(std::max(h->prm.min_occlusion_check_image_scale, h->current_image_scale));
+  const Cam& cam = in.model(best);
+  if (width) *width = cam.w; if (height) *height = cam.h; if (image_scale) *image_scale = best;
+  if (!out) return B2_OK;
+  begin_call(h);
+  const float* d = nullptr;
+  B2_TRY(render_depth(h, im, in, im.pose, best, &d));
+  const size_t px = (size_t)cam.w * cam.h;
+  if (d) { B2_CUDA(cudaMemcpyAsync(out, d, px * 4, cudaMemcpyDeviceToHost, h->stream)); }
+  end_call(h);
+  if (!d) for (size_t i = 0; i < px; ++i) out[i] = std::numeric_limits<float>::infinity();
+  return B2_OK;
+}
+
+int b2_reg_create_observations(b2_reg* h, int border) {
+  REG_ENTER(h);
+  if (!h->initialized) return set_error(B2_ERR_STATE, "not initialized");
+  begin_call(h);
+  B2_TRY(create_observations(h, border));
+  end_call(h);
+  return B2_OK;
+}
+
+static int check_obs(b2_reg* h, int image_id, int ps) {
+  if (image_id < 0 || image_id >= (int)h->obs.size() || ps < 0 || ps >= (int)h->pts.size() || ps >= (int)h->obs[image_id].size())
+    return set_error(B2_ERR_ARG, "no observations for image %d, point scale %d", image_id, ps);
+  return B2_OK;
+}
+
+int b2_reg_num_observations(b2_reg* h, int image_id, int ps, uint64_t* count) {
+  REG_ENTER(h); B2_TRY(check_obs(h, image_id, ps));
+  if (count) *count = h->obs[image_id][ps].count;
+  return B2_OK;
+}
+
+int b2_reg_get_observations(b2_reg* h, int image_id, int ps, uint64_t* pidx, float* x, float* y, float* s, uint8_t* nb) {
+  REG_ENTER(h); B2_TRY(check_obs(h, image_id, ps));
+  const ObsSet& o = h->obs[image_id][ps];
+  if (o.count == 0) return B2_OK;
+  std::vector<unsigned int> idx(o.count);
+  B2_CUDA(cudaMemcpy(idx.data(), o.idx.p, o.count * 4, cudaMemcpyDeviceToHost));
+  if (pidx) for (size_t i = 0; i < o.count; ++i) pidx[i] = idx[i];
+  if (x) B2_CUDA(cudaMemcpy(x, o.x.p, o.count * 4, cudaMemcpyDeviceToHost));
+  if (y) B2_CUDA(cudaMemcpy(y, o.y.p, o.count * 4, cudaMemcpyDeviceToHost));
+  if (s) B2_CUDA(cudaMemcpy(s, o.s.p, o.count * 4, cudaMemcpyDeviceToHost));
+  if (nb) B2_CUDA(cudaMemcpy(nb, o.nb.p, o.count, cudaMemcpyDeviceToHost));
+  return B2_OK;
+}
+
+int b2_reg_get_point_jacobians(b2_reg* h, int image_id, int ps, float* inten, float* jK, float* jP) {
+  REG_ENTER(h); B2_TRY(check_obs(h, image_id, ps));
+  ObsSet& o = h->obs[image_id][ps];
+  if (o.count == 0) return B2_OK;
+  const ImageB& I = h->images[image_id];
+  const Levels L = levels_of(h, I, h->intr[I.intrinsics_id]);
+  begin_call(h);
+  kr_jacobians<<<divup(o.count, 256), 256, 0, h->stream>>>(o.count, o.idx.as<unsigned int>(), o.x.as<float>(), o.y.as<float>(), o.s.as<float>(),
+                                                          h->pts[ps].xyz.as<float>(), pose3_of(I.pose), h->pts[ps].radius, L, o.inten.as<float>(),
+                                                          o.jK.as<float>(), o.jP.as<float>());
+  ++h->launches;
+  B2_CUDA(cudaGetLastError());
+  if (inten) B2_CUDA(cudaMemcpyAsync(inten, o.inten.p, o.count * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (jK) B2_CUDA(cudaMemcpyAsync(jK, o.jK.p, o.count * 16, cudaMemcpyDeviceToHost, h->stream));
+  if (jP) B2_CUDA(cudaMemcpyAsync(jP, o.jP.p, o.count * 24, cudaMemcpyDeviceToHost, h->stream));
+  end_call(h);
+  return B2_OK;
+}
+
+int b2_reg_color_update(b2_reg* h) {
+  REG_ENTER(h);
+  if (h->obs.size() != h->images.size()) return set_error(B2_ERR_STATE, "create_observations first");
+  begin_call(h); B2_TRY(color_update(h)); end_call(h);
+  return B2_OK;
+}
+
+int b2_reg_get_descriptors(b2_reg* h, int ps, float* fixed, float* variable, int32_t* counts) {
+  REG_ENTER(h);
+  if (ps < 0 || ps >= (int)h->pts.size()) return set_error(B2_ERR_ARG, "bad point scale");
+  const ScaleB& P = h->pts[ps];
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  if (P.n == 0) return B2_OK;
+  if (fixed) B2_CUDA(cudaMemcpy(fixed, P.fixed_desc.p, P.n * K(h) * 4, cudaMemcpyDeviceToHost));
+  if (variable) B2_CUDA(cudaMemcpy(variable, P.var_desc.p, P.n * K(h) * 4, cudaMemcpyDeviceToHost));
+  if (counts) B2_CUDA(cudaMemcpy(counts, P.obs_count.p, P.n * 4, cudaMemcpyDeviceToHost));
+  return B2_OK;
+}
+
+static void put_sums(const Sums& s, double out[6]) { if (out) { out[0] = s.fixed_sum; out[1] = s.nf; out[2] = s.var_sum; out[3] = s.nv; out[4] = out[5] = 0; } }
+
+int b2_reg_cost(b2_reg* h, double* cost, double sums[6]) {
+  REG_ENTER(h);
+  if (h->obs.size() != h->images.size()) return set_error(B2_ERR_STATE, "create_observations first");
+  begin_call(h);
+  Sums s; double c = 0;
+  B2_TRY(current_cost(h, &c, &s));
+  end_call(h);
+  if (cost) *cost = c;
+  put_sums(s, sums);
+  return B2_OK;
+}
+
+int b2_reg_accumulate(b2_reg* h, double* H, double* b, double sums[6], double* cost) {
+  REG_ENTER(h);
+  if (h->obs.size() != h->images.size()) return set_error(B2_ERR_STATE, "create_observations first");
+  begin_call(h);
+  std::vector<double> Hv, bv; Sums s;
+  B2_TRY(accumulate_all(h, &Hv, &bv, &s));
+  end_call(h);
+  if (H) std::copy(Hv.begin(), Hv.end(), H);
+  if (b) std::copy(bv.begin(), bv.end(), b);
+  put_sums(s, sums);
+  if (cost) *cost = compute_cost(h, s);
+  return B2_OK;
+}
+
+int b2_reg_get_state(b2_reg* h, float* ip, float* poses) {
+  REG_ENTER(h);
+  if (ip) for (size_t i = 0; i < h->intr.size(); ++i) { const Cam& m = h->intr[i].models[0]; ip[4 * i] = m.fx; ip[4 * i + 1] = m.fy; ip[4 * i + 2] = m.cx; ip[4 * i + 3] = m.cy; }
+  if (poses) for (size_t i = 0; i < h->images.size(); ++i) { for (int k = 0; k < 4; ++k) poses[7 * i + k] = h->images[i].pose.q[k]; for (int k = 0; k < 3; ++k) poses[7 * i + 4 + k] = h->images[i].pose.t[k]; }
+  return B2_OK;
+}
+
+int b2_reg_set_state(b2_reg* h, const float* ip, const float* poses) {
+  REG_ENTER(h);
+  if (ip) for (size_t i = 0; i < h->intr.size(); ++i) { Cam& m = h->intr[i].models[0]; cam_set(&m, m.w, m.h, ip[4 * i], ip[4 * i + 1], ip[4 * i + 2], ip[4 * i + 3]); h->intr[i].build_pyramid(); }
+  if (poses) for (size_t i = 0; i < h->images.size(); ++i) { for (int k = 0; k < 4; ++k) h->images[i].pose.q[k] = poses[7 * i + k]; for (int k = 0; k < 3; ++k) h->images[i].pose.t[k] = poses[7 * i + 4 + k]; }
+  return B2_OK;
+}
+
+int b2_reg_cost_for_delta(b2_reg* h, const double* delta, double* cost) {
+  REG_ENTER(h);
+  if (!delta || !cost) return set_error(B2_ERR_ARG, "null argument");
+  if (h->obs.size() != h->images.size()) return set_error(B2_ERR_STATE, "create_observations first");
+  begin_call(h);
+  const StateB ns = delta_state(h, current_state(h), delta);
+  B2_TRY(residual_for_state(h, ns, cost));
+  end_call(h);
+  return B2_OK;
+}
+
+int b2_reg_apply(b2_reg* h, float* lambda, float* max_change, int* applied, int* tries) {
+  REG_ENTER(h);
+  if (!lambda || !max_change || !applied) return set_error(B2_ERR_ARG, "null argument");
+  if (h->obs.size() != h->images.size()) return set_error(B2_ERR_STATE, "create_observations first");
+  begin_call(h);
+  B2_TRY(apply_lm(h, lambda, max_change, applied, tries));
+  end_call(h);
+  return B2_OK;
+}
+
+int b2_reg_run_on_current_scale(b2_reg* h, int max_it, float max_change_thr, int no_opt_thr, int print, double* optimum_cost, int* converged,
+                                int* iterations) {
+  REG_ENTER(h);
+  if (!h->initialized) return set_error(B2_ERR_STATE, "not initialized");
+  if (!optimum_cost || !converged) return set_error(B2_ERR_ARG, "null argument");
+  h->current_image_scale = std::min(h->current_image_scale, h->image_scale_count - 1 - 1);   // optimizer.cc:61
+  float lambda = 64.0f;
+  int without = 0, done = 0;
+  *optimum_cost = std::numeric_limits<double>::infinity();
+  *converged = 0;
+  StateB best = current_state(h);
+  for (int it = 0; it < max_it; ++it) {
+    ++done;
+    if (print) printf("Iteration %d\n", it + 1);
+    int applied = 1; float max_change = std::numeric_limits<float>::infinity();
+    if (it > 0) { applied = 0; max_change = 0; B2_TRY(apply_lm(h, &lambda, &max_change, &applied, nullptr)); }
+    B2_TRY(create_observations(h, 1));
+    if (h->prm.variable_residuals_weight > 0) B2_TRY(color_update(h));
+    Sums s; double cost = 0;
+    B2_TRY(current_cost(h, &cost, &s));
+    if (print) printf("  Cost (considering occlusions) is: %.9g\n", cost);
+    if (cost < *optimum_cost) { *optimum_cost = cost; without = 0; best = current_state(h); } else { ++without; }
+    if (!applied || max_change < max_change_thr || without >= no_opt_thr) { *converged = 1; break; }
+  }
+  set_current_state(h, best);
+  if (iterations) *iterations = done;
+  return B2_OK;
+}
+
+int b2_reg_last_stats(b2_reg* h, b2_reg_stats* out) {
+  REG_ENTER(h);
+  if (!out) return set_error(B2_ERR_ARG, "null");
+  *out = h->stats;
+  return B2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,414 @@
+// Device kernels of Path B (dense photometric image<->scan alignment) for sm_100a — pinhole cameras, no rigs.
+//
+//   K15 kr_pyr_down          u8 2x2 area mean ((a+b+c+d+2)>>2 = cv::resize INTER_AREA at factor 1/2) / mask OR    image.cc:106-154
+//   B1  kr_splat_depth       point-splat depth map, atomicMin on float bits                                        occlusion_geometry.cc:404-464
+//   K10 kr_visibility        R p + t, project, occlusion test, scale selection, border / mask / saturation tests  visibility_estimator.cc:258-295,366-532
+//   B6  kr_neighbors_observed  all 5 neighbours observed? via the point->observation slot map                      visibility_estimator.cc:199-256
+//   K11 kr_jacobians         trilinear taps on two pyramid levels, dI/d(K) (1x4), dI/d(pose) (1x6)               intrinsics_and_pose_optimizer.cc:933-1147
+//       kr_intensity         trilinear taps only                                                                 cost_calculator.cc:128-142
+//   K12 kr_accumulate        5-neighbour descriptor residual, robust weight, (4+6)^2 outer products in fp64     intrinsics_and_pose_optimizer.cc:770-930,1220-1296
+//   K13 kr_residual_sums     residual sums of a (trial) state                                                  cost_calculator.cc:170-271
+//   K14 kr_color_accumulate / kr_color_mean   variable descriptors = mean over images                              color_optimizer.cc:40-123
+// Arithmetic follows the oracle's fp32 evaluation order; the file is built with -fmad=false so plain operators are never
+// contracted. All of it is gather-bound byte / fp32 work: no tensor cores.
+#pragma once
+#include "b2_common.cuh"
+
+namespace b2 {
+
+static constexpr int kMaxLevels = 16;
+static constexpr int kMaxNbr = 8;
+
+struct Cam { int w, h; float fx, fy, cx, cy, fx_inv, fy_inv, cx_inv, cy_inv; };
+
+// Pyramid of one image (+ its intrinsics) as seen by the kernels. Level l is image scale (min_image_scale + l).
+struct Levels {
+  Cam cam[kMaxLevels];
+  const unsigned char* img[kMaxLevels];
+  const unsigned char* mask[kMaxLevels];   // null = no mask at that level
+  int nlevels, min_image_scale;
+};
+
+struct Pose3 { float R[9]; float t[3]; };   // image_T_global (row-major R)
+
+struct Robust { int type; float p; };
+__device__ __forceinline__ float robust_residual(const Robust& r, float x) {      // robust_weighting.h:61-86
+  if (r.type == 1) { const float a = fabsf(x); return a < r.p ? 0.5f * x * x : r.p * (a - 0.5f * r.p); }
+  if (r.type == 2) {
+    const float a = fabsf(x);
+    if (a < r.p) { const float q = x / r.p; const float t = 1.f - q * q; return (1 / 6.f) * r.p * r.p * (1 - t * t * t); }
+    return (1 / 6.f) * r.p * r.p;
+  }
+  return 0.5f * x * x;
+}
+__device__ __forceinline__ float robust_weight(const Robust& r, float x) {        // robust_weighting.h:90-106
+  if (r.type == 1) { const float a = fabsf(x); return a < r.p ? 1.f : r.p / a; }
+  if (r.type == 2) { const float a = fabsf(x); if (a < r.p) { const float q = x / r.p; const float t = 1.f - q * q; return t * t; } return 0.f; }
+  return 1.f;
+}
+
+__device__ __forceinline__ float sum3p(float a, float b, float c) { return a + (b + c); }   // Eigen 3-term reduction order
+
+__device__ __forceinline__ void cam_project(const Cam& c, float nx, float ny, float* ix, float* iy) {   // camera_base_impl.h:155-164
+  const float r2 = nx * nx + ny * ny;
+  if (isinf(r2)) { *ix = nx * INFINITY; *iy = ny * INFINITY; return; }
+  *ix = c.fx * nx + c.cx; *iy = c.fy * ny + c.cy;
+}
+__device__ __forceinline__ void cam_d_by_world(const Cam& c, float px, float py, float pz, float d[6]) {   // :333-360
+  const float nx = px / pz, ny = py / pz;
+  const float z_inv = 1.f / pz;
+  d[0] = c.fx * (1.f * z_inv); d[1] = c.fx * (0.f * z_inv); d[2] = c.fx * (-1.f * nx * z_inv);
+  d[3] = c.fy * (0.f * z_inv); d[4] = c.fy * (1.f * z_inv); d[5] = c.fy * (-1.f * ny * z_inv);
+}
+
+__device__ __forceinline__ void rigid(const Pose3& P, float x, float y, float z, float* ox, float* oy, float* oz) {
+  *ox = sum3p(P.R[0] * x, P.R[1] * y, P.R[2] * z) + P.t[0];
+  *oy = sum3p(P.R[3] * x, P.R[4] * y, P.R[5] * z) + P.t[1];
+  *oz = sum3p(P.R[6] * x, P.R[7] * y, P.R[8] * z) + P.t[2];
+}
+
+// interpolate_bilinear.h:36-74 on a u8 image with row pitch w.
+__device__ __forceinline__ float bilinear(const unsigned char* __restrict__ im, int w, float x, float y) {
+  const int ix = (int)x, iy = (int)y;
+  const float fx = x - ix, fx_inv = 1.f - fx, fy = y - iy, fy_inv = 1.f - fy;
+  const unsigned char* r0 = im + (size_t)iy * w + ix; const unsigned char* r1 = r0 + w;
+  return fy_inv * (fx_inv * __ldg(r0) + fx * __ldg(r0 + 1)) + fy * (fx_inv * __ldg(r1) + fx * __ldg(r1 + 1));
+}
+__device__ __forceinline__ void bilinear_d(const unsigned char* __restrict__ im, int w, float x, float y, float* v, float* dx, float* dy) {
+  const int ix = (int)x, iy = (int)y;
+  const unsigned char* r0 = im + (size_t)iy * w + ix; const unsigned char* r1 = r0 + w;
+  const unsigned char tl = __ldg(r0), tr = __ldg(r0 + 1), bl = __ldg(r1), br = __ldg(r1 + 1);
+  const float fx = x - ix, fx_inv = 1.f - fx, fy = y - iy, fy_inv = 1.f - fy;
+  const float top = fx_inv * tl + fx * tr, bottom = fx_inv * bl + fx * br;
+  *v = fy_inv * top + fy * bottom;
+  *dx = fy * (br - bl) + fy_inv * (tr - tl);
+  *dy = bottom - top;
+}
+// interpolate_trilinear.h:44-87: image0 = smaller level, image1 = twice the size.
+__device__ __forceinline__ float trilinear(const Levels& L, int small_level, float x0, float y0, float z) {
+  const float v0 = bilinear(L.img[small_level], L.cam[small_level].w, x0, y0);
+  const float x1 = 2 * (x0 + 0.5f) - 0.5f, y1 = 2 * (y0 + 0.5f) - 0.5f;
+  const float v1 = bilinear(L.img[small_level - 1], L.cam[small_level - 1].w, x1, y1);
+  return (1 - z) * v0 + z * v1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kr_pyr_down(const unsigned char* __restrict__ src, int sw, unsigned char* __restrict__ dst, int dw, int dh,
+                                                   int is_mask) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= dw || y >= dh) return;
+  const unsigned char* r0 = src + (size_t)(2 * y) * sw + 2 * x; const unsigned char* r1 = r0 + sw;
+  dst[(size_t)y * dw + x] = is_mask ? (unsigned char)(r0[0] | r0[1] | r1[0] | r1[1]) : (unsigned char)((r0[0] + r0[1] + r1[0] + r1[1] + 2) >> 2);
+}
+
+__global__ void __launch_bounds__(256) kr_fill_u32(unsigned int* __restrict__ p, size_t n, unsigned int v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// occlusion_geometry.cc:404-464: min over splats is order-independent, so atomicMin on the (positive) float bits is exact.
+__global__ void __launch_bounds__(256) kr_splat_depth(const float* __restrict__ xyz, size_t n, Pose3 P, Cam cam, float point_radius,
+                                                      unsigned int* __restrict__ depth_bits) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float px, py, pz; rigid(P, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &px, &py, &pz);
+  if (!(pz > 0.f)) return;
+  float ux, uy; cam_project(cam, px / pz, py / pz, &ux, &uy);
+  float d[6]; cam_d_by_world(cam, px, py, pz, d);
+  float rx = sqrtf(sum3p(d[0] * d[0], d[1] * d[1], d[2] * d[2])) * point_radius;
+  float ry = sqrtf(sum3p(d[3] * d[3], d[4] * d[4], d[5] * d[5])) * point_radius;
+  rx = fminf(rx, 10.f); ry = fminf(ry, 10.f);
+  const int ix = (int)(ux + 0.5f), iy = (int)(uy + 0.5f);
+  const int min_x = max(0, (int)(ix - rx + 0.5)), min_y = max(0, (int)(iy - ry + 0.5));
+  const int end_x = min(cam.w, (int)(ix + rx + 1.5)), end_y = min(cam.h, (int)(iy + ry + 1.5));
+  const unsigned int zb = __float_as_uint(pz);
+  for (int y = min_y; y < end_y; ++y) for (int x = min_x; x < end_x; ++x) atomicMin(&depth_bits[(size_t)y * cam.w + x], zb);
+}
+
+// K10. One thread per candidate point (all points of the scale, or the i-th entry of a visibility list).
+struct VisParams {
+  Pose3 P; Cam cam; int image_scale;            // camera of the occlusion-check scale
+  const float* depth;                           // null = no occlusion test (indexed visibility lists)
+  float occlusion_threshold, point_radius, max_valid_intensity;
+  int border, check_masks, current_image_scale, image_scale_count;
+};
+__global__ void __launch_bounds__(256) kr_visibility(const float* __restrict__ xyz, const unsigned int* __restrict__ list, size_t count, VisParams V,
+                                                     Levels L, unsigned int* __restrict__ flags, float* __restrict__ ox, float* __restrict__ oy,
+                                                     float* __restrict__ os) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const size_t pi = list ? list[i] : i;
+  unsigned int ok = 0;
+  float rx_ = 0.f, ry_ = 0.f, rs_ = 0.f;
+  float px, py, pz; rigid(V.P, xyz[3 * pi], xyz[3 * pi + 1], xyz[3 * pi + 2], &px, &py, &pz);
+  if (pz > 0.f) {
+    float ixx, ixy; cam_project(V.cam, px / pz, py / pz, &ixx, &ixy);
+    const int ix = (int)(ixx + 0.5f), iy = (int)(ixy + 0.5f);
+    if (ix >= 0 && iy >= 0 && ix < V.cam.w && iy < V.cam.h &&
+        (V.depth == nullptr || __ldg(V.depth + (size_t)iy * V.cam.w + ix) + V.occlusion_threshold >= pz)) {
+      // CreateObservationIfScaleFits (visibility_estimator.cc:405-532)
+      const float qx = px + V.point_radius, qy = py + 0, qz = pz + 0;
+      float rx, ry; cam_project(V.cam, qx / qz, qy / qz, &rx, &ry);
+      const float dx = rx - ixx, dy = ry - ixy;
+      const float radius_pixels = sqrtf(dx * dx + dy * dy);
+      const float observation_scale = (float)((double)V.image_scale + log2((double)(2 * radius_pixels)));
+      if (observation_scale >= (float)max(L.min_image_scale, V.current_image_scale) && (int)observation_scale < V.image_scale_count - 1) {
+        const int small = (int)observation_scale + 1;
+        const int lvl = max(0, small - L.min_image_scale);
+        const Cam& ic = L.cam[lvl];
+        const float nx = V.cam.fx_inv * ixx + V.cam.cx_inv, ny = V.cam.fy_inv * ixy + V.cam.cy_inv;
+        const float jx = ic.fx * nx + ic.cx, jy = ic.fy * ny + ic.cy;
+        const int jix = (int)(jx + 0.5f), jiy = (int)(jy + 0.5f);
+        if (jx + 0.5f >= (float)V.border && jy + 0.5f >= (float)V.border && jix >= V.border && jiy >= V.border && jix < ic.w - V.border &&
+            jiy < ic.h - V.border) {
+          bool keep = true;
+          if (V.check_masks) {
+            const int level = small - L.min_image_scale;
+            if (L.mask[level] != nullptr && __ldg(L.mask[level] + (size_t)jiy * ic.w + jix) != 0) keep = false;
+            else if ((float)__ldg(L.img[level] + (size_t)jiy * ic.w + jix) > V.max_valid_intensity) keep = false;
+          }
+          if (keep) { ok = 1; rx_ = jx; ry_ = jy; rs_ = observation_scale; }
+        }
+      }
+    }
+  }
+  flags[i] = ok; ox[i] = rx_; oy[i] = ry_; os[i] = rs_;
+}
+
+__global__ void __launch_bounds__(256) kr_compact(const unsigned int* __restrict__ flags, const unsigned int* __restrict__ offs,
+                                                  const unsigned int* __restrict__ list, size_t count, const float* __restrict__ cx,
+                                                  const float* __restrict__ cy, const float* __restrict__ cs, unsigned int* __restrict__ idx,
+                                                  float* __restrict__ ox, float* __restrict__ oy, float* __restrict__ os, int* __restrict__ slot) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count || !flags[i]) return;
+  const unsigned int o = offs[i];
+  const unsigned int pi = list ? list[i] : (unsigned int)i;
+  idx[o] = pi; ox[o] = cx[i]; oy[o] = cy[i]; os[o] = cs[i];
+  slot[pi] = (int)o;
+}
+
+__global__ void __launch_bounds__(256) kr_neighbors_observed(const unsigned int* __restrict__ idx, size_t count, const unsigned int* __restrict__ nbr,
+                                                             int K, const int* __restrict__ slot, unsigned char* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const size_t p = idx[i];
+  bool all = true;
+  for (int k = 0; k < K; ++k) if (slot[nbr[p * K + k]] < 0) { all = false; break; }
+  out[i] = all ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) kr_intensity(size_t count, const float* __restrict__ ox, const float* __restrict__ oy,
+                                                    const float* __restrict__ os, Levels L, float* __restrict__ inten) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float s = os[i];
+  const int small = (int)s + 1 - L.min_image_scale;
+  inten[i] = trilinear(L, small, ox[i], oy[i], 1 - (s - (int)s));
+}
+
+// K11 (intrinsics_and_pose_optimizer.cc:933-1147), non-rig, depth residuals off.
+__global__ void __launch_bounds__(256) kr_jacobians(size_t count, const unsigned int* __restrict__ idx, const float* __restrict__ ox,
+                                                    const float* __restrict__ oy, const float* __restrict__ os, const float* __restrict__ xyz,
+                                                    Pose3 P, float point_radius, Levels L, float* __restrict__ inten, float* __restrict__ jK,
+                                                    float* __restrict__ jP) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const Cam& cam = L.cam[0];
+  const size_t p = idx[i];
+  float tx, ty, tz; rigid(P, xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], &tx, &ty, &tz);
+  const float s = os[i], x0 = ox[i], y0 = oy[i];
+  const int smaller = (int)s + 1;
+  const int sl = smaller - L.min_image_scale;
+  const float z = 1 - (s - (int)s);
+  float v0, d0x, d0y, v1, d1x, d1y;
+  bilinear_d(L.img[sl], L.cam[sl].w, x0, y0, &v0, &d0x, &d0y);
+  const float x1 = 2 * (x0 + 0.5f) - 0.5f, y1 = 2 * (y0 + 0.5f) - 0.5f;
+  bilinear_d(L.img[sl - 1], L.cam[sl - 1].w, x1, y1, &v1, &d1x, &d1y);
+  inten[i] = (1 - z) * v0 + z * v1;
+  float ji0 = (1 - z) * d0x + z * 2 * d1x;
+  float ji1 = (1 - z) * d0y + z * 2 * d1y;
+  const float ji2 = -1 * (v1 - v0);
+  const float scale_factor = ldexpf(1.f, L.min_image_scale - smaller);      // pow(2, min_image_scale - smaller_interpolation_scale)
+  const float inv_scale_factor = 1.f / scale_factor;
+  ji0 *= scale_factor; ji1 *= scale_factor;
+  const float mx = inv_scale_factor * (x0 + 0.5f) - 0.5f, my = inv_scale_factor * (y0 + 0.5f) - 0.5f;
+  const float qx = tx + point_radius;
+  float oxp, oyp; cam_project(cam, qx / tz, ty / tz, &oxp, &oyp);
+  const float rdx = oxp - mx, rdy = oyp - my;
+  const float denom = fmaxf(1e-6f, 0.693147180559945f * (rdx * rdx + rdy * rdy));
+  // d(project)/d(intrinsics) rows: [x 0 1 0], [0 y 0 1], scale row from the offset point
+  const float a[8] = {tx / tz, 0.f, 1.f, 0.f, 0.f, ty / tz, 0.f, 1.f};
+  const float b[8] = {qx / tz, 0.f, 1.f, 0.f, 0.f, ty / tz, 0.f, 1.f};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float row2 = ((b[k] - a[k]) * rdx + (b[4 + k] - a[4 + k]) * rdy) / denom;
+    jK[4 * i + k] = sum3p(ji0 * a[k], ji1 * a[4 + k], ji2 * row2);
+  }
+  float dw[6], dq[6];
+  cam_d_by_world(cam, tx, ty, tz, dw);
+  cam_d_by_world(cam, qx, ty, tz, dq);
+  float g[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float row2 = ((dq[k] - dw[k]) * rdx + (dq[3 + k] - dw[3 + k]) * rdy) / denom;
+    g[k] = sum3p(ji0 * dw[k], ji1 * dw[3 + k], ji2 * row2);
+  }
+  // [I | -[p]x]: rows (1,0,0,0,z,-y), (0,1,0,-z,0,x), (0,0,1,y,-x,0)
+  const float C[18] = {1, 0, 0, 0, tz, -1 * ty, 0, 1, 0, -1 * tz, 0, tx, 0, 0, 1, ty, -1 * tx, 0};
+#pragma unroll
+  for (int c = 0; c < 6; ++c) jP[6 * i + c] = sum3p(g[0] * C[c], g[1] * C[6 + c], g[2] * C[12 + c]);
+}
+
+// Common inputs of the residual kernels for one (image, point scale).
+struct ResidualArgs {
+  size_t count;
+  const unsigned int* idx; const unsigned char* nb; const unsigned int* nbr; int K; const int* slot; const float* inten;
+  const float* fixed_desc; const float* var_desc; const int* obs_count;
+  Robust robust; float fixed_w, var_w;
+};
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_d(double* acc, double (*sm)[NV], int nthreads, double* out) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    acc[k] = v;
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sm[w][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double v = sm[0][threadIdx.x];
+    for (int i = 1; i < nthreads / 32; ++i) v += sm[i][threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+}
+
+// K13: residual sums [fixed_sum, n_fixed, var_sum, n_var] per block (cost_calculator.cc:170-271).
+__global__ void __launch_bounds__(256) kr_residual_sums(ResidualArgs A, double* __restrict__ partials /* [grid][4] */) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.count; i += (size_t)gridDim.x * blockDim.x) {
+    if (!A.nb[i]) continue;
+    const size_t p = A.idx[i];
+    const float Ic = A.inten[i];
+    float In[kMaxNbr];
+#pragma unroll
+    for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) In[k] = A.inten[A.slot[A.nbr[p * A.K + k]]];
+    if (A.fixed_w > 0) {
+      float pr = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) { const float c = (In[k] - Ic) - A.fixed_desc[p * A.K + k]; pr += c * c; }
+      acc[0] += (double)robust_residual(A.robust, sqrtf(pr)); acc[1] += 1.0;
+    }
+    if (A.var_w > 0 && A.obs_count[p] >= 2) {
+      float pr = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) { const float c = (In[k] - Ic) - A.var_desc[p * A.K + k]; pr += c * c; }
+      acc[2] += (double)robust_residual(A.robust, sqrtf(pr)); acc[3] += 1.0;
+    }
+  }
+  __shared__ double sm[8][4];
+  double out;
+  block_reduce_d<4>(acc, sm, 256, &out);
+  if (threadIdx.x < 4) partials[(size_t)blockIdx.x * 4 + threadIdx.x] = out;
+}
+
+// K12: per block [55 upper entries of the local (4+6)^2 system | 10 of b | fixed_sum n_fixed var_sum n_var] = 69 doubles.
+static constexpr int kNI = 4, kNV = kNI + 6, kNH = kNV * (kNV + 1) / 2, kAccB = kNH + kNV + 4;
+__global__ void __launch_bounds__(128) kr_accumulate(ResidualArgs A, const float* __restrict__ jK, const float* __restrict__ jP,
+                                                     double* __restrict__ partials /* [grid][kAccB] */) {
+  double acc[kAccB];
+#pragma unroll
+  for (int k = 0; k < kAccB; ++k) acc[k] = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.count; i += (size_t)gridDim.x * blockDim.x) {
+    if (!A.nb[i]) continue;
+    const size_t p = A.idx[i];
+    const float Ic = A.inten[i];
+    float jc[kNV];
+#pragma unroll
+    for (int v = 0; v < kNI; ++v) jc[v] = jK[kNI * i + v];
+#pragma unroll
+    for (int v = 0; v < 6; ++v) jc[kNI + v] = jP[6 * i + v];
+    int nj[kMaxNbr]; float In[kMaxNbr];
+#pragma unroll
+    for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) { nj[k] = A.slot[A.nbr[p * A.K + k]]; In[k] = A.inten[nj[k]]; }
+#pragma unroll
+    for (int type = 0; type < 2; ++type) {
+      const float sw = type == 0 ? A.fixed_w : A.var_w;
+      if (!(sw > 0)) continue;
+      if (type == 1 && A.obs_count[p] < 2) continue;
+      const float* desc = type == 0 ? A.fixed_desc : A.var_desc;
+      float comp[kMaxNbr]; float pr = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) { const float c = (In[k] - Ic) - desc[p * A.K + k]; comp[k] = c; pr += c * c; }
+      pr = sqrtf(pr);
+      acc[kNH + kNV + 2 * type] += (double)robust_residual(A.robust, pr);
+      acc[kNH + kNV + 2 * type + 1] += 1.0;
+      const float w = sw * robust_weight(A.robust, pr);
+      if (w != 0) {
+#pragma unroll
+        for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) {
+          float dj[kNV];
+#pragma unroll
+          for (int v = 0; v < kNI; ++v) dj[v] = jK[kNI * (size_t)nj[k] + v] - jc[v];
+#pragma unroll
+          for (int v = 0; v < 6; ++v) dj[kNI + v] = jP[6 * (size_t)nj[k] + v] - jc[kNI + v];
+          int e = 0;
+#pragma unroll
+          for (int c = 0; c < kNV; ++c)
+#pragma unroll
+            for (int r = 0; r <= c; ++r) { acc[e] += (double)((w * dj[r]) * dj[c]); ++e; }
+          const float wr = w * comp[k];
+#pragma unroll
+          for (int v = 0; v < kNV; ++v) acc[kNH + v] += (double)(wr * dj[v]);
+        }
+      }
+    }
+  }
+  __shared__ double sm[4][kAccB];
+  double out;
+  block_reduce_d<kAccB>(acc, sm, 128, &out);
+  if (threadIdx.x < kAccB) partials[(size_t)blockIdx.x * kAccB + threadIdx.x] = out;
+}
+
+// Fixed-order sum of the per-block partials: out[v] = sum_b partials[b][v].
+__global__ void __launch_bounds__(128) kr_reduce_partials(const double* __restrict__ partials, int nblocks, int nvals, double* __restrict__ out) {
+  const int v = threadIdx.x;
+  if (v >= nvals) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * nvals + v];
+  out[v] = s;
+}
+
+// K14 (color_optimizer.cc:84-108): one image at a time; a point has at most one observation per image and scale, so the
+// read-modify-write needs no atomics and images applied in ascending order reproduce the oracle's fp32 sums bit for bit.
+__global__ void __launch_bounds__(256) kr_color_accumulate(size_t count, const unsigned int* __restrict__ idx, const unsigned char* __restrict__ nb,
+                                                           const unsigned int* __restrict__ nbr, int K, const int* __restrict__ slot,
+                                                           const float* __restrict__ inten, float* __restrict__ var_desc, int* __restrict__ obs_count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count || !nb[i]) return;
+  const size_t p = idx[i];
+  const float Ic = inten[i];
+  obs_count[p] += 1;
+  for (int k = 0; k < K; ++k) var_desc[p * K + k] += inten[slot[nbr[p * K + k]]] - Ic;
+}
+__global__ void __launch_bounds__(256) kr_color_mean(size_t n, int K, float* __restrict__ var_desc, const int* __restrict__ obs_count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = obs_count[i];
+  if (c > 1) for (int k = 0; k < K; ++k) var_desc[i * K + k] /= c;
+}
+__global__ void __launch_bounds__(256) kr_fixed_descriptors(size_t n, int K, const unsigned int* __restrict__ nbr, const float* __restrict__ colors,
+                                                            float* __restrict__ fixed_desc, int* __restrict__ obs_count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < K; ++k) fixed_desc[i * K + k] = colors[nbr[i * K + k]] - colors[i];
+  obs_count[i] = 99999;    // problem.cc:570
+}
+
+}  // namespace b2

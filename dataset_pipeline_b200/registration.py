@@ -1,0 +1,224 @@
+"""Host-side mirror of the Path B seams (opt::Problem + opt::Optimizer and the pieces it drives,
+/root/reference/src/opt/optimizer.h:36-57, visibility_estimator.h:46-48, intrinsics_and_pose_optimizer.h:48-51,
+cost_calculator.cc:44-47, color_optimizer.cc:40-43) over the C ABI (b2_reg_*). Method names follow the reference."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class RegParams(C.Structure):
+    _fields_ = [("point_neighbor_count", C.c_int32), ("fixed_residuals_weight", C.c_float), ("variable_residuals_weight", C.c_float),
+                ("robust_weighting_type", C.c_int32), ("robust_weighting_parameter", C.c_float),
+                ("maximum_valid_intensity", C.c_float), ("occlusion_depth_threshold", C.c_float),
+                ("min_occlusion_check_image_scale", C.c_int32), ("max_initial_image_area_in_pixels", C.c_int32),
+                ("splat_radius", C.c_float), ("image_scale_count_override", C.c_int32), ("device", C.c_int32)]
+
+
+class RegStats(C.Structure):
+    _fields_ = [("observations", C.c_uint64), ("residual_evaluations", C.c_uint64), ("kernel_launches", C.c_int32),
+                ("ms_last_call", C.c_float), ("ms_jacobian_kernel", C.c_float), ("ms_accumulate_kernel", C.c_float)]
+
+
+_bound = False
+
+
+def _L():
+    global _bound
+    L = _lib.lib()
+    if _bound:
+        return L
+    fp, ip, dp, vp = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_void_p
+    u8, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
+    L.b2_reg_default_params.argtypes = [C.POINTER(RegParams)]; L.b2_reg_default_params.restype = None
+    L.b2_reg_create.argtypes = [C.POINTER(RegParams), C.POINTER(vp)]
+    L.b2_reg_destroy.argtypes = [vp]
+    L.b2_reg_add_intrinsics.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, C.c_int, ip]
+    L.b2_reg_add_image.argtypes = [vp, C.c_int, u8, u8, fp, ip]
+    L.b2_reg_initialize.argtypes = [vp, ip]
+    L.b2_reg_add_point_scale.argtypes = [vp, fp, C.c_size_t, C.c_float, u64p, fp, ip]
+    L.b2_reg_set_splat_points.argtypes = [vp, fp, C.c_size_t]
+    L.b2_reg_set_depth_map.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp]
+    L.b2_reg_set_image_scale.argtypes = [vp, C.c_int]
+    L.b2_reg_num_variables.argtypes = [vp, ip]
+    L.b2_reg_render_depth.argtypes = [vp, C.c_int, ip, ip, ip, fp]
+    L.b2_reg_create_observations.argtypes = [vp, C.c_int]
+    L.b2_reg_num_observations.argtypes = [vp, C.c_int, C.c_int, u64p]
+    L.b2_reg_get_observations.argtypes = [vp, C.c_int, C.c_int, u64p, fp, fp, fp, u8]
+    L.b2_reg_get_point_jacobians.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp]
+    L.b2_reg_color_update.argtypes = [vp]
+    L.b2_reg_get_descriptors.argtypes = [vp, C.c_int, fp, fp, ip]
+    L.b2_reg_cost.argtypes = [vp, dp, dp]
+    L.b2_reg_accumulate.argtypes = [vp, dp, dp, dp, dp]
+    L.b2_reg_get_state.argtypes = [vp, fp, fp]
+    L.b2_reg_set_state.argtypes = [vp, fp, fp]
+    L.b2_reg_cost_for_delta.argtypes = [vp, dp, dp]
+    L.b2_reg_apply.argtypes = [vp, fp, fp, ip, ip]
+    L.b2_reg_run_on_current_scale.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_int, dp, ip, ip]
+    L.b2_reg_last_stats.argtypes = [vp, C.POINTER(RegStats)]
+    _bound = True
+    return L
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _d(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def default_params(**kw):
+    p = RegParams()
+    _L().b2_reg_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class Registration:
+    """opt::Problem state in HBM + the optimizer pieces. PINHOLE cameras, no rigs (ABI version 1)."""
+
+    def __init__(self, params=None):
+        L = _L()
+        self.params = params or default_params()
+        self._h = C.c_void_p()
+        _lib.check(L.b2_reg_create(C.byref(self.params), C.byref(self._h)))
+        self.K = self.params.point_neighbor_count
+        self.n_intr = 0; self.n_img = 0; self.scale_sizes = []
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            _lib.lib().b2_reg_destroy(self._h); self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- problem set-up (opt::Problem) ----
+    def add_intrinsics(self, width, height, params, camera_model=0):
+        p = np.ascontiguousarray(params, np.float32); out = C.c_int32(0)
+        _lib.check(_L().b2_reg_add_intrinsics(self._h, camera_model, width, height, _f(p), p.size, C.byref(out)))
+        self.n_intr += 1
+        return out.value
+
+    def add_image(self, intrinsics_id, gray, mask, image_T_global):
+        g = np.ascontiguousarray(gray, np.uint8); T = np.ascontiguousarray(image_T_global, np.float32)
+        m = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
+        out = C.c_int32(0)
+        _lib.check(_L().b2_reg_add_image(self._h, intrinsics_id, _u8(g), _u8(m) if m is not None else None, _f(T), C.byref(out)))
+        self.n_img += 1
+        return out.value
+
+    def initialize(self):
+        c = C.c_int32(0)
+        _lib.check(_L().b2_reg_initialize(self._h, C.byref(c)))
+        return c.value
+
+    def add_point_scale(self, xyz, radius, neighbors, colors):
+        xyz = np.ascontiguousarray(xyz, np.float32); nb = np.ascontiguousarray(neighbors, np.uint64); col = np.ascontiguousarray(colors, np.float32)
+        out = C.c_int32(0)
+        _lib.check(_L().b2_reg_add_point_scale(self._h, _f(xyz), xyz.shape[0], radius, nb.ctypes.data_as(C.POINTER(C.c_uint64)), _f(col), C.byref(out)))
+        self.scale_sizes.append(xyz.shape[0])
+        return out.value
+
+    def set_splat_points(self, xyz):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        _lib.check(_L().b2_reg_set_splat_points(self._h, _f(xyz), xyz.shape[0]))
+
+    def set_depth_map(self, image, depth):
+        d = np.ascontiguousarray(depth, np.float32)
+        _lib.check(_L().b2_reg_set_depth_map(self._h, image, d.shape[1], d.shape[0], _f(d)))
+
+    def set_image_scale(self, s):
+        _lib.check(_L().b2_reg_set_image_scale(self._h, s))
+
+    def num_variables(self):
+        n = C.c_int32(0); _lib.check(_L().b2_reg_num_variables(self._h, C.byref(n))); return n.value
+
+    # ---- OcclusionGeometry::RenderDepthMap ----
+    def render_depth(self, image):
+        w, h, s = C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(_L().b2_reg_render_depth(self._h, image, C.byref(w), C.byref(h), C.byref(s), None))
+        out = np.zeros((h.value, w.value), np.float32)
+        _lib.check(_L().b2_reg_render_depth(self._h, image, C.byref(w), C.byref(h), C.byref(s), _f(out)))
+        return out, s.value
+
+    # ---- VisibilityEstimator ----
+    def CreateObservationsForAllImages(self, border_size=1):
+        _lib.check(_L().b2_reg_create_observations(self._h, border_size))
+
+    def observations(self, image, ps):
+        n = C.c_uint64(0)
+        _lib.check(_L().b2_reg_num_observations(self._h, image, ps, C.byref(n)))
+        n = n.value
+        idx = np.zeros(n, np.uint64); x = np.zeros(n, np.float32); y = np.zeros(n, np.float32); s = np.zeros(n, np.float32); nb = np.zeros(n, np.uint8)
+        if n:
+            _lib.check(_L().b2_reg_get_observations(self._h, image, ps, idx.ctypes.data_as(C.POINTER(C.c_uint64)), _f(x), _f(y), _f(s), _u8(nb)))
+        return idx, x, y, s, nb
+
+    def point_jacobians(self, image, ps):
+        n = len(self.observations(image, ps)[0])
+        I = np.zeros(n, np.float32); jK = np.zeros((n, 4), np.float32); jP = np.zeros((n, 6), np.float32)
+        if n:
+            _lib.check(_L().b2_reg_get_point_jacobians(self._h, image, ps, _f(I), _f(jK), _f(jP)))
+        return I, jK, jP
+
+    # ---- ColorOptimizer / CostCalculator / IntrinsicsAndPoseOptimizer ----
+    def ColorOptimizerApply(self):
+        _lib.check(_L().b2_reg_color_update(self._h))
+
+    def descriptors(self, ps):
+        n = self.scale_sizes[ps]
+        f = np.zeros(n * self.K, np.float32); v = np.zeros(n * self.K, np.float32); c = np.zeros(n, np.int32)
+        _lib.check(_L().b2_reg_get_descriptors(self._h, ps, _f(f), _f(v), c.ctypes.data_as(C.POINTER(C.c_int32))))
+        return f, v, c
+
+    def ComputeCost(self):
+        c = C.c_double(0); s = np.zeros(6)
+        _lib.check(_L().b2_reg_cost(self._h, C.byref(c), _d(s)))
+        return c.value, s
+
+    def accumulate(self):
+        nv = self.num_variables()
+        H = np.zeros((nv, nv), np.float64, order="F"); b = np.zeros(nv); s = np.zeros(6); c = C.c_double(0)
+        _lib.check(_L().b2_reg_accumulate(self._h, _d(H), _d(b), _d(s), C.byref(c)))
+        return np.asarray(H), b, s, c.value
+
+    def get_state(self):
+        ip = np.zeros((self.n_intr, 4), np.float32); po = np.zeros((self.n_img, 7), np.float32)
+        _lib.check(_L().b2_reg_get_state(self._h, _f(ip), _f(po)))
+        return ip, po
+
+    def set_state(self, intr_params, poses):
+        ip = np.ascontiguousarray(intr_params, np.float32); po = np.ascontiguousarray(poses, np.float32)
+        _lib.check(_L().b2_reg_set_state(self._h, _f(ip), _f(po)))
+
+    def cost_for_delta(self, delta):
+        d = np.ascontiguousarray(delta, np.float64); c = C.c_double(0)
+        _lib.check(_L().b2_reg_cost_for_delta(self._h, _d(d), C.byref(c)))
+        return c.value
+
+    def IntrinsicsAndPoseOptimizerApply(self, lam):
+        l = C.c_float(lam); mc = C.c_float(0); ap = C.c_int32(0); tr = C.c_int32(0)
+        _lib.check(_L().b2_reg_apply(self._h, C.byref(l), C.byref(mc), C.byref(ap), C.byref(tr)))
+        return bool(ap.value), l.value, mc.value, tr.value
+
+    # ---- Optimizer ----
+    def RunOnCurrentScale(self, max_num_iterations, max_change_convergence_threshold, iterations_without_new_optimum_threshold, print_progress=False):
+        oc = C.c_double(0); cv = C.c_int32(0); it = C.c_int32(0)
+        _lib.check(_L().b2_reg_run_on_current_scale(self._h, max_num_iterations, max_change_convergence_threshold,
+                                                    iterations_without_new_optimum_threshold, int(print_progress), C.byref(oc), C.byref(cv), C.byref(it)))
+        return it.value, oc.value, bool(cv.value)
+
+    def stats(self):
+        s = RegStats()
+        _lib.check(_L().b2_reg_last_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in RegStats._fields_}

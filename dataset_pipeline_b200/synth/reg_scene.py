@@ -1,0 +1,83 @@
+"""Synthetic Path B scene (data generator, not on the product path): a textured plane z = 0 seen by pinhole cameras looking
+down from ~2 m; images are rendered analytically (ray / plane intersection of every pixel, texture = sum of sinusoids); the
+multi-resolution point cloud is a set of regular grids on the plane with the texture as grey colour and 5 grid neighbours."""
+import math
+
+import numpy as np
+
+
+def texture(x, y):
+    v = (np.sin(7.0 * x) * np.cos(5.0 * y) + 0.6 * np.sin(19.0 * x + 1.3) * np.sin(23.0 * y + 0.4) + 0.35 * np.cos(41.0 * x - 29.0 * y)
+         + 0.25 * np.sin(83.0 * x + 61.0 * y))
+    return 120.0 + 45.0 * v
+
+
+def quat_from_R(R):
+    w = math.sqrt(max(0.0, 1 + R[0, 0] + R[1, 1] + R[2, 2])) / 2
+    x = (R[2, 1] - R[1, 2]) / (4 * w); y = (R[0, 2] - R[2, 0]) / (4 * w); z = (R[1, 0] - R[0, 1]) / (4 * w)
+    return np.array([x, y, z, w])
+
+
+def rot(rx, ry, rz):
+    cx, sx, cy, sy, cz, sz = math.cos(rx), math.sin(rx), math.cos(ry), math.sin(ry), math.cos(rz), math.sin(rz)
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]); Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def make_scene(num_images=3, width=640, height=480, fx=520.0, extent=(2.4, 1.8), base_radius=0.0025, num_scales=3, seed=31,
+               perturb=(0.002, 0.002)):
+    """Returns dict(intr=(w,h,[fx,fy,cx,cy]), images=[uint8 HxW], poses_gt, poses_init (qx qy qz qw tx ty tz), scales=[(xyz, radius, nbr, colors)])."""
+    rng = np.random.default_rng(seed)
+    K = np.array([fx, fx, (width - 1) / 2.0, (height - 1) / 2.0], np.float32)
+    images, poses_gt, poses_init = [], [], []
+    for i in range(num_images):
+        # camera centre above the plane, looking down (camera z axis = -world z), small tilts
+        c = np.array([0.25 * math.cos(2.1 * i), 0.2 * math.sin(1.7 * i), 2.0 + 0.1 * math.sin(i)])
+        R_wc = rot(math.pi + 0.08 * math.sin(1.3 * i), 0.07 * math.cos(0.9 * i), 0.3 * i)      # camera-to-world
+        R_cw = R_wc.T; t_cw = -R_cw @ c
+        # render: pixel ray in camera frame -> world -> z=0
+        yy, xx = np.mgrid[0:height, 0:width].astype(np.float64)
+        d_c = np.stack([(xx - K[2]) / K[0], (yy - K[3]) / K[1], np.ones_like(xx)], -1)
+        d_w = d_c @ R_wc.T
+        s = -c[2] / d_w[..., 2]
+        pw = c + d_w * s[..., None]
+        img = np.clip(np.rint(texture(pw[..., 0], pw[..., 1])), 0, 255).astype(np.uint8)
+        images.append(img)
+        q = quat_from_R(R_cw)
+        poses_gt.append(np.concatenate([q, t_cw]).astype(np.float32))
+        dR = rot(*(rng.uniform(-perturb[1], perturb[1], 3))); dt = rng.uniform(-perturb[0], perturb[0], 3)
+        Rp = dR @ R_cw; tp = dR @ t_cw + dt
+        poses_init.append(np.concatenate([quat_from_R(Rp), tp]).astype(np.float32))
+    scales = []
+    for sidx in range(num_scales):
+        radius = base_radius * (2 ** sidx)
+        step = 2 * radius
+        nx = int(extent[0] / step); ny = int(extent[1] / step)
+        gx, gy = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+        x = (gx.ravel() - (nx - 1) / 2.0) * step; y = (gy.ravel() - (ny - 1) / 2.0) * step
+        xyz = np.stack([x, y, np.zeros_like(x)], 1).astype(np.float32)
+        idx = (gy * nx + gx).ravel()
+        def nb(dx, dy):
+            return (np.clip(gy + dy, 0, ny - 1) * nx + np.clip(gx + dx, 0, nx - 1)).ravel()
+        nbr = np.stack([nb(1, 0), nb(-1, 0), nb(0, 1), nb(0, -1), nb(1, 1)], 1).astype(np.uint64)
+        same = nbr == idx[:, None].astype(np.uint64)           # clipped border neighbours: point elsewhere so they differ from the centre
+        alt = np.stack([nb(-2, 0), nb(2, 0), nb(0, -2), nb(0, 2), nb(-1, -1)], 1).astype(np.uint64)
+        nbr = np.where(same, alt, nbr)
+        colors = texture(x, y).astype(np.float32)
+        scales.append((xyz, np.float32(radius), nbr, colors))
+    return {"intr": (width, height, K), "images": images, "poses_gt": poses_gt, "poses_init": poses_init, "scales": scales}
+
+
+def load_into(reg, scene, use_init=True, splats=True):
+    """Feeds a scene into a Registration-like object (product mirror or oracle: same method names)."""
+    w, h, K = scene["intr"]
+    reg.add_intrinsics(w, h, K)
+    for img, T in zip(scene["images"], scene["poses_init"] if use_init else scene["poses_gt"]):
+        reg.add_image(0, img, None, T)
+    count = reg.initialize()
+    for xyz, radius, nbr, colors in scene["scales"]:
+        reg.add_point_scale(xyz, float(radius), nbr, colors)
+    if splats:
+        reg.set_splat_points(scene["scales"][0][0])
+    return count

@@ -76,7 +76,10 @@ typedef struct b2_icp_stats {
   int32_t kernel_launches;      /* kernels of this library launched (this outer iteration) */
   /* device time (ms, CUDA events on the handle's stream) of the last outer iteration */
   float ms_index, ms_search, ms_pack, ms_inner, ms_total;
-  float ms_accum_kernel_avg;    /* average duration of one accumulate-pass kernel */
+  float ms_accum_kernel_avg;    /* average duration of one accumulate-pass kernel (K5) */
+  float ms_search_kernel_avg;   /* average duration of one correspondence-search kernel (K3), one pair-direction */
+  int32_t search_launches;      /* pair-directions searched on this rank */
+  uint64_t search_algorithmic_bytes; /* sum over those launches of 12*Q + 8*Q_matched + 12*T */
 } b2_icp_stats;
 
 void b2_icp_default_config(b2_icp_config* cfg);
@@ -136,6 +139,87 @@ int b2_find_correspondences(const float* src_xyz, size_t n_src, const float* tgt
  * ------------------------------------------------------------------------------------------------------------------ */
 int b2_normals_estimate(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3],
                         float* out_nxyz_curv, int32_t* out_knn_idx, int* is_dense);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Path B — dense photometric image<->scan alignment (tool ImageRegistrator).
+ * Replaces, behind one handle, the pieces opt::Optimizer drives on an opt::Problem (src/opt/optimizer.h:36-57,
+ * optimizer.cc:49-190): VisibilityEstimator::CreateObservationsForAllImages + DetermineIfAllNeighborsAreObserved
+ * (visibility_estimator.h:46-48, .cc:49-91,199-256), ColorOptimizer::Apply (color_optimizer.cc:40-123),
+ * CostCalculator::ComputeCost (cost_calculator.cc:44-100), IntrinsicsAndPoseOptimizer::Apply
+ * (intrinsics_and_pose_optimizer.h:48-51, .cc:48-259), OcclusionGeometry::RenderDepthMap splat path
+ * (occlusion_geometry.cc:404-464) and the image / mask / intrinsics pyramids (image.cc:106-154, intrinsics.cc:45-79).
+ * Scope of this ABI version: PINHOLE cameras (camera_pinhole.h), no rigs, depth residuals off (the reference default,
+ * parameters.h:54); occlusion depth from splats, from a caller-supplied depth map, or none (all visible).
+ * Variable layout of H/b/delta: [4 per intrinsics (fx fy cx cy) | 6 per image (translation, rotation)], ascending ids.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct b2_reg b2_reg;
+
+typedef struct b2_reg_params {   /* mirror of opt::Parameters (src/opt/parameters.h:40-67) as far as Path B reads it */
+  int32_t point_neighbor_count;                 /* 5 */
+  float fixed_residuals_weight, variable_residuals_weight;   /* 1, 1 */
+  int32_t robust_weighting_type;                /* 0 none, 1 Huber (default), 2 Tukey (robust_weighting.h:42-46) */
+  float robust_weighting_parameter;             /* 30*sqrt(5)/sqrt(2) */
+  float maximum_valid_intensity;                /* 252 */
+  float occlusion_depth_threshold;              /* 0.01 */
+  int32_t min_occlusion_check_image_scale;      /* 0 */
+  int32_t max_initial_image_area_in_pixels;     /* 200*160 */
+  float splat_radius;                           /* 0.03 */
+  int32_t image_scale_count_override;           /* 0 = Problem::InitializeImages rule (problem.cc:478-494) */
+  int32_t device;                               /* -1 = current */
+} b2_reg_params;
+
+typedef struct b2_reg_stats {
+  uint64_t observations;            /* over all images and point scales (last create_observations) */
+  uint64_t residual_evaluations;    /* observations through pass 1+2 of the last accumulate (SURVEY §8d definition) */
+  int32_t kernel_launches;          /* kernels of this library launched by the last call */
+  float ms_last_call;               /* device time of the last call (CUDA events) */
+  float ms_jacobian_kernel, ms_accumulate_kernel;   /* of the last accumulate */
+} b2_reg_stats;
+
+void b2_reg_default_params(b2_reg_params* p);
+int b2_reg_create(const b2_reg_params* p, b2_reg** out);
+int b2_reg_destroy(b2_reg* h);
+/* camera_model: 0 = PINHOLE (params fx fy cx cy; COLMAP's -0.5 px shift, colmap_model.cc:833, is the caller's job). */
+int b2_reg_add_intrinsics(b2_reg* h, int camera_model, int width, int height, const float* params, int num_params, int* out_id);
+/* gray: width*height uint8 (cv::imread GRAYSCALE); mask: same size or NULL (values 0/1/2, image.h:43-47);
+ * image_T_global: Sophus::SE3f::data() order qx qy qz qw tx ty tz (what io::ReadColmapImages fills, colmap_model.cc:117-124). */
+int b2_reg_add_image(b2_reg* h, int intrinsics_id, const uint8_t* gray, const uint8_t* mask, const float image_T_global[7], int* out_id);
+/* Problem::InitializeImages + LoadImages pyramids. *image_scale_count receives Problem::image_scale_count(). */
+int b2_reg_initialize(b2_reg* h, int* image_scale_count);
+/* One scale of the multi-resolution point cloud (problem.h points()/point_radius()/neighbor indices) + grey colours from which the
+ * fixed descriptors are derived (problem.cc:550-572). neighbor_indices: n * point_neighbor_count. */
+int b2_reg_add_point_scale(b2_reg* h, const float* xyz, size_t n, float point_radius, const uint64_t* neighbor_indices,
+                           const float* colors, int* out_scale);
+int b2_reg_set_splat_points(b2_reg* h, const float* xyz, size_t n);              /* OcclusionGeometry::SetSplatPoints */
+int b2_reg_set_depth_map(b2_reg* h, int image_id, int width, int height, const float* depth);   /* given occlusion depth */
+int b2_reg_set_image_scale(b2_reg* h, int image_scale);                           /* Problem::SetImageScale */
+int b2_reg_num_variables(b2_reg* h, int* nv);
+/* RenderDepthMap at the occlusion-check scale; out may be NULL to query the size. */
+int b2_reg_render_depth(b2_reg* h, int image_id, int* width, int* height, int* image_scale, float* out);
+int b2_reg_create_observations(b2_reg* h, int border_size);
+int b2_reg_num_observations(b2_reg* h, int image_id, int point_scale, uint64_t* count);
+int b2_reg_get_observations(b2_reg* h, int image_id, int point_scale, uint64_t* point_index, float* x, float* y, float* image_scale,
+                            uint8_t* all_neighbors_observed);
+/* ComputePointIntensityAndJacobians of every observation of (image, scale): intensity[n], j_intrinsics[4n], j_pose[6n]. */
+int b2_reg_get_point_jacobians(b2_reg* h, int image_id, int point_scale, float* intensity, float* j_intrinsics, float* j_pose);
+int b2_reg_color_update(b2_reg* h);
+int b2_reg_get_descriptors(b2_reg* h, int point_scale, float* fixed_desc, float* variable_desc, int32_t* observation_counts);
+/* sums: fixed_sum, n_fixed, variable_sum, n_variable, 0, 0 (the six accumulators of cost_calculator.cc:48-53). */
+int b2_reg_cost(b2_reg* h, double* cost, double sums[6]);
+/* Normal equations of IntrinsicsAndPoseOptimizer::Apply (:102-185): H nv*nv column-major (the Upper view the solver reads,
+ * mirrored), b, sums, *cost = "initial residual". */
+int b2_reg_accumulate(b2_reg* h, double* H, double* b, double sums[6], double* cost);
+int b2_reg_get_state(b2_reg* h, float* intrinsics_params /*4 per intrinsics*/, float* poses /*7 per image*/);
+int b2_reg_set_state(b2_reg* h, const float* intrinsics_params, const float* poses);
+/* ComputeResidualForState for state (+) delta with the current observations' visibility lists frozen (:385-440). */
+int b2_reg_cost_for_delta(b2_reg* h, const double* delta, double* cost);
+/* IntrinsicsAndPoseOptimizer::Apply: LM with multiplicative damping, <=10 tries, last try always applied, signed max_change. */
+int b2_reg_apply(b2_reg* h, float* lambda, float* max_change, int* applied_update, int* lm_tries);
+/* Optimizer::RunOnCurrentScale (optimizer.h:44-50). */
+int b2_reg_run_on_current_scale(b2_reg* h, int max_num_iterations, float max_change_convergence_threshold,
+                                int iterations_without_new_optimum_threshold, int print_progress, double* optimum_cost,
+                                int* converged, int* iterations);
+int b2_reg_last_stats(b2_reg* h, b2_reg_stats* out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,187 @@
+"""Path B parity: every seam of the CUDA path (through the C ABI) against the oracle on the same synthetic scene.
+Integer / index results bit-exact; float results within 1e-5 relative (in practice identical: same fp32 evaluation order)."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def scene():
+    from dataset_pipeline_b200.synth import reg_scene
+    return reg_scene.make_scene(num_images=3)
+
+
+def _pair(oracle, scene, **kw):
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import registration
+    from dataset_pipeline_b200.synth import reg_scene
+    g = b2.Registration(registration.default_params(**kw))
+    o = oracle.Registration(oracle.reg_default_params(**kw))
+    ng = reg_scene.load_into(g, scene); no = reg_scene.load_into(o, scene)
+    assert ng == no
+    return g, o, ng
+
+
+def _obs_equal(g, o, n_img, n_scales, exact_scale=True):
+    total = 0
+    for im in range(n_img):
+        for ps in range(n_scales):
+            gi, gx, gy, gs, gn = g.observations(im, ps)
+            oi, ox, oy, os_, on = o.observations(im, ps)
+            assert np.array_equal(gi, oi), (im, ps)
+            assert np.array_equal(gx, ox) and np.array_equal(gy, oy)
+            assert np.array_equal(gs, os_) if exact_scale else np.allclose(gs, os_, rtol=0, atol=1e-6)
+            assert np.array_equal(gn, on)
+            total += len(gi)
+    return total
+
+
+def test_pyramid_depth_and_observations(oracle, scene):
+    g, o, n = _pair(oracle, scene)
+    assert n == 3
+    for s in (1, 0):
+        g.set_image_scale(s); o.set_image_scale(s)
+        dg, sg = g.render_depth(0); do, so = o.render_depth(0)
+        assert sg == so and np.array_equal(dg, do)            # splat depth map bit-exact (min is order independent)
+        g.CreateObservationsForAllImages(1); o.create_observations(1)
+        assert _obs_equal(g, o, 3, 3) > 50000
+
+
+def test_jacobians_descriptors_cost_normal_equations(oracle, scene):
+    g, o, n = _pair(oracle, scene)
+    g.set_image_scale(1); o.set_image_scale(1)
+    g.CreateObservationsForAllImages(1); o.create_observations(1)
+    # K11: a sample of observations against the oracle's per-observation function
+    I, jK, jP = g.point_jacobians(0, 1)
+    for k in np.linspace(0, len(I) - 1, 300).astype(int):
+        Io, jKo, jPo = o.point_jacobians(0, 1, int(k))
+        assert abs(I[k] - Io) <= 1e-5 * max(1, abs(Io))
+        assert np.allclose(jK[k], jKo, rtol=1e-5, atol=1e-5) and np.allclose(jP[k], jPo, rtol=1e-5, atol=1e-4)
+    # K14
+    g.ColorOptimizerApply(); o.color_update()
+    for ps in range(3):
+        fg, vg, cg = g.descriptors(ps); fo, vo, co = o.descriptors(ps)
+        assert np.array_equal(cg, co) and np.array_equal(fg, fo) and np.array_equal(vg, vo)
+    # B15/B16
+    cg, sg = g.ComputeCost(); co, so = o.cost()
+    assert sg[1] == so[1] and sg[3] == so[3] and sg[1] > 10000
+    assert abs(cg - co) <= 1e-9 * co and rel(sg, so) <= 1e-9
+    # K12
+    Hg, bg, s2, c2 = g.accumulate(); Ho, bo, s2o, c2o = o.accumulate()
+    assert rel(Hg, Ho) <= 1e-5 and rel(bg, bo) <= 1e-5 and abs(c2 - c2o) <= 1e-9 * c2o
+    assert g.stats()["residual_evaluations"] == sum(len(o.observations(im, ps)[0]) for im in range(3) for ps in range(3))
+    # K13: trial state with frozen visibility
+    rng = np.random.default_rng(0)
+    delta = np.concatenate([rng.normal(0, 0.05, 4), rng.normal(0, 5e-4, 18)])
+    assert abs(g.cost_for_delta(delta) - o.cost_for_delta(delta)) <= 1e-9 * co
+
+
+def test_lm_step_and_outer_loop(oracle, scene):
+    g, o, n = _pair(oracle, scene)
+    g.set_image_scale(1); o.set_image_scale(1)
+    g.CreateObservationsForAllImages(1); o.create_observations(1)
+    g.ColorOptimizerApply(); o.color_update()
+    ag = g.IntrinsicsAndPoseOptimizerApply(64.0); ao = o.apply(64.0)
+    assert ag[0] == ao[0] and ag[3] == ao[3] and ag[1] == ao[1]            # applied, LM tries, lambda
+    assert abs(ag[2] - ao[2]) <= 1e-5 * max(1e-3, abs(ao[2]))
+    (ig, pg), (io, po) = g.get_state(), o.get_state()
+    assert rel(ig, io) <= 1e-6 and rel(pg, po) <= 1e-6
+    # full RunOnCurrentScale from a fresh problem
+    g, o, n = _pair(oracle, scene)
+    g.set_image_scale(n - 2); o.set_image_scale(n - 2)
+    itg, cg, vg = g.RunOnCurrentScale(12, 0.0, 5); ito, co, vo = o.run_on_current_scale(12, 0.0, 5)
+    assert itg == ito and vg == vo
+    assert abs(cg - co) <= 1e-5 * co
+    (ig, pg), (io, po) = g.get_state(), o.get_state()
+    assert rel(ig, io) <= 1e-5 and rel(pg, po) <= 1e-5
+    assert cg < 0.5 * 24.0          # the alignment actually improves the photometric cost
+
+
+def test_masks_given_depth_and_options(oracle, scene):
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import registration
+    from dataset_pipeline_b200.synth import reg_scene
+    kw = dict(point_neighbor_count=3, robust_weighting_type=2, robust_weighting_parameter=25.0, variable_residuals_weight=0.0)
+    g = b2.Registration(registration.default_params(**kw)); o = oracle.Registration(oracle.reg_default_params(**kw))
+    w, h, K = scene["intr"]
+    mask = np.zeros((h, w), np.uint8); mask[100:200, 150:400] = 1; mask[300:340, 20:80] = 2
+    sat = scene["images"][1].copy(); sat[50:120, 500:620] = 255
+    for r in (g, o):
+        r.add_intrinsics(w, h, K)
+        r.add_image(0, scene["images"][0], mask, scene["poses_init"][0])
+        r.add_image(0, sat, None, scene["poses_init"][1])
+        r.initialize()
+        for xyz, radius, nbr, colors in scene["scales"]:
+            r.add_point_scale(xyz, float(radius), nbr[:, :3], colors)
+    # a given depth map that occludes the left half of image 0
+    g.set_image_scale(1); o.set_image_scale(1)
+    dm, _ = o.render_depth(0)
+    dm[:] = np.inf; dm[:, : dm.shape[1] // 2] = 0.5
+    g.set_depth_map(0, dm); o.set_depth_map(0, dm)
+    g.CreateObservationsForAllImages(1); o.create_observations(1)
+    n = _obs_equal(g, o, 2, 3)
+    assert n > 10000
+    assert len(g.observations(0, 1)[0]) < len(g.observations(1, 1)[0])
+    cg, sg = g.ComputeCost(); co, so = o.cost()
+    assert sg[3] == 0 and so[3] == 0 and abs(cg - co) <= 1e-9 * co
+    Hg, bg, _, _ = g.accumulate(); Ho, bo, _, _ = o.accumulate()
+    assert rel(Hg, Ho) <= 1e-5 and rel(bg, bo) <= 1e-5
+
+
+def test_ref_jacobian_finite_difference_through_cabi(oracle):
+    """The reference's own unit test (test_intrinsics_and_pose_optimizer.cc:101-336) on the GPU path."""
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import registration
+    from tests.test_oracle_reg import _from_two_vectors, _quat_R
+
+    def make(intr, T, point, radius):
+        r = b2.Registration(registration.default_params(point_neighbor_count=2, robust_weighting_type=2, robust_weighting_parameter=30.0,
+                                                        max_initial_image_area_in_pixels=80 * 60, image_scale_count_override=2))
+        r.add_intrinsics(40, 30, intr)
+        yy, xx = np.mgrid[0:30, 0:40]
+        r.add_image(0, ((xx + 3 * yy) % 256).astype(np.uint8), None, T)
+        assert r.initialize() == 2
+        r.add_point_scale(point[None, :], radius, np.zeros((1, 2), np.uint64), np.zeros(1, np.float32))
+        r.set_splat_points(point[None, :]); r.set_image_scale(0)
+        r.CreateObservationsForAllImages(0)
+        assert len(r.observations(0, 0)[0]) == 1
+        I, jK, jP = r.point_jacobians(0, 0)
+        return float(I[0]), jK[0], jP[0]
+
+    q = _from_two_vectors(np.array([0.1, 0.3, 0.785]), np.array([0.4375, 0.2458, 0.2724])); q /= np.linalg.norm(q)
+    t = np.array([0.89763, 0.789346, 0.21398]); R = _quat_R(q)
+    T = np.concatenate([[-q[0], -q[1], -q[2], q[3]], -(R.T @ t)]).astype(np.float32)
+    intr = np.array([40, 30, 20, 15], np.float32); radius = 0.036
+    for local in ((0.1, 0.23, 2.0), (0.4, 0.67, 2.1), (0.0, 0.0, 1.9)):
+        point = (R @ np.array(local) + t).astype(np.float32)
+        I0, jK, jP = make(intr, T, point, radius)
+        for c in range(4):
+            ip = intr.copy(); ip[c] += 1
+            assert abs(jK[c] - (make(ip, T, point, radius)[0] - I0)) < 1e-3
+        for c in range(6):
+            d = np.zeros(6); d[c] = 2 * radius if c < 2 else 0.002
+            qo, to = oracle.se3_exp_left_mul(d, T[:4], T[4:])
+            assert abs(d[c] * jP[c] - (make(intr, np.concatenate([qo, to]), point, radius)[0] - I0)) < 1e-3
+
+
+def test_reg_error_paths():
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200._lib import B2Error
+    from dataset_pipeline_b200 import registration
+    r = b2.Registration(registration.default_params(image_scale_count_override=3))
+    with pytest.raises(B2Error):
+        r.add_intrinsics(64, 48, [50, 50, 32, 24], camera_model=7)      # only PINHOLE in ABI v1
+    with pytest.raises(B2Error):
+        r.initialize()                                                  # nothing added yet
+    r.add_intrinsics(70, 50, [50, 50, 32, 24])
+    r.add_image(0, np.zeros((50, 70), np.uint8), None, [0, 0, 0, 1, 0, 0, 0])
+    with pytest.raises(B2Error):
+        r.initialize()                                                  # 70x50 -> 35x25 -> odd parent for a 3rd level
