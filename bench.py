@@ -223,7 +223,8 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=240))
     from dataset_pipeline_b200 import _lib
     if not os.path.exists(_lib.LIB_PATH):
         if rank == 0:
@@ -247,15 +248,27 @@ def run_b200(args):
     t_gen = time.perf_counter() - t_gen
     poses, _ = scene_poses(NS)
     npts = sum(c[0].shape[0] for c in clouds)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-null) stream shared by torch events, NCCL ordering and the library
+    torch.cuda.set_stream(stream)
 
     def allreduce(ptr, count, strm):
+        # the ONE exchange of the data path: sum-allreduce of [H | b | cost | counters] (NCCL over NVLink), completed before returning
         t = torch.as_tensor(_CudaArray(ptr, count), device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        torch.cuda.current_stream().synchronize()
+
+    comm = None
+    if world > 1 and os.environ.get("B2_ALLREDUCE", "nccl") == "nccl":
+        # library-owned NCCL communicator; the 128-byte id travels over torch.distributed
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(b2.Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        comm = b2.Comm(rank, world, bytes(idt.cpu().numpy().tobytes()), device=local)
 
     def make():
-        g = b2.PointToPlaneICP(device=local, rank=rank, world_size=world, allreduce=allreduce if world > 1 else None,
-                               stream=stream.cuda_stream)
+        g = b2.PointToPlaneICP(device=local, rank=rank, world_size=world, allreduce=allreduce if (world > 1 and comm is None) else None,
+                               stream=stream.cuda_stream, comm=comm)
         for (px, pn), T in zip(clouds, poses):
             g.AddPointCloud(px.numpy(), pn.numpy(), T)
         return g

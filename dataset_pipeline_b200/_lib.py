@@ -17,7 +17,7 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void
 class IcpConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("inner_max_iterations", C.c_int32), ("keep_correspondences", C.c_int32),
                 ("rank", C.c_int32), ("world_size", C.c_int32), ("allreduce", ALLREDUCE_FN), ("allreduce_user", C.c_void_p),
-                ("stream", C.c_void_p)]
+                ("stream", C.c_void_p), ("comm", C.c_void_p)]
 
 
 class IcpStats(C.Structure):
@@ -46,6 +46,11 @@ def build(force=False):
 # every symbol include/eth3d_b200.h declares
 EXPORTS = [
     "b2_abi_version",
+    "b2_comm_allreduce_f64",
+    "b2_comm_create",
+    "b2_comm_destroy",
+    "b2_comm_info",
+    "b2_comm_unique_id",
     "b2_device_info",
     "b2_find_correspondences",
     "b2_icp_add_cloud",
@@ -105,6 +110,11 @@ def lib():
     L.b2_last_error.restype = C.c_char_p
     L.b2_abi_version.restype = C.c_int
     L.b2_device_info.argtypes = [ip, C.c_char_p, C.c_size_t, ip, ip, ip]
+    L.b2_comm_unique_id.argtypes = [C.c_char_p]
+    L.b2_comm_create.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.b2_comm_destroy.argtypes = [vp]
+    L.b2_comm_allreduce_f64.argtypes = [vp, vp, C.c_size_t, vp]
+    L.b2_comm_info.argtypes = [vp, ip, ip]
     L.b2_icp_default_config.argtypes = [C.POINTER(IcpConfig)]
     L.b2_icp_default_config.restype = None
     L.b2_icp_create.argtypes = [C.POINTER(IcpConfig), C.POINTER(vp)]

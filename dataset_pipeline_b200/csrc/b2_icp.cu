@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "b2_common.cuh"
@@ -201,7 +202,18 @@ static int run_pass(b2_icp* h, const std::vector<Pose>& poses, bool with_h, int 
   if (h->total_records > 0) {
     B2_CUDA(cudaEventCreate(&e0)); B2_CUDA(cudaEventCreate(&e1));
     B2_CUDA(cudaEventRecord(e0, h->stream));
-    if (with_h)
+    static const bool use_tma = [] { const char* e = getenv("B2_K5"); return !(e && std::string(e) == "ldg"); }();
+    if (with_h && use_tma) {
+      // Blackwell path: record tiles staged by cp.async.bulk + mbarrier (bit-identical results, see k_accumulate_tma)
+      static bool attr_set = false;
+      if (!attr_set) {
+        B2_CUDA(cudaFuncSetAttribute(k_accumulate_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
+        attr_set = true;
+      }
+      k_accumulate_tma<true><<<h->grid_acc, kAccThreads, kTmaSmemBytes, h->stream>>>(h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>(),
+                                                                                   h->segs_dev.as<Segment>(), nseg, h->poses_dev.as<CloudPose>(),
+                                                                                   h->total_records, h->per_cta, h->partials.as<double>());
+    } else if (with_h)
       k_accumulate<true><<<h->grid_acc, kAccThreads, 0, h->stream>>>(h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>(),
                                                                     h->segs_dev.as<Segment>(), nseg, h->poses_dev.as<CloudPose>(),
                                                                     h->total_records, h->per_cta, h->partials.as<double>());
@@ -227,8 +239,15 @@ static int run_pass(b2_icp* h, const std::vector<Pose>& poses, bool with_h, int 
     double* buf = h->eq_dev.as<double>();
     size_t off = 0, cnt = eq_count;
     if (!with_h) { off = (size_t)nv * nv + nv; cnt = 3; }
-    if (h->cfg.allreduce(h->cfg.allreduce_user, buf + off, cnt, (void*)h->stream) != 0)
-      return set_error(B2_ERR_COMM, "allreduce hook failed");
+    if (h->cfg.comm) {
+      B2_TRY(b2_comm_allreduce_f64(h->cfg.comm, buf + off, cnt, (void*)h->stream));   // NCCL on the handle's stream: no host sync
+    } else {
+      // Host-language hook: the buffer is complete before it runs (it may reduce on a stream of its own), and it must have ordered
+      // its result on `stream` (or completed it) before it returns.
+      B2_CUDA(cudaStreamSynchronize(h->stream));
+      if (h->cfg.allreduce(h->cfg.allreduce_user, buf + off, cnt, (void*)h->stream) != 0)
+        return set_error(B2_ERR_COMM, "allreduce hook failed");
+    }
   }
   B2_CUDA(cudaMemcpyAsync(h->pin_eq.p, h->eq_dev.p, eq_count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   B2_CUDA(cudaStreamSynchronize(h->stream));
@@ -521,7 +540,7 @@ int b2_icp_create(const b2_icp_config* cfg, b2_icp** out) {
   b2_icp_config c; b2_icp_default_config(&c);
   if (cfg) c = *cfg;
   if (c.world_size < 1) c.world_size = 1;
-  if (c.world_size > 1 && !c.allreduce) return set_error(B2_ERR_ARG, "world_size > 1 needs an allreduce hook");
+  if (c.world_size > 1 && !c.allreduce && !c.comm) return set_error(B2_ERR_ARG, "world_size > 1 needs a b2_comm or an allreduce hook");
   if (c.rank < 0 || c.rank >= c.world_size) return set_error(B2_ERR_ARG, "rank %d out of range", c.rank);
   std::unique_ptr<b2_icp> h(new b2_icp());
   h->cfg = c;

@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(256) k_hash_ends(const unsigned long long* __r
 // d2 = ((dx*dx)+(dy*dy))+(dz*dz) in fp32 without contraction (FLANN L2_Simple order).
 // Grid cells are >= 2d wide, so every target within d of a query lies in the 2x2x2 block of cells on the query's side of
 // its own cell (per axis: the neighbour across the NEARER face; the farther face is >= cell/2 >= d away). One thread per
-// cell-sorted source point: the 8 table probes are issued together (independent LDG.128), the query's own cell is scanned
-// first and the other seven are skipped when their nearest face is already farther than the best match.
+// cell-sorted source point: the query's own cell is probed and scanned first, the other seven only when their nearest face
+// is not already farther than the best match (most matched queries touch 1-2 cells).
 // Neighbouring threads share cells, so probes and candidate rows are served from L1/L2. Output at the sorted source position.
 // ------------------------------------------------------------------------------------------------------------------
 // Chunk boxes over the cell-sorted points: level 1 = 32 consecutive points (one warp each), level 2 = 32 level-1 boxes.
@@ -228,13 +228,17 @@ __global__ void __launch_bounds__(128) k_nn_radius1(const float4* __restrict__ s
   const float ez = (float)((rz < 0.5 ? rz : 1.0 - rz) * cell * 0.9999);
   const float ex2 = ex * ex * 0.9999f, ey2 = ey * ey * 0.9999f, ez2 = ez * ez * 0.9999f;
 
-  // 8 probes up front: bit0 = x neighbour, bit1 = y, bit2 = z
-  unsigned int cb[8], ce[8];
+  // Own cell first; a neighbour (bit0 = x, bit1 = y, bit2 = z) is probed only if its nearest face is not already farther than the
+  // best match, which removes most of the 8 probes for matched queries.
   const unsigned int mask = (1u << log2size) - 1u;
+  float best = r2;
+  int best_pos = -1;
+  unsigned int best_idx = 0xFFFFFFFFu;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
+    const float lb = ((c & 1) ? ex2 : 0.f) + ((c & 2) ? ey2 : 0.f) + ((c & 4) ? ez2 : 0.f);
+    if (lb > best) continue;
     const int x = cx + ((c & 1) ? sx : 0), y = cy + ((c & 2) ? sy : 0), z = cz + ((c & 4) ? sz : 0);
-    cb[c] = 0; ce[c] = 0;
     if (x < 0 || x >= g.nx || y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
     const unsigned long long key = cell_key(g, x, y, z);
     unsigned int s = hash_slot(key, log2size);
@@ -245,18 +249,7 @@ __global__ void __launch_bounds__(128) k_nn_radius1(const float4* __restrict__ s
       e = __ldg(reinterpret_cast<const uint4*>(table + s));
       k = ((unsigned long long)e.y << 32) | e.x;
     }
-    if (k == key) { cb[c] = e.z; ce[c] = e.w; }
-  }
-  float best = r2;
-  int best_pos = -1;
-  unsigned int best_idx = 0xFFFFFFFFu;
-  scan_cell(tgt, box1, box2, cb[0], ce[0], q, best, best_pos, best_idx);
-#pragma unroll
-  for (int c = 1; c < 8; ++c) {
-    if (cb[c] == ce[c]) continue;
-    const float lb = ((c & 1) ? ex2 : 0.f) + ((c & 2) ? ey2 : 0.f) + ((c & 4) ? ez2 : 0.f);
-    if (lb > best) continue;
-    scan_cell(tgt, box1, box2, cb[c], ce[c], q, best, best_pos, best_idx);
+    if (k == key) scan_cell(tgt, box1, box2, e.z, e.w, q, best, best_pos, best_idx);
   }
   match_pos[j] = best_pos;
   match_d2[j] = best;
@@ -443,6 +436,123 @@ k_accumulate(const float4* __restrict__ ra, const float4* __restrict__ rb, const
     }
     double out;
     block_reduce<NV>(acc, smem, &out);
+    if (threadIdx.x < NV) {
+      const int slot = WITH_H ? threadIdx.x : (kAccVals - 1);
+      partials[((size_t)seg * gridDim.x + blockIdx.x) * kAccVals + slot] = out;
+    }
+    r0 = e;
+    ++seg;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K5 (Blackwell path): the same pass with the record stream staged through shared memory by the bulk-copy engine.
+// One producer lane issues cp.async.bulk (TMA 1-D) copies of 256-record tiles (3 planes x 4 KB) into a ring of stages guarded by
+// full/empty mbarriers; 8 consumer warps read their record with three conflict-free LDS.128 and run the identical arithmetic.
+// The bytes in flight per SM (stages x 12 KB x 2 CTAs) are decoupled from the consumers' register budget, which is what the
+// register-staged variant above runs out of (28 fp64 accumulators per thread). Same record partition, same reduction tree:
+// results are bit-identical to k_accumulate.
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr int kTmaStages = 6;
+static constexpr int kTmaTile = kAccThreads;                       // records per tile
+static constexpr size_t kTmaSmemBytes = (size_t)kTmaStages * 3 * kTmaTile * 16;
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+  unsigned int ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned int bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Walks the tile sequence of one CTA: tiles never straddle a segment ("correspondence set") boundary.
+struct TileCursor {
+  unsigned long long r, seg_end, r_end; int seg;
+  __device__ __forceinline__ bool valid() const { return r < r_end; }
+  __device__ __forceinline__ void settle(const Segment* __restrict__ segs) {      // move to the segment that contains r
+    while (r < r_end) { seg_end = min(r_end, segs[seg].end); if (seg_end > r) break; ++seg; }
+  }
+  __device__ __forceinline__ unsigned int count() const { return (unsigned int)min((unsigned long long)kTmaTile, seg_end - r); }
+  __device__ __forceinline__ void advance(const Segment* __restrict__ segs) { r += count(); if (r >= seg_end) { ++seg; settle(segs); } }
+};
+
+template <bool WITH_H>
+__global__ void __launch_bounds__(kAccThreads, 2)
+k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, const float4* __restrict__ rc,
+                 const Segment* __restrict__ segs, int nseg, const CloudPose* __restrict__ poses, unsigned long long total,
+                 unsigned long long per_cta, double* __restrict__ partials /* [nseg][gridDim.x][kAccVals] */) {
+  constexpr int NV = WITH_H ? kAccVals : 1;
+  extern __shared__ __align__(128) unsigned char tile_smem[];
+  __shared__ double red[kAccThreads / 32][NV];
+  __shared__ __align__(8) unsigned long long full_bar[kTmaStages], empty_bar[kTmaStages];
+  const unsigned long long r_begin = (unsigned long long)blockIdx.x * per_cta;
+  const unsigned long long r_end = min(total, r_begin + per_cta);
+  if (r_begin >= r_end) return;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTmaStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kAccThreads); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int lo = 0, hi = nseg - 1;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (segs[mid].end > r_begin) hi = mid; else lo = mid + 1; }
+  float4* const sa = reinterpret_cast<float4*>(tile_smem);       // stage s: planes at sa + (3*s + p) * kTmaTile
+
+  // Thread 0 doubles as the producer: it keeps kTmaStages-1 tiles in flight ahead of the tile being consumed.
+  TileCursor prod{r_begin, 0, r_end, lo}; unsigned int pit = 0;
+  auto produce = [&]() {
+    const unsigned int s = pit % kTmaStages, cnt = prod.count();
+    if (pit >= (unsigned int)kTmaStages) mbar_wait(&empty_bar[s], ((pit / kTmaStages) - 1) & 1);
+    mbar_expect_tx(&full_bar[s], 3u * cnt * 16u);
+    bulk_g2s(sa + (3 * s + 0) * kTmaTile, ra + prod.r, cnt * 16u, &full_bar[s]);
+    bulk_g2s(sa + (3 * s + 1) * kTmaTile, rb + prod.r, cnt * 16u, &full_bar[s]);
+    bulk_g2s(sa + (3 * s + 2) * kTmaTile, rc + prod.r, cnt * 16u, &full_bar[s]);
+    prod.advance(segs); ++pit;
+  };
+  if (threadIdx.x == 0) {
+    prod.settle(segs);
+    for (int k = 0; k < kTmaStages - 1 && prod.valid(); ++k) produce();
+  }
+
+  unsigned long long r0 = r_begin; int seg = lo; unsigned int it = 0;
+  while (r0 < r_end) {
+    const Segment sg = segs[seg];
+    const unsigned long long e = min(r_end, sg.end);
+    if (e <= r0) { ++seg; continue; }
+    float Rs[9], ts[3], Rt[9], tt[3];
+    load_pose(poses, sg.src, Rs, ts);
+    load_pose(poses, sg.tgt, Rt, tt);
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    for (unsigned long long r = r0; r < e; r += kTmaTile, ++it) {
+      if (threadIdx.x == 0 && prod.valid()) produce();            // refill the stage released one tile ago
+      const unsigned int s = it % kTmaStages, cnt = (unsigned int)min((unsigned long long)kTmaTile, e - r);
+      mbar_wait(&full_bar[s], (it / kTmaStages) & 1);
+      float4 a, b, c;
+      const bool mine = threadIdx.x < cnt;
+      if (mine) { a = sa[(3 * s + 0) * kTmaTile + threadIdx.x]; b = sa[(3 * s + 1) * kTmaTile + threadIdx.x]; c = sa[(3 * s + 2) * kTmaTile + threadIdx.x]; }
+      mbar_arrive(&empty_bar[s]);          // the values are in registers: the stage may be refilled
+      if (mine) {
+        if (WITH_H) accumulate_record(a, b, c, Rs, ts, Rt, tt, acc);
+        else cost_record(a, b, c, Rs, ts, Rt, tt, &acc[0]);
+      }
+    }
+    double out;
+    block_reduce<NV>(acc, red, &out);
     if (threadIdx.x < NV) {
       const int slot = WITH_H ? threadIdx.x : (kAccVals - 1);
       partials[((size_t)seg * gridDim.x + blockIdx.x) * kAccVals + slot] = out;

@@ -25,9 +25,31 @@ def _colmajor(T):
     return np.ascontiguousarray(np.asarray(T, dtype=np.float32).T.reshape(16))
 
 
+class Comm:
+    """Library-owned NCCL communicator (b2_comm_*): one process per GPU; rank 0 creates the id and ships it to the others."""
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.lib().b2_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, rank, world_size, unique_id, device=-1):
+        self._c = C.c_void_p()
+        self.rank, self.world_size = rank, world_size
+        _lib.check(_lib.lib().b2_comm_create(rank, world_size, unique_id, device, C.byref(self._c)))
+
+    def allreduce_f64(self, ptr, count, stream=0):
+        _lib.check(_lib.lib().b2_comm_allreduce_f64(self._c, C.c_void_p(ptr), count, C.c_void_p(stream)))
+
+    def close(self):
+        if getattr(self, "_c", None) is not None and self._c:
+            _lib.lib().b2_comm_destroy(self._c); self._c = None
+
+
 class PointToPlaneICP:
     def __init__(self, device=-1, inner_max_iterations=150, keep_correspondences=False, rank=0, world_size=1,
-                 allreduce=None, stream=None):
+                 allreduce=None, stream=None, comm=None):
         L = _lib.lib()
         cfg = _lib.IcpConfig()
         L.b2_icp_default_config(C.byref(cfg))
@@ -49,6 +71,10 @@ class PointToPlaneICP:
             cfg.allreduce = self._cb
         if stream is not None:
             cfg.stream = C.c_void_p(int(stream))
+        self._comm = comm
+        if comm is not None:
+            cfg.comm = comm._c
+            cfg.rank, cfg.world_size = comm.rank, comm.world_size
         self._h = C.c_void_p()
         _lib.check(L.b2_icp_create(C.byref(cfg), C.byref(self._h)))
 

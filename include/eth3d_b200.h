@@ -53,15 +53,26 @@ typedef struct b2_icp b2_icp;
  * success. NULL = single GPU. The host language supplies NCCL (ncclAllReduce(sum, double) over NVLink). */
 typedef int (*b2_allreduce_fn)(void* user, double* buf_dev, size_t count, void* stream);
 
+/* NCCL communicator owned by the library (one process per GPU). NCCL is bound with dlopen("libnccl.so.2"), i.e. the copy a
+ * PyTorch host already loaded, or the system one. Rank 0 calls b2_comm_unique_id and ships the 128 bytes to the other ranks by
+ * its own means (file, MPI, torch.distributed broadcast); then every rank calls b2_comm_create. */
+typedef struct b2_comm b2_comm;
+int b2_comm_unique_id(unsigned char id[128]);
+int b2_comm_create(int rank, int world_size, const unsigned char id[128], int device, b2_comm** out);
+int b2_comm_destroy(b2_comm* c);
+int b2_comm_allreduce_f64(b2_comm* c, double* buf_dev, size_t count, void* stream);   /* in-place sum, ordered on stream */
+int b2_comm_info(b2_comm* c, int* rank, int* world_size);
+
 typedef struct b2_icp_config {
   int32_t device;               /* CUDA device ordinal; -1 = current device */
   int32_t inner_max_iterations; /* 0 = reference value 150 (icp_point_to_plane.cc:312) */
   int32_t keep_correspondences; /* !=0: keep per-pair (query,match,d2) lists for b2_icp_get_pair_correspondences */
   int32_t rank, world_size;     /* pair-direction sharding: this handle searches/accumulates directions k with
                                    k % world_size == rank; 0/1 = everything */
-  b2_allreduce_fn allreduce;    /* required when world_size > 1 */
+  b2_allreduce_fn allreduce;    /* world_size > 1 needs this hook or `comm` */
   void* allreduce_user;
   void* stream;                 /* cudaStream_t to run on; NULL = a stream owned by the handle */
+  b2_comm* comm;                /* library-owned NCCL communicator (preferred): ncclAllReduce(sum, double) on the handle's stream */
 } b2_icp_config;
 
 typedef struct b2_icp_stats {
