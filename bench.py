@@ -215,6 +215,10 @@ class ClockSampler:
 
 
 def run_b200(args):
+    # stdout must carry exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version banner there) are sent to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -391,7 +395,11 @@ def run_b200(args):
         counts = {"C": mean("num_correspondences"), "n_acc": int(round(mean("inner_iterations"))), "n_cost": int(round(mean("lm_tries_total")))}
         cb = cpu_sample(args, counts)
         out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -93,6 +93,7 @@ EXPORTS = [
     "b2_reg_run_on_current_scale",
     "b2_reg_set_depth_map",
     "b2_reg_set_image_scale",
+    "b2_reg_set_mesh",
     "b2_reg_set_splat_points",
     "b2_reg_set_state",
 ]

@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdio>
 #include <limits>
+#include <map>
 #include <memory>
 #include <vector>
 
@@ -80,6 +81,7 @@ struct b2_reg {
   std::vector<ImageB> images;
   std::vector<ScaleB> pts;
   DevBuf splats; size_t nsplats = 0;
+  DevBuf mesh_v, mesh_f, mesh_fn, mesh_edges, big_list, big_count, depth_masked; size_t mesh_nv = 0, mesh_nf = 0, mesh_ne = 0;
   int image_scale_count = 0, current_image_scale = 0;
   bool initialized = false;
   std::vector<std::vector<ObsSet>> obs;      // [image][scale]
@@ -128,6 +130,38 @@ static int render_depth(b2_reg* h, const ImageB& im, const IntrinsicsB& in, cons
     if (im.gd_w != cam.w || im.gd_h != cam.h)
       return set_error(B2_ERR_ARG, "given depth map is %dx%d but the occlusion-check scale %d is %dx%d", im.gd_w, im.gd_h, image_scale, cam.w, cam.h);
     *out = im.given_depth.as<float>(); return B2_OK;
+  }
+  if (h->nsplats == 0 && h->mesh_nf > 0) {
+    // mesh path (occlusion_geometry.cc:211-270): K8 depth pass + K9 boundary masking
+    const size_t px = (size_t)cam.w * cam.h;
+    B2_TRY(h->depth.ensure(px * 4)); B2_TRY(h->depth_masked.ensure(px * 4));
+    B2_TRY(h->big_list.ensure(std::max<size_t>(h->mesh_nf, 1) * 4)); B2_TRY(h->big_count.ensure(4));
+    const Pose3 P3 = pose3_of(pose);
+    kr_fill_u32<<<divup(px, 256), 256, 0, h->stream>>>(h->depth.as<unsigned int>(), px, 0x7f800000u);
+    B2_CUDA(cudaMemsetAsync(h->big_count.p, 0, 4, h->stream));
+    kr_raster_small<<<divup(h->mesh_nf, 128), 128, 0, h->stream>>>(h->mesh_v.as<float>(), h->mesh_f.as<unsigned int>(), h->mesh_nf, P3, cam,
+                                                                   h->prm.min_occlusion_depth, h->prm.max_occlusion_depth, h->depth.as<unsigned int>(),
+                                                                   h->big_list.as<unsigned int>(), h->big_count.as<unsigned int>());
+    kr_raster_big<<<h->sms * 4, 256, 0, h->stream>>>(h->mesh_v.as<float>(), h->mesh_f.as<unsigned int>(), P3, cam, h->prm.min_occlusion_depth,
+                                                     h->prm.max_occlusion_depth, h->depth.as<unsigned int>(), h->big_list.as<unsigned int>(),
+                                                     h->big_count.as<unsigned int>());
+    const bool mask = h->prm.mask_occlusion_boundaries != 0 && h->mesh_ne > 0;
+    kr_depth_background<<<divup(px, 256), 256, 0, h->stream>>>(h->depth.as<float>(), mask ? h->depth_masked.as<float>() : nullptr, px);
+    h->launches += 4;
+    if (mask) {
+      // image position = global_T_image.translation() = inv(q) * (-t)   (sophus se3.hpp:208-211)
+      Pose inv; inv.q[0] = -pose.q[0]; inv.q[1] = -pose.q[1]; inv.q[2] = -pose.q[2]; inv.q[3] = pose.q[3];
+      Pose neg; neg.t[0] = pose.t[0] * -1.f; neg.t[1] = pose.t[1] * -1.f; neg.t[2] = pose.t[2] * -1.f;
+      const Pose ip = pose_mul(inv, neg);     // ip.t = 0 + inv.q (x) (-t)
+      kr_mask_edges<<<divup(h->mesh_ne, 128), 128, 0, h->stream>>>(h->mesh_edges.as<MeshEdgeDev>(), h->mesh_ne, h->mesh_v.as<float>(), h->mesh_fn.as<float>(),
+                                                                   P3, ip.t[0], ip.t[1], ip.t[2], cam, h->prm.splat_radius, h->depth.as<float>(),
+                                                                   h->depth_masked.as<float>());
+      ++h->launches;
+      *out = h->depth_masked.as<float>();
+    } else {
+      *out = h->depth.as<float>();
+    }
+    return B2_OK;
   }
   if (h->nsplats == 0) { *out = nullptr; return B2_OK; }
   const size_t px = (size_t)cam.w * cam.h;
@@ -439,6 +473,7 @@ void b2_reg_default_params(b2_reg_params* p) {
   p->robust_weighting_type = 1; p->robust_weighting_parameter = (float)(30 * std::sqrt(5.0) / std::sqrt(2.0));
   p->maximum_valid_intensity = 252; p->occlusion_depth_threshold = 0.01f; p->min_occlusion_check_image_scale = 0;
   p->max_initial_image_area_in_pixels = 200 * 160; p->splat_radius = 0.03f; p->image_scale_count_override = 0; p->device = -1;
+  p->min_occlusion_depth = 0.05f; p->max_occlusion_depth = 100.f; p->mask_occlusion_boundaries = 1;
 }
 
 int b2_reg_create(const b2_reg_params* p, b2_reg** out) {
@@ -465,6 +500,7 @@ int b2_reg_destroy(b2_reg* h) {
   for (auto& o : h->trial) free_set(o);
   for (auto& im : h->images) { for (auto& b : im.img) b.release(); for (auto& b : im.mask) b.release(); im.given_depth.release(); }
   for (auto& P : h->pts) for (DevBuf* b : {&P.xyz, &P.nbr, &P.fixed_desc, &P.var_desc, &P.obs_count}) b->release();
+  for (DevBuf* b : {&h->mesh_v, &h->mesh_f, &h->mesh_fn, &h->mesh_edges, &h->big_list, &h->big_count, &h->depth_masked}) b->release();
   for (DevBuf* b : {&h->splats, &h->flags, &h->offs, &h->cx, &h->cy, &h->cs, &h->cub_tmp, &h->depth, &h->partials, &h->results}) b->release();
   h->pin.release();
   for (cudaEvent_t e : {h->ev0, h->ev1, h->evj0, h->evj1, h->eva0, h->eva1}) if (e) cudaEventDestroy(e);
@@ -580,6 +616,79 @@ int b2_reg_add_point_scale(b2_reg* h, const float* xyz, size_t n, float radius, 
   }
   h->pts.push_back(P);
   if (out_scale) *out_scale = (int)h->pts.size() - 1;
+  return B2_OK;
+}
+
+// OcclusionGeometry::AddMesh with compute_edges (occlusion_geometry.cc:87-130) = ComputeEdgeNormalsList + FilterEdgeList (:466-645):
+// face normals, half edges keyed by the sorted vertex pair, and per edge the two outermost faces (or "open").
+int b2_reg_set_mesh(b2_reg* h, const float* vertices, size_t nv, const uint32_t* faces, size_t nf) {
+  REG_ENTER(h);
+  if ((nv && !vertices) || (nf && !faces)) return set_error(B2_ERR_ARG, "null argument");
+  if (nv >= (1ull << 32) || nf >= (1ull << 32)) return set_error(B2_ERR_ARG, "mesh too large");
+  for (size_t i = 0; i < 3 * nf; ++i) if (faces[i] >= nv) return set_error(B2_ERR_ARG, "face index out of range");
+  h->mesh_nv = nv; h->mesh_nf = nf; h->mesh_ne = 0;
+  if (nf == 0) return B2_OK;
+  auto P = [&](uint32_t i, int c) { return vertices[3 * (size_t)i + c]; };
+  auto nrm3 = [](float* a) { const float n = std::sqrt(a[0] * a[0] + (a[1] * a[1] + a[2] * a[2])); a[0] /= n; a[1] /= n; a[2] /= n; };
+  auto dot3f = [](const float* a, const float* b) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); };
+  std::vector<float> fn(3 * nf);
+  typedef std::pair<uint32_t, uint32_t> Key;
+  std::map<Key, std::vector<std::pair<uint32_t, bool>>> half_edges;
+  for (size_t fi = 0; fi < nf; ++fi) {
+    const uint32_t* t = faces + 3 * fi;
+    const float a[3] = {P(t[1], 0) - P(t[0], 0), P(t[1], 1) - P(t[0], 1), P(t[1], 2) - P(t[0], 2)};
+    const float b[3] = {P(t[2], 0) - P(t[0], 0), P(t[2], 1) - P(t[0], 1), P(t[2], 2) - P(t[0], 2)};
+    float n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    nrm3(n);
+    fn[3 * fi] = n[0]; fn[3 * fi + 1] = n[1]; fn[3 * fi + 2] = n[2];
+    for (int k = 0; k < 3; ++k) {
+      uint32_t u = t[k], w = t[(k + 1) % 3];
+      const bool swapped = u > w;
+      if (swapped) std::swap(u, w);
+      half_edges[Key(u, w)].push_back(std::make_pair((uint32_t)fi, swapped));
+    }
+  }
+  std::vector<MeshEdgeDev> edges;
+  for (const auto& kv : half_edges) {
+    const auto& fl = kv.second;
+    MeshEdgeDev e; e.v1 = kv.first.first; e.v2 = kv.first.second; e.f1 = fl[0].first; e.f2 = 0; e.flags = 0;
+    if (fl.size() == 1) { e.flags = 1; edges.push_back(e); continue; }
+    const float ed[3] = {P(e.v2, 0) - P(e.v1, 0), P(e.v2, 1) - P(e.v1, 1), P(e.v2, 2) - P(e.v1, 2)};
+    float s1 = fl[0].second ? -1.f : 1.f, s2 = fl[1].second ? -1.f : 1.f;
+    const float n1v[3] = {fn[3 * e.f1] * s1, fn[3 * e.f1 + 1] * s1, fn[3 * e.f1 + 2] * s1};
+    const uint32_t face2 = fl[1].first;
+    const float n2v[3] = {fn[3 * face2] * s2, fn[3 * face2 + 1] * s2, fn[3 * face2 + 2] * s2};
+    e.f2 = face2;
+    bool opposite = s1 * s2 > 0;
+    float bx[3] = {n1v[0], n1v[1], n1v[2]}; nrm3(bx);
+    float by[3] = {bx[1] * ed[2] - bx[2] * ed[1], bx[2] * ed[0] - bx[0] * ed[2], bx[0] * ed[1] - bx[1] * ed[0]}; nrm3(by);
+    float n1x = 1.f, n1y = 0.f, n2x = dot3f(bx, n2v), n2y = dot3f(by, n2v);
+    if (n2x < 0 && std::fabs(n2y) < 1e-4f) continue;                      // coplanar pair: not an edge (:571-575)
+    bool keep = true;
+    if (fl.size() > 2) {
+      const float c12 = n2y;
+      for (size_t k = 2; k < fl.size(); ++k) {
+        const uint32_t f3 = fl[k].first; const float s3 = fl[k].second ? -1.f : 1.f;
+        const float cn[3] = {fn[3 * f3] * s3, fn[3 * f3 + 1] * s3, fn[3 * f3 + 2] * s3};
+        const float n3x = dot3f(bx, cn), n3y = dot3f(by, cn);
+        const float c13 = n1x * n3y - n1y * n3x, c23 = n2x * n3y - n2y * n3x;
+        const bool sign1 = c13 * c12 > 0, sign2 = c23 * c12 < 0;
+        if (sign1 && !sign2) { n2x = n3x; n2y = n3y; e.f2 = f3; s2 = s3; opposite = s1 * s3 != 1; }
+        else if (sign2 && !sign1) { n1x = n3x; n1y = n3y; e.f1 = f3; s1 = s3; opposite = s3 * s2 != 1; }
+        else if (!sign2) { keep = false; break; }                          // `!sign2 && !sign2` in the reference (:633)
+      }
+    }
+    if (!keep) continue;
+    e.flags = opposite ? 2u : 0u;
+    edges.push_back(e);
+  }
+  h->mesh_ne = edges.size();
+  B2_TRY(h->mesh_v.ensure(nv * 12)); B2_TRY(h->mesh_f.ensure(nf * 12)); B2_TRY(h->mesh_fn.ensure(nf * 12));
+  B2_TRY(h->mesh_edges.ensure(std::max<size_t>(edges.size(), 1) * sizeof(MeshEdgeDev)));
+  B2_CUDA(cudaMemcpy(h->mesh_v.p, vertices, nv * 12, cudaMemcpyHostToDevice));
+  B2_CUDA(cudaMemcpy(h->mesh_f.p, faces, nf * 12, cudaMemcpyHostToDevice));
+  B2_CUDA(cudaMemcpy(h->mesh_fn.p, fn.data(), nf * 12, cudaMemcpyHostToDevice));
+  if (!edges.empty()) B2_CUDA(cudaMemcpy(h->mesh_edges.p, edges.data(), edges.size() * sizeof(MeshEdgeDev), cudaMemcpyHostToDevice));
   return B2_OK;
 }
 

@@ -125,6 +125,162 @@ __global__ void __launch_bounds__(256) kr_splat_depth(const float* __restrict__ 
   for (int y = min_y; y < end_y; ++y) for (int x = min_x; x < end_x; ++x) atomicMin(&depth_bits[(size_t)y * cam.w + x], zb);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// K8: triangle-mesh depth pass — the function of the reference's OpenGL renderer (occlusion_geometry.cc:213-245,
+// opengl/renderer.cc:42-131,745-847,913-974: linear camera z, GL_LEQUAL, no culling, near/far clip, background 0) as a CUDA
+// z-buffer. Rasterisation rule (shared with the oracle, oracle/orc_mesh.h): polygon clipped at z = min_depth in camera space,
+// window coordinates X = fx x/z + cx + 0.5, pixel centres at i + 0.5, edge functions in double with an ownership rule for
+// ties, perspective-correct depth 1 / sum(lambda_i / z_i), minimum kept by atomicMin on the float bits (order independent).
+// Small triangles are rasterised by one thread each; triangles whose pixel bounding box exceeds kBigTriPixels are queued and
+// rasterised by one block each.
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr int kBigTriPixels = 4096;
+
+struct ClippedTri { float x[4], y[4], z[4]; int n; };   // camera-space polygon after near clipping (n = 0, 3 or 4)
+
+__device__ __forceinline__ ClippedTri clip_triangle(const float* __restrict__ v, const unsigned int* __restrict__ f, size_t fi, const Pose3& P,
+                                                    float min_depth) {
+  float px[3], py[3], pz[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { const size_t vi = f[3 * fi + k]; rigid(P, v[3 * vi], v[3 * vi + 1], v[3 * vi + 2], &px[k], &py[k], &pz[k]); }
+  ClippedTri c; c.n = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int k2 = (k + 1) % 3;
+    const bool ain = pz[k] >= min_depth, bin = pz[k2] >= min_depth;
+    if (ain) { c.x[c.n] = px[k]; c.y[c.n] = py[k]; c.z[c.n] = pz[k]; ++c.n; }
+    if (ain != bin) {
+      const float tt = (min_depth - pz[k]) / (pz[k2] - pz[k]);
+      c.x[c.n] = px[k] + tt * (px[k2] - px[k]); c.y[c.n] = py[k] + tt * (py[k2] - py[k]); c.z[c.n] = min_depth; ++c.n;
+    }
+  }
+  if (c.n < 3) c.n = 0;
+  return c;
+}
+
+struct TriSetup { double x0, y0, x1, y1, x2, y2, z0, z1, z2, area; int ix0, ix1, iy0, iy1; bool o0, o1, o2, valid; };
+
+__device__ __forceinline__ bool edge_owns(double dx, double dy) { return dy < 0.0 || (dy == 0.0 && dx > 0.0); }
+
+__device__ __forceinline__ TriSetup setup_triangle(const Cam& c, const ClippedTri& t, int a, int b, int cc) {
+  TriSetup s; s.valid = false;
+  const float X0 = c.fx * (t.x[a] / t.z[a]) + c.cx + 0.5f, Y0 = c.fy * (t.y[a] / t.z[a]) + c.cy + 0.5f;
+  const float X1 = c.fx * (t.x[b] / t.z[b]) + c.cx + 0.5f, Y1 = c.fy * (t.y[b] / t.z[b]) + c.cy + 0.5f;
+  const float X2 = c.fx * (t.x[cc] / t.z[cc]) + c.cx + 0.5f, Y2 = c.fy * (t.y[cc] / t.z[cc]) + c.cy + 0.5f;
+  s.x0 = X0; s.y0 = Y0; s.x1 = X1; s.y1 = Y1; s.x2 = X2; s.y2 = Y2; s.z0 = t.z[a]; s.z1 = t.z[b]; s.z2 = t.z[cc];
+  s.area = (s.x1 - s.x0) * (s.y2 - s.y0) - (s.y1 - s.y0) * (s.x2 - s.x0);
+  if (s.area == 0.0 || !(s.area == s.area)) return s;
+  if (s.area < 0.0) { double q; q = s.x1; s.x1 = s.x2; s.x2 = q; q = s.y1; s.y1 = s.y2; s.y2 = q; q = s.z1; s.z1 = s.z2; s.z2 = q; s.area = -s.area; }
+  const double minx = fmin(s.x0, fmin(s.x1, s.x2)), maxx = fmax(s.x0, fmax(s.x1, s.x2));
+  const double miny = fmin(s.y0, fmin(s.y1, s.y2)), maxy = fmax(s.y0, fmax(s.y1, s.y2));
+  if (!(maxx >= 0.0 && maxy >= 0.0 && minx <= (double)c.w && miny <= (double)c.h)) return s;
+  s.ix0 = max(0, (int)floor(minx - 0.5)); s.ix1 = min(c.w - 1, (int)ceil(maxx - 0.5));
+  s.iy0 = max(0, (int)floor(miny - 0.5)); s.iy1 = min(c.h - 1, (int)ceil(maxy - 0.5));
+  if (s.ix1 < s.ix0 || s.iy1 < s.iy0) return s;
+  s.o0 = edge_owns(s.x2 - s.x1, s.y2 - s.y1); s.o1 = edge_owns(s.x0 - s.x2, s.y0 - s.y2); s.o2 = edge_owns(s.x1 - s.x0, s.y1 - s.y0);
+  s.valid = true;
+  return s;
+}
+
+__device__ __forceinline__ void raster_pixels(const Cam& c, const TriSetup& s, float max_depth, unsigned int* __restrict__ depth_bits, int first, int step) {
+  const int bw = s.ix1 - s.ix0 + 1, total = bw * (s.iy1 - s.iy0 + 1);
+  for (int k = first; k < total; k += step) {
+    const int ix = s.ix0 + k % bw, iy = s.iy0 + k / bw;
+    const double px = ix + 0.5, py = iy + 0.5;
+    const double w0 = (s.x2 - s.x1) * (py - s.y1) - (s.y2 - s.y1) * (px - s.x1);
+    const double w1 = (s.x0 - s.x2) * (py - s.y2) - (s.y0 - s.y2) * (px - s.x2);
+    const double w2 = (s.x1 - s.x0) * (py - s.y0) - (s.y1 - s.y0) * (px - s.x0);
+    if (!((w0 > 0.0 || (w0 == 0.0 && s.o0)) && (w1 > 0.0 || (w1 == 0.0 && s.o1)) && (w2 > 0.0 || (w2 == 0.0 && s.o2)))) continue;
+    const double inv = (w0 / s.area) / s.z0 + (w1 / s.area) / s.z1 + (w2 / s.area) / s.z2;
+    const float z = (float)(1.0 / inv);
+    if (!(z <= max_depth)) continue;
+    atomicMin(&depth_bits[(size_t)iy * c.w + ix], __float_as_uint(z));
+  }
+}
+
+__global__ void __launch_bounds__(128) kr_raster_small(const float* __restrict__ v, const unsigned int* __restrict__ f, size_t nf, Pose3 P, Cam cam,
+                                                       float min_depth, float max_depth, unsigned int* __restrict__ depth_bits,
+                                                       unsigned int* __restrict__ big_list, unsigned int* __restrict__ big_count) {
+  const size_t fi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (fi >= nf) return;
+  const ClippedTri t = clip_triangle(v, f, fi, P, min_depth);
+  if (t.n == 0) return;
+  const TriSetup s0 = setup_triangle(cam, t, 0, 1, 2);
+  TriSetup s1; s1.valid = false;
+  if (t.n == 4) s1 = setup_triangle(cam, t, 0, 2, 3);
+  long long px = 0;
+  if (s0.valid) px += (long long)(s0.ix1 - s0.ix0 + 1) * (s0.iy1 - s0.iy0 + 1);
+  if (s1.valid) px += (long long)(s1.ix1 - s1.ix0 + 1) * (s1.iy1 - s1.iy0 + 1);
+  if (px > kBigTriPixels) { big_list[atomicAdd(big_count, 1u)] = (unsigned int)fi; return; }
+  if (s0.valid) raster_pixels(cam, s0, max_depth, depth_bits, 0, 1);
+  if (s1.valid) raster_pixels(cam, s1, max_depth, depth_bits, 0, 1);
+}
+
+__global__ void __launch_bounds__(256) kr_raster_big(const float* __restrict__ v, const unsigned int* __restrict__ f, Pose3 P, Cam cam, float min_depth,
+                                                     float max_depth, unsigned int* __restrict__ depth_bits, const unsigned int* __restrict__ big_list,
+                                                     const unsigned int* __restrict__ big_count) {
+  for (unsigned int b = blockIdx.x; b < *big_count; b += gridDim.x) {
+    const ClippedTri t = clip_triangle(v, f, big_list[b], P, min_depth);
+    if (t.n == 0) continue;
+    const TriSetup s0 = setup_triangle(cam, t, 0, 1, 2);
+    if (s0.valid) raster_pixels(cam, s0, max_depth, depth_bits, threadIdx.x, blockDim.x);
+    if (t.n == 4) { const TriSetup s1 = setup_triangle(cam, t, 0, 2, 3); if (s1.valid) raster_pixels(cam, s1, max_depth, depth_bits, threadIdx.x, blockDim.x); }
+  }
+}
+
+// inf (nothing drawn) -> 0, the GL clear colour (renderer.cc:766); also seeds the masked copy.
+__global__ void __launch_bounds__(256) kr_depth_background(float* __restrict__ depth, float* __restrict__ copy, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float d = depth[i];
+  if (isinf(d)) { d = 0.f; depth[i] = d; }
+  if (copy) copy[i] = d;
+}
+
+// K9: MaskOutOcclusionBoundaries (occlusion_geometry.cc:284-402). One thread per mesh edge; silhouette test by face-normal signs,
+// splats along the edge; tests read the UNMASKED map `in`, writes (-1) go to `out` (write-write races all store -1: benign).
+struct MeshEdgeDev { unsigned int v1, v2, f1, f2, flags; };   // flags: bit0 open, bit1 opposite_normals
+__global__ void __launch_bounds__(128) kr_mask_edges(const MeshEdgeDev* __restrict__ edges, size_t ne, const float* __restrict__ v,
+                                                     const float* __restrict__ fn, Pose3 P, float ipx, float ipy, float ipz, Cam cam,
+                                                     float splat_radius, const float* __restrict__ in, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ne) return;
+  const MeshEdgeDev e = edges[i];
+  const float e1x = v[3 * (size_t)e.v1], e1y = v[3 * (size_t)e.v1 + 1], e1z = v[3 * (size_t)e.v1 + 2];
+  if (!(e.flags & 1u)) {
+    const float tx = ipx - e1x, ty = ipy - e1y, tz = ipz - e1z;
+    const bool face1 = sum3p(fn[3 * (size_t)e.f1] * tx, fn[3 * (size_t)e.f1 + 1] * ty, fn[3 * (size_t)e.f1 + 2] * tz) > 0;
+    const bool face2 = sum3p(fn[3 * (size_t)e.f2] * tx, fn[3 * (size_t)e.f2 + 1] * ty, fn[3 * (size_t)e.f2 + 2] * tz) > 0;
+    const bool opp = (e.flags & 2u) != 0;
+    if (!((opp && (face1 == face2)) || (face1 != face2 && !opp))) return;
+  }
+  float ax, ay, az; rigid(P, e1x, e1y, e1z, &ax, &ay, &az);
+  if (az <= 0) return;
+  float bx, by, bz; rigid(P, v[3 * (size_t)e.v2], v[3 * (size_t)e.v2 + 1], v[3 * (size_t)e.v2 + 2], &bx, &by, &bz);
+  if (bz <= 0) return;
+  const float dx = bx - ax, dy = by - ay, dz = bz - az;
+  const int count = 1 + min((int)(sqrtf(sum3p(dx * dx, dy * dy, dz * dz)) / splat_radius + 0.5f), 150);
+  for (int k = 0; k < count; ++k) {
+    const float factor = k / (count - 1.0f);
+    const float px = ax + factor * dx, py = ay + factor * dy, pz = az + factor * dz;
+    if (!(pz > 0)) continue;
+    const float nx = px / pz, ny = py / pz;
+    const float ux = cam.fx * nx + cam.cx, uy = cam.fy * ny + cam.cy;
+    const int ix = (int)(ux + 0.5f), iy = (int)(uy + 0.5f);
+    if (!(ux + 0.5f >= 0 && uy + 0.5f >= 0 && ix >= 0 && iy >= 0 && ix < cam.w && iy < cam.h && in[(size_t)iy * cam.w + ix] + 0.05f >= pz)) continue;
+    const float z_inv = 1.f / pz;
+    const float d0 = cam.fx * (1.f * z_inv), d1 = cam.fx * (0.f * z_inv), d2 = cam.fx * (-1.f * nx * z_inv);
+    const float d3 = cam.fy * (0.f * z_inv), d4 = cam.fy * (1.f * z_inv), d5 = cam.fy * (-1.f * ny * z_inv);
+    const float rx = sqrtf(sum3p(d0 * d0, d1 * d1, d2 * d2)) * splat_radius, ry = sqrtf(sum3p(d3 * d3, d4 * d4, d5 * d5)) * splat_radius;
+    const int min_x = max(0, (int)(ix - rx + 0.5)), min_y = max(0, (int)(iy - ry + 0.5));
+    const int end_x = min(cam.w, (int)(ix + rx + 1.5)), end_y = min(cam.h, (int)(iy + ry + 1.5));
+    for (int y = min_y; y < end_y; ++y) for (int x = min_x; x < end_x; ++x) {
+      const float old = in[(size_t)y * cam.w + x];
+      if (old == 0 || old + 0.05f > pz) out[(size_t)y * cam.w + x] = -1.f;
+    }
+  }
+}
+
 // K10. One thread per candidate point (all points of the scale, or the i-th entry of a visibility list).
 struct VisParams {
   Pose3 P; Cam cam; int image_scale;            // camera of the occlusion-check scale

@@ -13,7 +13,8 @@ class RegParams(C.Structure):
                 ("robust_weighting_type", C.c_int32), ("robust_weighting_parameter", C.c_float),
                 ("maximum_valid_intensity", C.c_float), ("occlusion_depth_threshold", C.c_float),
                 ("min_occlusion_check_image_scale", C.c_int32), ("max_initial_image_area_in_pixels", C.c_int32),
-                ("splat_radius", C.c_float), ("image_scale_count_override", C.c_int32), ("device", C.c_int32)]
+                ("splat_radius", C.c_float), ("image_scale_count_override", C.c_int32), ("device", C.c_int32),
+                ("min_occlusion_depth", C.c_float), ("max_occlusion_depth", C.c_float), ("mask_occlusion_boundaries", C.c_int32)]
 
 
 class RegStats(C.Structure):
@@ -39,6 +40,7 @@ def _L():
     L.b2_reg_initialize.argtypes = [vp, ip]
     L.b2_reg_add_point_scale.argtypes = [vp, fp, C.c_size_t, C.c_float, u64p, fp, ip]
     L.b2_reg_set_splat_points.argtypes = [vp, fp, C.c_size_t]
+    L.b2_reg_set_mesh.argtypes = [vp, fp, C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t]
     L.b2_reg_set_depth_map.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp]
     L.b2_reg_set_image_scale.argtypes = [vp, C.c_int]
     L.b2_reg_num_variables.argtypes = [vp, ip]
@@ -132,6 +134,11 @@ class Registration:
     def set_splat_points(self, xyz):
         xyz = np.ascontiguousarray(xyz, np.float32)
         _lib.check(_L().b2_reg_set_splat_points(self._h, _f(xyz), xyz.shape[0]))
+
+    def set_mesh(self, vertices, faces):
+        """OcclusionGeometry::AddMesh: triangle mesh in the global frame ((nv,3) float32, (nf,3) uint32)."""
+        v = np.ascontiguousarray(vertices, np.float32); f = np.ascontiguousarray(faces, np.uint32)
+        _lib.check(_L().b2_reg_set_mesh(self._h, _f(v), v.shape[0], f.ctypes.data_as(C.POINTER(C.c_uint32)), f.shape[0]))
 
     def set_depth_map(self, image, depth):
         d = np.ascontiguousarray(depth, np.float32)

@@ -177,6 +177,8 @@ typedef struct b2_reg_params {   /* mirror of opt::Parameters (src/opt/parameter
   float splat_radius;                           /* 0.03 */
   int32_t image_scale_count_override;           /* 0 = Problem::InitializeImages rule (problem.cc:478-494) */
   int32_t device;                               /* -1 = current */
+  float min_occlusion_depth, max_occlusion_depth;   /* 0.05, 100: near / far clip of the mesh depth pass (parameters.h:60-61) */
+  int32_t mask_occlusion_boundaries;            /* 1: RenderDepthMap's default (occlusion_geometry.h:86) */
 } b2_reg_params;
 
 typedef struct b2_reg_stats {
@@ -202,6 +204,10 @@ int b2_reg_initialize(b2_reg* h, int* image_scale_count);
 int b2_reg_add_point_scale(b2_reg* h, const float* xyz, size_t n, float point_radius, const uint64_t* neighbor_indices,
                            const float* colors, int* out_scale);
 int b2_reg_set_splat_points(b2_reg* h, const float* xyz, size_t n);              /* OcclusionGeometry::SetSplatPoints */
+/* OcclusionGeometry::AddMesh with edges (occlusion_geometry.cc:87-130,466-645): triangle mesh in the global frame. The depth pass
+ * (the reference's OpenGL render, :213-245) is a CUDA z-buffer, followed by MaskOutOcclusionBoundaries (:284-402). Splats, when
+ * set, take precedence (as in RenderDepthMap, :196-211). */
+int b2_reg_set_mesh(b2_reg* h, const float* vertices, size_t num_vertices, const uint32_t* faces, size_t num_faces);
 int b2_reg_set_depth_map(b2_reg* h, int image_id, int width, int height, const float* depth);   /* given occlusion depth */
 int b2_reg_set_image_scale(b2_reg* h, int image_scale);                           /* Problem::SetImageScale */
 int b2_reg_num_variables(b2_reg* h, int* nv);

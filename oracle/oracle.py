@@ -215,7 +215,8 @@ class RegParams(C.Structure):
                 ("robust_weighting_type", C.c_int32), ("robust_weighting_parameter", C.c_float),
                 ("maximum_valid_intensity", C.c_float), ("occlusion_depth_threshold", C.c_float),
                 ("min_occlusion_check_image_scale", C.c_int32), ("max_initial_image_area_in_pixels", C.c_int32),
-                ("splat_radius", C.c_float), ("image_scale_count_override", C.c_int32)]
+                ("splat_radius", C.c_float), ("image_scale_count_override", C.c_int32),
+                ("min_occlusion_depth", C.c_float), ("max_occlusion_depth", C.c_float), ("mask_occlusion_boundaries", C.c_int32)]
 
 
 _reg_bound = False
@@ -236,6 +237,9 @@ def _bind_reg():
     L.orc_reg_initialize.argtypes = [vp]
     L.orc_reg_add_point_scale.argtypes = [vp, fp, C.c_size_t, C.c_float, u64p, fp]
     L.orc_reg_set_splat_points.argtypes = [vp, fp, C.c_size_t]
+    L.orc_reg_set_mesh.argtypes = [vp, fp, C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t]
+    L.orc_reg_mesh_edges.argtypes = [vp] + [C.POINTER(C.c_uint32)] * 4 + [u8]
+    L.orc_reg_mesh_edges.restype = C.c_uint64
     L.orc_reg_set_depth_map.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp]
     L.orc_reg_set_image_scale.argtypes = [vp, C.c_int]
     L.orc_reg_image_scale_count.argtypes = [vp]
@@ -312,6 +316,16 @@ class Registration:
 
     def set_splat_points(self, xyz):
         xyz = _c32(xyz); lib().orc_reg_set_splat_points(self._h, _f(xyz), xyz.shape[0])
+
+    def set_mesh(self, vertices, faces):
+        v = _c32(vertices); f = np.ascontiguousarray(faces, np.uint32)
+        lib().orc_reg_set_mesh(self._h, _f(v), v.shape[0], f.ctypes.data_as(C.POINTER(C.c_uint32)), f.shape[0])
+
+    def mesh_edges(self):
+        n = lib().orc_reg_mesh_edges(self._h, None, None, None, None, None)
+        a = [np.zeros(n, np.uint32) for _ in range(4)]; fl = np.zeros(n, np.uint8)
+        lib().orc_reg_mesh_edges(self._h, *[x.ctypes.data_as(C.POINTER(C.c_uint32)) for x in a], _u8(fl))
+        return a[0], a[1], a[2], a[3], fl
 
     def set_depth_map(self, image, depth):
         d = _c32(depth); lib().orc_reg_set_depth_map(self._h, image, d.shape[1], d.shape[0], _f(d))

@@ -64,6 +64,8 @@ typedef struct orc_reg_params {   /* mirror of opt::Parameters (src/opt/paramete
   int32_t min_occlusion_check_image_scale, max_initial_image_area_in_pixels;
   float splat_radius;
   int32_t image_scale_count_override;   /* >0: force Problem::image_scale_count_ (tests do this through friend helpers) */
+  float min_occlusion_depth, max_occlusion_depth;   /* 0.05, 100 (parameters.h:60-61) */
+  int32_t mask_occlusion_boundaries;    /* RenderDepthMap default true (occlusion_geometry.h:86) */
 } orc_reg_params;
 void orc_reg_default_params(orc_reg_params*);
 orc_reg* orc_reg_create(const orc_reg_params*);
@@ -74,6 +76,8 @@ int orc_reg_add_image(orc_reg*, int intrinsics_id, const uint8_t* gray, const ui
 int orc_reg_initialize(orc_reg*);
 int orc_reg_add_point_scale(orc_reg*, const float* xyz, size_t n, float radius, const uint64_t* neighbor_indices, const float* colors);
 void orc_reg_set_splat_points(orc_reg*, const float* xyz, size_t n);
+void orc_reg_set_mesh(orc_reg*, const float* vertices, size_t nv, const uint32_t* faces, size_t nf);
+uint64_t orc_reg_mesh_edges(orc_reg*, uint32_t* v1, uint32_t* v2, uint32_t* f1, uint32_t* f2, uint8_t* flags);
 int orc_reg_set_depth_map(orc_reg*, int image, int w, int h, const float* depth);
 void orc_reg_set_image_scale(orc_reg*, int image_scale);
 int orc_reg_image_scale_count(orc_reg*);

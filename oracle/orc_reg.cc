@@ -30,6 +30,7 @@
 
 #include "orc_api.h"
 #include "orc_math.h"
+#include "orc_mesh.h"
 
 namespace orc {
 
@@ -158,6 +159,7 @@ struct orc_reg {
   State st;
   std::vector<ScalePoints> pts;
   std::vector<float> splat_xyz; bool has_splats = false;
+  OccMesh mesh; bool has_mesh = false;
   int image_scale_count = 0, current_image_scale = 0;
   // observations: [image][point_scale]
   std::vector<std::vector<std::vector<Observation>>> obs;
@@ -198,8 +200,20 @@ static ImgF render_depth(const orc_reg* h, const Intrinsics& intr, const Image& 
   const Pinhole& cam = intr.model(image_scale);
   ImgF out; out.w = cam.w; out.h = cam.h; out.d.assign((size_t)cam.w * cam.h, std::numeric_limits<float>::infinity());
   if (im.has_given_depth) return im.given_depth;
-  if (!h->has_splats) return out;
   float R[9]; quat_to_matrix(im.image_T_global.q, R);
+  if (!h->has_splats && h->has_mesh) {
+    // mesh path (occlusion_geometry.cc:211-270): depth pass + MaskOutOcclusionBoundaries; see orc_mesh.h for the rasteriser definition
+    const RasterCam rc{cam.w, cam.h, cam.fx, cam.fy, cam.cx, cam.cy};
+    std::vector<float> raw;
+    raster_mesh(h->mesh, rc, R, im.image_T_global.t, h->prm.min_occlusion_depth, h->prm.max_occlusion_depth, &raw);
+    // image position = global_T_image.translation() = inv(q) * (-t)   (sophus se3.hpp:208-211)
+    const Quat<float> qi{-im.image_T_global.q.x, -im.image_T_global.q.y, -im.image_T_global.q.z, im.image_T_global.q.w};
+    const V3f pos = quat_rotate(qi, V3f{im.image_T_global.t.x * -1.f, im.image_T_global.t.y * -1.f, im.image_T_global.t.z * -1.f});
+    if (h->prm.mask_occlusion_boundaries) mask_boundaries(h->mesh, rc, R, im.image_T_global.t, pos, h->prm.splat_radius, raw, &out.d);
+    else out.d = raw;
+    return out;
+  }
+  if (!h->has_splats) return out;
   const M3f& M = *reinterpret_cast<const M3f*>(R);
   const float max_splat_radius = 10;
   for (size_t i = 0; i < h->splat_xyz.size() / 3; ++i) {
@@ -474,6 +488,7 @@ void orc_reg_default_params(orc_reg_params* p) {
   p->robust_weighting_type = 1; p->robust_weighting_parameter = (float)(30 * sqrt(5) / sqrt(2));
   p->maximum_valid_intensity = 252; p->occlusion_depth_threshold = 0.01f; p->min_occlusion_check_image_scale = 0;
   p->max_initial_image_area_in_pixels = 200 * 160; p->splat_radius = 0.03f; p->image_scale_count_override = 0;
+  p->min_occlusion_depth = 0.05f; p->max_occlusion_depth = 100.f; p->mask_occlusion_boundaries = 1;
 }
 orc_reg* orc_reg_create(const orc_reg_params* p) {
   orc_reg* h = new orc_reg(); h->prm = *p; h->robust.type = p->robust_weighting_type; h->robust.p = p->robust_weighting_parameter; return h;
@@ -527,6 +542,17 @@ int orc_reg_add_point_scale(orc_reg* h, const float* xyz, size_t n, float radius
       P.obs_count[i] = 99999;
     }
   h->pts.push_back(std::move(P)); return (int)h->pts.size() - 1;
+}
+// OcclusionGeometry::AddMesh (occlusion_geometry.cc:87-130) with compute_edges = true. Vertices in the global frame.
+void orc_reg_set_mesh(orc_reg* h, const float* v, size_t nv, const uint32_t* f, size_t nf) {
+  h->mesh.v.assign(v, v + 3 * nv); h->mesh.f.assign(f, f + 3 * nf);
+  build_mesh_edges(&h->mesh);
+  h->has_mesh = nf > 0;
+}
+uint64_t orc_reg_mesh_edges(orc_reg* h, uint32_t* v1, uint32_t* v2, uint32_t* f1, uint32_t* f2, uint8_t* flags) {
+  const auto& E = h->mesh.edges;
+  if (v1) for (size_t i = 0; i < E.size(); ++i) { v1[i] = E[i].v1; v2[i] = E[i].v2; f1[i] = E[i].f1; f2[i] = E[i].f2; flags[i] = (E[i].open ? 1 : 0) | (E[i].opposite ? 2 : 0); }
+  return E.size();
 }
 void orc_reg_set_splat_points(orc_reg* h, const float* xyz, size_t n) { h->splat_xyz.assign(xyz, xyz + 3 * n); h->has_splats = n > 0; }
 int orc_reg_set_depth_map(orc_reg* h, int image, int w, int hh, const float* d) {

@@ -185,3 +185,83 @@ def test_reg_error_paths():
     r.add_image(0, np.zeros((50, 70), np.uint8), None, [0, 0, 0, 1, 0, 0, 0])
     with pytest.raises(B2Error):
         r.initialize()                                                  # 70x50 -> 35x25 -> odd parent for a 3rd level
+
+
+def _grid_mesh(x0, x1, y0, y1, z, n, tilt=0.0):
+    xs = np.linspace(x0, x1, n + 1); ys = np.linspace(y0, y1, n + 1)
+    X, Y = np.meshgrid(xs, ys, indexing="xy")
+    V = np.stack([X.ravel(), Y.ravel(), z + tilt * X.ravel()], 1).astype(np.float32)
+    F = []
+    for j in range(n):
+        for i in range(n):
+            a = j * (n + 1) + i; b = a + 1; c = a + n + 1; d = c + 1
+            F += [[a, b, d], [a, d, c]]
+    return V, np.array(F, np.uint32)
+
+
+def _box_mesh(c, h):
+    x, y, z = c
+    V = np.array([[x + sx * h, y + sy * h, z + sz * h] for sz in (-1, 1) for sy in (-1, 1) for sx in (-1, 1)], np.float32)
+    F = np.array([[0, 1, 3], [0, 3, 2], [4, 7, 5], [4, 6, 7], [0, 5, 1], [0, 4, 5], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4], [1, 5, 7], [1, 7, 3]], np.uint32)
+    return V, F
+
+
+def test_mesh_depth_pass_and_boundary_masking(oracle, scene):
+    """K8/K9: CUDA z-buffer + occlusion-boundary masking against the oracle's software rasteriser (bit-exact), including
+    near-plane clipping (a ground plane passing under the camera), big and small triangles, and a closed box (silhouette edges)."""
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import registration
+    V1, F1 = _grid_mesh(-6, 6, -5, 5, 3.0, 3, tilt=0.15)           # few, huge triangles (block-rasterised)
+    V2, F2 = _grid_mesh(-0.6, 0.7, -0.5, 0.4, 2.0, 40)             # many small ones
+    V3, F3 = _box_mesh((0.9, -0.6, 1.6), 0.2)
+    Vg = np.array([[-5, 0.8, -2], [5, 0.8, -2], [5, 0.8, 8], [-5, 0.8, 8]], np.float32); Fg = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)   # crosses z=0
+    V = np.concatenate([V1, V2, V3, Vg]); F = np.concatenate([F1, F2 + len(V1), F3 + len(V1) + len(V2), Fg + len(V1) + len(V2) + len(V3)])
+    q = np.array([0.03, -0.05, 0.02, 1.0]); q /= np.linalg.norm(q)
+    T = np.concatenate([q, [0.05, -0.02, 0.1]]).astype(np.float32)
+    for mask_flag in (1, 0):
+        kw = dict(image_scale_count_override=2, mask_occlusion_boundaries=mask_flag)
+        g = b2.Registration(registration.default_params(**kw)); o = oracle.Registration(oracle.reg_default_params(**kw))
+        for r in (g, o):
+            r.add_intrinsics(640, 480, [520, 515, 319.5, 239.5])
+            r.add_image(0, np.zeros((480, 640), np.uint8), None, T)
+            r.initialize(); r.set_mesh(V, F); r.set_image_scale(0)
+        dg, sg = g.render_depth(0); do, so = o.render_depth(0)
+        assert sg == so
+        assert np.array_equal(dg, do)
+        assert (do > 0).sum() > 100000
+        if mask_flag:
+            assert (do == -1).sum() > 1000                           # silhouettes of the box / small plane / open borders were masked
+        else:
+            assert (do < 0).sum() == 0
+    # analytic check of the rasteriser itself: untilted plane at z = 2 seen by an identity camera -> depth exactly 2 inside
+    g = b2.Registration(registration.default_params(image_scale_count_override=2, mask_occlusion_boundaries=0))
+    g.add_intrinsics(320, 240, [260, 260, 159.5, 119.5]); g.add_image(0, np.zeros((240, 320), np.uint8), None, [0, 0, 0, 1, 0, 0, 0])
+    g.initialize(); Vp, Fp = _grid_mesh(-0.5, 0.5, -0.4, 0.4, 2.0, 7); g.set_mesh(Vp, Fp); g.set_image_scale(0)
+    d, _ = g.render_depth(0)
+    inside = d[d > 0]
+    assert len(inside) > 20000 and np.abs(inside - 2.0).max() < 1e-6
+    # pixel coverage = the projected rectangle (pixel centres strictly inside), GL pixel-centre convention
+    xs = np.nonzero((d > 0).any(0))[0]; ys = np.nonzero((d > 0).any(1))[0]
+    assert abs(xs[0] - (159.5 - 65.0)) <= 1 and abs(xs[-1] - (159.5 + 65.0)) <= 1 and abs(ys[0] - (119.5 - 52.0)) <= 1
+
+
+def test_observations_with_mesh_occlusion(oracle, scene):
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import registration
+    from dataset_pipeline_b200.synth import reg_scene
+    g = b2.Registration(); o = oracle.Registration()
+    # the textured plane z=0 itself as occlusion mesh + a box floating above it that hides part of the plane
+    Vp, Fp = _grid_mesh(-1.3, 1.3, -1.0, 1.0, 0.0, 30)
+    Vb, Fb = _box_mesh((0.2, 0.1, 0.5), 0.15)
+    V = np.concatenate([Vp, Vb]); F = np.concatenate([Fp, Fb + len(Vp)])
+    for r in (g, o):
+        reg_scene.load_into(r, scene, splats=False)
+        r.set_mesh(V, F); r.set_image_scale(1)
+    g.CreateObservationsForAllImages(1); o.create_observations(1)
+    n = _obs_equal(g, o, 3, 3)
+    assert n > 30000
+    dg, _ = g.render_depth(1); do, _ = o.render_depth(1)
+    assert np.array_equal(dg, do)
+    # fewer observations than without occlusion geometry
+    g2 = b2.Registration(); reg_scene.load_into(g2, scene, splats=False); g2.set_image_scale(1); g2.CreateObservationsForAllImages(1)
+    assert n < sum(len(g2.observations(im, ps)[0]) for im in range(3) for ps in range(3))
