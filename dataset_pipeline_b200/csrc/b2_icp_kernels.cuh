@@ -199,6 +199,13 @@ __device__ __forceinline__ void scan_cell(const float4* __restrict__ tgt, const 
                                           unsigned int b, unsigned int e, const float4& q, float& best, int& best_pos, unsigned int& best_idx) {
   if (e - b <= 48u) { scan_range(tgt, b, e, q, best, best_pos, best_idx); return; }
   const unsigned int last = e - 1;
+  if (e - b > 2u * kChunk2) {
+    // Very dense cell: a strided sample of 64 candidates first, so that `best` is already tight when the chunk boxes are
+    // tested (a query inside a scanner-zenith cluster would otherwise walk most of its 10^4..10^5 points before any box
+    // could be pruned). Sampled points are real candidates; re-visiting them later changes nothing.
+    const unsigned int stride = (e - b) / 64u;
+    for (unsigned int p = b; p < e; p += stride) scan_range(tgt, p, p + 1, q, best, best_pos, best_idx);
+  }
   for (unsigned int c2 = b / kChunk2; c2 <= last / kChunk2; ++c2) {
     if (e - b > 2u * kChunk2 && dist2_box(q.x, q.y, q.z, box2[c2]) > best) continue;
     const unsigned int c1b = max(b / kChunk1, c2 * 32u), c1e = min(last / kChunk1, c2 * 32u + 31u);
@@ -453,8 +460,8 @@ k_accumulate(const float4* __restrict__ ra, const float4* __restrict__ rb, const
 // register-staged variant above runs out of (28 fp64 accumulators per thread). Same record partition, same reduction tree:
 // results are bit-identical to k_accumulate.
 // ------------------------------------------------------------------------------------------------------------------
-static constexpr int kTmaStages = 6;
-static constexpr int kTmaTile = kAccThreads;                       // records per tile
+static constexpr int kTmaStages = 4;
+static constexpr int kTmaTile = 2 * kAccThreads;                   // records per tile: two per consumer thread
 static constexpr size_t kTmaSmemBytes = (size_t)kTmaStages * 3 * kTmaTile * 16;
 
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
@@ -503,7 +510,7 @@ k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, c
   const unsigned long long r_end = min(total, r_begin + per_cta);
   if (r_begin >= r_end) return;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTmaStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kAccThreads); }
+    for (int s = 0; s < kTmaStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kAccThreads / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -542,14 +549,15 @@ k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, c
       if (threadIdx.x == 0 && prod.valid()) produce();            // refill the stage released one tile ago
       const unsigned int s = it % kTmaStages, cnt = (unsigned int)min((unsigned long long)kTmaTile, e - r);
       mbar_wait(&full_bar[s], (it / kTmaStages) & 1);
-      float4 a, b, c;
-      const bool mine = threadIdx.x < cnt;
-      if (mine) { a = sa[(3 * s + 0) * kTmaTile + threadIdx.x]; b = sa[(3 * s + 1) * kTmaTile + threadIdx.x]; c = sa[(3 * s + 2) * kTmaTile + threadIdx.x]; }
-      mbar_arrive(&empty_bar[s]);          // the values are in registers: the stage may be refilled
-      if (mine) {
-        if (WITH_H) accumulate_record(a, b, c, Rs, ts, Rt, tt, acc);
-        else cost_record(a, b, c, Rs, ts, Rt, tt, &acc[0]);
-      }
+      float4 a0, b0, c0, a1, b1, c1;
+      const bool m0 = threadIdx.x < cnt, m1 = threadIdx.x + kAccThreads < cnt;
+      const float4* st = sa + (3 * s) * kTmaTile;
+      if (m0) { a0 = st[threadIdx.x]; b0 = st[kTmaTile + threadIdx.x]; c0 = st[2 * kTmaTile + threadIdx.x]; }
+      if (m1) { a1 = st[kAccThreads + threadIdx.x]; b1 = st[kTmaTile + kAccThreads + threadIdx.x]; c1 = st[2 * kTmaTile + kAccThreads + threadIdx.x]; }
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[s]);     // this warp's values are in registers: one arrival per warp
+      if (m0) { if (WITH_H) accumulate_record(a0, b0, c0, Rs, ts, Rt, tt, acc); else cost_record(a0, b0, c0, Rs, ts, Rt, tt, &acc[0]); }
+      if (m1) { if (WITH_H) accumulate_record(a1, b1, c1, Rs, ts, Rt, tt, acc); else cost_record(a1, b1, c1, Rs, ts, Rt, tt, &acc[0]); }
     }
     double out;
     block_reduce<NV>(acc, red, &out);

@@ -239,7 +239,7 @@ def test_mesh_depth_pass_and_boundary_masking(oracle, scene):
     g.initialize(); Vp, Fp = _grid_mesh(-0.5, 0.5, -0.4, 0.4, 2.0, 7); g.set_mesh(Vp, Fp); g.set_image_scale(0)
     d, _ = g.render_depth(0)
     inside = d[d > 0]
-    assert len(inside) > 20000 and np.abs(inside - 2.0).max() < 1e-6
+    assert len(inside) == 130 * 104 and np.abs(inside - 2.0).max() < 1e-6      # 1.0 x 0.8 m at z = 2 with f = 260
     # pixel coverage = the projected rectangle (pixel centres strictly inside), GL pixel-centre convention
     xs = np.nonzero((d > 0).any(0))[0]; ys = np.nonzero((d > 0).any(1))[0]
     assert abs(xs[0] - (159.5 - 65.0)) <= 1 and abs(xs[-1] - (159.5 + 65.0)) <= 1 and abs(ys[0] - (119.5 - 52.0)) <= 1
