@@ -46,6 +46,7 @@ def build(force=False):
 # every symbol include/eth3d_b200.h declares
 EXPORTS = [
     "b2_abi_version",
+    "b2_camera_eval",
     "b2_comm_allreduce_f64",
     "b2_comm_create",
     "b2_comm_destroy",

@@ -1,0 +1,260 @@
+// Camera models of Path B on the device: projection, its derivatives by the 3-D point and by the intrinsics, and the radius
+// cut-off search the reference runs in every camera constructor (so: for every pyramid level of every LM trial state).
+//
+//   PinholeCamera   (type 4, 4 parameters)   /root/reference/src/camera/camera_pinhole.h:40-86
+//   ThinPrismCamera (type 14, 12 parameters) /root/reference/src/camera/camera_thin_prism.h:56-139
+//   BenchmarkCamera (type 5, 12 parameters)  /root/reference/src/camera/camera_benchmark.cc:36-46 = FisheyeBase<ThinPrismCamera>,
+//                                            /root/reference/src/camera/camera_base_impl_fisheye.h:65-146 (ETH3D's THIN_PRISM_FISHEYE)
+//   shared machinery                         /root/reference/src/camera/camera_base_impl.h:70-89,155-164,214-250,276-328,333-462
+// Arithmetic is written in the reference's evaluation order and the file is built with -fmad=false, so everything except
+// atan() is bit-identical to the CPU; atan(r) is computed in fp64 and rounded (glibc's atanf differs from that by <= 1 ulp
+// and depends on the host CPU's FMA dispatch, so fisheye parity is stated as a tolerance, not bit-exact).
+// K16 kr_cutoff_starts / kr_cutoff_points / kr_cutoff_final: InitCutoff as three kernels (one thread per border pixel and
+// Gauss-Newton start; one thread per border pixel replaying the reference's sequential best / second-best bookkeeping over
+// its 100 starts; one block for the max / min over border pixels).
+#pragma once
+#include "b2_common.cuh"
+
+namespace b2 {
+
+enum { kCamPinhole = 4, kCamBenchmark = 5, kCamThinPrism = 14 };
+static constexpr int kMaxIntrinsics = 12;
+
+struct Cam {
+  int w, h; float fx, fy, cx, cy, fx_inv, fy_inv, cx_inv, cy_inv;
+  int type; float cutoff2, inner_cutoff2;   // radius_cutoff_squared_ of the camera itself / of a fisheye camera's inner model
+  float d[8];                               // k1 k2 p1 p2 k3 k4 sx1 sy1 (zero for pinhole)
+};
+
+__host__ __device__ inline int cam_param_count(int type) { return type == kCamPinhole ? 4 : (type == kCamBenchmark || type == kCamThinPrism) ? 12 : -1; }
+
+// ---- thin-prism distortion (camera_thin_prism.h:56-139) ----
+__device__ __forceinline__ void tp_distort(const float* d, float x, float y, float* ox, float* oy) {
+  const float k1 = d[0], k2 = d[1], p1 = d[2], p2 = d[3], k3 = d[4], k4 = d[5], sx1 = d[6], sy1 = d[7];
+  const float x2 = x * x, xy = x * y, y2 = y * y, r2 = x2 + y2;
+  const float radial = 1 + r2 * (k1 + r2 * (k2 + r2 * (k3 + r2 * k4)));
+  const float dx = 2.f * p1 * xy + p2 * (r2 + 2.f * x2) + sx1 * r2;
+  const float dy = 2.f * p2 * xy + p1 * (r2 + 2.f * y2) + sy1 * r2;
+  *ox = x * radial + dx; *oy = y * radial + dy;
+}
+__device__ __forceinline__ void tp_deriv(const float* d, float nx, float ny, float J[4]) {
+  const float k1 = d[0], k2 = d[1], p1 = d[2], p2 = d[3], k3 = d[4], k4 = d[5], sx1 = d[6], sy1 = d[7];
+  const float nx_ny = nx * ny, nx2 = nx * nx, ny2 = ny * ny, r2 = nx2 + ny2;
+  const float term1 = 2 * k1 + r2 * (4 * k2 + r2 * (6 * k3 + r2 * 8 * k4));
+  const float term2 = 1 + r2 * (k1 + r2 * (k2 + r2 * (k3 + r2 * k4)));
+  const float term3 = nx_ny * term1 + 2 * (p1 * nx + p2 * ny);
+  J[0] = nx2 * term1 + term2 + 6 * p2 * nx + 2 * p1 * ny + 2 * sx1 * nx;
+  J[1] = term3 + 2 * sx1 * ny;
+  J[2] = term3 + 2 * sy1 * nx;
+  J[3] = ny2 * term1 + term2 + 6 * p1 * ny + 2 * p2 * nx + 2 * sy1 * ny;
+}
+__device__ __forceinline__ void tp_deriv_params(float nx, float ny, float D[16]) {
+  const float nx2 = nx * nx, ny2 = ny * ny, two_nx_ny = 2.f * nx * ny, r2 = nx2 + ny2;
+  D[0] = nx * r2; D[1] = D[0] * r2; D[2] = two_nx_ny; D[3] = (r2 + 2.f * nx2); D[4] = D[1] * r2; D[5] = D[4] * r2; D[6] = r2; D[7] = 0;
+  D[8] = ny * r2; D[9] = D[8] * r2; D[10] = (r2 + 2.f * ny2); D[11] = two_nx_ny; D[12] = D[9] * r2; D[13] = D[12] * r2; D[14] = 0; D[15] = r2;
+}
+
+__device__ __forceinline__ float atan_pos(float r) { return (float)atan((double)r); }   // atan2(r, 1.f), r > 0
+
+// Child::Distort
+__device__ __forceinline__ void cam_distort(const Cam& c, float x, float y, float* ox, float* oy) {
+  if (c.type == kCamPinhole) { *ox = x; *oy = y; return; }
+  if (c.type == kCamThinPrism) { tp_distort(c.d, x, y, ox, oy); return; }
+  const float r = sqrtf(x * x + y * y);                                    // camera_base_impl_fisheye.h:65-78
+  if (r > 1e-6f) {
+    const float atan_r = atan_pos(r);
+    if (atan_r * atan_r > c.inner_cutoff2) { *ox = x * INFINITY; *oy = y * INFINITY; return; }
+    const float theta_by_r = atan_r / r;
+    tp_distort(c.d, x * theta_by_r, y * theta_by_r, ox, oy);
+  } else {
+    tp_distort(c.d, x, y, ox, oy);
+  }
+}
+// Child::DistortedDerivativeByNormalized, row-major 2x2
+__device__ __forceinline__ void cam_distort_deriv(const Cam& c, float nx, float ny, float J[4]) {
+  if (c.type == kCamPinhole) { J[0] = 1; J[1] = 0; J[2] = 0; J[3] = 1; return; }
+  if (c.type == kCamThinPrism) { tp_deriv(c.d, nx, ny, J); return; }
+  const float nx_ny = nx * ny, nx2 = nx * nx, ny2 = ny * ny, r2 = nx2 + ny2;   // camera_base_impl_fisheye.h:96-126
+  const float r = sqrtf(r2);
+  if (r > 1e-6f) {
+    const float atan_r = atan_pos(r);
+    if (atan_r * atan_r > c.inner_cutoff2) { J[0] = J[1] = J[2] = J[3] = 0; return; }
+    const float theta_by_r = atan_r / r;
+    const float term1 = r2 * (r2 + 1);
+    const float term2 = theta_by_r / r2;
+    const float a = ny2 * term2 + nx2 / term1;
+    const float b = nx_ny / term1 - nx_ny * term2;
+    const float dd = nx2 * term2 + ny2 / term1;
+    float Jd[4]; tp_deriv(c.d, theta_by_r * nx, theta_by_r * ny, Jd);
+    J[0] = Jd[0] * a + Jd[1] * b; J[1] = Jd[0] * b + Jd[1] * dd;
+    J[2] = Jd[2] * a + Jd[3] * b; J[3] = Jd[2] * b + Jd[3] * dd;
+  } else {
+    tp_deriv(c.d, nx, ny, J);
+  }
+}
+// Child::DistortedDerivativeByDistortionParameters, 2 x 8 row-major (non-pinhole only)
+__device__ __forceinline__ void cam_distort_deriv_params(const Cam& c, float nx, float ny, float D[16]) {
+  if (c.type == kCamThinPrism) { tp_deriv_params(nx, ny, D); return; }
+  const float r = sqrtf(nx * nx + ny * ny);                                // camera_base_impl_fisheye.h:128-146
+  if (r > 1e-6f) {
+    const float atan_r = atan_pos(r);
+    if (atan_r * atan_r > c.inner_cutoff2) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) D[i] = 0;
+      return;
+    }
+    const float theta_by_r = atan_r / r;
+    tp_deriv_params(theta_by_r * nx, theta_by_r * ny, D);
+  } else {
+    tp_deriv_params(nx, ny, D);
+  }
+}
+
+// NormalizedToImage (camera_base_impl.h:155-164)
+__device__ __forceinline__ void cam_project(const Cam& c, float nx, float ny, float* ix, float* iy) {
+  const float r2 = nx * nx + ny * ny;
+  if (isinf(r2) || r2 > c.cutoff2) { *ix = nx * INFINITY; *iy = ny * INFINITY; return; }
+  float dx, dy; cam_distort(c, nx, ny, &dx, &dy);
+  *ix = c.fx * dx + c.cx; *iy = c.fy * dy + c.cy;
+}
+// ImageDerivativeByWorld (camera_base_impl.h:333-360), 2x3 row-major
+__device__ __forceinline__ void cam_d_by_world(const Cam& c, float px, float py, float pz, float o[6]) {
+  const float nx = px / pz, ny = py / pz;
+  if (nx * nx + ny * ny < c.cutoff2) {
+    const float z_inv = 1.f / pz;
+    float J[4]; cam_distort_deriv(c, nx, ny, J);
+    const float N[6] = {1.f * z_inv, 0.f * z_inv, -1.f * nx * z_inv, 0.f * z_inv, 1.f * z_inv, -1.f * ny * z_inv};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      o[k] = c.fx * (J[0] * N[k] + J[1] * N[3 + k]);
+      o[3 + k] = c.fy * (J[2] * N[k] + J[3] * N[3 + k]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o[k] = 0.f;
+  }
+}
+// ImageDerivativeByIntrinsics (camera_base_impl.h:362-408): row 0 in ox[NI], row 1 in oy[NI]
+template <int NI>
+__device__ __forceinline__ void cam_d_by_intrinsics(const Cam& c, float px, float py, float pz, float* ox, float* oy) {
+  const float nx = px / pz, ny = py / pz;
+  if (nx * nx + ny * ny > c.cutoff2) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) { ox[i] = 0.f; oy[i] = 0.f; }
+    return;
+  }
+  float dx, dy; cam_distort(c, nx, ny, &dx, &dy);
+  ox[0] = dx; ox[1] = 0.f; ox[2] = 1.f; ox[3] = 0.f;
+  oy[0] = 0.f; oy[1] = dy; oy[2] = 0.f; oy[3] = 1.f;
+  if (NI > 4) {
+    float D[16]; cam_distort_deriv_params(c, nx, ny, D);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ox[(4 + i) % NI] = c.fx * D[i]; oy[(4 + i) % NI] = c.fy * D[8 + i]; }
+  }
+}
+
+// x86 cvttss2si semantics (INT_MIN for non-finite / out-of-range), which is what the reference's `int ix = f` does on its hosts;
+// CUDA's cast would saturate / map NaN to 0 and let a point beyond the cut-off radius land on pixel 0.
+__device__ __forceinline__ int f2i_x86(float v) { return (v > -2147483904.f && v < 2147483648.f) ? (int)v : (int)0x80000000; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// K16: the thin-prism cut-off search (camera_base_impl.h:214-250 IterativeUndistort, :276-328 UndistortFromInside,
+// :410-462 InitCutoff). `cams` lists the cameras (pyramid levels) to search; border pixel t of camera k:
+//   t < 2w: (t/2, t odd ? h-1 : 0), else u = t-2w: (u odd ? w-1 : 0, u/2)      -- the reference's test_points order
+// ------------------------------------------------------------------------------------------------------------------
+struct CutoffStart { float x, y; int converged; };
+struct CutoffPoint { float r2, s2; int converged, second; };
+
+__device__ __forceinline__ void cutoff_border_pixel(const Cam& c, int t, float* px, float* py) {
+  if (t < 2 * c.w) { *px = (float)(t >> 1); *py = (t & 1) ? (float)(c.h - 1) : 0.f; }
+  else { const int u = t - 2 * c.w; *px = (u & 1) ? (float)(c.w - 1) : 0.f; *py = (float)(u >> 1); }
+}
+
+__global__ void __launch_bounds__(128) kr_cutoff_starts(const Cam* __restrict__ cams, const int* __restrict__ first_point /* [ncam+1] */,
+                                                        int ncam, CutoffStart* __restrict__ out) {
+  const int gp = blockIdx.x;                  // global border-pixel index
+  const int s = threadIdx.x;                  // Gauss-Newton start (100 used)
+  int k = 0;
+  while (k + 1 < ncam && gp >= first_point[k + 1]) ++k;
+  if (s >= 100) return;
+  const Cam c = cams[k];
+  float px, py; cutoff_border_pixel(c, gp - first_point[k], &px, &py);
+  const float tx = c.fx_inv * px + c.cx_inv, ty = c.fy_inv * py + c.cy_inv;
+  const int gy = s / 10, gx = s % 10;
+  const float iy = ty + 1.5f * (gy - 0.5f * 10) / (0.5f * 10);
+  const float ix = tx + 1.5f * (gx - 0.5f * 10) / (0.5f * 10);
+  float ux = ix, uy = iy;
+  int converged = 0;
+  for (int i = 0; i < 100; ++i) {
+    float qx, qy; tp_distort(c.d, ux, uy, &qx, &qy);
+    const float ex = qx - tx, ey = qy - ty;
+    if (ex * ex + ey * ey < 1e-10f) { converged = 1; break; }
+    float J[4]; tp_deriv(c.d, ux, uy, J);
+    const float a = J[0] * J[0] + J[2] * J[2], b = J[0] * J[1] + J[2] * J[3], cc = J[1] * J[0] + J[3] * J[2], dd = J[1] * J[1] + J[3] * J[3];
+    const float invdet = 1.f / (a * dd - cc * b);
+    const float i00 = dd * invdet, i10 = -cc * invdet, i01 = -b * invdet, i11 = a * invdet;
+    const float m00 = i00 * J[0] + i01 * J[2], m01 = i00 * J[1] + i01 * J[3];
+    const float m10 = i10 * J[0] + i11 * J[2], m11 = i10 * J[1] + i11 * J[3];
+    ux -= m00 * ex + m01 * ey;
+    uy -= m10 * ex + m11 * ey;
+  }
+  CutoffStart r; r.x = ux; r.y = uy; r.converged = converged;
+  out[(size_t)gp * 100 + s] = r;
+}
+
+__global__ void __launch_bounds__(128) kr_cutoff_points(const CutoffStart* __restrict__ starts, int npoints, CutoffPoint* __restrict__ out) {
+  const int gp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gp >= npoints) return;
+  const float kImproveThreshold = 0.99f;
+  int converged = 0, second = 0;
+  float best_radius = INFINITY, second_best_radius = INFINITY, bx = 0.f, by = 0.f, sx = INFINITY, sy = INFINITY;
+  for (int s = 0; s < 100; ++s) {
+    const CutoffStart r = starts[(size_t)gp * 100 + s];
+    if (!r.converged) continue;
+    const float radius = sqrtf(r.x * r.x + r.y * r.y);
+    if (radius < kImproveThreshold * best_radius) {
+      second_best_radius = best_radius; sx = bx; sy = by; second = converged;
+      best_radius = radius; bx = r.x; by = r.y; converged = 1;
+    } else if (radius > 1 / kImproveThreshold * best_radius && radius < kImproveThreshold * second_best_radius) {
+      second_best_radius = radius; sx = r.x; sy = r.y; second = 1;
+    }
+  }
+  CutoffPoint p; p.converged = converged; p.second = second; p.r2 = bx * bx + by * by; p.s2 = sx * sx + sy * sy;
+  out[gp] = p;
+}
+
+// one block per camera: radius_cutoff_squared = min(max_p(r2) * 1.01, min_p(s2))
+__global__ void __launch_bounds__(256) kr_cutoff_final(const CutoffPoint* __restrict__ pts, const int* __restrict__ first_point, float* __restrict__ out) {
+  const int k = blockIdx.x;
+  float mx = 0.f, mn = INFINITY;
+  for (int i = first_point[k] + threadIdx.x; i < first_point[k + 1]; i += blockDim.x) {
+    const CutoffPoint p = pts[i];
+    if (p.converged) { mx = fmaxf(p.r2, mx); if (p.second) mn = fminf(p.s2, mn); }
+  }
+  __shared__ float smx[256], smn[256];
+  smx[threadIdx.x] = mx; smn[threadIdx.x] = mn;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { smx[threadIdx.x] = fmaxf(smx[threadIdx.x], smx[threadIdx.x + o]); smn[threadIdx.x] = fminf(smn[threadIdx.x], smn[threadIdx.x + o]); }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[k] = fminf(smx[0] * 1.01f, smn[0]);
+}
+
+// op 1: NormalizedToImage (n x 2 -> n x 2), 2: ImageDerivativeByWorld (n x 3 -> n x 6), 3: ImageDerivativeByIntrinsics (n x 3 -> n x 2np)
+__global__ void __launch_bounds__(128) kr_camera_eval(Cam cam, int op, const float* __restrict__ in, size_t n, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (op == 1) { cam_project(cam, in[2 * i], in[2 * i + 1], &out[2 * i], &out[2 * i + 1]); return; }
+  const float x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
+  if (op == 2) { float d[6]; cam_d_by_world(cam, x, y, z, d); for (int k = 0; k < 6; ++k) out[6 * i + k] = d[k]; return; }
+  if (cam.type == kCamPinhole) {
+    float a[4], b[4]; cam_d_by_intrinsics<4>(cam, x, y, z, a, b);
+    for (int k = 0; k < 4; ++k) { out[8 * i + k] = a[k]; out[8 * i + 4 + k] = b[k]; }
+  } else {
+    float a[12], b[12]; cam_d_by_intrinsics<12>(cam, x, y, z, a, b);
+    for (int k = 0; k < 12; ++k) { out[24 * i + k] = a[k]; out[24 * i + 12 + k] = b[k]; }
+  }
+}
+
+}  // namespace b2

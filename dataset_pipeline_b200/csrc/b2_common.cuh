@@ -117,6 +117,7 @@ struct GridParams {
   double ox, oy, oz;   // origin (bbox min)
   double inv;          // 1 / cell size
   int nx, ny, nz;      // cells per axis (each < 2^21)
+  int fbits;           // bits per axis of the in-cell Morton code appended to the cell key (5..8)
 };
 __host__ __device__ __forceinline__ int cell_of(float v, double o, double inv) {
   return (int)floor(((double)v - o) * inv);
@@ -126,17 +127,25 @@ __host__ __device__ __forceinline__ unsigned long long cell_key(const GridParams
          (unsigned long long)cx;
 }
 
-// Sort key = (cell key << kFineBits) | 15-bit Morton code of the position inside the cell: points of one cell stay contiguous
-// (the hash table is keyed by key >> kFineBits) and are ordered along a space-filling curve, so the per-32 / per-1024 point
-// chunk boxes of dense cells are compact and prune well.
-static constexpr int kFineBits = 15;
-__host__ __device__ __forceinline__ unsigned int spread5(unsigned int v) {   // 5 bits -> every third bit
-  v &= 31u;
-  return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8);
+// Sort key = (cell key << 3*fbits) | Morton code of the position inside the cell (fbits bits per axis): points of one cell
+// stay contiguous (the hash table is keyed by key >> 3*fbits) and are ordered along a space-filling curve, so the per-32 /
+// per-1024 point chunk boxes of dense cells are compact and prune well. fbits = 8 (cell/256 sub-cells) unless the cell key of
+// an enormous sparse scene leaves less room in 63 bits; scanner-zenith clusters (thousands of points within millimetres)
+// need the fine resolution, at 5 bits per axis their chunk boxes all overlapped (r01 profile: one CTA ran 2x the kernel mean).
+static constexpr int kMinFineBits = 5, kMaxFineBits = 8;
+__host__ __device__ __forceinline__ unsigned int spread3(unsigned int v) {   // 10 bits -> every third bit
+  v &= 0x3FFu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
 }
-__host__ __device__ __forceinline__ unsigned int fine_code(double rx, double ry, double rz) {   // r* in [0,1)
-  const int x = min(31, max(0, (int)(rx * 32.0))), y = min(31, max(0, (int)(ry * 32.0))), z = min(31, max(0, (int)(rz * 32.0)));
-  return spread5((unsigned)x) | (spread5((unsigned)y) << 1) | (spread5((unsigned)z) << 2);
+__host__ __device__ __forceinline__ unsigned int fine_code(double rx, double ry, double rz, int fbits) {   // r* in [0,1)
+  const int m = (1 << fbits) - 1;
+  const double s = (double)(1 << fbits);
+  const int x = min(m, max(0, (int)(rx * s))), y = min(m, max(0, (int)(ry * s))), z = min(m, max(0, (int)(rz * s)));
+  return spread3((unsigned)x) | (spread3((unsigned)y) << 1) | (spread3((unsigned)z) << 2);
 }
 
 struct Aabb { float lo[3], hi[3]; };

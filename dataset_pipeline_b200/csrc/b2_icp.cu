@@ -35,7 +35,7 @@ struct Cloud {
 struct Direction {
   int src = 0, tgt = 0;                 // impl cloud indices
   bool local = false;                   // searched / accumulated on this rank
-  DevBuf match, d2, flags, offs;
+  DevBuf match, d2, flags, offs, cta_cost;
   unsigned long long count = 0, rec_begin = 0;
 };
 
@@ -49,6 +49,7 @@ using namespace b2;
 struct b2_icp {
   b2_icp_config cfg;
   int device = 0, sms = 148;
+  bool lpt_order = true;                // K3 CTAs issued longest-first (B2_K3_ORDER=grid disables, for A/B runs)
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::vector<std::unique_ptr<Cloud>> movable;
@@ -121,7 +122,7 @@ static int index_cloud_phase1(b2_icp* h, Cloud* c, const GridParams& g, int key_
                                           c->idx_in.as<unsigned int>(), c->perm.as<unsigned int>(), (long long)n, 0, key_bits, h->stream));
   k_apply<<<div_up(n, 256), 256, 0, h->stream>>>(c->local_xyz.as<float>(), c->local_nrm.as<float>(), n, T, c->perm.as<unsigned int>(),
                                                  c->s_xyz.as<float4>(), c->s_nrm.as<float4>());
-  k_count_cells<<<div_up(n, 256), 256, 0, h->stream>>>(c->keys_out.as<unsigned long long>(), n, h->cell_counts.as<unsigned int>() + slot);
+  k_count_cells<<<div_up(n, 256), 256, 0, h->stream>>>(c->keys_out.as<unsigned long long>(), n, h->cell_counts.as<unsigned int>() + slot, 3 * g.fbits);
   const unsigned int nb1 = div_up(n, kChunk1), nb2 = div_up(nb1, 32);
   B2_TRY(c->box1.ensure(sizeof(Aabb) * nb1)); B2_TRY(c->box2.ensure(sizeof(Aabb) * nb2));
   k_chunk_boxes1<<<div_up((size_t)nb1 * 32, 256), 256, 0, h->stream>>>(c->s_xyz.as<float4>(), n, c->box1.as<Aabb>(), nb1);
@@ -129,7 +130,7 @@ static int index_cloud_phase1(b2_icp* h, Cloud* c, const GridParams& g, int key_
   h->launches += 4;
   return B2_OK;
 }
-static int index_cloud_phase2(b2_icp* h, Cloud* c) {
+static int index_cloud_phase2(b2_icp* h, Cloud* c, const GridParams& g) {
   const size_t n = c->n;
   if (n == 0) return B2_OK;
   int lg = 4;
@@ -137,8 +138,8 @@ static int index_cloud_phase2(b2_icp* h, Cloud* c) {
   c->log2size = lg;
   B2_TRY(c->table.ensure(sizeof(HashEntry) << lg));
   B2_CUDA(cudaMemsetAsync(c->table.p, 0xFF, sizeof(HashEntry) << lg, h->stream));
-  k_hash_insert<<<div_up(n, 256), 256, 0, h->stream>>>(c->keys_out.as<unsigned long long>(), n, c->table.as<HashEntry>(), lg);
-  k_hash_ends<<<div_up(n, 256), 256, 0, h->stream>>>(c->keys_out.as<unsigned long long>(), n, c->table.as<HashEntry>(), lg);
+  k_hash_insert<<<div_up(n, 256), 256, 0, h->stream>>>(c->keys_out.as<unsigned long long>(), n, c->table.as<HashEntry>(), lg, 3 * g.fbits);
+  k_hash_ends<<<div_up(n, 256), 256, 0, h->stream>>>(c->keys_out.as<unsigned long long>(), n, c->table.as<HashEntry>(), lg, 3 * g.fbits);
   h->launches += 2;
   return B2_OK;
 }
@@ -177,7 +178,7 @@ static int compute_grid(b2_icp* h, float max_dist, GridParams* g, int* key_bits)
   g->nx = cell_of(mx[0], g->ox, g->inv) + 1;
   g->ny = cell_of(mx[1], g->oy, g->inv) + 1;
   g->nz = cell_of(mx[2], g->oz, g->inv) + 1;
-  // keep the cell key below 2^47 so that (key << kFineBits) fits 63 bits: enlarge the cells of enormous sparse scenes
+  // keep the cell key below 2^47 so that (key << 3*kMinFineBits) fits 63 bits: enlarge the cells of enormous sparse scenes
   while ((double)g->nx * (double)g->ny * (double)g->nz >= 140737488355328.0) {
     cell *= 2.0; g->inv = 1.0 / cell;
     g->nx = cell_of(mx[0], g->ox, g->inv) + 1; g->ny = cell_of(mx[1], g->oy, g->inv) + 1; g->nz = cell_of(mx[2], g->oz, g->inv) + 1;
@@ -185,7 +186,8 @@ static int compute_grid(b2_icp* h, float max_dist, GridParams* g, int* key_bits)
   const unsigned long long maxkey = cell_key(*g, g->nx - 1, g->ny - 1, g->nz - 1);
   int bits = 1;
   while (bits < 64 && (maxkey >> bits) != 0ull) ++bits;
-  *key_bits = bits + kFineBits;
+  g->fbits = std::max(kMinFineBits, std::min(kMaxFineBits, (63 - bits) / 3));
+  *key_bits = bits + 3 * g->fbits;
   return B2_OK;
 }
 
@@ -301,7 +303,7 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   for (int i = 0; i < nc; ++i) B2_TRY(index_cloud_phase1(h, impl_cloud(h, i), g, key_bits, i));
   B2_CUDA(cudaMemcpyAsync(h->pin_counts.p, h->cell_counts.p, sizeof(unsigned int) * nc, cudaMemcpyDeviceToHost, h->stream));
   B2_CUDA(cudaStreamSynchronize(h->stream));
-  for (int i = 0; i < nc; ++i) { impl_cloud(h, i)->ncells = h->pin_counts.as<unsigned int>()[i]; B2_TRY(index_cloud_phase2(h, impl_cloud(h, i))); }
+  for (int i = 0; i < nc; ++i) { impl_cloud(h, i)->ncells = h->pin_counts.as<unsigned int>()[i]; B2_TRY(index_cloud_phase2(h, impl_cloud(h, i), g)); }
   B2_CUDA(cudaEventRecord(h->ev[1], h->stream));
 
   // ---- pair scheduling in ik order (icp_point_to_plane.cc:208-309); ownership from the shared planner ----
@@ -336,9 +338,38 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
     cudaEvent_t n0 = nullptr, n1 = nullptr;
     B2_CUDA(cudaEventCreate(&n0)); B2_CUDA(cudaEventCreate(&n1));
     B2_CUDA(cudaEventRecord(n0, h->stream));
-    k_nn_radius1<<<div_up(ns, 128), 128, 0, h->stream>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(), T->box2.as<Aabb>(),
-                                                         T->table.as<HashEntry>(),
-                                                         T->log2size, g, r2, d->match.as<int>(), d->d2.as<float>(), d->flags.as<unsigned int>());
+    // longest-first launch order (k_cta_cost + a 10^4..10^5-element radix sort: a few tens of microseconds per direction)
+    const unsigned int ncta = div_up(ns, 128);
+    const unsigned int* order = nullptr;
+    static const bool grid_order = [] { const char* e = getenv("B2_K3_ORDER"); return e && std::string(e) == "grid"; }();
+    if (h->lpt_order && !grid_order && ncta > 4u * (unsigned int)h->sms) {
+      B2_TRY(d->cta_cost.ensure((size_t)ncta * 16));
+      unsigned int* cc = d->cta_cost.as<unsigned int>();
+      k_cta_cost<<<div_up(ncta, 256), 256, 0, h->stream>>>(S->s_xyz.as<float4>(), ns, T->table.as<HashEntry>(), T->log2size, g, ncta, cc, cc + ncta);
+      size_t tmp2 = 0;
+      B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp2, cc, cc + 2 * (size_t)ncta, cc + ncta, cc + 3 * (size_t)ncta, (int)ncta, 0, 32, h->stream));
+      B2_TRY(h->cub_tmp.ensure(tmp2));
+      B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(h->cub_tmp.p, tmp2, cc, cc + 2 * (size_t)ncta, cc + ncta, cc + 3 * (size_t)ncta, (int)ncta, 0, 32, h->stream));
+      order = cc + 3 * (size_t)ncta;
+      h->launches += 2;
+    }
+    const char* work_path = getenv("B2_K3_WORK");   // diagnostic: per-query work counters of every search launch -> <path>.<k>.bin
+    if (work_path && *work_path) {
+      DevBuf wk; B2_TRY(wk.ensure(ns * 16));
+      k_nn_radius1<true><<<div_up(ns, 128), 128, 0, h->stream>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(),
+                                                                 T->box2.as<Aabb>(), T->table.as<HashEntry>(), T->log2size, g, r2,
+                                                                 d->match.as<int>(), d->d2.as<float>(), d->flags.as<unsigned int>(), wk.as<uint4>(), order);
+      std::vector<uint4> hw(ns); std::vector<float4> hq(ns);
+      B2_CUDA(cudaMemcpyAsync(hw.data(), wk.p, ns * 16, cudaMemcpyDeviceToHost, h->stream));
+      B2_CUDA(cudaMemcpyAsync(hq.data(), S->s_xyz.p, ns * 16, cudaMemcpyDeviceToHost, h->stream));
+      B2_CUDA(cudaStreamSynchronize(h->stream));
+      const std::string fn = std::string(work_path) + "." + std::to_string(k) + ".bin";
+      if (FILE* f = fopen(fn.c_str(), "wb")) { fwrite(hq.data(), 16, ns, f); fwrite(hw.data(), 16, ns, f); fclose(f); }
+    } else {
+      k_nn_radius1<false><<<div_up(ns, 128), 128, 0, h->stream>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(),
+                                                                  T->box2.as<Aabb>(), T->table.as<HashEntry>(), T->log2size, g, r2,
+                                                                  d->match.as<int>(), d->d2.as<float>(), d->flags.as<unsigned int>(), nullptr, order);
+    }
     B2_CUDA(cudaEventRecord(n1, h->stream));
     h->nn_events.emplace_back(n0, n1);
     h->stats.search_algorithmic_bytes += 12ull * ns + 12ull * T->n;

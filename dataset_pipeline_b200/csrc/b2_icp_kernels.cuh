@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) k_keys(const float* __restrict__ xyz, siz
   const float3 p = xform_point(T, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
   const double fx = ((double)p.x - g.ox) * g.inv, fy = ((double)p.y - g.oy) * g.inv, fz = ((double)p.z - g.oz) * g.inv;
   const int cx = (int)floor(fx), cy = (int)floor(fy), cz = (int)floor(fz);
-  keys[i] = (cell_key(g, cx, cy, cz) << kFineBits) | fine_code(fx - cx, fy - cy, fz - cz);
+  keys[i] = (cell_key(g, cx, cy, cz) << (3 * g.fbits)) | fine_code(fx - cx, fy - cy, fz - cz, g.fbits);
   idx[i] = (unsigned int)i;
 }
 
@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256) k_transform(const float* __restrict__ xyz
 // ------------------------------------------------------------------------------------------------------------------
 // K2: occupied-cell hash table over the sorted keys. Entry = {key, begin, end} (16 B, one LDG.128 per probe).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_count_cells(const unsigned long long* __restrict__ keys, size_t n, unsigned int* __restrict__ count) {
+__global__ void __launch_bounds__(256) k_count_cells(const unsigned long long* __restrict__ keys, size_t n, unsigned int* __restrict__ count,
+                                                     int kFineBits) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool head = j < n && (j == 0 || (keys[j] >> kFineBits) != (keys[j - 1] >> kFineBits));
   const unsigned int m = __ballot_sync(0xffffffffu, head);
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(256) k_count_cells(const unsigned long long* _
 }
 
 __global__ void __launch_bounds__(256) k_hash_insert(const unsigned long long* __restrict__ keys, size_t n, HashEntry* __restrict__ table,
-                                                     int log2size) {
+                                                     int log2size, int kFineBits) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const unsigned long long key = keys[j] >> kFineBits;
@@ -121,7 +122,7 @@ __device__ __forceinline__ bool hash_find(const HashEntry* __restrict__ table, i
 }
 
 __global__ void __launch_bounds__(256) k_hash_ends(const unsigned long long* __restrict__ keys, size_t n, HashEntry* __restrict__ table,
-                                                   int log2size) {
+                                                   int log2size, int kFineBits) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const unsigned long long key = keys[j] >> kFineBits;
@@ -171,59 +172,107 @@ __global__ void __launch_bounds__(256) k_chunk_boxes2(const Aabb* __restrict__ b
   if (lane == 0) { Aabb b; b.lo[0] = lx; b.lo[1] = ly; b.lo[2] = lz; b.hi[0] = hx; b.hi[1] = hy; b.hi[2] = hz; box2[c] = b; }
 }
 
+struct SearchWork { unsigned int points, box1, box2, cells; };   // per-query work counters of the diagnostic K3 variant (B2_K3_WORK)
+
+// candidate test; ties on d2 go to the lower original target index so the result does not depend on the visiting order
+#define B2_NN_TEST(T, P)                                                                                              \
+  {                                                                                                                   \
+    const float ax_ = fsub(q.x, (T).x), ay_ = fsub(q.y, (T).y), az_ = fsub(q.z, (T).z);                                \
+    const float d_ = fadd(fadd(fmul(ax_, ax_), fmul(ay_, ay_)), fmul(az_, az_));                                      \
+    const unsigned int i_ = __float_as_uint((T).w);                                                                   \
+    if (d_ < best || (d_ == best && best_pos >= 0 && i_ < best_idx)) { best = d_; best_pos = (int)(P); best_idx = i_; } \
+  }
+
 __device__ __forceinline__ void scan_range(const float4* __restrict__ tgt, unsigned int b, unsigned int e, const float4& q, float& best,
-                                           int& best_pos, unsigned int& best_idx) {
+                                           int& best_pos, unsigned int& best_idx, SearchWork& wk) {
+  wk.points += e - b;
   unsigned int p = b;
-  for (; p + 1 < e; p += 2) {   // two candidates in flight
-    const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + p + 1);
-    const float ax = fsub(q.x, t0.x), ay = fsub(q.y, t0.y), az = fsub(q.z, t0.z);
-    const float bx = fsub(q.x, t1.x), by = fsub(q.y, t1.y), bz = fsub(q.z, t1.z);
-    const float d0 = fadd(fadd(fmul(ax, ax), fmul(ay, ay)), fmul(az, az));
-    const float d1 = fadd(fadd(fmul(bx, bx), fmul(by, by)), fmul(bz, bz));
-    const unsigned int i0 = __float_as_uint(t0.w), i1 = __float_as_uint(t1.w);
-    if (d0 < best || (d0 == best && best_pos >= 0 && i0 < best_idx)) { best = d0; best_pos = (int)p; best_idx = i0; }
-    if (d1 < best || (d1 == best && best_pos >= 0 && i1 < best_idx)) { best = d1; best_pos = (int)p + 1; best_idx = i1; }
+  for (; p + 3 < e; p += 4) {   // four candidate loads in flight: the heavy lanes of this kernel are latency bound
+    const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + p + 1), t2 = __ldg(tgt + p + 2), t3 = __ldg(tgt + p + 3);
+    B2_NN_TEST(t0, p) B2_NN_TEST(t1, p + 1) B2_NN_TEST(t2, p + 2) B2_NN_TEST(t3, p + 3)
   }
-  if (p < e) {
+  for (; p < e; ++p) {
     const float4 t0 = __ldg(tgt + p);
-    const float ax = fsub(q.x, t0.x), ay = fsub(q.y, t0.y), az = fsub(q.z, t0.z);
-    const float d0 = fadd(fadd(fmul(ax, ax), fmul(ay, ay)), fmul(az, az));
-    const unsigned int i0 = __float_as_uint(t0.w);
-    if (d0 < best || (d0 == best && best_pos >= 0 && i0 < best_idx)) { best = d0; best_pos = (int)p; best_idx = i0; }
+    B2_NN_TEST(t0, p)
   }
+}
+// candidates p, p+stride, p+2 stride, p+3 stride (those below e)
+__device__ __forceinline__ void scan_strided4(const float4* __restrict__ tgt, unsigned int p, unsigned int stride, unsigned int e, const float4& q,
+                                              float& best, int& best_pos, unsigned int& best_idx, SearchWork& wk) {
+  const unsigned int p1 = p + stride, p2 = p + 2u * stride, p3 = p + 3u * stride;
+  const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + min(p1, e - 1)), t2 = __ldg(tgt + min(p2, e - 1)), t3 = __ldg(tgt + min(p3, e - 1));
+  wk.points += 1u + (p1 < e) + (p2 < e) + (p3 < e);
+  B2_NN_TEST(t0, p)
+  if (p1 < e) B2_NN_TEST(t1, p1)
+  if (p2 < e) B2_NN_TEST(t2, p2)
+  if (p3 < e) B2_NN_TEST(t3, p3)
 }
 
 // One cell's candidates [b,e). Small cells are scanned directly; dense cells (scanner-zenith clusters reach 10^4..10^5 points in
-// one cell) go through the chunk boxes so the work per query stays bounded and the warps stay balanced.
+// one cell) go through the chunk boxes so the work per query stays bounded. What remains expensive is inherent to exact search:
+// a query a few millimetres off a dense slab (range-noise outliers) has to visit every chunk whose box is nearer than its true
+// neighbour — ~10^3 candidates against a mean of ~20 (measured with B2_K3_WORK / tools/k3_work.py). Those lanes are latency
+// bound, so scan_range keeps four candidate loads in flight, and the launch order of the CTAs is longest-first (k_cta_cost).
 __device__ __forceinline__ void scan_cell(const float4* __restrict__ tgt, const Aabb* __restrict__ box1, const Aabb* __restrict__ box2,
-                                          unsigned int b, unsigned int e, const float4& q, float& best, int& best_pos, unsigned int& best_idx) {
-  if (e - b <= 48u) { scan_range(tgt, b, e, q, best, best_pos, best_idx); return; }
+                                          unsigned int b, unsigned int e, const float4& q, float& best, int& best_pos, unsigned int& best_idx,
+                                          SearchWork& wk) {
+  ++wk.cells;
+  if (e - b <= 48u) { scan_range(tgt, b, e, q, best, best_pos, best_idx, wk); return; }
   const unsigned int last = e - 1;
   if (e - b > 2u * kChunk2) {
-    // Very dense cell: a strided sample of 64 candidates first, so that `best` is already tight when the chunk boxes are
-    // tested (a query inside a scanner-zenith cluster would otherwise walk most of its 10^4..10^5 points before any box
-    // could be pruned). Sampled points are real candidates; re-visiting them later changes nothing.
+    // Very dense cell: a strided sample of 64 candidates first (independent loads), so that `best` is already tight when the
+    // chunk boxes are tested. Sampled points are real candidates; re-visiting them later changes nothing.
     const unsigned int stride = (e - b) / 64u;
-    for (unsigned int p = b; p < e; p += stride) scan_range(tgt, p, p + 1, q, best, best_pos, best_idx);
+    for (unsigned int p = b; p < e; p += 4u * stride) scan_strided4(tgt, p, stride, e, q, best, best_pos, best_idx, wk);
   }
   for (unsigned int c2 = b / kChunk2; c2 <= last / kChunk2; ++c2) {
+    ++wk.box2;
     if (e - b > 2u * kChunk2 && dist2_box(q.x, q.y, q.z, box2[c2]) > best) continue;
     const unsigned int c1b = max(b / kChunk1, c2 * 32u), c1e = min(last / kChunk1, c2 * 32u + 31u);
     for (unsigned int c1 = c1b; c1 <= c1e; ++c1) {
+      ++wk.box1;
       if (dist2_box(q.x, q.y, q.z, box1[c1]) > best) continue;
-      scan_range(tgt, max(b, c1 * kChunk1), min(e, (c1 + 1u) * kChunk1), q, best, best_pos, best_idx);
+      scan_range(tgt, max(b, c1 * kChunk1), min(e, (c1 + 1u) * kChunk1), q, best, best_pos, best_idx, wk);
     }
   }
 }
 
+// Launch-order heuristic for K3: estimated cost of each 128-query CTA = target population of the cells of four of its queries.
+// The CTAs are then issued longest-first (the ids sorted by descending cost), so the expensive ones (queries inside scanner-zenith
+// clusters; with the z-major cell key they would otherwise sit at the very end of the grid and run alone) overlap with the rest.
+__global__ void __launch_bounds__(256) k_cta_cost(const float4* __restrict__ src, size_t ns, const HashEntry* __restrict__ table, int log2size,
+                                                  GridParams g, unsigned int ncta, unsigned int* __restrict__ cost, unsigned int* __restrict__ ids) {
+  const unsigned int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncta) return;
+  const unsigned int mask = (1u << log2size) - 1u;
+  unsigned int total = 0;
+  for (int k = 0; k < 4; ++k) {
+    const size_t j = (size_t)c * 128 + 32 * k;
+    if (j >= ns) break;
+    const float4 q = src[j];
+    const int cx = cell_of(q.x, g.ox, g.inv), cy = cell_of(q.y, g.oy, g.inv), cz = cell_of(q.z, g.oz, g.inv);
+    if (cx < 0 || cx >= g.nx || cy < 0 || cy >= g.ny || cz < 0 || cz >= g.nz) continue;
+    const unsigned long long key = cell_key(g, cx, cy, cz);
+    unsigned int s = hash_slot(key, log2size);
+    uint4 e = __ldg(reinterpret_cast<const uint4*>(table + s));
+    unsigned long long kk = ((unsigned long long)e.y << 32) | e.x;
+    while (kk != key && kk != kEmptyKey) { s = (s + 1) & mask; e = __ldg(reinterpret_cast<const uint4*>(table + s)); kk = ((unsigned long long)e.y << 32) | e.x; }
+    if (kk == key) total += e.w - e.z;
+  }
+  cost[c] = total; ids[c] = c;
+}
+
+template <bool STATS>
 __global__ void __launch_bounds__(128) k_nn_radius1(const float4* __restrict__ src, size_t ns, const float4* __restrict__ tgt,
                                                     const Aabb* __restrict__ box1, const Aabb* __restrict__ box2,
                                                     const HashEntry* __restrict__ table, int log2size, GridParams g, float r2,
                                                     int* __restrict__ match_pos, float* __restrict__ match_d2,
-                                                    unsigned int* __restrict__ flags) {
-  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                    unsigned int* __restrict__ flags, uint4* __restrict__ work,
+                                                    const unsigned int* __restrict__ order) {
+  const size_t j = (size_t)(order ? order[blockIdx.x] : blockIdx.x) * blockDim.x + threadIdx.x;
   if (j >= ns) return;
   const float4 q = src[j];
+  SearchWork wk = {0u, 0u, 0u, 0u};
   const double fx = ((double)q.x - g.ox) * g.inv, fy = ((double)q.y - g.oy) * g.inv, fz = ((double)q.z - g.oz) * g.inv;
   const int cx = (int)floor(fx), cy = (int)floor(fy), cz = (int)floor(fz);
   const double rx = fx - cx, ry = fy - cy, rz = fz - cz;               // position inside the cell, [0,1)
@@ -256,8 +305,9 @@ __global__ void __launch_bounds__(128) k_nn_radius1(const float4* __restrict__ s
       e = __ldg(reinterpret_cast<const uint4*>(table + s));
       k = ((unsigned long long)e.y << 32) | e.x;
     }
-    if (k == key) scan_cell(tgt, box1, box2, e.z, e.w, q, best, best_pos, best_idx);
+    if (k == key) scan_cell(tgt, box1, box2, e.z, e.w, q, best, best_pos, best_idx, wk);
   }
+  if (STATS) work[j] = make_uint4(wk.points, wk.box1, wk.box2, wk.cells);
   match_pos[j] = best_pos;
   match_d2[j] = best;
   flags[j] = best_pos >= 0 ? 1u : 0u;

@@ -27,20 +27,31 @@
 
 namespace b2 {
 
-static void cam_set(Cam* c, int w, int h, float fx, float fy, float cx, float cy) {
-  c->w = w; c->h = h; c->fx = fx; c->fy = fy; c->cx = cx; c->cy = cy;
-  c->fx_inv = (float)(1.0 / fx); c->fy_inv = (float)(1.0 / fy);            // camera_base.cc:83
-  c->cx_inv = (float)(-1.0 * cx / fx); c->cy_inv = (float)(-1.0 * cy / fy);
+// One camera (pyramid level) from the reference's parameter vector (GetParameters order). Cut-offs are filled in by
+// compute_cutoffs() — the constructors' InitCutoff (camera_thin_prism.cc:40,50).
+static void cam_set(Cam* c, int type, int w, int h, const float* p) {
+  c->type = type; c->w = w; c->h = h; c->fx = p[0]; c->fy = p[1]; c->cx = p[2]; c->cy = p[3];
+  c->fx_inv = (float)(1.0 / c->fx); c->fy_inv = (float)(1.0 / c->fy);            // camera_base.cc:83
+  c->cx_inv = (float)(-1.0 * c->cx / c->fx); c->cy_inv = (float)(-1.0 * c->cy / c->fy);
+  for (int i = 0; i < 8; ++i) c->d[i] = type == kCamPinhole ? 0.f : p[4 + i];
+  c->cutoff2 = c->inner_cutoff2 = std::numeric_limits<float>::infinity();
+}
+static void cam_get(const Cam& c, float* p) {
+  p[0] = c.fx; p[1] = c.fy; p[2] = c.cx; p[3] = c.cy;
+  if (c.type != kCamPinhole) for (int i = 0; i < 8; ++i) p[4 + i] = c.d[i];
 }
 static Cam cam_half(const Cam& s) {                                          // CameraBaseImpl::ScaledBy(0.5), camera_base_impl.h:70-89
   const float f = 0.5f;
-  Cam d; cam_set(&d, (int)(f * s.w + 0.5f), (int)(f * s.h + 0.5f), s.fx * f, s.fy * f, f * (s.cx + 0.5f) - 0.5f, f * (s.cy + 0.5f) - 0.5f);
+  float p[kMaxIntrinsics] = {0}; cam_get(s, p);
+  p[0] *= f; p[1] *= f; p[2] = f * (s.cx + 0.5f) - 0.5f; p[3] = f * (s.cy + 0.5f) - 0.5f;
+  Cam d; cam_set(&d, s.type, (int)(f * s.w + 0.5f), (int)(f * s.h + 0.5f), p);
   return d;
 }
 
 struct IntrinsicsB {
   std::vector<Cam> models;   // [0] = original resolution
   int min_image_scale = -1;
+  int np() const { return cam_param_count(models[0].type); }
   const Cam& model(int image_scale) const { return models[std::max(0, image_scale - min_image_scale)]; }
   int best_available(int image_scale) const { return std::min<int>(min_image_scale + (int)models.size() - 1, std::max<int>(min_image_scale, image_scale)); }
   void build_pyramid() { for (size_t i = 1; i < models.size(); ++i) models[i] = cam_half(models[i - 1]); }
@@ -87,7 +98,7 @@ struct b2_reg {
   std::vector<std::vector<ObsSet>> obs;      // [image][scale]
   std::vector<ObsSet> trial;                 // scratch sets for trial states, [scale]
   // scratch
-  DevBuf flags, offs, cx, cy, cs, cub_tmp, depth, partials, results;
+  DevBuf flags, offs, cx, cy, cs, cub_tmp, depth, partials, results, cut_cams, cut_first, cut_starts, cut_points, cut_out;
   PinnedBuf pin;
   b2_reg_stats stats;
   int launches = 0;
@@ -97,9 +108,43 @@ struct b2_reg {
 namespace b2 {
 
 static int K(const b2_reg* h) { return h->prm.point_neighbor_count; }
-static int nvars(const b2_reg* h) { return 4 * (int)h->intr.size() + 6 * (int)h->images.size(); }
-static int intr_var(const b2_reg*, int id) { return 4 * id; }
-static int pose_var(const b2_reg* h, int im) { return 4 * (int)h->intr.size() + 6 * im; }
+// variable layout: [intrinsics 0 | intrinsics 1 | ... | image poses (6 each)]; an intrinsics block has the camera model's ParameterCount()
+static int intr_var(const b2_reg* h, int id) { int v = 0; for (int i = 0; i < id; ++i) v += h->intr[i].np(); return v; }
+static int pose_var(const b2_reg* h, int im) { return intr_var(h, (int)h->intr.size()) + 6 * im; }
+static int nvars(const b2_reg* h) { return pose_var(h, (int)h->images.size()); }
+
+// K16: radius cut-offs of every pyramid level of the given intrinsics (the reference re-runs InitCutoff in each camera
+// constructor: CreateUpdatedCamera + ScaledBy per level, intrinsics.cc:66-79). One batched search, one readback.
+static int compute_cutoffs(b2_reg* h, std::vector<IntrinsicsB>* intr) {
+  std::vector<Cam> cams; std::vector<int> first(1, 0); std::vector<std::pair<int, int>> where;
+  for (size_t i = 0; i < intr->size(); ++i)
+    for (size_t l = 0; l < (*intr)[i].models.size(); ++l) {
+      const Cam& c = (*intr)[i].models[l];
+      if (c.type == kCamPinhole) continue;
+      cams.push_back(c); where.emplace_back((int)i, (int)l);
+      first.push_back(first.back() + 2 * (c.w + c.h));
+    }
+  if (cams.empty()) return B2_OK;
+  const int ncam = (int)cams.size(), npoints = first.back();
+  B2_TRY(h->cut_cams.ensure(sizeof(Cam) * ncam)); B2_TRY(h->cut_first.ensure(sizeof(int) * (ncam + 1)));
+  B2_TRY(h->cut_starts.ensure(sizeof(CutoffStart) * (size_t)npoints * 100)); B2_TRY(h->cut_points.ensure(sizeof(CutoffPoint) * (size_t)npoints));
+  B2_TRY(h->cut_out.ensure(sizeof(float) * ncam));
+  B2_CUDA(cudaMemcpyAsync(h->cut_cams.p, cams.data(), sizeof(Cam) * ncam, cudaMemcpyHostToDevice, h->stream));
+  B2_CUDA(cudaMemcpyAsync(h->cut_first.p, first.data(), sizeof(int) * (ncam + 1), cudaMemcpyHostToDevice, h->stream));
+  kr_cutoff_starts<<<npoints, 128, 0, h->stream>>>(h->cut_cams.as<Cam>(), h->cut_first.as<int>(), ncam, h->cut_starts.as<CutoffStart>());
+  kr_cutoff_points<<<divup(npoints, 128), 128, 0, h->stream>>>(h->cut_starts.as<CutoffStart>(), npoints, h->cut_points.as<CutoffPoint>());
+  kr_cutoff_final<<<ncam, 256, 0, h->stream>>>(h->cut_points.as<CutoffPoint>(), h->cut_first.as<int>(), h->cut_out.as<float>());
+  h->launches += 3;
+  std::vector<float> out(ncam);
+  B2_CUDA(cudaMemcpyAsync(out.data(), h->cut_out.p, sizeof(float) * ncam, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  B2_CUDA(cudaGetLastError());
+  for (int k = 0; k < ncam; ++k) {
+    Cam& c = (*intr)[where[k].first].models[where[k].second];
+    if (c.type == kCamThinPrism) c.cutoff2 = out[k]; else c.inner_cutoff2 = out[k];
+  }
+  return B2_OK;
+}
 
 static Pose3 pose3_of(const Pose& p) { Pose3 o; quat_matrix(p.q, o.R); for (int k = 0; k < 3; ++k) o.t[k] = p.t[k]; return o; }
 
@@ -178,7 +223,7 @@ static int ensure_obs_set(ObsSet* o, size_t cap, size_t npoints, bool with_jac) 
   cap = std::max<size_t>(cap, 1);
   B2_TRY(o->idx.ensure(cap * 4)); B2_TRY(o->x.ensure(cap * 4)); B2_TRY(o->y.ensure(cap * 4)); B2_TRY(o->s.ensure(cap * 4));
   B2_TRY(o->nb.ensure(cap)); B2_TRY(o->inten.ensure(cap * 4));
-  if (with_jac) { B2_TRY(o->jK.ensure(cap * 16)); B2_TRY(o->jP.ensure(cap * 24)); }
+  if (with_jac) { B2_TRY(o->jK.ensure(cap * 4 * kMaxIntrinsics)); B2_TRY(o->jP.ensure(cap * 24)); }
   B2_TRY(o->slot.ensure(std::max<size_t>(npoints, 1) * 4));
   return B2_OK;
 }
@@ -276,7 +321,7 @@ static int residual_sums_image(b2_reg* h, const StateB& st, int im, std::vector<
     any = true;
     kr_intensity<<<divup(o.count, 256), 256, 0, h->stream>>>(o.count, o.x.as<float>(), o.y.as<float>(), o.s.as<float>(), L, o.inten.as<float>());
     kr_residual_sums<<<grid, 256, 0, h->stream>>>(residual_args(h, (int)ps, o), h->partials.as<double>());
-    kr_reduce_partials<<<1, 128, 0, h->stream>>>(h->partials.as<double>(), grid, 4, h->results.as<double>() + 4 * ps);
+    kr_reduce_partials<<<1, 256, 0, h->stream>>>(h->partials.as<double>(), grid, 4, h->results.as<double>() + 4 * ps);
     h->launches += 3;
   }
   if (!any) return B2_OK;
@@ -299,17 +344,19 @@ static void set_current_state(b2_reg* h, const StateB& s) {
 }
 
 // CreateDeltaState (intrinsics_and_pose_optimizer.cc:475-558).
-static StateB delta_state(const b2_reg* h, const StateB& base, const double* delta) {
-  StateB n = base;
+static int delta_state(b2_reg* h, const StateB& base, const double* delta, StateB* out) {
+  StateB& n = *out;
+  n = base;
   for (size_t i = 0; i < n.intr.size(); ++i) {
     Cam& m = n.intr[i].models[0];
-    float p[4] = {m.fx, m.fy, m.cx, m.cy};
-    for (int k = 0; k < 4; ++k) p[k] += delta[intr_var(h, (int)i) + k];      // float += double (intrinsics.cc:72-74)
-    cam_set(&m, m.w, m.h, p[0], p[1], p[2], p[3]);
+    float p[kMaxIntrinsics] = {0}; cam_get(m, p);
+    for (int k = 0; k < n.intr[i].np(); ++k) p[k] += delta[intr_var(h, (int)i) + k];      // float += double (intrinsics.cc:72-74)
+    cam_set(&m, m.type, m.w, m.h, p);
     n.intr[i].build_pyramid();
   }
+  B2_TRY(compute_cutoffs(h, &n.intr));
   for (size_t i = 0; i < n.poses.size(); ++i) n.poses[i] = pose_mul(pose_exp(delta + pose_var(h, (int)i)), base.poses[i]);   // image.cc:161
-  return n;
+  return B2_OK;
 }
 
 // ComputeResidualForState with frozen visibility lists (intrinsics_and_pose_optimizer.cc:385-440).
@@ -323,16 +370,27 @@ static int residual_for_state(b2_reg* h, const StateB& st, double* cost) {
   return B2_OK;
 }
 
+static void launch_jacobians(b2_reg* h, int np, ObsSet& o, const ScaleB& P, const Pose3& P3, const Levels& L) {
+  if (np == 4)
+    kr_jacobians<4><<<divup(o.count, 256), 256, 0, h->stream>>>(o.count, o.idx.as<unsigned int>(), o.x.as<float>(), o.y.as<float>(), o.s.as<float>(),
+                                                                 P.xyz.as<float>(), P3, P.radius, L, o.inten.as<float>(), o.jK.as<float>(), o.jP.as<float>());
+  else
+    kr_jacobians<12><<<divup(o.count, 256), 256, 0, h->stream>>>(o.count, o.idx.as<unsigned int>(), o.x.as<float>(), o.y.as<float>(), o.s.as<float>(),
+                                                                  P.xyz.as<float>(), P3, P.radius, L, o.inten.as<float>(), o.jK.as<float>(), o.jP.as<float>());
+  ++h->launches;
+}
+
 // AccumulateHAndBAndResidualsForObservations over all images and point scales (intrinsics_and_pose_optimizer.cc:102-185).
 static int accumulate_all(b2_reg* h, std::vector<double>* H, std::vector<double>* b, Sums* sums) {
   const int nv = nvars(h);
-  const int grid = h->sms * 2;
+  const int grid = h->sms * 2, grid_wide = h->sms * 4;
   const size_t S = h->pts.size(), NI = h->images.size();
+  constexpr int kAccW = 18 * 19 / 2 + 18 + 4;      // result stride: the widest local system (12 intrinsics + 6 pose)
   H->assign((size_t)nv * nv, 0.0); b->assign(nv, 0.0);
-  B2_TRY(h->partials.ensure(sizeof(double) * kAccB * grid));
-  B2_TRY(h->results.ensure(sizeof(double) * kAccB * NI * S));
-  B2_TRY(h->pin.ensure(std::max<size_t>(sizeof(double) * kAccB * NI * S, 64)));
-  B2_CUDA(cudaMemsetAsync(h->results.p, 0, sizeof(double) * kAccB * NI * S, h->stream));
+  B2_TRY(h->partials.ensure(sizeof(double) * kAccW * grid_wide));
+  B2_TRY(h->results.ensure(sizeof(double) * kAccW * NI * S));
+  B2_TRY(h->pin.ensure(std::max<size_t>(sizeof(double) * kAccW * NI * S, 64)));
+  B2_CUDA(cudaMemsetAsync(h->results.p, 0, sizeof(double) * kAccW * NI * S, h->stream));
   const StateB st = current_state(h);
   uint64_t evals = 0;
   float ms_j = 0.f, ms_a = 0.f;
@@ -344,35 +402,41 @@ static int accumulate_all(b2_reg* h, std::vector<double>* H, std::vector<double>
       ObsSet& o = h->obs[im][ps];
       if (o.count == 0) continue;
       evals += o.count;
+      const int np = st.intr[I.intrinsics_id].np();
       cudaEventRecord(h->evj0, h->stream);
-      kr_jacobians<<<divup(o.count, 256), 256, 0, h->stream>>>(o.count, o.idx.as<unsigned int>(), o.x.as<float>(), o.y.as<float>(), o.s.as<float>(),
-                                                              h->pts[ps].xyz.as<float>(), P3, h->pts[ps].radius, L, o.inten.as<float>(),
-                                                              o.jK.as<float>(), o.jP.as<float>());
+      launch_jacobians(h, np, o, h->pts[ps], P3, L);
       cudaEventRecord(h->evj1, h->stream);
       cudaEventRecord(h->eva0, h->stream);
-      kr_accumulate<<<grid, 128, 0, h->stream>>>(residual_args(h, (int)ps, o), o.jK.as<float>(), o.jP.as<float>(), h->partials.as<double>());
-      cudaEventRecord(h->eva1, h->stream);
-      kr_reduce_partials<<<1, 128, 0, h->stream>>>(h->partials.as<double>(), grid, kAccB, h->results.as<double>() + kAccB * (im * S + ps));
-      h->launches += 3;
+      if (np == 4) {
+        kr_accumulate<<<grid, 128, 0, h->stream>>>(residual_args(h, (int)ps, o), o.jK.as<float>(), o.jP.as<float>(), h->partials.as<double>());
+        cudaEventRecord(h->eva1, h->stream);
+        kr_reduce_partials<<<1, 256, 0, h->stream>>>(h->partials.as<double>(), grid, kAccB, h->results.as<double>() + kAccW * (im * S + ps));
+      } else {
+        kr_accumulate_wide<12><<<grid_wide, 128, 0, h->stream>>>(residual_args(h, (int)ps, o), o.jK.as<float>(), o.jP.as<float>(), h->partials.as<double>());
+        cudaEventRecord(h->eva1, h->stream);
+        kr_reduce_partials<<<1, 256, 0, h->stream>>>(h->partials.as<double>(), grid_wide, kAccW, h->results.as<double>() + kAccW * (im * S + ps));
+      }
+      h->launches += 2;
       cudaEventSynchronize(h->eva1);
       float a = 0, c = 0; cudaEventElapsedTime(&a, h->evj0, h->evj1); cudaEventElapsedTime(&c, h->eva0, h->eva1);
       ms_j += a; ms_a += c;
     }
   }
-  B2_CUDA(cudaMemcpyAsync(h->pin.p, h->results.p, sizeof(double) * kAccB * NI * S, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaMemcpyAsync(h->pin.p, h->results.p, sizeof(double) * kAccW * NI * S, cudaMemcpyDeviceToHost, h->stream));
   B2_CUDA(cudaStreamSynchronize(h->stream));
   B2_CUDA(cudaGetLastError());
   const double* r = h->pin.as<double>();
   *sums = Sums();
   for (size_t im = 0; im < NI; ++im) {
     const int iv = intr_var(h, h->images[im].intrinsics_id), pv = pose_var(h, (int)im);
-    auto g = [&](int l) { return l < kNI ? iv + l : pv + (l - kNI); };
+    const int ni = st.intr[h->images[im].intrinsics_id].np(), lv = ni + 6, lh = lv * (lv + 1) / 2;
+    auto g = [&](int l) { return l < ni ? iv + l : pv + (l - ni); };
     for (size_t ps = 0; ps < S; ++ps) {
-      const double* v = r + kAccB * (im * S + ps);
+      const double* v = r + kAccW * (im * S + ps);
       int e = 0;
-      for (int c = 0; c < kNV; ++c) for (int rr = 0; rr <= c; ++rr) { (*H)[(size_t)g(c) * nv + g(rr)] += v[e]; ++e; }
-      for (int k = 0; k < kNV; ++k) (*b)[g(k)] += v[kNH + k];
-      sums->fixed_sum += v[kNH + kNV]; sums->nf += v[kNH + kNV + 1]; sums->var_sum += v[kNH + kNV + 2]; sums->nv += v[kNH + kNV + 3];
+      for (int c = 0; c < lv; ++c) for (int rr = 0; rr <= c; ++rr) { (*H)[(size_t)g(c) * nv + g(rr)] += v[e]; ++e; }
+      for (int k = 0; k < lv; ++k) (*b)[g(k)] += v[lh + k];
+      sums->fixed_sum += v[lh + lv]; sums->nf += v[lh + lv + 1]; sums->var_sum += v[lh + lv + 2]; sums->nv += v[lh + lv + 3];
     }
   }
   for (int c = 0; c < nv; ++c) for (int rr = 0; rr < c; ++rr) (*H)[(size_t)rr * nv + c] = (*H)[(size_t)c * nv + rr];   // mirror the Upper view
@@ -440,7 +504,7 @@ static int apply_lm(b2_reg* h, float* lambda, float* max_change, int* applied, i
     for (int i = 0; i < nv; ++i) HL[(size_t)i * nv + i] *= (1 + (*lambda));
     sym_solve(HL, nv, b.data(), x.data());
     for (int i = 0; i < nv; ++i) neg[i] = -1 * x[i];
-    const StateB ns = delta_state(h, base, neg.data());
+    StateB ns; B2_TRY(delta_state(h, base, neg.data(), &ns));
     double nr = 0;
     B2_TRY(residual_for_state(h, ns, &nr));
     if (nr < initial || lm == 9) {      // kAlwaysApplyLastUpdate (:199,239-240)
@@ -511,10 +575,12 @@ int b2_reg_destroy(b2_reg* h) {
 
 int b2_reg_add_intrinsics(b2_reg* h, int camera_model, int width, int height, const float* params, int num_params, int* out_id) {
   REG_ENTER(h);
-  if (camera_model != 0) return set_error(B2_ERR_ARG, "camera model %d not supported by this ABI version (0 = PINHOLE only)", camera_model);
-  if (!params || num_params != 4 || width < 2 || height < 2) return set_error(B2_ERR_ARG, "PINHOLE needs 4 parameters and a size >= 2x2");
+  if (camera_model == 0) camera_model = kCamPinhole;   // ABI v1 alias
+  const int np = cam_param_count(camera_model);
+  if (np < 0) return set_error(B2_ERR_ARG, "camera model %d not supported (4 = PINHOLE, 14 = THIN_PRISM, 5 = BENCHMARK / thin-prism fisheye)", camera_model);
+  if (!params || num_params != np || width < 2 || height < 2) return set_error(B2_ERR_ARG, "camera model %d needs %d parameters and a size >= 2x2", camera_model, np);
   if (h->initialized) return set_error(B2_ERR_STATE, "add_intrinsics after initialize");
-  IntrinsicsB in; in.models.resize(1); cam_set(&in.models[0], width, height, params[0], params[1], params[2], params[3]);
+  IntrinsicsB in; in.models.resize(1); cam_set(&in.models[0], camera_model, width, height, params);
   h->intr.push_back(in);
   if (out_id) *out_id = (int)h->intr.size() - 1;
   return B2_OK;
@@ -558,6 +624,7 @@ int b2_reg_initialize(b2_reg* h, int* image_scale_count) {
     in.build_pyramid();
   }
   begin_call(h);
+  B2_TRY(compute_cutoffs(h, &h->intr));
   for (ImageB& im : h->images) {
     const IntrinsicsB& in = h->intr[im.intrinsics_id];
     const size_t levels = in.models.size();
@@ -773,13 +840,11 @@ int b2_reg_get_point_jacobians(b2_reg* h, int image_id, int ps, float* inten, fl
   const ImageB& I = h->images[image_id];
   const Levels L = levels_of(h, I, h->intr[I.intrinsics_id]);
   begin_call(h);
-  kr_jacobians<<<divup(o.count, 256), 256, 0, h->stream>>>(o.count, o.idx.as<unsigned int>(), o.x.as<float>(), o.y.as<float>(), o.s.as<float>(),
-                                                          h->pts[ps].xyz.as<float>(), pose3_of(I.pose), h->pts[ps].radius, L, o.inten.as<float>(),
-                                                          o.jK.as<float>(), o.jP.as<float>());
-  ++h->launches;
+  const int np = h->intr[I.intrinsics_id].np();
+  launch_jacobians(h, np, o, h->pts[ps], pose3_of(I.pose), L);
   B2_CUDA(cudaGetLastError());
   if (inten) B2_CUDA(cudaMemcpyAsync(inten, o.inten.p, o.count * 4, cudaMemcpyDeviceToHost, h->stream));
-  if (jK) B2_CUDA(cudaMemcpyAsync(jK, o.jK.p, o.count * 16, cudaMemcpyDeviceToHost, h->stream));
+  if (jK) B2_CUDA(cudaMemcpyAsync(jK, o.jK.p, o.count * 4 * np, cudaMemcpyDeviceToHost, h->stream));
   if (jP) B2_CUDA(cudaMemcpyAsync(jP, o.jP.p, o.count * 24, cudaMemcpyDeviceToHost, h->stream));
   end_call(h);
   return B2_OK;
@@ -834,14 +899,17 @@ int b2_reg_accumulate(b2_reg* h, double* H, double* b, double sums[6], double* c
 
 int b2_reg_get_state(b2_reg* h, float* ip, float* poses) {
   REG_ENTER(h);
-  if (ip) for (size_t i = 0; i < h->intr.size(); ++i) { const Cam& m = h->intr[i].models[0]; ip[4 * i] = m.fx; ip[4 * i + 1] = m.fy; ip[4 * i + 2] = m.cx; ip[4 * i + 3] = m.cy; }
+  if (ip) for (size_t i = 0; i < h->intr.size(); ++i) cam_get(h->intr[i].models[0], ip + intr_var(h, (int)i));
   if (poses) for (size_t i = 0; i < h->images.size(); ++i) { for (int k = 0; k < 4; ++k) poses[7 * i + k] = h->images[i].pose.q[k]; for (int k = 0; k < 3; ++k) poses[7 * i + 4 + k] = h->images[i].pose.t[k]; }
   return B2_OK;
 }
 
 int b2_reg_set_state(b2_reg* h, const float* ip, const float* poses) {
   REG_ENTER(h);
-  if (ip) for (size_t i = 0; i < h->intr.size(); ++i) { Cam& m = h->intr[i].models[0]; cam_set(&m, m.w, m.h, ip[4 * i], ip[4 * i + 1], ip[4 * i + 2], ip[4 * i + 3]); h->intr[i].build_pyramid(); }
+  if (ip) {
+    for (size_t i = 0; i < h->intr.size(); ++i) { Cam& m = h->intr[i].models[0]; cam_set(&m, m.type, m.w, m.h, ip + intr_var(h, (int)i)); h->intr[i].build_pyramid(); }
+    B2_TRY(compute_cutoffs(h, &h->intr));
+  }
   if (poses) for (size_t i = 0; i < h->images.size(); ++i) { for (int k = 0; k < 4; ++k) h->images[i].pose.q[k] = poses[7 * i + k]; for (int k = 0; k < 3; ++k) h->images[i].pose.t[k] = poses[7 * i + 4 + k]; }
   return B2_OK;
 }
@@ -851,7 +919,7 @@ int b2_reg_cost_for_delta(b2_reg* h, const double* delta, double* cost) {
   if (!delta || !cost) return set_error(B2_ERR_ARG, "null argument");
   if (h->obs.size() != h->images.size()) return set_error(B2_ERR_STATE, "create_observations first");
   begin_call(h);
-  const StateB ns = delta_state(h, current_state(h), delta);
+  StateB ns; B2_TRY(delta_state(h, current_state(h), delta, &ns));
   B2_TRY(residual_for_state(h, ns, cost));
   end_call(h);
   return B2_OK;
@@ -901,6 +969,37 @@ int b2_reg_last_stats(b2_reg* h, b2_reg_stats* out) {
   if (!out) return set_error(B2_ERR_ARG, "null");
   *out = h->stats;
   return B2_OK;
+}
+
+// Stand-alone camera evaluation (the camera::CameraBase calls Path B makes), mainly for parity tests of the camera models.
+int b2_camera_eval(int camera_model, int width, int height, const float* params, int num_params, int op, const float* in, size_t n, float* out,
+                   float cutoffs[2]) {
+  if (camera_model == 0) camera_model = kCamPinhole;
+  const int np = cam_param_count(camera_model);
+  if (np < 0 || !params || num_params != np || width < 2 || height < 2) return set_error(B2_ERR_ARG, "unsupported camera model or parameter count");
+  if (op < 0 || op > 3 || (op != 0 && n != 0 && (!in || !out))) return set_error(B2_ERR_ARG, "bad op / null buffers");
+  b2_reg_params prm; b2_reg_default_params(&prm);
+  b2_reg* h = nullptr;
+  B2_TRY(b2_reg_create(&prm, &h));
+  int rc = B2_OK;
+  do {
+    std::vector<IntrinsicsB> intr(1); intr[0].models.resize(1); cam_set(&intr[0].models[0], camera_model, width, height, params);
+    if ((rc = compute_cutoffs(h, &intr)) != B2_OK) break;
+    const Cam cam = intr[0].models[0];
+    if (cutoffs) { cutoffs[0] = cam.cutoff2; cutoffs[1] = cam.inner_cutoff2; }
+    if (op == 0 || n == 0) break;
+    const int nin = op == 1 ? 2 : 3, nout = op == 1 ? 2 : op == 2 ? 6 : 2 * np;
+    DevBuf din, dout;
+    if ((rc = din.ensure(n * nin * 4)) != B2_OK || (rc = dout.ensure(n * nout * 4)) != B2_OK) break;
+    if (cudaMemcpyAsync(din.p, in, n * nin * 4, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { rc = set_error(B2_ERR_CUDA, "H2D copy failed"); break; }
+    kr_camera_eval<<<divup(n, 128), 128, 0, h->stream>>>(cam, op, din.as<float>(), n, dout.as<float>());
+    if (cudaMemcpyAsync(out, dout.p, n * nout * 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) {
+      rc = set_error(B2_ERR_CUDA, "camera_eval failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+  } while (false);
+  b2_reg_destroy(h);
+  return rc;
 }
 
 }  // extern "C"

@@ -1,4 +1,5 @@
-// Device kernels of Path B (dense photometric image<->scan alignment) for sm_100a — pinhole cameras, no rigs.
+// Device kernels of Path B (dense photometric image<->scan alignment) for sm_100a — pinhole, thin-prism and thin-prism-fisheye
+// ("benchmark") cameras (b2_camera.cuh), no rigs.
 //
 //   K15 kr_pyr_down          u8 2x2 area mean ((a+b+c+d+2)>>2 = cv::resize INTER_AREA at factor 1/2) / mask OR    image.cc:106-154
 //   B1  kr_splat_depth       point-splat depth map, atomicMin on float bits                                        occlusion_geometry.cc:404-464
@@ -12,14 +13,13 @@
 // Arithmetic follows the oracle's fp32 evaluation order; the file is built with -fmad=false so plain operators are never
 // contracted. All of it is gather-bound byte / fp32 work: no tensor cores.
 #pragma once
+#include "b2_camera.cuh"
 #include "b2_common.cuh"
 
 namespace b2 {
 
 static constexpr int kMaxLevels = 16;
 static constexpr int kMaxNbr = 8;
-
-struct Cam { int w, h; float fx, fy, cx, cy, fx_inv, fy_inv, cx_inv, cy_inv; };
 
 // Pyramid of one image (+ its intrinsics) as seen by the kernels. Level l is image scale (min_image_scale + l).
 struct Levels {
@@ -48,18 +48,6 @@ __device__ __forceinline__ float robust_weight(const Robust& r, float x) {      
 }
 
 __device__ __forceinline__ float sum3p(float a, float b, float c) { return a + (b + c); }   // Eigen 3-term reduction order
-
-__device__ __forceinline__ void cam_project(const Cam& c, float nx, float ny, float* ix, float* iy) {   // camera_base_impl.h:155-164
-  const float r2 = nx * nx + ny * ny;
-  if (isinf(r2)) { *ix = nx * INFINITY; *iy = ny * INFINITY; return; }
-  *ix = c.fx * nx + c.cx; *iy = c.fy * ny + c.cy;
-}
-__device__ __forceinline__ void cam_d_by_world(const Cam& c, float px, float py, float pz, float d[6]) {   // :333-360
-  const float nx = px / pz, ny = py / pz;
-  const float z_inv = 1.f / pz;
-  d[0] = c.fx * (1.f * z_inv); d[1] = c.fx * (0.f * z_inv); d[2] = c.fx * (-1.f * nx * z_inv);
-  d[3] = c.fy * (0.f * z_inv); d[4] = c.fy * (1.f * z_inv); d[5] = c.fy * (-1.f * ny * z_inv);
-}
 
 __device__ __forceinline__ void rigid(const Pose3& P, float x, float y, float z, float* ox, float* oy, float* oz) {
   *ox = sum3p(P.R[0] * x, P.R[1] * y, P.R[2] * z) + P.t[0];
@@ -118,7 +106,8 @@ __global__ void __launch_bounds__(256) kr_splat_depth(const float* __restrict__ 
   float rx = sqrtf(sum3p(d[0] * d[0], d[1] * d[1], d[2] * d[2])) * point_radius;
   float ry = sqrtf(sum3p(d[3] * d[3], d[4] * d[4], d[5] * d[5])) * point_radius;
   rx = fminf(rx, 10.f); ry = fminf(ry, 10.f);
-  const int ix = (int)(ux + 0.5f), iy = (int)(uy + 0.5f);
+  const int ix = f2i_x86(ux + 0.5f), iy = f2i_x86(uy + 0.5f);
+  if (ix == (int)0x80000000 || iy == (int)0x80000000) return;   // beyond the cut-off radius
   const int min_x = max(0, (int)(ix - rx + 0.5)), min_y = max(0, (int)(iy - ry + 0.5));
   const int end_x = min(cam.w, (int)(ix + rx + 1.5)), end_y = min(cam.h, (int)(iy + ry + 1.5));
   const unsigned int zb = __float_as_uint(pz);
@@ -299,7 +288,7 @@ __global__ void __launch_bounds__(256) kr_visibility(const float* __restrict__ x
   float px, py, pz; rigid(V.P, xyz[3 * pi], xyz[3 * pi + 1], xyz[3 * pi + 2], &px, &py, &pz);
   if (pz > 0.f) {
     float ixx, ixy; cam_project(V.cam, px / pz, py / pz, &ixx, &ixy);
-    const int ix = (int)(ixx + 0.5f), iy = (int)(ixy + 0.5f);
+    const int ix = f2i_x86(ixx + 0.5f), iy = f2i_x86(ixy + 0.5f);
     if (ix >= 0 && iy >= 0 && ix < V.cam.w && iy < V.cam.h &&
         (V.depth == nullptr || __ldg(V.depth + (size_t)iy * V.cam.w + ix) + V.occlusion_threshold >= pz)) {
       // CreateObservationIfScaleFits (visibility_estimator.cc:405-532)
@@ -308,7 +297,9 @@ __global__ void __launch_bounds__(256) kr_visibility(const float* __restrict__ x
       const float dx = rx - ixx, dy = ry - ixy;
       const float radius_pixels = sqrtf(dx * dx + dy * dy);
       const float observation_scale = (float)((double)V.image_scale + log2((double)(2 * radius_pixels)));
-      if (observation_scale >= (float)max(L.min_image_scale, V.current_image_scale) && (int)observation_scale < V.image_scale_count - 1) {
+      // a non-finite scale (offset point beyond the cut-off radius) is undefined behaviour in the reference: no observation
+      if (isfinite(observation_scale) && observation_scale >= (float)max(L.min_image_scale, V.current_image_scale) &&
+          (int)observation_scale < V.image_scale_count - 1) {
         const int small = (int)observation_scale + 1;
         const int lvl = max(0, small - L.min_image_scale);
         const Cam& ic = L.cam[lvl];
@@ -362,7 +353,8 @@ __global__ void __launch_bounds__(256) kr_intensity(size_t count, const float* _
   inten[i] = trilinear(L, small, ox[i], oy[i], 1 - (s - (int)s));
 }
 
-// K11 (intrinsics_and_pose_optimizer.cc:933-1147), non-rig, depth residuals off.
+// K11 (intrinsics_and_pose_optimizer.cc:933-1147), non-rig, depth residuals off. NI = intrinsics parameter count of the camera model.
+template <int NI>
 __global__ void __launch_bounds__(256) kr_jacobians(size_t count, const unsigned int* __restrict__ idx, const float* __restrict__ ox,
                                                     const float* __restrict__ oy, const float* __restrict__ os, const float* __restrict__ xyz,
                                                     Pose3 P, float point_radius, Levels L, float* __restrict__ inten, float* __restrict__ jK,
@@ -392,13 +384,14 @@ __global__ void __launch_bounds__(256) kr_jacobians(size_t count, const unsigned
   float oxp, oyp; cam_project(cam, qx / tz, ty / tz, &oxp, &oyp);
   const float rdx = oxp - mx, rdy = oyp - my;
   const float denom = fmaxf(1e-6f, 0.693147180559945f * (rdx * rdx + rdy * rdy));
-  // d(project)/d(intrinsics) rows: [x 0 1 0], [0 y 0 1], scale row from the offset point
-  const float a[8] = {tx / tz, 0.f, 1.f, 0.f, 0.f, ty / tz, 0.f, 1.f};
-  const float b[8] = {qx / tz, 0.f, 1.f, 0.f, 0.f, ty / tz, 0.f, 1.f};
+  // d(project)/d(intrinsics) rows (pinhole: [x 0 1 0], [0 y 0 1]), scale row from the offset point
+  float ax[NI], ay[NI], bx[NI], by[NI];
+  cam_d_by_intrinsics<NI>(cam, tx, ty, tz, ax, ay);
+  cam_d_by_intrinsics<NI>(cam, qx, ty, tz, bx, by);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float row2 = ((b[k] - a[k]) * rdx + (b[4 + k] - a[4 + k]) * rdy) / denom;
-    jK[4 * i + k] = sum3p(ji0 * a[k], ji1 * a[4 + k], ji2 * row2);
+  for (int k = 0; k < NI; ++k) {
+    const float row2 = ((bx[k] - ax[k]) * rdx + (by[k] - ay[k]) * rdy) / denom;
+    jK[(size_t)NI * i + k] = sum3p(ji0 * ax[k], ji1 * ay[k], ji2 * row2);
   }
   float dw[6], dq[6];
   cam_d_by_world(cam, tx, ty, tz, dw);
@@ -532,8 +525,79 @@ __global__ void __launch_bounds__(128) kr_accumulate(ResidualArgs A, const float
   if (threadIdx.x < kAccB) partials[(size_t)blockIdx.x * kAccB + threadIdx.x] = out;
 }
 
+// K12w: the same accumulation for camera models with more intrinsics (NI = 12: (12+6)^2 local system = 171 upper entries + 18 of b),
+// which no longer fits one thread's registers. One WARP per observation: lane l < NI+6 holds Jacobian column l of the centre /
+// neighbour rows, the 189 accumulators are spread over the lanes (6 each) and every (r, c) product fetches its two factors with
+// shuffles. Same fp32 products and fp64 accumulation as the per-thread kernel; per-block output [NH | NV | 4 sums].
+template <int NI>
+__global__ void __launch_bounds__(128) kr_accumulate_wide(ResidualArgs A, const float* __restrict__ jK, const float* __restrict__ jP,
+                                                          double* __restrict__ partials /* [grid][NH + NV + 4] */) {
+  constexpr int NV = NI + 6, NH = NV * (NV + 1) / 2, NE = NH + NV, SL = (NE + 31) / 32, NOUT = NE + 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int er[SL], ec[SL];   // entry e = s*32 + lane: H(r, c) for e < NH (e = c(c+1)/2 + r), b(c) with r = -1 for NH <= e < NE, unused r = -2
+#pragma unroll
+  for (int s = 0; s < SL; ++s) {
+    const int e = s * 32 + lane;
+    if (e < NH) { int c = 0; while ((c + 1) * (c + 2) / 2 <= e) ++c; ec[s] = c; er[s] = e - c * (c + 1) / 2; }
+    else if (e < NE) { er[s] = -1; ec[s] = e - NH; }
+    else { er[s] = -2; ec[s] = 0; }
+  }
+  double acc[SL];
+#pragma unroll
+  for (int s = 0; s < SL; ++s) acc[s] = 0.0;
+  double sums[4] = {0.0, 0.0, 0.0, 0.0};
+  const size_t nw = (size_t)gridDim.x * 4;
+  for (size_t i = (size_t)blockIdx.x * 4 + warp; i < A.count; i += nw) {
+    if (!A.nb[i]) continue;
+    const size_t p = A.idx[i];
+    const float Ic = A.inten[i];
+    int nj = 0; float In = 0.f;
+    if (lane < A.K) { nj = A.slot[A.nbr[p * A.K + lane]]; In = A.inten[nj]; }
+    float jc = 0.f;
+    if (lane < NI) jc = jK[(size_t)NI * i + lane]; else if (lane < NV) jc = jP[6 * i + (lane - NI)];
+#pragma unroll
+    for (int type = 0; type < 2; ++type) {
+      const float sw = type == 0 ? A.fixed_w : A.var_w;
+      if (!(sw > 0)) continue;
+      if (type == 1 && A.obs_count[p] < 2) continue;
+      const float* desc = type == 0 ? A.fixed_desc : A.var_desc;
+      float cmp = 0.f;
+      if (lane < A.K) cmp = (In - Ic) - desc[p * A.K + lane];
+      float pr = 0.f;
+      for (int k = 0; k < A.K; ++k) { const float c = __shfl_sync(0xffffffffu, cmp, k); pr += c * c; }
+      pr = sqrtf(pr);
+      sums[2 * type] += (double)robust_residual(A.robust, pr);
+      sums[2 * type + 1] += 1.0;
+      const float w = sw * robust_weight(A.robust, pr);
+      if (w != 0) {
+        for (int k = 0; k < A.K; ++k) {
+          const int njk = __shfl_sync(0xffffffffu, nj, k);
+          const float wr = w * __shfl_sync(0xffffffffu, cmp, k);
+          float dj = 0.f;
+          if (lane < NI) dj = jK[(size_t)NI * njk + lane] - jc; else if (lane < NV) dj = jP[(size_t)6 * njk + (lane - NI)] - jc;
+#pragma unroll
+          for (int s = 0; s < SL; ++s) {
+            const float a = __shfl_sync(0xffffffffu, dj, max(er[s], 0)), b = __shfl_sync(0xffffffffu, dj, ec[s]);
+            if (er[s] >= 0) acc[s] += (double)((w * a) * b);
+            else if (er[s] == -1) acc[s] += (double)(wr * b);
+          }
+        }
+      }
+    }
+  }
+  __shared__ double sm[4][SL * 32 + 4];
+#pragma unroll
+  for (int s = 0; s < SL; ++s) sm[warp][s * 32 + lane] = acc[s];
+  if (lane == 0) { for (int k = 0; k < 4; ++k) sm[warp][SL * 32 + k] = sums[k]; }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NOUT; t += blockDim.x) {
+    const int src = t < NE ? t : SL * 32 + (t - NE);
+    partials[(size_t)blockIdx.x * NOUT + t] = ((sm[0][src] + sm[1][src]) + sm[2][src]) + sm[3][src];
+  }
+}
+
 // Fixed-order sum of the per-block partials: out[v] = sum_b partials[b][v].
-__global__ void __launch_bounds__(128) kr_reduce_partials(const double* __restrict__ partials, int nblocks, int nvals, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) kr_reduce_partials(const double* __restrict__ partials, int nblocks, int nvals, double* __restrict__ out) {
   const int v = threadIdx.x;
   if (v >= nvals) return;
   double s = 0.0;

@@ -59,6 +59,7 @@ def _L():
     L.b2_reg_apply.argtypes = [vp, fp, fp, ip, ip]
     L.b2_reg_run_on_current_scale.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_int, dp, ip, ip]
     L.b2_reg_last_stats.argtypes = [vp, C.POINTER(RegStats)]
+    L.b2_camera_eval.argtypes = [C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, fp, C.c_size_t, fp, fp]
     _bound = True
     return L
 
@@ -75,6 +76,25 @@ def _u8(a):
     return a.ctypes.data_as(C.POINTER(C.c_uint8))
 
 
+CAM_PINHOLE, CAM_BENCHMARK, CAM_THIN_PRISM = 4, 5, 14   # camera::CameraBase::Type (camera_base.h:67-84)
+
+
+_CAM_OPS = {"cutoff": (0, 2, 0), "project": (1, 2, 2), "d_by_world": (2, 3, 6), "d_by_intrinsics": (3, 3, None)}
+
+
+def camera_eval(camera_model, width, height, params, op="cutoff", pts=None):
+    """camera::CameraBase evaluation on the device (b2_camera_eval): returns (out, (cutoff2, inner_cutoff2)).
+    op: "cutoff" | "project" (n x 2 normalized -> pixels) | "d_by_world" (n x 3 -> n x 6) | "d_by_intrinsics" (n x 3 -> n x 2np)."""
+    code, nin, nout = _CAM_OPS[op]
+    p = np.ascontiguousarray(params, np.float32)
+    x = np.ascontiguousarray(pts if pts is not None else np.zeros((0, nin)), np.float32).reshape(-1, nin)
+    if nout is None:
+        nout = 2 * p.size
+    out = np.zeros((x.shape[0], nout), np.float32); cut = np.zeros(2, np.float32)
+    _lib.check(_L().b2_camera_eval(camera_model, width, height, _f(p), p.size, code, _f(x), x.shape[0], _f(out), _f(cut)))
+    return out, (float(cut[0]), float(cut[1]))
+
+
 def default_params(**kw):
     p = RegParams()
     _L().b2_reg_default_params(C.byref(p))
@@ -84,7 +104,7 @@ def default_params(**kw):
 
 
 class Registration:
-    """opt::Problem state in HBM + the optimizer pieces. PINHOLE cameras, no rigs (ABI version 1)."""
+    """opt::Problem state in HBM + the optimizer pieces. PINHOLE / THIN_PRISM / BENCHMARK (thin-prism fisheye) cameras, no rigs."""
 
     def __init__(self, params=None):
         L = _L()
@@ -92,7 +112,7 @@ class Registration:
         self._h = C.c_void_p()
         _lib.check(L.b2_reg_create(C.byref(self.params), C.byref(self._h)))
         self.K = self.params.point_neighbor_count
-        self.n_intr = 0; self.n_img = 0; self.scale_sizes = []
+        self.n_intr = 0; self.n_img = 0; self.scale_sizes = []; self.intr_np = []; self.image_intr = []
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -105,18 +125,22 @@ class Registration:
             pass
 
     # ---- problem set-up (opt::Problem) ----
-    def add_intrinsics(self, width, height, params, camera_model=0):
+    def add_intrinsics(self, width, height, params, camera_model=CAM_PINHOLE):
+        """camera_model: CAM_PINHOLE (4 params), CAM_THIN_PRISM or CAM_BENCHMARK (12 params) — camera::CameraBase::Type values."""
         p = np.ascontiguousarray(params, np.float32); out = C.c_int32(0)
         _lib.check(_L().b2_reg_add_intrinsics(self._h, camera_model, width, height, _f(p), p.size, C.byref(out)))
-        self.n_intr += 1
+        self.n_intr += 1; self.intr_np.append(int(p.size))
         return out.value
+
+    def _intr_shape(self, flat):
+        return flat.reshape(self.n_intr, -1) if len(set(self.intr_np)) == 1 else flat
 
     def add_image(self, intrinsics_id, gray, mask, image_T_global):
         g = np.ascontiguousarray(gray, np.uint8); T = np.ascontiguousarray(image_T_global, np.float32)
         m = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
         out = C.c_int32(0)
         _lib.check(_L().b2_reg_add_image(self._h, intrinsics_id, _u8(g), _u8(m) if m is not None else None, _f(T), C.byref(out)))
-        self.n_img += 1
+        self.n_img += 1; self.image_intr.append(int(intrinsics_id))
         return out.value
 
     def initialize(self):
@@ -173,7 +197,7 @@ class Registration:
 
     def point_jacobians(self, image, ps):
         n = len(self.observations(image, ps)[0])
-        I = np.zeros(n, np.float32); jK = np.zeros((n, 4), np.float32); jP = np.zeros((n, 6), np.float32)
+        I = np.zeros(n, np.float32); jK = np.zeros((n, self.intr_np[self.image_intr[image]]), np.float32); jP = np.zeros((n, 6), np.float32)
         if n:
             _lib.check(_L().b2_reg_get_point_jacobians(self._h, image, ps, _f(I), _f(jK), _f(jP)))
         return I, jK, jP
@@ -200,12 +224,14 @@ class Registration:
         return np.asarray(H), b, s, c.value
 
     def get_state(self):
-        ip = np.zeros((self.n_intr, 4), np.float32); po = np.zeros((self.n_img, 7), np.float32)
+        ip = np.zeros(sum(self.intr_np), np.float32); po = np.zeros((self.n_img, 7), np.float32)
         _lib.check(_L().b2_reg_get_state(self._h, _f(ip), _f(po)))
-        return ip, po
+        return self._intr_shape(ip), po
 
     def set_state(self, intr_params, poses):
-        ip = np.ascontiguousarray(intr_params, np.float32); po = np.ascontiguousarray(poses, np.float32)
+        ip = np.ascontiguousarray(intr_params, np.float32).reshape(-1); po = np.ascontiguousarray(poses, np.float32)
+        if ip.size != sum(self.intr_np):
+            raise ValueError("intrinsics parameter vector has %d entries, expected %d" % (ip.size, sum(self.intr_np)))
         _lib.check(_L().b2_reg_set_state(self._h, _f(ip), _f(po)))
 
     def cost_for_delta(self, delta):

@@ -1,5 +1,6 @@
-"""Synthetic Path B scene (data generator, not on the product path): a textured plane z = 0 seen by pinhole cameras looking
-down from ~2 m; images are rendered analytically (ray / plane intersection of every pixel, texture = sum of sinusoids); the
+"""Synthetic Path B scene (data generator, not on the product path): a textured plane z = 0 seen by cameras looking down from
+~2 m (pinhole, thin-prism or thin-prism-fisheye "benchmark" model); images are rendered analytically (every pixel is
+unprojected — numerically for the distorted models — and its ray intersected with the plane; texture = sum of sinusoids); the
 multi-resolution point cloud is a set of regular grids on the plane with the texture as grey colour and 5 grid neighbours."""
 import math
 
@@ -25,11 +26,41 @@ def rot(rx, ry, rz):
     return Rz @ Ry @ Rx
 
 
+CAM_PINHOLE, CAM_BENCHMARK, CAM_THIN_PRISM = 4, 5, 14
+# the distortion of the reference's benchmark-camera test (camera/test/test_camera.cc:508-515)
+DEFAULT_DISTORTION = (0.221184, 0.128597, 0.000531602, -0.000388873, 0.0623079, 0.20419, -0.000805024, 4.07704e-05)
+
+
+def _thin_prism(d, x, y):
+    k1, k2, p1, p2, k3, k4, sx1, sy1 = d
+    x2, xy, y2 = x * x, x * y, y * y
+    r2 = x2 + y2
+    radial = 1 + r2 * (k1 + r2 * (k2 + r2 * (k3 + r2 * k4)))
+    return (x * radial + 2 * p1 * xy + p2 * (r2 + 2 * x2) + sx1 * r2, y * radial + 2 * p2 * xy + p1 * (r2 + 2 * y2) + sy1 * r2)
+
+
+def unproject(camera_model, dist, dx, dy):
+    """Distorted (f-normalised) coordinates -> normalized ray coordinates (float64, damped fixed-point inversion)."""
+    if camera_model == CAM_PINHOLE:
+        return dx, dy
+    ux, uy = dx.copy(), dy.copy()
+    for _ in range(60):
+        fx_, fy_ = _thin_prism(dist, ux, uy)
+        ux = ux + 0.8 * (dx - fx_); uy = uy + 0.8 * (dy - fy_)
+    if camera_model == CAM_BENCHMARK:
+        r = np.sqrt(ux * ux + uy * uy)
+        f = np.where(r > 1e-9, np.tan(np.minimum(r, 1.5)) / np.maximum(r, 1e-9), 1.0)
+        ux, uy = ux * f, uy * f
+    return ux, uy
+
+
 def make_scene(num_images=3, width=640, height=480, fx=520.0, extent=(2.4, 1.8), base_radius=0.0025, num_scales=3, seed=31,
-               perturb=(0.002, 0.002)):
-    """Returns dict(intr=(w,h,[fx,fy,cx,cy]), images=[uint8 HxW], poses_gt, poses_init (qx qy qz qw tx ty tz), scales=[(xyz, radius, nbr, colors)])."""
+               perturb=(0.002, 0.002), camera_model=CAM_PINHOLE, distortion=DEFAULT_DISTORTION):
+    """Returns dict(intr=(w,h,params), camera_model, images=[uint8 HxW], poses_gt, poses_init (qx qy qz qw tx ty tz),
+    scales=[(xyz, radius, nbr, colors)]). params = fx fy cx cy (+ k1 k2 p1 p2 k3 k4 sx1 sy1 for the distorted models)."""
     rng = np.random.default_rng(seed)
     K = np.array([fx, fx, (width - 1) / 2.0, (height - 1) / 2.0], np.float32)
+    params = K if camera_model == CAM_PINHOLE else np.concatenate([K, np.asarray(distortion, np.float32)])
     images, poses_gt, poses_init = [], [], []
     for i in range(num_images):
         # camera centre above the plane, looking down (camera z axis = -world z), small tilts
@@ -38,7 +69,8 @@ def make_scene(num_images=3, width=640, height=480, fx=520.0, extent=(2.4, 1.8),
         R_cw = R_wc.T; t_cw = -R_cw @ c
         # render: pixel ray in camera frame -> world -> z=0
         yy, xx = np.mgrid[0:height, 0:width].astype(np.float64)
-        d_c = np.stack([(xx - K[2]) / K[0], (yy - K[3]) / K[1], np.ones_like(xx)], -1)
+        ux, uy = unproject(camera_model, distortion, (xx - K[2]) / K[0], (yy - K[3]) / K[1])
+        d_c = np.stack([ux, uy, np.ones_like(xx)], -1)
         d_w = d_c @ R_wc.T
         s = -c[2] / d_w[..., 2]
         pw = c + d_w * s[..., None]
@@ -66,13 +98,13 @@ def make_scene(num_images=3, width=640, height=480, fx=520.0, extent=(2.4, 1.8),
         nbr = np.where(same, alt, nbr)
         colors = texture(x, y).astype(np.float32)
         scales.append((xyz, np.float32(radius), nbr, colors))
-    return {"intr": (width, height, K), "images": images, "poses_gt": poses_gt, "poses_init": poses_init, "scales": scales}
+    return {"intr": (width, height, params), "camera_model": camera_model, "images": images, "poses_gt": poses_gt, "poses_init": poses_init, "scales": scales}
 
 
 def load_into(reg, scene, use_init=True, splats=True):
     """Feeds a scene into a Registration-like object (product mirror or oracle: same method names)."""
     w, h, K = scene["intr"]
-    reg.add_intrinsics(w, h, K)
+    reg.add_intrinsics(w, h, K, camera_model=scene.get("camera_model", CAM_PINHOLE))
     for img, T in zip(scene["images"], scene["poses_init"] if use_init else scene["poses_gt"]):
         reg.add_image(0, img, None, T)
     count = reg.initialize()

@@ -189,10 +189,21 @@ typedef struct b2_reg_stats {
   float ms_jacobian_kernel, ms_accumulate_kernel;   /* of the last accumulate */
 } b2_reg_stats;
 
+/* Stand-alone camera model evaluation: constructs the camera as the reference's constructors do (including the radius cut-off
+ * search, camera_base_impl.h:410-462; cutoffs[0] = radius_cutoff_squared() of the camera, cutoffs[1] = of a fisheye camera's inner
+ * model) and evaluates on the device: op 0 nothing, 1 NormalizedToImage (camera_base_impl.h:155-164; in n x 2, out n x 2),
+ * 2 ImageDerivativeByWorld (:350-356; in n x 3, out n x 6 row-major 2x3), 3 ImageDerivativeByIntrinsics (:362-408; in n x 3,
+ * out n x 2*num_params row-major). */
+int b2_camera_eval(int camera_model, int width, int height, const float* params, int num_params, int op, const float* in, size_t n, float* out,
+                   float cutoffs[2]);
+
 void b2_reg_default_params(b2_reg_params* p);
 int b2_reg_create(const b2_reg_params* p, b2_reg** out);
 int b2_reg_destroy(b2_reg* h);
-/* camera_model: 0 = PINHOLE (params fx fy cx cy; COLMAP's -0.5 px shift, colmap_model.cc:833, is the caller's job). */
+/* camera_model = camera::CameraBase::Type (camera_base.h:67-84): 4 PINHOLE (fx fy cx cy), 14 THIN_PRISM and 5 BENCHMARK = ETH3D's
+ * THIN_PRISM_FISHEYE (fx fy cx cy k1 k2 p1 p2 k3 k4 sx1 sy1, GetParameters order); 0 is accepted as PINHOLE. num_params must
+ * equal the model's ParameterCount(). COLMAP's -0.5 px shift (colmap_model.cc:833) is the caller's job. The radius cut-off
+ * search of the reference's camera constructors (camera_base_impl.h:410-462) runs on the device whenever intrinsics change. */
 int b2_reg_add_intrinsics(b2_reg* h, int camera_model, int width, int height, const float* params, int num_params, int* out_id);
 /* gray: width*height uint8 (cv::imread GRAYSCALE); mask: same size or NULL (values 0/1/2, image.h:43-47);
  * image_T_global: Sophus::SE3f::data() order qx qy qz qw tx ty tz (what io::ReadColmapImages fills, colmap_model.cc:117-124). */
@@ -217,7 +228,8 @@ int b2_reg_create_observations(b2_reg* h, int border_size);
 int b2_reg_num_observations(b2_reg* h, int image_id, int point_scale, uint64_t* count);
 int b2_reg_get_observations(b2_reg* h, int image_id, int point_scale, uint64_t* point_index, float* x, float* y, float* image_scale,
                             uint8_t* all_neighbors_observed);
-/* ComputePointIntensityAndJacobians of every observation of (image, scale): intensity[n], j_intrinsics[4n], j_pose[6n]. */
+/* ComputePointIntensityAndJacobians of every observation of (image, scale): intensity[n], j_intrinsics[np*n] (np = the image's
+ * camera model parameter count), j_pose[6n]. */
 int b2_reg_get_point_jacobians(b2_reg* h, int image_id, int point_scale, float* intensity, float* j_intrinsics, float* j_pose);
 int b2_reg_color_update(b2_reg* h);
 int b2_reg_get_descriptors(b2_reg* h, int point_scale, float* fixed_desc, float* variable_desc, int32_t* observation_counts);
@@ -226,7 +238,9 @@ int b2_reg_cost(b2_reg* h, double* cost, double sums[6]);
 /* Normal equations of IntrinsicsAndPoseOptimizer::Apply (:102-185): H nv*nv column-major (the Upper view the solver reads,
  * mirrored), b, sums, *cost = "initial residual". */
 int b2_reg_accumulate(b2_reg* h, double* H, double* b, double sums[6], double* cost);
-int b2_reg_get_state(b2_reg* h, float* intrinsics_params /*4 per intrinsics*/, float* poses /*7 per image*/);
+/* intrinsics_params: the parameter vectors of all intrinsics concatenated in id order (4 or 12 floats each) — also the order of
+ * the intrinsics blocks in the optimizer's variable vector, followed by 6 per image. */
+int b2_reg_get_state(b2_reg* h, float* intrinsics_params, float* poses /*7 per image*/);
 int b2_reg_set_state(b2_reg* h, const float* intrinsics_params, const float* poses);
 /* ComputeResidualForState for state (+) delta with the current observations' visibility lists frozen (:385-440). */
 int b2_reg_cost_for_delta(b2_reg* h, const double* delta, double* cost);

@@ -233,8 +233,18 @@ def _bind_reg():
     L.orc_reg_create.argtypes = [C.POINTER(RegParams)]; L.orc_reg_create.restype = vp
     L.orc_reg_destroy.argtypes = [vp]
     L.orc_reg_add_intrinsics.argtypes = [vp, C.c_int, C.c_int, fp]
+    L.orc_reg_add_intrinsics_model.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp]
+    L.orc_cam_param_count.argtypes = [C.c_int]
+    L.orc_cam_cutoff.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp]
+    L.orc_cam_eval.argtypes = [C.c_int, C.c_int, C.c_int, fp, C.c_int, fp, C.c_size_t, fp]
     L.orc_reg_add_image.argtypes = [vp, C.c_int, u8, u8, fp]
     L.orc_reg_initialize.argtypes = [vp]
+    L.orc_reg_add_rig.argtypes = [vp, C.c_int, fp]
+    L.orc_reg_add_rig_images.argtypes = [vp, C.c_int, ip]
+    L.orc_reg_get_rigs.argtypes = [vp, fp]
+    L.orc_reg_set_rigs.argtypes = [vp, fp]
+    L.orc_reg_variable_index.argtypes = [vp, C.c_int, C.c_int]
+    L.orc_reg_point_jacobians_rig.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, fp, fp, fp, fp]
     L.orc_reg_add_point_scale.argtypes = [vp, fp, C.c_size_t, C.c_float, u64p, fp]
     L.orc_reg_set_splat_points.argtypes = [vp, fp, C.c_size_t]
     L.orc_reg_set_mesh.argtypes = [vp, fp, C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t]
@@ -270,6 +280,39 @@ def _u8(a):
     return a.ctypes.data_as(C.POINTER(C.c_uint8))
 
 
+CAM_PINHOLE, CAM_BENCHMARK, CAM_THIN_PRISM = 4, 5, 14   # camera::CameraBase::Type values (camera_base.h:67-84)
+
+
+def cam_param_count(model):
+    n = _bind_reg().orc_cam_param_count(model)
+    if n < 0:
+        raise ValueError("unsupported camera model %d" % model)
+    return n
+
+
+def cam_cutoff(model, w, h, params):
+    """(radius_cutoff_squared of the camera, of a fisheye camera's inner model) after construction."""
+    p = _c32(params); out = np.zeros(2, np.float32)
+    if _bind_reg().orc_cam_cutoff(model, w, h, _f(p), _f(out)) != 0:
+        raise ValueError("unsupported camera model")
+    return float(out[0]), float(out[1])
+
+
+_CAM_OPS = {"distort": (0, 2, 2), "project": (1, 2, 2), "d_by_world": (2, 3, 6), "d_by_intrinsics": (3, 3, None), "undistort": (4, 2, 2),
+            "distort_deriv": (5, 2, 4)}
+
+
+def cam_eval(model, w, h, params, op, pts):
+    code, nin, nout = _CAM_OPS[op]
+    p = _c32(params); x = _c32(pts).reshape(-1, nin)
+    if nout is None:
+        nout = 2 * cam_param_count(model)
+    out = np.zeros((x.shape[0], nout), np.float32)
+    if _bind_reg().orc_cam_eval(model, w, h, _f(p), code, _f(x), x.shape[0], _f(out)) != 0:
+        raise ValueError("orc_cam_eval failed")
+    return out
+
+
 def reg_default_params(**kw):
     p = RegParams()
     _bind_reg().orc_reg_default_params(C.byref(p))
@@ -287,15 +330,52 @@ class Registration:
         self.params = params or reg_default_params()
         self._h = C.c_void_p(L.orc_reg_create(C.byref(self.params)))
         self.K = self.params.point_neighbor_count
-        self.n_intr = 0; self.n_img = 0; self.scale_sizes = []
+        self.n_intr = 0; self.n_img = 0; self.scale_sizes = []; self.intr_np = []; self.rig_cams = []
 
     def __del__(self):
         if getattr(self, "_h", None):
             lib().orc_reg_destroy(self._h); self._h = None
 
-    def add_intrinsics(self, w, h, params):
-        p = _c32(params); self.n_intr += 1
-        return lib().orc_reg_add_intrinsics(self._h, w, h, _f(p))
+    def add_intrinsics(self, w, h, params, camera_model=CAM_PINHOLE):
+        model = camera_model
+        p = _c32(params)
+        if p.size != cam_param_count(model):
+            raise ValueError("camera model %d takes %d parameters" % (model, cam_param_count(model)))
+        self.n_intr += 1; self.intr_np.append(int(p.size))
+        return lib().orc_reg_add_intrinsics_model(self._h, model, w, h, _f(p))
+
+    def add_rig(self, image_T_rig):
+        """image_T_rig: (num_cameras, 7) qx qy qz qw tx ty tz, camera 0 = reference (identity)."""
+        T = _c32(image_T_rig).reshape(-1, 7)
+        rid = lib().orc_reg_add_rig(self._h, T.shape[0], _f(T))
+        if rid < 0:
+            raise ValueError("a rig needs at least two cameras")
+        self.rig_cams.append(T.shape[0])
+        return rid
+
+    def add_rig_images(self, rig_id, image_ids):
+        ids = np.ascontiguousarray(image_ids, np.int32)
+        r = lib().orc_reg_add_rig_images(self._h, rig_id, ids.ctypes.data_as(C.POINTER(C.c_int)))
+        if r < 0:
+            raise ValueError("bad rig image set")
+        return r
+
+    def get_rigs(self):
+        out = np.zeros((sum(self.rig_cams), 7), np.float32)
+        lib().orc_reg_get_rigs(self._h, _f(out))
+        return out
+
+    def set_rigs(self, image_T_rig_all):
+        T = _c32(image_T_rig_all).reshape(-1, 7)
+        assert T.shape[0] == sum(self.rig_cams)
+        lib().orc_reg_set_rigs(self._h, _f(T))
+
+    def variable_index(self, kind, idx):
+        """kind: "intrinsics" | "rig" | "image" -> first variable of that block."""
+        return lib().orc_reg_variable_index(self._h, {"intrinsics": 0, "rig": 1, "image": 2}[kind], idx)
+
+    def _intr_shape(self, flat):
+        return flat.reshape(self.n_intr, -1) if len(set(self.intr_np)) == 1 else flat
 
     def add_image(self, intr_id, gray, mask, image_T_global):
         g = np.ascontiguousarray(gray, np.uint8); T = _c32(image_T_global)
@@ -375,12 +455,13 @@ class Registration:
         return np.asarray(H), b, s, c
 
     def get_state(self):
-        ip = np.zeros((self.n_intr, 4), np.float32); po = np.zeros((self.n_img, 7), np.float32)
+        ip = np.zeros(sum(self.intr_np), np.float32); po = np.zeros((self.n_img, 7), np.float32)
         lib().orc_reg_get_state(self._h, _f(ip), _f(po))
-        return ip, po
+        return self._intr_shape(ip), po
 
     def set_state(self, intr_params, poses):
-        ip = _c32(intr_params); po = _c32(poses)
+        ip = _c32(intr_params).reshape(-1); po = _c32(poses)
+        assert ip.size == sum(self.intr_np)
         lib().orc_reg_set_state(self._h, _f(ip), _f(po))
 
     def cost_for_delta(self, delta):
@@ -397,8 +478,13 @@ class Registration:
         it = lib().orc_reg_run_on_current_scale(self._h, max_it, max_change_thr, no_opt_thr, C.byref(oc), C.byref(cv))
         return it, oc.value, bool(cv.value)
 
-    def point_jacobians(self, image, ps, obs_index):
-        I = C.c_float(0); jk = np.zeros(4, np.float32); jp = np.zeros(6, np.float32)
+    def point_jacobians_rig(self, image, ps, obs_index, np_intr=4):
+        I = C.c_float(0); jk = np.zeros(np_intr, np.float32); jp = np.zeros(6, np.float32); jr = np.zeros(6, np.float32)
+        lib().orc_reg_point_jacobians_rig(self._h, image, ps, obs_index, C.byref(I), _f(jk), _f(jp), _f(jr))
+        return I.value, jk, jp, jr
+
+    def point_jacobians(self, image, ps, obs_index, np_intr=4):
+        I = C.c_float(0); jk = np.zeros(np_intr, np.float32); jp = np.zeros(6, np.float32)
         lib().orc_reg_point_jacobians(self._h, image, ps, obs_index, C.byref(I), _f(jk), _f(jp))
         return I.value, jk, jp
 

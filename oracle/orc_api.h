@@ -70,10 +70,22 @@ typedef struct orc_reg_params {   /* mirror of opt::Parameters (src/opt/paramete
 void orc_reg_default_params(orc_reg_params*);
 orc_reg* orc_reg_create(const orc_reg_params*);
 void orc_reg_destroy(orc_reg*);
-int orc_reg_add_intrinsics(orc_reg*, int w, int h, const float fx_fy_cx_cy[4]);
+int orc_reg_add_intrinsics(orc_reg*, int w, int h, const float fx_fy_cx_cy[4]);   /* pinhole */
+/* type = camera::CameraBase::Type value: 4 pinhole (4 params), 14 thin prism (12), 5 benchmark = thin-prism fisheye (12);
+ * params in GetParameters order: fx fy cx cy k1 k2 p1 p2 k3 k4 sx1 sy1. Returns -1 for an unsupported type. */
+int orc_reg_add_intrinsics_model(orc_reg*, int type, int w, int h, const float* params);
 /* image_T_global as Sophus::SE3f::data(): qx qy qz qw tx ty tz */
 int orc_reg_add_image(orc_reg*, int intrinsics_id, const uint8_t* gray, const uint8_t* mask_or_null, const float image_T_global[7]);
 int orc_reg_initialize(orc_reg*);
+/* rigs (rig.h:40-73, rig_images.h:38-64): image_T_rig 7 floats per camera, camera 0 = reference; add_rig_images binds one image per
+ * camera (all present) and sets the dependent images' poses to image_T_rig[c] * pose(reference). -1 on bad arguments. */
+int orc_reg_add_rig(orc_reg*, int num_cameras, const float* image_T_rig);
+int orc_reg_add_rig_images(orc_reg*, int rig_id, const int* image_ids);
+void orc_reg_get_rigs(orc_reg*, float* image_T_rig_all);
+void orc_reg_set_rigs(orc_reg*, const float* image_T_rig_all);
+/* first variable of an intrinsics block (kind 0), of a rig's extrinsics block (1), of the pose block an image uses (2) */
+int orc_reg_variable_index(orc_reg*, int kind, int id);
+void orc_reg_point_jacobians_rig(orc_reg*, int image, int point_scale, uint64_t obs_index, float* intensity, float* jK, float jP[6], float* jR);
 int orc_reg_add_point_scale(orc_reg*, const float* xyz, size_t n, float radius, const uint64_t* neighbor_indices, const float* colors);
 void orc_reg_set_splat_points(orc_reg*, const float* xyz, size_t n);
 void orc_reg_set_mesh(orc_reg*, const float* vertices, size_t nv, const uint32_t* faces, size_t nf);
@@ -95,10 +107,20 @@ void orc_reg_set_state(orc_reg*, const float* intr_params, const float* poses);
 double orc_reg_cost_for_delta(orc_reg*, const double* delta);
 int orc_reg_apply(orc_reg*, float* lambda, float* max_change, int* applied);
 int orc_reg_run_on_current_scale(orc_reg*, int max_it, float max_change_thr, int no_opt_thr, double* optimum_cost, int* converged);
-void orc_reg_point_jacobians(orc_reg*, int image, int point_scale, uint64_t obs_index, float* intensity, float jK[4], float jP[6]);
+void orc_reg_point_jacobians(orc_reg*, int image, int point_scale, uint64_t obs_index, float* intensity, float* jK /* np */, float jP[6]);
 int orc_interp_bilinear(const uint8_t* img, int w, int h, float x, float y, float* v, float* dx, float* dy);
 void orc_interp_trilinear(const uint8_t* img0, int w0, int h0, const uint8_t* img1, float x, float y, float z, float* v, float* dx, float* dy, float* dz);
 float orc_robust(int type, float p, float r, int weight);
+
+/* ---- camera models (orc_camera.h) ---- */
+int orc_cam_param_count(int type);   /* -1 unsupported */
+/* constructs the camera (runs the cut-off search as the reference constructors do); out[0] = radius_cutoff_squared of the
+ * camera itself, out[1] = of the inner model of a fisheye camera (inf otherwise) */
+int orc_cam_cutoff(int type, int w, int h, const float* params, float out[2]);
+/* op: 0 Distort(n) -> 2, 1 NormalizedToImage(n) -> 2, 2 ImageDerivativeByWorld(p) -> 6, 3 ImageDerivativeByIntrinsics(p) -> 2*np,
+ * 4 Undistort(distorted) -> 2 (camera_base_impl.h:252-255 / camera_base_impl_fisheye.h:80-91), 5 DistortedDerivativeByNormalized(n) -> 4.
+ * in: n x 2 (ops 0,1,4,5) or n x 3 (ops 2,3) floats. */
+int orc_cam_eval(int type, int w, int h, const float* params, int op, const float* in, size_t n, float* out);
 void orc_image_pyramid_level(const uint8_t* src, int w, int h, uint8_t* dst);
 
 #ifdef __cplusplus

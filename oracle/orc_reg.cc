@@ -29,44 +29,13 @@
 #include <vector>
 
 #include "orc_api.h"
+#include "orc_camera.h"
 #include "orc_math.h"
 #include "orc_mesh.h"
 
 namespace orc {
 
-struct Pinhole {   // one pyramid level of camera::PinholeCamera
-  int w, h;
-  float fx, fy, cx, cy, fx_inv, fy_inv, cx_inv, cy_inv;
-  void set(int w_, int h_, float fx_, float fy_, float cx_, float cy_) {
-    w = w_; h = h_; fx = fx_; fy = fy_; cx = cx_; cy = cy_;
-    fx_inv = (float)(1.0 / fx); fy_inv = (float)(1.0 / fy);                 // camera_base.cc:83
-    cx_inv = (float)(-1.0 * cx / fx); cy_inv = (float)(-1.0 * cy / fy);
-  }
-  Pinhole scaled_half() const {                                            // camera_base_impl.h:70-89, factor 0.5
-    const float f = 0.5f;
-    Pinhole s;
-    s.set((int)(f * w + 0.5f), (int)(f * h + 0.5f), fx * f, fy * f, f * (cx + 0.5f) - 0.5f, f * (cy + 0.5f) - 0.5f);
-    return s;
-  }
-  // NormalizedToImage (camera_base_impl.h:155-164): pinhole has no cutoff; inf r2 -> inf.
-  void project(float nx, float ny, float* ix, float* iy) const {
-    const float r2 = nx * nx + ny * ny;
-    if (std::isinf(r2)) { *ix = nx * std::numeric_limits<float>::infinity(); *iy = ny * std::numeric_limits<float>::infinity(); return; }
-    *ix = fx * nx + cx; *iy = fy * ny + cy;
-  }
-  // ImageDerivativeByWorld (camera_base_impl.h:333-360): f.asDiagonal() * [I/z | -n/z]
-  void d_by_world(const V3f& p, float d[6]) const {
-    const float nx = p.x / p.z, ny = p.y / p.z;
-    const float z_inv = 1.f / p.z;
-    d[0] = fx * (1.f * z_inv); d[1] = fx * (0.f * z_inv); d[2] = fx * (-1.f * nx * z_inv);
-    d[3] = fy * (0.f * z_inv); d[4] = fy * (1.f * z_inv); d[5] = fy * (-1.f * ny * z_inv);
-  }
-  // ImageDerivativeByIntrinsics (camera_base_impl.h:369-408), 2x4: [x 0 1 0; 0 y 0 1]
-  void d_by_intrinsics(const V3f& p, float d[8]) const {
-    d[0] = p.x / p.z; d[1] = 0.f; d[2] = 1.f; d[3] = 0.f;
-    d[4] = 0.f; d[5] = p.y / p.z; d[6] = 0.f; d[7] = 1.f;
-  }
-};
+typedef Camera Pinhole;   // historical name: one pyramid level of a camera model (orc_camera.h)
 
 struct Img8 { int w = 0, h = 0; std::vector<uint8_t> d; uint8_t at(int y, int x) const { return d[(size_t)y * w + x]; } };
 struct ImgF { int w = 0, h = 0; std::vector<float> d; float at(int y, int x) const { return d[(size_t)y * w + x]; } };
@@ -135,6 +104,7 @@ struct Intrinsics {
 
 struct Image {
   int intrinsics_id = 0;
+  int rig_images_id = -1, rig_camera_index = 0;   // image.h rig_images_id; index of this image in its RigImages::image_ids
   SE3f image_T_global;
   std::vector<Img8> image, mask;   // pyramids (mask levels may be empty)
   ImgF given_depth; bool has_given_depth = false;
@@ -147,7 +117,11 @@ struct ScalePoints {
   size_t n() const { return xyz.size() / 3; }
 };
 
-struct State { std::vector<Intrinsics> intr; std::vector<Image> images; };
+// rig.h:40-73, rig_images.h:38-64. image_T_rig[0] stays identity; the other extrinsics are optimized.
+struct Rig { std::vector<SE3f> image_T_rig; };
+struct RigImages { int rig_id = 0; std::vector<int> image_ids; };
+
+struct State { std::vector<Intrinsics> intr; std::vector<Image> images; std::vector<Rig> rigs; };
 
 }  // namespace orc
 
@@ -158,6 +132,7 @@ struct orc_reg {
   Robust robust;
   State st;
   std::vector<ScalePoints> pts;
+  std::vector<RigImages> rig_images;
   std::vector<float> splat_xyz; bool has_splats = false;
   OccMesh mesh; bool has_mesh = false;
   int image_scale_count = 0, current_image_scale = 0;
@@ -225,7 +200,8 @@ static ImgF render_depth(const orc_reg* h, const Intrinsics& intr, const Image& 
     float rx = std::sqrt(sum3(d[0] * d[0], d[1] * d[1], d[2] * d[2])) * h->prm.splat_radius;
     float ry = std::sqrt(sum3(d[3] * d[3], d[4] * d[4], d[5] * d[5])) * h->prm.splat_radius;
     rx = std::min(rx, max_splat_radius); ry = std::min(ry, max_splat_radius);
-    const int ix = px + 0.5f, iy = py + 0.5f;
+    const int ix = f2i(px + 0.5f), iy = f2i(py + 0.5f);
+    if (ix == std::numeric_limits<int>::min() || iy == std::numeric_limits<int>::min()) continue;   // beyond the cut-off radius
     const int min_x = std::max(0, int(ix - rx + 0.5)), min_y = std::max(0, int(iy - ry + 0.5));
     const int end_x = std::min(cam.w, int(ix + rx + 1.5)), end_y = std::min(cam.h, int(iy + ry + 1.5));
     if (min_y < end_y && min_x < end_x)
@@ -244,6 +220,7 @@ static void create_observation_if_scale_fits(const orc_reg* h, const Intrinsics&
   const float dx = rx - ixx, dy = ry - ixy;
   const float radius_pixels = std::sqrt(dx * dx + dy * dy);
   const float observation_scale = image_scale + log2((double)(2 * radius_pixels));   // ::log2(double); float-vs-double overload UNPINNED (differs by <= 1 ulp)
+  if (!std::isfinite(observation_scale)) return;   // offset point beyond the cut-off radius: the reference's int cast is UB there
   if (observation_scale >= std::max(intr.min_image_scale, h->current_image_scale) &&
       static_cast<int>(observation_scale) < h->image_scale_count - 1) {
     const int small = static_cast<int>(observation_scale) + 1;
@@ -287,7 +264,7 @@ static void append_observations(const orc_reg* h, const Image& im, const Intrins
       V3f pp; rigid_pp(R, im.image_T_global.t, &P.xyz[3 * pi], &pp);
       if (pp.z > 0.f) {
         float ixx, ixy; cam.project(pp.x / pp.z, pp.y / pp.z, &ixx, &ixy);
-        const int ix = ixx + 0.5f, iy = ixy + 0.5f;
+        const int ix = f2i(ixx + 0.5f), iy = f2i(ixy + 0.5f);
         if (ix >= 0 && iy >= 0 && ix < cam.w && iy < cam.h &&
             (lists || depth.d[(size_t)iy * depth.w + ix] + h->prm.occlusion_depth_threshold >= pp.z))
           create_observation_if_scale_fits(h, intr, im, cam, best, pi, pp, P.radius, ixx, ixy, border, !lists, &o);
@@ -311,10 +288,16 @@ static void neighbors_observed(const orc_reg* h, int ps, const std::vector<Obser
   }
 }
 
-// ComputePointIntensityAndJacobians (intrinsics_and_pose_optimizer.cc:933-1147), non-rig, no depth residual.
+// What a dependent rig image (camera index > 0) adds to ComputePointIntensityAndJacobians (intrinsics_and_pose_optimizer.cc:651-670).
+struct RigCtx { bool dependent = false; SE3f image_T_rig, rig_T_global; };
+
+// ComputePointIntensityAndJacobians (intrinsics_and_pose_optimizer.cc:933-1147), no depth residual. For a dependent rig image jP is
+// the derivative by the REFERENCE image's pose and jR (6) the derivative by the rig extrinsics of this camera.
 static void point_intensity_and_jacobians(const orc_reg* h, const Intrinsics& intr, const Image& im, const float R[9], float point_radius,
-                                          const float* point, const Observation& ob, float* intensity, float jK[4], float jP[6]) {
+                                          const float* point, const Observation& ob, float* intensity, float* jK /* np */, float jP[6],
+                                          const RigCtx* rig = nullptr, float* jR = nullptr) {
   const Pinhole& cam = intr.model(0);
+  const int np = cam.np();
   V3f tp; rigid_pp(R, im.image_T_global.t, point, &tp);
   float ji[3];
   const Img8& i0 = im.image[smaller_scale(ob) - intr.min_image_scale];
@@ -329,10 +312,10 @@ static void point_intensity_and_jacobians(const orc_reg* h, const Intrinsics& in
   float ox, oy; cam.project(tpo.x / tpo.z, tpo.y / tpo.z, &ox, &oy);
   const float rdx = ox - mx, rdy = oy - my;
   const float denom = std::max(1e-6f, 0.693147180559945f * (rdx * rdx + rdy * rdy));
-  float jpi[12], jpoi[8];   // 3x4 row-major, 2x4
+  float jpi[36], jpoi[24];   // 3 x np row-major, 2 x np
   cam.d_by_intrinsics(tp, jpi); cam.d_by_intrinsics(tpo, jpoi);
-  for (int i = 0; i < 4; ++i) jpi[8 + i] = ((jpoi[i] - jpi[i]) * rdx + (jpoi[4 + i] - jpi[4 + i]) * rdy) / denom;
-  for (int i = 0; i < 4; ++i) jK[i] = sum3(ji[0] * jpi[i], ji[1] * jpi[4 + i], ji[2] * jpi[8 + i]);
+  for (int i = 0; i < np; ++i) jpi[2 * np + i] = ((jpoi[i] - jpi[i]) * rdx + (jpoi[np + i] - jpi[np + i]) * rdy) / denom;
+  for (int i = 0; i < np; ++i) jK[i] = sum3(ji[0] * jpi[i], ji[1] * jpi[np + i], ji[2] * jpi[2 * np + i]);
   float jpp[9], jpop[6];    // 3x3 row-major, 2x3
   cam.d_by_world(tp, jpp); cam.d_by_world(tpo, jpop);
   for (int i = 0; i < 3; ++i) jpp[6 + i] = ((jpop[i] - jpp[i]) * rdx + (jpop[3 + i] - jpp[3 + i]) * rdy) / denom;
@@ -340,6 +323,19 @@ static void point_intensity_and_jacobians(const orc_reg* h, const Intrinsics& in
   for (int i = 0; i < 3; ++i) a[i] = sum3(ji[0] * jpp[i], ji[1] * jpp[3 + i], ji[2] * jpp[6 + i]);
   // [I | -[p]x] rows: (1,0,0,0,z,-y), (0,1,0,-z,0,x), (0,0,1,y,-x,0)
   const float C[18] = {1, 0, 0, 0, tp.z, -1 * tp.y, 0, 1, 0, -1 * tp.z, 0, tp.x, 0, 0, 1, tp.y, -1 * tp.x, 0};
+  if (rig && rig->dependent) {
+    // :1107-1143: j_pose = ((ji * jpp) * image_T_rig.rotationMatrix()) * [I | -[rig_point]x], rig_point = rig_T_global * point (Sophus
+    // SE3 * point: quaternion rotation + translation); j_rig_extrinsics = (ji * jpp) * [I | -[transformed_point]x]
+    const V3f rp0 = quat_rotate(rig->rig_T_global.q, V3f{point[0], point[1], point[2]});
+    const V3f rp{rp0.x + rig->rig_T_global.t.x, rp0.y + rig->rig_T_global.t.y, rp0.z + rig->rig_T_global.t.z};
+    float Rr[9]; quat_to_matrix(rig->image_T_rig.q, Rr);
+    float ar[3];
+    for (int i = 0; i < 3; ++i) ar[i] = sum3(a[0] * Rr[i], a[1] * Rr[3 + i], a[2] * Rr[6 + i]);
+    const float Cr[18] = {1, 0, 0, 0, rp.z, -1 * rp.y, 0, 1, 0, -1 * rp.z, 0, rp.x, 0, 0, 1, rp.y, -1 * rp.x, 0};
+    for (int c = 0; c < 6; ++c) jP[c] = sum3(ar[0] * Cr[c], ar[1] * Cr[6 + c], ar[2] * Cr[12 + c]);
+    for (int c = 0; c < 6; ++c) jR[c] = sum3(a[0] * C[c], a[1] * C[6 + c], a[2] * C[12 + c]);
+    return;
+  }
   for (int c = 0; c < 6; ++c) jP[c] = sum3(a[0] * C[c], a[1] * C[6 + c], a[2] * C[12 + c]);
 }
 
@@ -379,26 +375,37 @@ static void accumulate_residuals(const orc_reg* h, const Intrinsics& intr, const
 }
 
 // AccumulateOnHAndB (intrinsics_and_pose_optimizer.cc:1220-1296): fp32 products cast to double, upper triangles + full cross block.
-static void accumulate_on_H_b(float w, float res, int iv, int pv, const float jK[4], const float jP[6], std::vector<double>* H, std::vector<double>* b, int nv) {
+static void accumulate_on_H_b(float w, float res, int iv, int pv, int np, const float* jK, const float jP[6], std::vector<double>* H, std::vector<double>* b, int nv,
+                              int rv = -1, const float* jR = nullptr) {
   if (w == 0) return;
   auto Hh = [&](int r, int c) -> double& { return (*H)[(size_t)c * nv + r]; };
-  for (int c = 0; c < 4; ++c) for (int r = 0; r <= c; ++r) Hh(iv + r, iv + c) += (double)(w * jK[r] * jK[c]);
-  for (int r = 0; r < 4; ++r) for (int c = 0; c < 6; ++c) Hh(iv + r, pv + c) += (double)(w * jK[r] * jP[c]);
+  for (int c = 0; c < np; ++c) for (int r = 0; r <= c; ++r) Hh(iv + r, iv + c) += (double)(w * jK[r] * jK[c]);
+  for (int r = 0; r < np; ++r) for (int c = 0; c < 6; ++c) Hh(iv + r, pv + c) += (double)(w * jK[r] * jP[c]);
   for (int c = 0; c < 6; ++c) for (int r = 0; r <= c; ++r) Hh(pv + r, pv + c) += (double)(w * jP[r] * jP[c]);
+  if (rv >= 0) {   // dependent rig image (:1262-1283): top middle, middle (upper), middle right
+    for (int r = 0; r < np; ++r) for (int c = 0; c < 6; ++c) Hh(iv + r, rv + c) += (double)(w * jK[r] * jR[c]);
+    for (int c = 0; c < 6; ++c) for (int r = 0; r <= c; ++r) Hh(rv + r, rv + c) += (double)(w * jR[r] * jR[c]);
+    for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) Hh(rv + r, pv + c) += (double)(w * jR[r] * jP[c]);
+  }
   const float wr = w * res;
-  for (int i = 0; i < 4; ++i) (*b)[iv + i] += (double)(wr * jK[i]);
+  for (int i = 0; i < np; ++i) (*b)[iv + i] += (double)(wr * jK[i]);
   for (int i = 0; i < 6; ++i) (*b)[pv + i] += (double)(wr * jP[i]);
+  if (rv >= 0) for (int i = 0; i < 6; ++i) (*b)[rv + i] += (double)(wr * jR[i]);
 }
 
 // AccumulateHAndBAndResidualsForObservations (intrinsics_and_pose_optimizer.cc:624-837) + ...ForColorObservation (:840-930)
 static void accumulate_H_b(const orc_reg* h, const Intrinsics& intr, const Image& im, int ps, const std::vector<Observation>& o,
-                           const std::vector<uint8_t>& nb, int iv, int pv, Sums* s, std::vector<double>* H, std::vector<double>* b, int nv) {
+                           const std::vector<uint8_t>& nb, int iv, int pv, Sums* s, std::vector<double>* H, std::vector<double>* b, int nv,
+                           const RigCtx* rig = nullptr, int rv = -1) {
   const ScalePoints& P = h->pts[ps];
   float R[9]; quat_to_matrix(im.image_T_global.q, R);
-  std::vector<float> inten(o.size()), jK(4 * o.size()), jP(6 * o.size());
+  const int np = intr.model(0).np();
+  const bool dep = rig && rig->dependent;
+  std::vector<float> inten(o.size()), jK((size_t)np * o.size()), jP(6 * o.size()), jR(dep ? 6 * o.size() : 0);
   std::vector<int64_t> jac_of_point(P.n(), -1);
   for (size_t i = 0; i < o.size(); ++i) {
-    point_intensity_and_jacobians(h, intr, im, R, P.radius, &P.xyz[3 * o[i].point_index], o[i], &inten[i], &jK[4 * i], &jP[6 * i]);
+    point_intensity_and_jacobians(h, intr, im, R, P.radius, &P.xyz[3 * o[i].point_index], o[i], &inten[i], &jK[(size_t)np * i], &jP[6 * i],
+                                  rig, dep ? &jR[6 * i] : nullptr);
     jac_of_point[o[i].point_index] = (int64_t)i;
   }
   if (h->prm.fixed_residuals_weight == 0 && h->prm.variable_residuals_weight == 0) return;
@@ -417,10 +424,11 @@ static void accumulate_H_b(const orc_reg* h, const Intrinsics& intr, const Image
     if (w != 0) {
       for (int k = 0; k < K(h); ++k) {
         const size_t nj = (size_t)jac_of_point[P.nbr[pi * K(h) + k]];
-        float dK[4], dP[6];
-        for (int i = 0; i < 4; ++i) dK[i] = jK[4 * nj + i] - jK[4 * oj + i];
+        float dK[12], dP[6], dR[6];
+        for (int i = 0; i < np; ++i) dK[i] = jK[(size_t)np * nj + i] - jK[(size_t)np * oj + i];
         for (int i = 0; i < 6; ++i) dP[i] = jP[6 * nj + i] - jP[6 * oj + i];
-        accumulate_on_H_b(w, comp[k], iv, pv, dK, dP, H, b, nv);
+        if (dep) for (int i = 0; i < 6; ++i) dR[i] = jR[6 * nj + i] - jR[6 * oj + i];
+        accumulate_on_H_b(w, comp[k], iv, pv, np, dK, dP, H, b, nv, dep ? rv : -1, dR);
       }
     }
   };
@@ -432,17 +440,48 @@ static void accumulate_H_b(const orc_reg* h, const Intrinsics& intr, const Image
   }
 }
 
-static int num_variables(const orc_reg* h) { return 4 * (int)h->st.intr.size() + 6 * (int)h->st.images.size(); }
-static int intr_var(const orc_reg*, int id) { return 4 * id; }
-static int pose_var(const orc_reg* h, int image_id) { return 4 * (int)h->st.intr.size() + 6 * image_id; }
+// Variable layout (CountAndIndexVariables, intrinsics_and_pose_optimizer.cc:442-473): [intrinsics 0 (np0) | intrinsics 1 | ... |
+// rig 0 extrinsics (6 per camera after the first) | rig 1 | ... | poses (6 each) of the images that own one: non-rig images and rig
+// reference images, ascending image id]. A dependent rig image uses its reference image's pose block.
+static int intr_var(const orc_reg* h, int id) { int v = 0; for (int i = 0; i < id; ++i) v += h->st.intr[i].models[0].np(); return v; }
+static int rig_var(const orc_reg* h, int rig_id) {
+  int v = intr_var(h, (int)h->st.intr.size());
+  for (int r = 0; r < rig_id; ++r) v += 6 * ((int)h->st.rigs[r].image_T_rig.size() - 1);
+  return v;
+}
+static bool is_dependent(const orc_reg* h, int image_id) { const Image& im = h->st.images[image_id]; return im.rig_images_id >= 0 && im.rig_camera_index > 0; }
+static int ref_image(const orc_reg* h, int image_id) {
+  const Image& im = h->st.images[image_id];
+  return is_dependent(h, image_id) ? h->rig_images[im.rig_images_id].image_ids[0] : image_id;
+}
+static int pose_var(const orc_reg* h, int image_id) {
+  const int owner = image_id < (int)h->st.images.size() ? ref_image(h, image_id) : image_id;
+  int v = rig_var(h, (int)h->st.rigs.size());
+  for (int i = 0; i < owner; ++i) if (!is_dependent(h, i)) v += 6;
+  return v;
+}
+static int num_variables(const orc_reg* h) { return pose_var(h, (int)h->st.images.size()); }
+static RigCtx rig_ctx(const orc_reg* h, const State& st, int image_id, int* rv) {
+  RigCtx c; *rv = -1;
+  if (!is_dependent(h, image_id)) return c;
+  const Image& im = st.images[image_id];
+  const RigImages& ri = h->rig_images[im.rig_images_id];
+  c.dependent = true;
+  c.image_T_rig = st.rigs[ri.rig_id].image_T_rig[im.rig_camera_index];
+  c.rig_T_global = st.images[ri.image_ids[0]].image_T_global;
+  *rv = rig_var(h, ri.rig_id) + 6 * (im.rig_camera_index - 1);
+  return c;
+}
 
 static void accumulate_all(const orc_reg* h, std::vector<double>* H, std::vector<double>* b, Sums* s) {
   const int nv = num_variables(h);
   H->assign((size_t)nv * nv, 0.0); b->assign(nv, 0.0);
-  for (size_t im = 0; im < h->st.images.size(); ++im)
+  for (size_t im = 0; im < h->st.images.size(); ++im) {
+    int rv; const RigCtx rc = rig_ctx(h, h->st, (int)im, &rv);
     for (size_t ps = 0; ps < h->pts.size(); ++ps)
       accumulate_H_b(h, h->st.intr[h->st.images[im].intrinsics_id], h->st.images[im], (int)ps, h->obs[im][ps], h->nbr_obs[im][ps],
-                     intr_var(h, h->st.images[im].intrinsics_id), pose_var(h, (int)im), s, H, b, nv);
+                     intr_var(h, h->st.images[im].intrinsics_id), pose_var(h, (int)im), s, H, b, nv, &rc, rv);
+  }
 }
 
 // CreateDeltaState (intrinsics_and_pose_optimizer.cc:475-558): params += delta (fp32 += double), pose <- exp(delta).cast<float>() * pose.
@@ -450,14 +489,25 @@ static State delta_state(const orc_reg* h, const std::vector<double>& delta) {
   State n = h->st;
   for (size_t i = 0; i < n.intr.size(); ++i) {
     Pinhole& m = n.intr[i].models[0];
-    float p[4] = {m.fx, m.fy, m.cx, m.cy};
-    for (int k = 0; k < 4; ++k) p[k] += delta[intr_var(h, (int)i) + k];
-    m.set(m.w, m.h, p[0], p[1], p[2], p[3]);
+    float p[12]; m.get_params(p);
+    for (int k = 0; k < m.np(); ++k) p[k] += delta[intr_var(h, (int)i) + k];
+    m.set(m.type, m.w, m.h, p);
     n.intr[i].build_pyramid();
   }
-  for (size_t i = 0; i < n.images.size(); ++i) {
+  for (size_t r = 0; r < n.rigs.size(); ++r)           // Rig::Update (rig.cc:9-23)
+    for (size_t c = 1; c < n.rigs[r].image_T_rig.size(); ++c) {
+      double d[6]; for (int k = 0; k < 6; ++k) d[k] = delta[rig_var(h, (int)r) + 6 * ((int)c - 1) + k];
+      n.rigs[r].image_T_rig[c] = se3_mul(se3d_exp_cast_float(d), h->st.rigs[r].image_T_rig[c]);
+    }
+  for (size_t i = 0; i < n.images.size(); ++i) {        // pose owners first (:517-534, 556-563)
+    if (is_dependent(h, (int)i)) continue;
     double d[6]; for (int k = 0; k < 6; ++k) d[k] = delta[pose_var(h, (int)i) + k];
     n.images[i].image_T_global = se3_mul(se3d_exp_cast_float(d), h->st.images[i].image_T_global);
+  }
+  for (size_t i = 0; i < n.images.size(); ++i) {        // dependent rig images from the UPDATED rig pose and extrinsics (:546-555)
+    if (!is_dependent(h, (int)i)) continue;
+    const RigImages& ri = h->rig_images[n.images[i].rig_images_id];
+    n.images[i].image_T_global = se3_mul(n.rigs[ri.rig_id].image_T_rig[n.images[i].rig_camera_index], n.images[ri.image_ids[0]].image_T_global);
   }
   return n;
 }
@@ -495,8 +545,10 @@ orc_reg* orc_reg_create(const orc_reg_params* p) {
 }
 void orc_reg_destroy(orc_reg* h) { delete h; }
 
-int orc_reg_add_intrinsics(orc_reg* h, int w, int hh, const float p[4]) {
-  Intrinsics in; in.models.resize(1); in.models[0].set(w, hh, p[0], p[1], p[2], p[3]);
+int orc_reg_add_intrinsics(orc_reg* h, int w, int hh, const float p[4]) { return orc_reg_add_intrinsics_model(h, kCamPinhole, w, hh, p); }
+int orc_reg_add_intrinsics_model(orc_reg* h, int type, int w, int hh, const float* p) {
+  if (!Camera::known(type)) return -1;
+  Intrinsics in; in.models.resize(1); in.models[0].set(type, w, hh, p);
   h->st.intr.push_back(in); return (int)h->st.intr.size() - 1;
 }
 int orc_reg_add_image(orc_reg* h, int intr_id, const uint8_t* gray, const uint8_t* mask, const float T[7]) {
@@ -555,6 +607,42 @@ uint64_t orc_reg_mesh_edges(orc_reg* h, uint32_t* v1, uint32_t* v2, uint32_t* f1
   return E.size();
 }
 void orc_reg_set_splat_points(orc_reg* h, const float* xyz, size_t n) { h->splat_xyz.assign(xyz, xyz + 3 * n); h->has_splats = n > 0; }
+// A rig with `ncam` cameras (rig.h:40-73); image_T_rig: 7 floats per camera (qx qy qz qw tx ty tz), camera 0 = reference (identity).
+int orc_reg_add_rig(orc_reg* h, int ncam, const float* image_T_rig) {
+  if (ncam < 2) return -1;
+  Rig r; r.image_T_rig.resize(ncam);
+  for (int c = 0; c < ncam; ++c) { const float* T = image_T_rig + 7 * c; r.image_T_rig[c].q = {T[0], T[1], T[2], T[3]}; r.image_T_rig[c].t = {T[4], T[5], T[6]}; }
+  h->st.rigs.push_back(r); return (int)h->st.rigs.size() - 1;
+}
+// One set of images recorded together by a rig (rig_images.h:38-64); image_ids[c] = image of camera c, all present. The dependent
+// images' poses are set to image_T_rig[c] * image_T_global(reference), as AssignRigs leaves them (rig.cc:216-250).
+int orc_reg_add_rig_images(orc_reg* h, int rig_id, const int* image_ids) {
+  if (rig_id < 0 || rig_id >= (int)h->st.rigs.size()) return -1;
+  const Rig& rig = h->st.rigs[rig_id];
+  RigImages ri; ri.rig_id = rig_id;
+  for (size_t c = 0; c < rig.image_T_rig.size(); ++c) {
+    const int id = image_ids[c];
+    if (id < 0 || id >= (int)h->st.images.size() || h->st.images[id].rig_images_id >= 0) return -1;
+    ri.image_ids.push_back(id);
+  }
+  h->rig_images.push_back(ri);
+  const int rid = (int)h->rig_images.size() - 1;
+  for (size_t c = 0; c < ri.image_ids.size(); ++c) {
+    Image& im = h->st.images[ri.image_ids[c]];
+    im.rig_images_id = rid; im.rig_camera_index = (int)c;
+    if (c > 0) im.image_T_global = se3_mul(rig.image_T_rig[c], h->st.images[ri.image_ids[0]].image_T_global);
+  }
+  return rid;
+}
+void orc_reg_get_rigs(orc_reg* h, float* out) {
+  for (const Rig& r : h->st.rigs) for (const SE3f& T : r.image_T_rig) { out[0] = T.q.x; out[1] = T.q.y; out[2] = T.q.z; out[3] = T.q.w; out[4] = T.t.x; out[5] = T.t.y; out[6] = T.t.z; out += 7; }
+}
+void orc_reg_set_rigs(orc_reg* h, const float* in) {
+  for (Rig& r : h->st.rigs) for (SE3f& T : r.image_T_rig) { T.q = {in[0], in[1], in[2], in[3]}; T.t = {in[4], in[5], in[6]}; in += 7; }
+}
+// variable index of an intrinsics block (kind 0), a rig's extrinsics block (1), the pose block an image uses (2)
+int orc_reg_variable_index(orc_reg* h, int kind, int id) { return kind == 0 ? intr_var(h, id) : kind == 1 ? rig_var(h, id) : pose_var(h, id); }
+
 int orc_reg_set_depth_map(orc_reg* h, int image, int w, int hh, const float* d) {
   Image& im = h->st.images[image]; im.given_depth.w = w; im.given_depth.h = hh; im.given_depth.d.assign(d, d + (size_t)w * hh); im.has_given_depth = true; return 0;
 }
@@ -638,14 +726,14 @@ double orc_reg_accumulate(orc_reg* h, double* H, double* b, double sums[6]) {
 }
 
 void orc_reg_get_state(orc_reg* h, float* intr_params, float* poses) {
-  for (size_t i = 0; i < h->st.intr.size(); ++i) { const Pinhole& m = h->st.intr[i].models[0]; float* p = intr_params + 4 * i; p[0] = m.fx; p[1] = m.fy; p[2] = m.cx; p[3] = m.cy; }
+  for (size_t i = 0; i < h->st.intr.size(); ++i) h->st.intr[i].models[0].get_params(intr_params + intr_var(h, (int)i));
   for (size_t i = 0; i < h->st.images.size(); ++i) {
     const SE3f& T = h->st.images[i].image_T_global; float* p = poses + 7 * i;
     p[0] = T.q.x; p[1] = T.q.y; p[2] = T.q.z; p[3] = T.q.w; p[4] = T.t.x; p[5] = T.t.y; p[6] = T.t.z;
   }
 }
 void orc_reg_set_state(orc_reg* h, const float* intr_params, const float* poses) {
-  for (size_t i = 0; i < h->st.intr.size(); ++i) { Pinhole& m = h->st.intr[i].models[0]; const float* p = intr_params + 4 * i; m.set(m.w, m.h, p[0], p[1], p[2], p[3]); h->st.intr[i].build_pyramid(); }
+  for (size_t i = 0; i < h->st.intr.size(); ++i) { Pinhole& m = h->st.intr[i].models[0]; m.set(m.type, m.w, m.h, intr_params + intr_var(h, (int)i)); h->st.intr[i].build_pyramid(); }
   for (size_t i = 0; i < h->st.images.size(); ++i) {
     SE3f& T = h->st.images[i].image_T_global; const float* p = poses + 7 * i;
     T.q = {p[0], p[1], p[2], p[3]}; T.t = {p[4], p[5], p[6]};
@@ -721,11 +809,18 @@ int orc_reg_run_on_current_scale(orc_reg* h, int max_it, float max_change_thr, i
 }
 
 // Unit hooks for the reference's own unit tests.
-void orc_reg_point_jacobians(orc_reg* h, int image, int ps, uint64_t obs_index, float* intensity, float jK[4], float jP[6]) {
+void orc_reg_point_jacobians(orc_reg* h, int image, int ps, uint64_t obs_index, float* intensity, float* jK, float jP[6]) {
+  orc_reg_point_jacobians_rig(h, image, ps, obs_index, intensity, jK, jP, nullptr);
+}
+// jR (6, may be null): derivative by the rig extrinsics for a dependent rig image (zeros otherwise)
+void orc_reg_point_jacobians_rig(orc_reg* h, int image, int ps, uint64_t obs_index, float* intensity, float* jK, float jP[6], float* jR) {
   const Image& im = h->st.images[image]; const Intrinsics& in = h->st.intr[im.intrinsics_id];
   float R[9]; quat_to_matrix(im.image_T_global.q, R);
   const Observation& ob = h->obs[image][ps][obs_index];
-  point_intensity_and_jacobians(h, in, im, R, h->pts[ps].radius, &h->pts[ps].xyz[3 * ob.point_index], ob, intensity, jK, jP);
+  int rv; const RigCtx rc = rig_ctx(h, h->st, image, &rv);
+  float tmp[6] = {0, 0, 0, 0, 0, 0};
+  point_intensity_and_jacobians(h, in, im, R, h->pts[ps].radius, &h->pts[ps].xyz[3 * ob.point_index], ob, intensity, jK, jP, &rc, tmp);
+  if (jR) for (int i = 0; i < 6; ++i) jR[i] = tmp[i];
 }
 int orc_interp_bilinear(const uint8_t* img, int w, int hh, float x, float y, float* v, float* dx, float* dy) {
   Img8 im; im.w = w; im.h = hh; im.d.assign(img, img + (size_t)w * hh);
@@ -741,6 +836,34 @@ void orc_interp_trilinear(const uint8_t* img0, int w0, int h0, const uint8_t* im
   float pv; trilinear(a, b, x, y, z, &pv);
   trilinear_d(a, b, x, y, z, v, dx, dy, dz);
   if (pv != *v) *v = std::numeric_limits<float>::quiet_NaN();
+}
+int orc_cam_param_count(int type) { return Camera::known(type) ? Camera::param_count(type) : -1; }
+int orc_cam_cutoff(int type, int w, int hh, const float* params, float out[2]) {
+  if (!Camera::known(type)) return -1;
+  Camera c; c.set(type, w, hh, params); out[0] = c.cutoff2; out[1] = c.inner_cutoff2; return 0;
+}
+int orc_cam_eval(int type, int w, int hh, const float* params, int op, const float* in, size_t n, float* out) {
+  if (!Camera::known(type)) return -1;
+  Camera c; c.set(type, w, hh, params);
+  const int np = c.np();
+  for (size_t i = 0; i < n; ++i) {
+    if (op == 0) c.distort(in[2 * i], in[2 * i + 1], &out[2 * i], &out[2 * i + 1]);
+    else if (op == 1) c.project(in[2 * i], in[2 * i + 1], &out[2 * i], &out[2 * i + 1]);
+    else if (op == 2) c.d_by_world(V3f{in[3 * i], in[3 * i + 1], in[3 * i + 2]}, &out[6 * i]);
+    else if (op == 3) c.d_by_intrinsics(V3f{in[3 * i], in[3 * i + 1], in[3 * i + 2]}, &out[(size_t)2 * np * i]);
+    else if (op == 4) {
+      float ux = in[2 * i], uy = in[2 * i + 1];
+      if (type != kCamPinhole) c.tp_iterative_undistort(in[2 * i], in[2 * i + 1], in[2 * i], in[2 * i + 1], &ux, &uy);
+      if (type == kCamBenchmark) {   // camera_base_impl_fisheye.h:80-91
+        const float r = std::sqrt(ux * ux + uy * uy);
+        const float factor = (r < 1e-6f) ? 1.f : (r > M_PI / 2.f) ? std::numeric_limits<float>::infinity() : tanf(r) / r;
+        ux = factor * ux; uy = factor * uy;
+      }
+      out[2 * i] = ux; out[2 * i + 1] = uy;
+    } else if (op == 5) c.distort_deriv(in[2 * i], in[2 * i + 1], &out[4 * i]);
+    else return -2;
+  }
+  return 0;
 }
 float orc_robust(int type, float p, float r, int weight) { Robust R; R.type = type; R.p = p; return weight ? R.weight(r) : R.residual(r); }
 void orc_image_pyramid_level(const uint8_t* src, int w, int hh, uint8_t* dst) {

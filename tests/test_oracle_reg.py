@@ -123,3 +123,72 @@ def test_ref_point_intensity_and_jacobians_fd(oracle):
             r2 = _make_problem(oracle, base_intr, np.concatenate([qo, to]), point, radius)
             I1, _, _ = r2.point_jacobians(0, 0, 0)
             assert abs(d[c] * jP[c] - (I1 - I0)) < 1e-3, ("pose", c)
+
+
+# ---- test_intrinsics_and_pose_optimizer.cc:338-700 (ComputePointIntensityAndJacobiansForRig) -------------------------------------
+def _qmul(a, b):
+    ax, ay, az, aw = a; bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw,
+                     aw * bw - ax * bx - ay * by - az * bz])
+
+
+def _se3_mul(A, B):
+    q = _qmul(A[:4], B[:4]); t = _quat_R(A[:4]) @ B[4:] + A[4:]
+    return np.concatenate([q / np.linalg.norm(q), t])
+
+
+def _se3_inv(A):
+    qi = np.array([-A[0], -A[1], -A[2], A[3]])
+    return np.concatenate([qi, -(_quat_R(qi) @ A[4:])])
+
+
+def _make_rig_problem(oracle, intr_params, rig_T_global, image_T_rig, point, radius):
+    p = oracle.reg_default_params(point_neighbor_count=2, robust_weighting_type=2, robust_weighting_parameter=30.0,
+                                  max_initial_image_area_in_pixels=80 * 60, image_scale_count_override=2)
+    r = oracle.Registration(p)
+    r.add_intrinsics(40, 30, intr_params)
+    yy, xx = np.mgrid[0:30, 0:40]
+    img = ((1 * xx + 3 * yy) % 256).astype(np.uint8)
+    r.add_image(0, img, None, rig_T_global.astype(np.float32))                        # rig reference image
+    r.add_image(0, img, None, np.array([0, 0, 0, 1, 0, 0, 0], np.float32))             # dependent image: pose comes from the rig
+    rig = r.add_rig(np.stack([np.array([0, 0, 0, 1, 0, 0, 0.0]), image_T_rig]).astype(np.float32))
+    r.add_rig_images(rig, [0, 1])
+    assert r.initialize() == 2
+    r.add_point_scale(point[None, :], radius, np.zeros((1, 2), np.uint64), np.zeros(1, np.float32))
+    r.set_splat_points(point[None, :])
+    r.set_image_scale(0)
+    r.create_observations(0)
+    assert len(r.observations(1, 0)[0]) == 1
+    return r
+
+
+def test_ref_point_intensity_and_jacobians_for_rig_fd(oracle):
+    q = _from_two_vectors(np.array([0.1, 0.3, 0.785]), np.array([0.4375, 0.2458, 0.2724])); q = q / np.linalg.norm(q)
+    global_T_image = np.concatenate([q, [0.89763, 0.789346, 0.21398]])
+    qr = _from_two_vectors(np.array([0.2467, 0.7474, 0.42724]), np.array([0.2721, 0.9656, 0.2424])); qr = qr / np.linalg.norm(qr)
+    rig_T_global = np.concatenate([qr, [0.537, 0.84527, 0.2472]])
+    image_T_rig = _se3_mul(_se3_inv(global_T_image), _se3_inv(rig_T_global))           # :366
+    base_intr = np.array([40, 30, 20, 15], np.float32)
+    radius = 0.036
+    R, t = _quat_R(global_T_image[:4]), global_T_image[4:]
+    for local in ((0.1, 0.23, 2.0), (0.4, 0.67, 2.1), (0.0, 0.0, 1.9)):
+        point = (R @ np.array(local) + t).astype(np.float32)
+        r = _make_rig_problem(oracle, base_intr, rig_T_global, image_T_rig, point, radius)
+        # layout [intrinsics(4) | rig extrinsics (6) | pose of image 0 (6)]; image 1 uses image 0's pose block
+        assert r.num_variables() == 16
+        assert (r.variable_index("intrinsics", 0), r.variable_index("rig", 0), r.variable_index("image", 0), r.variable_index("image", 1)) == (0, 4, 10, 10)
+        I0, jK, jP, jR = r.point_jacobians_rig(1, 0, 0)
+        for c in range(4):                                             # intrinsics, delta = 1 (:457-507)
+            ip = base_intr.copy(); ip[c] += 1
+            I1 = _make_rig_problem(oracle, ip, rig_T_global, image_T_rig, point, radius).point_jacobians_rig(1, 0, 0)[0]
+            assert abs(1.0 * jK[c] - (I1 - I0)) < 1e-3, ("intrinsics", c)
+        for c in range(6):                                             # rig reference pose (:509-571), always the small delta
+            d = np.zeros(6); d[c] = 0.002
+            qo, to = oracle.se3_exp_left_mul(d, rig_T_global[:4].astype(np.float32), rig_T_global[4:].astype(np.float32))
+            I1 = _make_rig_problem(oracle, base_intr, np.concatenate([qo, to]), image_T_rig, point, radius).point_jacobians_rig(1, 0, 0)[0]
+            assert abs(d[c] * jP[c] - (I1 - I0)) < 1e-3, ("rig pose", c)
+        for c in range(6):                                             # intra-rig extrinsics (:573-640)
+            d = np.zeros(6); d[c] = 2 * radius if c < 2 else 0.002
+            qo, to = oracle.se3_exp_left_mul(d, image_T_rig[:4].astype(np.float32), image_T_rig[4:].astype(np.float32))
+            I1 = _make_rig_problem(oracle, base_intr, rig_T_global, np.concatenate([qo, to]), point, radius).point_jacobians_rig(1, 0, 0)[0]
+            assert abs(d[c] * jR[c] - (I1 - I0)) < 1e-3, ("extrinsics", c)
