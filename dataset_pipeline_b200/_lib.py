@@ -47,6 +47,7 @@ def build(force=False):
 EXPORTS = [
     "b2_abi_version",
     "b2_camera_eval",
+    "b2_comm_allreduce",
     "b2_comm_allreduce_f64",
     "b2_comm_create",
     "b2_comm_destroy",
@@ -74,6 +75,8 @@ EXPORTS = [
     "b2_reg_add_image",
     "b2_reg_add_intrinsics",
     "b2_reg_add_point_scale",
+    "b2_reg_add_rig",
+    "b2_reg_add_rig_images",
     "b2_reg_apply",
     "b2_reg_color_update",
     "b2_reg_cost",
@@ -85,18 +88,25 @@ EXPORTS = [
     "b2_reg_get_descriptors",
     "b2_reg_get_observations",
     "b2_reg_get_point_jacobians",
+    "b2_reg_get_point_jacobians_rig",
+    "b2_reg_get_rigs",
     "b2_reg_get_state",
+    "b2_reg_image_owner",
     "b2_reg_initialize",
     "b2_reg_last_stats",
     "b2_reg_num_observations",
     "b2_reg_num_variables",
     "b2_reg_render_depth",
     "b2_reg_run_on_current_scale",
+    "b2_reg_set_camera_mask",
+    "b2_reg_set_comm",
     "b2_reg_set_depth_map",
     "b2_reg_set_image_scale",
     "b2_reg_set_mesh",
+    "b2_reg_set_rigs",
     "b2_reg_set_splat_points",
     "b2_reg_set_state",
+    "b2_reg_variable_index",
 ]
 
 

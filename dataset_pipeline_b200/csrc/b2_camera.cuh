@@ -6,9 +6,9 @@
 //   BenchmarkCamera (type 5, 12 parameters)  /root/reference/src/camera/camera_benchmark.cc:36-46 = FisheyeBase<ThinPrismCamera>,
 //                                            /root/reference/src/camera/camera_base_impl_fisheye.h:65-146 (ETH3D's THIN_PRISM_FISHEYE)
 //   shared machinery                         /root/reference/src/camera/camera_base_impl.h:70-89,155-164,214-250,276-328,333-462
-// Arithmetic is written in the reference's evaluation order and the file is built with -fmad=false, so everything except
-// atan() is bit-identical to the CPU; atan(r) is computed in fp64 and rounded (glibc's atanf differs from that by <= 1 ulp
-// and depends on the host CPU's FMA dispatch, so fisheye parity is stated as a tolerance, not bit-exact).
+// Arithmetic is written in the reference's evaluation order and the file is built with -fmad=false, so it is bit-identical to
+// the CPU; atan2(r, 1.f) is the correctly rounded fp32 arctangent (fp64 atan, rounded once) — what glibc >= 2.41 returns; older
+// glibc's atan2f differs by <= 1 ulp in ~5 % of the calls, which is why the oracle pins the same definition (orc_camera.h).
 // K16 kr_cutoff_starts / kr_cutoff_points / kr_cutoff_final: InitCutoff as three kernels (one thread per border pixel and
 // Gauss-Newton start; one thread per border pixel replaying the reference's sequential best / second-best bookkeeping over
 // its 100 starts; one block for the max / min over border pixels).

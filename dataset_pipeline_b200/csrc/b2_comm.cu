@@ -14,7 +14,7 @@ namespace b2 {
 
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
-enum { kNcclSuccess = 0, kNcclSum = 0, kNcclFloat64 = 8 };
+enum { kNcclSuccess = 0, kNcclSum = 0, kNcclInt32 = 2, kNcclFloat32 = 7, kNcclFloat64 = 8 };
 
 struct NcclApi {
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -89,6 +89,16 @@ int b2_comm_destroy(b2_comm* c) {
 int b2_comm_allreduce_f64(b2_comm* c, double* buf_dev, size_t count, void* stream) {
   if (!c || !buf_dev) return set_error(B2_ERR_ARG, "null");
   const int rc = nccl().AllReduce(buf_dev, buf_dev, count, kNcclFloat64, kNcclSum, c->comm, (cudaStream_t)stream);
+  if (rc != kNcclSuccess) return set_error(B2_ERR_COMM, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
+  return B2_OK;
+}
+
+int b2_comm_allreduce(b2_comm* c, void* buf_dev, size_t count, int dtype, void* stream) {
+  if (!c || !buf_dev) return set_error(B2_ERR_ARG, "null");
+  const int t = dtype == B2_F64 ? kNcclFloat64 : dtype == B2_F32 ? kNcclFloat32 : dtype == B2_I32 ? kNcclInt32 : -1;
+  if (t < 0) return set_error(B2_ERR_ARG, "bad dtype");
+  if (count == 0) return B2_OK;
+  const int rc = nccl().AllReduce(buf_dev, buf_dev, count, t, kNcclSum, c->comm, (cudaStream_t)stream);
   if (rc != kNcclSuccess) return set_error(B2_ERR_COMM, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
   return B2_OK;
 }

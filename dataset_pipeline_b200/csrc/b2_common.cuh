@@ -129,9 +129,8 @@ __host__ __device__ __forceinline__ unsigned long long cell_key(const GridParams
 
 // Sort key = (cell key << 3*fbits) | Morton code of the position inside the cell (fbits bits per axis): points of one cell
 // stay contiguous (the hash table is keyed by key >> 3*fbits) and are ordered along a space-filling curve, so the per-32 /
-// per-1024 point chunk boxes of dense cells are compact and prune well. fbits = 8 (cell/256 sub-cells) unless the cell key of
-// an enormous sparse scene leaves less room in 63 bits; scanner-zenith clusters (thousands of points within millimetres)
-// need the fine resolution, at 5 bits per axis their chunk boxes all overlapped (r01 profile: one CTA ran 2x the kernel mean).
+// per-1024 point chunk boxes of dense cells are compact and prune well. fbits is chosen by compute_grid(): 5..8 bits per axis,
+// as many as keep the whole key within 40 bits (= 5 radix-sort passes).
 static constexpr int kMinFineBits = 5, kMaxFineBits = 8;
 __host__ __device__ __forceinline__ unsigned int spread3(unsigned int v) {   // 10 bits -> every third bit
   v &= 0x3FFu;

@@ -57,8 +57,12 @@ struct IntrinsicsB {
   void build_pyramid() { for (size_t i = 1; i < models.size(); ++i) models[i] = cam_half(models[i - 1]); }
 };
 
+struct RigB { std::vector<Pose> image_T_rig; };                      // rig.h:40-73 ([0] = reference camera, identity)
+struct RigImagesB { int rig_id = 0; std::vector<int> image_ids; };   // rig_images.h:38-64
+
 struct ImageB {
   int intrinsics_id = 0;
+  int rig_images_id = -1, rig_camera_index = 0;
   Pose pose;                               // image_T_global
   std::vector<DevBuf> img, mask;           // pyramids in HBM (mask empty = none)
   std::vector<int> lw, lh;                 // level sizes (image pyramid: truncating halving)
@@ -73,10 +77,10 @@ struct ScaleB {
 
 struct ObsSet {       // observations of one (image, point scale)
   size_t count = 0;
-  DevBuf idx, x, y, s, nb, inten, jK, jP, slot;   // slot: per POINT (n), -1 = unobserved
+  DevBuf idx, x, y, s, nb, inten, jK, jP, jR, slot;   // slot: per POINT (n), -1 = unobserved; jR only for dependent rig images
 };
 
-struct StateB { std::vector<IntrinsicsB> intr; std::vector<Pose> poses; };
+struct StateB { std::vector<IntrinsicsB> intr; std::vector<Pose> poses; std::vector<RigB> rigs; };
 
 static inline unsigned int divup(size_t a, size_t b) { return (unsigned int)((a + b - 1) / b); }
 
@@ -90,11 +94,16 @@ struct b2_reg {
   cudaStream_t stream = nullptr;
   std::vector<IntrinsicsB> intr;
   std::vector<ImageB> images;
+  std::vector<RigB> rigs;
+  std::vector<RigImagesB> rig_images;
+  std::map<int, std::vector<DevBuf>> cam_masks;      // camera-mask pyramids by intrinsics id (not part of the optimised state)
   std::vector<ScaleB> pts;
   DevBuf splats; size_t nsplats = 0;
   DevBuf mesh_v, mesh_f, mesh_fn, mesh_edges, big_list, big_count, depth_masked; size_t mesh_nv = 0, mesh_nf = 0, mesh_ne = 0;
   int image_scale_count = 0, current_image_scale = 0;
   bool initialized = false;
+  b2_comm* comm = nullptr; int rank = 0, world = 1;     // multi-GPU: images dealt round-robin, sums allreduced (b2_reg_set_comm)
+  DevBuf xchg;                                           // device staging of host-side partial sums for the allreduce
   std::vector<std::vector<ObsSet>> obs;      // [image][scale]
   std::vector<ObsSet> trial;                 // scratch sets for trial states, [scale]
   // scratch
@@ -108,9 +117,24 @@ struct b2_reg {
 namespace b2 {
 
 static int K(const b2_reg* h) { return h->prm.point_neighbor_count; }
-// variable layout: [intrinsics 0 | intrinsics 1 | ... | image poses (6 each)]; an intrinsics block has the camera model's ParameterCount()
+// Variable layout (CountAndIndexVariables, intrinsics_and_pose_optimizer.cc:442-473): [intrinsics 0 | intrinsics 1 | ... | rig 0
+// extrinsics (6 per camera after the first) | rig 1 | ... | poses (6 each) of the images that own one — non-rig images and rig
+// reference images, ascending id]. An intrinsics block has the camera model's ParameterCount(); a dependent rig image uses its
+// reference image's pose block.
 static int intr_var(const b2_reg* h, int id) { int v = 0; for (int i = 0; i < id; ++i) v += h->intr[i].np(); return v; }
-static int pose_var(const b2_reg* h, int im) { return intr_var(h, (int)h->intr.size()) + 6 * im; }
+static int rig_var(const b2_reg* h, int rig_id) {
+  int v = intr_var(h, (int)h->intr.size());
+  for (int r = 0; r < rig_id; ++r) v += 6 * ((int)h->rigs[r].image_T_rig.size() - 1);
+  return v;
+}
+static bool is_dependent(const b2_reg* h, int im) { return h->images[im].rig_images_id >= 0 && h->images[im].rig_camera_index > 0; }
+static int ref_image(const b2_reg* h, int im) { return is_dependent(h, im) ? h->rig_images[h->images[im].rig_images_id].image_ids[0] : im; }
+static int pose_var(const b2_reg* h, int im) {
+  const int owner = im < (int)h->images.size() ? ref_image(h, im) : im;
+  int v = rig_var(h, (int)h->rigs.size());
+  for (int i = 0; i < owner; ++i) if (!is_dependent(h, i)) v += 6;
+  return v;
+}
 static int nvars(const b2_reg* h) { return pose_var(h, (int)h->images.size()); }
 
 // K16: radius cut-offs of every pyramid level of the given intrinsics (the reference re-runs InitCutoff in each camera
@@ -146,6 +170,20 @@ static int compute_cutoffs(b2_reg* h, std::vector<IntrinsicsB>* intr) {
   return B2_OK;
 }
 
+static bool owned(const b2_reg* h, size_t im) { return (int)(im % (size_t)h->world) == h->rank; }
+
+// Sum-allreduce of `n` host doubles across the ranks (no-op on one GPU): staged through HBM, NCCL on the handle's stream.
+static int allreduce_host(b2_reg* h, double* v, size_t n) {
+  if (h->world == 1 || n == 0) return B2_OK;
+  B2_TRY(h->xchg.ensure(n * 8));
+  B2_CUDA(cudaMemcpyAsync(h->xchg.p, v, n * 8, cudaMemcpyHostToDevice, h->stream));
+  B2_TRY(b2_comm_allreduce(h->comm, h->xchg.p, n, B2_F64, (void*)h->stream));
+  B2_CUDA(cudaMemcpyAsync(v, h->xchg.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  return B2_OK;
+}
+static int allreduce_sums(b2_reg* h, struct Sums* s);
+
 static Pose3 pose3_of(const Pose& p) { Pose3 o; quat_matrix(p.q, o.R); for (int k = 0; k < 3; ++k) o.t[k] = p.t[k]; return o; }
 
 static Levels levels_of(const b2_reg* h, const ImageB& im, const IntrinsicsB& in) {
@@ -156,7 +194,8 @@ static Levels levels_of(const b2_reg* h, const ImageB& im, const IntrinsicsB& in
     L.img[l] = im.img[l].as<unsigned char>();
     L.mask[l] = im.has_mask ? im.mask[l].as<unsigned char>() : nullptr;
   }
-  (void)h;
+  const auto cm = h->cam_masks.find(im.intrinsics_id);
+  if (cm != h->cam_masks.end()) for (int l = 0; l < L.nlevels && l < (int)cm->second.size(); ++l) L.cmask[l] = cm->second[l].as<unsigned char>();
   return L;
 }
 
@@ -223,7 +262,7 @@ static int ensure_obs_set(ObsSet* o, size_t cap, size_t npoints, bool with_jac) 
   cap = std::max<size_t>(cap, 1);
   B2_TRY(o->idx.ensure(cap * 4)); B2_TRY(o->x.ensure(cap * 4)); B2_TRY(o->y.ensure(cap * 4)); B2_TRY(o->s.ensure(cap * 4));
   B2_TRY(o->nb.ensure(cap)); B2_TRY(o->inten.ensure(cap * 4));
-  if (with_jac) { B2_TRY(o->jK.ensure(cap * 4 * kMaxIntrinsics)); B2_TRY(o->jP.ensure(cap * 24)); }
+  if (with_jac) { B2_TRY(o->jK.ensure(cap * 4 * kMaxIntrinsics)); B2_TRY(o->jP.ensure(cap * 24)); B2_TRY(o->jR.ensure(cap * 24)); }
   B2_TRY(o->slot.ensure(std::max<size_t>(npoints, 1) * 4));
   return B2_OK;
 }
@@ -294,6 +333,12 @@ static ResidualArgs residual_args(const b2_reg* h, int ps, const ObsSet& o) {
 }
 
 struct Sums { double fixed_sum = 0, var_sum = 0, nf = 0, nv = 0; };
+static int allreduce_sums(b2_reg* h, Sums* s) {
+  double v[4] = {s->fixed_sum, s->nf, s->var_sum, s->nv};
+  B2_TRY(allreduce_host(h, v, 4));
+  s->fixed_sum = v[0]; s->nf = v[1]; s->var_sum = v[2]; s->nv = v[3];
+  return B2_OK;
+}
 
 // Problem::ComputeCost (problem.cc:602-631), depth weight 0.
 static double compute_cost(const b2_reg* h, const Sums& s) {
@@ -334,13 +379,29 @@ static int residual_sums_image(b2_reg* h, const StateB& st, int im, std::vector<
 }
 
 static StateB current_state(const b2_reg* h) {
-  StateB s; s.intr = h->intr;
+  StateB s; s.intr = h->intr; s.rigs = h->rigs;
   for (const ImageB& im : h->images) s.poses.push_back(im.pose);
   return s;
 }
 static void set_current_state(b2_reg* h, const StateB& s) {
-  h->intr = s.intr;
+  h->intr = s.intr; h->rigs = s.rigs;
   for (size_t i = 0; i < h->images.size(); ++i) h->images[i].pose = s.poses[i];
+}
+
+// Rig context of an image under `st` (zero / not dependent for non-rig and reference images); *rv = its extrinsics variable block.
+static RigDev rig_dev(const b2_reg* h, const StateB& st, int im, int* rv) {
+  RigDev r; std::memset(&r, 0, sizeof(r)); *rv = -1;
+  if (!is_dependent(h, im)) return r;
+  const RigImagesB& ri = h->rig_images[h->images[im].rig_images_id];
+  const int c = h->images[im].rig_camera_index;
+  const Pose& T = st.rigs[ri.rig_id].image_T_rig[c];
+  const Pose& G = st.poses[ri.image_ids[0]];
+  r.dependent = 1;
+  quat_matrix(T.q, r.Rr);
+  for (int k = 0; k < 4; ++k) r.q[k] = G.q[k];
+  for (int k = 0; k < 3; ++k) r.t[k] = G.t[k];
+  *rv = rig_var(h, ri.rig_id) + 6 * (c - 1);
+  return r;
 }
 
 // CreateDeltaState (intrinsics_and_pose_optimizer.cc:475-558).
@@ -355,7 +416,16 @@ static int delta_state(b2_reg* h, const StateB& base, const double* delta, State
     n.intr[i].build_pyramid();
   }
   B2_TRY(compute_cutoffs(h, &n.intr));
-  for (size_t i = 0; i < n.poses.size(); ++i) n.poses[i] = pose_mul(pose_exp(delta + pose_var(h, (int)i)), base.poses[i]);   // image.cc:161
+  for (size_t r = 0; r < n.rigs.size(); ++r)                                   // Rig::Update (rig.cc:9-23)
+    for (size_t c = 1; c < n.rigs[r].image_T_rig.size(); ++c)
+      n.rigs[r].image_T_rig[c] = pose_mul(pose_exp(delta + rig_var(h, (int)r) + 6 * ((int)c - 1)), base.rigs[r].image_T_rig[c]);
+  for (size_t i = 0; i < n.poses.size(); ++i)                                  // pose owners (image.cc:161; :517-534, 556-563)
+    if (!is_dependent(h, (int)i)) n.poses[i] = pose_mul(pose_exp(delta + pose_var(h, (int)i)), base.poses[i]);
+  for (size_t i = 0; i < n.poses.size(); ++i)                                  // dependent rig images from the UPDATED rig pose (:546-555)
+    if (is_dependent(h, (int)i)) {
+      const RigImagesB& ri = h->rig_images[h->images[i].rig_images_id];
+      n.poses[i] = pose_mul(n.rigs[ri.rig_id].image_T_rig[h->images[i].rig_camera_index], n.poses[ri.image_ids[0]]);
+    }
   return B2_OK;
 }
 
@@ -363,20 +433,24 @@ static int delta_state(b2_reg* h, const StateB& base, const double* delta, State
 static int residual_for_state(b2_reg* h, const StateB& st, double* cost) {
   Sums total;
   for (size_t im = 0; im < h->images.size(); ++im) {
+    if (!owned(h, im)) continue;
     B2_TRY(observations_for_image(h, st, (int)im, 1, &h->obs[im], &h->trial));
     B2_TRY(residual_sums_image(h, st, (int)im, h->trial, &total));
   }
+  B2_TRY(allreduce_sums(h, &total));
   *cost = compute_cost(h, total);
   return B2_OK;
 }
 
-static void launch_jacobians(b2_reg* h, int np, ObsSet& o, const ScaleB& P, const Pose3& P3, const Levels& L) {
+static void launch_jacobians(b2_reg* h, int np, ObsSet& o, const ScaleB& P, const Pose3& P3, const Levels& L, const RigDev& rig) {
   if (np == 4)
     kr_jacobians<4><<<divup(o.count, 256), 256, 0, h->stream>>>(o.count, o.idx.as<unsigned int>(), o.x.as<float>(), o.y.as<float>(), o.s.as<float>(),
-                                                                 P.xyz.as<float>(), P3, P.radius, L, o.inten.as<float>(), o.jK.as<float>(), o.jP.as<float>());
+                                                                 P.xyz.as<float>(), P3, P.radius, L, o.inten.as<float>(), o.jK.as<float>(), o.jP.as<float>(),
+                                                                 rig, o.jR.as<float>());
   else
     kr_jacobians<12><<<divup(o.count, 256), 256, 0, h->stream>>>(o.count, o.idx.as<unsigned int>(), o.x.as<float>(), o.y.as<float>(), o.s.as<float>(),
-                                                                  P.xyz.as<float>(), P3, P.radius, L, o.inten.as<float>(), o.jK.as<float>(), o.jP.as<float>());
+                                                                  P.xyz.as<float>(), P3, P.radius, L, o.inten.as<float>(), o.jK.as<float>(), o.jP.as<float>(),
+                                                                  rig, o.jR.as<float>());
   ++h->launches;
 }
 
@@ -385,7 +459,7 @@ static int accumulate_all(b2_reg* h, std::vector<double>* H, std::vector<double>
   const int nv = nvars(h);
   const int grid = h->sms * 2, grid_wide = h->sms * 4;
   const size_t S = h->pts.size(), NI = h->images.size();
-  constexpr int kAccW = 18 * 19 / 2 + 18 + 4;      // result stride: the widest local system (12 intrinsics + 6 pose)
+  constexpr int kAccW = 24 * 25 / 2 + 24 + 4;      // result stride: the widest local system (12 intrinsics + 6 rig extrinsics + 6 pose)
   H->assign((size_t)nv * nv, 0.0); b->assign(nv, 0.0);
   B2_TRY(h->partials.ensure(sizeof(double) * kAccW * grid_wide));
   B2_TRY(h->results.ensure(sizeof(double) * kAccW * NI * S));
@@ -395,27 +469,30 @@ static int accumulate_all(b2_reg* h, std::vector<double>* H, std::vector<double>
   uint64_t evals = 0;
   float ms_j = 0.f, ms_a = 0.f;
   for (size_t im = 0; im < NI; ++im) {
+    if (!owned(h, im)) continue;
     const ImageB& I = h->images[im];
     const Levels L = levels_of(h, I, st.intr[I.intrinsics_id]);
     const Pose3 P3 = pose3_of(I.pose);
+    int rv; const RigDev rig = rig_dev(h, st, (int)im, &rv);
     for (size_t ps = 0; ps < S; ++ps) {
       ObsSet& o = h->obs[im][ps];
       if (o.count == 0) continue;
       evals += o.count;
       const int np = st.intr[I.intrinsics_id].np();
       cudaEventRecord(h->evj0, h->stream);
-      launch_jacobians(h, np, o, h->pts[ps], P3, L);
+      launch_jacobians(h, np, o, h->pts[ps], P3, L, rig);
       cudaEventRecord(h->evj1, h->stream);
       cudaEventRecord(h->eva0, h->stream);
-      if (np == 4) {
-        kr_accumulate<<<grid, 128, 0, h->stream>>>(residual_args(h, (int)ps, o), o.jK.as<float>(), o.jP.as<float>(), h->partials.as<double>());
-        cudaEventRecord(h->eva1, h->stream);
-        kr_reduce_partials<<<1, 256, 0, h->stream>>>(h->partials.as<double>(), grid, kAccB, h->results.as<double>() + kAccW * (im * S + ps));
-      } else {
-        kr_accumulate_wide<12><<<grid_wide, 128, 0, h->stream>>>(residual_args(h, (int)ps, o), o.jK.as<float>(), o.jP.as<float>(), h->partials.as<double>());
-        cudaEventRecord(h->eva1, h->stream);
-        kr_reduce_partials<<<1, 256, 0, h->stream>>>(h->partials.as<double>(), grid_wide, kAccW, h->results.as<double>() + kAccW * (im * S + ps));
-      }
+      const ResidualArgs A = residual_args(h, (int)ps, o);
+      const float *pK = o.jK.as<float>(), *pP = o.jP.as<float>(), *pR = o.jR.as<float>();
+      double* part = h->partials.as<double>();
+      const int lv = np + 6 + (rig.dependent ? 6 : 0), nout = lv * (lv + 1) / 2 + lv + 4;
+      if (np == 4 && !rig.dependent) kr_accumulate<<<grid, 128, 0, h->stream>>>(A, pK, pP, part);
+      else if (np == 4) kr_accumulate_wide<4, true><<<grid_wide, 128, 0, h->stream>>>(A, pK, pP, pR, part);
+      else if (!rig.dependent) kr_accumulate_wide<12, false><<<grid_wide, 128, 0, h->stream>>>(A, pK, pP, pR, part);
+      else kr_accumulate_wide<12, true><<<grid_wide, 128, 0, h->stream>>>(A, pK, pP, pR, part);
+      cudaEventRecord(h->eva1, h->stream);
+      kr_reduce_partials<<<1, 256, 0, h->stream>>>(part, (np == 4 && !rig.dependent) ? grid : grid_wide, nout, h->results.as<double>() + kAccW * (im * S + ps));
       h->launches += 2;
       cudaEventSynchronize(h->eva1);
       float a = 0, c = 0; cudaEventElapsedTime(&a, h->evj0, h->evj1); cudaEventElapsedTime(&c, h->eva0, h->eva1);
@@ -428,16 +505,29 @@ static int accumulate_all(b2_reg* h, std::vector<double>* H, std::vector<double>
   const double* r = h->pin.as<double>();
   *sums = Sums();
   for (size_t im = 0; im < NI; ++im) {
+    if (!owned(h, im)) continue;
     const int iv = intr_var(h, h->images[im].intrinsics_id), pv = pose_var(h, (int)im);
-    const int ni = st.intr[h->images[im].intrinsics_id].np(), lv = ni + 6, lh = lv * (lv + 1) / 2;
-    auto g = [&](int l) { return l < ni ? iv + l : pv + (l - ni); };
+    int rv; const bool dep = rig_dev(h, st, (int)im, &rv).dependent != 0;
+    const int ni = st.intr[h->images[im].intrinsics_id].np(), nr = dep ? 6 : 0, lv = ni + nr + 6, lh = lv * (lv + 1) / 2;
+    auto g = [&](int l) { return l < ni ? iv + l : l < ni + nr ? rv + (l - ni) : pv + (l - ni - nr); };
     for (size_t ps = 0; ps < S; ++ps) {
       const double* v = r + kAccW * (im * S + ps);
       int e = 0;
-      for (int c = 0; c < lv; ++c) for (int rr = 0; rr <= c; ++rr) { (*H)[(size_t)g(c) * nv + g(rr)] += v[e]; ++e; }
+      for (int c = 0; c < lv; ++c) for (int rr = 0; rr <= c; ++rr) { (*H)[(size_t)std::max(g(c), g(rr)) * nv + std::min(g(c), g(rr))] += v[e]; ++e; }
       for (int k = 0; k < lv; ++k) (*b)[g(k)] += v[lh + k];
       sums->fixed_sum += v[lh + lv]; sums->nf += v[lh + lv + 1]; sums->var_sum += v[lh + lv + 2]; sums->nv += v[lh + lv + 3];
     }
+  }
+  if (h->world > 1) {   // data-parallel exchange: one sum-allreduce of [H | b | sums | evals] (nv^2 + nv + 5 doubles)
+    std::vector<double> pack(H->begin(), H->end());
+    pack.insert(pack.end(), b->begin(), b->end());
+    const double tail[5] = {sums->fixed_sum, sums->nf, sums->var_sum, sums->nv, (double)evals};
+    pack.insert(pack.end(), tail, tail + 5);
+    B2_TRY(allreduce_host(h, pack.data(), pack.size()));
+    std::copy(pack.begin(), pack.begin() + (size_t)nv * nv, H->begin());
+    std::copy(pack.begin() + (size_t)nv * nv, pack.begin() + (size_t)nv * nv + nv, b->begin());
+    const double* t = pack.data() + (size_t)nv * nv + nv;
+    sums->fixed_sum = t[0]; sums->nf = t[1]; sums->var_sum = t[2]; sums->nv = t[3]; evals = (uint64_t)t[4];
   }
   for (int c = 0; c < nv; ++c) for (int rr = 0; rr < c; ++rr) (*H)[(size_t)rr * nv + c] = (*H)[(size_t)c * nv + rr];   // mirror the Upper view
   h->stats.residual_evaluations = evals; h->stats.ms_jacobian_kernel = ms_j; h->stats.ms_accumulate_kernel = ms_a;
@@ -449,10 +539,13 @@ static int create_observations(b2_reg* h, int border) {
   h->obs.resize(h->images.size());
   uint64_t total = 0;
   for (size_t im = 0; im < h->images.size(); ++im) {
+    if (!owned(h, im)) { h->obs[im].resize(h->pts.size()); for (ObsSet& o : h->obs[im]) o.count = 0; continue; }
     B2_TRY(observations_for_image(h, st, (int)im, border, nullptr, &h->obs[im]));
     for (const ObsSet& o : h->obs[im]) total += o.count;
   }
-  h->stats.observations = total;
+  double t = (double)total;
+  B2_TRY(allreduce_host(h, &t, 1));
+  h->stats.observations = (uint64_t)t;
   return B2_OK;
 }
 
@@ -472,6 +565,10 @@ static int color_update(b2_reg* h) {
                                                                      K(h), o.slot.as<int>(), o.inten.as<float>(), P.var_desc.as<float>(), P.obs_count.as<int>());
       h->launches += 2;
     }
+    if (h->world > 1) {   // descriptor sums and observation counts over ALL images: 5 floats + 1 int per point
+      B2_TRY(b2_comm_allreduce(h->comm, P.var_desc.p, P.n * K(h), B2_F32, (void*)h->stream));
+      B2_TRY(b2_comm_allreduce(h->comm, P.obs_count.p, P.n, B2_I32, (void*)h->stream));
+    }
     kr_color_mean<<<divup(P.n, 256), 256, 0, h->stream>>>(P.n, K(h), P.var_desc.as<float>(), P.obs_count.as<int>());
     ++h->launches;
   }
@@ -482,7 +579,8 @@ static int color_update(b2_reg* h) {
 static int current_cost(b2_reg* h, double* cost, Sums* s) {
   const StateB st = current_state(h);
   *s = Sums();
-  for (size_t im = 0; im < h->images.size(); ++im) B2_TRY(residual_sums_image(h, st, (int)im, h->obs[im], s));
+  for (size_t im = 0; im < h->images.size(); ++im) if (owned(h, im)) B2_TRY(residual_sums_image(h, st, (int)im, h->obs[im], s));
+  B2_TRY(allreduce_sums(h, s));
   if (s->nf == 0 && s->nv == 0) { *cost = std::numeric_limits<double>::infinity(); return B2_OK; }   // cost_calculator.cc:88-93
   *cost = compute_cost(h, *s);
   return B2_OK;
@@ -559,13 +657,15 @@ int b2_reg_destroy(b2_reg* h) {
   if (!h) return B2_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  auto free_set = [](ObsSet& o) { for (DevBuf* b : {&o.idx, &o.x, &o.y, &o.s, &o.nb, &o.inten, &o.jK, &o.jP, &o.slot}) b->release(); };
+  auto free_set = [](ObsSet& o) { for (DevBuf* b : {&o.idx, &o.x, &o.y, &o.s, &o.nb, &o.inten, &o.jK, &o.jP, &o.jR, &o.slot}) b->release(); };
   for (auto& v : h->obs) for (auto& o : v) free_set(o);
   for (auto& o : h->trial) free_set(o);
   for (auto& im : h->images) { for (auto& b : im.img) b.release(); for (auto& b : im.mask) b.release(); im.given_depth.release(); }
   for (auto& P : h->pts) for (DevBuf* b : {&P.xyz, &P.nbr, &P.fixed_desc, &P.var_desc, &P.obs_count}) b->release();
   for (DevBuf* b : {&h->mesh_v, &h->mesh_f, &h->mesh_fn, &h->mesh_edges, &h->big_list, &h->big_count, &h->depth_masked}) b->release();
   for (DevBuf* b : {&h->splats, &h->flags, &h->offs, &h->cx, &h->cy, &h->cs, &h->cub_tmp, &h->depth, &h->partials, &h->results}) b->release();
+  for (DevBuf* b : {&h->cut_cams, &h->cut_first, &h->cut_starts, &h->cut_points, &h->cut_out, &h->xchg}) b->release();
+  for (auto& kv : h->cam_masks) for (auto& b : kv.second) b.release();
   h->pin.release();
   for (cudaEvent_t e : {h->ev0, h->ev1, h->evj0, h->evj1, h->eva0, h->eva1}) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
@@ -588,19 +688,103 @@ int b2_reg_add_intrinsics(b2_reg* h, int camera_model, int width, int height, co
 
 int b2_reg_add_image(b2_reg* h, int intrinsics_id, const uint8_t* gray, const uint8_t* mask, const float T[7], int* out_id) {
   REG_ENTER(h);
-  if (intrinsics_id < 0 || intrinsics_id >= (int)h->intr.size() || !gray || !T) return set_error(B2_ERR_ARG, "bad argument");
+  const bool mine = owned(h, h->images.size());
+  if (intrinsics_id < 0 || intrinsics_id >= (int)h->intr.size() || (mine && !gray) || !T) return set_error(B2_ERR_ARG, "bad argument");
   if (h->initialized) return set_error(B2_ERR_STATE, "add_image after initialize");
   ImageB im; im.intrinsics_id = intrinsics_id;
   for (int k = 0; k < 4; ++k) im.pose.q[k] = T[k];
   for (int k = 0; k < 3; ++k) im.pose.t[k] = T[4 + k];
   const Cam& c = h->intr[intrinsics_id].models[0];
   const size_t px = (size_t)c.w * c.h;
+  if (!mine) { im.has_mask = mask != nullptr; h->images.push_back(std::move(im)); if (out_id) *out_id = (int)h->images.size() - 1; return B2_OK; }
   im.img.resize(1); B2_TRY(im.img[0].ensure(px));
   B2_CUDA(cudaMemcpyAsync(im.img[0].p, gray, px, cudaMemcpyHostToDevice, h->stream));
   if (mask) { im.has_mask = true; im.mask.resize(1); B2_TRY(im.mask[0].ensure(px)); B2_CUDA(cudaMemcpyAsync(im.mask[0].p, mask, px, cudaMemcpyHostToDevice, h->stream)); }
   B2_CUDA(cudaStreamSynchronize(h->stream));
   h->images.push_back(std::move(im));
   if (out_id) *out_id = (int)h->images.size() - 1;
+  return B2_OK;
+}
+
+int b2_reg_add_rig(b2_reg* h, int num_cameras, const float* image_T_rig, int* out_id) {
+  REG_ENTER(h);
+  if (num_cameras < 2 || !image_T_rig) return set_error(B2_ERR_ARG, "a rig needs at least two cameras (single cameras get no rig, rig.cc:31-34)");
+  RigB r; r.image_T_rig.resize(num_cameras);
+  for (int c = 0; c < num_cameras; ++c) {
+    for (int k = 0; k < 4; ++k) r.image_T_rig[c].q[k] = image_T_rig[7 * c + k];
+    for (int k = 0; k < 3; ++k) r.image_T_rig[c].t[k] = image_T_rig[7 * c + 4 + k];
+  }
+  h->rigs.push_back(r);
+  if (out_id) *out_id = (int)h->rigs.size() - 1;
+  return B2_OK;
+}
+
+int b2_reg_add_rig_images(b2_reg* h, int rig_id, const int32_t* image_ids, int* out_id) {
+  REG_ENTER(h);
+  if (rig_id < 0 || rig_id >= (int)h->rigs.size() || !image_ids) return set_error(B2_ERR_ARG, "bad rig id");
+  const RigB& rig = h->rigs[rig_id];
+  RigImagesB ri; ri.rig_id = rig_id;
+  for (size_t c = 0; c < rig.image_T_rig.size(); ++c) {
+    const int id = image_ids[c];
+    if (id < 0 || id >= (int)h->images.size() || h->images[id].rig_images_id >= 0)
+      return set_error(B2_ERR_ARG, "rig image set needs one registered, not yet assigned image per camera (camera %d)", (int)c);
+    for (int prev : ri.image_ids) if (prev == id) return set_error(B2_ERR_ARG, "image %d listed twice", id);
+    ri.image_ids.push_back(id);
+  }
+  h->rig_images.push_back(ri);
+  const int rid = (int)h->rig_images.size() - 1;
+  for (size_t c = 0; c < ri.image_ids.size(); ++c) {
+    ImageB& im = h->images[ri.image_ids[c]];
+    im.rig_images_id = rid; im.rig_camera_index = (int)c;
+    if (c > 0) im.pose = pose_mul(rig.image_T_rig[c], h->images[ri.image_ids[0]].pose);   // as AssignRigs leaves them (rig.cc:216-250)
+  }
+  if (out_id) *out_id = rid;
+  return B2_OK;
+}
+
+int b2_reg_get_rigs(b2_reg* h, float* out) {
+  REG_ENTER(h);
+  if (!out) return set_error(B2_ERR_ARG, "null");
+  for (const RigB& r : h->rigs) for (const Pose& T : r.image_T_rig) { for (int k = 0; k < 4; ++k) out[k] = T.q[k]; for (int k = 0; k < 3; ++k) out[4 + k] = T.t[k]; out += 7; }
+  return B2_OK;
+}
+
+int b2_reg_set_rigs(b2_reg* h, const float* in) {
+  REG_ENTER(h);
+  if (!in) return set_error(B2_ERR_ARG, "null");
+  for (RigB& r : h->rigs) for (Pose& T : r.image_T_rig) { for (int k = 0; k < 4; ++k) T.q[k] = in[k]; for (int k = 0; k < 3; ++k) T.t[k] = in[4 + k]; in += 7; }
+  return B2_OK;
+}
+
+int b2_reg_variable_index(b2_reg* h, int kind, int id, int* out) {
+  REG_ENTER(h);
+  if (!out) return set_error(B2_ERR_ARG, "null");
+  if (kind == 0 && id >= 0 && id <= (int)h->intr.size()) *out = intr_var(h, id);
+  else if (kind == 1 && id >= 0 && id <= (int)h->rigs.size()) *out = rig_var(h, id);
+  else if (kind == 2 && id >= 0 && id <= (int)h->images.size()) *out = pose_var(h, id);
+  else return set_error(B2_ERR_ARG, "bad kind / id");
+  return B2_OK;
+}
+
+int b2_reg_set_camera_mask(b2_reg* h, int intrinsics_id, const uint8_t* mask) {
+  REG_ENTER(h);
+  if (intrinsics_id < 0 || intrinsics_id >= (int)h->intr.size() || !mask) return set_error(B2_ERR_ARG, "bad argument");
+  if (h->initialized) return set_error(B2_ERR_STATE, "set_camera_mask after initialize");
+  const Cam& c = h->intr[intrinsics_id].models[0];
+  std::vector<DevBuf>& pyr = h->cam_masks[intrinsics_id];
+  pyr.resize(1);
+  B2_TRY(pyr[0].ensure((size_t)c.w * c.h));
+  B2_CUDA(cudaMemcpy(pyr[0].p, mask, (size_t)c.w * c.h, cudaMemcpyHostToDevice));
+  return B2_OK;
+}
+
+int b2_reg_image_owner(int image_id, int world_size) { return world_size > 0 && image_id >= 0 ? image_id % world_size : -1; }
+
+int b2_reg_set_comm(b2_reg* h, b2_comm* comm) {
+  REG_ENTER(h);
+  if (!h->images.empty()) return set_error(B2_ERR_STATE, "b2_reg_set_comm must precede b2_reg_add_image (ownership decides which pixels are uploaded)");
+  h->comm = comm; h->rank = 0; h->world = 1;
+  if (comm) B2_TRY(b2_comm_info(comm, &h->rank, &h->world));
   return B2_OK;
 }
 
@@ -625,7 +809,9 @@ int b2_reg_initialize(b2_reg* h, int* image_scale_count) {
   }
   begin_call(h);
   B2_TRY(compute_cutoffs(h, &h->intr));
-  for (ImageB& im : h->images) {
+  for (size_t ii = 0; ii < h->images.size(); ++ii) {
+    ImageB& im = h->images[ii];
+    if (!owned(h, ii)) continue;
     const IntrinsicsB& in = h->intr[im.intrinsics_id];
     const size_t levels = in.models.size();
     im.img.resize(levels); if (im.has_mask) im.mask.resize(levels);
@@ -648,6 +834,19 @@ int b2_reg_initialize(b2_reg* h, int* image_scale_count) {
         kr_pyr_down<<<g, 256, 0, h->stream>>>(im.mask[l - 1].as<unsigned char>(), im.lw[l - 1], im.mask[l].as<unsigned char>(), im.lw[l], im.lh[l], 1);
         ++h->launches;
       }
+    }
+  }
+  for (auto& kv : h->cam_masks) {                                         // camera-mask pyramids (image.cc:62-72 + BuildMaskPyramid)
+    const IntrinsicsB& in = h->intr[kv.first];
+    std::vector<DevBuf>& pyr = kv.second;
+    pyr.resize(in.models.size());
+    for (size_t l = 1; l < in.models.size(); ++l) {
+      const Cam &a = in.models[l - 1], &b = in.models[l];
+      if ((int)(0.5 * a.w) != b.w || (int)(0.5 * a.h) != b.h) return set_error(B2_ERR_ARG, "camera mask pyramid level %zu disagrees with the camera pyramid", l);
+      B2_TRY(pyr[l].ensure((size_t)b.w * b.h));
+      dim3 g(divup(b.w, 256), b.h);
+      kr_pyr_down<<<g, 256, 0, h->stream>>>(pyr[l - 1].as<unsigned char>(), a.w, pyr[l].as<unsigned char>(), b.w, b.h, 1);
+      ++h->launches;
     }
   }
   B2_CUDA(cudaGetLastError());
@@ -770,6 +969,7 @@ int b2_reg_set_depth_map(b2_reg* h, int image_id, int width, int height, const f
   REG_ENTER(h);
   if (image_id < 0 || image_id >= (int)h->images.size() || !depth || width < 1 || height < 1) return set_error(B2_ERR_ARG, "bad argument");
   ImageB& im = h->images[image_id];
+  if (!owned(h, (size_t)image_id)) return B2_OK;   // only the owner renders / taps this image's depth map
   B2_TRY(im.given_depth.ensure((size_t)width * height * 4));
   B2_CUDA(cudaMemcpy(im.given_depth.p, depth, (size_t)width * height * 4, cudaMemcpyHostToDevice));
   im.gd_w = width; im.gd_h = height; im.has_given_depth = true;
@@ -783,6 +983,7 @@ int b2_reg_render_depth(b2_reg* h, int image_id, int* width, int* height, int* i
   REG_ENTER(h);
   if (!h->initialized) return set_error(B2_ERR_STATE, "not initialized");
   if (image_id < 0 || image_id >= (int)h->images.size()) return set_error(B2_ERR_ARG, "bad image id");
+  if (!owned(h, (size_t)image_id)) return set_error(B2_ERR_STATE, "image %d is owned by rank %d", image_id, image_id % h->world);
   const ImageB& im = h->images[image_id]; const IntrinsicsB& in = h->intr[im.intrinsics_id];
   const int best = in.best_available(std::max(h->prm.min_occlusion_check_image_scale, h->current_image_scale));
   const Cam& cam = in.model(best);
@@ -834,6 +1035,10 @@ int b2_reg_get_observations(b2_reg* h, int image_id, int ps, uint64_t* pidx, flo
 }
 
 int b2_reg_get_point_jacobians(b2_reg* h, int image_id, int ps, float* inten, float* jK, float* jP) {
+  return b2_reg_get_point_jacobians_rig(h, image_id, ps, inten, jK, jP, nullptr);
+}
+
+int b2_reg_get_point_jacobians_rig(b2_reg* h, int image_id, int ps, float* inten, float* jK, float* jP, float* jR) {
   REG_ENTER(h); B2_TRY(check_obs(h, image_id, ps));
   ObsSet& o = h->obs[image_id][ps];
   if (o.count == 0) return B2_OK;
@@ -841,8 +1046,13 @@ int b2_reg_get_point_jacobians(b2_reg* h, int image_id, int ps, float* inten, fl
   const Levels L = levels_of(h, I, h->intr[I.intrinsics_id]);
   begin_call(h);
   const int np = h->intr[I.intrinsics_id].np();
-  launch_jacobians(h, np, o, h->pts[ps], pose3_of(I.pose), L);
+  int rv; const RigDev rig = rig_dev(h, current_state(h), image_id, &rv);
+  launch_jacobians(h, np, o, h->pts[ps], pose3_of(I.pose), L, rig);
   B2_CUDA(cudaGetLastError());
+  if (jR) {
+    if (rig.dependent) B2_CUDA(cudaMemcpyAsync(jR, o.jR.p, o.count * 24, cudaMemcpyDeviceToHost, h->stream));
+    else std::memset(jR, 0, o.count * 24);
+  }
   if (inten) B2_CUDA(cudaMemcpyAsync(inten, o.inten.p, o.count * 4, cudaMemcpyDeviceToHost, h->stream));
   if (jK) B2_CUDA(cudaMemcpyAsync(jK, o.jK.p, o.count * 4 * np, cudaMemcpyDeviceToHost, h->stream));
   if (jP) B2_CUDA(cudaMemcpyAsync(jP, o.jP.p, o.count * 24, cudaMemcpyDeviceToHost, h->stream));

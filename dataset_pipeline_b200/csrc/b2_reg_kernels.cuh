@@ -26,6 +26,7 @@ struct Levels {
   Cam cam[kMaxLevels];
   const unsigned char* img[kMaxLevels];
   const unsigned char* mask[kMaxLevels];   // null = no mask at that level
+  const unsigned char* cmask[kMaxLevels];  // camera mask of the intrinsics (intrinsics.h:104), null = none
   int nlevels, min_image_scale;
 };
 
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(256) kr_visibility(const float* __restrict__ x
           if (V.check_masks) {
             const int level = small - L.min_image_scale;
             if (L.mask[level] != nullptr && __ldg(L.mask[level] + (size_t)jiy * ic.w + jix) != 0) keep = false;
+            else if (L.cmask[level] != nullptr && __ldg(L.cmask[level] + (size_t)jiy * ic.w + jix) != 0) keep = false;
             else if ((float)__ldg(L.img[level] + (size_t)jiy * ic.w + jix) > V.max_valid_intensity) keep = false;
           }
           if (keep) { ok = 1; rx_ = jx; ry_ = jy; rs_ = observation_scale; }
@@ -353,12 +355,22 @@ __global__ void __launch_bounds__(256) kr_intensity(size_t count, const float* _
   inten[i] = trilinear(L, small, ox[i], oy[i], 1 - (s - (int)s));
 }
 
-// K11 (intrinsics_and_pose_optimizer.cc:933-1147), non-rig, depth residuals off. NI = intrinsics parameter count of the camera model.
+// What a dependent rig image (camera index > 0) adds to K11 (intrinsics_and_pose_optimizer.cc:651-670, 1107-1143).
+struct RigDev { int dependent; float Rr[9]; float q[4]; float t[3]; };   // image_T_rig rotation matrix; rig_T_global as quaternion + translation
+__device__ __forceinline__ void quat_rotate_dev(const float q[4], float px, float py, float pz, float* ox, float* oy, float* oz) {   // so3.hpp:360-370
+  float ux = q[1] * pz - q[2] * py, uy = q[2] * px - q[0] * pz, uz = q[0] * py - q[1] * px;
+  ux = ux + ux; uy = uy + uy; uz = uz + uz;
+  const float cx = q[1] * uz - q[2] * uy, cy = q[2] * ux - q[0] * uz, cz = q[0] * uy - q[1] * ux;
+  *ox = px + q[3] * ux + cx; *oy = py + q[3] * uy + cy; *oz = pz + q[3] * uz + cz;
+}
+
+// K11 (intrinsics_and_pose_optimizer.cc:933-1147), depth residuals off. NI = intrinsics parameter count of the camera model. For a
+// dependent rig image jP is the derivative by the rig REFERENCE image's pose and jR (6 per observation) by this camera's extrinsics.
 template <int NI>
 __global__ void __launch_bounds__(256) kr_jacobians(size_t count, const unsigned int* __restrict__ idx, const float* __restrict__ ox,
                                                     const float* __restrict__ oy, const float* __restrict__ os, const float* __restrict__ xyz,
                                                     Pose3 P, float point_radius, Levels L, float* __restrict__ inten, float* __restrict__ jK,
-                                                    float* __restrict__ jP) {
+                                                    float* __restrict__ jP, RigDev rig, float* __restrict__ jR) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const Cam& cam = L.cam[0];
@@ -404,6 +416,20 @@ __global__ void __launch_bounds__(256) kr_jacobians(size_t count, const unsigned
   }
   // [I | -[p]x]: rows (1,0,0,0,z,-y), (0,1,0,-z,0,x), (0,0,1,y,-x,0)
   const float C[18] = {1, 0, 0, 0, tz, -1 * ty, 0, 1, 0, -1 * tz, 0, tx, 0, 0, 1, ty, -1 * tx, 0};
+  if (rig.dependent) {
+    float rx, ry, rz; quat_rotate_dev(rig.q, xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], &rx, &ry, &rz);
+    rx += rig.t[0]; ry += rig.t[1]; rz += rig.t[2];
+    float gr[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gr[k] = sum3p(g[0] * rig.Rr[k], g[1] * rig.Rr[3 + k], g[2] * rig.Rr[6 + k]);
+    const float Cr[18] = {1, 0, 0, 0, rz, -1 * ry, 0, 1, 0, -1 * rz, 0, rx, 0, 0, 1, ry, -1 * rx, 0};
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      jP[6 * i + c] = sum3p(gr[0] * Cr[c], gr[1] * Cr[6 + c], gr[2] * Cr[12 + c]);
+      jR[6 * i + c] = sum3p(g[0] * C[c], g[1] * C[6 + c], g[2] * C[12 + c]);
+    }
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < 6; ++c) jP[6 * i + c] = sum3p(g[0] * C[c], g[1] * C[6 + c], g[2] * C[12 + c]);
 }
@@ -529,10 +555,12 @@ __global__ void __launch_bounds__(128) kr_accumulate(ResidualArgs A, const float
 // which no longer fits one thread's registers. One WARP per observation: lane l < NI+6 holds Jacobian column l of the centre /
 // neighbour rows, the 189 accumulators are spread over the lanes (6 each) and every (r, c) product fetches its two factors with
 // shuffles. Same fp32 products and fp64 accumulation as the per-thread kernel; per-block output [NH | NV | 4 sums].
-template <int NI>
+// With RIG (dependent rig image) the local system has 6 more columns, ordered [intrinsics | rig extrinsics | reference pose] like the
+// global variable vector, so that every upper-triangle product has the factor order of AccumulateOnHAndB (:1262-1283).
+template <int NI, bool RIG>
 __global__ void __launch_bounds__(128) kr_accumulate_wide(ResidualArgs A, const float* __restrict__ jK, const float* __restrict__ jP,
-                                                          double* __restrict__ partials /* [grid][NH + NV + 4] */) {
-  constexpr int NV = NI + 6, NH = NV * (NV + 1) / 2, NE = NH + NV, SL = (NE + 31) / 32, NOUT = NE + 4;
+                                                          const float* __restrict__ jR, double* __restrict__ partials /* [grid][NH + NV + 4] */) {
+  constexpr int NR = RIG ? 6 : 0, NV = NI + NR + 6, NH = NV * (NV + 1) / 2, NE = NH + NV, SL = (NE + 31) / 32, NOUT = NE + 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int er[SL], ec[SL];   // entry e = s*32 + lane: H(r, c) for e < NH (e = c(c+1)/2 + r), b(c) with r = -1 for NH <= e < NE, unused r = -2
 #pragma unroll
@@ -554,7 +582,9 @@ __global__ void __launch_bounds__(128) kr_accumulate_wide(ResidualArgs A, const 
     int nj = 0; float In = 0.f;
     if (lane < A.K) { nj = A.slot[A.nbr[p * A.K + lane]]; In = A.inten[nj]; }
     float jc = 0.f;
-    if (lane < NI) jc = jK[(size_t)NI * i + lane]; else if (lane < NV) jc = jP[6 * i + (lane - NI)];
+    if (lane < NI) jc = jK[(size_t)NI * i + lane];
+    else if (RIG && lane < NI + NR) jc = jR[6 * i + (lane - NI)];
+    else if (lane < NV) jc = jP[6 * i + (lane - NI - NR)];
 #pragma unroll
     for (int type = 0; type < 2; ++type) {
       const float sw = type == 0 ? A.fixed_w : A.var_w;
@@ -574,7 +604,9 @@ __global__ void __launch_bounds__(128) kr_accumulate_wide(ResidualArgs A, const 
           const int njk = __shfl_sync(0xffffffffu, nj, k);
           const float wr = w * __shfl_sync(0xffffffffu, cmp, k);
           float dj = 0.f;
-          if (lane < NI) dj = jK[(size_t)NI * njk + lane] - jc; else if (lane < NV) dj = jP[(size_t)6 * njk + (lane - NI)] - jc;
+          if (lane < NI) dj = jK[(size_t)NI * njk + lane] - jc;
+          else if (RIG && lane < NI + NR) dj = jR[(size_t)6 * njk + (lane - NI)] - jc;
+          else if (lane < NV) dj = jP[(size_t)6 * njk + (lane - NI - NR)] - jc;
 #pragma unroll
           for (int s = 0; s < SL; ++s) {
             const float a = __shfl_sync(0xffffffffu, dj, max(er[s], 0)), b = __shfl_sync(0xffffffffu, dj, ec[s]);
@@ -598,11 +630,11 @@ __global__ void __launch_bounds__(128) kr_accumulate_wide(ResidualArgs A, const 
 
 // Fixed-order sum of the per-block partials: out[v] = sum_b partials[b][v].
 __global__ void __launch_bounds__(256) kr_reduce_partials(const double* __restrict__ partials, int nblocks, int nvals, double* __restrict__ out) {
-  const int v = threadIdx.x;
-  if (v >= nvals) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * nvals + v];
-  out[v] = s;
+  for (int v = threadIdx.x; v < nvals; v += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * nvals + v];
+    out[v] = s;
+  }
 }
 
 // K14 (color_optimizer.cc:84-108): one image at a time; a point has at most one observation per image and scale, so the

@@ -59,6 +59,15 @@ def _L():
     L.b2_reg_apply.argtypes = [vp, fp, fp, ip, ip]
     L.b2_reg_run_on_current_scale.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_int, dp, ip, ip]
     L.b2_reg_last_stats.argtypes = [vp, C.POINTER(RegStats)]
+    L.b2_reg_add_rig.argtypes = [vp, C.c_int, fp, ip]
+    L.b2_reg_add_rig_images.argtypes = [vp, C.c_int, ip, ip]
+    L.b2_reg_get_rigs.argtypes = [vp, fp]
+    L.b2_reg_set_rigs.argtypes = [vp, fp]
+    L.b2_reg_variable_index.argtypes = [vp, C.c_int, C.c_int, ip]
+    L.b2_reg_get_point_jacobians_rig.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, fp]
+    L.b2_reg_set_camera_mask.argtypes = [vp, C.c_int, u8]
+    L.b2_reg_set_comm.argtypes = [vp, vp]
+    L.b2_reg_image_owner.argtypes = [C.c_int, C.c_int]
     L.b2_camera_eval.argtypes = [C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, fp, C.c_size_t, fp, fp]
     _bound = True
     return L
@@ -112,7 +121,7 @@ class Registration:
         self._h = C.c_void_p()
         _lib.check(L.b2_reg_create(C.byref(self.params), C.byref(self._h)))
         self.K = self.params.point_neighbor_count
-        self.n_intr = 0; self.n_img = 0; self.scale_sizes = []; self.intr_np = []; self.image_intr = []
+        self.n_intr = 0; self.n_img = 0; self.scale_sizes = []; self.intr_np = []; self.image_intr = []; self.rig_cams = []
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -132,14 +141,64 @@ class Registration:
         self.n_intr += 1; self.intr_np.append(int(p.size))
         return out.value
 
+    def set_camera_mask(self, intrinsics_id, mask):
+        m = np.ascontiguousarray(mask, np.uint8)
+        _lib.check(_L().b2_reg_set_camera_mask(self._h, intrinsics_id, _u8(m)))
+
+    # ---- multi-GPU ----
+    def set_comm(self, comm):
+        """comm: dataset_pipeline_b200.icp.Comm (library-owned NCCL communicator) or None. Before add_image. Images are dealt
+        round-robin (image_owner); every rank makes the same calls, and may pass gray=None for images it does not own."""
+        _lib.check(_L().b2_reg_set_comm(self._h, comm._c if comm is not None else None))
+        self._comm = comm
+        self._rank, self._world = (comm.rank, comm.world_size) if comm is not None else (0, 1)
+
+    def owns(self, image_id):
+        return image_id % getattr(self, "_world", 1) == getattr(self, "_rank", 0)
+
+    # ---- rigs (opt::Rig / opt::RigImages) ----
+    def add_rig(self, image_T_rig):
+        """image_T_rig: (num_cameras, 7) qx qy qz qw tx ty tz, camera 0 = reference (identity)."""
+        T = np.ascontiguousarray(image_T_rig, np.float32).reshape(-1, 7); out = C.c_int32(0)
+        _lib.check(_L().b2_reg_add_rig(self._h, T.shape[0], _f(T), C.byref(out)))
+        self.rig_cams.append(T.shape[0])
+        return out.value
+
+    def add_rig_images(self, rig_id, image_ids):
+        ids = np.ascontiguousarray(image_ids, np.int32); out = C.c_int32(0)
+        if ids.size != self.rig_cams[rig_id]:
+            raise ValueError("one image id per rig camera")
+        _lib.check(_L().b2_reg_add_rig_images(self._h, rig_id, ids.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(out)))
+        return out.value
+
+    def get_rigs(self):
+        out = np.zeros((sum(self.rig_cams), 7), np.float32)
+        if out.size:
+            _lib.check(_L().b2_reg_get_rigs(self._h, _f(out)))
+        return out
+
+    def set_rigs(self, image_T_rig_all):
+        T = np.ascontiguousarray(image_T_rig_all, np.float32).reshape(-1, 7)
+        if T.shape[0] != sum(self.rig_cams):
+            raise ValueError("expected %d rig camera poses" % sum(self.rig_cams))
+        _lib.check(_L().b2_reg_set_rigs(self._h, _f(T)))
+
+    def variable_index(self, kind, idx):
+        """kind: "intrinsics" | "rig" | "image" -> first variable of that block in the optimizer's vector."""
+        out = C.c_int32(0)
+        _lib.check(_L().b2_reg_variable_index(self._h, {"intrinsics": 0, "rig": 1, "image": 2}[kind], idx, C.byref(out)))
+        return out.value
+
     def _intr_shape(self, flat):
         return flat.reshape(self.n_intr, -1) if len(set(self.intr_np)) == 1 else flat
 
     def add_image(self, intrinsics_id, gray, mask, image_T_global):
-        g = np.ascontiguousarray(gray, np.uint8); T = np.ascontiguousarray(image_T_global, np.float32)
+        T = np.ascontiguousarray(image_T_global, np.float32)
+        g = np.ascontiguousarray(gray, np.uint8) if gray is not None else None
         m = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
         out = C.c_int32(0)
-        _lib.check(_L().b2_reg_add_image(self._h, intrinsics_id, _u8(g), _u8(m) if m is not None else None, _f(T), C.byref(out)))
+        _lib.check(_L().b2_reg_add_image(self._h, intrinsics_id, _u8(g) if g is not None else None, _u8(m) if m is not None else None, _f(T),
+                                         C.byref(out)))
         self.n_img += 1; self.image_intr.append(int(intrinsics_id))
         return out.value
 
@@ -201,6 +260,14 @@ class Registration:
         if n:
             _lib.check(_L().b2_reg_get_point_jacobians(self._h, image, ps, _f(I), _f(jK), _f(jP)))
         return I, jK, jP
+
+    def point_jacobians_rig(self, image, ps):
+        n = len(self.observations(image, ps)[0])
+        I = np.zeros(n, np.float32); jK = np.zeros((n, self.intr_np[self.image_intr[image]]), np.float32)
+        jP = np.zeros((n, 6), np.float32); jR = np.zeros((n, 6), np.float32)
+        if n:
+            _lib.check(_L().b2_reg_get_point_jacobians_rig(self._h, image, ps, _f(I), _f(jK), _f(jP), _f(jR)))
+        return I, jK, jP, jR
 
     # ---- ColorOptimizer / CostCalculator / IntrinsicsAndPoseOptimizer ----
     def ColorOptimizerApply(self):

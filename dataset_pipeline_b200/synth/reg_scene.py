@@ -54,6 +54,66 @@ def unproject(camera_model, dist, dx, dy):
     return ux, uy
 
 
+def render_image(width, height, K, camera_model, distortion, R_wc, c):
+    """Image of the textured plane z = 0 from the camera with centre c and camera-to-world rotation R_wc."""
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float64)
+    ux, uy = unproject(camera_model, distortion, (xx - K[2]) / K[0], (yy - K[3]) / K[1])
+    d_w = np.stack([ux, uy, np.ones_like(xx)], -1) @ R_wc.T
+    s = -c[2] / d_w[..., 2]
+    pw = c + d_w * s[..., None]
+    return np.clip(np.rint(texture(pw[..., 0], pw[..., 1])), 0, 255).astype(np.uint8)
+
+
+def pose7(R_cw, t_cw):
+    return np.concatenate([quat_from_R(R_cw), t_cw]).astype(np.float32)
+
+
+def make_rig_scene(num_sets=2, width=320, height=240, fx=260.0, camera_model=CAM_PINHOLE, distortion=DEFAULT_DISTORTION, num_scales=3,
+                   base_radius=0.004, seed=5, perturb=(0.002, 0.002)):
+    """Two-camera rig recorded `num_sets` times. Returns the make_scene dict (images ordered set0-cam0, set0-cam1, set1-cam0, ...)
+    plus rig_gt / rig_init ((2,7) image_T_rig, camera 0 identity) and rig_sets (image ids per set)."""
+    rng = np.random.default_rng(seed)
+    base = make_scene(num_images=0, width=width, height=height, fx=fx, num_scales=num_scales, base_radius=base_radius, camera_model=camera_model,
+                      distortion=distortion)
+    K = base["intr"][2][:4]
+    E_R = rot(0.02, -0.05, 0.03); E_t = np.array([-0.18, 0.01, 0.005])          # cam1_T_cam0 (image_T_rig of camera 1)
+    images, poses_gt, poses_init, sets = [], [], [], []
+    dE = rot(*(rng.uniform(-perturb[1], perturb[1], 3))); dEt = rng.uniform(-perturb[0], perturb[0], 3)
+    Ei_R, Ei_t = dE @ E_R, dE @ E_t + dEt
+    for i in range(num_sets):
+        c = np.array([0.2 * math.cos(1.9 * i), 0.15 * math.sin(1.3 * i), 2.0 + 0.08 * i])
+        R_wc = rot(math.pi + 0.06 * math.sin(1.1 * i + 0.3), 0.05 * math.cos(0.7 * i), 0.4 * i)
+        R0 = R_wc.T; t0 = -R0 @ c
+        dR = rot(*(rng.uniform(-perturb[1], perturb[1], 3))); dt = rng.uniform(-perturb[0], perturb[0], 3)
+        R0i, t0i = dR @ R0, dR @ t0 + dt
+        ids = []
+        for cam, (R, t, Ri, ti) in enumerate([(R0, t0, R0i, t0i), (E_R @ R0, E_R @ t0 + E_t, Ei_R @ R0i, Ei_R @ t0i + Ei_t)]):
+            images.append(render_image(width, height, K, camera_model, distortion, R.T, -R.T @ t))
+            poses_gt.append(pose7(R, t)); poses_init.append(pose7(Ri, ti))
+            ids.append(len(images) - 1)
+        sets.append(ids)
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
+    base.update(images=images, poses_gt=poses_gt, poses_init=poses_init, rig_sets=sets,
+                rig_gt=np.stack([ident, pose7(E_R, E_t)]), rig_init=np.stack([ident, pose7(Ei_R, Ei_t)]))
+    return base
+
+
+def load_rig_into(reg, scene, use_init=True):
+    """load_into for a make_rig_scene scene: images, then the rig and its image sets (which define the dependent images' poses)."""
+    w, h, K = scene["intr"]
+    reg.add_intrinsics(w, h, K, camera_model=scene.get("camera_model", CAM_PINHOLE))
+    for img, T in zip(scene["images"], scene["poses_init"] if use_init else scene["poses_gt"]):
+        reg.add_image(0, img, None, T)
+    rig = reg.add_rig(scene["rig_init"] if use_init else scene["rig_gt"])
+    for ids in scene["rig_sets"]:
+        reg.add_rig_images(rig, ids)
+    count = reg.initialize()
+    for xyz, radius, nbr, colors in scene["scales"]:
+        reg.add_point_scale(xyz, float(radius), nbr, colors)
+    reg.set_splat_points(scene["scales"][0][0])
+    return count
+
+
 def make_scene(num_images=3, width=640, height=480, fx=520.0, extent=(2.4, 1.8), base_radius=0.0025, num_scales=3, seed=31,
                perturb=(0.002, 0.002), camera_model=CAM_PINHOLE, distortion=DEFAULT_DISTORTION):
     """Returns dict(intr=(w,h,params), camera_model, images=[uint8 HxW], poses_gt, poses_init (qx qy qz qw tx ty tz),
@@ -67,15 +127,7 @@ def make_scene(num_images=3, width=640, height=480, fx=520.0, extent=(2.4, 1.8),
         c = np.array([0.25 * math.cos(2.1 * i), 0.2 * math.sin(1.7 * i), 2.0 + 0.1 * math.sin(i)])
         R_wc = rot(math.pi + 0.08 * math.sin(1.3 * i), 0.07 * math.cos(0.9 * i), 0.3 * i)      # camera-to-world
         R_cw = R_wc.T; t_cw = -R_cw @ c
-        # render: pixel ray in camera frame -> world -> z=0
-        yy, xx = np.mgrid[0:height, 0:width].astype(np.float64)
-        ux, uy = unproject(camera_model, distortion, (xx - K[2]) / K[0], (yy - K[3]) / K[1])
-        d_c = np.stack([ux, uy, np.ones_like(xx)], -1)
-        d_w = d_c @ R_wc.T
-        s = -c[2] / d_w[..., 2]
-        pw = c + d_w * s[..., None]
-        img = np.clip(np.rint(texture(pw[..., 0], pw[..., 1])), 0, 255).astype(np.uint8)
-        images.append(img)
+        images.append(render_image(width, height, K, camera_model, distortion, R_wc, c))
         q = quat_from_R(R_cw)
         poses_gt.append(np.concatenate([q, t_cw]).astype(np.float32))
         dR = rot(*(rng.uniform(-perturb[1], perturb[1], 3))); dt = rng.uniform(-perturb[0], perturb[0], 3)

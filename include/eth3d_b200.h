@@ -61,6 +61,8 @@ int b2_comm_unique_id(unsigned char id[128]);
 int b2_comm_create(int rank, int world_size, const unsigned char id[128], int device, b2_comm** out);
 int b2_comm_destroy(b2_comm* c);
 int b2_comm_allreduce_f64(b2_comm* c, double* buf_dev, size_t count, void* stream);   /* in-place sum, ordered on stream */
+enum { B2_F64 = 0, B2_F32 = 1, B2_I32 = 2 };
+int b2_comm_allreduce(b2_comm* c, void* buf_dev, size_t count, int dtype /* B2_F64 | B2_F32 | B2_I32 */, void* stream);   /* in-place sum */
 int b2_comm_info(b2_comm* c, int* rank, int* world_size);
 
 typedef struct b2_icp_config {
@@ -208,6 +210,30 @@ int b2_reg_add_intrinsics(b2_reg* h, int camera_model, int width, int height, co
 /* gray: width*height uint8 (cv::imread GRAYSCALE); mask: same size or NULL (values 0/1/2, image.h:43-47);
  * image_T_global: Sophus::SE3f::data() order qx qy qz qw tx ty tz (what io::ReadColmapImages fills, colmap_model.cc:117-124). */
 int b2_reg_add_image(b2_reg* h, int intrinsics_id, const uint8_t* gray, const uint8_t* mask, const float image_T_global[7], int* out_id);
+/* Camera mask of an intrinsics (opt::Intrinsics::camera_mask, intrinsics.h:104; loaded next to the image masks, image.cc:62-72):
+ * width*height uint8 with the image-mask values; observations on non-zero pixels are discarded (visibility_estimator.cc:492-501).
+ * Before b2_reg_initialize. */
+int b2_reg_set_camera_mask(b2_reg* h, int intrinsics_id, const uint8_t* mask);
+/* Camera rigs (opt::Rig, rig.h:40-73; opt::RigImages, rig_images.h:38-64). image_T_rig: 7 floats per camera (qx qy qz qw tx ty tz),
+ * camera 0 is the reference (identity); the other extrinsics are optimisation variables (6 each, after all intrinsics blocks and
+ * before the image poses, CountAndIndexVariables :442-473). b2_reg_add_rig_images binds one already added image per camera (all
+ * present) recorded at the same time; the dependent images lose their own pose variables and get image_T_rig[c] * pose(reference),
+ * as AssignRigs leaves them (rig.cc:216-250; the averaging that produces the initial extrinsics there is the caller's job). */
+int b2_reg_add_rig(b2_reg* h, int num_cameras, const float* image_T_rig, int* out_rig_id);
+int b2_reg_add_rig_images(b2_reg* h, int rig_id, const int32_t* image_ids, int* out_rig_images_id);
+int b2_reg_get_rigs(b2_reg* h, float* image_T_rig_all /* 7 per camera, rigs in id order */);
+int b2_reg_set_rigs(b2_reg* h, const float* image_T_rig_all);
+/* First variable of an intrinsics block (kind 0), a rig's extrinsics block (1) or the pose block an image uses (2; a dependent rig
+ * image reports its reference image's block). id == count gives the end of that group. */
+int b2_reg_variable_index(b2_reg* h, int kind, int id, int* out_index);
+/* Multi-GPU: one process per GPU, images dealt round-robin (b2_reg_image_owner: image_id % world_size). Every rank
+ * makes the SAME calls with the same arguments (a rank may pass gray = mask = NULL to b2_reg_add_image for images it does not
+ * own); points, descriptors and the state (intrinsics, rigs, all poses) are replicated, pyramids / depth maps / observation sets
+ * exist only on the owner. Exchanges, all sum-allreduces on the handle's stream: the descriptor sums and counts of
+ * b2_reg_color_update (5 floats + 1 int per point and scale), [H | b | sums] of b2_reg_accumulate / b2_reg_apply, the four
+ * residual sums of every cost evaluation. Call before b2_reg_add_image; comm = NULL returns to single-GPU operation. */
+int b2_reg_set_comm(b2_reg* h, b2_comm* comm);
+int b2_reg_image_owner(int image_id, int world_size);
 /* Problem::InitializeImages + LoadImages pyramids. *image_scale_count receives Problem::image_scale_count(). */
 int b2_reg_initialize(b2_reg* h, int* image_scale_count);
 /* One scale of the multi-resolution point cloud (problem.h points()/point_radius()/neighbor indices) + grey colours from which the
@@ -231,6 +257,10 @@ int b2_reg_get_observations(b2_reg* h, int image_id, int point_scale, uint64_t* 
 /* ComputePointIntensityAndJacobians of every observation of (image, scale): intensity[n], j_intrinsics[np*n] (np = the image's
  * camera model parameter count), j_pose[6n]. */
 int b2_reg_get_point_jacobians(b2_reg* h, int image_id, int point_scale, float* intensity, float* j_intrinsics, float* j_pose);
+/* As above plus j_rig_extrinsics[6n]: for a dependent rig image j_pose is the derivative by the rig REFERENCE image's pose and
+ * j_rig_extrinsics by this camera's image_T_rig (intrinsics_and_pose_optimizer.cc:1107-1143); zeros for other images. */
+int b2_reg_get_point_jacobians_rig(b2_reg* h, int image_id, int point_scale, float* intensity, float* j_intrinsics, float* j_pose,
+                                   float* j_rig_extrinsics);
 int b2_reg_color_update(b2_reg* h);
 int b2_reg_get_descriptors(b2_reg* h, int point_scale, float* fixed_desc, float* variable_desc, int32_t* observation_counts);
 /* sums: fixed_sum, n_fixed, variable_sum, n_variable, 0, 0 (the six accumulators of cost_calculator.cc:48-53). */

@@ -239,6 +239,7 @@ def _bind_reg():
     L.orc_cam_eval.argtypes = [C.c_int, C.c_int, C.c_int, fp, C.c_int, fp, C.c_size_t, fp]
     L.orc_reg_add_image.argtypes = [vp, C.c_int, u8, u8, fp]
     L.orc_reg_initialize.argtypes = [vp]
+    L.orc_reg_set_camera_mask.argtypes = [vp, C.c_int, u8]
     L.orc_reg_add_rig.argtypes = [vp, C.c_int, fp]
     L.orc_reg_add_rig_images.argtypes = [vp, C.c_int, ip]
     L.orc_reg_get_rigs.argtypes = [vp, fp]
@@ -343,6 +344,11 @@ class Registration:
             raise ValueError("camera model %d takes %d parameters" % (model, cam_param_count(model)))
         self.n_intr += 1; self.intr_np.append(int(p.size))
         return lib().orc_reg_add_intrinsics_model(self._h, model, w, h, _f(p))
+
+    def set_camera_mask(self, intr_id, mask):
+        m = np.ascontiguousarray(mask, np.uint8)
+        if lib().orc_reg_set_camera_mask(self._h, intr_id, _u8(m)) != 0:
+            raise ValueError("bad intrinsics id")
 
     def add_rig(self, image_T_rig):
         """image_T_rig: (num_cameras, 7) qx qy qz qw tx ty tz, camera 0 = reference (identity)."""

@@ -76,6 +76,7 @@ int orc_reg_add_intrinsics(orc_reg*, int w, int h, const float fx_fy_cx_cy[4]); 
 int orc_reg_add_intrinsics_model(orc_reg*, int type, int w, int h, const float* params);
 /* image_T_global as Sophus::SE3f::data(): qx qy qz qw tx ty tz */
 int orc_reg_add_image(orc_reg*, int intrinsics_id, const uint8_t* gray, const uint8_t* mask_or_null, const float image_T_global[7]);
+int orc_reg_set_camera_mask(orc_reg*, int intrinsics_id, const uint8_t* mask);   /* intrinsics.h:104; before initialize */
 int orc_reg_initialize(orc_reg*);
 /* rigs (rig.h:40-73, rig_images.h:38-64): image_T_rig 7 floats per camera, camera 0 = reference; add_rig_images binds one image per
  * camera (all present) and sets the dependent images' poses to image_T_rig[c] * pose(reference). -1 on bad arguments. */

@@ -15,7 +15,7 @@
 // Pinned by the reference's camera tests ported in tests/test_oracle_camera.py (camera/test/test_camera.cc:40-420,508-515).
 // Eigen evaluation order restated by hand: 2-term sums are a*b + c*d, Matrix2f::inverse() is the cofactor form times 1/det
 // (Eigen/src/LU/InverseImpl.h, size-2 specialisation), no fused multiply-add (the reference builds without -mfma).
-// Defined here where the reference is undefined behaviour: float->int of a non-finite value yields INT_MIN (x86 cvttss2si).
+// Defined here where the reference is platform-dependent: atan2f -> correctly rounded (atan_r1 below). Where it is undefined behaviour: float->int of a non-finite value yields INT_MIN (x86 cvttss2si).
 #ifndef ORC_CAMERA_H_
 #define ORC_CAMERA_H_
 #include <algorithm>
@@ -27,6 +27,11 @@
 namespace orc {
 
 enum CameraType { kCamPinhole = 4, kCamBenchmark = 5, kCamThinPrism = 14 };
+
+// atan2(r, 1.f) of camera_base_impl_fisheye.h:68,104,135. The reference gets whatever its libm's atan2f returns: correctly rounded
+// with glibc >= 2.41 (CORE-MATH), up to 1 ulp off (and dependent on the CPU's FMA dispatch) with older glibc. The oracle pins the
+// correctly rounded value, computed as the rounding of the fp64 arctangent — the same definition the device code uses.
+static inline float atan_r1(float r) { return (float)std::atan((double)r); }
 
 static inline int f2i(float v) {   // x86 cvttss2si semantics made explicit
   if (!(v > -2147483904.f && v < 2147483648.f)) return std::numeric_limits<int>::min();
@@ -98,7 +103,7 @@ struct Camera {
     if (type == kCamThinPrism) { tp_distort(x, y, ox, oy); return; }
     const float r = std::sqrt(x * x + y * y);                              // camera_base_impl_fisheye.h:65-78
     if (r > 1e-6f) {
-      const float atan_r = atan2f(r, 1.f);
+      const float atan_r = atan_r1(r);
       if (atan_r * atan_r > inner_cutoff2) { *ox = x * std::numeric_limits<float>::infinity(); *oy = y * std::numeric_limits<float>::infinity(); return; }
       const float theta_by_r = atan_r / r;
       tp_distort(x * theta_by_r, y * theta_by_r, ox, oy);
@@ -112,7 +117,7 @@ struct Camera {
     const float nx_ny = nx * ny, nx2 = nx * nx, ny2 = ny * ny, r2 = nx2 + ny2;   // camera_base_impl_fisheye.h:96-126
     const float r = sqrtf(r2);
     if (r > 1e-6f) {
-      const float atan_r = atan2f(r, 1.f);
+      const float atan_r = atan_r1(r);
       if (atan_r * atan_r > inner_cutoff2) { J[0] = J[1] = J[2] = J[3] = 0; return; }
       const float theta_by_r = atan_r / r;
       const float term1 = r2 * (r2 + 1);
@@ -132,7 +137,7 @@ struct Camera {
     if (type == kCamThinPrism) { tp_deriv_params(nx, ny, D); return; }
     const float r = std::sqrt(nx * nx + ny * ny);
     if (r > 1e-6f) {
-      const float atan_r = atan2f(r, 1.f);
+      const float atan_r = atan_r1(r);
       if (atan_r * atan_r > inner_cutoff2) { for (int i = 0; i < 16; ++i) D[i] = 0; return; }
       const float theta_by_r = atan_r / r;
       tp_deriv_params(theta_by_r * nx, theta_by_r * ny, D);

@@ -96,6 +96,7 @@ static inline int larger_scale(const Observation& o) { return (int)o.scale; }
 
 struct Intrinsics {
   std::vector<Pinhole> models;   // index 0 = original resolution
+  std::vector<Img8> camera_mask; // intrinsics.h:104: one mask pyramid per camera (empty = none), same semantics as the image masks
   int min_image_scale = -1;
   const Pinhole& model(int image_scale) const { return models[std::max(0, image_scale - min_image_scale)]; }
   int best_available(int image_scale) const { return std::min<int>(min_image_scale + (int)models.size() - 1, std::max<int>(min_image_scale, image_scale)); }
@@ -232,6 +233,7 @@ static void create_observation_if_scale_fits(const orc_reg* h, const Intrinsics&
       if (check_masks) {
         const int level = small - intr.min_image_scale;
         if (level < (int)im.mask.size() && !im.mask[level].d.empty() && im.mask[level].at(iy, ix) != 0) return;
+        if (level < (int)intr.camera_mask.size() && !intr.camera_mask[level].d.empty() && intr.camera_mask[level].at(iy, ix) != 0) return;   // :492-501
         if (im.image[level].at(iy, ix) > h->prm.maximum_valid_intensity) return;
       }
       out->push_back(Observation{point_index, jx, jy, observation_scale});
@@ -559,6 +561,14 @@ int orc_reg_add_image(orc_reg* h, int intr_id, const uint8_t* gray, const uint8_
   if (mask) { im.mask.resize(1); im.mask[0].w = c.w; im.mask[0].h = c.h; im.mask[0].d.assign(mask, mask + (size_t)c.w * c.h); }
   h->st.images.push_back(std::move(im)); return (int)h->st.images.size() - 1;
 }
+// Camera mask of an intrinsics (image.cc:62-72, intrinsics.h:104): full-resolution uint8, values as the image masks; before initialize.
+int orc_reg_set_camera_mask(orc_reg* h, int intr_id, const uint8_t* mask) {
+  if (intr_id < 0 || intr_id >= (int)h->st.intr.size()) return -1;
+  Intrinsics& in = h->st.intr[intr_id];
+  in.camera_mask.resize(1); in.camera_mask[0].w = in.models[0].w; in.camera_mask[0].h = in.models[0].h;
+  in.camera_mask[0].d.assign(mask, mask + (size_t)in.models[0].w * in.models[0].h);
+  return 0;
+}
 // Problem::InitializeImages (problem.cc:478-494) + pyramids. Returns image_scale_count, or -1 on odd pyramid parents.
 int orc_reg_initialize(orc_reg* h) {
   int count = 1;
@@ -576,6 +586,7 @@ int orc_reg_initialize(orc_reg* h) {
     in.models.resize(count - in.min_image_scale);
     in.build_pyramid();
   }
+  for (Intrinsics& in : h->st.intr) if (!in.camera_mask.empty()) { in.camera_mask.resize(in.models.size()); build_mask_pyramid(in.camera_mask); }
   for (Image& im : h->st.images) {
     const size_t levels = h->st.intr[im.intrinsics_id].models.size();
     im.image.resize(levels);

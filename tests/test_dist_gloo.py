@@ -98,3 +98,66 @@ def test_two_rank_allreduce_reproduces_single_rank_system(oracle):
     assert all(p.exitcode == 0 for p in procs)
     assert ret["pairs"] == ret["expected_pairs"]
     assert ret["H_err"] < 1e-5 and ret["b_err"] < 1e-5 and ret["cost_err"] < 1e-9
+
+
+def _reg_rank(rank, world, port, ret):
+    """One rank of the image-sharded Path B exchange on CPU: the oracle evaluates a problem holding only this rank's images (same
+    points, same replicated state), the partial [H | b | sums] are summed with gloo, rank 0 compares with the full problem."""
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as orc
+    from dataset_pipeline_b200.synth import reg_scene
+    from dataset_pipeline_b200._lib import lib
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    sc = reg_scene.make_scene(num_images=4, width=160, height=120, fx=130.0, num_scales=2, base_radius=0.008)
+    area = 160 * 120 // 4
+    owner = [lib().b2_reg_image_owner(i, world) for i in range(4)]
+
+    def problem(images):
+        r = orc.Registration(orc.reg_default_params(max_initial_image_area_in_pixels=area, variable_residuals_weight=0.0))
+        w, h, K = sc["intr"]
+        r.add_intrinsics(w, h, K)
+        for i in images:
+            r.add_image(0, sc["images"][i], None, sc["poses_init"][i])
+        r.initialize()
+        for xyz, radius, nbr, colors in sc["scales"]:
+            r.add_point_scale(xyz, float(radius), nbr, colors)
+        r.set_splat_points(sc["scales"][0][0])
+        r.set_image_scale(0); r.create_observations(1)
+        return r
+
+    mine = [i for i in range(4) if owner[i] == rank]
+    H, b, sums, _ = problem(mine).accumulate()
+    # scatter the local system into the global variable layout [intrinsics(4) | 6 per image]
+    nv = 4 + 6 * 4
+    Hg = np.zeros((nv, nv)); bg = np.zeros(nv)
+    idx = list(range(4)) + [4 + 6 * i + k for i in mine for k in range(6)]
+    Hg[np.ix_(idx, idx)] = H; bg[idx] = b
+    buf = torch.from_numpy(np.concatenate([Hg.ravel(), bg, sums[:4]]))
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)        # the exchange of b2_reg_accumulate: [H | b | sums]
+    if rank == 0:
+        Hf, bf, sf, _ = problem(list(range(4))).accumulate()
+        tot = buf.numpy()
+        ret["H"] = float(np.abs(tot[:nv * nv].reshape(nv, nv) - Hf).max() / np.abs(Hf).max())
+        ret["b"] = float(np.abs(tot[nv * nv:nv * nv + nv] - bf).max() / np.abs(bf).max())
+        ret["sums"] = float(np.abs(tot[nv * nv + nv:] - sf[:4]).max() / np.abs(sf[:4]).max())
+        ret["owners"] = owner
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_registration_exchange_reproduces_single_rank_system(oracle):
+    """SURVEY §8e registration: images dealt round-robin, one sum-allreduce of [H | b | sums]. With fixed descriptors only (no
+    colour update: its per-point means are a second allreduce, covered on the GPU by tests/dist_reg_check.py) the sharded sums
+    equal the single-rank ones up to fp64 association."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 29611
+    ps = [ctx.Process(target=_reg_rank, args=(r, 2, port, ret)) for r in range(2)]
+    for p in ps:
+        p.start()
+    for p in ps:
+        p.join(240)
+        assert p.exitcode == 0
+    assert ret["owners"] == [0, 1, 0, 1]
+    assert ret["H"] < 1e-12 and ret["b"] < 1e-12 and ret["sums"] < 1e-12, dict(ret)

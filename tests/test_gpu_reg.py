@@ -265,3 +265,38 @@ def test_observations_with_mesh_occlusion(oracle, scene):
     # fewer observations than without occlusion geometry
     g2 = b2.Registration(); reg_scene.load_into(g2, scene, splats=False); g2.set_image_scale(1); g2.CreateObservationsForAllImages(1)
     assert n < sum(len(g2.observations(im, ps)[0]) for im in range(3) for ps in range(3))
+
+
+def test_camera_mask(oracle, scene):
+    """opt::Intrinsics::camera_mask (intrinsics.h:104, visibility_estimator.cc:492-501): a per-camera mask pyramid (OR-downsampled like
+    the image masks) removes observations in every image of that camera; observation sets stay bit-identical to the oracle's."""
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import registration
+    w, h, K = scene["intr"]
+    cmask = np.zeros((h, w), np.uint8); cmask[:, : w // 3] = 1; cmask[h - 60:, :] = 2
+    counts = {}
+    for with_mask in (False, True):
+        g = b2.Registration(registration.default_params()); o = oracle.Registration(oracle.reg_default_params())
+        for r in (g, o):
+            r.add_intrinsics(w, h, K)
+            if with_mask:
+                r.set_camera_mask(0, cmask)
+            for i in range(2):
+                r.add_image(0, scene["images"][i], None, scene["poses_init"][i])
+            r.initialize()
+            for xyz, radius, nbr, colors in scene["scales"]:
+                r.add_point_scale(xyz, float(radius), nbr, colors)
+            r.set_image_scale(0)
+        g.CreateObservationsForAllImages(1); o.create_observations(1)
+        counts[with_mask] = _obs_equal(g, o, 2, 3)
+        if with_mask:
+            for im in range(2):
+                _, x, y, s, _ = g.observations(im, 0)
+                lvl = (s.astype(np.int32) + 1)                       # the observation's pixel is at pyramid level int(scale)+1
+                fx = (x + 0.5) * (2.0 ** lvl) - 0.5                  # -> full-resolution pixel
+                assert fx.min() > w // 3 - 2 ** int(lvl.max()) - 1  # nothing inside the masked left third (up to one coarse pixel)
+    assert counts[True] < 0.8 * counts[False] and counts[True] > 1000
+    g = b2.Registration()
+    g.add_intrinsics(w, h, K)
+    with pytest.raises(Exception):
+        g.set_camera_mask(3, cmask)

@@ -1,7 +1,7 @@
 """GPU parity of Path B with the distorted camera models (THIN_PRISM, BENCHMARK = thin-prism fisheye) against the oracle.
-Thin-prism arithmetic has no transcendental function: the radius cut-off search, projection and derivatives must be bit-identical.
-The fisheye model calls atan(): the device rounds an fp64 atan, glibc's atanf may differ by 1 ulp, so those comparisons carry
-the tolerance stated in each test (projection 1e-6 relative; normal equations / states 1e-5 relative)."""
+The radius cut-off search, projection, derivatives, observation sets and Jacobians must be bit-identical (fp32, same evaluation
+order; the fisheye atan is the correctly rounded value on both sides, oracle/orc_camera.h); normal equations agree to the fp64
+summation order; states after LM steps within the north_star tolerance (1e-5 relative)."""
 import numpy as np
 import pytest
 
@@ -38,7 +38,7 @@ def test_cutoff_search_bit_exact(oracle):
 def test_projection_and_derivatives(oracle):
     _, R = _b2()
     nrm, pts = _grid_points()
-    for model, p, exact in [(oracle.CAM_PINHOLE, PINHOLE, True), (oracle.CAM_THIN_PRISM, BENCH, True), (oracle.CAM_BENCHMARK, BENCH, False)]:
+    for model, p, exact in [(oracle.CAM_PINHOLE, PINHOLE, True), (oracle.CAM_THIN_PRISM, BENCH, True), (oracle.CAM_BENCHMARK, BENCH, True)]:
         for op, x in [("project", nrm), ("d_by_world", pts), ("d_by_intrinsics", pts)]:
             got, _ = R.camera_eval(model, W, H, p, op, x)
             ref = oracle.cam_eval(model, W, H, p, op, x)
@@ -68,7 +68,7 @@ def _pair(oracle, model, **kw):
 @pytest.mark.parametrize("model", [14, 5])
 def test_observations_jacobians_normal_equations(oracle, model):
     g, o = _pair(oracle, model)
-    exact = model == 14
+    exact = True
     g.set_image_scale(0); o.set_image_scale(0)
     g.CreateObservationsForAllImages(1); o.create_observations(1)
     total = 0
@@ -144,8 +144,7 @@ def test_mixed_models_variable_layout(oracle):
     g.ColorOptimizerApply(); o.color_update()
     Hg, bg, _, cg = g.accumulate(); Ho, bo, _, co = o.accumulate()
     assert Hg.shape == Ho.shape == (28, 28)
-    assert np.abs(Hg - Ho).max() <= 1e-3 * np.abs(Ho).max() and np.abs(bg - bo).max() <= 1e-3 * np.abs(bo).max()
-    assert np.abs(Hg[:4, :4] - Ho[:4, :4]).max() <= 1e-9 * np.abs(Ho[:4, :4]).max()      # the pinhole image's own block: no atan involved
+    assert np.abs(Hg - Ho).max() <= 1e-9 * np.abs(Ho).max() and np.abs(bg - bo).max() <= 1e-9 * np.abs(bo).max()
     # the pinhole image's rows couple only to its own intrinsics block [0,4) and pose block [16,22)
     assert np.all(Hg[0:4, 4:16] == 0) and np.all(Hg[0:4, 22:28] == 0) and np.abs(Hg[0:4, 16:22]).max() > 0
     ip, _ = g.get_state()
