@@ -353,12 +353,13 @@ def run_b200(args):
     tp = os.path.join(ROOT, "profiles", "accumulate_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))      # ncu capture (profiles/): DRAM bytes over algorithmic bytes of that capture, applied to this launch
+            traffic = tj["dram_over_algorithmic"] * 48.0 * recs if "dram_over_algorithmic" in tj else tj.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     src = "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
     mean = lambda k: float(np.mean([s[k] for s in step_stats]))
-    roof_acc = {"bound": "hbm", "kernel": "k_accumulate<true> (K5, 48 B/correspondence/pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roof_acc = {"bound": "hbm", "kernel": "k_accumulate_tma<true> (K5, 48 B/correspondence/pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": src,
                 "algorithmic_bytes_per_launch": 48.0 * recs, "avg_launch_ms": acc_ms,
                 "share_of_step": mean("passes") * acc_ms / (ms / args.steps)}
@@ -369,7 +370,8 @@ def run_b200(args):
     tp = os.path.join(ROOT, "profiles", "search_traffic.json")
     if os.path.exists(tp):
         try:
-            nn_traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            nn_traffic = tj["dram_over_algorithmic"] * nn_bytes if "dram_over_algorithmic" in tj else tj.get("dram_bytes_per_launch")
         except Exception:
             nn_traffic = None
     roof_nn = {"bound": "hbm", "kernel": "k_nn_radius1 (K3, 12Q+8Qm+12T B/pair-direction; gather/L2-latency bound in practice)", "achieved": nn_ach,

@@ -153,6 +153,29 @@ __device__ __forceinline__ void cam_d_by_intrinsics(const Cam& c, float px, floa
   }
 }
 
+// The vertex stage of the reference's depth renderer (opengl/renderer.cc:42-131 with the distortion snippets :581-583 pinhole,
+// :630-653 benchmark): camera-space (x, y) <- z * distort(x/z, y/z), or (x, y) * 99 beyond the camera's own cut-off (never for the
+// benchmark camera: its radius_cutoff_squared() is +inf). Same operations as oracle/orc_mesh.h:vertex_distort.
+__device__ __forceinline__ void cam_vertex_distort(const Cam& c, float* x, float* y, float z) {
+  if (c.type == kCamPinhole) return;
+  float nx = *x / z, ny = *y / z;
+  float r2 = nx * nx + ny * ny;
+  if (r2 <= c.cutoff2) {
+    if (c.type == kCamBenchmark) {
+      const float r = sqrtf(r2);
+      if (r > 1e-6f) { const float theta_by_r = atan_pos(r) / r; nx = theta_by_r * nx; ny = theta_by_r * ny; }
+    }
+    const float k1 = c.d[0], k2 = c.d[1], p1 = c.d[2], p2 = c.d[3], k3 = c.d[4], k4 = c.d[5], sx1 = c.d[6], sy1 = c.d[7];
+    const float x2 = nx * nx, xy = nx * ny, y2 = ny * ny;
+    r2 = x2 + y2;
+    const float radial = 1.0f + r2 * (k1 + r2 * (k2 + r2 * (k3 + r2 * k4)));
+    *x = z * (radial * nx + 2.0f * p1 * xy + p2 * (r2 + 2.0f * x2) + sx1 * r2);
+    *y = z * (radial * ny + 2.0f * p2 * xy + p1 * (r2 + 2.0f * y2) + sy1 * r2);
+  } else {
+    *x = *x * 99.0f; *y = *y * 99.0f;
+  }
+}
+
 // x86 cvttss2si semantics (INT_MIN for non-finite / out-of-range), which is what the reference's `int ix = f` does on its hosts;
 // CUDA's cast would saturate / map NaN to 0 and let a point beyond the cut-off radius land on pixel 0.
 __device__ __forceinline__ int f2i_x86(float v) { return (v > -2147483904.f && v < 2147483648.f) ? (int)v : (int)0x80000000; }

@@ -52,6 +52,13 @@ struct b2_icp {
   bool lpt_order = true;                // K3 CTAs issued longest-first (B2_K3_ORDER=grid disables, for A/B runs)
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // K3 runs the pair-directions of an iteration round-robin over `nsearch` streams (the handle's + auxiliaries) so that one
+  // direction's tail overlaps the next direction's head; each stream has its own CUB scratch.
+  static constexpr int kMaxSearchStreams = 8;
+  int nsearch = 4;
+  cudaStream_t aux[kMaxSearchStreams - 1] = {};
+  cudaEvent_t fork_ev = nullptr, join_ev[kMaxSearchStreams - 1] = {};
+  DevBuf search_tmp[kMaxSearchStreams];
   std::vector<std::unique_ptr<Cloud>> movable;
   std::unique_ptr<Cloud> fixed;         // concatenated global-frame fixed cloud (may be null)
   std::vector<std::unique_ptr<Direction>> dirs;   // pool, reused across outer iterations
@@ -328,6 +335,13 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   unsigned long long* counts = h->pin_counts.as<unsigned long long>();
   B2_TRY(h->pin_misc.ensure(sizeof(unsigned int) * 2 * (size_t)std::max(1, h->ndirs)));
   unsigned int* tails = h->pin_misc.as<unsigned int>();
+  const bool diag = getenv("B2_K3_WORK") && *getenv("B2_K3_WORK");
+  const int nstreams = diag ? 1 : h->nsearch;
+  if (nstreams > 1) {
+    B2_CUDA(cudaEventRecord(h->fork_ev, h->stream));
+    for (int i = 0; i + 1 < nstreams; ++i) B2_CUDA(cudaStreamWaitEvent(h->aux[i], h->fork_ev, 0));
+  }
+  int issued = 0;
   for (int k = 0; k < h->ndirs; ++k) {
     Direction* d = h->dirs[k].get();
     d->count = 0;
@@ -336,10 +350,13 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
     const size_t ns = S->n;
     tails[2 * k] = tails[2 * k + 1] = 0;
     if (ns == 0 || T->n == 0) continue;
+    const int si = issued++ % nstreams;
+    cudaStream_t st = si == 0 ? h->stream : h->aux[si - 1];
+    DevBuf& cub_tmp = h->search_tmp[si];
     B2_TRY(d->match.ensure(ns * 4)); B2_TRY(d->d2.ensure(ns * 4)); B2_TRY(d->flags.ensure(ns * 4)); B2_TRY(d->offs.ensure(ns * 4));
     cudaEvent_t n0 = nullptr, n1 = nullptr;
     B2_CUDA(cudaEventCreate(&n0)); B2_CUDA(cudaEventCreate(&n1));
-    B2_CUDA(cudaEventRecord(n0, h->stream));
+    B2_CUDA(cudaEventRecord(n0, st));
     // longest-first launch order (k_cta_cost + a 10^4..10^5-element radix sort: a few tens of microseconds per direction)
     const unsigned int ncta = div_up(ns, 128);
     const unsigned int* order = nullptr;
@@ -347,42 +364,45 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
     if (h->lpt_order && !grid_order && ncta > 4u * (unsigned int)h->sms) {
       B2_TRY(d->cta_cost.ensure((size_t)ncta * 16));
       unsigned int* cc = d->cta_cost.as<unsigned int>();
-      k_cta_cost<<<div_up(ncta, 256), 256, 0, h->stream>>>(S->s_xyz.as<float4>(), ns, T->table.as<HashEntry>(), T->log2size, g, ncta, cc, cc + ncta);
+      k_cta_cost<<<div_up(ncta, 256), 256, 0, st>>>(S->s_xyz.as<float4>(), ns, T->table.as<HashEntry>(), T->log2size, g, ncta, cc, cc + ncta);
       size_t tmp2 = 0;
-      B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp2, cc, cc + 2 * (size_t)ncta, cc + ncta, cc + 3 * (size_t)ncta, (int)ncta, 0, 32, h->stream));
-      B2_TRY(h->cub_tmp.ensure(tmp2));
-      B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(h->cub_tmp.p, tmp2, cc, cc + 2 * (size_t)ncta, cc + ncta, cc + 3 * (size_t)ncta, (int)ncta, 0, 32, h->stream));
+      B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp2, cc, cc + 2 * (size_t)ncta, cc + ncta, cc + 3 * (size_t)ncta, (int)ncta, 0, 32, st));
+      B2_TRY(cub_tmp.ensure(tmp2));
+      B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(cub_tmp.p, tmp2, cc, cc + 2 * (size_t)ncta, cc + ncta, cc + 3 * (size_t)ncta, (int)ncta, 0, 32, st));
       order = cc + 3 * (size_t)ncta;
       h->launches += 2;
     }
     const char* work_path = getenv("B2_K3_WORK");   // diagnostic: per-query work counters of every search launch -> <path>.<k>.bin
     if (work_path && *work_path) {
       DevBuf wk; B2_TRY(wk.ensure(ns * 16));
-      k_nn_radius1<true><<<div_up(ns, 128), 128, 0, h->stream>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(),
+      k_nn_radius1<true><<<div_up(ns, 128), 128, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(),
                                                                  T->box2.as<Aabb>(), T->table.as<HashEntry>(), T->log2size, g, r2,
                                                                  d->match.as<int>(), d->d2.as<float>(), d->flags.as<unsigned int>(), wk.as<uint4>(), order);
       std::vector<uint4> hw(ns); std::vector<float4> hq(ns);
-      B2_CUDA(cudaMemcpyAsync(hw.data(), wk.p, ns * 16, cudaMemcpyDeviceToHost, h->stream));
-      B2_CUDA(cudaMemcpyAsync(hq.data(), S->s_xyz.p, ns * 16, cudaMemcpyDeviceToHost, h->stream));
-      B2_CUDA(cudaStreamSynchronize(h->stream));
+      B2_CUDA(cudaMemcpyAsync(hw.data(), wk.p, ns * 16, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(hq.data(), S->s_xyz.p, ns * 16, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
       const std::string fn = std::string(work_path) + "." + std::to_string(k) + ".bin";
       if (FILE* f = fopen(fn.c_str(), "wb")) { fwrite(hq.data(), 16, ns, f); fwrite(hw.data(), 16, ns, f); fclose(f); }
+      wk.release();
     } else {
-      k_nn_radius1<false><<<div_up(ns, 128), 128, 0, h->stream>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(),
+      k_nn_radius1<false><<<div_up(ns, 128), 128, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(),
                                                                   T->box2.as<Aabb>(), T->table.as<HashEntry>(), T->log2size, g, r2,
                                                                   d->match.as<int>(), d->d2.as<float>(), d->flags.as<unsigned int>(), nullptr, order);
     }
-    B2_CUDA(cudaEventRecord(n1, h->stream));
+    B2_CUDA(cudaEventRecord(n1, st));
     h->nn_events.emplace_back(n0, n1);
     h->stats.search_algorithmic_bytes += 12ull * ns + 12ull * T->n;
     ++h->launches;
     size_t tmp = 0;
-    B2_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d->flags.as<unsigned int>(), d->offs.as<unsigned int>(), (long long)ns, h->stream));
-    B2_TRY(h->cub_tmp.ensure(tmp));
-    B2_CUDA(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tmp, d->flags.as<unsigned int>(), d->offs.as<unsigned int>(), (long long)ns, h->stream));
-    B2_CUDA(cudaMemcpyAsync(&tails[2 * k], d->offs.as<unsigned int>() + (ns - 1), 4, cudaMemcpyDeviceToHost, h->stream));
-    B2_CUDA(cudaMemcpyAsync(&tails[2 * k + 1], d->flags.as<unsigned int>() + (ns - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d->flags.as<unsigned int>(), d->offs.as<unsigned int>(), (long long)ns, st));
+    B2_TRY(cub_tmp.ensure(tmp));
+    B2_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp, d->flags.as<unsigned int>(), d->offs.as<unsigned int>(), (long long)ns, st));
+    B2_CUDA(cudaMemcpyAsync(&tails[2 * k], d->offs.as<unsigned int>() + (ns - 1), 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(&tails[2 * k + 1], d->flags.as<unsigned int>() + (ns - 1), 4, cudaMemcpyDeviceToHost, st));
   }
+  if (nstreams > 1)
+    for (int i = 0; i + 1 < nstreams; ++i) { B2_CUDA(cudaEventRecord(h->join_ev[i], h->aux[i])); B2_CUDA(cudaStreamWaitEvent(h->stream, h->join_ev[i], 0)); }
   B2_CUDA(cudaStreamSynchronize(h->stream));
   B2_CUDA(cudaEventRecord(h->ev[2], h->stream));
   (void)counts;
@@ -517,7 +537,8 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   double acc = 0; for (auto& pr : h->acc_events) acc += elapsed(pr.first, pr.second);
   h->stats.ms_accum_kernel_avg = h->acc_events.empty() ? 0.f : (float)(acc / h->acc_events.size());
   double nn = 0; for (auto& pr : h->nn_events) nn += elapsed(pr.first, pr.second);
-  h->stats.ms_search_kernel_avg = h->nn_events.empty() ? 0.f : (float)(nn / h->nn_events.size());
+  // with several search streams the per-launch spans overlap, so the per-launch figure is the phase time over the launches
+  h->stats.ms_search_kernel_avg = h->nn_events.empty() ? 0.f : (float)((h->nsearch > 1 ? (double)h->stats.ms_search : nn) / h->nn_events.size());
   h->stats.search_launches = (int)h->nn_events.size();
   return B2_OK;
 }
@@ -580,6 +601,12 @@ int b2_icp_create(const b2_icp_config* cfg, b2_icp** out) {
   B2_TRY(select_device(c.device, &h->device, &h->sms));
   if (c.stream) { h->stream = (cudaStream_t)c.stream; }
   else { B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  if (const char* e = getenv("B2_K3_STREAMS")) h->nsearch = std::max(1, std::min((int)b2_icp::kMaxSearchStreams, atoi(e)));
+  for (int i = 0; i + 1 < h->nsearch; ++i) {
+    B2_CUDA(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
+    B2_CUDA(cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
+  }
+  B2_CUDA(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
   for (auto& e : h->ev) B2_CUDA(cudaEventCreate(&e));
   std::memset(&h->stats, 0, sizeof(h->stats));
   *out = h.release();
@@ -603,6 +630,9 @@ int b2_icp_destroy(b2_icp* h) {
   for (auto& pr : h->acc_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto& pr : h->nn_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < b2_icp::kMaxSearchStreams - 1; ++i) { if (h->aux[i]) cudaStreamDestroy(h->aux[i]); if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]); }
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  for (DevBuf& b : h->search_tmp) b.release();
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return B2_OK;

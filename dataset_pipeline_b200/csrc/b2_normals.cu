@@ -189,12 +189,12 @@ __device__ __forceinline__ void cross3(const float* a, const float* b, float* o)
 
 __global__ void __launch_bounds__(kKnnThreads)
 kn_knn_normals(const float4* __restrict__ s_xyz, size_t n, const Aabb* __restrict__ nodes, BvhLevels lv, int k, float vpx, float vpy, float vpz,
-               float4* __restrict__ out, int* __restrict__ out_idx, unsigned int* __restrict__ nan_count) {
+               float4* __restrict__ out, int* __restrict__ out_idx, unsigned int* __restrict__ nan_count, size_t q_begin, size_t q_end) {
   extern __shared__ unsigned char smem_raw[];
   float* sm_d2 = reinterpret_cast<float*>(smem_raw);
   unsigned int* sm_pos = reinterpret_cast<unsigned int*>(smem_raw + sizeof(float) * (size_t)k * kKnnThreads);
-  const size_t j = (size_t)blockIdx.x * kKnnThreads + threadIdx.x;
-  if (j >= n) return;
+  const size_t j = q_begin + (size_t)blockIdx.x * kKnnThreads + threadIdx.x;   // this rank's slice of the Morton-sorted queries
+  if (j >= q_end) return;
   const float4 q = s_xyz[j];
   KBest h{sm_d2 + threadIdx.x, sm_pos + threadIdx.x, k, 0, 0, INFINITY};
 
@@ -298,8 +298,11 @@ static inline unsigned int div_up_u(size_t a, size_t b) { return (unsigned int)(
 
 using namespace b2;
 
-extern "C" int b2_normals_estimate(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3], float* out_nxyz_curv,
-                                   int32_t* out_knn_idx, int* is_dense) {
+// Multi-GPU: every rank holds the whole cloud (search set) and answers a contiguous slice of the Morton-sorted
+// queries; the zero-initialised outputs are merged by one sum-allreduce (NaN normals survive the sum), so every rank returns
+// the full result. No exchange during the search itself.
+static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3], float* out_nxyz_curv,
+                        int32_t* out_knn_idx, int* is_dense, b2_comm* comm, int device) {
   if ((n && (!xyz || !out_nxyz_curv)) || !viewpoint) return set_error(B2_ERR_ARG, "null argument");
   if (stride_bytes < 12) return set_error(B2_ERR_ARG, "stride_bytes must be >= 12");
   if (k < 1 || k > 128) return set_error(B2_ERR_ARG, "k must be in [1,128]");
@@ -307,7 +310,11 @@ extern "C" int b2_normals_estimate(const float* xyz, size_t n, size_t stride_byt
   if (is_dense) *is_dense = 1;
   if (n == 0) return B2_OK;
   int dev = 0, sms = 0;
-  B2_TRY(select_device(-1, &dev, &sms));
+  B2_TRY(select_device(device, &dev, &sms));
+  int rank = 0, world = 1;
+  if (comm) B2_TRY(b2_comm_info(comm, &rank, &world));
+  if (world > 1 && out_knn_idx) return set_error(B2_ERR_ARG, "neighbour index output is single-GPU only");
+  const size_t q_begin = n * (size_t)rank / (size_t)world, q_end = n * (size_t)(rank + 1) / (size_t)world;
   cudaStream_t st; B2_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   DevBuf d_xyz, d_part, d_keys, d_keys2, d_idx, d_perm, d_sxyz, d_nodes, d_tmp, d_out, d_oidx, d_nan;
   PinnedBuf p_part;
@@ -352,12 +359,19 @@ extern "C" int b2_normals_estimate(const float* xyz, size_t n, size_t stride_byt
     if (out_knn_idx) B2_TRY(d_oidx.ensure(n * (size_t)k * 4));
     B2_TRY(d_nan.ensure(4));
     B2_CUDA(cudaMemsetAsync(d_nan.p, 0, 4, st));
+    if (world > 1) B2_CUDA(cudaMemsetAsync(d_out.p, 0, n * 16, st));
     const size_t smem = (size_t)k * kKnnThreads * 8;
     B2_CUDA(cudaFuncSetAttribute(kn_knn_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kn_knn_normals<<<div_up_u(n, kKnnThreads), kKnnThreads, smem, st>>>(d_sxyz.as<float4>(), n, d_nodes.as<Aabb>(), lv, k, viewpoint[0], viewpoint[1],
-                                                                       viewpoint[2], d_out.as<float4>(), out_knn_idx ? d_oidx.as<int>() : nullptr,
-                                                                       d_nan.as<unsigned int>());
+    if (q_end > q_begin)
+      kn_knn_normals<<<div_up_u(q_end - q_begin, kKnnThreads), kKnnThreads, smem, st>>>(d_sxyz.as<float4>(), n, d_nodes.as<Aabb>(), lv, k, viewpoint[0],
+                                                                                        viewpoint[1], viewpoint[2], d_out.as<float4>(),
+                                                                                        out_knn_idx ? d_oidx.as<int>() : nullptr,
+                                                                                        d_nan.as<unsigned int>(), q_begin, q_end);
     B2_CUDA(cudaGetLastError());
+    if (world > 1) {
+      B2_TRY(b2_comm_allreduce(comm, d_out.p, n * 4, B2_F32, (void*)st));
+      B2_TRY(b2_comm_allreduce(comm, d_nan.p, 1, B2_I32, (void*)st));
+    }
     unsigned int nans = 0;
     B2_CUDA(cudaMemcpyAsync(out_nxyz_curv, d_out.p, n * 16, cudaMemcpyDeviceToHost, st));
     if (out_knn_idx) B2_CUDA(cudaMemcpyAsync(out_knn_idx, d_oidx.p, n * (size_t)k * 4, cudaMemcpyDeviceToHost, st));
@@ -371,4 +385,15 @@ extern "C" int b2_normals_estimate(const float* xyz, size_t n, size_t stride_byt
   p_part.release();
   cudaStreamDestroy(st);
   return rc;
+}
+
+extern "C" int b2_normals_estimate(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3], float* out_nxyz_curv,
+                                   int32_t* out_knn_idx, int* is_dense) {
+  return normals_impl(xyz, n, stride_bytes, k, viewpoint, out_nxyz_curv, out_knn_idx, is_dense, nullptr, -1);
+}
+
+extern "C" int b2_normals_estimate_dist(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3], b2_comm* comm, int device,
+                                        float* out_nxyz_curv, int* is_dense) {
+  if (!comm) return set_error(B2_ERR_ARG, "null communicator");
+  return normals_impl(xyz, n, stride_bytes, k, viewpoint, out_nxyz_curv, nullptr, is_dense, comm, device);
 }

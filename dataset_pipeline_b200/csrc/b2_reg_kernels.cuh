@@ -129,10 +129,14 @@ static constexpr int kBigTriPixels = 4096;
 struct ClippedTri { float x[4], y[4], z[4]; int n; };   // camera-space polygon after near clipping (n = 0, 3 or 4)
 
 __device__ __forceinline__ ClippedTri clip_triangle(const float* __restrict__ v, const unsigned int* __restrict__ f, size_t fi, const Pose3& P,
-                                                    float min_depth) {
+                                                    const Cam& cam, float min_depth) {
   float px[3], py[3], pz[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { const size_t vi = f[3 * fi + k]; rigid(P, v[3 * vi], v[3 * vi + 1], v[3 * vi + 2], &px[k], &py[k], &pz[k]); }
+  for (int k = 0; k < 3; ++k) {
+    const size_t vi = f[3 * fi + k];
+    rigid(P, v[3 * vi], v[3 * vi + 1], v[3 * vi + 2], &px[k], &py[k], &pz[k]);
+    cam_vertex_distort(cam, &px[k], &py[k], pz[k]);      // the renderer's vertex stage; clipping follows it, as in GL
+  }
   ClippedTri c; c.n = 0;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(128) kr_raster_small(const float* __restrict__
                                                        unsigned int* __restrict__ big_list, unsigned int* __restrict__ big_count) {
   const size_t fi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (fi >= nf) return;
-  const ClippedTri t = clip_triangle(v, f, fi, P, min_depth);
+  const ClippedTri t = clip_triangle(v, f, fi, P, cam, min_depth);
   if (t.n == 0) return;
   const TriSetup s0 = setup_triangle(cam, t, 0, 1, 2);
   TriSetup s1; s1.valid = false;
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(256) kr_raster_big(const float* __restrict__ v
                                                      float max_depth, unsigned int* __restrict__ depth_bits, const unsigned int* __restrict__ big_list,
                                                      const unsigned int* __restrict__ big_count) {
   for (unsigned int b = blockIdx.x; b < *big_count; b += gridDim.x) {
-    const ClippedTri t = clip_triangle(v, f, big_list[b], P, min_depth);
+    const ClippedTri t = clip_triangle(v, f, big_list[b], P, cam, min_depth);
     if (t.n == 0) continue;
     const TriSetup s0 = setup_triangle(cam, t, 0, 1, 2);
     if (s0.valid) raster_pixels(cam, s0, max_depth, depth_bits, threadIdx.x, blockDim.x);
@@ -255,13 +259,11 @@ __global__ void __launch_bounds__(128) kr_mask_edges(const MeshEdgeDev* __restri
     const float px = ax + factor * dx, py = ay + factor * dy, pz = az + factor * dz;
     if (!(pz > 0)) continue;
     const float nx = px / pz, ny = py / pz;
-    const float ux = cam.fx * nx + cam.cx, uy = cam.fy * ny + cam.cy;
-    const int ix = (int)(ux + 0.5f), iy = (int)(uy + 0.5f);
+    float ux, uy; cam_project(cam, nx, ny, &ux, &uy);
+    const int ix = f2i_x86(ux + 0.5f), iy = f2i_x86(uy + 0.5f);
     if (!(ux + 0.5f >= 0 && uy + 0.5f >= 0 && ix >= 0 && iy >= 0 && ix < cam.w && iy < cam.h && in[(size_t)iy * cam.w + ix] + 0.05f >= pz)) continue;
-    const float z_inv = 1.f / pz;
-    const float d0 = cam.fx * (1.f * z_inv), d1 = cam.fx * (0.f * z_inv), d2 = cam.fx * (-1.f * nx * z_inv);
-    const float d3 = cam.fy * (0.f * z_inv), d4 = cam.fy * (1.f * z_inv), d5 = cam.fy * (-1.f * ny * z_inv);
-    const float rx = sqrtf(sum3p(d0 * d0, d1 * d1, d2 * d2)) * splat_radius, ry = sqrtf(sum3p(d3 * d3, d4 * d4, d5 * d5)) * splat_radius;
+    float dd[6]; cam_d_by_world(cam, px, py, pz, dd);
+    const float rx = sqrtf(sum3p(dd[0] * dd[0], dd[1] * dd[1], dd[2] * dd[2])) * splat_radius, ry = sqrtf(sum3p(dd[3] * dd[3], dd[4] * dd[4], dd[5] * dd[5])) * splat_radius;
     const int min_x = max(0, (int)(ix - rx + 0.5)), min_y = max(0, (int)(iy - ry + 0.5));
     const int end_x = min(cam.w, (int)(ix + rx + 1.5)), end_y = min(cam.h, (int)(iy + ry + 1.5));
     for (int y = min_y; y < end_y; ++y) for (int x = min_x; x < end_x; ++x) {
@@ -551,10 +553,14 @@ __global__ void __launch_bounds__(128) kr_accumulate(ResidualArgs A, const float
   if (threadIdx.x < kAccB) partials[(size_t)blockIdx.x * kAccB + threadIdx.x] = out;
 }
 
-// K12w: the same accumulation for camera models with more intrinsics (NI = 12: (12+6)^2 local system = 171 upper entries + 18 of b),
-// which no longer fits one thread's registers. One WARP per observation: lane l < NI+6 holds Jacobian column l of the centre /
-// neighbour rows, the 189 accumulators are spread over the lanes (6 each) and every (r, c) product fetches its two factors with
-// shuffles. Same fp32 products and fp64 accumulation as the per-thread kernel; per-block output [NH | NV | 4 sums].
+// K12w: the same accumulation for local systems that no longer fit one thread's registers (12 intrinsics: (12+6)^2 = 171 upper
+// entries + 18 of b; with rig extrinsics up to (12+6+6)^2 = 300 + 24). A warp takes 32 observations at a time:
+//   1. lane-parallel: lane l does observation l's scalar work (neighbour slots, descriptor residuals, robust weights, residual sums);
+//   2. serial over the 32 observations: lane l < NV holds column l of the centre row and of the K neighbour rows (all K+1 row loads
+//      issued together), the NH + NV accumulators are spread over the lanes (<= 11 each) and every (r, c) product fetches its two
+//      factors with shuffles.
+// Same fp32 products and fp64 accumulation as the per-thread kernel; per-block output [NH | NV | 4 sums]. The kernel is bound by
+// the fp32->fp64 conversion of every product (quarter-rate pipe) and by the shuffles, not by memory.
 // With RIG (dependent rig image) the local system has 6 more columns, ordered [intrinsics | rig extrinsics | reference pose] like the
 // global variable vector, so that every upper-triangle product has the factor order of AccumulateOnHAndB (:1262-1283).
 template <int NI, bool RIG>
@@ -573,50 +579,80 @@ __global__ void __launch_bounds__(128) kr_accumulate_wide(ResidualArgs A, const 
   double acc[SL];
 #pragma unroll
   for (int s = 0; s < SL; ++s) acc[s] = 0.0;
-  double sums[4] = {0.0, 0.0, 0.0, 0.0};
+  double sums[4] = {0.0, 0.0, 0.0, 0.0};   // per lane: this lane's observations
+  // Jacobian row `slot`, column `lane` of the local system
+  auto row = [&](size_t slot) -> float {
+    if (lane < NI) return jK[(size_t)NI * slot + lane];
+    if (RIG && lane < NI + NR) return jR[6 * slot + (lane - NI)];
+    if (lane < NV) return jP[6 * slot + (lane - NI - NR)];
+    return 0.f;
+  };
   const size_t nw = (size_t)gridDim.x * 4;
-  for (size_t i = (size_t)blockIdx.x * 4 + warp; i < A.count; i += nw) {
-    if (!A.nb[i]) continue;
-    const size_t p = A.idx[i];
-    const float Ic = A.inten[i];
-    int nj = 0; float In = 0.f;
-    if (lane < A.K) { nj = A.slot[A.nbr[p * A.K + lane]]; In = A.inten[nj]; }
-    float jc = 0.f;
-    if (lane < NI) jc = jK[(size_t)NI * i + lane];
-    else if (RIG && lane < NI + NR) jc = jR[6 * i + (lane - NI)];
-    else if (lane < NV) jc = jP[6 * i + (lane - NI - NR)];
+  for (size_t base = ((size_t)blockIdx.x * 4 + warp) * 32; base < A.count; base += nw * 32) {
+    // ---- 1. lane-parallel scalar work of observation base + lane ----
+    const size_t i = base + lane;
+    int nj[kMaxNbr]; float cf[kMaxNbr], cv[kMaxNbr];
+    float wf = 0.f, wv = 0.f;
 #pragma unroll
-    for (int type = 0; type < 2; ++type) {
-      const float sw = type == 0 ? A.fixed_w : A.var_w;
-      if (!(sw > 0)) continue;
-      if (type == 1 && A.obs_count[p] < 2) continue;
-      const float* desc = type == 0 ? A.fixed_desc : A.var_desc;
-      float cmp = 0.f;
-      if (lane < A.K) cmp = (In - Ic) - desc[p * A.K + lane];
-      float pr = 0.f;
-      for (int k = 0; k < A.K; ++k) { const float c = __shfl_sync(0xffffffffu, cmp, k); pr += c * c; }
-      pr = sqrtf(pr);
-      sums[2 * type] += (double)robust_residual(A.robust, pr);
-      sums[2 * type + 1] += 1.0;
-      const float w = sw * robust_weight(A.robust, pr);
-      if (w != 0) {
-        for (int k = 0; k < A.K; ++k) {
-          const int njk = __shfl_sync(0xffffffffu, nj, k);
-          const float wr = w * __shfl_sync(0xffffffffu, cmp, k);
-          float dj = 0.f;
-          if (lane < NI) dj = jK[(size_t)NI * njk + lane] - jc;
-          else if (RIG && lane < NI + NR) dj = jR[(size_t)6 * njk + (lane - NI)] - jc;
-          else if (lane < NV) dj = jP[(size_t)6 * njk + (lane - NI - NR)] - jc;
+    for (int k = 0; k < kMaxNbr; ++k) { nj[k] = 0; cf[k] = 0.f; cv[k] = 0.f; }
+    if (i < A.count && A.nb[i]) {
+      const size_t p = A.idx[i];
+      const float Ic = A.inten[i];
+      float In[kMaxNbr];
 #pragma unroll
-          for (int s = 0; s < SL; ++s) {
-            const float a = __shfl_sync(0xffffffffu, dj, max(er[s], 0)), b = __shfl_sync(0xffffffffu, dj, ec[s]);
-            if (er[s] >= 0) acc[s] += (double)((w * a) * b);
-            else if (er[s] == -1) acc[s] += (double)(wr * b);
+      for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) { nj[k] = A.slot[A.nbr[p * A.K + k]]; In[k] = A.inten[nj[k]]; }
+      if (A.fixed_w > 0) {
+        float pr = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) { const float c = (In[k] - Ic) - A.fixed_desc[p * A.K + k]; cf[k] = c; pr += c * c; }
+        pr = sqrtf(pr);
+        sums[0] += (double)robust_residual(A.robust, pr); sums[1] += 1.0;
+        wf = A.fixed_w * robust_weight(A.robust, pr);
+      }
+      if (A.var_w > 0 && A.obs_count[p] >= 2) {
+        float pr = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) { const float c = (In[k] - Ic) - A.var_desc[p * A.K + k]; cv[k] = c; pr += c * c; }
+        pr = sqrtf(pr);
+        sums[2] += (double)robust_residual(A.robust, pr); sums[3] += 1.0;
+        wv = A.var_w * robust_weight(A.robust, pr);
+      }
+    }
+    // ---- 2. the outer products, one observation at a time, all lanes cooperating ----
+    unsigned int todo = __ballot_sync(0xffffffffu, wf != 0 || wv != 0);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const float jc = row(base + src);
+      float dj[kMaxNbr];
+#pragma unroll
+      for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) dj[k] = row((size_t)__shfl_sync(0xffffffffu, nj[k], src));
+#pragma unroll
+      for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) dj[k] -= jc;
+      // the two factors of an entry are the same for the fixed and the variable descriptor residual: fetch once, use twice
+      const float w0 = __shfl_sync(0xffffffffu, wf, src), w1 = __shfl_sync(0xffffffffu, wv, src);
+#pragma unroll
+      for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) {
+        const float wr0 = w0 * __shfl_sync(0xffffffffu, cf[k], src), wr1 = w1 * __shfl_sync(0xffffffffu, cv[k], src);
+#pragma unroll
+        for (int s = 0; s < SL; ++s) {
+          const float a = __shfl_sync(0xffffffffu, dj[k], max(er[s], 0)), b = __shfl_sync(0xffffffffu, dj[k], ec[s]);
+          if (er[s] >= 0) {
+            if (w0 != 0) acc[s] += (double)((w0 * a) * b);
+            if (w1 != 0) acc[s] += (double)((w1 * a) * b);
+          } else if (er[s] == -1) {
+            if (w0 != 0) acc[s] += (double)(wr0 * b);
+            if (w1 != 0) acc[s] += (double)(wr1 * b);
           }
         }
       }
     }
   }
+  // residual sums: lanes -> warp (fixed shuffle tree), then the four warps in order
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sums[k] += __shfl_xor_sync(0xffffffffu, sums[k], o);
   __shared__ double sm[4][SL * 32 + 4];
 #pragma unroll
   for (int s = 0; s < SL; ++s) sm[warp][s * 32 + lane] = acc[s];

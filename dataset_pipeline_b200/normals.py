@@ -44,6 +44,19 @@ class NormalEstimationTwoPassOMP:
         return (out, idx) if return_indices else out
 
 
+def estimate_normals_dist(xyz, k, viewpoint, comm, device=-1):
+    """Multi-GPU variant (one process per GPU): every rank passes the whole cloud and gets the whole (n,4) result; the ranks share
+    the queries and merge with one allreduce over `comm` (dataset_pipeline_b200.icp.Comm)."""
+    x = np.ascontiguousarray(xyz, np.float32); vp = np.asarray(viewpoint, np.float32)
+    out = np.zeros((x.shape[0], 4), np.float32); dense = C.c_int32(1)
+    fp = C.POINTER(C.c_float)
+    L = _lib.lib()
+    L.b2_normals_estimate_dist.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, fp, C.c_void_p, C.c_int, fp, C.POINTER(C.c_int32)]
+    _lib.check(L.b2_normals_estimate_dist(x.ctypes.data, x.shape[0], 12, int(k), vp.ctypes.data_as(fp), comm._c, device, out.ctypes.data_as(fp),
+                                          C.byref(dense)))
+    return out, bool(dense.value)
+
+
 def estimate_normals(xyz, k, viewpoint=(0.0, 0.0, 0.0), return_indices=False):
     ne = NormalEstimationTwoPassOMP()
     ne.setInputCloud(xyz); ne.setKSearch(k); ne.setViewPoint(*viewpoint)

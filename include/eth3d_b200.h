@@ -152,6 +152,10 @@ int b2_find_correspondences(const float* src_xyz, size_t n_src, const float* tgt
  * ------------------------------------------------------------------------------------------------------------------ */
 int b2_normals_estimate(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3],
                         float* out_nxyz_curv, int32_t* out_knn_idx, int* is_dense);
+/* The same over several GPUs (one process per GPU): every rank passes the whole cloud and gets the whole result; rank r
+ * answers the r-th slice of the Morton-sorted queries and one sum-allreduce over `comm` merges the outputs. */
+int b2_normals_estimate_dist(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3], b2_comm* comm, int device,
+                             float* out_nxyz_curv, int* is_dense);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Path B — dense photometric image<->scan alignment (tool ImageRegistrator).

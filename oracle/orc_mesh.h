@@ -102,7 +102,32 @@ static void build_mesh_edges(OccMesh* m) {
   }
 }
 
-struct RasterCam { int w, h; float fx, fy, cx, cy; };
+typedef Camera RasterCam;   // orc_camera.h (included before this header)
+
+// What the reference's vertex shader does to a camera-space vertex before the pinhole projection matrix (opengl/renderer.cc:42-131,
+// distortion snippets :581-583 pinhole, :630-653 benchmark): (x, y) <- z * distort(x/z, y/z); beyond the camera's own cut-off
+// (never for the benchmark camera, whose radius_cutoff_squared() is +inf, :668-680) the vertex is pushed far out (x, y) *= 99.
+// The thin-prism model has no renderer program of its own in the reference (its objects report Type::kBenchmark,
+// camera_thin_prism.cc:37,47); here it gets the same snippet without the fisheye step.
+static inline void vertex_distort(const Camera& c, V3f* p) {
+  if (c.type == kCamPinhole) return;
+  float nx = p->x / p->z, ny = p->y / p->z;
+  float r2 = nx * nx + ny * ny;
+  if (r2 <= c.cutoff2) {
+    if (c.type == kCamBenchmark) {
+      const float r = std::sqrt(r2);
+      if (r > 1e-6f) { const float theta_by_r = atan_r1(r) / r; nx = theta_by_r * nx; ny = theta_by_r * ny; }
+    }
+    const float k1 = c.d[0], k2 = c.d[1], p1 = c.d[2], p2 = c.d[3], k3 = c.d[4], k4 = c.d[5], sx1 = c.d[6], sy1 = c.d[7];
+    const float x2 = nx * nx, xy = nx * ny, y2 = ny * ny;
+    r2 = x2 + y2;
+    const float radial = 1.0f + r2 * (k1 + r2 * (k2 + r2 * (k3 + r2 * k4)));
+    p->x = p->z * (radial * nx + 2.0f * p1 * xy + p2 * (r2 + 2.0f * x2) + sx1 * r2);
+    p->y = p->z * (radial * ny + 2.0f * p2 * xy + p1 * (r2 + 2.0f * y2) + sy1 * r2);
+  } else {
+    p->x = p->x * 99.0f; p->y = p->y * 99.0f;
+  }
+}
 
 // One clipped, camera-space triangle (all z >= zn > 0) into the min-depth buffer (inf = empty).
 static inline void raster_triangle(const RasterCam& c, const V3f& a, const V3f& b, const V3f& cc, float max_depth, float* depth) {
@@ -144,8 +169,8 @@ static void raster_mesh(const OccMesh& m, const RasterCam& c, const float R[9], 
   const M3f& M = *reinterpret_cast<const M3f*>(R);
   for (size_t fi = 0; fi < m.f.size() / 3; ++fi) {
     V3f p[3];
-    for (int k = 0; k < 3; ++k) { const V3f r = mul(M, v3(&m.v[3 * m.f[3 * fi + k]])); p[k] = V3f{r.x + t.x, r.y + t.y, r.z + t.z}; }
-    // clip against z >= min_depth
+    for (int k = 0; k < 3; ++k) { const V3f r = mul(M, v3(&m.v[3 * m.f[3 * fi + k]])); p[k] = V3f{r.x + t.x, r.y + t.y, r.z + t.z}; vertex_distort(c, &p[k]); }
+    // clip against z >= min_depth (after the vertex stage, as GL clips)
     V3f poly[4]; int np = 0;
     for (int k = 0; k < 3; ++k) {
       const V3f& A = p[k]; const V3f& B = p[(k + 1) % 3];
@@ -188,13 +213,11 @@ static void mask_boundaries(const OccMesh& m, const RasterCam& c, const float R[
       const V3f p{a.x + factor * delta.x, a.y + factor * delta.y, a.z + factor * delta.z};
       if (!(p.z > 0)) continue;
       const float nx = p.x / p.z, ny = p.y / p.z;
-      const float px = c.fx * nx + c.cx, py = c.fy * ny + c.cy;
-      const int ix = px + 0.5f, iy = py + 0.5f;
+      float px, py; c.project(nx, ny, &px, &py);                      // camera.NormalizedToImage (occlusion_geometry.cc:377)
+      const int ix = f2i(px + 0.5f), iy = f2i(py + 0.5f);
       if (!(px + 0.5f >= 0 && py + 0.5f >= 0 && ix >= 0 && iy >= 0 && ix < c.w && iy < c.h && in[(size_t)iy * c.w + ix] + kOcclusionDepthThreshold >= p.z)) continue;
-      const float z_inv = 1.f / p.z;
-      const float d0 = c.fx * (1.f * z_inv), d1 = c.fx * (0.f * z_inv), d2 = c.fx * (-1.f * nx * z_inv);
-      const float d3 = c.fy * (0.f * z_inv), d4 = c.fy * (1.f * z_inv), d5 = c.fy * (-1.f * ny * z_inv);
-      const float rx = std::sqrt(sum3(d0 * d0, d1 * d1, d2 * d2)) * splat_radius, ry = std::sqrt(sum3(d3 * d3, d4 * d4, d5 * d5)) * splat_radius;
+      float dd[6]; c.d_by_world(p, dd);                                // camera.ImageDerivativeByWorld (:386)
+      const float rx = std::sqrt(sum3(dd[0] * dd[0], dd[1] * dd[1], dd[2] * dd[2])) * splat_radius, ry = std::sqrt(sum3(dd[3] * dd[3], dd[4] * dd[4], dd[5] * dd[5])) * splat_radius;
       const int min_x = std::max(0, int(ix - rx + 0.5)), min_y = std::max(0, int(iy - ry + 0.5));
       const int end_x = std::min(c.w, int(ix + rx + 1.5)), end_y = std::min(c.h, int(iy + ry + 1.5));
       for (int y = min_y; y < end_y; ++y) for (int x = min_x; x < end_x; ++x) {

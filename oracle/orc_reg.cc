@@ -179,7 +179,7 @@ static ImgF render_depth(const orc_reg* h, const Intrinsics& intr, const Image& 
   float R[9]; quat_to_matrix(im.image_T_global.q, R);
   if (!h->has_splats && h->has_mesh) {
     // mesh path (occlusion_geometry.cc:211-270): depth pass + MaskOutOcclusionBoundaries; see orc_mesh.h for the rasteriser definition
-    const RasterCam rc{cam.w, cam.h, cam.fx, cam.fy, cam.cx, cam.cy};
+    const RasterCam& rc = cam;
     std::vector<float> raw;
     raster_mesh(h->mesh, rc, R, im.image_T_global.t, h->prm.min_occlusion_depth, h->prm.max_occlusion_depth, &raw);
     // image position = global_T_image.translation() = inv(q) * (-t)   (sophus se3.hpp:208-211)

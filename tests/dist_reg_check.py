@@ -24,6 +24,14 @@ def main():
     dist.broadcast_object_list(ids, 0)
     comm = Comm(rank, world, ids[0], device=local)
 
+    # ---- sharded normals (b2_normals_estimate_dist): every rank gets the full result, identical to the single-GPU call ----
+    from dataset_pipeline_b200.normals import estimate_normals, estimate_normals_dist
+    rng = np.random.default_rng(4)
+    pts = np.concatenate([rng.uniform(-1, 1, (60000, 3)) * [1, 1, 0.02], [[50.0, 50.0, 50.0]]]).astype(np.float32)   # + one isolated point
+    nd, dense_d = estimate_normals_dist(pts, 12, (0.0, 0.0, 5.0), comm, device=local)
+    ns = estimate_normals(pts, 12, (0.0, 0.0, 5.0))
+    assert np.array_equal(np.nan_to_num(nd, nan=7.0), np.nan_to_num(ns, nan=7.0)), "sharded normals differ from the single-GPU result"
+
     model = int(os.environ.get("B2_TEST_CAMERA", "5"))
     sc = reg_scene.make_rig_scene(num_sets=3, camera_model=model)          # 6 images: ranks own 3 each; rig sets span both ranks
     area = 320 * 240 // 4

@@ -158,3 +158,48 @@ def test_rejects_unknown_model_and_wrong_count():
         g.add_intrinsics(64, 48, [50, 50, 32, 24, 0.1], camera_model=0 + 8)      # RADIAL: not supported
     with pytest.raises(Exception):
         g.add_intrinsics(64, 48, [50, 50, 32, 24], camera_model=5)                # BENCHMARK needs 12
+
+
+@pytest.mark.parametrize("model", [14, 5])
+def test_mesh_occlusion_with_distorted_cameras(oracle, model):
+    """K8/K9 with the renderer's vertex-stage distortion (opengl/renderer.cc:630-653): depth maps (incl. boundary masking) and the
+    observation sets behind them stay bit-identical to the oracle's software rasteriser. This is the configuration of the real ETH3D
+    pipeline (THIN_PRISM_FISHEYE images + mesh occlusion geometry)."""
+    b2, R = _b2()
+    from dataset_pipeline_b200.synth import reg_scene
+    from test_gpu_reg import _grid_mesh, _box_mesh
+    sc = reg_scene.make_scene(num_images=2, width=320, height=240, fx=260.0, camera_model=model, num_scales=3, base_radius=0.004)
+    Vp, Fp = _grid_mesh(-1.3, 1.3, -1.0, 1.0, 0.0, 30)                 # the textured plane itself
+    Vb, Fb = _box_mesh((0.2, 0.1, 0.5), 0.15)                          # a box above it: silhouettes + hidden points
+    Vg = np.array([[-4, -3, 1.9], [4, -3, 1.9], [4, 3, 2.3], [-4, 3, 2.3]], np.float32); Fg = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)   # passes behind the cameras' near plane
+    V = np.concatenate([Vp, Vb, Vg]); F = np.concatenate([Fp, Fb + len(Vp), Fg + len(Vp) + len(Vb)])
+    area = 320 * 240 // 4
+    for mask_flag in (1, 0):
+        kw = dict(max_initial_image_area_in_pixels=area, mask_occlusion_boundaries=mask_flag)
+        g = b2.Registration(R.default_params(**kw)); o = oracle.Registration(oracle.reg_default_params(**kw))
+        for r in (g, o):
+            reg_scene.load_into(r, sc, splats=False)
+            r.set_mesh(V, F); r.set_image_scale(0)
+        for im in range(2):
+            dg, sg = g.render_depth(im); do, so = o.render_depth(im)
+            assert sg == so and np.array_equal(dg, do), (model, mask_flag, im, int((dg != do).sum()))
+            assert (do > 0).mean() > 0.5
+            if mask_flag:
+                assert (do == -1).sum() > 200
+        g.CreateObservationsForAllImages(1); o.create_observations(1)
+        n = 0
+        for im in range(2):
+            for ps in range(3):
+                go, oo = g.observations(im, ps), o.observations(im, ps)
+                assert all(np.array_equal(a, b) for a, b in zip(go, oo)), (model, mask_flag, im, ps)
+                n += len(oo[0])
+        assert n > 10000
+    # the distortion matters: a pinhole camera with the same f, c sees a different depth map
+    gp = b2.Registration(R.default_params(max_initial_image_area_in_pixels=area, mask_occlusion_boundaries=0))
+    gp.add_intrinsics(320, 240, sc["intr"][2][:4]); gp.add_image(0, sc["images"][0], None, sc["poses_init"][0]); gp.initialize()
+    gp.set_mesh(V, F); gp.set_image_scale(0)
+    dp, _ = gp.render_depth(0)
+    g = b2.Registration(R.default_params(max_initial_image_area_in_pixels=area, mask_occlusion_boundaries=0))
+    reg_scene.load_into(g, sc, splats=False); g.set_mesh(V, F); g.set_image_scale(0)
+    dd, _ = g.render_depth(0)
+    assert dd.shape == dp.shape and (np.abs(dd - dp) > 0.05).mean() > 0.01
