@@ -6,5 +6,5 @@ the thin host-side mirror of the reference's class interfaces.
 """
 from . import _lib  # noqa: F401
 from .icp import Comm, PointToPlaneICP, find_correspondences  # noqa: F401
-from .normals import NormalEstimationTwoPassOMP, estimate_normals  # noqa: F401
+from .normals import NormalEstimationTwoPassOMP, estimate_normals, estimate_normals_radius  # noqa: F401
 from .registration import Registration  # noqa: F401

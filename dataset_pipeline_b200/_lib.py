@@ -72,6 +72,7 @@ EXPORTS = [
     "b2_last_error",
     "b2_normals_estimate",
     "b2_normals_estimate_dist",
+    "b2_normals_estimate_radius",
     "b2_reg_accumulate",
     "b2_reg_add_image",
     "b2_reg_add_intrinsics",

@@ -12,6 +12,8 @@
 // (squared distance, original index) ascending; the AABB lower bound is evaluated with the same fp32 operations as the
 // point distance, so pruning can never drop a neighbour (rounding is monotone).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_segmented_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -187,6 +189,53 @@ __device__ __forceinline__ void cross3(const float* a, const float* b, float* o)
   o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
 }
 
+// Normal + curvature from a neighbour list given in the reference's order (pos(a) = sorted position of neighbour a, cnt >= 3):
+// two-pass mean / covariance in fp32 (two_pass_centroid.hpp:164-258), pcl::eigen33 smallest eigenpair, viewpoint flip.
+template <typename PosFn>
+__device__ __forceinline__ float4 normal_from_list(const float4* __restrict__ s_xyz, PosFn pos, int cnt, const float4& q, float vpx, float vpy, float vpz) {
+  // two-pass mean / covariance, fp32, sequential in neighbour order, no contraction (two_pass_centroid.hpp:164-258)
+  float a6 = 0.f, a7 = 0.f, a8 = 0.f;
+  for (int a = 0; a < cnt; ++a) { const float4 p = __ldg(&s_xyz[pos(a)]); a6 = fadd(a6, p.x); a7 = fadd(a7, p.y); a8 = fadd(a8, p.z); }
+  const float fn = (float)cnt;
+  a6 = a6 / fn; a7 = a7 / fn; a8 = a8 / fn;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
+  for (int a = 0; a < cnt; ++a) {
+    const float4 p = __ldg(&s_xyz[pos(a)]);
+    const float dx = fsub(p.x, a6), dy = fsub(p.y, a7), dz = fsub(p.z, a8);
+    a0 = fadd(a0, fmul(dx, dx)); a1 = fadd(a1, fmul(dx, dy)); a2 = fadd(a2, fmul(dx, dz));
+    a3 = fadd(a3, fmul(dy, dy)); a4 = fadd(a4, fmul(dy, dz)); a5 = fadd(a5, fmul(dz, dz));
+  }
+  float cov[9];
+  cov[0] = a0 / fn; cov[1] = a1 / fn; cov[2] = a2 / fn; cov[4] = a3 / fn; cov[5] = a4 / fn; cov[8] = a5 / fn;
+  cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+
+  // pcl::eigen33: scale, closed-form roots, eigenvector from the largest cross product of rows of (A - l0 I)
+  float scale = 0.f;
+  for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(cov[i]));
+  if (scale <= 1.17549435e-38f) scale = 1.f;
+  float sc[9];
+  for (int i = 0; i < 9; ++i) sc[i] = cov[i] / scale;
+  float r[3];
+  compute_roots(sc, r);
+  const float ev = r[0] * scale;
+  sc[0] -= r[0]; sc[4] -= r[0]; sc[8] -= r[0];
+  float v1[3], v2[3], v3[3];
+  cross3(sc, sc + 3, v1); cross3(sc, sc + 6, v2); cross3(sc + 3, sc + 6, v3);
+  const float n1 = v1[0] * v1[0] + (v1[1] * v1[1] + v1[2] * v1[2]);
+  const float n2 = v2[0] * v2[0] + (v2[1] * v2[1] + v2[2] * v2[2]);
+  const float n3 = v3[0] * v3[0] + (v3[1] * v3[1] + v3[2] * v3[2]);
+  const float* v; float len;
+  if (n1 >= n2 && n1 >= n3) { v = v1; len = n1; } else if (n2 >= n1 && n2 >= n3) { v = v2; len = n2; } else { v = v3; len = n3; }
+  const float inv = sqrtf(len);
+  float nx = v[0] / inv, ny = v[1] / inv, nz = v[2] / inv;
+  const float eig_sum = cov[0] + cov[4] + cov[8];
+  const float curv = eig_sum != 0.f ? fabsf(ev / eig_sum) : 0.f;
+  // flipNormalTowardsViewpoint
+  const float wx = vpx - q.x, wy = vpy - q.y, wz = vpz - q.z;
+  if ((wx * nx + wy * ny + wz * nz) < 0.f) { nx *= -1.f; ny *= -1.f; nz *= -1.f; }
+  return make_float4(nx, ny, nz, curv);
+}
+
 __global__ void __launch_bounds__(kKnnThreads)
 kn_knn_normals(const float4* __restrict__ s_xyz, size_t n, const Aabb* __restrict__ nodes, BvhLevels lv, int k, float vpx, float vpy, float vpz,
                float4* __restrict__ out, int* __restrict__ out_idx, unsigned int* __restrict__ nan_count, size_t q_begin, size_t q_end) {
@@ -249,47 +298,68 @@ kn_knn_normals(const float4* __restrict__ s_xyz, size_t n, const Aabb* __restric
   const float nanv = __int_as_float(0x7fc00000);
   if (cnt < 3) { out[qi] = make_float4(nanv, nanv, nanv, nanv); atomicAdd(nan_count, 1u); return; }
 
-  // two-pass mean / covariance, fp32, sequential in neighbour order, no contraction (two_pass_centroid.hpp:164-258)
-  float a6 = 0.f, a7 = 0.f, a8 = 0.f;
-  for (int a = 0; a < cnt; ++a) { const float4 p = __ldg(&s_xyz[h.P(a)]); a6 = fadd(a6, p.x); a7 = fadd(a7, p.y); a8 = fadd(a8, p.z); }
-  const float fn = (float)cnt;
-  a6 = a6 / fn; a7 = a7 / fn; a8 = a8 / fn;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
-  for (int a = 0; a < cnt; ++a) {
-    const float4 p = __ldg(&s_xyz[h.P(a)]);
-    const float dx = fsub(p.x, a6), dy = fsub(p.y, a7), dz = fsub(p.z, a8);
-    a0 = fadd(a0, fmul(dx, dx)); a1 = fadd(a1, fmul(dx, dy)); a2 = fadd(a2, fmul(dx, dz));
-    a3 = fadd(a3, fmul(dy, dy)); a4 = fadd(a4, fmul(dy, dz)); a5 = fadd(a5, fmul(dz, dz));
-  }
-  float cov[9];
-  cov[0] = a0 / fn; cov[1] = a1 / fn; cov[2] = a2 / fn; cov[4] = a3 / fn; cov[5] = a4 / fn; cov[8] = a5 / fn;
-  cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+  out[qi] = normal_from_list(s_xyz, [&](int a) { return h.P(a); }, cnt, q, vpx, vpy, vpz);
+}
 
-  // pcl::eigen33: scale, closed-form roots, eigenvector from the largest cross product of rows of (A - l0 I)
-  float scale = 0.f;
-  for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(cov[i]));
-  if (scale <= 1.17549435e-38f) scale = 1.f;
-  float sc[9];
-  for (int i = 0; i < 9; ++i) sc[i] = cov[i] / scale;
-  float r[3];
-  compute_roots(sc, r);
-  const float ev = r[0] * scale;
-  sc[0] -= r[0]; sc[4] -= r[0]; sc[8] -= r[0];
-  float v1[3], v2[3], v3[3];
-  cross3(sc, sc + 3, v1); cross3(sc, sc + 6, v2); cross3(sc + 3, sc + 6, v3);
-  const float n1 = v1[0] * v1[0] + (v1[1] * v1[1] + v1[2] * v1[2]);
-  const float n2 = v2[0] * v2[0] + (v2[1] * v2[1] + v2[2] * v2[2]);
-  const float n3 = v3[0] * v3[0] + (v3[1] * v3[1] + v3[2] * v3[2]);
-  const float* v; float len;
-  if (n1 >= n2 && n1 >= n3) { v = v1; len = n1; } else if (n2 >= n1 && n2 >= n3) { v = v2; len = n2; } else { v = v3; len = n3; }
-  const float inv = sqrtf(len);
-  float nx = v[0] / inv, ny = v[1] / inv, nz = v[2] / inv;
-  const float eig_sum = cov[0] + cov[4] + cov[8];
-  const float curv = eig_sum != 0.f ? fabsf(ev / eig_sum) : 0.f;
-  // flipNormalTowardsViewpoint
-  const float wx = vpx - q.x, wy = vpy - q.y, wz = vpz - q.z;
-  if ((wx * nx + wy * ny + wz * nz) < 0.f) { nx *= -1.f; ny *= -1.f; nz *= -1.f; }
-  out[qi] = make_float4(nx, ny, nz, curv);
+// ---- radius mode (setRadiusSearch): every point with d2 < r2, in (d2, index) order --------------------------------------------
+// Three kernels per batch of Morton-sorted queries: count -> (scan) -> fill keys ((d2 bits << 32) | original index, value = sorted
+// position) -> (segmented radix sort: for non-negative floats the bit pattern orders like the value) -> normals.
+template <typename F>
+__device__ __forceinline__ void radius_visit(const float4& q, float r2, const float4* __restrict__ s_xyz, size_t n, const Aabb* __restrict__ nodes,
+                                             const BvhLevels& lv, F&& f) {
+  unsigned int stack[2 * kMaxLevels + 2];
+  int sp = 0;
+  stack[sp++] = ((unsigned int)(lv.nlevels - 1) << 27);
+  while (sp > 0) {
+    const unsigned int e = stack[--sp];
+    const int level = (int)(e >> 27);
+    const unsigned int i = e & 0x7FFFFFFu;
+    if (dist2_box(q, nodes[lv.offset[level] + i]) >= r2) continue;    // bound <= every d2 inside (monotone fp32), and the test is strict
+    if (level == 0) {
+      const size_t b = (size_t)i * kLeaf, e2 = min(n, b + kLeaf);
+      for (size_t p = b; p < e2; ++p) { const float4 t = __ldg(&s_xyz[p]); const float d = dist2_pt(q, t); if (d < r2) f(d, (unsigned int)p, __float_as_uint(t.w)); }
+      continue;
+    }
+    const unsigned int c0 = 2 * i, c1 = 2 * i + 1;
+    stack[sp++] = ((unsigned int)(level - 1) << 27) | c0;
+    if (c1 < lv.count[level - 1]) stack[sp++] = ((unsigned int)(level - 1) << 27) | c1;
+  }
+}
+__global__ void __launch_bounds__(128) kn_radius_count(const float4* __restrict__ s_xyz, size_t n, const Aabb* __restrict__ nodes, BvhLevels lv, float r2,
+                                                       size_t q_begin, size_t q_end, unsigned int* __restrict__ counts) {
+  const size_t j = q_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= q_end) return;
+  unsigned int c = 0;
+  radius_visit(s_xyz[j], r2, s_xyz, n, nodes, lv, [&](float, unsigned int, unsigned int) { ++c; });
+  counts[j - q_begin] = c;
+}
+__global__ void __launch_bounds__(128) kn_radius_fill(const float4* __restrict__ s_xyz, size_t n, const Aabb* __restrict__ nodes, BvhLevels lv, float r2,
+                                                      size_t q_begin, size_t q_end, const unsigned long long* __restrict__ offs,
+                                                      unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals) {
+  const size_t j = q_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= q_end) return;
+  unsigned long long o = offs[j - q_begin];
+  radius_visit(s_xyz[j], r2, s_xyz, n, nodes, lv, [&](float d, unsigned int p, unsigned int idx) {
+    keys[o] = ((unsigned long long)__float_as_uint(d) << 32) | idx; vals[o] = p; ++o;
+  });
+}
+__global__ void __launch_bounds__(128) kn_radius_normals(const float4* __restrict__ s_xyz, size_t q_begin, size_t q_end, const unsigned long long* __restrict__ offs,
+                                                         const unsigned int* __restrict__ vals, float vpx, float vpy, float vpz, float4* __restrict__ out,
+                                                         int* __restrict__ out_count, unsigned int* __restrict__ nan_count) {
+  const size_t j = q_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= q_end) return;
+  const float4 q = s_xyz[j];
+  const unsigned long long b = offs[j - q_begin];
+  const int cnt = (int)(offs[j - q_begin + 1] - b);
+  const unsigned int qi = __float_as_uint(q.w);
+  if (out_count) out_count[qi] = cnt;
+  const float nanv = __int_as_float(0x7fc00000);
+  if (cnt < 3) { out[qi] = make_float4(nanv, nanv, nanv, nanv); atomicAdd(nan_count, 1u); return; }
+  out[qi] = normal_from_list(s_xyz, [&](int a) { return __ldg(&vals[b + a]); }, cnt, q, vpx, vpy, vpz);
+}
+__global__ void __launch_bounds__(256) kn_widen(const unsigned int* __restrict__ in, size_t n, unsigned long long* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
 }
 
 static inline unsigned int div_up_u(size_t a, size_t b) { return (unsigned int)((a + b - 1) / b); }
@@ -302,10 +372,12 @@ using namespace b2;
 // queries; the zero-initialised outputs are merged by one sum-allreduce (NaN normals survive the sum), so every rank returns
 // the full result. No exchange during the search itself.
 static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3], float* out_nxyz_curv,
-                        int32_t* out_knn_idx, int* is_dense, b2_comm* comm, int device) {
+                        int32_t* out_knn_idx, int* is_dense, b2_comm* comm, int device, float radius = 0.f, int32_t* out_count = nullptr) {
   if ((n && (!xyz || !out_nxyz_curv)) || !viewpoint) return set_error(B2_ERR_ARG, "null argument");
   if (stride_bytes < 12) return set_error(B2_ERR_ARG, "stride_bytes must be >= 12");
-  if (k < 1 || k > 128) return set_error(B2_ERR_ARG, "k must be in [1,128]");
+  const bool radius_mode = radius > 0.f;
+  if (!radius_mode && (k < 1 || k > 128)) return set_error(B2_ERR_ARG, "k must be in [1,128]");
+  if (radius_mode && !(radius < INFINITY)) return set_error(B2_ERR_ARG, "radius must be finite");
   if (n >= (1ull << 30)) return set_error(B2_ERR_ARG, "clouds above 2^30 points are not supported");
   if (is_dense) *is_dense = 1;
   if (n == 0) return B2_OK;
@@ -317,6 +389,7 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
   const size_t q_begin = n * (size_t)rank / (size_t)world, q_end = n * (size_t)(rank + 1) / (size_t)world;
   cudaStream_t st; B2_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   DevBuf d_xyz, d_part, d_keys, d_keys2, d_idx, d_perm, d_sxyz, d_nodes, d_tmp, d_out, d_oidx, d_nan;
+  DevBuf r_cnt, r_cnt64, r_offs, r_keys, r_keys2, r_vals, r_vals2, r_ocount;
   PinnedBuf p_part;
   int rc = B2_OK;
   auto body = [&]() -> int {
@@ -360,9 +433,45 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
     B2_TRY(d_nan.ensure(4));
     B2_CUDA(cudaMemsetAsync(d_nan.p, 0, 4, st));
     if (world > 1) B2_CUDA(cudaMemsetAsync(d_out.p, 0, n * 16, st));
-    const size_t smem = (size_t)k * kKnnThreads * 8;
+    if (radius_mode) {
+      // setRadiusSearch: batches of Morton-sorted queries so that the neighbour lists (12 B per entry, double-buffered) stay bounded
+      const float r2 = (float)((double)radius * (double)radius);      // PCL: radiusSearch(point, radius) -> FLANN with (float)(radius*radius)
+      const size_t kBatch = 1u << 20;
+      B2_TRY(r_cnt.ensure(kBatch * 4)); B2_TRY(r_cnt64.ensure((kBatch + 1) * 8)); B2_TRY(r_offs.ensure((kBatch + 1) * 8));
+      if (out_count) { B2_TRY(r_ocount.ensure(n * 4)); B2_CUDA(cudaMemsetAsync(r_ocount.p, 0, n * 4, st)); }
+      for (size_t qb = q_begin; qb < q_end; qb += kBatch) {
+        const size_t qe = std::min(q_end, qb + kBatch), nb = qe - qb;
+        kn_radius_count<<<div_up_u(nb, 128), 128, 0, st>>>(d_sxyz.as<float4>(), n, d_nodes.as<Aabb>(), lv, r2, qb, qe, r_cnt.as<unsigned int>());
+        B2_CUDA(cudaMemsetAsync(r_cnt64.as<unsigned long long>() + nb, 0, 8, st));
+        kn_widen<<<div_up_u(nb, 256), 256, 0, st>>>(r_cnt.as<unsigned int>(), nb, r_cnt64.as<unsigned long long>());
+        size_t t1 = 0;
+        B2_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t1, r_cnt64.as<unsigned long long>(), r_offs.as<unsigned long long>(), (int)(nb + 1), st));
+        B2_TRY(d_tmp.ensure(t1));
+        B2_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, t1, r_cnt64.as<unsigned long long>(), r_offs.as<unsigned long long>(), (int)(nb + 1), st));
+        unsigned long long total = 0;
+        B2_CUDA(cudaMemcpyAsync(&total, r_offs.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        if (total > 0x7FFFFFFFull) return set_error(B2_ERR_ARG, "radius %g gathers more than 2^31 neighbours per 2^20 points", (double)radius);
+        const size_t tot = std::max<size_t>((size_t)total, 1);
+        B2_TRY(r_keys.ensure(tot * 8)); B2_TRY(r_keys2.ensure(tot * 8)); B2_TRY(r_vals.ensure(tot * 4)); B2_TRY(r_vals2.ensure(tot * 4));
+        kn_radius_fill<<<div_up_u(nb, 128), 128, 0, st>>>(d_sxyz.as<float4>(), n, d_nodes.as<Aabb>(), lv, r2, qb, qe, r_offs.as<unsigned long long>(),
+                                                          r_keys.as<unsigned long long>(), r_vals.as<unsigned int>());
+        size_t t2 = 0;
+        B2_CUDA(cub::DeviceSegmentedSort::SortPairs(nullptr, t2, r_keys.as<unsigned long long>(), r_keys2.as<unsigned long long>(), r_vals.as<unsigned int>(),
+                                                    r_vals2.as<unsigned int>(), (int)total, (int)nb, r_offs.as<unsigned long long>(),
+                                                    r_offs.as<unsigned long long>() + 1, st));
+        B2_TRY(d_tmp.ensure(t2));
+        B2_CUDA(cub::DeviceSegmentedSort::SortPairs(d_tmp.p, t2, r_keys.as<unsigned long long>(), r_keys2.as<unsigned long long>(), r_vals.as<unsigned int>(),
+                                                    r_vals2.as<unsigned int>(), (int)total, (int)nb, r_offs.as<unsigned long long>(),
+                                                    r_offs.as<unsigned long long>() + 1, st));
+        kn_radius_normals<<<div_up_u(nb, 128), 128, 0, st>>>(d_sxyz.as<float4>(), qb, qe, r_offs.as<unsigned long long>(), r_vals2.as<unsigned int>(),
+                                                             viewpoint[0], viewpoint[1], viewpoint[2], d_out.as<float4>(),
+                                                             out_count ? r_ocount.as<int>() : nullptr, d_nan.as<unsigned int>());
+      }
+    }
+    const size_t smem = (size_t)std::max(k, 1) * kKnnThreads * 8;
     B2_CUDA(cudaFuncSetAttribute(kn_knn_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (q_end > q_begin)
+    if (!radius_mode && q_end > q_begin)
       kn_knn_normals<<<div_up_u(q_end - q_begin, kKnnThreads), kKnnThreads, smem, st>>>(d_sxyz.as<float4>(), n, d_nodes.as<Aabb>(), lv, k, viewpoint[0],
                                                                                         viewpoint[1], viewpoint[2], d_out.as<float4>(),
                                                                                         out_knn_idx ? d_oidx.as<int>() : nullptr,
@@ -375,6 +484,10 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
     unsigned int nans = 0;
     B2_CUDA(cudaMemcpyAsync(out_nxyz_curv, d_out.p, n * 16, cudaMemcpyDeviceToHost, st));
     if (out_knn_idx) B2_CUDA(cudaMemcpyAsync(out_knn_idx, d_oidx.p, n * (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+    if (radius_mode && out_count) {
+      if (world > 1) B2_TRY(b2_comm_allreduce(comm, r_ocount.p, n, B2_I32, (void*)st));
+      B2_CUDA(cudaMemcpyAsync(out_count, r_ocount.p, n * 4, cudaMemcpyDeviceToHost, st));
+    }
     B2_CUDA(cudaMemcpyAsync(&nans, d_nan.p, 4, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
     if (is_dense) *is_dense = nans == 0;
@@ -382,6 +495,7 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
   };
   rc = body();
   for (DevBuf* b : {&d_xyz, &d_part, &d_keys, &d_keys2, &d_idx, &d_perm, &d_sxyz, &d_nodes, &d_tmp, &d_out, &d_oidx, &d_nan}) b->release();
+  for (DevBuf* b : {&r_cnt, &r_cnt64, &r_offs, &r_keys, &r_keys2, &r_vals, &r_vals2, &r_ocount}) b->release();
   p_part.release();
   cudaStreamDestroy(st);
   return rc;
@@ -390,6 +504,12 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
 extern "C" int b2_normals_estimate(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3], float* out_nxyz_curv,
                                    int32_t* out_knn_idx, int* is_dense) {
   return normals_impl(xyz, n, stride_bytes, k, viewpoint, out_nxyz_curv, out_knn_idx, is_dense, nullptr, -1);
+}
+
+extern "C" int b2_normals_estimate_radius(const float* xyz, size_t n, size_t stride_bytes, float radius, const float viewpoint[3], b2_comm* comm,
+                                          int device, float* out_nxyz_curv, int32_t* out_neighbor_count, int* is_dense) {
+  if (!(radius > 0.f)) return set_error(B2_ERR_ARG, "radius must be > 0");
+  return normals_impl(xyz, n, stride_bytes, 0, viewpoint, out_nxyz_curv, nullptr, is_dense, comm, device, radius, out_neighbor_count);
 }
 
 extern "C" int b2_normals_estimate_dist(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3], b2_comm* comm, int device,

@@ -11,6 +11,7 @@ class NormalEstimationTwoPassOMP:
     def __init__(self):
         self._xyz = None
         self._k = 0
+        self._radius = 0.0
         self._vp = np.zeros(3, np.float32)
         self.is_dense = True
 
@@ -23,17 +24,30 @@ class NormalEstimationTwoPassOMP:
         pass
 
     def setKSearch(self, k):
-        self._k = int(k)
+        self._k = int(k); self._radius = 0.0
+
+    def setRadiusSearch(self, radius):
+        """All neighbours within `radius` (normal_estimator.cc:181-182) instead of the k nearest."""
+        self._radius = float(radius); self._k = 0
 
     def setViewPoint(self, x, y, z):
         self._vp = np.array([x, y, z], np.float32)
 
     def compute(self, return_indices=False):
         """Returns (n,4) float32: normal_x, normal_y, normal_z, curvature (NaN rows where < 3 neighbours)."""
-        if self._xyz is None or self._k <= 0:
-            raise _lib.B2Error(2, "setInputCloud and setKSearch must be called first")
+        if self._xyz is None or (self._k <= 0 and self._radius <= 0):
+            raise _lib.B2Error(2, "setInputCloud and setKSearch / setRadiusSearch must be called first")
         n = self._xyz.shape[0]
         out = np.zeros((n, 4), np.float32)
+        if self._radius > 0:
+            cnt = np.zeros(n, np.int32); dense = C.c_int32(1)
+            fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+            L = _lib.lib()
+            L.b2_normals_estimate_radius.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_float, fp, C.c_void_p, C.c_int, fp, ip, ip]
+            _lib.check(L.b2_normals_estimate_radius(self._xyz.ctypes.data, n, 12, self._radius, self._vp.ctypes.data_as(fp), None, -1,
+                                                    out.ctypes.data_as(fp), cnt.ctypes.data_as(ip), C.byref(dense)))
+            self.is_dense = bool(dense.value)
+            return (out, cnt) if return_indices else out
         idx = np.zeros((n, self._k), np.int32) if return_indices else None
         dense = C.c_int32(1)
         fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
@@ -55,6 +69,12 @@ def estimate_normals_dist(xyz, k, viewpoint, comm, device=-1):
     _lib.check(L.b2_normals_estimate_dist(x.ctypes.data, x.shape[0], 12, int(k), vp.ctypes.data_as(fp), comm._c, device, out.ctypes.data_as(fp),
                                           C.byref(dense)))
     return out, bool(dense.value)
+
+
+def estimate_normals_radius(xyz, radius, viewpoint=(0.0, 0.0, 0.0), return_counts=False):
+    ne = NormalEstimationTwoPassOMP()
+    ne.setInputCloud(xyz); ne.setRadiusSearch(radius); ne.setViewPoint(*viewpoint)
+    return ne.compute(return_counts)
 
 
 def estimate_normals(xyz, k, viewpoint=(0.0, 0.0, 0.0), return_indices=False):

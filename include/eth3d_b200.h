@@ -156,6 +156,12 @@ int b2_normals_estimate(const float* xyz, size_t n, size_t stride_bytes, int k, 
  * answers the r-th slice of the Morton-sorted queries and one sum-allreduce over `comm` merges the outputs. */
 int b2_normals_estimate_dist(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3], b2_comm* comm, int device,
                              float* out_nxyz_curv, int* is_dense);
+/* setRadiusSearch mode (two_pass_normal_3d_omp.hpp:66 with search_parameter_ = radius; normal_estimator.cc:181-182): the neighbours of
+ * a point are ALL points with squared distance < (float)((double)radius*radius) (itself included), taken in the order radiusSearch
+ * returns them (by distance, ties to the lower index). comm may be NULL (single GPU, device = -1 for the default).
+ * out_neighbor_count (nullable): n counts. */
+int b2_normals_estimate_radius(const float* xyz, size_t n, size_t stride_bytes, float radius, const float viewpoint[3], b2_comm* comm, int device,
+                               float* out_nxyz_curv, int32_t* out_neighbor_count, int* is_dense);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Path B — dense photometric image<->scan alignment (tool ImageRegistrator).

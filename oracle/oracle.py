@@ -207,6 +207,17 @@ def normals_knn(xyz, k, viewpoint=(0.0, 0.0, 0.0), return_indices=False):
     return (out, idx) if return_indices else out
 
 
+def normals_radius(xyz, radius, viewpoint=(0.0, 0.0, 0.0), return_counts=False):
+    """setRadiusSearch mode: all neighbours within `radius` (strict), sorted by (distance, index)."""
+    x = _c32(xyz); vp = _c32(viewpoint)
+    n = x.shape[0]
+    out = np.zeros((n, 4), np.float32); cnt = np.zeros(n, np.int32)
+    L = lib()
+    L.orc_normals_radius.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.orc_normals_radius(_f(x), n, float(radius), _f(vp), _f(out), cnt.ctypes.data_as(C.POINTER(C.c_int)))
+    return (out, cnt) if return_counts else out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Path B (orc_reg.cc)
 # ---------------------------------------------------------------------------------------------------------------------

@@ -53,6 +53,9 @@ int orc_ldlt_solve_upper(const double* A_colmajor, int n, const double* b, doubl
 int orc_normals_knn(const float* xyz, size_t n, int k, const float viewpoint[3], float* out_nxyz_curv /* n x 4 */,
                     int* out_knn_idx /* n x k or NULL */);
 
+/* radius mode: every point with d2 < (float)((double)r*r), sorted by (distance, index); out_count (nullable) = neighbours found */
+int orc_normals_radius(const float* xyz, size_t n, float radius, const float viewpoint[3], float* out_nxyz_curv, int* out_count);
+
 /* ---- Path B: photometric image<->scan alignment (orc_reg.cc), pinhole cameras, no rigs, no depth residuals ---- */
 typedef struct orc_reg orc_reg;
 typedef struct orc_reg_params {   /* mirror of opt::Parameters (src/opt/parameters.h:40-67) restricted to what Path B reads */

@@ -142,3 +142,26 @@ extern "C" int orc_normals_knn(const float* xyz, size_t n, int k, const float vi
   }
   return 0;
 }
+
+// setRadiusSearch mode (two_pass_normal_3d_omp.hpp:66 with search_parameter_ = radius; normal_estimator.cc:181-182): ALL points with
+// d2 < (float)((double)r*r) (self included), in the order radiusSearch returns them (sorted by distance; ties to the lower index).
+extern "C" int orc_normals_radius(const float* xyz, size_t n, float radius, const float viewpoint[3], float* out, int* out_count) {
+  orc::KdTree tree;
+  tree.build(xyz, n, 3, 15);
+  const float r2 = (float)((double)radius * (double)radius);
+#pragma omp parallel
+  {
+    std::vector<std::pair<float, int>> found;
+    std::vector<int> idx;
+#pragma omp for schedule(dynamic, 1024)
+    for (long long i = 0; i < (long long)n; ++i) {
+      tree.radius(xyz + 3 * i, r2, &found);
+      std::sort(found.begin(), found.end());
+      idx.resize(found.size());
+      for (size_t j = 0; j < found.size(); ++j) idx[j] = found[j].second;
+      if (out_count) out_count[i] = (int)found.size();
+      orc::point_normal(xyz, idx.data(), (int)idx.size(), xyz + 3 * i, viewpoint, out + 4 * i);
+    }
+  }
+  return 0;
+}

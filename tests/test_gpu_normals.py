@@ -61,3 +61,31 @@ def test_small_and_degenerate(oracle):
     o, oi = oracle.normals_knn(xyz, 16, return_indices=True)
     assert np.array_equal(gi, oi)
     assert np.allclose(g, o, atol=1e-4, equal_nan=True)
+
+
+def test_radius_mode(oracle):
+    """setRadiusSearch (normal_estimator.cc:181-182): neighbour counts bit-exact (strict d2 < (float)((double)r*r)), normals from the
+    (distance, index)-ordered lists within the same tolerances as the kNN mode; isolated points (< 3 neighbours) give NaN."""
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import synth
+    xyz, nrm, _ = synth.room_scan(0, 300, 120)
+    xyz = np.concatenate([xyz, [[40.0, 40.0, 40.0], [40.0, 40.0, 40.004]]]).astype(np.float32)     # two far points: only each other + self
+    for radius in (0.05, 0.12):
+        g, gc = b2.estimate_normals_radius(xyz, radius, (0.0, 0.0, 0.0), return_counts=True)
+        o, oc = oracle.normals_radius(xyz, radius, (0.0, 0.0, 0.0), return_counts=True)
+        assert np.array_equal(gc, oc), "neighbour counts differ"
+        nan_g, nan_o = np.isnan(g[:, 0]), np.isnan(o[:, 0])
+        assert np.array_equal(nan_g, nan_o) and nan_o[-2:].all() and np.array_equal(nan_o, oc < 3)
+        ok = ~nan_o
+        well = ok & (o[:, 3] < 0.05) & (oc >= 6)
+        ang = np.arccos(np.clip(np.abs((g[well, :3] * o[well, :3]).sum(1)), -1, 1))
+        assert np.quantile(ang, 0.999) <= 1e-3
+        assert np.abs(g[ok, 3] - o[ok, 3]).max() <= 2e-5
+        assert oc.max() > 40 and well.sum() > 10000
+    # exact duplicates and the strict radius edge: points at distance exactly r are excluded
+    line = np.array([[0, 0, 0], [0.5, 0, 0], [0, 0.5, 0], [0, 0, 0], [0.25, 0.25, 0.1]], np.float32)
+    g, gc = b2.estimate_normals_radius(line, 0.5, return_counts=True)
+    o, oc = oracle.normals_radius(line, 0.5, return_counts=True)
+    assert np.array_equal(gc, oc) and gc[0] == 3          # itself, its duplicate and the interior point; the two at d = r are out
+    with pytest.raises(Exception):
+        b2.estimate_normals_radius(line, -1.0)

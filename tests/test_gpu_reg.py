@@ -1,9 +1,13 @@
 """Path B parity: every seam of the CUDA path (through the C ABI) against the oracle on the same synthetic scene.
 Integer / index results bit-exact; float results within 1e-5 relative (in practice identical: same fp32 evaluation order)."""
 import math
+import os
+import sys
 
 import numpy as np
 import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -187,23 +191,7 @@ def test_reg_error_paths():
         r.initialize()                                                  # 70x50 -> 35x25 -> odd parent for a 3rd level
 
 
-def _grid_mesh(x0, x1, y0, y1, z, n, tilt=0.0):
-    xs = np.linspace(x0, x1, n + 1); ys = np.linspace(y0, y1, n + 1)
-    X, Y = np.meshgrid(xs, ys, indexing="xy")
-    V = np.stack([X.ravel(), Y.ravel(), z + tilt * X.ravel()], 1).astype(np.float32)
-    F = []
-    for j in range(n):
-        for i in range(n):
-            a = j * (n + 1) + i; b = a + 1; c = a + n + 1; d = c + 1
-            F += [[a, b, d], [a, d, c]]
-    return V, np.array(F, np.uint32)
-
-
-def _box_mesh(c, h):
-    x, y, z = c
-    V = np.array([[x + sx * h, y + sy * h, z + sz * h] for sz in (-1, 1) for sy in (-1, 1) for sx in (-1, 1)], np.float32)
-    F = np.array([[0, 1, 3], [0, 3, 2], [4, 7, 5], [4, 6, 7], [0, 5, 1], [0, 4, 5], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4], [1, 5, 7], [1, 7, 3]], np.uint32)
-    return V, F
+from mesh_util import _box_mesh, _grid_mesh  # noqa: E402
 
 
 def test_mesh_depth_pass_and_boundary_masking(oracle, scene):

@@ -167,7 +167,9 @@ def test_mesh_occlusion_with_distorted_cameras(oracle, model):
     pipeline (THIN_PRISM_FISHEYE images + mesh occlusion geometry)."""
     b2, R = _b2()
     from dataset_pipeline_b200.synth import reg_scene
-    from test_gpu_reg import _grid_mesh, _box_mesh
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from mesh_util import _grid_mesh, _box_mesh
     sc = reg_scene.make_scene(num_images=2, width=320, height=240, fx=260.0, camera_model=model, num_scales=3, base_radius=0.004)
     Vp, Fp = _grid_mesh(-1.3, 1.3, -1.0, 1.0, 0.0, 30)                 # the textured plane itself
     Vb, Fb = _box_mesh((0.2, 0.1, 0.5), 0.15)                          # a box above it: silhouettes + hidden points
@@ -202,4 +204,4 @@ def test_mesh_occlusion_with_distorted_cameras(oracle, model):
     g = b2.Registration(R.default_params(max_initial_image_area_in_pixels=area, mask_occlusion_boundaries=0))
     reg_scene.load_into(g, sc, splats=False); g.set_mesh(V, F); g.set_image_scale(0)
     dd, _ = g.render_depth(0)
-    assert dd.shape == dp.shape and (np.abs(dd - dp) > 0.05).mean() > 0.01
+    assert dd.shape == dp.shape and (np.abs(dd - dp) > 0.005).mean() > 0.01
