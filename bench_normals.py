@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--cpu-points", type=int, default=2000000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around one call (for `ncu --profile-from-start off`)")
     a = ap.parse_args()
     import torch
     if not torch.cuda.is_available():
@@ -38,6 +39,13 @@ def main():
     for _ in range(a.warmup):
         out = b2.estimate_normals(x, a.k, (0.0, 0.0, 0.0))
     torch.cuda.synchronize()
+    if a.profile:
+        torch.cuda.profiler.start()
+        out = b2.estimate_normals(x, a.k, (0.0, 0.0, 0.0))
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profile": True, "points": int(n)}))
+        return
     t = time.perf_counter()
     for _ in range(a.steps):
         out = b2.estimate_normals(x, a.k, (0.0, 0.0, 0.0))

@@ -107,6 +107,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--camera", default="pinhole", choices=["pinhole", "thin_prism", "benchmark"])
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--profile", action="store_true", help="finest image scale only; cudaProfilerStart/Stop around one CreateObservations + ColorOptimizer + accumulate "
+                    "(for `ncu --profile-from-start off`); prints no benchmark value")
     a = ap.parse_args()
     import torch
     if not torch.cuda.is_available():
@@ -133,6 +135,16 @@ def main():
     if comm is not None:
         g.set_comm(comm)
     nsc = reg_scene.load_into(g, sc, splats=False)
+    if a.profile:
+        g.set_image_scale(0)
+        g.CreateObservationsForAllImages(1); g.ColorOptimizerApply(); g.accumulate()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        g.CreateObservationsForAllImages(1); g.ColorOptimizerApply(); g.accumulate()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profile": True, "stats": g.stats()}))
+        return
     res = {}
     for scale in (nsc - 2, 0):
         g.set_image_scale(scale)

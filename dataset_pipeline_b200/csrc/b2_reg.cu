@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <limits>
 #include <map>
 #include <memory>
@@ -108,6 +110,8 @@ struct b2_reg {
   std::vector<ObsSet> trial;                 // scratch sets for trial states, [scale]
   // scratch
   DevBuf flags, offs, cx, cy, cs, cub_tmp, depth, partials, results, cut_cams, cut_first, cut_starts, cut_points, cut_out;
+  DevBuf w_nj, w_ws, w_wr, w_part;           // K12b: per-observation slots / merged weights / residual factors + their residual-sum partials
+  int k12_mode = 0;                          // B2_K12: 0 = fp64 products (default), 1 = fp32 products + shuffle kernel (reference op order)
   PinnedBuf pin;
   b2_reg_stats stats;
   int launches = 0;
@@ -487,12 +491,34 @@ static int accumulate_all(b2_reg* h, std::vector<double>* H, std::vector<double>
       const float *pK = o.jK.as<float>(), *pP = o.jP.as<float>(), *pR = o.jR.as<float>();
       double* part = h->partials.as<double>();
       const int lv = np + 6 + (rig.dependent ? 6 : 0), nout = lv * (lv + 1) / 2 + lv + 4;
-      if (np == 4 && !rig.dependent) kr_accumulate<<<grid, 128, 0, h->stream>>>(A, pK, pP, part);
+      const bool blocks = h->k12_mode == 0 && K(h) == 5 && !(np == 4 && !rig.dependent);
+      const int gridb = h->sms * ((np == 12 && rig.dependent) ? BlockCfg<12, true>::CTAS : 2);   // persistent CTAs of kr_accumulate_blocks
+      if (np == 4 && !rig.dependent) {
+        if (h->k12_mode == 0) kr_accumulate<false><<<grid, 128, 0, h->stream>>>(A, pK, pP, part);
+        else kr_accumulate<true><<<grid, 128, 0, h->stream>>>(A, pK, pP, part);
+      } else if (blocks) {
+        const int gridw = h->sms * 4;
+        B2_TRY(h->w_nj.ensure(o.count * 5 * 4)); B2_TRY(h->w_ws.ensure(o.count * 8)); B2_TRY(h->w_wr.ensure(o.count * 5 * 8));
+        B2_TRY(h->w_part.ensure(sizeof(double) * 4 * gridw));
+        kr_residual_weights<5><<<gridw, 256, 0, h->stream>>>(A, h->w_nj.as<int>(), h->w_ws.as<double>(), h->w_wr.as<double>(), h->w_part.as<double>());
+        const int* pn = h->w_nj.as<int>(); const double *pws = h->w_ws.as<double>(), *pwr = h->w_wr.as<double>();
+        if (np == 4) kr_accumulate_blocks<4, true, 5><<<gridb, BlockCfg<4, true>::T, BlockCfg<4, true>::smem(5), h->stream>>>(o.count, pn, pws, pwr, pK, pP, pR, part);
+        else if (!rig.dependent) kr_accumulate_blocks<12, false, 5><<<gridb, BlockCfg<12, false>::T, BlockCfg<12, false>::smem(5), h->stream>>>(o.count, pn, pws, pwr, pK, pP, pR, part);
+        else kr_accumulate_blocks<12, true, 5><<<gridb, BlockCfg<12, true>::T, BlockCfg<12, true>::smem(5), h->stream>>>(o.count, pn, pws, pwr, pK, pP, pR, part);
+        ++h->launches;
+      }
       else if (np == 4) kr_accumulate_wide<4, true><<<grid_wide, 128, 0, h->stream>>>(A, pK, pP, pR, part);
       else if (!rig.dependent) kr_accumulate_wide<12, false><<<grid_wide, 128, 0, h->stream>>>(A, pK, pP, pR, part);
       else kr_accumulate_wide<12, true><<<grid_wide, 128, 0, h->stream>>>(A, pK, pP, pR, part);
       cudaEventRecord(h->eva1, h->stream);
-      kr_reduce_partials<<<1, 256, 0, h->stream>>>(part, (np == 4 && !rig.dependent) ? grid : grid_wide, nout, h->results.as<double>() + kAccW * (im * S + ps));
+      double* res = h->results.as<double>() + kAccW * (im * S + ps);
+      if (blocks) {
+        kr_reduce_partials<<<1, 256, 0, h->stream>>>(part, gridb, nout - 4, res);
+        kr_reduce_partials<<<1, 256, 0, h->stream>>>(h->w_part.as<double>(), h->sms * 4, 4, res + (nout - 4));
+        ++h->launches;
+      } else {
+        kr_reduce_partials<<<1, 256, 0, h->stream>>>(part, (np == 4 && !rig.dependent) ? grid : grid_wide, nout, res);
+      }
       h->launches += 2;
       cudaEventSynchronize(h->eva1);
       float a = 0, c = 0; cudaEventElapsedTime(&a, h->evj0, h->evj1); cudaEventElapsedTime(&c, h->eva0, h->eva1);
@@ -649,6 +675,7 @@ int b2_reg_create(const b2_reg_params* p, b2_reg** out) {
   for (cudaEvent_t* e : {&h->ev0, &h->ev1, &h->evj0, &h->evj1, &h->eva0, &h->eva1}) B2_CUDA(cudaEventCreate(e));
   B2_TRY(h->pin.ensure(4096));
   std::memset(&h->stats, 0, sizeof(h->stats));
+  if (const char* e = std::getenv("B2_K12")) h->k12_mode = std::strcmp(e, "f32") == 0 ? 1 : 0;   // A/B switch, see kr_accumulate
   *out = h.release();
   return B2_OK;
 }
@@ -664,7 +691,7 @@ int b2_reg_destroy(b2_reg* h) {
   for (auto& P : h->pts) for (DevBuf* b : {&P.xyz, &P.nbr, &P.fixed_desc, &P.var_desc, &P.obs_count}) b->release();
   for (DevBuf* b : {&h->mesh_v, &h->mesh_f, &h->mesh_fn, &h->mesh_edges, &h->big_list, &h->big_count, &h->depth_masked}) b->release();
   for (DevBuf* b : {&h->splats, &h->flags, &h->offs, &h->cx, &h->cy, &h->cs, &h->cub_tmp, &h->depth, &h->partials, &h->results}) b->release();
-  for (DevBuf* b : {&h->cut_cams, &h->cut_first, &h->cut_starts, &h->cut_points, &h->cut_out, &h->xchg}) b->release();
+  for (DevBuf* b : {&h->cut_cams, &h->cut_first, &h->cut_starts, &h->cut_points, &h->cut_out, &h->xchg, &h->w_nj, &h->w_ws, &h->w_wr, &h->w_part}) b->release();
   for (auto& kv : h->cam_masks) for (auto& b : kv.second) b.release();
   h->pin.release();
   for (cudaEvent_t e : {h->ev0, h->ev1, h->evj0, h->evj1, h->eva0, h->eva1}) if (e) cudaEventDestroy(e);

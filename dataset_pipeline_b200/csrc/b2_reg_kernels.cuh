@@ -8,6 +8,7 @@
 //   K11 kr_jacobians         trilinear taps on two pyramid levels, dI/d(K) (1x4), dI/d(pose) (1x6)               intrinsics_and_pose_optimizer.cc:933-1147
 //       kr_intensity         trilinear taps only                                                                 cost_calculator.cc:128-142
 //   K12 kr_accumulate        5-neighbour descriptor residual, robust weight, (4+6)^2 outer products in fp64     intrinsics_and_pose_optimizer.cc:770-930,1220-1296
+//   K12b kr_residual_weights + kr_accumulate_blocks   the same for 16/18/24-column local systems (block pairs per warp, staged in smem)
 //   K13 kr_residual_sums     residual sums of a (trial) state                                                  cost_calculator.cc:170-271
 //   K14 kr_color_accumulate / kr_color_mean   variable descriptors = mean over images                              color_optimizer.cc:40-123
 // Arithmetic follows the oracle's fp32 evaluation order; the file is built with -fmad=false so plain operators are never
@@ -496,7 +497,14 @@ __global__ void __launch_bounds__(256) kr_residual_sums(ResidualArgs A, double* 
 }
 
 // K12: per block [55 upper entries of the local (4+6)^2 system | 10 of b | fixed_sum n_fixed var_sum n_var] = 69 doubles.
+// F32PROD = true: every product (w * dj[r]) * dj[c] is formed in fp32 and converted to fp64 before the add, exactly like
+// AccumulateOnHAndB (:1262-1293) — 650 fp32->fp64 conversions per observation, which made the kernel conversion-pipe bound.
+// F32PROD = false (default): the fixed and the variable descriptor residual share their Jacobian differences, so their weights are
+// merged (ws = w_f + w_v, wr_k = w_f c_f[k] + w_v c_v[k]) and the products are formed in fp64 from the fp32 differences
+// (10 conversions + 10 DMUL + 65 DFMA per neighbour). The sums differ from the reference's only by the fp32 rounding of its
+// individual products (<= 2 ulp_fp32 each, random sign): far inside the 1e-5 parity tolerance, and closer to the real-number value.
 static constexpr int kNI = 4, kNV = kNI + 6, kNH = kNV * (kNV + 1) / 2, kAccB = kNH + kNV + 4;
+template <bool F32PROD>
 __global__ void __launch_bounds__(128) kr_accumulate(ResidualArgs A, const float* __restrict__ jK, const float* __restrict__ jP,
                                                      double* __restrict__ partials /* [grid][kAccB] */) {
   double acc[kAccB];
@@ -514,35 +522,59 @@ __global__ void __launch_bounds__(128) kr_accumulate(ResidualArgs A, const float
     int nj[kMaxNbr]; float In[kMaxNbr];
 #pragma unroll
     for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) { nj[k] = A.slot[A.nbr[p * A.K + k]]; In[k] = A.inten[nj[k]]; }
+    float wt[2] = {0.f, 0.f}; float comp[2][kMaxNbr];
 #pragma unroll
     for (int type = 0; type < 2; ++type) {
+#pragma unroll
+      for (int k = 0; k < kMaxNbr; ++k) comp[type][k] = 0.f;
       const float sw = type == 0 ? A.fixed_w : A.var_w;
       if (!(sw > 0)) continue;
       if (type == 1 && A.obs_count[p] < 2) continue;
       const float* desc = type == 0 ? A.fixed_desc : A.var_desc;
-      float comp[kMaxNbr]; float pr = 0.f;
+      float pr = 0.f;
 #pragma unroll
-      for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) { const float c = (In[k] - Ic) - desc[p * A.K + k]; comp[k] = c; pr += c * c; }
+      for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) { const float c = (In[k] - Ic) - desc[p * A.K + k]; comp[type][k] = c; pr += c * c; }
       pr = sqrtf(pr);
       acc[kNH + kNV + 2 * type] += (double)robust_residual(A.robust, pr);
       acc[kNH + kNV + 2 * type + 1] += 1.0;
-      const float w = sw * robust_weight(A.robust, pr);
-      if (w != 0) {
+      wt[type] = sw * robust_weight(A.robust, pr);
+    }
+    if (!(wt[0] != 0 || wt[1] != 0)) continue;
+    const double ws = (double)wt[0] + (double)wt[1];
 #pragma unroll
-        for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) {
-          float dj[kNV];
+    for (int k = 0; k < kMaxNbr; ++k) if (k < A.K) {
+      float dj[kNV];
 #pragma unroll
-          for (int v = 0; v < kNI; ++v) dj[v] = jK[kNI * (size_t)nj[k] + v] - jc[v];
+      for (int v = 0; v < kNI; ++v) dj[v] = jK[kNI * (size_t)nj[k] + v] - jc[v];
 #pragma unroll
-          for (int v = 0; v < 6; ++v) dj[kNI + v] = jP[6 * (size_t)nj[k] + v] - jc[kNI + v];
-          int e = 0;
+      for (int v = 0; v < 6; ++v) dj[kNI + v] = jP[6 * (size_t)nj[k] + v] - jc[kNI + v];
+      if (F32PROD) {
 #pragma unroll
-          for (int c = 0; c < kNV; ++c)
+        for (int type = 0; type < 2; ++type) {
+          const float w = wt[type];
+          if (w != 0) {
+            int e = 0;
 #pragma unroll
-            for (int r = 0; r <= c; ++r) { acc[e] += (double)((w * dj[r]) * dj[c]); ++e; }
-          const float wr = w * comp[k];
+            for (int c = 0; c < kNV; ++c)
 #pragma unroll
-          for (int v = 0; v < kNV; ++v) acc[kNH + v] += (double)(wr * dj[v]);
+              for (int r = 0; r <= c; ++r) { acc[e] += (double)((w * dj[r]) * dj[c]); ++e; }
+            const float wr = w * comp[type][k];
+#pragma unroll
+            for (int v = 0; v < kNV; ++v) acc[kNH + v] += (double)(wr * dj[v]);
+          }
+        }
+      } else {
+        double d[kNV];
+#pragma unroll
+        for (int v = 0; v < kNV; ++v) d[v] = (double)dj[v];
+        const double wr = (double)wt[0] * (double)comp[0][k] + (double)wt[1] * (double)comp[1][k];
+        int e = 0;
+#pragma unroll
+        for (int c = 0; c < kNV; ++c) {
+          const double t = ws * d[c];
+#pragma unroll
+          for (int r = 0; r <= c; ++r) { acc[e] = fma(t, d[r], acc[e]); ++e; }
+          acc[kNH + c] = fma(wr, d[c], acc[kNH + c]);
         }
       }
     }
@@ -661,6 +693,219 @@ __global__ void __launch_bounds__(128) kr_accumulate_wide(ResidualArgs A, const 
   for (int t = threadIdx.x; t < NOUT; t += blockDim.x) {
     const int src = t < NE ? t : SL * 32 + (t - NE);
     partials[(size_t)blockIdx.x * NOUT + t] = ((sm[0][src] + sm[1][src]) + sm[2][src]) + sm[3][src];
+  }
+}
+
+// K12b = kr_residual_weights + kr_accumulate_blocks: the wide local systems (16, 18 or 24 columns) without shuffles.
+//
+// kr_residual_weights (thread per observation) does the scalar part once: neighbour slots nj[k] (-1 = observation contributes nothing),
+// the merged weight ws = w_f + w_v, the residual factors wr_k = w_f c_f[k] + w_v c_v[k] (fp64; see kr_accumulate) and the residual sums.
+//
+// kr_accumulate_blocks: the local system is cut into column blocks of <= 6 ([4|6|6], [6|6|6] or [6|6|6|6] = intrinsics | rig | pose);
+// a CTA has one warp per block pair (bi <= bj): 6 or 10 warps. Per chunk of 32 observations
+//   1. all threads stage the Jacobian differences dj[k][col] = row(nj[k])[col] - row(centre)[col] (fp32 subtraction as the reference,
+//      :880-905), converted ONCE to fp64, into shared memory as [k][col][observation] — coalesced row reads, every row read once per CTA;
+//   2. warp (bi, bj), lane = observation: acc[r][c] += (ws * dj[bi,r]) * dj[bj,c] (36 DFMA per neighbour), diagonal warps also
+//      b[c] += wr_k * dj[bj,c]. The accumulators (42 doubles) stay in registers for the whole kernel.
+// Slots, weights and rows of the next chunk(s) are prefetched while the current chunk is multiplied, so the gather latency hides
+// behind the DFMAs. Per-CTA partials [NH | NV]; fixed shuffle tree + fixed CTA order => deterministic.
+template <int KN>
+__global__ void __launch_bounds__(256) kr_residual_weights(ResidualArgs A, int* __restrict__ nj_out /* [KN][count] */, double* __restrict__ ws_out,
+                                                           double* __restrict__ wr_out /* [KN][count] */, double* __restrict__ partials /* [grid][4] */) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.count; i += (size_t)gridDim.x * blockDim.x) {
+    int nj[KN]; double wr[KN]; double ws = 0.0;
+#pragma unroll
+    for (int k = 0; k < KN; ++k) { nj[k] = -1; wr[k] = 0.0; }
+    if (A.nb[i]) {
+      const size_t p = A.idx[i];
+      const float Ic = A.inten[i];
+      int sl[KN]; float In[KN], cf[KN], cv[KN];
+#pragma unroll
+      for (int k = 0; k < KN; ++k) { sl[k] = A.slot[A.nbr[p * KN + k]]; In[k] = A.inten[sl[k]]; cf[k] = 0.f; cv[k] = 0.f; }
+      float wf = 0.f, wv = 0.f;
+      if (A.fixed_w > 0) {
+        float pr = 0.f;
+#pragma unroll
+        for (int k = 0; k < KN; ++k) { const float c = (In[k] - Ic) - A.fixed_desc[p * KN + k]; cf[k] = c; pr += c * c; }
+        pr = sqrtf(pr);
+        acc[0] += (double)robust_residual(A.robust, pr); acc[1] += 1.0;
+        wf = A.fixed_w * robust_weight(A.robust, pr);
+      }
+      if (A.var_w > 0 && A.obs_count[p] >= 2) {
+        float pr = 0.f;
+#pragma unroll
+        for (int k = 0; k < KN; ++k) { const float c = (In[k] - Ic) - A.var_desc[p * KN + k]; cv[k] = c; pr += c * c; }
+        pr = sqrtf(pr);
+        acc[2] += (double)robust_residual(A.robust, pr); acc[3] += 1.0;
+        wv = A.var_w * robust_weight(A.robust, pr);
+      }
+      if (wf != 0 || wv != 0) {
+        ws = (double)wf + (double)wv;
+#pragma unroll
+        for (int k = 0; k < KN; ++k) { nj[k] = sl[k]; wr[k] = (double)wf * (double)cf[k] + (double)wv * (double)cv[k]; }
+      }
+    }
+    ws_out[i] = ws;
+#pragma unroll
+    for (int k = 0; k < KN; ++k) { nj_out[(size_t)k * A.count + i] = nj[k]; wr_out[(size_t)k * A.count + i] = wr[k]; }
+  }
+  __shared__ double sm[8][4];
+  double out;
+  block_reduce_d<4>(acc, sm, 256, &out);
+  if (threadIdx.x < 4) partials[(size_t)blockIdx.x * 4 + threadIdx.x] = out;
+}
+
+template <int NI, bool RIG>
+struct BlockCfg {
+  static constexpr int NR = RIG ? 6 : 0, NV = NI + NR + 6, NH = NV * (NV + 1) / 2, NE = NH + NV;
+  static constexpr int B0 = NI == 4 ? 4 : 6;              // length of the first column block; all others are 6
+  static constexpr int NBLK = (NV - B0) / 6 + 1;           // 3 or 4
+  static constexpr int G = NBLK * (NBLK + 1) / 2;          // block pairs = warps per CTA: 6 or 10
+  static constexpr int T = 32 * G;
+  static constexpr int CTAS = G <= 6 ? 2 : 1;              // resident CTAs per SM the register budget is set for
+  static constexpr int EPT = (32 * NV + T - 1) / T;        // staged (observation, column) elements per thread
+  static constexpr int SDS = 33;                           // padded observation stride of the staged differences
+  static constexpr size_t smem(int kn) { return sizeof(double) * (size_t)kn * NV * SDS; }
+};
+
+template <int NI, bool RIG, int KN>
+__global__ void __launch_bounds__(BlockCfg<NI, RIG>::T, BlockCfg<NI, RIG>::CTAS) kr_accumulate_blocks(size_t count, const int* __restrict__ nj_in, const double* __restrict__ ws_in,
+                                                                             const double* __restrict__ wr_in, const float* __restrict__ jK,
+                                                                             const float* __restrict__ jP, const float* __restrict__ jR,
+                                                                             double* __restrict__ partials /* [grid][NE] */) {
+  using C = BlockCfg<NI, RIG>;
+  constexpr int NR = C::NR, NV = C::NV, NH = C::NH, NE = C::NE, B0 = C::B0, T = C::T, EPT = C::EPT, SDS = C::SDS;
+  extern __shared__ double sd[];                           // [KN][NV][SDS]
+  const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+  int bj = 0;
+  while ((bj + 1) * (bj + 2) / 2 <= g) ++bj;
+  const int bi = g - bj * (bj + 1) / 2;                    // pairs in column-major upper order: (0,0) (0,1) (1,1) (0,2) ...
+  const int ca = bi == 0 ? 0 : B0 + 6 * (bi - 1), cb = bj == 0 ? 0 : B0 + 6 * (bj - 1);
+  const int la = (B0 != 6 && bi == 0) ? B0 : 6, lb = (B0 != 6 && bj == 0) ? B0 : 6;
+  const bool diag = bi == bj;
+  double acc[36], accb[6];
+#pragma unroll
+  for (int e = 0; e < 36; ++e) acc[e] = 0.0;
+#pragma unroll
+  for (int e = 0; e < 6; ++e) accb[e] = 0.0;
+
+  int eo[EPT], ecol[EPT];                                  // this thread's staged elements: observation within the chunk, local column
+#pragma unroll
+  for (int j = 0; j < EPT; ++j) { const int e = tid + j * T; eo[j] = e < 32 * NV ? e / NV : -1; ecol[j] = e % NV; }
+  auto row = [&](int col, size_t slot) -> float {
+    if (col < NI) return jK[(size_t)NI * slot + col];
+    if (RIG && col < NI + NR) return jR[6 * slot + (col - NI)];
+    return jP[6 * slot + (col - NI - NR)];
+  };
+  const size_t nchunks = (count + 31) / 32, stride = gridDim.x;
+  // Software pipeline over this CTA's chunks c, c + stride, ...: slots travel global -> register (one per thread) -> s_nj two chunks
+  // ahead, weights global -> register -> s_w one chunk ahead, rows global -> registers (issued right after the first barrier, consumed
+  // at the top of the next iteration), so every global load has a whole multiply phase to land.
+  __shared__ int s_nj[KN][32];
+  __shared__ double s_w[KN + 1][32];                       // [0] = ws, [1 + k] = wr_k
+  float rw[EPT][KN + 1]; bool rv[EPT];
+  const int sk = tid >> 5;                                 // this thread's (k, observation) = (sk, lane) of the slot / weight planes
+  auto load_nj = [&](size_t chunk) -> int {
+    const size_t i = chunk * 32 + lane;
+    return (sk < KN && chunk < nchunks && i < count) ? nj_in[(size_t)sk * count + i] : -1;
+  };
+  auto load_w = [&](size_t chunk) -> double {
+    const size_t i = chunk * 32 + lane;
+    if (!(sk <= KN && chunk < nchunks && i < count)) return 0.0;
+    return sk == 0 ? ws_in[i] : wr_in[(size_t)(sk - 1) * count + i];
+  };
+  auto load_rows = [&](size_t chunk) {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      rv[j] = false;
+      if (eo[j] >= 0 && chunk < nchunks) {
+        const int n0 = s_nj[0][eo[j]];
+        if (n0 >= 0) {
+          rv[j] = true;
+          rw[j][KN] = row(ecol[j], chunk * 32 + (size_t)eo[j]);
+          rw[j][0] = row(ecol[j], (size_t)n0);
+#pragma unroll
+          for (int k = 1; k < KN; ++k) rw[j][k] = row(ecol[j], (size_t)s_nj[k][eo[j]]);
+        }
+      }
+    }
+  };
+
+  size_t c = blockIdx.x;
+  if (sk < KN) s_nj[sk][lane] = load_nj(c);
+  __syncthreads();
+  load_rows(c);
+  int njreg = load_nj(c + stride);
+  double wreg = load_w(c);
+  __syncthreads();
+  for (; c < nchunks; c += stride) {
+    // stage chunk c: fp32 difference (as the reference), one conversion per element; publish slots(c + stride) and weights(c)
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      if (eo[j] >= 0) {
+#pragma unroll
+        for (int k = 0; k < KN; ++k) sd[(k * NV + ecol[j]) * SDS + eo[j]] = rv[j] ? (double)(rw[j][k] - rw[j][KN]) : 0.0;
+      }
+    }
+    if (sk < KN) s_nj[sk][lane] = njreg;
+    if (sk <= KN) s_w[sk][lane] = wreg;
+    __syncthreads();
+    load_rows(c + stride);
+    njreg = load_nj(c + 2 * stride);
+    wreg = load_w(c + stride);
+    // multiply chunk c
+    const double ws = s_w[0][lane];
+    if (__any_sync(0xffffffffu, ws != 0.0)) {
+#pragma unroll
+      for (int k = 0; k < KN; ++k) {
+        double a[6], b[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) a[r] = r < la ? sd[(k * NV + ca + r) * SDS + lane] : 0.0;
+        if (diag) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) b[r] = a[r];
+        } else {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) b[r] = r < lb ? sd[(k * NV + cb + r) * SDS + lane] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const double t = ws * a[r];
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) acc[r * 6 + cc] = fma(t, b[cc], acc[r * 6 + cc]);
+        }
+        if (diag) {
+          const double wrk = s_w[1 + k][lane];
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) accb[cc] = fma(wrk, b[cc], accb[cc]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // lanes -> warp with a fixed shuffle tree; lane 0 of warp (bi, bj) owns the entries of its block pair
+#pragma unroll
+  for (int e = 0; e < 36; ++e)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+#pragma unroll
+  for (int e = 0; e < 6; ++e)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) accb[e] += __shfl_xor_sync(0xffffffffu, accb[e], o);
+  if (lane == 0) {
+    double* out = partials + (size_t)blockIdx.x * NE;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) {
+        const int R = ca + r, Cc = cb + cc;
+        if (r < la && cc < lb && R <= Cc) out[Cc * (Cc + 1) / 2 + R] = acc[r * 6 + cc];
+      }
+    if (diag) {
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) if (cc < lb) out[NH + cb + cc] = accb[cc];
+    }
   }
 }
 
