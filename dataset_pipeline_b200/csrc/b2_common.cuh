@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -29,21 +30,56 @@ inline int set_error(int code, const char* fmt, ...) {
   } while (0)
 #define B2_TRY(expr) do { int _rc = (expr); if (_rc != B2_OK) return _rc; } while (0)
 
-// ---- grow-only device buffer ----------------------------------------------------------------------------------
+// ---- grow-only device buffer, carved from the device's stream-ordered memory pool ---------------------------------
+// A handle owns GBs of index / direction / record buffers; with plain cudaMalloc / cudaFree a create -> add clouds -> run -> destroy
+// cycle spent more time mapping and unmapping memory than computing. The device's default pool is told to keep what is freed
+// (release threshold = max), so every cycle after the first re-uses the same physical memory. Semantics stay those of
+// cudaMalloc / cudaFree: memory returned by ensure() is usable on any stream at once, release() waits for the device first.
+// B2_POOL=0 restores cudaMalloc / cudaFree (A/B runs, memory debugging tools).
+inline bool pool_enabled() {
+  static const bool on = [] { const char* e = std::getenv("B2_POOL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+inline void pool_retain(int dev) {
+  static bool done[64] = {};
+  if (dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[dev] = true;
+}
+inline cudaError_t dev_alloc(void** p, size_t bytes) {
+  if (!pool_enabled()) return cudaMalloc(p, bytes);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  pool_retain(dev);
+  cudaError_t e = cudaMallocAsync(p, bytes, cudaStreamPerThread);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
+  return e;
+}
+inline void dev_free(void* p) {
+  if (!p) return;
+  if (!pool_enabled()) { cudaFree(p); return; }
+  cudaDeviceSynchronize();                         // cudaFree's implicit guarantee: nothing in flight still uses the block
+  cudaFreeAsync(p, cudaStreamPerThread);
+}
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   int ensure(size_t bytes) {
     if (bytes <= cap) return B2_OK;
-    if (p) cudaFree(p);
+    if (p) dev_free(p);
     p = nullptr; cap = 0;
     const size_t want = bytes + bytes / 8 + 256;   // slack so small growth does not re-allocate
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) return set_error(B2_ERR_ALLOC, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    cudaError_t e = dev_alloc(&p, want);
+    if (e != cudaSuccess) return set_error(B2_ERR_ALLOC, "device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
     cap = want;
     return B2_OK;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p) dev_free(p); p = nullptr; cap = 0; }
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 

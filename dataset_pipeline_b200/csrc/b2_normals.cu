@@ -19,96 +19,12 @@
 #include <cmath>
 #include <vector>
 
+#include "b2_bvh.cuh"
 #include "b2_common.cuh"
 
 namespace b2 {
 
-static constexpr int kLeaf = 8;
 static constexpr int kKnnThreads = 128;
-
-
-__global__ void __launch_bounds__(256) kn_bbox(const float* __restrict__ xyz, size_t n, float* __restrict__ partial) {
-  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    for (int d = 0; d < 3; ++d) { const float v = xyz[3 * i + d]; mn[d] = fminf(mn[d], v); mx[d] = fmaxf(mx[d], v); }
-  for (int o = 16; o > 0; o >>= 1)
-    for (int d = 0; d < 3; ++d) {
-      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o)); mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
-    }
-  __shared__ float s[8][6];
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) for (int d = 0; d < 3; ++d) { s[w][d] = mn[d]; s[w][3 + d] = mx[d]; }
-  __syncthreads();
-  if (threadIdx.x < 6) {
-    float v = s[0][threadIdx.x];
-    for (int i = 1; i < 8; ++i) v = threadIdx.x < 3 ? fminf(v, s[i][threadIdx.x]) : fmaxf(v, s[i][threadIdx.x]);
-    partial[blockIdx.x * 6 + threadIdx.x] = v;
-  }
-}
-
-__device__ __forceinline__ unsigned long long spread21(unsigned long long v) {
-  v &= 0x1FFFFFull;
-  v = (v | (v << 32)) & 0x1F00000000FFFFull;
-  v = (v | (v << 16)) & 0x1F0000FF0000FFull;
-  v = (v | (v << 8)) & 0x100F00F00F00F00Full;
-  v = (v | (v << 4)) & 0x10C30C30C30C30C3ull;
-  v = (v | (v << 2)) & 0x1249249249249249ull;
-  return v;
-}
-
-__global__ void __launch_bounds__(256) kn_morton(const float* __restrict__ xyz, size_t n, float ox, float oy, float oz, float scale,
-                                                 unsigned long long* __restrict__ keys, unsigned int* __restrict__ idx) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float m = 2097151.f;
-  const unsigned int x = (unsigned int)fminf(fmaxf((xyz[3 * i] - ox) * scale, 0.f), m);
-  const unsigned int y = (unsigned int)fminf(fmaxf((xyz[3 * i + 1] - oy) * scale, 0.f), m);
-  const unsigned int z = (unsigned int)fminf(fmaxf((xyz[3 * i + 2] - oz) * scale, 0.f), m);
-  keys[i] = spread21(x) | (spread21(y) << 1) | (spread21(z) << 2);
-  idx[i] = (unsigned int)i;
-}
-
-__global__ void __launch_bounds__(256) kn_gather(const float* __restrict__ xyz, size_t n, const unsigned int* __restrict__ perm,
-                                                 float4* __restrict__ s_xyz) {
-  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const unsigned int i = perm[j];
-  s_xyz[j] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], __uint_as_float(i));
-}
-
-__global__ void __launch_bounds__(256) kn_leaf_aabb(const float4* __restrict__ s_xyz, size_t n, unsigned int nleaf, Aabb* __restrict__ nodes) {
-  const unsigned int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= nleaf) return;
-  Aabb b; for (int d = 0; d < 3; ++d) { b.lo[d] = INFINITY; b.hi[d] = -INFINITY; }
-  const size_t e = min(n, (size_t)(l + 1) * kLeaf);
-  for (size_t p = (size_t)l * kLeaf; p < e; ++p) {
-    const float4 v = s_xyz[p];
-    b.lo[0] = fminf(b.lo[0], v.x); b.lo[1] = fminf(b.lo[1], v.y); b.lo[2] = fminf(b.lo[2], v.z);
-    b.hi[0] = fmaxf(b.hi[0], v.x); b.hi[1] = fmaxf(b.hi[1], v.y); b.hi[2] = fmaxf(b.hi[2], v.z);
-  }
-  nodes[l] = b;
-}
-
-__global__ void __launch_bounds__(256) kn_merge_level(const Aabb* __restrict__ child, unsigned int nchild, Aabb* __restrict__ parent,
-                                                      unsigned int nparent) {
-  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nparent) return;
-  Aabb b = child[2 * i];
-  if (2 * i + 1 < nchild) {
-    const Aabb c = child[2 * i + 1];
-    for (int d = 0; d < 3; ++d) { b.lo[d] = fminf(b.lo[d], c.lo[d]); b.hi[d] = fmaxf(b.hi[d], c.hi[d]); }
-  }
-  parent[i] = b;
-}
-
-static constexpr int kMaxLevels = 32;
-struct BvhLevels { unsigned int offset[kMaxLevels]; unsigned int count[kMaxLevels]; int nlevels; };
-
-__device__ __forceinline__ float dist2_pt(const float4& q, const float4& t) {
-  const float dx = fsub(q.x, t.x), dy = fsub(q.y, t.y), dz = fsub(q.z, t.z);
-  return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
-}
-__device__ __forceinline__ float dist2_box(const float4& q, const Aabb& b) { return dist2_box(q.x, q.y, q.z, b); }
 
 // k-best list of one thread in shared memory, element e of thread t at [e * kKnnThreads + t] (conflict-free).
 struct KBest {
@@ -254,7 +170,7 @@ kn_knn_normals(const float4* __restrict__ s_xyz, size_t n, const Aabb* __restric
   for (unsigned int l = l0; l <= l1; ++l) scan_leaf(h, q, l, n, s_xyz);
 
   // near-first depth-first walk from the root; entries are (level << 27 | index)
-  unsigned int stack[kMaxLevels + 2];
+  unsigned int stack[kBvhMaxLevels + 2];
   int sp = 0;
   stack[sp++] = ((unsigned int)(lv.nlevels - 1) << 27);
   while (sp > 0) {
@@ -304,27 +220,6 @@ kn_knn_normals(const float4* __restrict__ s_xyz, size_t n, const Aabb* __restric
 // ---- radius mode (setRadiusSearch): every point with d2 < r2, in (d2, index) order --------------------------------------------
 // Three kernels per batch of Morton-sorted queries: count -> (scan) -> fill keys ((d2 bits << 32) | original index, value = sorted
 // position) -> (segmented radix sort: for non-negative floats the bit pattern orders like the value) -> normals.
-template <typename F>
-__device__ __forceinline__ void radius_visit(const float4& q, float r2, const float4* __restrict__ s_xyz, size_t n, const Aabb* __restrict__ nodes,
-                                             const BvhLevels& lv, F&& f) {
-  unsigned int stack[2 * kMaxLevels + 2];
-  int sp = 0;
-  stack[sp++] = ((unsigned int)(lv.nlevels - 1) << 27);
-  while (sp > 0) {
-    const unsigned int e = stack[--sp];
-    const int level = (int)(e >> 27);
-    const unsigned int i = e & 0x7FFFFFFu;
-    if (dist2_box(q, nodes[lv.offset[level] + i]) >= r2) continue;    // bound <= every d2 inside (monotone fp32), and the test is strict
-    if (level == 0) {
-      const size_t b = (size_t)i * kLeaf, e2 = min(n, b + kLeaf);
-      for (size_t p = b; p < e2; ++p) { const float4 t = __ldg(&s_xyz[p]); const float d = dist2_pt(q, t); if (d < r2) f(d, (unsigned int)p, __float_as_uint(t.w)); }
-      continue;
-    }
-    const unsigned int c0 = 2 * i, c1 = 2 * i + 1;
-    stack[sp++] = ((unsigned int)(level - 1) << 27) | c0;
-    if (c1 < lv.count[level - 1]) stack[sp++] = ((unsigned int)(level - 1) << 27) | c1;
-  }
-}
 __global__ void __launch_bounds__(128) kn_radius_count(const float4* __restrict__ s_xyz, size_t n, const Aabb* __restrict__ nodes, BvhLevels lv, float r2,
                                                        size_t q_begin, size_t q_end, unsigned int* __restrict__ counts) {
   const size_t j = q_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
