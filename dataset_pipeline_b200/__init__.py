@@ -8,3 +8,4 @@ from . import _lib  # noqa: F401
 from .icp import Comm, PointToPlaneICP, find_correspondences  # noqa: F401
 from .normals import NormalEstimationTwoPassOMP, estimate_normals, estimate_normals_radius  # noqa: F401
 from .registration import Registration  # noqa: F401
+from .multiscale import CreateMultiScalePointCloud, DeterminePointNeighbors, MergeClosePoints  # noqa: F401

@@ -70,6 +70,9 @@ EXPORTS = [
     "b2_icp_run",
     "b2_icp_set_pose",
     "b2_last_error",
+    "b2_ms_create",
+    "b2_ms_merge_close_points",
+    "b2_ms_point_neighbors",
     "b2_normals_estimate",
     "b2_normals_estimate_dist",
     "b2_normals_estimate_radius",

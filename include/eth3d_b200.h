@@ -164,6 +164,39 @@ int b2_normals_estimate_radius(const float* xyz, size_t n, size_t stride_bytes, 
                                float* out_nxyz_curv, int32_t* out_neighbor_count, int* is_dense);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Multi-resolution point cloud — the producer of Path B's point scales and neighbour indices.
+ * Replaces opt::MergeClosePoints (src/opt/multi_scale_point_cloud.cc:44-124), the scale loop of
+ * opt::CreateMultiScalePointCloud (:263-368) and opt::Problem::DeterminePointNeighbors (src/opt/problem.cc:706-786) as driven by
+ * Problem::AddPointCloud... (problem.cc:161-362). Host buffers in and out; colours are the grey values of PreprocessScans (:186-212).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct b2_ms_stats {
+  uint64_t neighbor_pairs;   /* (i, j > i) pairs closer than the merge distance, summed over the scales */
+  int32_t rounds;            /* dependency rounds of the centre selection, summed over the scales */
+  int32_t scales;
+  float ms_device;           /* device time of the merges (CUDA events) */
+} b2_ms_stats;
+/* MergeClosePoints: in index order a point not yet merged becomes a centre and averages ALL points with squared distance
+ * < (float)((double)merge_distance^2) (radiusSearch order: by distance, ties to the lower index): position = fp32 sum / count; colour =
+ * mean over the scan contributing most points (the first to reach the maximal count); max_radius = maximum; every merged point is
+ * marked done. Outputs sized for n points; *out_n = merged points. num_scans <= 32. stats nullable. */
+int b2_ms_merge_close_points(const float* xyz, size_t n, const float* colors, const uint8_t* scan_indices, const float* max_radius, int num_scans,
+                             float merge_distance, float* out_xyz, float* out_colors, uint8_t* out_scan_indices, float* out_max_radius, size_t* out_n,
+                             b2_ms_stats* stats);
+/* CreateMultiScalePointCloud after ComputeMinMaxPointRadius: min_radius / max_radius per point (+inf / -inf where no image observes the
+ * point). radius_0 = min(min_radius) * min_radius_bias, doubled per scale until radius >= 0.99 * max(max_radius); scale s merges, at
+ * distance merge_distance_factor * radius_s, the survivors of scale s-1 (radius_s <= their max_radius) followed by the input points whose
+ * min_radius was passed. Outputs concatenated over the scales (out_capacity points in total); out_radius / out_counts hold max_scales. */
+int b2_ms_create(const float* xyz, size_t n, const float* colors, const uint8_t* scan_indices, const float* min_radius, const float* max_radius,
+                 int num_scans, float min_radius_bias, float merge_distance_factor, int max_scales, size_t out_capacity, int* out_scale_count,
+                 float* out_radius, uint64_t* out_counts, float* out_xyz, float* out_colors, uint8_t* out_scan_indices, b2_ms_stats* stats);
+/* DeterminePointNeighbors: the candidate_count nearest other points (nearestKSearch of candidate_count + 1 incl. the point itself, among
+ * the points of the same scan when limit_neighbors_to_same_scan_index), shuffled by std::shuffle with one std::mt19937(0) for the whole
+ * call (libstdc++ 9 algorithm, the reference's toolchain), first neighbor_count kept. out: n x neighbor_count (size_t in the reference).
+ * B2_ERR_STATE where the reference CHECKs (too few points per scan; a point that is not its own nearest neighbour). */
+int b2_ms_point_neighbors(const float* xyz, size_t n, const uint8_t* scan_indices, int scan_count, int limit_neighbors_to_same_scan_index,
+                          int candidate_count, int neighbor_count, uint64_t* out_neighbor_indices);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Path B — dense photometric image<->scan alignment (tool ImageRegistrator).
  * Replaces, behind one handle, the pieces opt::Optimizer drives on an opt::Problem (src/opt/optimizer.h:36-57,
  * optimizer.cc:49-190): VisibilityEstimator::CreateObservationsForAllImages + DetermineIfAllNeighborsAreObserved

@@ -219,6 +219,63 @@ def normals_radius(xyz, radius, viewpoint=(0.0, 0.0, 0.0), return_counts=False):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# Multi-resolution point cloud (orc_multiscale.cc)
+# ---------------------------------------------------------------------------------------------------------------------
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def ms_merge_close_points(xyz, colors, scan_indices, max_radius, num_scans, merge_distance):
+    """MergeClosePoints (multi_scale_point_cloud.cc:44-124) -> (xyz, colors, scan_indices, max_radius) of the merged cloud."""
+    x = _c32(xyz); c = _c32(colors); m = _c32(max_radius); s = np.ascontiguousarray(scan_indices, np.uint8)
+    n = x.shape[0]
+    ox = np.zeros((n, 3), np.float32); oc = np.zeros(n, np.float32); om = np.zeros(n, np.float32); os_ = np.zeros(n, np.uint8)
+    L = lib()
+    L.orc_ms_merge_close_points.restype = C.c_uint64
+    L.orc_ms_merge_close_points.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.c_int,
+                                            C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_float)]
+    k = int(L.orc_ms_merge_close_points(_f(x), n, _f(c), _u8(s), _f(m), int(num_scans), float(merge_distance), _f(ox), _f(oc), _u8(os_), _f(om)))
+    return ox[:k].copy(), oc[:k].copy(), os_[:k].copy(), om[:k].copy()
+
+
+def ms_create(xyz, colors, scan_indices, min_radius, max_radius, num_scans, min_radius_bias=1.05, merge_distance_factor=4.0, max_scales=32):
+    """CreateMultiScalePointCloud's scale loop (multi_scale_point_cloud.cc:263-368) -> list of (radius, xyz, colors, scan_indices)."""
+    x = _c32(xyz); c = _c32(colors); lo = _c32(min_radius); hi = _c32(max_radius); s = np.ascontiguousarray(scan_indices, np.uint8)
+    n = x.shape[0]
+    cap = max(1, n) * max_scales
+    rad = np.zeros(max_scales, np.float32); cnt = np.zeros(max_scales, np.uint64)
+    ox = np.zeros((cap, 3), np.float32); oc = np.zeros(cap, np.float32); os_ = np.zeros(cap, np.uint8)
+    L = lib()
+    L.orc_ms_create.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                C.c_int, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_float),
+                                C.POINTER(C.c_float), C.POINTER(C.c_uint8)]
+    k = L.orc_ms_create(_f(x), n, _f(c), _u8(s), _f(lo), _f(hi), int(num_scans), float(min_radius_bias), float(merge_distance_factor), int(max_scales),
+                        _f(rad), cnt.ctypes.data_as(C.POINTER(C.c_uint64)), _f(ox), _f(oc), _u8(os_))
+    if k < 0:
+        raise RuntimeError("orc_ms_create: more than %d scales" % max_scales)
+    out, off = [], 0
+    for i in range(k):
+        m = int(cnt[i])
+        out.append((float(rad[i]), ox[off:off + m].copy(), oc[off:off + m].copy(), os_[off:off + m].copy()))
+        off += m
+    return out
+
+
+def ms_point_neighbors(xyz, scan_indices, scan_count, limit_to_same_scan, candidate_count=25, neighbor_count=5):
+    """Problem::DeterminePointNeighbors (problem.cc:706-786) -> (n, neighbor_count) uint64."""
+    x = _c32(xyz); s = np.ascontiguousarray(scan_indices, np.uint8)
+    n = x.shape[0]
+    out = np.zeros((n, neighbor_count), np.uint64)
+    L = lib()
+    L.orc_ms_point_neighbors.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    rc = L.orc_ms_point_neighbors(_f(x), n, _u8(s), int(scan_count), int(bool(limit_to_same_scan)), int(candidate_count), int(neighbor_count),
+                                  out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    if rc != 0:
+        raise RuntimeError("orc_ms_point_neighbors failed (%d): too few points per scan or no self-match" % rc)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # Path B (orc_reg.cc)
 # ---------------------------------------------------------------------------------------------------------------------
 class RegParams(C.Structure):

@@ -116,6 +116,16 @@ int orc_interp_bilinear(const uint8_t* img, int w, int h, float x, float y, floa
 void orc_interp_trilinear(const uint8_t* img0, int w0, int h0, const uint8_t* img1, float x, float y, float z, float* v, float* dx, float* dy, float* dz);
 float orc_robust(int type, float p, float r, int weight);
 
+/* ---- multi-resolution point cloud (orc_multiscale.cc): MergeClosePoints, CreateMultiScalePointCloud's scale loop,
+ * Problem::DeterminePointNeighbors ---- */
+uint64_t orc_ms_merge_close_points(const float* xyz, size_t n, const float* colors, const uint8_t* scan, const float* max_radius, int num_scans,
+                                   float merge_distance, float* oxyz, float* ocol, uint8_t* oscan, float* omaxr);
+int orc_ms_create(const float* xyz, size_t n, const float* colors, const uint8_t* scan, const float* min_radius, const float* max_radius,
+                  int num_scans, float min_radius_bias, float merge_distance_factor, int max_scales, float* out_radius, uint64_t* out_counts,
+                  float* oxyz, float* ocol, uint8_t* oscan);
+int orc_ms_point_neighbors(const float* xyz, size_t n, const uint8_t* scan, int scan_count, int limit_to_same_scan, int candidate_count,
+                           int neighbor_count, uint64_t* out);
+
 /* ---- camera models (orc_camera.h) ---- */
 int orc_cam_param_count(int type);   /* -1 unsupported */
 /* constructs the camera (runs the cut-off search as the reference constructors do); out[0] = radius_cutoff_squared of the
