@@ -270,10 +270,10 @@ def run_b200(args):
         dist.broadcast(idt, 0)
         comm = b2.Comm(rank, world, bytes(idt.cpu().numpy().tobytes()), device=local)
 
-    def make():
+    def make(start_poses=None):
         g = b2.PointToPlaneICP(device=local, rank=rank, world_size=world, allreduce=allreduce if (world > 1 and comm is None) else None,
                                stream=stream.cuda_stream, comm=comm)
-        for (px, pn), T in zip(clouds, poses):
+        for (px, pn), T in zip(clouds, start_poses if start_poses is not None else poses):
             g.AddPointCloud(px.numpy(), pn.numpy(), T)
         return g
 
@@ -316,13 +316,17 @@ def run_b200(args):
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            ge = make()
-            ge.Run(args.d, 0, 1, thr, False)
+            ge = make(final_poses)          # the same kind of iteration as the timed ones: the alignment state after warm-up + steps
+            t1 = time.perf_counter()
+            ge.Run(args.d, args.warmup + args.steps, 1, thr, False)
+            t2 = time.perf_counter()
             _ = [ge.GetResultGlobalTCloud(i) for i in range(NS)]
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             st_e = ge.stats()
             ge.close()
+            parts = {"create_and_upload_ms": 1e3 * (t1 - t0), "run_ms": 1e3 * (t2 - t1), "run_device_ms": st_e["ms_total"], "destroy_ms": 1e3 * (time.perf_counter() - t0 - dt),
+                     "run_phases_ms": {k: st_e["ms_" + k] for k in ("index", "search", "pack", "inner")}, "passes": st_e["passes"]}
             if world > 1:
                 t = torch.tensor([dt], device="cuda", dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -332,7 +336,7 @@ def run_b200(args):
         nv = 6 * (NS - 1)
         d2h = st_e["passes"] * (nv * nv + nv + 3) * 8 + NS * 2 * 148 * 6 * 4 + 8 * NS * (NS - 1) + 4 * NS
         e2e = {"value": len(times) / sum(times), "unit": UNIT, "h2d_bytes_per_step": int(npts * 24), "d2h_bytes_per_step": int(d2h),
-               "steps": len(times), "note": "each step: b2_icp_create + 8 x b2_icp_add_cloud from pinned host memory + b2_icp_run(1 iteration) + b2_icp_get_pose + destroy"}
+               "steps": len(times), "last_step_breakdown": parts, "h2d_gb_per_s_in_upload": npts * 24 / 1e9 / max(parts["create_and_upload_ms"] * 1e-3, 1e-9), "note": "each step: b2_icp_create + 8 x b2_icp_add_cloud from pinned host memory (poses = the state the timed iterations ended in) + b2_icp_run(1 iteration) + b2_icp_get_pose + destroy"}
 
     if rank != 0:
         if world > 1:

@@ -99,6 +99,7 @@ EXPORTS = [
     "b2_reg_image_owner",
     "b2_reg_initialize",
     "b2_reg_last_stats",
+    "b2_reg_min_max_point_radius",
     "b2_reg_num_observations",
     "b2_reg_num_variables",
     "b2_reg_render_depth",

@@ -264,6 +264,54 @@ __global__ void __launch_bounds__(256) kr_cutoff_final(const CutoffPoint* __rest
   if (threadIdx.x == 0) out[k] = fminf(smx[0] * 1.01f, smn[0]);
 }
 
+// Undistort(distorted) — camera_base_impl.h:251-253 (IterativeUndistort started at the distorted point itself), camera_pinhole.h:65-68
+// (identity), camera_base_impl_fisheye.h:80-91 (inner Undistort, then r -> tan r; tanf is the device's, within an ulp or two of glibc's).
+__device__ __forceinline__ void cam_undistort(const Cam& c, float tx, float ty, float* ox, float* oy) {
+  float ux = tx, uy = ty;
+  if (c.type != kCamPinhole) {
+    for (int i = 0; i < 100; ++i) {
+      float qx, qy; tp_distort(c.d, ux, uy, &qx, &qy);
+      const float ex = qx - tx, ey = qy - ty;
+      if (ex * ex + ey * ey < 1e-10f) break;
+      float J[4]; tp_deriv(c.d, ux, uy, J);
+      const float a = J[0] * J[0] + J[2] * J[2], b = J[0] * J[1] + J[2] * J[3], cc = J[1] * J[0] + J[3] * J[2], dd = J[1] * J[1] + J[3] * J[3];
+      const float invdet = 1.f / (a * dd - cc * b);
+      const float i00 = dd * invdet, i10 = -cc * invdet, i01 = -b * invdet, i11 = a * invdet;
+      const float m00 = i00 * J[0] + i01 * J[2], m01 = i00 * J[1] + i01 * J[3];
+      const float m10 = i10 * J[0] + i11 * J[2], m11 = i10 * J[1] + i11 * J[3];
+      ux -= m00 * ex + m01 * ey;
+      uy -= m10 * ex + m11 * ey;
+    }
+  }
+  if (c.type == kCamBenchmark) {
+    const float r = sqrtf(ux * ux + uy * uy);
+    const float factor = (r < 1e-6f) ? 1.f : (r > 1.57079637f) ? INFINITY : tanf(r) / r;      // M_PI / 2.f rounds to 1.57079637f
+    ux = factor * ux; uy = factor * uy;
+  }
+  *ox = ux; *oy = uy;
+}
+// InitializeUndistortionLookup (camera_base_impl.h:255-269): one thread per pixel, table[y * w + x] = Undistort(k_inv * (x, y)).
+__global__ void __launch_bounds__(128) kr_undistortion_lookup(Cam cam, float2* __restrict__ table) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)cam.w * cam.h) return;
+  const int x = (int)(i % cam.w), y = (int)(i / cam.w);
+  float ux, uy; cam_undistort(cam, cam.fx_inv * x + cam.cx_inv, cam.fy_inv * y + cam.cy_inv, &ux, &uy);
+  table[i] = make_float2(ux, uy);
+}
+// ImageToNormalized(pixel_position) (camera_base_impl.h:187-212; camera_pinhole.h:60-63 for pinhole). The reference reads one row past the
+// table when the clamped y is exactly h - 1 (weight 0): read the last row instead.
+__device__ __forceinline__ void cam_image_to_normalized(const Cam& c, const float2* __restrict__ table, float px, float py, float* ox, float* oy) {
+  if (c.type == kCamPinhole) { *ox = c.fx_inv * px + c.cx_inv; *oy = c.fy_inv * py + c.cy_inv; return; }
+  const float cxp = fmaxf(fminf(px, c.w - 1.001f), 0.f), cyp = fmaxf(fminf(py, c.h - 1.00f), 0.f);
+  const int ix = (int)cxp, iy = (int)cyp;
+  const float fx_ = cxp - (float)ix, fy_ = cyp - (float)iy;
+  const int ix1 = min(ix + 1, c.w - 1), iy1 = min(iy + 1, c.h - 1);
+  const float2 tl = __ldg(&table[(size_t)iy * c.w + ix]), tr = __ldg(&table[(size_t)iy * c.w + ix1]);
+  const float2 bl = __ldg(&table[(size_t)iy1 * c.w + ix]), br = __ldg(&table[(size_t)iy1 * c.w + ix1]);
+  *ox = (1 - fy_) * ((1 - fx_) * tl.x + fx_ * tr.x) + fy_ * ((1 - fx_) * bl.x + fx_ * br.x);
+  *oy = (1 - fy_) * ((1 - fx_) * tl.y + fx_ * tr.y) + fy_ * ((1 - fx_) * bl.y + fx_ * br.y);
+}
+
 // op 1: NormalizedToImage (n x 2 -> n x 2), 2: ImageDerivativeByWorld (n x 3 -> n x 6), 3: ImageDerivativeByIntrinsics (n x 3 -> n x 2np)
 __global__ void __launch_bounds__(128) kr_camera_eval(Cam cam, int op, const float* __restrict__ in, size_t n, float* __restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -24,7 +24,11 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "b2_bvh.cuh"
@@ -326,50 +330,78 @@ static int merge_device(MsScratch& S, const MsCloud& in, float merge_distance, i
   return B2_OK;
 }
 
-// libstdc++ 9 (the reference's toolchain, Dockerfile: Ubuntu 20.04) std::shuffle for a 32-bit engine: one draw yields two swap
-// positions while range^2 fits the engine's range; uniform_int_distribution scales the engine output down and rejects the tail.
+// std::mt19937 + libstdc++ 9 (the reference's toolchain, Dockerfile: Ubuntu 20.04) std::shuffle for a 32-bit engine: one draw yields two
+// swap positions while range^2 fits the engine's range; uniform_int_distribution scales the engine output down (scaling = 2^32-1 / range)
+// and rejects the tail (v >= range * scaling). The engine is one sequential stream over ALL points of a call, so the work is split:
+//   * sequential: draw the accepted engine outputs of every point (a compare per output; rejections are ~1e-7 per draw but shift the
+//     stream, so they must be replayed exactly);
+//   * parallel (host threads): turn the accepted outputs into swap positions and apply them to the neighbour lists.
 struct Mt19937 {
   uint32_t mt[624]; int idx;
   explicit Mt19937(uint32_t seed) { mt[0] = seed; for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i; idx = 624; }
-  uint32_t next() {
-    if (idx >= 624) {
-      for (int i = 0; i < 624; ++i) {
-        const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
-        mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-      }
-      idx = 0;
-    }
+  static inline uint32_t twist(uint32_t u, uint32_t v, uint32_t m) { const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu); return m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+  void refill() {
+    int i = 0;
+    for (; i < 624 - 397; ++i) mt[i] = twist(mt[i], mt[i + 1], mt[i + 397]);
+    for (; i < 623; ++i) mt[i] = twist(mt[i], mt[i + 1], mt[i + 397 - 624]);
+    mt[623] = twist(mt[623], mt[0], mt[396]);
+    idx = 0;
+  }
+  inline uint32_t next() {
+    if (idx >= 624) refill();
     uint32_t y = mt[idx++];
     y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
     return y;
   }
-  uint64_t below(uint64_t range) {                    // uniform in [0, range)
-    const uint64_t span = 0xFFFFFFFFull;
-    if (span > range - 1) {
-      const uint64_t scaling = span / range, past = range * scaling;
-      uint64_t v;
-      do v = next(); while (v >= past);
-      return v / scaling;
-    }
-    return (uint64_t)next() % range;
-  }
-  void shuffle(int32_t* first, int32_t* last) {
-    const uint64_t len = (uint64_t)(last - first);
-    if (len < 2) return;
-    if (0xFFFFFFFFull / len >= len) {
-      int32_t* it = first + 1;
-      if ((len % 2) == 0) { std::swap(*it, first[below(2)]); ++it; }
-      while (it != last) {
-        const uint64_t a = (uint64_t)(it - first) + 1, b = a + 1;
-        const uint64_t x = below(a * b);
-        std::swap(*it, first[x / b]); ++it;
-        std::swap(*it, first[x % b]); ++it;
-      }
-      return;
-    }
-    for (int32_t* it = first + 1; it != last; ++it) std::swap(*it, first[below((uint64_t)(it - first) + 1)]);
-  }
 };
+
+// The draws std::shuffle makes for a list of `len` elements: draw d has `range` outcomes and moves one (b == 0) or two elements.
+struct ShuffleDraw { uint64_t range, scaling, past, b; int pos; };
+static std::vector<ShuffleDraw> shuffle_plan(uint64_t len) {
+  std::vector<ShuffleDraw> plan;
+  auto add = [&](uint64_t range, uint64_t b, int pos) {
+    ShuffleDraw d; d.range = range; d.b = b; d.pos = pos;
+    d.scaling = 0xFFFFFFFFull / range; d.past = range * d.scaling;       // urngrange = 2^32 - 1 > range - 1 always holds here
+    plan.push_back(d);
+  };
+  if (len < 2) return plan;
+  if (0xFFFFFFFFull / len >= len) {
+    uint64_t i = 1;
+    if ((len % 2) == 0) { add(2, 0, (int)i); ++i; }
+    while (i != len) { add((i + 1) * (i + 2), i + 2, (int)i); i += 2; }
+  } else {
+    for (uint64_t i = 1; i != len; ++i) add(i + 1, 0, (int)i);
+  }
+  return plan;
+}
+static inline void shuffle_apply(int32_t* first, const std::vector<ShuffleDraw>& plan, const uint32_t* accepted) {
+  for (size_t d = 0; d < plan.size(); ++d) {
+    const ShuffleDraw& D = plan[d];
+    const uint64_t x = (uint64_t)accepted[d] / D.scaling;
+    if (D.b == 0) { std::swap(first[D.pos], first[x]); }
+    else { std::swap(first[D.pos], first[x / D.b]); std::swap(first[D.pos + 1], first[x % D.b]); }
+  }
+}
+// Shuffles rows[i][1..k1) for i in [0, m) with the shared engine, in the reference's point order.
+static void shuffle_rows(Mt19937& gen, int32_t* rows, size_t m, int k1) {
+  const std::vector<ShuffleDraw> plan = shuffle_plan((uint64_t)(k1 - 1));
+  const size_t D = plan.size();
+  if (D == 0 || m == 0) return;
+  const size_t kBlock = 1u << 20;
+  std::vector<uint32_t> acc(std::min(m, kBlock) * D);
+  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  for (size_t b0 = 0; b0 < m; b0 += kBlock) {
+    const size_t cnt = std::min(kBlock, m - b0);
+    for (size_t i = 0; i < cnt; ++i)
+      for (size_t d = 0; d < D; ++d) { uint32_t v; do v = gen.next(); while ((uint64_t)v >= plan[d].past); acc[i * D + d] = v; }
+    auto work = [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) shuffle_apply(rows + (b0 + i) * (size_t)k1 + 1, plan, &acc[i * D]); };
+    const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, cnt / 4096));
+    if (nt <= 1) { work(0, cnt); continue; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, cnt * t / nt, cnt * (t + 1) / nt);
+    for (auto& t : th) t.join();
+  }
+}
 
 }  // namespace b2
 
@@ -549,6 +581,7 @@ extern "C" int b2_ms_point_neighbors(const float* xyz, size_t n, const uint8_t* 
     return set_error(B2_ERR_ARG, "need 1 <= neighbor_count <= candidate_count <= 127");
   const int k1 = candidate_count + 1;
   Mt19937 gen(0);                                        // std::mt19937 generator(/*seed*/ 0)  (problem.cc:712)
+  const bool trace = std::getenv("B2_MS_TRACE") != nullptr;
   const float vp[3] = {0.f, 0.f, 0.f};
   auto knn = [&](const float* pts, size_t m, std::vector<int32_t>* idx) -> int {
     std::vector<float> nrm(m * 4);
@@ -568,22 +601,31 @@ extern "C" int b2_ms_point_neighbors(const float* xyz, size_t n, const uint8_t* 
     for (int s = 0; s < scan_count; ++s)
       if ((int)orig[s].size() < k1) return set_error(B2_ERR_STATE, "scan %d has %zu points, fewer than point_neighbor_candidate_count + 1 (reference: CHECK_GE, problem.cc:738)", s, orig[s].size());
     for (int s = 0; s < scan_count; ++s) {
+      const auto t0 = std::chrono::steady_clock::now();
       B2_TRY(knn(clouds[s].data(), orig[s].size(), &idx));
+      const auto t1 = std::chrono::steady_clock::now();
+      shuffle_rows(gen, idx.data(), orig[s].size(), k1);
       for (size_t i = 0; i < orig[s].size(); ++i) {
-        int32_t* row = idx.data() + i * (size_t)k1;
-        gen.shuffle(row + 1, row + k1);
+        const int32_t* row = idx.data() + i * (size_t)k1;
         for (int k = 0; k < neighbor_count; ++k) out_neighbor_indices[orig[s][i] * (size_t)neighbor_count + k] = orig[s][(size_t)row[k + 1]];
       }
+      if (trace) fprintf(stderr, "[b2_ms_point_neighbors] scan %d: %zu points, kNN %.1f ms, shuffle + scatter %.1f ms\n", s, orig[s].size(),
+                         std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     }
     return B2_OK;
   }
   if ((int)std::min<size_t>(n, 1u << 20) < k1) return set_error(B2_ERR_STATE, "cloud has %zu points, fewer than point_neighbor_candidate_count + 1", n);
+  const auto t0 = std::chrono::steady_clock::now();
   B2_TRY(knn(xyz, n, &idx));
+  const auto t1 = std::chrono::steady_clock::now();
+  for (size_t i = 0; i < n; ++i)
+    if (idx[i * (size_t)k1] != (int32_t)i) return set_error(B2_ERR_STATE, "point %zu is not its own nearest neighbour (duplicate points; reference: CHECK_EQ, problem.cc:773)", i);
+  shuffle_rows(gen, idx.data(), n, k1);
   for (size_t i = 0; i < n; ++i) {
-    int32_t* row = idx.data() + i * (size_t)k1;
-    if (row[0] != (int32_t)i) return set_error(B2_ERR_STATE, "point %zu is not its own nearest neighbour (duplicate points; reference: CHECK_EQ, problem.cc:773)", i);
-    gen.shuffle(row + 1, row + k1);
+    const int32_t* row = idx.data() + i * (size_t)k1;
     for (int k = 0; k < neighbor_count; ++k) out_neighbor_indices[i * (size_t)neighbor_count + k] = (uint64_t)row[k + 1];
   }
+  if (trace) fprintf(stderr, "[b2_ms_point_neighbors] %zu points, kNN %.1f ms, shuffle + scatter %.1f ms\n", n,
+                     std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
   return B2_OK;
 }

@@ -111,11 +111,14 @@ struct b2_reg {
   // scratch
   DevBuf flags, offs, cx, cy, cs, cub_tmp, depth, partials, results, cut_cams, cut_first, cut_starts, cut_points, cut_out;
   DevBuf w_nj, w_ws, w_wr, w_part;           // K12b: per-observation slots / merged weights / residual factors + their residual-sum partials
-  int k12_mode = 0;                          // B2_K12: 0 = fp64 products (default), 1 = fp32 products + shuffle kernel (reference op order)
+  int k12_mode = 0;                          // B2_K12: 0 = fp64 products, pre-pass (kr_residual_weights) + kr_accumulate_weighted (pinhole) / block-pair
+                                             // kernels (wide systems) (default); 1 ("f32") = fp32 products, thread / shuffle kernels (reference op order);
+                                             // 2 ("thread") = pinhole in one thread-per-observation kernel; 3 ("blocks") = block-pair kernel for pinhole too
   PinnedBuf pin;
   b2_reg_stats stats;
   int launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evj0 = nullptr, evj1 = nullptr, eva0 = nullptr, eva1 = nullptr;
+  std::vector<cudaEvent_t> ev_pool;          // three events per (image, scale) of an accumulate call: K11 start, K11 end = K12 start, K12 end
 };
 
 namespace b2 {
@@ -472,6 +475,13 @@ static int accumulate_all(b2_reg* h, std::vector<double>* H, std::vector<double>
   const StateB st = current_state(h);
   uint64_t evals = 0;
   float ms_j = 0.f, ms_a = 0.f;
+  size_t nsets = 0;                          // (image, scale) sets launched; their kernels are queued back to back, timed by events read at the end
+  size_t max_count = 1;                      // the pre-pass buffers are sized once, so no set waits for a re-allocation
+  for (size_t im = 0; im < NI; ++im) if (owned(h, im)) for (size_t ps = 0; ps < S; ++ps) max_count = std::max(max_count, h->obs[im][ps].count);
+  if (K(h) == 5 && h->k12_mode != 1) {
+    B2_TRY(h->w_nj.ensure(max_count * 5 * 4)); B2_TRY(h->w_ws.ensure(max_count * 8)); B2_TRY(h->w_wr.ensure(max_count * 5 * 8));
+    B2_TRY(h->w_part.ensure(sizeof(double) * 4 * h->sms * 4));
+  }
   for (size_t im = 0; im < NI; ++im) {
     if (!owned(h, im)) continue;
     const ImageB& I = h->images[im];
@@ -483,26 +493,29 @@ static int accumulate_all(b2_reg* h, std::vector<double>* H, std::vector<double>
       if (o.count == 0) continue;
       evals += o.count;
       const int np = st.intr[I.intrinsics_id].np();
-      cudaEventRecord(h->evj0, h->stream);
+      while (h->ev_pool.size() < 3 * (nsets + 1)) { cudaEvent_t e; B2_CUDA(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
+      cudaEvent_t* ev = &h->ev_pool[3 * nsets];
+      ++nsets;
+      cudaEventRecord(ev[0], h->stream);
       launch_jacobians(h, np, o, h->pts[ps], P3, L, rig);
-      cudaEventRecord(h->evj1, h->stream);
-      cudaEventRecord(h->eva0, h->stream);
+      cudaEventRecord(ev[1], h->stream);
       const ResidualArgs A = residual_args(h, (int)ps, o);
       const float *pK = o.jK.as<float>(), *pP = o.jP.as<float>(), *pR = o.jR.as<float>();
       double* part = h->partials.as<double>();
       const int lv = np + 6 + (rig.dependent ? 6 : 0), nout = lv * (lv + 1) / 2 + lv + 4;
-      const bool blocks = h->k12_mode == 0 && K(h) == 5 && !(np == 4 && !rig.dependent);
-      const int gridb = h->sms * ((np == 12 && rig.dependent) ? BlockCfg<12, true>::CTAS : 2);   // persistent CTAs of kr_accumulate_blocks
-      if (np == 4 && !rig.dependent) {
-        if (h->k12_mode == 0) kr_accumulate<false><<<grid, 128, 0, h->stream>>>(A, pK, pP, part);
+      const bool pin = np == 4 && !rig.dependent;
+      const bool blocks = K(h) == 5 && (pin ? (h->k12_mode == 0 || h->k12_mode == 3) : h->k12_mode != 1);   // pre-pass + second kernel
+      const int gridb = h->sms * (pin ? BlockCfg<4, false>::CTAS : (np == 12 && rig.dependent) ? BlockCfg<12, true>::CTAS : 2);   // persistent CTAs of kr_accumulate_blocks
+      if (pin && !blocks) {
+        if (h->k12_mode != 1) kr_accumulate<false><<<grid, 128, 0, h->stream>>>(A, pK, pP, part);
         else kr_accumulate<true><<<grid, 128, 0, h->stream>>>(A, pK, pP, part);
       } else if (blocks) {
         const int gridw = h->sms * 4;
-        B2_TRY(h->w_nj.ensure(o.count * 5 * 4)); B2_TRY(h->w_ws.ensure(o.count * 8)); B2_TRY(h->w_wr.ensure(o.count * 5 * 8));
-        B2_TRY(h->w_part.ensure(sizeof(double) * 4 * gridw));
         kr_residual_weights<5><<<gridw, 256, 0, h->stream>>>(A, h->w_nj.as<int>(), h->w_ws.as<double>(), h->w_wr.as<double>(), h->w_part.as<double>());
         const int* pn = h->w_nj.as<int>(); const double *pws = h->w_ws.as<double>(), *pwr = h->w_wr.as<double>();
-        if (np == 4) kr_accumulate_blocks<4, true, 5><<<gridb, BlockCfg<4, true>::T, BlockCfg<4, true>::smem(5), h->stream>>>(o.count, pn, pws, pwr, pK, pP, pR, part);
+        if (pin && h->k12_mode == 0) kr_accumulate_weighted<5><<<gridb, 128, 0, h->stream>>>(o.count, pn, pws, pwr, pK, pP, part);
+        else if (pin) kr_accumulate_blocks<4, false, 5><<<gridb, BlockCfg<4, false>::T, BlockCfg<4, false>::smem(5), h->stream>>>(o.count, pn, pws, pwr, pK, pP, pR, part);
+        else if (np == 4) kr_accumulate_blocks<4, true, 5><<<gridb, BlockCfg<4, true>::T, BlockCfg<4, true>::smem(5), h->stream>>>(o.count, pn, pws, pwr, pK, pP, pR, part);
         else if (!rig.dependent) kr_accumulate_blocks<12, false, 5><<<gridb, BlockCfg<12, false>::T, BlockCfg<12, false>::smem(5), h->stream>>>(o.count, pn, pws, pwr, pK, pP, pR, part);
         else kr_accumulate_blocks<12, true, 5><<<gridb, BlockCfg<12, true>::T, BlockCfg<12, true>::smem(5), h->stream>>>(o.count, pn, pws, pwr, pK, pP, pR, part);
         ++h->launches;
@@ -510,24 +523,25 @@ static int accumulate_all(b2_reg* h, std::vector<double>* H, std::vector<double>
       else if (np == 4) kr_accumulate_wide<4, true><<<grid_wide, 128, 0, h->stream>>>(A, pK, pP, pR, part);
       else if (!rig.dependent) kr_accumulate_wide<12, false><<<grid_wide, 128, 0, h->stream>>>(A, pK, pP, pR, part);
       else kr_accumulate_wide<12, true><<<grid_wide, 128, 0, h->stream>>>(A, pK, pP, pR, part);
-      cudaEventRecord(h->eva1, h->stream);
+      cudaEventRecord(ev[2], h->stream);
       double* res = h->results.as<double>() + kAccW * (im * S + ps);
       if (blocks) {
         kr_reduce_partials<<<1, 256, 0, h->stream>>>(part, gridb, nout - 4, res);
         kr_reduce_partials<<<1, 256, 0, h->stream>>>(h->w_part.as<double>(), h->sms * 4, 4, res + (nout - 4));
         ++h->launches;
       } else {
-        kr_reduce_partials<<<1, 256, 0, h->stream>>>(part, (np == 4 && !rig.dependent) ? grid : grid_wide, nout, res);
+        kr_reduce_partials<<<1, 256, 0, h->stream>>>(part, pin ? grid : grid_wide, nout, res);
       }
       h->launches += 2;
-      cudaEventSynchronize(h->eva1);
-      float a = 0, c = 0; cudaEventElapsedTime(&a, h->evj0, h->evj1); cudaEventElapsedTime(&c, h->eva0, h->eva1);
-      ms_j += a; ms_a += c;
     }
   }
   B2_CUDA(cudaMemcpyAsync(h->pin.p, h->results.p, sizeof(double) * kAccW * NI * S, cudaMemcpyDeviceToHost, h->stream));
   B2_CUDA(cudaStreamSynchronize(h->stream));
   B2_CUDA(cudaGetLastError());
+  for (size_t k = 0; k < nsets; ++k) {
+    float a = 0, c = 0; cudaEventElapsedTime(&a, h->ev_pool[3 * k], h->ev_pool[3 * k + 1]); cudaEventElapsedTime(&c, h->ev_pool[3 * k + 1], h->ev_pool[3 * k + 2]);
+    ms_j += a; ms_a += c;
+  }
   const double* r = h->pin.as<double>();
   *sums = Sums();
   for (size_t im = 0; im < NI; ++im) {
@@ -675,7 +689,7 @@ int b2_reg_create(const b2_reg_params* p, b2_reg** out) {
   for (cudaEvent_t* e : {&h->ev0, &h->ev1, &h->evj0, &h->evj1, &h->eva0, &h->eva1}) B2_CUDA(cudaEventCreate(e));
   B2_TRY(h->pin.ensure(4096));
   std::memset(&h->stats, 0, sizeof(h->stats));
-  if (const char* e = std::getenv("B2_K12")) h->k12_mode = std::strcmp(e, "f32") == 0 ? 1 : 0;   // A/B switch, see kr_accumulate
+  if (const char* e = std::getenv("B2_K12")) h->k12_mode = std::strcmp(e, "f32") == 0 ? 1 : std::strcmp(e, "thread") == 0 ? 2 : std::strcmp(e, "blocks") == 0 ? 3 : 0;   // A/B switch, see kr_accumulate
   *out = h.release();
   return B2_OK;
 }
@@ -695,6 +709,7 @@ int b2_reg_destroy(b2_reg* h) {
   for (auto& kv : h->cam_masks) for (auto& b : kv.second) b.release();
   h->pin.release();
   for (cudaEvent_t e : {h->ev0, h->ev1, h->evj0, h->evj1, h->eva0, h->eva1}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
   delete h;
   return B2_OK;
@@ -1023,6 +1038,54 @@ int b2_reg_render_depth(b2_reg* h, int image_id, int* width, int* height, int* i
   if (d) { B2_CUDA(cudaMemcpyAsync(out, d, px * 4, cudaMemcpyDeviceToHost, h->stream)); }
   end_call(h);
   if (!d) for (size_t i = 0; i < px; ++i) out[i] = std::numeric_limits<float>::infinity();
+  return B2_OK;
+}
+
+// ComputeMinMaxPointRadius over all images (multi_scale_point_cloud.cc:126-184 as called from CreateMultiScalePointCloud, :232-255).
+int b2_reg_min_max_point_radius(b2_reg* h, const float* xyz, size_t n, double min_scaling_factor, float* min_radius, float* max_radius) {
+  REG_ENTER(h);
+  if (!h->initialized) return set_error(B2_ERR_STATE, "not initialized");
+  if (n && (!xyz || !min_radius || !max_radius)) return set_error(B2_ERR_ARG, "null argument");
+  if (!(min_scaling_factor > 0)) return set_error(B2_ERR_ARG, "min_scaling_factor must be positive");
+  if (h->world > 1) return set_error(B2_ERR_STATE, "b2_reg_min_max_point_radius is single-GPU (every image must be resident)");
+  if (n == 0) return B2_OK;
+  begin_call(h);
+  DevBuf d_xyz, d_min, d_max, d_table;
+  struct Rel { DevBuf* b[4]; ~Rel() { for (DevBuf* x : b) x->release(); } } rel{{&d_xyz, &d_min, &d_max, &d_table}};
+  B2_TRY(d_xyz.ensure(n * 12)); B2_TRY(d_min.ensure(n * 4)); B2_TRY(d_max.ensure(n * 4));
+  B2_CUDA(cudaMemcpyAsync(d_xyz.p, xyz, n * 12, cudaMemcpyHostToDevice, h->stream));
+  B2_CUDA(cudaMemcpyAsync(d_min.p, min_radius, n * 4, cudaMemcpyHostToDevice, h->stream));
+  B2_CUDA(cudaMemcpyAsync(d_max.p, max_radius, n * 4, cudaMemcpyHostToDevice, h->stream));
+  int table_for = -1;                                    // intrinsics id the undistortion lookup currently holds
+  for (size_t ii = 0; ii < h->images.size(); ++ii) {
+    const ImageB& im = h->images[ii]; const IntrinsicsB& in = h->intr[im.intrinsics_id];
+    const int best = in.best_available(std::max(h->prm.min_occlusion_check_image_scale, h->current_image_scale));
+    const float* depth = nullptr;
+    B2_TRY(render_depth(h, im, in, im.pose, best, &depth));
+    const Levels L = levels_of(h, im, in);
+    RadiusParams V;
+    V.P = pose3_of(im.pose); V.cam = in.model(best); V.cam0 = in.model(0); V.image_scale = best; V.min_image_scale = in.min_image_scale;
+    V.level = best - in.min_image_scale;
+    V.depth = depth; V.mask = L.mask[V.level]; V.cmask = L.cmask[V.level]; V.img = L.img[V.level];
+    V.occlusion_threshold = h->prm.occlusion_depth_threshold; V.max_valid_intensity = h->prm.maximum_valid_intensity;
+    V.min_scaling_factor = min_scaling_factor;
+    V.table = nullptr;
+    if (V.cam0.type != kCamPinhole) {
+      const size_t px = (size_t)V.cam0.w * V.cam0.h;
+      if (table_for != im.intrinsics_id) {
+        B2_TRY(d_table.ensure(px * 8));
+        kr_undistortion_lookup<<<divup(px, 128), 128, 0, h->stream>>>(V.cam0, d_table.as<float2>());
+        ++h->launches; table_for = im.intrinsics_id;
+      }
+      V.table = d_table.as<float2>();
+    }
+    kr_min_max_radius<<<divup(n, 256), 256, 0, h->stream>>>(d_xyz.as<float>(), n, V, d_min.as<float>(), d_max.as<float>());
+    ++h->launches;
+  }
+  B2_CUDA(cudaMemcpyAsync(min_radius, d_min.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaMemcpyAsync(max_radius, d_max.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaGetLastError());
+  end_call(h);
   return B2_OK;
 }
 

@@ -327,6 +327,43 @@ __global__ void __launch_bounds__(256) kr_visibility(const float* __restrict__ x
   flags[i] = ok; ox[i] = rx_; oy[i] = ry_; os[i] = rs_;
 }
 
+// ComputeMinMaxPointRadius (multi_scale_point_cloud.cc:126-184) fused with the visibility test of _AppendObservationsForImageNoScale
+// (visibility_estimator.cc:296-364): one thread per point, one launch per image (images in sequence on one stream, so the per-point
+// min / max need no atomics). cam0 / table: the camera of image scale `min_image_scale` and its undistortion lookup (null for pinhole).
+struct RadiusParams {
+  Pose3 P; Cam cam; Cam cam0; int image_scale, min_image_scale, level;
+  const float* depth; const unsigned char* mask; const unsigned char* cmask; const unsigned char* img;
+  const float2* table;
+  float occlusion_threshold, max_valid_intensity; double min_scaling_factor;
+};
+__global__ void __launch_bounds__(256) kr_min_max_radius(const float* __restrict__ xyz, size_t n, RadiusParams V, float* __restrict__ min_radius,
+                                                         float* __restrict__ max_radius) {
+  const size_t pi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pi >= n) return;
+  float px, py, pz; rigid(V.P, xyz[3 * pi], xyz[3 * pi + 1], xyz[3 * pi + 2], &px, &py, &pz);
+  if (!(pz > 0.f)) return;
+  float ixx, ixy; cam_project(V.cam, px / pz, py / pz, &ixx, &ixy);
+  const int ix = f2i_x86(ixx + 0.5f), iy = f2i_x86(ixy + 0.5f);
+  if (!(ixx + 0.5f >= 0 && ixy + 0.5f >= 0 && ix >= 0 && iy >= 0 && ix < V.cam.w && iy < V.cam.h &&
+        (V.depth == nullptr || __ldg(V.depth + (size_t)iy * V.cam.w + ix) + V.occlusion_threshold >= pz))) return;
+  const size_t pix = (size_t)iy * V.cam.w + ix;
+  if (V.mask != nullptr && __ldg(V.mask + pix) != 0) return;
+  if (V.cmask != nullptr && __ldg(V.cmask + pix) != 0) return;
+  if ((float)__ldg(V.img + pix) > V.max_valid_intensity) return;
+  float returned_scale = (float)V.image_scale - 1e-6f;
+  float ox = ixx, oy = ixy;
+  if (returned_scale < 0.f) { returned_scale = 0.f; ox = 0.5f * (ixx + 0.5f) - 0.5f; oy = 0.5f * (ixy + 0.5f) - 0.5f; }
+  // image_x_at_scale(min_image_scale) (point_observation.h:84-93): 2^(smaller scale - desired) in double (exact power of two)
+  const double p2 = ldexp(1.0, ((int)returned_scale + 1) - V.min_image_scale);
+  const float x0 = (float)(p2 * (double)(ox + 0.5f) - 0.5), y0 = (float)(p2 * (double)(oy + 0.5f) - 0.5);
+  const float offx = (x0 - 0.5f < 0) ? (x0 + 0.5f) : (x0 - 0.5f);
+  float nx, ny; cam_image_to_normalized(V.cam0, V.table, offx, y0, &nx, &ny);
+  const float dx = px - pz * nx, dy = py - pz * ny, dz = pz - pz * 1.f;
+  const float point_radius = sqrtf(sum3p(dx * dx, dy * dy, dz * dz));
+  min_radius[pi] = fminf(min_radius[pi], point_radius);
+  max_radius[pi] = fmaxf(max_radius[pi], (float)((double)point_radius / V.min_scaling_factor));
+}
+
 __global__ void __launch_bounds__(256) kr_compact(const unsigned int* __restrict__ flags, const unsigned int* __restrict__ offs,
                                                   const unsigned int* __restrict__ list, size_t count, const float* __restrict__ cx,
                                                   const float* __restrict__ cy, const float* __restrict__ cs, unsigned int* __restrict__ idx,
@@ -701,8 +738,8 @@ __global__ void __launch_bounds__(128) kr_accumulate_wide(ResidualArgs A, const 
 // kr_residual_weights (thread per observation) does the scalar part once: neighbour slots nj[k] (-1 = observation contributes nothing),
 // the merged weight ws = w_f + w_v, the residual factors wr_k = w_f c_f[k] + w_v c_v[k] (fp64; see kr_accumulate) and the residual sums.
 //
-// kr_accumulate_blocks: the local system is cut into column blocks of <= 6 ([4|6|6], [6|6|6] or [6|6|6|6] = intrinsics | rig | pose);
-// a CTA has one warp per block pair (bi <= bj): 6 or 10 warps. Per chunk of 32 observations
+// kr_accumulate_blocks: the local system is cut into column blocks of <= 6 ([4|6], [4|6|6], [6|6|6] or [6|6|6|6] = intrinsics | rig | pose);
+// a CTA has one warp per block pair (bi <= bj): 3, 6 or 10 warps. Per chunk of 32 observations
 //   1. all threads stage the Jacobian differences dj[k][col] = row(nj[k])[col] - row(centre)[col] (fp32 subtraction as the reference,
 //      :880-905), converted ONCE to fp64, into shared memory as [k][col][observation] — coalesced row reads, every row read once per CTA;
 //   2. warp (bi, bj), lane = observation: acc[r][c] += (ws * dj[bi,r]) * dj[bj,c] (36 DFMA per neighbour), diagonal warps also
@@ -756,6 +793,62 @@ __global__ void __launch_bounds__(256) kr_residual_weights(ResidualArgs A, int* 
   if (threadIdx.x < 4) partials[(size_t)blockIdx.x * 4 + threadIdx.x] = out;
 }
 
+// K12 for pinhole on top of the pre-pass: thread per observation, the scalar chain (point -> neighbour indices -> observation slots ->
+// intensities, descriptors, robust weights) already done by kr_residual_weights at full occupancy, so what is left per thread is one
+// coalesced read of (slots, ws, wr_k), six row reads and the 5 x (10 DMUL + 65 DFMA). Per-block output [55 | 10].
+template <int KN>
+__global__ void __launch_bounds__(128) kr_accumulate_weighted(size_t count, const int* __restrict__ nj_in, const double* __restrict__ ws_in,
+                                                              const double* __restrict__ wr_in, const float* __restrict__ jK, const float* __restrict__ jP,
+                                                              double* __restrict__ partials /* [grid][kNH + kNV] */) {
+  constexpr int NE = kNH + kNV;
+  double acc[NE];
+#pragma unroll
+  for (int k = 0; k < NE; ++k) acc[k] = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    int nj[KN];
+#pragma unroll
+    for (int k = 0; k < KN; ++k) nj[k] = nj_in[(size_t)k * count + i];
+    if (nj[0] < 0) continue;
+    const double ws = ws_in[i];
+    double wr[KN];
+#pragma unroll
+    for (int k = 0; k < KN; ++k) wr[k] = wr_in[(size_t)k * count + i];
+    float jc[kNV];
+    {
+      const float4 a = *reinterpret_cast<const float4*>(jK + kNI * i);
+      const float2 b0 = *reinterpret_cast<const float2*>(jP + 6 * i), b1 = *reinterpret_cast<const float2*>(jP + 6 * i + 2), b2 = *reinterpret_cast<const float2*>(jP + 6 * i + 4);
+      jc[0] = a.x; jc[1] = a.y; jc[2] = a.z; jc[3] = a.w; jc[4] = b0.x; jc[5] = b0.y; jc[6] = b1.x; jc[7] = b1.y; jc[8] = b2.x; jc[9] = b2.y;
+    }
+    float rows[KN][kNV];
+#pragma unroll
+    for (int k = 0; k < KN; ++k) {
+      const size_t s = (size_t)nj[k];
+      const float4 a = *reinterpret_cast<const float4*>(jK + kNI * s);
+      const float2 b0 = *reinterpret_cast<const float2*>(jP + 6 * s), b1 = *reinterpret_cast<const float2*>(jP + 6 * s + 2), b2 = *reinterpret_cast<const float2*>(jP + 6 * s + 4);
+      rows[k][0] = a.x; rows[k][1] = a.y; rows[k][2] = a.z; rows[k][3] = a.w;
+      rows[k][4] = b0.x; rows[k][5] = b0.y; rows[k][6] = b1.x; rows[k][7] = b1.y; rows[k][8] = b2.x; rows[k][9] = b2.y;
+    }
+#pragma unroll
+    for (int k = 0; k < KN; ++k) {
+      double d[kNV];
+#pragma unroll
+      for (int v = 0; v < kNV; ++v) d[v] = (double)(rows[k][v] - jc[v]);
+      int e = 0;
+#pragma unroll
+      for (int c = 0; c < kNV; ++c) {
+        const double t = ws * d[c];
+#pragma unroll
+        for (int r = 0; r <= c; ++r) { acc[e] = fma(t, d[r], acc[e]); ++e; }
+        acc[kNH + c] = fma(wr[k], d[c], acc[kNH + c]);
+      }
+    }
+  }
+  __shared__ double sm[4][NE];
+  double out;
+  block_reduce_d<NE>(acc, sm, 128, &out);
+  if (threadIdx.x < NE) partials[(size_t)blockIdx.x * NE + threadIdx.x] = out;
+}
+
 template <int NI, bool RIG>
 struct BlockCfg {
   static constexpr int NR = RIG ? 6 : 0, NV = NI + NR + 6, NH = NV * (NV + 1) / 2, NE = NH + NV;
@@ -763,7 +856,7 @@ struct BlockCfg {
   static constexpr int NBLK = (NV - B0) / 6 + 1;           // 3 or 4
   static constexpr int G = NBLK * (NBLK + 1) / 2;          // block pairs = warps per CTA: 6 or 10
   static constexpr int T = 32 * G;
-  static constexpr int CTAS = G <= 6 ? 2 : 1;              // resident CTAs per SM the register budget is set for
+  static constexpr int CTAS = G <= 3 ? 4 : G <= 6 ? 2 : 1; // resident CTAs per SM the register budget is set for
   static constexpr int EPT = (32 * NV + T - 1) / T;        // staged (observation, column) elements per thread
   static constexpr int SDS = 33;                           // padded observation stride of the staged differences
   static constexpr size_t smem(int kn) { return sizeof(double) * (size_t)kn * NV * SDS; }
@@ -805,15 +898,32 @@ __global__ void __launch_bounds__(BlockCfg<NI, RIG>::T, BlockCfg<NI, RIG>::CTAS)
   __shared__ int s_nj[KN][32];
   __shared__ double s_w[KN + 1][32];                       // [0] = ws, [1 + k] = wr_k
   float rw[EPT][KN + 1]; bool rv[EPT];
-  const int sk = tid >> 5;                                 // this thread's (k, observation) = (sk, lane) of the slot / weight planes
-  auto load_nj = [&](size_t chunk) -> int {
+  // slot planes k = sk, sk + G, ... and weight planes (0 = ws, 1 + k = wr_k) sk, sk + G, ... belong to warp sk; lane = observation
+  const int sk = tid >> 5;
+  constexpr int G = C::G, NJP = (KN + G - 1) / G, NWP = (KN + 1 + G - 1) / G;
+  auto load_nj = [&](size_t chunk, int (&r)[NJP]) {
     const size_t i = chunk * 32 + lane;
-    return (sk < KN && chunk < nchunks && i < count) ? nj_in[(size_t)sk * count + i] : -1;
+#pragma unroll
+    for (int a = 0; a < NJP; ++a) {
+      const int k = sk + a * G;
+      r[a] = (k < KN && chunk < nchunks && i < count) ? nj_in[(size_t)k * count + i] : -1;
+    }
   };
-  auto load_w = [&](size_t chunk) -> double {
+  auto load_w = [&](size_t chunk, double (&r)[NWP]) {
     const size_t i = chunk * 32 + lane;
-    if (!(sk <= KN && chunk < nchunks && i < count)) return 0.0;
-    return sk == 0 ? ws_in[i] : wr_in[(size_t)(sk - 1) * count + i];
+#pragma unroll
+    for (int a = 0; a < NWP; ++a) {
+      const int k = sk + a * G;
+      r[a] = !(k <= KN && chunk < nchunks && i < count) ? 0.0 : k == 0 ? ws_in[i] : wr_in[(size_t)(k - 1) * count + i];
+    }
+  };
+  auto publish_nj = [&](const int (&r)[NJP]) {
+#pragma unroll
+    for (int a = 0; a < NJP; ++a) if (sk + a * G < KN) s_nj[sk + a * G][lane] = r[a];
+  };
+  auto publish_w = [&](const double (&r)[NWP]) {
+#pragma unroll
+    for (int a = 0; a < NWP; ++a) if (sk + a * G <= KN) s_w[sk + a * G][lane] = r[a];
   };
   auto load_rows = [&](size_t chunk) {
 #pragma unroll
@@ -833,11 +943,12 @@ __global__ void __launch_bounds__(BlockCfg<NI, RIG>::T, BlockCfg<NI, RIG>::CTAS)
   };
 
   size_t c = blockIdx.x;
-  if (sk < KN) s_nj[sk][lane] = load_nj(c);
+  int njreg[NJP]; double wreg[NWP];
+  load_nj(c, njreg); publish_nj(njreg);
   __syncthreads();
   load_rows(c);
-  int njreg = load_nj(c + stride);
-  double wreg = load_w(c);
+  load_nj(c + stride, njreg);
+  load_w(c, wreg);
   __syncthreads();
   for (; c < nchunks; c += stride) {
     // stage chunk c: fp32 difference (as the reference), one conversion per element; publish slots(c + stride) and weights(c)
@@ -848,12 +959,11 @@ __global__ void __launch_bounds__(BlockCfg<NI, RIG>::T, BlockCfg<NI, RIG>::CTAS)
         for (int k = 0; k < KN; ++k) sd[(k * NV + ecol[j]) * SDS + eo[j]] = rv[j] ? (double)(rw[j][k] - rw[j][KN]) : 0.0;
       }
     }
-    if (sk < KN) s_nj[sk][lane] = njreg;
-    if (sk <= KN) s_w[sk][lane] = wreg;
+    publish_nj(njreg); publish_w(wreg);
     __syncthreads();
     load_rows(c + stride);
-    njreg = load_nj(c + 2 * stride);
-    wreg = load_w(c + stride);
+    load_nj(c + 2 * stride, njreg);
+    load_w(c + stride, wreg);
     // multiply chunk c
     const double ws = s_w[0][lane];
     if (__any_sync(0xffffffffu, ws != 0.0)) {

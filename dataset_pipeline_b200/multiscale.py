@@ -89,3 +89,48 @@ def DeterminePointNeighbors(scan_count, limit_neighbors_to_same_scan_index, poin
     _lib.check(_bind().b2_ms_point_neighbors(_f(x), n, _u8(s), int(scan_count), int(bool(limit_neighbors_to_same_scan_index)),
                                              int(point_neighbor_candidate_count), int(point_neighbor_count), out.ctypes.data_as(C.POINTER(C.c_uint64))))
     return out
+
+
+def PreprocessScans(scans):
+    """multi_scale_point_cloud.cc:186-212: scans = [(xyz (n,3) float32, rgb (n,3) uint8), ...] -> (points, colors, scan_indices);
+    colour = 0.299 r + 0.587 g + 0.114 b evaluated in double, stored as float."""
+    pts = np.concatenate([np.ascontiguousarray(x, np.float32) for x, _ in scans])
+    cols = np.concatenate([(0.299 * c[:, 0].astype(np.float64) + 0.587 * c[:, 1].astype(np.float64) + 0.114 * c[:, 2].astype(np.float64)).astype(np.float32)
+                           for _, c in scans])
+    idx = np.concatenate([np.full(len(x), i, np.uint8) for i, (x, _) in enumerate(scans)])
+    return pts, cols, idx
+
+
+def _enough_points(scan_indices, num_scans, use_fixed_scan_colors, candidate_count):
+    if use_fixed_scan_colors:
+        return bool((np.bincount(scan_indices, minlength=num_scans)[:num_scans] >= candidate_count + 1).all())
+    return len(scan_indices) >= candidate_count + 1
+
+
+def ComputeMultiResPointCloud(reg, scans, image_scale_count, fixed_residuals_weight=1.0, point_neighbor_count=5, point_neighbor_candidate_count=25,
+                              min_mean_intensity_difference_for_points=5, min_radius_bias=1.05, merge_distance_factor=4.0):
+    """Problem::ComputeMultiResPointCloud (/root/reference/src/opt/problem.cc:161-362) on top of the C ABI: `reg` is an initialised
+    Registration holding the images, intrinsics and occlusion geometry (ComputeMinMaxPointRadius needs them).
+    -> (point_radii, points, colors, scan_indices, neighbor_indices), one entry per remaining point scale."""
+    use_fixed = fixed_residuals_weight > 0
+    num_scans = len(scans)
+    pts, cols, sidx = PreprocessScans(scans)
+    min_scaling = np.float32(2.0 ** (-1 * (image_scale_count - 1)))                    # float minimum_scaling_factor = pow(2, -(count - 1))  (:181-182)
+    lo, hi = reg.ComputeMinMaxPointRadius(pts, float(min_scaling))
+    scales = CreateMultiScalePointCloud(pts, cols, sidx, lo, hi, num_scans, min_radius_bias, merge_distance_factor)
+    scales = [list(s) for s in scales if _enough_points(s[3], num_scans, use_fixed, point_neighbor_candidate_count)]          # :205-241
+    K = point_neighbor_count
+    for s in scales:                                                                     # :243-302
+        _, p, c, si = s
+        nb = DeterminePointNeighbors(num_scans, use_fixed, p, si, point_neighbor_candidate_count, K).astype(np.int64)
+        diff = np.zeros(len(c), np.float32)
+        for k in range(K):
+            diff = (diff + np.abs(c[nb[:, k]] - c)).astype(np.float32)
+        drop = (diff / np.float32(K)) < np.float32(min_mean_intensity_difference_for_points)
+        keep = ~drop
+        keep2 = keep.copy()
+        keep2[nb[keep].ravel()] = True                                                    # neighbours of kept points stay too
+        s[1], s[2], s[3] = p[keep2], c[keep2], si[keep2]
+    scales = [s for s in scales if _enough_points(s[3], num_scans, use_fixed, point_neighbor_candidate_count)]                 # :304-350
+    nbrs = [DeterminePointNeighbors(num_scans, use_fixed, s[1], s[3], point_neighbor_candidate_count, K) for s in scales]    # :352-361
+    return [s[0] for s in scales], [s[1] for s in scales], [s[2] for s in scales], [s[3] for s in scales], nbrs

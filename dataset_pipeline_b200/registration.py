@@ -45,6 +45,7 @@ def _L():
     L.b2_reg_set_image_scale.argtypes = [vp, C.c_int]
     L.b2_reg_num_variables.argtypes = [vp, ip]
     L.b2_reg_render_depth.argtypes = [vp, C.c_int, ip, ip, ip, fp]
+    L.b2_reg_min_max_point_radius.argtypes = [vp, fp, C.c_size_t, C.c_double, fp, fp]
     L.b2_reg_create_observations.argtypes = [vp, C.c_int]
     L.b2_reg_num_observations.argtypes = [vp, C.c_int, C.c_int, u64p]
     L.b2_reg_get_observations.argtypes = [vp, C.c_int, C.c_int, u64p, fp, fp, fp, u8]
@@ -234,6 +235,16 @@ class Registration:
         n = C.c_int32(0); _lib.check(_L().b2_reg_num_variables(self._h, C.byref(n))); return n.value
 
     # ---- OcclusionGeometry::RenderDepthMap ----
+    def ComputeMinMaxPointRadius(self, points, min_scaling_factor, min_radius=None, max_radius=None):
+        """ComputeMinMaxPointRadius over all images (multi_scale_point_cloud.cc:126-184, 232-255) -> (min_radius, max_radius); points no
+        image observes keep +inf / -inf."""
+        x = np.ascontiguousarray(points, np.float32)
+        n = x.shape[0]
+        lo = np.full(n, np.inf, np.float32) if min_radius is None else np.ascontiguousarray(min_radius, np.float32).copy()
+        hi = np.full(n, -np.inf, np.float32) if max_radius is None else np.ascontiguousarray(max_radius, np.float32).copy()
+        _lib.check(_L().b2_reg_min_max_point_radius(self._h, _f(x), n, float(min_scaling_factor), _f(lo), _f(hi)))
+        return lo, hi
+
     def render_depth(self, image):
         w, h, s = C.c_int32(), C.c_int32(), C.c_int32()
         _lib.check(_L().b2_reg_render_depth(self._h, image, C.byref(w), C.byref(h), C.byref(s), None))

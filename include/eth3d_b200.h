@@ -324,6 +324,12 @@ int b2_reg_run_on_current_scale(b2_reg* h, int max_num_iterations, float max_cha
                                 int iterations_without_new_optimum_threshold, int print_progress, double* optimum_cost,
                                 int* converged, int* iterations);
 int b2_reg_last_stats(b2_reg* h, b2_reg_stats* out);
+/* ComputeMinMaxPointRadius (src/opt/multi_scale_point_cloud.cc:126-184) over all images, as CreateMultiScalePointCloud calls it (:232-255):
+ * a point visible in an image (visibility_estimator.cc:296-364: in front, inside, not occluded, not masked, not saturated, at the
+ * occlusion-check image scale) gets the radius that spans 0.5 px at the finest image scale (ImageToNormalized through the undistortion
+ * lookup for distorted models); min_radius[i] = min(..., r), max_radius[i] = max(..., r / min_scaling_factor). In/out arrays: the caller
+ * initialises them (+inf / -inf). After b2_reg_initialize; single GPU. Feeds b2_ms_create. */
+int b2_reg_min_max_point_radius(b2_reg* h, const float* xyz, size_t n, double min_scaling_factor, float* min_radius, float* max_radius);
 
 #ifdef __cplusplus
 }

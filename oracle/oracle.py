@@ -275,6 +275,45 @@ def ms_point_neighbors(xyz, scan_indices, scan_count, limit_to_same_scan, candid
     return out
 
 
+def ms_compute_multi_res_point_cloud(reg, scans, image_scale_count, fixed_residuals_weight=1.0, K=5, candidates=25, min_diff=5, bias=1.05, factor=4.0):
+    """Problem::ComputeMultiResPointCloud (problem.cc:161-362) restated on the oracle's pieces; `reg` = oracle Registration (initialised).
+    scans: [(xyz float32 (n,3), rgb uint8 (n,3))]. Loops are written point by point where the reference's order matters."""
+    use_fixed = fixed_residuals_weight > 0
+    ns = len(scans)
+    pts = np.concatenate([_c32(x) for x, _ in scans])
+    cols = np.concatenate([np.array([np.float32(0.299 * float(r) + 0.587 * float(g) + 0.114 * float(b)) for r, g, b in c], np.float32) for _, c in scans])
+    sidx = np.concatenate([np.full(len(x), i, np.uint8) for i, (x, _) in enumerate(scans)])
+    lo, hi = reg.min_max_point_radius(pts, float(np.float32(2.0 ** (-(image_scale_count - 1)))))
+    scales = [list(t) for t in ms_create(pts, cols, sidx, lo, hi, ns, bias, factor)]
+
+    def enough(si):
+        if use_fixed:
+            return all(int((si == k).sum()) >= candidates + 1 for k in range(ns))
+        return len(si) >= candidates + 1
+
+    scales = [s for s in scales if enough(s[3])]
+    for s in scales:
+        _, p, c, si = s
+        nb = ms_point_neighbors(p, si, ns, use_fixed, candidates, K)
+        n = len(c)
+        delete1 = np.zeros(n, bool)
+        for i in range(n):
+            acc = np.float32(0)
+            for k in range(K):
+                acc = np.float32(acc + np.float32(abs(np.float32(c[int(nb[i, k])] - c[i]))))
+            delete1[i] = np.float32(acc / np.float32(K)) < min_diff
+        delete2 = np.ones(n, bool)
+        for i in range(n):
+            if not delete1[i]:
+                delete2[i] = False
+                for k in range(K):
+                    delete2[int(nb[i, k])] = False
+        s[1], s[2], s[3] = p[~delete2], c[~delete2], si[~delete2]
+    scales = [s for s in scales if enough(s[3])]
+    nbrs = [ms_point_neighbors(s[1], s[3], ns, use_fixed, candidates, K) for s in scales]
+    return [s[0] for s in scales], [s[1] for s in scales], [s[2] for s in scales], [s[3] for s in scales], nbrs
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Path B (orc_reg.cc)
 # ---------------------------------------------------------------------------------------------------------------------
@@ -492,6 +531,19 @@ class Registration:
 
     def num_variables(self):
         return lib().orc_reg_num_variables(self._h)
+
+    def min_max_point_radius(self, points, min_scaling_factor, min_radius=None, max_radius=None):
+        x = _c32(points)
+        n = x.shape[0]
+        lo = np.full(n, np.inf, np.float32) if min_radius is None else _c32(min_radius).copy()
+        hi = np.full(n, -np.inf, np.float32) if max_radius is None else _c32(max_radius).copy()
+        L = lib()
+        L.orc_reg_min_max_point_radius.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_size_t, C.c_double, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.orc_reg_min_max_point_radius.restype = None
+        L.orc_reg_min_max_point_radius(self._h, _f(x), n, float(min_scaling_factor), _f(lo), _f(hi))
+        return lo, hi
+
+    ComputeMinMaxPointRadius = min_max_point_radius
 
     def render_depth(self, image):
         w, h = C.c_int(), C.c_int()

@@ -100,6 +100,8 @@ int orc_reg_image_scale_count(orc_reg*);
 int orc_reg_num_variables(orc_reg*);
 int orc_reg_render_depth(orc_reg*, int image, int* w, int* h, float* out_or_null);
 void orc_reg_create_observations(orc_reg*, int border);
+/* ComputeMinMaxPointRadius over all images (multi_scale_point_cloud.cc:126-184, 232-255); min/max in-out (+inf / -inf initially) */
+void orc_reg_min_max_point_radius(orc_reg*, const float* xyz, size_t n, double min_scaling_factor, float* min_radius, float* max_radius);
 uint64_t orc_reg_num_observations(orc_reg*, int image, int point_scale);
 void orc_reg_get_observations(orc_reg*, int image, int point_scale, uint64_t* idx, float* x, float* y, float* s, uint8_t* nbrs_observed);
 void orc_reg_color_update(orc_reg*);

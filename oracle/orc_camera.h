@@ -182,6 +182,37 @@ struct Camera {
     }
   }
 
+  // Undistort(distorted) (camera_base_impl.h:251-253 = IterativeUndistort started at the distorted point; camera_pinhole.h:65-68 identity;
+  // camera_base_impl_fisheye.h:80-91 inner Undistort then r -> tan(r))
+  void undistort(float dx, float dy, float* ox, float* oy) const {
+    float ux = dx, uy = dy;
+    if (type != kCamPinhole) tp_iterative_undistort(dx, dy, dx, dy, &ux, &uy);
+    if (type == kCamBenchmark) {
+      const float r = std::sqrt(ux * ux + uy * uy);
+      const float factor = (r < 1e-6f) ? 1.f : (r > M_PI / 2.f) ? std::numeric_limits<float>::infinity() : tanf(r) / r;
+      ux = factor * ux; uy = factor * uy;
+    }
+    *ox = ux; *oy = uy;
+  }
+  // InitializeUndistortionLookup (camera_base_impl.h:255-269): Undistort at every integer pixel; w*h x 2 floats
+  void undistortion_lookup(float* table) const {
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) undistort(fx_inv * x + cx_inv, fy_inv * y + cy_inv, &table[2 * ((size_t)y * w + x)], &table[2 * ((size_t)y * w + x) + 1]);
+  }
+  // ImageToNormalized(pixel_position) (camera_base_impl.h:187-212): bilinear filter of the lookup; camera_pinhole.h:60-63: ImageToDistorted.
+  // The reference reads row h of the table when the clamped y is exactly h - 1 (weight 0): defined here as a clamped (finite) read.
+  void image_to_normalized(const float* table, float px, float py, float* ox, float* oy) const {
+    if (type == kCamPinhole) { *ox = fx_inv * px + cx_inv; *oy = fy_inv * py + cy_inv; return; }
+    const float cxp = std::max(std::min(px, w - 1.001f), 0.f), cyp = std::max(std::min(py, h - 1.00f), 0.f);
+    const int ix = (int)cxp, iy = (int)cyp;
+    const float fx_ = cxp - (float)ix, fy_ = cyp - (float)iy;
+    const int ix1 = std::min(ix + 1, w - 1), iy1 = std::min(iy + 1, h - 1);
+    const float* tl = &table[2 * ((size_t)iy * w + ix)]; const float* tr = &table[2 * ((size_t)iy * w + ix1)];
+    const float* bl = &table[2 * ((size_t)iy1 * w + ix)]; const float* br = &table[2 * ((size_t)iy1 * w + ix1)];
+    *ox = (1 - fy_) * ((1 - fx_) * tl[0] + fx_ * tr[0]) + fy_ * ((1 - fx_) * bl[0] + fx_ * br[0]);
+    *oy = (1 - fy_) * ((1 - fx_) * tl[1] + fx_ * tr[1]) + fy_ * ((1 - fx_) * bl[1] + fx_ * br[1]);
+  }
+
   // ---- cut-off search of the thin-prism model (camera_base_impl.h:214-250, 276-328, 410-462) ----
   bool tp_iterative_undistort(float tx, float ty, float sx, float sy, float* ox, float* oy) const {
     float ux = sx, uy = sy;

@@ -670,6 +670,49 @@ int orc_reg_render_depth(orc_reg* h, int image, int* w, int* hh, float* out) {
   return best;
 }
 
+// ComputeMinMaxPointRadius over all images (multi_scale_point_cloud.cc:126-184 called from :232-255) with the visibility test of
+// _AppendObservationsForImageNoScale (visibility_estimator.cc:296-364). min_radius / max_radius: in/out, initialised by the caller
+// (+inf / -inf in CreateMultiScalePointCloud). Needs initialize() (pyramids) and the occlusion geometry of the handle.
+void orc_reg_min_max_point_radius(orc_reg* h, const float* xyz, size_t n, double min_scaling_factor, float* min_radius, float* max_radius) {
+  for (size_t ii = 0; ii < h->st.images.size(); ++ii) {
+    const Image& im = h->st.images[ii]; const Intrinsics& intr = h->st.intr[im.intrinsics_id];
+    const int image_scale = intr.best_available(std::max(h->prm.min_occlusion_check_image_scale, h->current_image_scale));
+    const ImgF depth = render_depth(h, intr, im, image_scale);
+    const Pinhole& cam = intr.model(image_scale);
+    const Pinhole& cam0 = intr.model(0);                 // min_image_scale_camera = *intrinsics.model(0) (:240)
+    std::vector<float> table;
+    if (cam0.type != kCamPinhole) { table.resize((size_t)2 * cam0.w * cam0.h); cam0.undistortion_lookup(table.data()); }
+    float R[9]; quat_to_matrix(im.image_T_global.q, R);
+    const int level = image_scale - intr.min_image_scale;
+    for (size_t pi = 0; pi < n; ++pi) {
+      V3f pp; rigid_pp(R, im.image_T_global.t, &xyz[3 * pi], &pp);
+      if (!(pp.z > 0.f)) continue;
+      float ixx, ixy; cam.project(pp.x / pp.z, pp.y / pp.z, &ixx, &ixy);
+      const int ix = f2i(ixx + 0.5f), iy = f2i(ixy + 0.5f);
+      if (!(ixx + 0.5f >= 0 && ixy + 0.5f >= 0 && ix >= 0 && iy >= 0 && ix < cam.w && iy < cam.h &&
+            depth.d[(size_t)iy * depth.w + ix] + h->prm.occlusion_depth_threshold >= pp.z)) continue;
+      if (level < (int)im.mask.size() && !im.mask[level].d.empty() && im.mask[level].at(iy, ix) != 0) continue;
+      if (level < (int)intr.camera_mask.size() && !intr.camera_mask[level].d.empty() && intr.camera_mask[level].at(iy, ix) != 0) continue;
+      if (im.image[level].at(iy, ix) > h->prm.maximum_valid_intensity) continue;
+      float returned_scale = image_scale - 1e-6f;
+      float ox = ixx, oy = ixy;
+      if (returned_scale < 0.f) { returned_scale = 0.f; ox = 0.5f * (ixx + 0.5f) - 0.5f; oy = 0.5f * (ixy + 0.5f) - 0.5f; }
+      const Observation o{pi, ox, oy, returned_scale};
+      // image_x_at_scale(intrinsics.min_image_scale) (point_observation.h:84-93): double pow, float result
+      const double p2 = std::pow(2, smaller_scale(o) - intr.min_image_scale);
+      const float x0 = (float)(p2 * (o.x + 0.5f) - 0.5f), y0 = (float)(p2 * (o.y + 0.5f) - 0.5f);
+      const float kPixelDistance = 0.5f;
+      const float offx = (x0 - kPixelDistance < 0) ? (x0 + kPixelDistance) : (x0 - kPixelDistance);
+      float nx, ny; cam0.image_to_normalized(table.data(), offx, y0, &nx, &ny);
+      const V3f off{pp.z * nx, pp.z * ny, pp.z * 1.f};
+      const float dx = pp.x - off.x, dy = pp.y - off.y, dz = pp.z - off.z;
+      const float point_radius = std::sqrt(sum3(dx * dx, dy * dy, dz * dz));
+      min_radius[pi] = std::min<float>(min_radius[pi], point_radius);
+      max_radius[pi] = std::max<float>(max_radius[pi], (float)(point_radius / min_scaling_factor));
+    }
+  }
+}
+
 // CreateObservationsForAllImages + DetermineIfAllNeighborsAreObserved (optimizer.cc:123-128)
 void orc_reg_create_observations(orc_reg* h, int border) {
   h->obs.assign(h->st.images.size(), {}); h->nbr_obs.assign(h->st.images.size(), {});
@@ -863,14 +906,7 @@ int orc_cam_eval(int type, int w, int hh, const float* params, int op, const flo
     else if (op == 2) c.d_by_world(V3f{in[3 * i], in[3 * i + 1], in[3 * i + 2]}, &out[6 * i]);
     else if (op == 3) c.d_by_intrinsics(V3f{in[3 * i], in[3 * i + 1], in[3 * i + 2]}, &out[(size_t)2 * np * i]);
     else if (op == 4) {
-      float ux = in[2 * i], uy = in[2 * i + 1];
-      if (type != kCamPinhole) c.tp_iterative_undistort(in[2 * i], in[2 * i + 1], in[2 * i], in[2 * i + 1], &ux, &uy);
-      if (type == kCamBenchmark) {   // camera_base_impl_fisheye.h:80-91
-        const float r = std::sqrt(ux * ux + uy * uy);
-        const float factor = (r < 1e-6f) ? 1.f : (r > M_PI / 2.f) ? std::numeric_limits<float>::infinity() : tanf(r) / r;
-        ux = factor * ux; uy = factor * uy;
-      }
-      out[2 * i] = ux; out[2 * i + 1] = uy;
+      c.undistort(in[2 * i], in[2 * i + 1], &out[2 * i], &out[2 * i + 1]);
     } else if (op == 5) c.distort_deriv(in[2 * i], in[2 * i + 1], &out[4 * i]);
     else return -2;
   }

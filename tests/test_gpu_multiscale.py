@@ -113,3 +113,70 @@ def test_reference_test_problem_through_the_abi(oracle):
     from dataset_pipeline_b200._lib import B2Error
     with pytest.raises(B2Error):
         b2.DeterminePointNeighbors(2, True, pts, scan, 25, 5)                      # fewer than 26 points per scan: reference CHECK_GE
+
+
+def _radius_scene(model, seed=8):
+    """Images of the textured plane + two 'scans' of it (jittered grids with the texture as colour)."""
+    from dataset_pipeline_b200.synth import reg_scene
+    sc = reg_scene.make_scene(num_images=3, width=320, height=240, fx=260.0, camera_model=model, num_scales=1, base_radius=0.004)
+    rng = np.random.default_rng(seed)
+    scans = []
+    for s, (step, x0, x1) in enumerate(((0.011, -1.3, 0.25), (0.012, -0.25, 1.3))):      # two scans with a strip of overlap
+        gx, gy = np.meshgrid(np.arange(x0, x1, step), np.arange(-1.0, 1.0, step), indexing="xy")
+        x = gx.ravel() + rng.uniform(-0.3, 0.3, gx.size) * step; y = gy.ravel() + rng.uniform(-0.3, 0.3, gx.size) * step
+        xyz = np.stack([x, y, rng.normal(0, 2e-4, gx.size)], 1).astype(np.float32)
+        g = np.clip(reg_scene.texture(x, y), 0, 255).astype(np.uint8)
+        scans.append((xyz, np.stack([g, g, g], 1)))
+    return sc, scans
+
+
+def _load_images(reg, sc, splat_points):
+    w, h, K = sc["intr"]
+    reg.add_intrinsics(w, h, K, camera_model=sc["camera_model"])
+    for img, T in zip(sc["images"], sc["poses_gt"]):
+        reg.add_image(0, img, None, T)
+    count = reg.initialize()
+    reg.set_splat_points(splat_points)
+    reg.set_image_scale(0)
+    return count
+
+
+@pytest.mark.parametrize("model", [4, 14, 5])
+def test_compute_min_max_point_radius(oracle, model):
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import registration as R
+    sc, scans = _radius_scene(model)
+    pts = np.concatenate([x for x, _ in scans])
+    area = 320 * 240 // 64
+    g = b2.Registration(R.default_params(max_initial_image_area_in_pixels=area)); o = oracle.Registration(oracle.reg_default_params(max_initial_image_area_in_pixels=area))
+    cg = _load_images(g, sc, pts); co = _load_images(o, sc, pts)
+    assert cg == co == 4
+    msf = float(np.float32(2.0 ** (-(cg - 1))))
+    lg, hg = g.ComputeMinMaxPointRadius(pts, msf); lo, ho = o.min_max_point_radius(pts, msf)
+    seen = np.isfinite(lo)
+    assert np.array_equal(np.isfinite(lg), seen) and 0.3 < seen.mean() <= 1.0
+    if model == 5:        # the fisheye Undistort goes through tanf(): device and glibc agree to a couple of ulps
+        assert np.allclose(lg[seen], lo[seen], rtol=2e-5, atol=0) and np.allclose(hg[seen], ho[seen], rtol=2e-5, atol=0)
+    else:
+        assert np.array_equal(lg, lo) and np.array_equal(hg, ho)
+    assert np.array_equal(hg[seen] >= lg[seen], np.ones(seen.sum(), bool))
+
+
+def test_compute_multi_res_point_cloud_pipeline(oracle):
+    """Problem::ComputeMultiResPointCloud (problem.cc:161-362) end to end: radii, scale loop, scale filter, neighbours, gradient filter."""
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import multiscale as MS
+    from dataset_pipeline_b200 import registration as R
+    sc, scans = _radius_scene(4)
+    pts = np.concatenate([x for x, _ in scans])
+    area = 320 * 240 // 64
+    g = b2.Registration(R.default_params(max_initial_image_area_in_pixels=area)); o = oracle.Registration(oracle.reg_default_params(max_initial_image_area_in_pixels=area))
+    cg = _load_images(g, sc, pts); _load_images(o, sc, pts)
+    got = MS.ComputeMultiResPointCloud(g, scans, cg)
+    ref = oracle.ms_compute_multi_res_point_cloud(o, scans, cg)
+    assert len(got[0]) == len(ref[0]) >= 2
+    for k in range(len(ref[0])):
+        assert got[0][k] == ref[0][k]
+        for a in range(1, 5):
+            assert np.array_equal(got[a][k], ref[a][k]), (k, a)
+        assert len(ref[1][k]) >= 52
