@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--cpu-w", type=int, default=1000)
     ap.add_argument("--cpu-h", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around one pass (for `ncu --profile-from-start off`)")
     a = ap.parse_args()
     import torch
     if not torch.cuda.is_available():
@@ -68,6 +69,10 @@ def main():
 
     for _ in range(a.warmup):
         run()
+    if a.profile:
+        torch.cuda.profiler.start(); run(); torch.cuda.synchronize(); torch.cuda.profiler.stop()
+        print(json.dumps({"profile": True, "points": int(n)}))
+        return
     tm, tn = [], []
     for _ in range(a.steps):
         scales, st, nb, dm, dn = run()

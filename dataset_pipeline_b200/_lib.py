@@ -91,6 +91,8 @@ EXPORTS = [
     "b2_reg_default_params",
     "b2_reg_destroy",
     "b2_reg_get_descriptors",
+    "b2_reg_gt_accumulate_observations",
+    "b2_reg_gt_create",
     "b2_reg_get_observations",
     "b2_reg_get_point_jacobians",
     "b2_reg_get_point_jacobians_rig",

@@ -28,6 +28,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -337,21 +338,29 @@ static int merge_device(MsScratch& S, const MsCloud& in, float merge_distance, i
 //     stream, so they must be replayed exactly);
 //   * parallel (host threads): turn the accepted outputs into swap positions and apply them to the neighbour lists.
 struct Mt19937 {
-  uint32_t mt[624]; int idx;
+  uint32_t mt[624]; uint32_t out[624]; int idx;
   explicit Mt19937(uint32_t seed) { mt[0] = seed; for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i; idx = 624; }
-  static inline uint32_t twist(uint32_t u, uint32_t v, uint32_t m) { const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu); return m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+  static inline uint32_t twist(uint32_t u, uint32_t v, uint32_t m) { const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu); return m ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu); }
+  // the whole state at once, in three branch-free loops the host compiler vectorises (no element depends on one written in the same loop
+  // within 227 positions), then the tempering of all 624 outputs
+#if defined(__GNUC__) && !defined(__clang__)
+  __attribute__((optimize("O3")))
+#endif
   void refill() {
-    int i = 0;
-    for (; i < 624 - 397; ++i) mt[i] = twist(mt[i], mt[i + 1], mt[i + 397]);
-    for (; i < 623; ++i) mt[i] = twist(mt[i], mt[i + 1], mt[i + 397 - 624]);
+    for (int i = 0; i < 227; ++i) mt[i] = twist(mt[i], mt[i + 1], mt[i + 397]);
+    for (int i = 227; i < 454; ++i) mt[i] = twist(mt[i], mt[i + 1], mt[i - 227]);
+    for (int i = 454; i < 623; ++i) mt[i] = twist(mt[i], mt[i + 1], mt[i - 227]);
     mt[623] = twist(mt[623], mt[0], mt[396]);
+    for (int i = 0; i < 624; ++i) {
+      uint32_t y = mt[i];
+      y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+      out[i] = y;
+    }
     idx = 0;
   }
   inline uint32_t next() {
     if (idx >= 624) refill();
-    uint32_t y = mt[idx++];
-    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
-    return y;
+    return out[idx++];
   }
 };
 
@@ -377,9 +386,9 @@ static std::vector<ShuffleDraw> shuffle_plan(uint64_t len) {
 static inline void shuffle_apply(int32_t* first, const std::vector<ShuffleDraw>& plan, const uint32_t* accepted) {
   for (size_t d = 0; d < plan.size(); ++d) {
     const ShuffleDraw& D = plan[d];
-    const uint64_t x = (uint64_t)accepted[d] / D.scaling;
+    const uint32_t x = accepted[d] / (uint32_t)D.scaling;          // scaling <= 2^32 - 1 and x < range: 32-bit divisions suffice
     if (D.b == 0) { std::swap(first[D.pos], first[x]); }
-    else { std::swap(first[D.pos], first[x / D.b]); std::swap(first[D.pos + 1], first[x % D.b]); }
+    else { const uint32_t b = (uint32_t)D.b, q = x / b; std::swap(first[D.pos], first[q]); std::swap(first[D.pos + 1], first[x - q * b]); }
   }
 }
 // Shuffles rows[i][1..k1) for i in [0, m) with the shared engine, in the reference's point order.
@@ -389,7 +398,7 @@ static void shuffle_rows(Mt19937& gen, int32_t* rows, size_t m, int k1) {
   if (D == 0 || m == 0) return;
   const size_t kBlock = 1u << 20;
   std::vector<uint32_t> acc(std::min(m, kBlock) * D);
-  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   for (size_t b0 = 0; b0 < m; b0 += kBlock) {
     const size_t cnt = std::min(kBlock, m - b0);
     for (size_t i = 0; i < cnt; ++i)
@@ -583,16 +592,25 @@ extern "C" int b2_ms_point_neighbors(const float* xyz, size_t n, const uint8_t* 
   Mt19937 gen(0);                                        // std::mt19937 generator(/*seed*/ 0)  (problem.cc:712)
   const bool trace = std::getenv("B2_MS_TRACE") != nullptr;
   const float vp[3] = {0.f, 0.f, 0.f};
-  auto knn = [&](const float* pts, size_t m, std::vector<int32_t>* idx) -> int {
-    std::vector<float> nrm(m * 4);
-    idx->assign(m * (size_t)k1, -1);
+  // neighbour lists land in a pinned, grow-only scratch of the library (one D2H at PCIe rate; pageable destinations cost 3-10x)
+  static PinnedBuf scratch;
+  static std::mutex scratch_mutex;
+  std::lock_guard<std::mutex> lock(scratch_mutex);
+  struct Rows { int32_t* p = nullptr; int32_t* data() const { return p; } int32_t& operator[](size_t i) const { return p[i]; } } idx;
+  auto knn = [&](const float* pts, size_t m, Rows* rows) -> int {
+    B2_TRY(scratch.ensure(std::max<size_t>(m, 1) * (size_t)k1 * 4));
+    rows->p = scratch.as<int32_t>();
     int dense = 0;
-    return b2_normals_estimate(pts, m, 12, k1, vp, nrm.data(), idx->data(), &dense);     // K7's exact kNN lists, (d2, index) order
+    return b2_normals_estimate(pts, m, 12, k1, vp, nullptr, rows->p, &dense);            // K7's exact kNN lists, (d2, index) order
   };
-  std::vector<int32_t> idx;
   if (limit_neighbors_to_same_scan_index) {
     if (!scan_indices || scan_count < 1 || scan_count > 256) return set_error(B2_ERR_ARG, "bad scan arguments");
     std::vector<std::vector<float>> clouds(scan_count); std::vector<std::vector<size_t>> orig(scan_count);
+    {
+      std::vector<size_t> cnt(scan_count, 0);
+      for (size_t i = 0; i < n; ++i) if (scan_indices[i] < scan_count) ++cnt[scan_indices[i]];
+      for (int s = 0; s < scan_count; ++s) { clouds[s].reserve(3 * cnt[s]); orig[s].reserve(cnt[s]); }
+    }
     for (size_t i = 0; i < n; ++i) {
       const int s = scan_indices[i];
       if (s >= scan_count) return set_error(B2_ERR_ARG, "scan index %d of point %zu is outside [0,%d)", s, i, scan_count);
@@ -600,18 +618,34 @@ extern "C" int b2_ms_point_neighbors(const float* xyz, size_t n, const uint8_t* 
     }
     for (int s = 0; s < scan_count; ++s)
       if ((int)orig[s].size() < k1) return set_error(B2_ERR_STATE, "scan %d has %zu points, fewer than point_neighbor_candidate_count + 1 (reference: CHECK_GE, problem.cc:738)", s, orig[s].size());
-    for (int s = 0; s < scan_count; ++s) {
+    // two pinned buffers: the host shuffles scan s (one worker thread, so the engine stream stays in scan order) while the GPU searches scan s + 1
+    static PinnedBuf scratch2;
+    std::thread worker;
+    int rc = B2_OK;
+    for (int s = 0; s < scan_count && rc == B2_OK; ++s) {
       const auto t0 = std::chrono::steady_clock::now();
-      B2_TRY(knn(clouds[s].data(), orig[s].size(), &idx));
+      PinnedBuf& buf = (s & 1) ? scratch2 : scratch;
+      const size_t m = orig[s].size();
+      rc = buf.ensure(std::max<size_t>(m, 1) * (size_t)k1 * 4);
+      int dense = 0;
+      if (rc == B2_OK) rc = b2_normals_estimate(clouds[s].data(), m, 12, k1, vp, nullptr, buf.as<int32_t>(), &dense);
       const auto t1 = std::chrono::steady_clock::now();
-      shuffle_rows(gen, idx.data(), orig[s].size(), k1);
-      for (size_t i = 0; i < orig[s].size(); ++i) {
-        const int32_t* row = idx.data() + i * (size_t)k1;
-        for (int k = 0; k < neighbor_count; ++k) out_neighbor_indices[orig[s][i] * (size_t)neighbor_count + k] = orig[s][(size_t)row[k + 1]];
-      }
-      if (trace) fprintf(stderr, "[b2_ms_point_neighbors] scan %d: %zu points, kNN %.1f ms, shuffle + scatter %.1f ms\n", s, orig[s].size(),
-                         std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
+      if (worker.joinable()) worker.join();
+      if (rc != B2_OK) break;
+      int32_t* rows = buf.as<int32_t>();
+      worker = std::thread([&, s, m, rows, t0, t1]() {
+        const auto t2 = std::chrono::steady_clock::now();
+        shuffle_rows(gen, rows, m, k1);
+        for (size_t i = 0; i < m; ++i) {
+          const int32_t* row = rows + i * (size_t)k1;
+          for (int k = 0; k < neighbor_count; ++k) out_neighbor_indices[orig[s][i] * (size_t)neighbor_count + k] = orig[s][(size_t)row[k + 1]];
+        }
+        if (trace) fprintf(stderr, "[b2_ms_point_neighbors] scan %d: %zu points, kNN %.1f ms, shuffle + scatter %.1f ms (overlapped with the next search)\n", s, m,
+                           std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count());
+      });
     }
+    if (worker.joinable()) worker.join();
+    return rc;
     return B2_OK;
   }
   if ((int)std::min<size_t>(n, 1u << 20) < k1) return set_error(B2_ERR_STATE, "cloud has %zu points, fewer than point_neighbor_candidate_count + 1", n);

@@ -268,7 +268,7 @@ using namespace b2;
 // the full result. No exchange during the search itself.
 static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3], float* out_nxyz_curv,
                         int32_t* out_knn_idx, int* is_dense, b2_comm* comm, int device, float radius = 0.f, int32_t* out_count = nullptr) {
-  if ((n && (!xyz || !out_nxyz_curv)) || !viewpoint) return set_error(B2_ERR_ARG, "null argument");
+  if ((n && (!xyz || (!out_nxyz_curv && !out_knn_idx))) || !viewpoint) return set_error(B2_ERR_ARG, "null argument");
   if (stride_bytes < 12) return set_error(B2_ERR_ARG, "stride_bytes must be >= 12");
   const bool radius_mode = radius > 0.f;
   if (!radius_mode && (k < 1 || k > 128)) return set_error(B2_ERR_ARG, "k must be in [1,128]");
@@ -377,7 +377,7 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
       B2_TRY(b2_comm_allreduce(comm, d_nan.p, 1, B2_I32, (void*)st));
     }
     unsigned int nans = 0;
-    B2_CUDA(cudaMemcpyAsync(out_nxyz_curv, d_out.p, n * 16, cudaMemcpyDeviceToHost, st));
+    if (out_nxyz_curv) B2_CUDA(cudaMemcpyAsync(out_nxyz_curv, d_out.p, n * 16, cudaMemcpyDeviceToHost, st));
     if (out_knn_idx) B2_CUDA(cudaMemcpyAsync(out_knn_idx, d_oidx.p, n * (size_t)k * 4, cudaMemcpyDeviceToHost, st));
     if (radius_mode && out_count) {
       if (world > 1) B2_TRY(b2_comm_allreduce(comm, r_ocount.p, n, B2_I32, (void*)st));

@@ -373,7 +373,7 @@ static int residual_sums_image(b2_reg* h, const StateB& st, int im, std::vector<
     any = true;
     kr_intensity<<<divup(o.count, 256), 256, 0, h->stream>>>(o.count, o.x.as<float>(), o.y.as<float>(), o.s.as<float>(), L, o.inten.as<float>());
     kr_residual_sums<<<grid, 256, 0, h->stream>>>(residual_args(h, (int)ps, o), h->partials.as<double>());
-    kr_reduce_partials<<<1, 256, 0, h->stream>>>(h->partials.as<double>(), grid, 4, h->results.as<double>() + 4 * ps);
+    kr_reduce_partials<<<4, 64, 0, h->stream>>>(h->partials.as<double>(), grid, 4, h->results.as<double>() + 4 * ps);
     h->launches += 3;
   }
   if (!any) return B2_OK;
@@ -505,7 +505,7 @@ static int accumulate_all(b2_reg* h, std::vector<double>* H, std::vector<double>
       const int lv = np + 6 + (rig.dependent ? 6 : 0), nout = lv * (lv + 1) / 2 + lv + 4;
       const bool pin = np == 4 && !rig.dependent;
       const bool blocks = K(h) == 5 && (pin ? (h->k12_mode == 0 || h->k12_mode == 3) : h->k12_mode != 1);   // pre-pass + second kernel
-      const int gridb = h->sms * (pin ? BlockCfg<4, false>::CTAS : (np == 12 && rig.dependent) ? BlockCfg<12, true>::CTAS : 2);   // persistent CTAs of kr_accumulate_blocks
+      const int gridb = h->sms * (pin ? (h->k12_mode == 0 ? 2 : BlockCfg<4, false>::CTAS) : (np == 12 && rig.dependent) ? BlockCfg<12, true>::CTAS : 2);   // persistent CTAs of kr_accumulate_blocks
       if (pin && !blocks) {
         if (h->k12_mode != 1) kr_accumulate<false><<<grid, 128, 0, h->stream>>>(A, pK, pP, part);
         else kr_accumulate<true><<<grid, 128, 0, h->stream>>>(A, pK, pP, part);
@@ -526,11 +526,11 @@ static int accumulate_all(b2_reg* h, std::vector<double>* H, std::vector<double>
       cudaEventRecord(ev[2], h->stream);
       double* res = h->results.as<double>() + kAccW * (im * S + ps);
       if (blocks) {
-        kr_reduce_partials<<<1, 256, 0, h->stream>>>(part, gridb, nout - 4, res);
-        kr_reduce_partials<<<1, 256, 0, h->stream>>>(h->w_part.as<double>(), h->sms * 4, 4, res + (nout - 4));
+        kr_reduce_partials<<<nout - 4, 64, 0, h->stream>>>(part, gridb, nout - 4, res);
+        kr_reduce_partials<<<4, 64, 0, h->stream>>>(h->w_part.as<double>(), h->sms * 4, 4, res + (nout - 4));
         ++h->launches;
       } else {
-        kr_reduce_partials<<<1, 256, 0, h->stream>>>(part, pin ? grid : grid_wide, nout, res);
+        kr_reduce_partials<<<nout, 64, 0, h->stream>>>(part, pin ? grid : grid_wide, nout, res);
       }
       h->launches += 2;
     }
@@ -1084,6 +1084,86 @@ int b2_reg_min_max_point_radius(b2_reg* h, const float* xyz, size_t n, double mi
   }
   B2_CUDA(cudaMemcpyAsync(min_radius, d_min.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
   B2_CUDA(cudaMemcpyAsync(max_radius, d_max.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaGetLastError());
+  end_call(h);
+  return B2_OK;
+}
+
+// ---- GroundTruthCreator (src/exe/ground_truth_creator.cc:44-215) ----
+static int gt_params(b2_reg* h, int image_id, GtParams* V) {
+  const ImageB& im = h->images[image_id]; const IntrinsicsB& in = h->intr[im.intrinsics_id];
+  const float* depth = nullptr;
+  B2_TRY(render_depth(h, im, in, im.pose, in.min_image_scale, &depth));     // RenderDepthMap(intrinsics, image, intrinsics.min_image_scale, ...)
+  const Levels L = levels_of(h, im, in);
+  V->P = pose3_of(im.pose); V->cam = in.model(0); V->depth = depth; V->mask = L.mask[0];
+  V->occlusion_threshold = h->prm.occlusion_depth_threshold;
+  return B2_OK;
+}
+static int gt_check(b2_reg* h, int image_id) {
+  if (!h->initialized) return set_error(B2_ERR_STATE, "not initialized");
+  if (image_id < 0 || image_id >= (int)h->images.size()) return set_error(B2_ERR_ARG, "bad image id");
+  if (!owned(h, (size_t)image_id)) return set_error(B2_ERR_STATE, "image %d is owned by rank %d", image_id, image_id % h->world);
+  return B2_OK;
+}
+int b2_reg_gt_accumulate_observations(b2_reg* h, int image_id, const float* xyz, size_t n, int32_t* observation_counts) {
+  REG_ENTER(h);
+  B2_TRY(gt_check(h, image_id));
+  if (n && (!xyz || !observation_counts)) return set_error(B2_ERR_ARG, "null argument");
+  if (n == 0) return B2_OK;
+  begin_call(h);
+  DevBuf d_xyz, d_cnt;
+  struct Rel { DevBuf* b[2]; ~Rel() { for (DevBuf* x : b) x->release(); } } rel{{&d_xyz, &d_cnt}};
+  B2_TRY(d_xyz.ensure(n * 12)); B2_TRY(d_cnt.ensure(n * 4));
+  B2_CUDA(cudaMemcpyAsync(d_xyz.p, xyz, n * 12, cudaMemcpyHostToDevice, h->stream));
+  B2_CUDA(cudaMemcpyAsync(d_cnt.p, observation_counts, n * 4, cudaMemcpyHostToDevice, h->stream));
+  GtParams V; B2_TRY(gt_params(h, image_id, &V));
+  kg_count<<<divup(n, 256), 256, 0, h->stream>>>(d_xyz.as<float>(), n, V, d_cnt.as<int>());
+  ++h->launches;
+  B2_CUDA(cudaMemcpyAsync(observation_counts, d_cnt.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaGetLastError());
+  end_call(h);
+  return B2_OK;
+}
+int b2_reg_gt_create(b2_reg* h, int image_id, const float* xyz, const uint8_t* rgb, size_t n, const int32_t* observation_counts, int scan_point_radius,
+                     float* out_occlusion_depth, float* out_gt_depth, uint8_t* inout_scan_rendering_bgr) {
+  REG_ENTER(h);
+  B2_TRY(gt_check(h, image_id));
+  if (n && (!xyz || !observation_counts)) return set_error(B2_ERR_ARG, "null argument");
+  if (inout_scan_rendering_bgr && !rgb) return set_error(B2_ERR_ARG, "scan rendering needs the point colours");
+  if (scan_point_radius < 0) return set_error(B2_ERR_ARG, "scan_point_radius must be >= 0");
+  if (n >= 0xFFFFFFFFull) return set_error(B2_ERR_ARG, "more than 2^32 - 2 points");
+  begin_call(h);
+  GtParams V; B2_TRY(gt_params(h, image_id, &V));
+  const size_t npix = (size_t)V.cam.w * V.cam.h;
+  DevBuf d_xyz, d_cnt, d_rgb, d_depth, d_owner, d_img;
+  struct Rel { DevBuf* b[6]; ~Rel() { for (DevBuf* x : b) x->release(); } } rel{{&d_xyz, &d_cnt, &d_rgb, &d_depth, &d_owner, &d_img}};
+  if (out_occlusion_depth) {
+    if (V.depth) B2_CUDA(cudaMemcpyAsync(out_occlusion_depth, V.depth, npix * 4, cudaMemcpyDeviceToHost, h->stream));
+    else for (size_t i = 0; i < npix; ++i) out_occlusion_depth[i] = std::numeric_limits<float>::infinity();
+  }
+  if (n && (out_gt_depth || inout_scan_rendering_bgr)) {
+    B2_TRY(d_xyz.ensure(n * 12)); B2_TRY(d_cnt.ensure(n * 4));
+    B2_CUDA(cudaMemcpyAsync(d_xyz.p, xyz, n * 12, cudaMemcpyHostToDevice, h->stream));
+    B2_CUDA(cudaMemcpyAsync(d_cnt.p, observation_counts, n * 4, cudaMemcpyHostToDevice, h->stream));
+    if (out_gt_depth) { B2_TRY(d_depth.ensure(npix * 4)); kr_fill_u32<<<divup(npix, 256), 256, 0, h->stream>>>(d_depth.as<unsigned int>(), npix, 0x7f800000u); }
+    if (inout_scan_rendering_bgr) {
+      B2_TRY(d_owner.ensure(npix * 4)); B2_TRY(d_rgb.ensure(n * 3)); B2_TRY(d_img.ensure(npix * 3));
+      B2_CUDA(cudaMemsetAsync(d_owner.p, 0, npix * 4, h->stream));
+      B2_CUDA(cudaMemcpyAsync(d_rgb.p, rgb, n * 3, cudaMemcpyHostToDevice, h->stream));
+      B2_CUDA(cudaMemcpyAsync(d_img.p, inout_scan_rendering_bgr, npix * 3, cudaMemcpyHostToDevice, h->stream));
+    }
+    kg_splat<<<divup(n, 256), 256, 0, h->stream>>>(d_xyz.as<float>(), n, V, d_cnt.as<int>(), scan_point_radius,
+                                                   out_gt_depth ? d_depth.as<unsigned int>() : nullptr, inout_scan_rendering_bgr ? d_owner.as<unsigned int>() : nullptr);
+    ++h->launches;
+    if (out_gt_depth) B2_CUDA(cudaMemcpyAsync(out_gt_depth, d_depth.p, npix * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (inout_scan_rendering_bgr) {
+      kg_paint<<<divup(npix, 256), 256, 0, h->stream>>>(npix, d_owner.as<unsigned int>(), d_rgb.as<unsigned char>(), d_img.as<unsigned char>());
+      ++h->launches;
+      B2_CUDA(cudaMemcpyAsync(inout_scan_rendering_bgr, d_img.p, npix * 3, cudaMemcpyDeviceToHost, h->stream));
+    }
+  } else if (out_gt_depth) {
+    for (size_t i = 0; i < npix; ++i) out_gt_depth[i] = std::numeric_limits<float>::infinity();
+  }
   B2_CUDA(cudaGetLastError());
   end_call(h);
   return B2_OK;

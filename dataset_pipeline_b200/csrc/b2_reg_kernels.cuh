@@ -364,6 +364,52 @@ __global__ void __launch_bounds__(256) kr_min_max_radius(const float* __restrict
   max_radius[pi] = fmaxf(max_radius[pi], (float)((double)point_radius / V.min_scaling_factor));
 }
 
+// GroundTruthCreator (src/exe/ground_truth_creator.cc:44-215). The visibility test both passes share (:66-79, :163-174).
+struct GtParams { Pose3 P; Cam cam; const float* depth; const unsigned char* mask; float occlusion_threshold; };
+__device__ __forceinline__ bool gt_visible(const GtParams& V, const float* __restrict__ xyz, size_t i, int* ox, int* oy, float* oz) {
+  float px, py, pz; rigid(V.P, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &px, &py, &pz);
+  if (!(pz > 0)) return false;
+  float ixx, ixy; cam_project(V.cam, px / pz, py / pz, &ixx, &ixy);
+  const int ix = f2i_x86(ixx + 0.5f), iy = f2i_x86(ixy + 0.5f);
+  if (!(ix >= 0 && iy >= 0 && ix < V.cam.w && iy < V.cam.h)) return false;
+  const size_t pix = (size_t)iy * V.cam.w + ix;
+  if (V.depth != nullptr && !(__ldg(V.depth + pix) + V.occlusion_threshold >= pz)) return false;
+  if (V.mask != nullptr && __ldg(V.mask + pix) == 2) return false;      // opt::MaskType::kEvalObs
+  *ox = ix; *oy = iy; *oz = pz;
+  return true;
+}
+// AccumulateScanObservationsForImage (:44-82)
+__global__ void __launch_bounds__(256) kg_count(const float* __restrict__ xyz, size_t n, GtParams V, int* __restrict__ counts) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int ix, iy; float z;
+  if (gt_visible(V, xyz, i, &ix, &iy, &z)) counts[i] += 1;
+}
+// CreateGroundTruthForImage (:150-190): depth = per-pixel minimum (order independent: atomicMin on the bits of positive floats); the
+// rendering paints squares in scan order, later points over earlier ones = per pixel the HIGHEST point index wins (atomicMax on
+// index + 1), resolved to colours by kg_paint.
+__global__ void __launch_bounds__(256) kg_splat(const float* __restrict__ xyz, size_t n, GtParams V, const int* __restrict__ counts, int radius,
+                                                unsigned int* __restrict__ depth_bits /* nullable */, unsigned int* __restrict__ owner /* nullable */) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || counts[i] < 2) return;
+  int ix, iy; float z;
+  if (!gt_visible(V, xyz, i, &ix, &iy, &z)) return;
+  if (owner != nullptr) {
+    const int min_x = max(0, ix - radius), min_y = max(0, iy - radius), end_x = min(V.cam.w, ix + radius + 1), end_y = min(V.cam.h, iy + radius + 1);
+    for (int y = min_y; y < end_y; ++y) for (int x = min_x; x < end_x; ++x) atomicMax(&owner[(size_t)y * V.cam.w + x], (unsigned int)i + 1u);
+  }
+  if (depth_bits != nullptr) atomicMin(&depth_bits[(size_t)iy * V.cam.w + ix], __float_as_uint(z));
+}
+__global__ void __launch_bounds__(256) kg_paint(size_t npix, const unsigned int* __restrict__ owner, const unsigned char* __restrict__ rgb,
+                                                unsigned char* __restrict__ bgr) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const unsigned int o = owner[p];
+  if (o == 0u) return;
+  const size_t i = (size_t)o - 1;
+  bgr[3 * p] = rgb[3 * i + 2]; bgr[3 * p + 1] = rgb[3 * i + 1]; bgr[3 * p + 2] = rgb[3 * i];
+}
+
 __global__ void __launch_bounds__(256) kr_compact(const unsigned int* __restrict__ flags, const unsigned int* __restrict__ offs,
                                                   const unsigned int* __restrict__ list, size_t count, const float* __restrict__ cx,
                                                   const float* __restrict__ cy, const float* __restrict__ cs, unsigned int* __restrict__ idx,
@@ -1019,13 +1065,22 @@ __global__ void __launch_bounds__(BlockCfg<NI, RIG>::T, BlockCfg<NI, RIG>::CTAS)
   }
 }
 
-// Fixed-order sum of the per-block partials: out[v] = sum_b partials[b][v].
-__global__ void __launch_bounds__(256) kr_reduce_partials(const double* __restrict__ partials, int nblocks, int nvals, double* __restrict__ out) {
-  for (int v = threadIdx.x; v < nvals; v += blockDim.x) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * nvals + v];
-    out[v] = s;
+// Fixed-order sum of the per-block partials: out[v] = sum_b partials[b][v]. One CTA of 64 threads per value: thread t adds the blocks
+// t, t + 64, ... in order, then a fixed shared-memory tree combines the 64 partial sums (deterministic; a single serial loop over
+// ~600 blocks per value cost 20-40 us per launch and showed up 240 times per accumulate call).
+__global__ void __launch_bounds__(64) kr_reduce_partials(const double* __restrict__ partials, int nblocks, int nvals, double* __restrict__ out) {
+  const int v = blockIdx.x;
+  if (v >= nvals) return;
+  double s = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += 64) s += partials[(size_t)b * nvals + v];
+  __shared__ double sm[64];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 32; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
   }
+  if (threadIdx.x == 0) out[v] = sm[0];
 }
 
 // K14 (color_optimizer.cc:84-108): one image at a time; a point has at most one observation per image and scale, so the

@@ -46,6 +46,8 @@ def _L():
     L.b2_reg_num_variables.argtypes = [vp, ip]
     L.b2_reg_render_depth.argtypes = [vp, C.c_int, ip, ip, ip, fp]
     L.b2_reg_min_max_point_radius.argtypes = [vp, fp, C.c_size_t, C.c_double, fp, fp]
+    L.b2_reg_gt_accumulate_observations.argtypes = [vp, C.c_int, fp, C.c_size_t, ip]
+    L.b2_reg_gt_create.argtypes = [vp, C.c_int, fp, C.POINTER(C.c_uint8), C.c_size_t, ip, C.c_int, fp, fp, C.POINTER(C.c_uint8)]
     L.b2_reg_create_observations.argtypes = [vp, C.c_int]
     L.b2_reg_num_observations.argtypes = [vp, C.c_int, C.c_int, u64p]
     L.b2_reg_get_observations.argtypes = [vp, C.c_int, C.c_int, u64p, fp, fp, fp, u8]
@@ -140,6 +142,7 @@ class Registration:
         p = np.ascontiguousarray(params, np.float32); out = C.c_int32(0)
         _lib.check(_L().b2_reg_add_intrinsics(self._h, camera_model, width, height, _f(p), p.size, C.byref(out)))
         self.n_intr += 1; self.intr_np.append(int(p.size))
+        self.__dict__.setdefault("_intr_sizes", []).append((int(width), int(height)))
         return out.value
 
     def set_camera_mask(self, intrinsics_id, mask):
@@ -244,6 +247,33 @@ class Registration:
         hi = np.full(n, -np.inf, np.float32) if max_radius is None else np.ascontiguousarray(max_radius, np.float32).copy()
         _lib.check(_L().b2_reg_min_max_point_radius(self._h, _f(x), n, float(min_scaling_factor), _f(lo), _f(hi)))
         return lo, hi
+
+    # ---- GroundTruthCreator (src/exe/ground_truth_creator.cc) ----
+    def AccumulateScanObservationsForImage(self, image, points, observation_counts):
+        """observation_counts (int32, n) += 1 for the scan points visible in `image` (:44-82); returns the updated array."""
+        x = np.ascontiguousarray(points, np.float32)
+        c = np.ascontiguousarray(observation_counts, np.int32).copy()
+        _lib.check(_L().b2_reg_gt_accumulate_observations(self._h, int(image), _f(x), x.shape[0], c.ctypes.data_as(C.POINTER(C.c_int32))))
+        return c
+
+    def CreateGroundTruthForImage(self, image, points, colors_rgb, observation_counts, scan_point_radius=2, scan_rendering_bgr=None,
+                                  write_depth_maps=True, write_occlusion_depth=True):
+        """-> (occlusion_depth or None, ground_truth_depth or None, scan_rendering or None)   (:84-215, without the file I/O)"""
+        x = np.ascontiguousarray(points, np.float32)
+        c = np.ascontiguousarray(observation_counts, np.int32)
+        w, h = self._gt_size(image)
+        occ = np.zeros((h, w), np.float32) if write_occlusion_depth else None
+        gt = np.zeros((h, w), np.float32) if write_depth_maps else None
+        rgb = np.ascontiguousarray(colors_rgb, np.uint8) if colors_rgb is not None else None
+        ren = np.ascontiguousarray(scan_rendering_bgr, np.uint8).copy() if scan_rendering_bgr is not None else None
+        u8 = C.POINTER(C.c_uint8)
+        _lib.check(_L().b2_reg_gt_create(self._h, int(image), _f(x), rgb.ctypes.data_as(u8) if rgb is not None else None, x.shape[0],
+                                        c.ctypes.data_as(C.POINTER(C.c_int32)), int(scan_point_radius), _f(occ) if occ is not None else None,
+                                        _f(gt) if gt is not None else None, ren.ctypes.data_as(u8) if ren is not None else None))
+        return occ, gt, ren
+
+    def _gt_size(self, image):
+        return self._intr_sizes[self.image_intr[int(image)]]
 
     def render_depth(self, image):
         w, h, s = C.c_int32(), C.c_int32(), C.c_int32()

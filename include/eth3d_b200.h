@@ -148,7 +148,7 @@ int b2_find_correspondences(const float* src_xyz, size_t n_src, const float* tgt
  * icp_scan_aligner.cc:323-330 and normal_estimator.cc:177-194: setInputCloud, setKSearch(k), setViewPoint, compute.
  * out_nxyz_curv: n x 4 floats (normal_x, normal_y, normal_z, curvature); NaN where fewer than 3 neighbours
  * (two_pass_normal_3d.h:100-105). *is_dense = 0 if any NaN was written. out_knn_idx (nullable): n x k neighbour
- * indices sorted by (distance, index), -1 padded.
+ * indices sorted by (distance, index), -1 padded. out_nxyz_curv may be NULL when out_knn_idx is given (neighbour lists only).
  * ------------------------------------------------------------------------------------------------------------------ */
 int b2_normals_estimate(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3],
                         float* out_nxyz_curv, int32_t* out_knn_idx, int* is_dense);
@@ -324,6 +324,19 @@ int b2_reg_run_on_current_scale(b2_reg* h, int max_num_iterations, float max_cha
                                 int iterations_without_new_optimum_threshold, int print_progress, double* optimum_cost,
                                 int* converged, int* iterations);
 int b2_reg_last_stats(b2_reg* h, b2_reg_stats* out);
+/* GroundTruthCreator (src/exe/ground_truth_creator.cc) on the images, intrinsics and occlusion geometry of the handle.
+ * A scan point is visible in an image when it lies in front of the camera, projects inside the highest-resolution image
+ * (intrinsics.model(0)), is not behind the occlusion depth map rendered at intrinsics.min_image_scale (+ occlusion_depth_threshold) and
+ * does not fall on a kEvalObs (= 2) pixel of the image mask (:66-79, :163-174).
+ * b2_reg_gt_accumulate_observations = AccumulateScanObservationsForImage (:44-82): observation_counts[i] += 1 for every visible point
+ * (exact counts; the reference's unsynchronised increments under `omp parallel for` are a race, not a semantic).
+ * b2_reg_gt_create = CreateGroundTruthForImage (:84-215) without the file I/O. out_occlusion_depth (nullable, w x h floats); out_gt_depth
+ * (nullable): per-pixel minimum depth of the visible points with observation_counts >= 2, +inf elsewhere; inout_scan_rendering_bgr
+ * (nullable, w x h x 3, initialised by the caller with the image as cv::imread gives it): squares of 2 * scan_point_radius + 1 pixels in
+ * the point's colour (rgb: n x 3), points painted in index order, later over earlier. Points = all scans concatenated in scan order. */
+int b2_reg_gt_accumulate_observations(b2_reg* h, int image_id, const float* xyz, size_t n, int32_t* observation_counts);
+int b2_reg_gt_create(b2_reg* h, int image_id, const float* xyz, const uint8_t* rgb, size_t n, const int32_t* observation_counts, int scan_point_radius,
+                     float* out_occlusion_depth, float* out_gt_depth, uint8_t* inout_scan_rendering_bgr);
 /* ComputeMinMaxPointRadius (src/opt/multi_scale_point_cloud.cc:126-184) over all images, as CreateMultiScalePointCloud calls it (:232-255):
  * a point visible in an image (visibility_estimator.cc:296-364: in front, inside, not occluded, not masked, not saturated, at the
  * occlusion-check image scale) gets the radius that spans 0.5 px at the finest image scale (ImageToNormalized through the undistortion

@@ -545,6 +545,29 @@ class Registration:
 
     ComputeMinMaxPointRadius = min_max_point_radius
 
+    # ---- GroundTruthCreator (ground_truth_creator.cc:44-215) ----
+    def gt_accumulate_observations(self, image, points, counts):
+        x = _c32(points); c = np.ascontiguousarray(counts, np.int32).copy()
+        L = lib()
+        L.orc_reg_gt_accumulate_observations.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_int32)]
+        L.orc_reg_gt_accumulate_observations.restype = None
+        L.orc_reg_gt_accumulate_observations(self._h, int(image), _f(x), x.shape[0], c.ctypes.data_as(C.POINTER(C.c_int32)))
+        return c
+
+    def gt_create(self, image, points, rgb, counts, radius, size_wh, rendering_bgr=None):
+        x = _c32(points); c = np.ascontiguousarray(counts, np.int32); col = np.ascontiguousarray(rgb, np.uint8)
+        w, h = size_wh
+        occ = np.zeros((h, w), np.float32); gt = np.zeros((h, w), np.float32)
+        ren = np.ascontiguousarray(rendering_bgr, np.uint8).copy() if rendering_bgr is not None else None
+        u8 = C.POINTER(C.c_uint8)
+        L = lib()
+        L.orc_reg_gt_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), u8, C.c_size_t, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_float),
+                                        C.POINTER(C.c_float), u8]
+        L.orc_reg_gt_create.restype = None
+        L.orc_reg_gt_create(self._h, int(image), _f(x), col.ctypes.data_as(u8), x.shape[0], c.ctypes.data_as(C.POINTER(C.c_int32)), int(radius), _f(occ), _f(gt),
+                            ren.ctypes.data_as(u8) if ren is not None else None)
+        return occ, gt, ren
+
     def render_depth(self, image):
         w, h = C.c_int(), C.c_int()
         lib().orc_reg_render_depth(self._h, image, C.byref(w), C.byref(h), None)

@@ -100,6 +100,11 @@ int orc_reg_image_scale_count(orc_reg*);
 int orc_reg_num_variables(orc_reg*);
 int orc_reg_render_depth(orc_reg*, int image, int* w, int* h, float* out_or_null);
 void orc_reg_create_observations(orc_reg*, int border);
+/* GroundTruthCreator (src/exe/ground_truth_creator.cc:44-215): visibility counts per scan point, then per image the occlusion depth, the
+ * ground-truth depth map and the scan rendering (BGR, in/out). */
+void orc_reg_gt_accumulate_observations(orc_reg*, int image, const float* xyz, size_t n, int32_t* counts);
+void orc_reg_gt_create(orc_reg*, int image, const float* xyz, const uint8_t* rgb, size_t n, const int32_t* counts, int scan_point_radius,
+                       float* occlusion_depth, float* gt_depth, uint8_t* rendering_bgr);
 /* ComputeMinMaxPointRadius over all images (multi_scale_point_cloud.cc:126-184, 232-255); min/max in-out (+inf / -inf initially) */
 void orc_reg_min_max_point_radius(orc_reg*, const float* xyz, size_t n, double min_scaling_factor, float* min_radius, float* max_radius);
 uint64_t orc_reg_num_observations(orc_reg*, int image, int point_scale);

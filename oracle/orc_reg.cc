@@ -713,6 +713,55 @@ void orc_reg_min_max_point_radius(orc_reg* h, const float* xyz, size_t n, double
   }
 }
 
+// ---- GroundTruthCreator (src/exe/ground_truth_creator.cc:44-215) ----
+// The visibility test both passes share (:66-79, :163-174): in front of the camera, inside the highest-resolution image, not behind
+// the occlusion depth map rendered at intrinsics.min_image_scale, not on a kEvalObs (= 2) pixel of the image mask.
+static bool gt_visible(const orc_reg* h, const Image& im, const Intrinsics& intr, const Pinhole& cam, const ImgF& depth, const float R[9], const float* p,
+                       int* ox, int* oy, float* oz) {
+  V3f pp; rigid_pp(R, im.image_T_global.t, p, &pp);
+  if (!(pp.z > 0)) return false;
+  float px, py; cam.project(pp.x / pp.z, pp.y / pp.z, &px, &py);
+  const int ix = f2i(px + 0.5f), iy = f2i(py + 0.5f);
+  if (!(ix >= 0 && iy >= 0 && ix < cam.w && iy < cam.h && depth.d[(size_t)iy * depth.w + ix] + h->prm.occlusion_depth_threshold >= pp.z)) return false;
+  if (!im.mask.empty() && !im.mask[0].d.empty() && im.mask[0].at(iy, ix) == 2) return false;
+  *ox = ix; *oy = iy; *oz = pp.z;
+  return true;
+}
+// AccumulateScanObservationsForImage (:44-82): counts[i] += 1 for every scan point visible in `image`.
+void orc_reg_gt_accumulate_observations(orc_reg* h, int image, const float* xyz, size_t n, int32_t* counts) {
+  const Image& im = h->st.images[image]; const Intrinsics& intr = h->st.intr[im.intrinsics_id];
+  const Pinhole& cam = intr.model(0);
+  const ImgF depth = render_depth(h, intr, im, intr.min_image_scale);
+  float R[9]; quat_to_matrix(im.image_T_global.q, R);
+  for (size_t i = 0; i < n; ++i) { int ix, iy; float z; if (gt_visible(h, im, intr, cam, depth, R, &xyz[3 * i], &ix, &iy, &z)) counts[i] += 1; }
+}
+// CreateGroundTruthForImage (:84-215) without the file I/O: occlusion depth (nullable), ground-truth depth = per-pixel minimum depth of
+// the visible points observed in >= 2 images (+inf elsewhere), scan rendering (in/out BGR image, nullable): squares of
+// 2 * scan_point_radius + 1 pixels painted in scan order, later points over earlier ones.
+void orc_reg_gt_create(orc_reg* h, int image, const float* xyz, const uint8_t* rgb, size_t n, const int32_t* counts, int scan_point_radius,
+                       float* occlusion_depth, float* gt_depth, uint8_t* rendering_bgr) {
+  const Image& im = h->st.images[image]; const Intrinsics& intr = h->st.intr[im.intrinsics_id];
+  const Pinhole& cam = intr.model(0);
+  const ImgF depth = render_depth(h, intr, im, intr.min_image_scale);
+  if (occlusion_depth) std::memcpy(occlusion_depth, depth.d.data(), depth.d.size() * sizeof(float));
+  if (gt_depth) for (size_t i = 0; i < (size_t)cam.w * cam.h; ++i) gt_depth[i] = std::numeric_limits<float>::infinity();
+  float R[9]; quat_to_matrix(im.image_T_global.q, R);
+  for (size_t i = 0; i < n; ++i) {
+    if (counts[i] < 2) continue;
+    int ix, iy; float z;
+    if (!gt_visible(h, im, intr, cam, depth, R, &xyz[3 * i], &ix, &iy, &z)) continue;
+    if (rendering_bgr && rgb) {
+      const int min_x = std::max(0, ix - scan_point_radius), min_y = std::max(0, iy - scan_point_radius);
+      const int end_x = std::min(cam.w, ix + scan_point_radius + 1), end_y = std::min(cam.h, iy + scan_point_radius + 1);
+      for (int y = min_y; y < end_y; ++y) for (int x = min_x; x < end_x; ++x) {
+        uint8_t* px = rendering_bgr + 3 * ((size_t)y * cam.w + x);
+        px[0] = rgb[3 * i + 2]; px[1] = rgb[3 * i + 1]; px[2] = rgb[3 * i];
+      }
+    }
+    if (gt_depth) gt_depth[(size_t)iy * cam.w + ix] = std::min(gt_depth[(size_t)iy * cam.w + ix], z);
+  }
+}
+
 // CreateObservationsForAllImages + DetermineIfAllNeighborsAreObserved (optimizer.cc:123-128)
 void orc_reg_create_observations(orc_reg* h, int border) {
   h->obs.assign(h->st.images.size(), {}); h->nbr_obs.assign(h->st.images.size(), {});
