@@ -64,7 +64,7 @@ struct b2_icp {
   std::vector<std::unique_ptr<Direction>> dirs;   // pool, reused across outer iterations
   int ndirs = 0;
   // scratch
-  DevBuf bbox_partial, cub_tmp, cell_counts, rec_a, rec_b, rec_c, segs_dev, poses_dev, partials, segsum, eq_dev, scatter_m, scatter_d;
+  DevBuf bbox_partial, cub_tmp, cell_counts, rec_a, rec_b, rec_c, segs_dev, poses_dev, partials, xpartials, segsum, xsegsum, eq_dev, scatter_m, scatter_d;
   PinnedBuf pin_bbox, pin_counts, pin_eq, pin_poses, pin_segs, pin_misc;
   // last outer iteration
   b2_icp_stats stats;
@@ -200,56 +200,84 @@ static int compute_grid(b2_icp* h, float max_dist, GridParams* g, int* key_bits)
   return B2_OK;
 }
 
-// One streaming pass (K5 + K6) at the given increments; returns [H|b|cost|extras] in h->pin_eq (host) after the
-// optional cross-rank reduction.
-static int run_pass(b2_icp* h, const std::vector<Pose>& poses, bool with_h, int nv) {
-  const int nc = (int)poses.size();
+// One streaming pass (K5 + K6) at the given increments; returns [H|b|cost|extras|costs of the speculative trials] in h->pin_eq (host)
+// after the optional cross-rank reduction. trials[0] is the state the normal equations (with_h) and the cost are evaluated at;
+// trials[1..] (at most kMaxExtraTrials) are further LM trial states whose costs ride along on the same read of the records.
+template <bool WITH_H, int NX>
+static int launch_accumulate_tma(b2_icp* h, int nseg, int nc) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(k_accumulate_tma<WITH_H, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
+    attr_set = true;
+  }
+  k_accumulate_tma<WITH_H, NX><<<h->grid_acc, kAccThreads, kTmaSmemBytes, h->stream>>>(
+      h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>(), h->segs_dev.as<Segment>(), nseg, h->poses_dev.as<CloudPose>(), nc,
+      h->total_records, h->per_cta, h->partials.as<double>(), h->xpartials.as<double>());
+  return B2_OK;
+}
+
+static int run_pass(b2_icp* h, const std::vector<std::vector<Pose>>& trials, bool with_h, int nv) {
+  const int nc = (int)trials[0].size();
+  const int nx = (int)trials.size() - 1;
+  if (nx < 0 || nx > kMaxExtraTrials) return set_error(B2_ERR_ARG, "run_pass: bad trial count");
   CloudPose* pp = h->pin_poses.as<CloudPose>();
-  for (int i = 0; i < nc; ++i) { quat_matrix(poses[i].q, pp[i].R); for (int k = 0; k < 3; ++k) pp[i].t[k] = poses[i].t[k]; }
-  B2_CUDA(cudaMemcpyAsync(h->poses_dev.p, pp, sizeof(CloudPose) * nc, cudaMemcpyHostToDevice, h->stream));
+  for (int j = 0; j <= nx; ++j)
+    for (int i = 0; i < nc; ++i) {
+      CloudPose& o = pp[(size_t)j * nc + i];
+      quat_matrix(trials[j][i].q, o.R); for (int k = 0; k < 3; ++k) o.t[k] = trials[j][i].t[k];
+    }
+  B2_CUDA(cudaMemcpyAsync(h->poses_dev.p, pp, sizeof(CloudPose) * nc * (1 + nx), cudaMemcpyHostToDevice, h->stream));
   const int nseg = (int)h->segs_host.size();
-  const size_t eq_count = (size_t)nv * nv + nv + 3;
+  const size_t eq_count = (size_t)nv * nv + nv + 3 + kMaxExtraTrials;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->total_records > 0) {
     B2_CUDA(cudaEventCreate(&e0)); B2_CUDA(cudaEventCreate(&e1));
     B2_CUDA(cudaEventRecord(e0, h->stream));
     static const bool use_tma = [] { const char* e = getenv("B2_K5"); return !(e && std::string(e) == "ldg"); }();
-    if (with_h && use_tma) {
+    if (use_tma) {
       // Blackwell path: record tiles staged by cp.async.bulk + mbarrier (bit-identical results, see k_accumulate_tma)
-      static bool attr_set = false;
-      if (!attr_set) {
-        B2_CUDA(cudaFuncSetAttribute(k_accumulate_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
-        attr_set = true;
+      switch ((with_h ? 4 : 0) + nx) {
+        case 0: B2_TRY((launch_accumulate_tma<false, 0>(h, nseg, nc))); break;
+        case 1: B2_TRY((launch_accumulate_tma<false, 1>(h, nseg, nc))); break;
+        case 2: B2_TRY((launch_accumulate_tma<false, 2>(h, nseg, nc))); break;
+        case 3: B2_TRY((launch_accumulate_tma<false, 3>(h, nseg, nc))); break;
+        case 4: B2_TRY((launch_accumulate_tma<true, 0>(h, nseg, nc))); break;
+        case 5: B2_TRY((launch_accumulate_tma<true, 1>(h, nseg, nc))); break;
+        case 6: B2_TRY((launch_accumulate_tma<true, 2>(h, nseg, nc))); break;
+        default: B2_TRY((launch_accumulate_tma<true, 3>(h, nseg, nc))); break;
       }
-      k_accumulate_tma<true><<<h->grid_acc, kAccThreads, kTmaSmemBytes, h->stream>>>(h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>(),
-                                                                                   h->segs_dev.as<Segment>(), nseg, h->poses_dev.as<CloudPose>(),
-                                                                                   h->total_records, h->per_cta, h->partials.as<double>());
-    } else if (with_h)
-      k_accumulate<true><<<h->grid_acc, kAccThreads, 0, h->stream>>>(h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>(),
-                                                                    h->segs_dev.as<Segment>(), nseg, h->poses_dev.as<CloudPose>(),
-                                                                    h->total_records, h->per_cta, h->partials.as<double>());
-    else
-      k_accumulate<false><<<h->grid_acc, kAccThreads, 0, h->stream>>>(h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>(),
-                                                                     h->segs_dev.as<Segment>(), nseg, h->poses_dev.as<CloudPose>(),
-                                                                     h->total_records, h->per_cta, h->partials.as<double>());
+    } else {
+      if (nx != 0) return set_error(B2_ERR_STATE, "run_pass: the register-staged K5 has no speculative trials");
+      if (with_h)
+        k_accumulate<true><<<h->grid_acc, kAccThreads, 0, h->stream>>>(h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>(),
+                                                                      h->segs_dev.as<Segment>(), nseg, h->poses_dev.as<CloudPose>(),
+                                                                      h->total_records, h->per_cta, h->partials.as<double>());
+      else
+        k_accumulate<false><<<h->grid_acc, kAccThreads, 0, h->stream>>>(h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>(),
+                                                                       h->segs_dev.as<Segment>(), nseg, h->poses_dev.as<CloudPose>(),
+                                                                       h->total_records, h->per_cta, h->partials.as<double>());
+    }
     B2_CUDA(cudaEventRecord(e1, h->stream));
     h->acc_events.emplace_back(e0, e1);
     ++h->launches;
   }
   double local_pairs = (double)nseg, local_corr = (double)h->total_records;
+  const int nxf = h->total_records > 0 ? nx : 0;
   if (with_h)
     k_finalize<true><<<1, 1024, 0, h->stream>>>(h->partials.as<double>(), h->segs_dev.as<Segment>(), nseg, h->grid_acc, h->per_cta, nv,
-                                                h->segsum.as<double>(), h->eq_dev.as<double>(), local_pairs, local_corr);
+                                                h->segsum.as<double>(), h->eq_dev.as<double>(), local_pairs, local_corr,
+                                                h->xpartials.as<double>(), nxf, h->xsegsum.as<double>());
   else
     k_finalize<false><<<1, 1024, 0, h->stream>>>(h->partials.as<double>(), h->segs_dev.as<Segment>(), nseg, h->grid_acc, h->per_cta, nv,
-                                                 h->segsum.as<double>(), h->eq_dev.as<double>(), local_pairs, local_corr);
+                                                 h->segsum.as<double>(), h->eq_dev.as<double>(), local_pairs, local_corr,
+                                                 h->xpartials.as<double>(), nxf, h->xsegsum.as<double>());
   ++h->launches;
   B2_CUDA(cudaGetLastError());
   if (h->cfg.world_size > 1) {
     // Data-parallel exchange: ONE sum-allreduce of the packed normal equations per pass (NCCL over NVLink on the host side).
     double* buf = h->eq_dev.as<double>();
     size_t off = 0, cnt = eq_count;
-    if (!with_h) { off = (size_t)nv * nv + nv; cnt = 3; }
+    if (!with_h) { off = (size_t)nv * nv + nv; cnt = 3 + kMaxExtraTrials; }
     if (h->cfg.comm) {
       B2_TRY(b2_comm_allreduce_f64(h->cfg.comm, buf + off, cnt, (void*)h->stream));   // NCCL on the handle's stream: no host sync
     } else {
@@ -453,23 +481,38 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   unsigned long long per = (total + h->grid_acc - 1) / (unsigned long long)h->grid_acc;
   per = std::max<unsigned long long>(kAccThreads, (per + kAccThreads - 1) / kAccThreads * kAccThreads);
   h->per_cta = per;
-  const size_t eq_count = (size_t)nv * nv + nv + 3;
+  const size_t eq_count = (size_t)nv * nv + nv + 3 + kMaxExtraTrials;
   B2_TRY(h->partials.ensure(sizeof(double) * kAccVals * (size_t)std::max(1, nseg) * h->grid_acc));
+  B2_TRY(h->xpartials.ensure(sizeof(double) * kMaxExtraTrials * (size_t)std::max(1, nseg) * h->grid_acc));
   B2_TRY(h->segsum.ensure(sizeof(double) * kAccVals * std::max(1, nseg)));
+  B2_TRY(h->xsegsum.ensure(sizeof(double) * kMaxExtraTrials * std::max(1, nseg)));
   B2_TRY(h->eq_dev.ensure(sizeof(double) * eq_count));
   B2_TRY(h->pin_eq.ensure(sizeof(double) * eq_count));
-  B2_TRY(h->poses_dev.ensure(sizeof(CloudPose) * nc));
-  B2_TRY(h->pin_poses.ensure(sizeof(CloudPose) * nc));
+  B2_TRY(h->poses_dev.ensure(sizeof(CloudPose) * nc * (1 + kMaxExtraTrials)));
+  B2_TRY(h->pin_poses.ensure(sizeof(CloudPose) * nc * (1 + kMaxExtraTrials)));
 
   // ---- compute() (icp_point_to_plane_impl.h:115-293): LM over the fixed correspondence sets ----
-  std::vector<Pose> poses(nc), trial(nc);
-  std::vector<double> H((size_t)nv * nv), b(nv), Ht, bt, x(nv), HL;
+  // The reference evaluates the tries of one LM iteration one after the other (lambda doubles after each rejection, :217-285); the
+  // trial states do not depend on the outcome of earlier tries, so a pass evaluates the costs of several consecutive tries at once
+  // (see k_accumulate_tma) and the decisions are then taken in the reference's order. B2_LM_SPEC="a,b": extra tries riding along with
+  // the first pass of an iteration (which also carries the normal equations at its first try) / with the follow-up passes.
+  static const std::pair<int, int> spec = [] {
+    int a = 1, b = kMaxExtraTrials;
+    if (const char* e = getenv("B2_LM_SPEC")) { if (sscanf(e, "%d,%d", &a, &b) < 2) b = a; }
+    if (const char* e = getenv("B2_K5")) if (std::string(e) == "ldg") a = b = 0;
+    return std::make_pair(std::max(0, std::min(a, kMaxExtraTrials)), std::max(0, std::min(b, kMaxExtraTrials)));
+  }();
+  std::vector<Pose> poses(nc);
+  std::vector<std::vector<Pose>> batch;
+  std::vector<double> H((size_t)nv * nv), b(nv), x(nv), HL;
   const double* eq = h->pin_eq.as<double>();
-  B2_TRY(run_pass(h, poses, true, nv));
-  std::copy(eq, eq + (size_t)nv * nv, H.begin()); std::copy(eq + (size_t)nv * nv, eq + (size_t)nv * nv + nv, b.begin());
-  double cost = eq[(size_t)nv * nv + nv];
-  h->stats.num_pairs = (int)std::llround(eq[(size_t)nv * nv + nv + 1]);
-  h->stats.num_correspondences = (uint64_t)std::llround(eq[(size_t)nv * nv + nv + 2]);
+  const size_t cost_at = (size_t)nv * nv + nv;
+  batch.assign(1, poses);
+  B2_TRY(run_pass(h, batch, true, nv));
+  std::copy(eq, eq + (size_t)nv * nv, H.begin()); std::copy(eq + (size_t)nv * nv, eq + cost_at, b.begin());
+  double cost = eq[cost_at];
+  h->stats.num_pairs = (int)std::llround(eq[cost_at + 1]);
+  h->stats.num_correspondences = (uint64_t)std::llround(eq[cost_at + 2]);
   h->stats.local_correspondences = total;
   h->stats.num_variables = nv;
   h->stats.first_cost = cost;
@@ -480,32 +523,48 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
     ++h->stats.inner_iterations;
     bool applied = false;
     int ntries = 0;
-    for (int lm = 0; lm < 10; ++lm) {
-      ++ntries;
-      HL = H;
-      for (int i = 0; i < nv; ++i) HL[(size_t)i * nv + i] += lambda;
-      if (nv > 0) sym_solve(HL, nv, b.data(), x.data());
-      trial = poses;
-      for (int ci = 1; ci < nc; ++ci) {
-        double neg[6];
-        for (int k = 0; k < 6; ++k) neg[k] = -x[6 * (ci - 1) + k];
-        trial[ci] = pose_mul(pose_exp(neg), poses[ci]);
+    for (int lm = 0; lm < 10 && !applied;) {
+      // tries lm .. lm + nb - 1 of this iteration: damping lambda, 2 lambda, 4 lambda, ...
+      const int nb = std::min(10 - lm, 1 + (lm == 0 ? spec.first : spec.second));
+      const bool with_h = lm == 0;
+      batch.assign(nb, poses);
+      double lam_j = lambda;
+      for (int j = 0; j < nb; ++j, lam_j = 2.f * lam_j) {
+        HL = H;
+        for (int i = 0; i < nv; ++i) HL[(size_t)i * nv + i] += lam_j;
+        if (nv > 0) sym_solve(HL, nv, b.data(), x.data());
+        for (int ci = 1; ci < nc; ++ci) {
+          double neg[6];
+          for (int k = 0; k < 6; ++k) neg[k] = -x[6 * (ci - 1) + k];
+          batch[j][ci] = pose_mul(pose_exp(neg), poses[ci]);
+        }
       }
-      // Speculative fused pass: cost at the trial poses AND the normal equations there; if the try is accepted they are
-      // exactly what the next iteration of compute() would recompute (same poses, same arithmetic).
-      B2_TRY(run_pass(h, trial, true, nv));
-      ++h->stats.lm_tries_total;
-      const double new_cost = eq[(size_t)nv * nv + nv];
-      if (new_cost < cost) {
-        poses = trial;
-        std::copy(eq, eq + (size_t)nv * nv, H.begin()); std::copy(eq + (size_t)nv * nv, eq + (size_t)nv * nv + nv, b.begin());
-        cost = new_cost;
-        lambda = 0.5f * lambda;
-        applied = true;
-        break;
-      } else {
-        lambda = 2.f * lambda;
+      // Fused pass: the costs at the nb trial states and (first pass of an iteration) the normal equations at its first try; if
+      // that try is accepted they are exactly what the next iteration of compute() would recompute (same poses, same arithmetic).
+      B2_TRY(run_pass(h, batch, with_h, nv));
+      for (int j = 0; j < nb; ++j) {
+        ++ntries;
+        ++h->stats.lm_tries_total;
+        const double new_cost = j == 0 ? eq[cost_at] : eq[cost_at + 3 + (j - 1)];
+        if (new_cost < cost) {
+          poses = batch[j];
+          if (j == 0 && with_h) {
+            std::copy(eq, eq + (size_t)nv * nv, H.begin()); std::copy(eq + (size_t)nv * nv, eq + cost_at, b.begin());
+          } else {
+            // accepted a try whose normal equations were not speculated: one pass at the accepted state
+            batch.assign(1, poses);
+            B2_TRY(run_pass(h, batch, true, nv));
+            std::copy(eq, eq + (size_t)nv * nv, H.begin()); std::copy(eq + (size_t)nv * nv, eq + cost_at, b.begin());
+          }
+          cost = new_cost;
+          lambda = 0.5f * lambda;
+          applied = true;
+          break;
+        } else {
+          lambda = 2.f * lambda;
+        }
       }
+      lm += nb;
     }
     h->tries.push_back(ntries);
     if (!applied) break;
@@ -625,7 +684,7 @@ int b2_icp_destroy(b2_icp* h) {
   free_cloud(h->fixed.get());
   for (auto& d : h->dirs) for (DevBuf* b : {&d->match, &d->d2, &d->flags, &d->offs}) b->release();
   for (DevBuf* b : {&h->bbox_partial, &h->cub_tmp, &h->cell_counts, &h->rec_a, &h->rec_b, &h->rec_c, &h->segs_dev, &h->poses_dev, &h->partials,
-                    &h->segsum, &h->eq_dev, &h->scatter_m, &h->scatter_d}) b->release();
+                    &h->segsum, &h->eq_dev, &h->scatter_m, &h->scatter_d, &h->xpartials, &h->xsegsum}) b->release();
   for (PinnedBuf* b : {&h->pin_bbox, &h->pin_counts, &h->pin_eq, &h->pin_poses, &h->pin_segs, &h->pin_misc}) b->release();
   for (auto& pr : h->acc_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto& pr : h->nn_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }

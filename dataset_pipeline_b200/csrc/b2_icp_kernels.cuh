@@ -510,6 +510,12 @@ k_accumulate(const float4* __restrict__ ra, const float4* __restrict__ rb, const
 // register-staged variant above runs out of (28 fp64 accumulators per thread). Same record partition, same reduction tree:
 // results are bit-identical to k_accumulate.
 // ------------------------------------------------------------------------------------------------------------------
+// Speculative LM trials (NX > 0): the poses of NX further trial states (the next damping factors of the LM loop,
+// icp_point_to_plane_impl.h:217-285: lambda doubles after every rejected try) ride along with the pass. Their costs are evaluated on
+// the records while these are in registers, with the arithmetic, record partition and reduction tree of the trial-0 cost, so every
+// value is bit-identical to what a pass of its own would return and the accept / reject sequence is unchanged; a rejected chain of
+// 10 tries then costs 3-4 passes over the 16 GB of records instead of 10. Extra poses are staged in shared memory per segment.
+static constexpr int kMaxExtraTrials = 3;
 static constexpr int kTmaStages = 4;
 static constexpr int kTmaTile = 2 * kAccThreads;                   // records per tile: two per consumer thread
 static constexpr size_t kTmaSmemBytes = (size_t)kTmaStages * 3 * kTmaTile * 16;
@@ -547,14 +553,18 @@ struct TileCursor {
   __device__ __forceinline__ void advance(const Segment* __restrict__ segs) { r += count(); if (r >= seg_end) { ++seg; settle(segs); } }
 };
 
-template <bool WITH_H>
+template <bool WITH_H, int NX>
 __global__ void __launch_bounds__(kAccThreads, 2)
 k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, const float4* __restrict__ rc,
-                 const Segment* __restrict__ segs, int nseg, const CloudPose* __restrict__ poses, unsigned long long total,
-                 unsigned long long per_cta, double* __restrict__ partials /* [nseg][gridDim.x][kAccVals] */) {
+                 const Segment* __restrict__ segs, int nseg, const CloudPose* __restrict__ poses /* [1 + NX][nclouds] */, int nclouds,
+                 unsigned long long total, unsigned long long per_cta, double* __restrict__ partials /* [nseg][gridDim.x][kAccVals] */,
+                 double* __restrict__ xpartials /* [nseg][gridDim.x][kMaxExtraTrials] */) {
   constexpr int NV = WITH_H ? kAccVals : 1;
+  constexpr int NXS = NX > 0 ? NX : 1;
   extern __shared__ __align__(128) unsigned char tile_smem[];
   __shared__ double red[kAccThreads / 32][NV];
+  __shared__ double xred[kAccThreads / 32][NXS];
+  __shared__ __align__(16) float xpose[NXS][24];                 // per extra trial: source pose (R, t), target pose (R, t)
   __shared__ __align__(8) unsigned long long full_bar[kTmaStages], empty_bar[kTmaStages];
   const unsigned long long r_begin = (unsigned long long)blockIdx.x * per_cta;
   const unsigned long long r_end = min(total, r_begin + per_cta);
@@ -595,6 +605,18 @@ k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, c
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    double xacc[NXS];
+#pragma unroll
+    for (int j = 0; j < NXS; ++j) xacc[j] = 0.0;
+    if (NX > 0) {   // (the reductions at the end of the previous segment separate its readers from this write)
+      if ((int)threadIdx.x < NX * 24) {
+        const int j = threadIdx.x / 24, w = threadIdx.x % 24;
+        const CloudPose* P = poses + (size_t)(1 + j) * nclouds + (w < 12 ? sg.src : sg.tgt);
+        const int q = w % 12;
+        xpose[j][w] = q < 9 ? __ldg(&P->R[q]) : __ldg(&P->t[q - 9]);
+      }
+      __syncthreads();
+    }
     for (unsigned long long r = r0; r < e; r += kTmaTile, ++it) {
       if (threadIdx.x == 0 && prod.valid()) produce();            // refill the stage released one tile ago
       const unsigned int s = it % kTmaStages, cnt = (unsigned int)min((unsigned long long)kTmaTile, e - r);
@@ -608,12 +630,28 @@ k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, c
       if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[s]);     // this warp's values are in registers: one arrival per warp
       if (m0) { if (WITH_H) accumulate_record(a0, b0, c0, Rs, ts, Rt, tt, acc); else cost_record(a0, b0, c0, Rs, ts, Rt, tt, &acc[0]); }
       if (m1) { if (WITH_H) accumulate_record(a1, b1, c1, Rs, ts, Rt, tt, acc); else cost_record(a1, b1, c1, Rs, ts, Rt, tt, &acc[0]); }
+      if (NX > 0) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+          float P[24];
+          const float4* xp = reinterpret_cast<const float4*>(xpose[j]);
+#pragma unroll
+          for (int q = 0; q < 6; ++q) { const float4 v = xp[q]; P[4 * q] = v.x; P[4 * q + 1] = v.y; P[4 * q + 2] = v.z; P[4 * q + 3] = v.w; }
+          if (m0) cost_record(a0, b0, c0, P, P + 9, P + 12, P + 21, &xacc[j]);
+          if (m1) cost_record(a1, b1, c1, P, P + 9, P + 12, P + 21, &xacc[j]);
+        }
+      }
     }
     double out;
     block_reduce<NV>(acc, red, &out);
     if (threadIdx.x < NV) {
       const int slot = WITH_H ? threadIdx.x : (kAccVals - 1);
       partials[((size_t)seg * gridDim.x + blockIdx.x) * kAccVals + slot] = out;
+    }
+    if (NX > 0) {
+      double xout;
+      block_reduce<NXS>(xacc, xred, &xout);
+      if ((int)threadIdx.x < NX) xpartials[((size_t)seg * gridDim.x + blockIdx.x) * kMaxExtraTrials + threadIdx.x] = xout;
     }
     r0 = e;
     ++seg;
@@ -630,7 +668,18 @@ k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, c
 template <bool WITH_H>
 __global__ void __launch_bounds__(1024) k_finalize(const double* __restrict__ partials, const Segment* __restrict__ segs, int nseg,
                                                    int grid_acc, unsigned long long per_cta, int nv, double* __restrict__ segsum,
-                                                   double* __restrict__ eq, double extra0, double extra1) {
+                                                   double* __restrict__ eq, double extra0, double extra1,
+                                                   const double* __restrict__ xpartials, int nx, double* __restrict__ xsegsum) {
+  // costs of the speculative trials: the same two-stage order as the trial-0 cost (CTAs ascending, then segments ascending)
+  for (int w = threadIdx.x; w < nseg * nx; w += blockDim.x) {
+    const int s = w / nx, j = w % nx;
+    double v = 0.0;
+    if (segs[s].end > segs[s].begin) {
+      const int b0 = (int)(segs[s].begin / per_cta), b1 = (int)((segs[s].end - 1) / per_cta);
+      for (int b = b0; b <= b1; ++b) v += xpartials[((size_t)s * grid_acc + b) * kMaxExtraTrials + j];
+    }
+    xsegsum[w] = v;
+  }
   for (int w = threadIdx.x; w < nseg * kAccVals; w += blockDim.x) {
     const int s = w / kAccVals, k = w % kAccVals;
     double v = 0.0;
@@ -675,6 +724,12 @@ __global__ void __launch_bounds__(1024) k_finalize(const double* __restrict__ pa
     eq[nh + nv] = c;
     eq[nh + nv + 1] = extra0;
     eq[nh + nv + 2] = extra1;
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + kMaxExtraTrials) {
+    const int j = threadIdx.x - 32;
+    double c = 0.0;
+    if (j < nx) for (int s = 0; s < nseg; ++s) c += xsegsum[s * nx + j];
+    eq[nh + nv + 3 + j] = c;
   }
 }
 
