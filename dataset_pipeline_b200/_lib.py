@@ -70,6 +70,8 @@ EXPORTS = [
     "b2_icp_run",
     "b2_icp_set_pose",
     "b2_last_error",
+    "b2_lsor_filter",
+    "b2_mesh_squared_distance",
     "b2_ms_create",
     "b2_ms_merge_close_points",
     "b2_ms_point_neighbors",
@@ -91,13 +93,13 @@ EXPORTS = [
     "b2_reg_default_params",
     "b2_reg_destroy",
     "b2_reg_get_descriptors",
-    "b2_reg_gt_accumulate_observations",
-    "b2_reg_gt_create",
     "b2_reg_get_observations",
     "b2_reg_get_point_jacobians",
     "b2_reg_get_point_jacobians_rig",
     "b2_reg_get_rigs",
     "b2_reg_get_state",
+    "b2_reg_gt_accumulate_observations",
+    "b2_reg_gt_create",
     "b2_reg_image_owner",
     "b2_reg_initialize",
     "b2_reg_last_stats",
@@ -115,6 +117,7 @@ EXPORTS = [
     "b2_reg_set_splat_points",
     "b2_reg_set_state",
     "b2_reg_variable_index",
+    "b2_splat_create",
 ]
 
 

@@ -21,6 +21,7 @@
 
 #include "b2_bvh.cuh"
 #include "b2_common.cuh"
+#include "b2_knn.h"
 
 namespace b2 {
 
@@ -154,7 +155,8 @@ __device__ __forceinline__ float4 normal_from_list(const float4* __restrict__ s_
 
 __global__ void __launch_bounds__(kKnnThreads)
 kn_knn_normals(const float4* __restrict__ s_xyz, size_t n, const Aabb* __restrict__ nodes, BvhLevels lv, int k, float vpx, float vpy, float vpz,
-               float4* __restrict__ out, int* __restrict__ out_idx, unsigned int* __restrict__ nan_count, size_t q_begin, size_t q_end) {
+               float4* __restrict__ out, int* __restrict__ out_idx, unsigned int* __restrict__ nan_count, size_t q_begin, size_t q_end,
+               int stat_mode, float* __restrict__ out_stat) {
   extern __shared__ unsigned char smem_raw[];
   float* sm_d2 = reinterpret_cast<float*>(smem_raw);
   unsigned int* sm_pos = reinterpret_cast<unsigned int*>(smem_raw + sizeof(float) * (size_t)k * kKnnThreads);
@@ -211,6 +213,15 @@ kn_knn_normals(const float4* __restrict__ s_xyz, size_t n, const Aabb* __restric
   if (out_idx) {
     for (int a = 0; a < k; ++a) out_idx[(size_t)qi * k + a] = a < cnt ? (int)__float_as_uint(__ldg(&s_xyz[h.P(a)].w)) : -1;
   }
+  if (stat_mode == kKnnStatMeanDistance) {
+    // LocalStatisticalOutlierRemoval, first pass (local_statistical_outlier_removal.hpp:113-117): neighbour 0 is the query point
+    double dist_sum = 0.0;
+    for (int a = 1; a < cnt; ++a) dist_sum += (double)sqrtf(h.D(a));
+    out_stat[qi] = (float)(dist_sum / (double)(k - 1));
+  } else if (stat_mode == kKnnStatLastD2) {
+    out_stat[qi] = cnt == k ? h.D(k - 1) : INFINITY;      // squared distance of the (k-1)-th neighbour (splat_creator.cc:166)
+  }
+  if (!out) return;
   const float nanv = __int_as_float(0x7fc00000);
   if (cnt < 3) { out[qi] = make_float4(nanv, nanv, nanv, nanv); atomicAdd(nan_count, 1u); return; }
 
@@ -267,8 +278,9 @@ using namespace b2;
 // queries; the zero-initialised outputs are merged by one sum-allreduce (NaN normals survive the sum), so every rank returns
 // the full result. No exchange during the search itself.
 static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3], float* out_nxyz_curv,
-                        int32_t* out_knn_idx, int* is_dense, b2_comm* comm, int device, float radius = 0.f, int32_t* out_count = nullptr) {
-  if ((n && (!xyz || (!out_nxyz_curv && !out_knn_idx))) || !viewpoint) return set_error(B2_ERR_ARG, "null argument");
+                        int32_t* out_knn_idx, int* is_dense, b2_comm* comm, int device, float radius = 0.f, int32_t* out_count = nullptr,
+                        const KnnHook* hook = nullptr) {
+  if ((n && (!xyz || (!out_nxyz_curv && !out_knn_idx && !hook))) || !viewpoint) return set_error(B2_ERR_ARG, "null argument");
   if (stride_bytes < 12) return set_error(B2_ERR_ARG, "stride_bytes must be >= 12");
   const bool radius_mode = radius > 0.f;
   if (!radius_mode && (k < 1 || k > 128)) return set_error(B2_ERR_ARG, "k must be in [1,128]");
@@ -283,7 +295,7 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
   if (world > 1 && out_knn_idx) return set_error(B2_ERR_ARG, "neighbour index output is single-GPU only");
   const size_t q_begin = n * (size_t)rank / (size_t)world, q_end = n * (size_t)(rank + 1) / (size_t)world;
   cudaStream_t st; B2_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  DevBuf d_xyz, d_part, d_keys, d_keys2, d_idx, d_perm, d_sxyz, d_nodes, d_tmp, d_out, d_oidx, d_nan;
+  DevBuf d_xyz, d_part, d_keys, d_keys2, d_idx, d_perm, d_sxyz, d_nodes, d_tmp, d_out, d_oidx, d_nan, d_stat;
   DevBuf r_cnt, r_cnt64, r_offs, r_keys, r_keys2, r_vals, r_vals2, r_ocount;
   PinnedBuf p_part;
   int rc = B2_OK;
@@ -324,7 +336,10 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
       kn_merge_level<<<div_up_u(lv.count[l], 256), 256, 0, st>>>(d_nodes.as<Aabb>() + lv.offset[l - 1], lv.count[l - 1],
                                                                  d_nodes.as<Aabb>() + lv.offset[l], lv.count[l]);
     B2_TRY(d_out.ensure(n * 16));
-    if (out_knn_idx) B2_TRY(d_oidx.ensure(n * (size_t)k * 4));
+    const bool want_idx = out_knn_idx || (hook && hook->need_idx);
+    const int stat_mode = hook ? hook->stat_mode : kKnnStatNone;
+    if (want_idx) B2_TRY(d_oidx.ensure(n * (size_t)k * 4));
+    if (stat_mode != kKnnStatNone) B2_TRY(d_stat.ensure(n * 4));
     B2_TRY(d_nan.ensure(4));
     B2_CUDA(cudaMemsetAsync(d_nan.p, 0, 4, st));
     if (world > 1) B2_CUDA(cudaMemsetAsync(d_out.p, 0, n * 16, st));
@@ -368,10 +383,13 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
     B2_CUDA(cudaFuncSetAttribute(kn_knn_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (!radius_mode && q_end > q_begin)
       kn_knn_normals<<<div_up_u(q_end - q_begin, kKnnThreads), kKnnThreads, smem, st>>>(d_sxyz.as<float4>(), n, d_nodes.as<Aabb>(), lv, k, viewpoint[0],
-                                                                                        viewpoint[1], viewpoint[2], d_out.as<float4>(),
-                                                                                        out_knn_idx ? d_oidx.as<int>() : nullptr,
-                                                                                        d_nan.as<unsigned int>(), q_begin, q_end);
+                                                                                        viewpoint[1], viewpoint[2],
+                                                                                        (out_nxyz_curv || !hook) ? d_out.as<float4>() : nullptr,
+                                                                                        want_idx ? d_oidx.as<int>() : nullptr,
+                                                                                        d_nan.as<unsigned int>(), q_begin, q_end, stat_mode,
+                                                                                        d_stat.as<float>());
     B2_CUDA(cudaGetLastError());
+    if (hook && hook->run) B2_TRY(hook->run(st, d_xyz.as<float>(), want_idx ? d_oidx.as<int>() : nullptr, d_stat.as<float>(), n, k));
     if (world > 1) {
       B2_TRY(b2_comm_allreduce(comm, d_out.p, n * 4, B2_F32, (void*)st));
       B2_TRY(b2_comm_allreduce(comm, d_nan.p, 1, B2_I32, (void*)st));
@@ -389,11 +407,18 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
     return B2_OK;
   };
   rc = body();
-  for (DevBuf* b : {&d_xyz, &d_part, &d_keys, &d_keys2, &d_idx, &d_perm, &d_sxyz, &d_nodes, &d_tmp, &d_out, &d_oidx, &d_nan}) b->release();
+  for (DevBuf* b : {&d_xyz, &d_part, &d_keys, &d_keys2, &d_idx, &d_perm, &d_sxyz, &d_nodes, &d_tmp, &d_out, &d_oidx, &d_nan, &d_stat}) b->release();
   for (DevBuf* b : {&r_cnt, &r_cnt64, &r_offs, &r_keys, &r_keys2, &r_vals, &r_vals2, &r_ocount}) b->release();
   p_part.release();
   cudaStreamDestroy(st);
   return rc;
+}
+
+// Exact kNN lists / per-point statistics left on the device for a follow-up stage (b2_cleaner.cu).
+int b2::knn_with_hook(const float* xyz, size_t n, size_t stride_bytes, int k, const KnnHook& hook) {
+  const float vp[3] = {0.f, 0.f, 0.f};
+  if (hook.stat_mode == kKnnStatNone && !hook.need_idx) return set_error(B2_ERR_ARG, "knn_with_hook: nothing requested");
+  return normals_impl(xyz, n, stride_bytes, k, vp, nullptr, nullptr, nullptr, nullptr, -1, 0.f, nullptr, &hook);
 }
 
 extern "C" int b2_normals_estimate(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3], float* out_nxyz_curv,

@@ -164,6 +164,33 @@ int b2_normals_estimate_radius(const float* xyz, size_t n, size_t stride_bytes, 
                                float* out_nxyz_curv, int32_t* out_neighbor_count, int* is_dense);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Point-cloud tools next to the hot paths, built on the exact kNN search of the normals.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* pcl::LocalStatisticalOutlierRemoval<PointT>::applyFilterIndices (src/geometry/local_statistical_outlier_removal.hpp:72-176) with
+ * indices_ = the whole cloud, as PointCloudCleaner runs it (src/exe/point_cloud_cleaner.cc:80-96: setMeanK(knn),
+ * setDistanceFactorThresh(factor), filter): pass 1, per point the mean distance to its mean_k nearest other points (double sum of float
+ * sqrt, result float); pass 2, a point is an outlier when that mean exceeds distance_factor_threshold x the mean of its neighbours' means
+ * (only means > 0 count). negative != 0 inverts the test (setNegative). Non-finite points are never part of the search and are reported
+ * as removed. out_indices (capacity n): ascending indices of the kept points; out_removed_indices (nullable, capacity n): the others;
+ * out_mean_distances (nullable, n): the pass-1 means, 0 for non-finite points. B2_ERR_STATE when fewer than mean_k + 1 finite points. */
+int b2_lsor_filter(const float* xyz, size_t n, size_t stride_bytes, int mean_k, double distance_factor_threshold, int negative,
+                   int32_t* out_indices, size_t* out_count, int32_t* out_removed_indices, size_t* out_removed_count, float* out_mean_distances);
+/* igl::AABB<MatrixXf,3>::squared_distance (thirdparty/igl/AABB.cpp:344-430) per point: the minimum over the triangles of
+ * igl::point_simplex_squared_distance (thirdparty/igl/point_simplex_squared_distance.cpp:44-135), fp32, libigl's operation order.
+ * points: n x 3; vertices: num_vertices x 3; faces: num_faces x 3 vertex indices. */
+int b2_mesh_squared_distance(const float* points, size_t n, const float* vertices, size_t num_vertices, const uint32_t* faces, size_t num_faces,
+                             float* out_squared_distance);
+/* SplatCreator's per-point body (src/exe/splat_creator.cc:146-215): splat radius = min(distance to the 4th nearest other point,
+ * max_splat_size); right = normal.unitOrthogonal(), up = normal x right; corners = point + radius * (+-right +- up) in the order top right,
+ * bottom right, bottom left, top left (out_corners: n x 4 x 3, zeros for points with a NaN normal); out_added[i] = 1 when the point or
+ * one of its corners is farther than sqrt(squared_distance_threshold) from the mesh (the splat the tool appends: faces (2,1,0), (0,3,2) of
+ * its four vertices). Splats are reported in point order (the reference's `omp parallel for` appends them in arrival order).
+ * xyz / normals: n points, stride_bytes apart in each array. out_radius, out_splat_count nullable. */
+int b2_splat_create(const float* xyz, const float* normals, size_t n, size_t stride_bytes, const float* vertices, size_t num_vertices,
+                    const uint32_t* faces, size_t num_faces, float max_splat_size, float squared_distance_threshold, float* out_corners,
+                    uint8_t* out_added, float* out_radius, size_t* out_splat_count);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Multi-resolution point cloud — the producer of Path B's point scales and neighbour indices.
  * Replaces opt::MergeClosePoints (src/opt/multi_scale_point_cloud.cc:44-124), the scale loop of
  * opt::CreateMultiScalePointCloud (:263-368) and opt::Problem::DeterminePointNeighbors (src/opt/problem.cc:706-786) as driven by

@@ -219,6 +219,50 @@ def normals_radius(xyz, radius, viewpoint=(0.0, 0.0, 0.0), return_counts=False):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# Point-cloud tools (orc_cleaner.cc): LocalStatisticalOutlierRemoval, SplatCreator
+# ---------------------------------------------------------------------------------------------------------------------
+def lsor_filter(xyz, mean_k, factor, negative=False):
+    """Returns (kept indices, removed indices, pass-1 mean distances)."""
+    x = _c32(xyz); n = x.shape[0]
+    keep = np.zeros(n, np.int32); rem = np.zeros(n, np.int32); dist = np.zeros(n, np.float32)
+    nk, nr = C.c_uint64(0), C.c_uint64(0)
+    L = lib()
+    L.orc_lsor_filter.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint64),
+                                  C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
+    L.orc_lsor_filter.restype = C.c_int
+    rc = L.orc_lsor_filter(_f(x), n, int(mean_k), float(factor), int(bool(negative)), keep.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(nk),
+                           rem.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(nr), _f(dist))
+    if rc != 0:
+        raise ValueError("fewer than mean_k + 1 finite points")
+    return keep[:nk.value].copy(), rem[:nr.value].copy(), dist
+
+
+def mesh_squared_distance(points, vertices, faces):
+    p = _c32(points); v = _c32(vertices); f = np.ascontiguousarray(faces, np.uint32)
+    out = np.zeros(p.shape[0], np.float32)
+    L = lib()
+    L.orc_mesh_squared_distance.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_float), C.c_void_p, C.c_size_t, C.POINTER(C.c_float)]
+    L.orc_mesh_squared_distance.restype = None
+    L.orc_mesh_squared_distance(_f(p), p.shape[0], _f(v), f.ctypes.data, f.shape[0], _f(out))
+    return out
+
+
+def create_splats(xyz, normals, vertices, faces, distance_threshold=0.02, max_splat_size=np.inf):
+    x = _c32(xyz); nr = _c32(normals); v = _c32(vertices); f = np.ascontiguousarray(faces, np.uint32)
+    n = x.shape[0]
+    corners = np.zeros((n, 4, 3), np.float32); added = np.zeros(n, np.uint8); radius = np.zeros(n, np.float32)
+    thr2 = np.float32(distance_threshold) * np.float32(distance_threshold)
+    L = lib()
+    L.orc_splat_create.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_float), C.c_void_p, C.c_size_t, C.c_float,
+                                   C.c_float, C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_float)]
+    L.orc_splat_create.restype = C.c_uint64
+    cnt = L.orc_splat_create(_f(x), _f(nr), n, _f(v), f.ctypes.data, f.shape[0], float(max_splat_size), float(thr2), _f(corners), added.ctypes.data,
+                             _f(radius))
+    assert cnt == int(added.sum())
+    return corners, added.astype(bool), radius
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # Multi-resolution point cloud (orc_multiscale.cc)
 # ---------------------------------------------------------------------------------------------------------------------
 def _u8(a):

@@ -133,6 +133,13 @@ int orc_ms_create(const float* xyz, size_t n, const float* colors, const uint8_t
 int orc_ms_point_neighbors(const float* xyz, size_t n, const uint8_t* scan, int scan_count, int limit_to_same_scan, int candidate_count,
                            int neighbor_count, uint64_t* out);
 
+/* ---- point-cloud tools (orc_cleaner.cc): LocalStatisticalOutlierRemoval (PointCloudCleaner), SplatCreator ---- */
+int orc_lsor_filter(const float* xyz, size_t n, int mean_k, double distance_factor_threshold, int negative, int32_t* out_indices,
+                    uint64_t* out_count, int32_t* out_removed, uint64_t* out_removed_count, float* out_distances);
+void orc_mesh_squared_distance(const float* points, size_t n, const float* vertices, const uint32_t* faces, size_t nf, float* out);
+uint64_t orc_splat_create(const float* xyz, const float* normals, size_t n, const float* vertices, const uint32_t* faces, size_t nf,
+                          float max_splat_size, float squared_distance_threshold, float* corners, uint8_t* added, float* radius);
+
 /* ---- camera models (orc_camera.h) ---- */
 int orc_cam_param_count(int type);   /* -1 unsupported */
 /* constructs the camera (runs the cut-off search as the reference constructors do); out[0] = radius_cutoff_squared of the

@@ -1,0 +1,103 @@
+"""GPU parity for the point-cloud tools through the C ABI: b2_lsor_filter, b2_mesh_squared_distance, b2_splat_create
+against the oracle (oracle/orc_cleaner.cc) — bit-exact: kept / removed index lists, mean distances, squared distances, corners, flags."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(seed, n, outliers):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+    x[:, 2] = (0.2 * np.sin(2 * x[:, 0]) * np.cos(x[:, 1])).astype(np.float32) + rng.normal(0, 0.002, n).astype(np.float32)
+    o = rng.choice(n, outliers, replace=False)
+    x[o, 2] += rng.uniform(0.05, 0.5, outliers).astype(np.float32)
+    return x
+
+
+def _mesh(seed, g=60, nt=200):
+    rng = np.random.default_rng(seed)
+    u, v = np.meshgrid(np.linspace(-2, 2, g), np.linspace(-2, 2, g), indexing="ij")
+    verts = np.stack([u.ravel(), v.ravel(), 0.2 * np.sin(2 * u.ravel()) * np.cos(v.ravel())], axis=1).astype(np.float32)
+    a = (np.arange(g - 1)[:, None] * g + np.arange(g - 1)[None, :]).ravel()
+    faces = np.concatenate([np.stack([a, a + 1, a + g], 1), np.stack([a + 1, a + g + 1, a + g], 1)])
+    keep = rng.uniform(size=len(faces)) > 0.15          # holes: the parts of the scan the mesh does not represent
+    faces = faces[keep]
+    extra = rng.uniform(-1, 1, (nt, 3, 3)).astype(np.float32) * 0.2 + rng.uniform(-2, 2, (nt, 1, 3)).astype(np.float32)
+    base = len(verts)
+    verts = np.concatenate([verts, extra.reshape(-1, 3)])
+    faces = np.concatenate([faces, base + np.arange(3 * nt).reshape(nt, 3), [[0, 0, 7], [3, 3, 3]]])   # + degenerate triangles
+    return verts, faces.astype(np.uint32)
+
+
+@pytest.mark.parametrize("n,mean_k,factor", [(20000, 16, 2.0), (5000, 50, 1.2), (3000, 1, 3.0), (40, 20, 2.0)])
+def test_lsor_filter_matches_oracle(n, mean_k, factor):
+    import dataset_pipeline_b200 as b2
+    from oracle import oracle as orc
+    x = _scene(n + mean_k, n, max(2, n // 50))
+    sor = b2.LocalStatisticalOutlierRemoval()
+    sor.setInputCloud(x); sor.setMeanK(mean_k); sor.setDistanceFactorThresh(factor)
+    keep = sor.filter()
+    k2, r2, d2 = orc.lsor_filter(x, mean_k, factor)
+    assert np.array_equal(sor.mean_distances, d2)
+    assert np.array_equal(keep, k2) and np.array_equal(sor.getRemovedIndices(), r2)
+    assert len(r2) < n and (n < 1000 or len(r2) > 0)
+
+
+def test_lsor_nonfinite_negative_duplicates_and_errors():
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200._lib import B2Error
+    from oracle import oracle as orc
+    x = _scene(7, 6000, 100)
+    x[[0, 17, 5999]] = np.nan; x[300, 2] = -np.inf
+    x[1000:1012] = x[1000]                                  # coincident points: zero mean distance, ties broken by index
+    for negative in (False, True):
+        sor = b2.LocalStatisticalOutlierRemoval()
+        sor.setInputCloud(x); sor.setMeanK(8); sor.setDistanceFactorThresh(1.8); sor.setNegative(negative)
+        keep = sor.filter()
+        k2, r2, d2 = orc.lsor_filter(x, 8, 1.8, negative)
+        assert np.array_equal(keep, k2) and np.array_equal(sor.getRemovedIndices(), r2) and np.array_equal(sor.mean_distances, d2)
+    sor = b2.LocalStatisticalOutlierRemoval()
+    sor.setInputCloud(x[:5]); sor.setMeanK(8)
+    with pytest.raises(B2Error):
+        sor.filter()
+    sor.setInputCloud(np.zeros((0, 3), np.float32))
+    assert len(sor.filter()) == 0
+    # PointCloudCleaner's loop: two filters in a row
+    alive = b2.clean_point_cloud(x, [(8, 1.8), (16, 2.5)])
+    k1, _, _ = orc.lsor_filter(x, 8, 1.8)
+    k2, _, _ = orc.lsor_filter(x[k1], 16, 2.5)
+    assert np.array_equal(alive, k1[k2])
+
+
+def test_mesh_squared_distance_matches_oracle():
+    import dataset_pipeline_b200 as b2
+    from oracle import oracle as orc
+    verts, faces = _mesh(11)
+    rng = np.random.default_rng(12)
+    pts = np.concatenate([rng.uniform(-2.5, 2.5, (20000, 3)), verts[rng.choice(len(verts), 500)].astype(np.float64),
+                          rng.uniform(-2, 2, (5000, 3)) * [1, 1, 0.1], [[50.0, -40.0, 30.0]]]).astype(np.float32)
+    got = b2.mesh_squared_distance(pts, verts, faces)
+    ref = orc.mesh_squared_distance(pts, verts, faces)
+    assert np.array_equal(got, ref)
+    # far from the origin: the pruning margin scales with the coordinates
+    off = np.float32([900.0, -700.0, 300.0])
+    got = b2.mesh_squared_distance(pts[:6000] + off, verts + off, faces)
+    ref = orc.mesh_squared_distance(pts[:6000] + off, verts + off, faces)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("max_splat_size", [np.inf, 0.03])
+def test_splat_create_matches_oracle(max_splat_size):
+    import dataset_pipeline_b200 as b2
+    from oracle import oracle as orc
+    verts, faces = _mesh(21)
+    x = _scene(22, 30000, 600)
+    nrm = b2.estimate_normals(x, 16)[:, :3].copy()
+    nrm[5] = [0, 0, 1]; nrm[6] = [1e-7, 0, -1]; nrm[7] = np.nan
+    c1, a1, r1 = b2.create_splats(x, nrm, verts, faces, 0.02, max_splat_size)
+    c2, a2, r2 = orc.create_splats(x, nrm, verts, faces, 0.02, max_splat_size)
+    assert np.array_equal(r1, r2)
+    assert np.array_equal(c1, c2)
+    assert np.array_equal(a1, a2)
+    assert 0.02 * len(x) < a1.sum() < 0.9 * len(x)      # holes and outliers become splats, the represented surface does not
