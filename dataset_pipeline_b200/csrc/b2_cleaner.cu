@@ -14,7 +14,10 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -293,7 +296,7 @@ extern "C" int b2_lsor_filter(const float* xyz, size_t n, size_t stride_bytes, i
                               float* out_mean_distances) {
   if ((n && !xyz) || !out_indices || !out_count) return set_error(B2_ERR_ARG, "null argument");
   if (stride_bytes < 12 || stride_bytes % 4) return set_error(B2_ERR_ARG, "stride_bytes must be a multiple of 4, >= 12");
-  if (mean_k < 1 || mean_k > 127) return set_error(B2_ERR_ARG, "mean_k must be in [1,127]");
+  if (mean_k < 1 || mean_k > 2047) return set_error(B2_ERR_ARG, "mean_k must be in [1,2047]");
   if (n >= (1ull << 30)) return set_error(B2_ERR_ARG, "clouds above 2^30 points are not supported");
   *out_count = 0;
   if (out_removed_count) *out_removed_count = 0;
@@ -324,7 +327,16 @@ extern "C" int b2_lsor_filter(const float* xyz, size_t n, size_t stride_bytes, i
     KnnHook hook;
     hook.stat_mode = kKnnStatMeanDistance;
     hook.need_idx = true;
+    const bool trace = std::getenv("B2_CLEAN_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     hook.run = [&](cudaStream_t st, const float*, const int* idx_dev, const float* stat_dev, size_t cnt, int kk) -> int {
+      if (trace) {
+        B2_CUDA(cudaStreamSynchronize(st));
+        fprintf(stderr, "[b2_lsor_filter] %zu points, k = %d: upload + index + kNN %.1f ms\n", cnt, kk,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+      }
+      const auto t1 = std::chrono::steady_clock::now();
+      struct Tail { bool on; std::chrono::steady_clock::time_point t; ~Tail() { if (on) fprintf(stderr, "[b2_lsor_filter] classify + download %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count()); } } tail{trace, t1};
       B2_TRY(d_keep.ensure(cnt));
       kc_lsor_classify<<<bvh_div_up(cnt, 256), 256, 0, st>>>(idx_dev, stat_dev, cnt, kk, distance_factor_threshold, negative, d_keep.as<unsigned char>());
       B2_CUDA(cudaGetLastError());

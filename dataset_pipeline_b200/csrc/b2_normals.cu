@@ -17,6 +17,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "b2_bvh.cuh"
@@ -165,10 +167,14 @@ kn_knn_normals(const float4* __restrict__ s_xyz, size_t n, const Aabb* __restric
   const float4 q = s_xyz[j];
   KBest h{sm_d2 + threadIdx.x, sm_pos + threadIdx.x, k, 0, 0, INFINITY};
 
-  // seed with the query's own leaf and its two neighbours in Morton order
+  // seed with the query's own leaf and its neighbours in Morton order: three leaves, or as many as hold k points (the list is then
+  // full, with a near-final bound, before the walk starts)
   const unsigned int nleaf = lv.count[0];
   const unsigned int own = (unsigned int)(j / kLeaf);
-  const unsigned int l0 = own > 0 ? own - 1 : 0, l1 = min(nleaf - 1, own + 1);
+  const unsigned int nseed = max(3u, (unsigned int)((k + kLeaf - 1) / kLeaf) + 1u);
+  unsigned int l0 = own > nseed / 2 ? own - nseed / 2 : 0;
+  if (l0 + nseed > nleaf) l0 = nleaf > nseed ? nleaf - nseed : 0;
+  const unsigned int l1 = min(nleaf, l0 + nseed) - 1;
   for (unsigned int l = l0; l <= l1; ++l) scan_leaf(h, q, l, n, s_xyz);
 
   // near-first depth-first walk from the root; entries are (level << 27 | index)
@@ -228,6 +234,154 @@ kn_knn_normals(const float4* __restrict__ s_xyz, size_t n, const Aabb* __restric
   out[qi] = normal_from_list(s_xyz, [&](int a) { return h.P(a); }, cnt, q, vpx, vpy, vpz);
 }
 
+// ---- long neighbour lists (k > 64; PointCloudCleaner's recipe is kNN = 270): one WARP per query -------------------------------------------
+// A per-thread list of hundreds of entries leaves room for two warps per SM. Here the list lives in shared memory per warp (24 B x k), the
+// BVH walk is warp-uniform (no divergence), the eight points of a leaf are tested by eight lanes at once, and an insertion replaces the worst
+// entry and re-finds the maximum with a strided scan + shuffle reduction. Keys are (d2 bits << 32 | original index): for non-negative floats
+// the integer order is the (d2, index) order of the per-thread kernel, so both produce identical lists.
+static constexpr int kWideWarps = 4;
+__global__ void __launch_bounds__(32 * kWideWarps)
+kn_knn_wide(const float4* __restrict__ s_xyz, size_t n, const Aabb* __restrict__ nodes, BvhLevels lv, int k, float vpx, float vpy, float vpz,
+            float4* __restrict__ out, int* __restrict__ out_idx, unsigned int* __restrict__ nan_count, size_t q_begin, size_t q_end,
+            int stat_mode, float* __restrict__ out_stat, unsigned long long* __restrict__ dbg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned int c_nodes = 0, c_leaves = 0, c_inserts = 0;
+  const size_t j = q_begin + (size_t)blockIdx.x * kWideWarps + w;
+  if (j >= q_end) return;                                            // whole warp
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)w * 2 * k;   // [k] list, [k] sorted
+  unsigned long long* skeys = keys + k;
+  unsigned int* pos = reinterpret_cast<unsigned int*>(smem_raw + (size_t)kWideWarps * 16 * k) + (size_t)w * 2 * k;
+  unsigned int* spos = pos + k;
+  const float4 q = __ldg(&s_xyz[j]);
+  int count = 0, worst_slot = 0;
+  unsigned long long worst_key = ~0ull;
+
+  auto refind_worst = [&]() {
+    unsigned long long m = 0ull; int slot = 0;
+    for (int e = lane; e < k; e += 32) { const unsigned long long v = keys[e]; if (v >= m) { m = v; slot = e; } }
+    unsigned long long g = m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, g, o); g = t > g ? t : g; }
+    const int owner = __ffs(__ballot_sync(0xffffffffu, m == g && lane < k)) - 1;    // keys are unique (the index is part of the key)
+    worst_key = g; worst_slot = __shfl_sync(0xffffffffu, slot, owner);
+  };
+  auto offer_points = [&](size_t first, int npts) {          // candidates first .. first + npts - 1 (npts <= 32), one per lane
+    ++c_leaves;
+    const size_t p = first + lane;
+    const bool valid = lane < npts && p < n;
+    unsigned long long key = ~0ull;
+    if (valid) {
+      const float4 t = __ldg(&s_xyz[p]);
+      key = ((unsigned long long)__float_as_uint(dist2_pt(q, t)) << 32) | (unsigned long long)__float_as_uint(t.w);
+    }
+    unsigned int m = __ballot_sync(0xffffffffu, valid && (count < k || key < worst_key));
+    while (m) {
+      const int src = __ffs(m) - 1; m &= m - 1;
+      const unsigned long long ck = __shfl_sync(0xffffffffu, key, src);
+      const unsigned int cp = (unsigned int)(first + src);
+      if (count < k) {
+        if (lane == 0) { keys[count] = ck; pos[count] = cp; }
+        ++count;
+        if (count == k) { __syncwarp(); refind_worst(); }
+      } else if (ck < worst_key) {
+        ++c_inserts;
+        if (lane == 0) { keys[worst_slot] = ck; pos[worst_slot] = cp; }
+        __syncwarp();
+        refind_worst();
+      }
+    }
+  };
+
+  auto offer_leaf = [&](unsigned int leaf) { offer_points((size_t)leaf * kLeaf, kLeaf); };
+
+  // Seed: the list is FILLED, with coalesced loads and no insertion logic, from the ceil(k / 8) leaves around the query in Morton order
+  // (spatially close points), so the walk below starts with a near-final bound instead of discovering it replacement by replacement.
+  const unsigned int nleaf = lv.count[0];
+  const unsigned int own = (unsigned int)(j / kLeaf);
+  const unsigned int nfill_leaves = (unsigned int)((k + kLeaf - 1) / kLeaf);
+  unsigned int l0 = own > nfill_leaves / 2 ? own - nfill_leaves / 2 : 0;
+  if (l0 + nfill_leaves > nleaf) l0 = nleaf > nfill_leaves ? nleaf - nfill_leaves : 0;
+  const unsigned int l1 = min(nleaf, l0 + nfill_leaves) - 1;
+  {
+    const size_t pb = (size_t)l0 * kLeaf, pe = min(n, (size_t)(l1 + 1) * kLeaf);
+    const int nfill = (int)min((size_t)k, pe - pb);
+    for (int e = lane; e < nfill; e += 32) {
+      const float4 t = __ldg(&s_xyz[pb + e]);
+      keys[e] = ((unsigned long long)__float_as_uint(dist2_pt(q, t)) << 32) | (unsigned long long)__float_as_uint(t.w);
+      pos[e] = (unsigned int)(pb + e);
+    }
+    count = nfill;
+    __syncwarp();
+    if (count == k) refind_worst();
+    if (pb + nfill < pe) offer_points(pb + nfill, (int)(pe - pb - nfill));     // the (< 8) points of the last seed leaf beyond k
+  }
+  unsigned int stack[kBvhMaxLevels + 2];
+  int sp = 0;
+  stack[sp++] = ((unsigned int)(lv.nlevels - 1) << 27);
+  while (sp > 0) {
+    const unsigned int e = stack[--sp];
+    const int level = (int)(e >> 27);
+    const unsigned int i = e & 0x7FFFFFFu;
+    const bool full = count == k;
+    const float worst_d2 = __uint_as_float((unsigned int)(worst_key >> 32));
+    ++c_nodes;
+    if (full && dist2_box(q, nodes[lv.offset[level] + i]) > worst_d2) continue;
+    if (level == 0) {
+      if (i < l0 || i > l1) offer_leaf(i);
+      continue;
+    }
+    const unsigned int c0 = 2 * i, c1 = 2 * i + 1;
+    const unsigned int nchild = lv.count[level - 1];
+    if (c1 >= nchild) { stack[sp++] = ((unsigned int)(level - 1) << 27) | c0; continue; }
+    const float d0 = dist2_box(q, nodes[lv.offset[level - 1] + c0]);
+    const float d1 = dist2_box(q, nodes[lv.offset[level - 1] + c1]);
+    const bool v0 = !full || d0 <= worst_d2, v1 = !full || d1 <= worst_d2;
+    if (d0 <= d1) {
+      if (v1) stack[sp++] = ((unsigned int)(level - 1) << 27) | c1;
+      if (v0) stack[sp++] = ((unsigned int)(level - 1) << 27) | c0;
+    } else {
+      if (v0) stack[sp++] = ((unsigned int)(level - 1) << 27) | c0;
+      if (v1) stack[sp++] = ((unsigned int)(level - 1) << 27) | c1;
+    }
+  }
+
+  if (dbg && lane == 0) { atomicAdd(&dbg[0], (unsigned long long)c_nodes); atomicAdd(&dbg[1], (unsigned long long)c_leaves); atomicAdd(&dbg[2], (unsigned long long)c_inserts); }
+  // rank every entry (keys are unique): sorted position = number of smaller keys
+  const int cnt = count;
+  __syncwarp();
+  for (int e = lane; e < cnt; e += 32) {
+    const unsigned long long mine = keys[e];
+    int rank = 0;
+    for (int f = 0; f < cnt; ++f) rank += keys[f] < mine ? 1 : 0;
+    skeys[rank] = mine; spos[rank] = pos[e];
+  }
+  __syncwarp();
+  const unsigned int qi = __float_as_uint(q.w);
+  if (out_idx)
+    for (int a = lane; a < k; a += 32) out_idx[(size_t)qi * k + a] = a < cnt ? (int)(unsigned int)(skeys[a] & 0xFFFFFFFFull) : -1;
+  if (stat_mode == kKnnStatMeanDistance) {
+    float* sq = reinterpret_cast<float*>(pos);                        // the unsorted positions are no longer needed
+    for (int a = lane; a < cnt; a += 32) sq[a] = sqrtf(__uint_as_float((unsigned int)(skeys[a] >> 32)));
+    __syncwarp();
+    if (lane == 0) {
+      double dist_sum = 0.0;
+      for (int a = 1; a < cnt; ++a) dist_sum += (double)sq[a];        // neighbour order, as the reference (:113-117)
+      out_stat[qi] = (float)(dist_sum / (double)(k - 1));
+    }
+  } else if (stat_mode == kKnnStatLastD2) {
+    if (lane == 0) out_stat[qi] = cnt == k ? __uint_as_float((unsigned int)(skeys[k - 1] >> 32)) : INFINITY;
+  }
+  if (!out || lane != 0) return;
+  const float nanv = __int_as_float(0x7fc00000);
+  if (cnt < 3) { out[qi] = make_float4(nanv, nanv, nanv, nanv); atomicAdd(nan_count, 1u); return; }
+  out[qi] = normal_from_list(s_xyz, [&](int a) { return spos[a]; }, cnt, q, vpx, vpy, vpz);
+}
+static int knn_wide_from() {     // list length from which the warp-per-query kernel takes over (B2_KNN_WIDE_FROM for A/B runs)
+  static const int v = [] { const char* e = std::getenv("B2_KNN_WIDE_FROM"); const int x = e ? atoi(e) : 0; return x >= 8 && x <= 129 ? x : 56; }();
+  return v;
+}
+
 // ---- radius mode (setRadiusSearch): every point with d2 < r2, in (d2, index) order --------------------------------------------
 // Three kernels per batch of Morton-sorted queries: count -> (scan) -> fill keys ((d2 bits << 32) | original index, value = sorted
 // position) -> (segmented radix sort: for non-negative floats the bit pattern orders like the value) -> normals.
@@ -283,7 +437,7 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
   if ((n && (!xyz || (!out_nxyz_curv && !out_knn_idx && !hook))) || !viewpoint) return set_error(B2_ERR_ARG, "null argument");
   if (stride_bytes < 12) return set_error(B2_ERR_ARG, "stride_bytes must be >= 12");
   const bool radius_mode = radius > 0.f;
-  if (!radius_mode && (k < 1 || k > 128)) return set_error(B2_ERR_ARG, "k must be in [1,128]");
+  if (!radius_mode && (k < 1 || k > 2048)) return set_error(B2_ERR_ARG, "k must be in [1,2048]");
   if (radius_mode && !(radius < INFINITY)) return set_error(B2_ERR_ARG, "radius must be finite");
   if (n >= (1ull << 30)) return set_error(B2_ERR_ARG, "clouds above 2^30 points are not supported");
   if (is_dense) *is_dense = 1;
@@ -295,7 +449,7 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
   if (world > 1 && out_knn_idx) return set_error(B2_ERR_ARG, "neighbour index output is single-GPU only");
   const size_t q_begin = n * (size_t)rank / (size_t)world, q_end = n * (size_t)(rank + 1) / (size_t)world;
   cudaStream_t st; B2_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  DevBuf d_xyz, d_part, d_keys, d_keys2, d_idx, d_perm, d_sxyz, d_nodes, d_tmp, d_out, d_oidx, d_nan, d_stat;
+  DevBuf d_xyz, d_part, d_keys, d_keys2, d_idx, d_perm, d_sxyz, d_nodes, d_tmp, d_out, d_oidx, d_nan, d_stat, d_dbg;
   DevBuf r_cnt, r_cnt64, r_offs, r_keys, r_keys2, r_vals, r_vals2, r_ocount;
   PinnedBuf p_part;
   int rc = B2_OK;
@@ -380,8 +534,23 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
       }
     }
     const size_t smem = (size_t)std::max(k, 1) * kKnnThreads * 8;
-    B2_CUDA(cudaFuncSetAttribute(kn_knn_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (!radius_mode && q_end > q_begin)
+    const bool trace = std::getenv("B2_KNN_TRACE") != nullptr;
+    cudaEvent_t te0 = nullptr, te1 = nullptr;
+    if (trace) {
+      B2_TRY(d_dbg.ensure(32)); B2_CUDA(cudaMemsetAsync(d_dbg.p, 0, 32, st));
+      B2_CUDA(cudaEventCreate(&te0)); B2_CUDA(cudaEventCreate(&te1)); B2_CUDA(cudaEventRecord(te0, st));
+    }
+    if (!radius_mode && q_end > q_begin && k >= knn_wide_from()) {
+      const size_t wsmem = (size_t)kWideWarps * 24 * k;
+      B2_CUDA(cudaFuncSetAttribute(kn_knn_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+      kn_knn_wide<<<div_up_u(q_end - q_begin, kWideWarps), 32 * kWideWarps, wsmem, st>>>(d_sxyz.as<float4>(), n, d_nodes.as<Aabb>(), lv, k, viewpoint[0],
+                                                                                        viewpoint[1], viewpoint[2],
+                                                                                        (out_nxyz_curv || !hook) ? d_out.as<float4>() : nullptr,
+                                                                                        want_idx ? d_oidx.as<int>() : nullptr,
+                                                                                        d_nan.as<unsigned int>(), q_begin, q_end, stat_mode,
+                                                                                        d_stat.as<float>(), trace ? d_dbg.as<unsigned long long>() : nullptr);
+    } else if (!radius_mode) B2_CUDA(cudaFuncSetAttribute(kn_knn_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!radius_mode && q_end > q_begin && k < knn_wide_from())
       kn_knn_normals<<<div_up_u(q_end - q_begin, kKnnThreads), kKnnThreads, smem, st>>>(d_sxyz.as<float4>(), n, d_nodes.as<Aabb>(), lv, k, viewpoint[0],
                                                                                         viewpoint[1], viewpoint[2],
                                                                                         (out_nxyz_curv || !hook) ? d_out.as<float4>() : nullptr,
@@ -389,6 +558,15 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
                                                                                         d_nan.as<unsigned int>(), q_begin, q_end, stat_mode,
                                                                                         d_stat.as<float>());
     B2_CUDA(cudaGetLastError());
+    if (trace) {
+      B2_CUDA(cudaEventRecord(te1, st)); B2_CUDA(cudaEventSynchronize(te1));
+      float ms = 0.f; cudaEventElapsedTime(&ms, te0, te1);
+      unsigned long long c[4] = {0, 0, 0, 0};
+      B2_CUDA(cudaMemcpy(c, d_dbg.p, 32, cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[b2 knn] %zu points, k = %d: search kernel %.2f ms (%s); per query: %.1f nodes, %.1f leaves, %.1f replacements\n", n, k, ms,
+              radius_mode ? "radius" : k >= knn_wide_from() ? "warp per query" : "thread per query", (double)c[0] / n, (double)c[1] / n, (double)c[2] / n);
+      cudaEventDestroy(te0); cudaEventDestroy(te1);
+    }
     if (hook && hook->run) B2_TRY(hook->run(st, d_xyz.as<float>(), want_idx ? d_oidx.as<int>() : nullptr, d_stat.as<float>(), n, k));
     if (world > 1) {
       B2_TRY(b2_comm_allreduce(comm, d_out.p, n * 4, B2_F32, (void*)st));
@@ -407,7 +585,7 @@ static int normals_impl(const float* xyz, size_t n, size_t stride_bytes, int k, 
     return B2_OK;
   };
   rc = body();
-  for (DevBuf* b : {&d_xyz, &d_part, &d_keys, &d_keys2, &d_idx, &d_perm, &d_sxyz, &d_nodes, &d_tmp, &d_out, &d_oidx, &d_nan, &d_stat}) b->release();
+  for (DevBuf* b : {&d_xyz, &d_part, &d_keys, &d_keys2, &d_idx, &d_perm, &d_sxyz, &d_nodes, &d_tmp, &d_out, &d_oidx, &d_nan, &d_stat, &d_dbg}) b->release();
   for (DevBuf* b : {&r_cnt, &r_cnt64, &r_offs, &r_keys, &r_keys2, &r_vals, &r_vals2, &r_ocount}) b->release();
   p_part.release();
   cudaStreamDestroy(st);

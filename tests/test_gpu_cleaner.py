@@ -101,3 +101,20 @@ def test_splat_create_matches_oracle(max_splat_size):
     assert np.array_equal(c1, c2)
     assert np.array_equal(a1, a2)
     assert 0.02 * len(x) < a1.sum() < 0.9 * len(x)      # holes and outliers become splats, the represented surface does not
+
+
+def test_long_neighbour_lists_warp_per_query():
+    """k from 56 switches K7 to the warp-per-query kernel (kn_knn_wide): ETH3D's cleaner recipe is kNN = 270."""
+    import dataset_pipeline_b200 as b2
+    from oracle import oracle as orc
+    x = _scene(31, 9000, 150)
+    x[2000:2040] = x[2000]                                  # ties inside the list
+    for k in (40, 56, 100, 200):
+        _, i1 = b2.estimate_normals(x, k, return_indices=True)
+        _, i2 = orc.normals_knn(x, k, return_indices=True)
+        assert np.array_equal(i1, i2), k
+    sor = b2.LocalStatisticalOutlierRemoval()
+    sor.setInputCloud(x); sor.setMeanK(270); sor.setDistanceFactorThresh(1.15)
+    keep = sor.filter()
+    k2, r2, d2 = orc.lsor_filter(x, 270, 1.15)
+    assert np.array_equal(sor.mean_distances, d2) and np.array_equal(keep, k2)
