@@ -432,7 +432,9 @@ def _u8(a):
     return a.ctypes.data_as(C.POINTER(C.c_uint8))
 
 
-CAM_PINHOLE, CAM_BENCHMARK, CAM_THIN_PRISM = 4, 5, 14   # camera::CameraBase::Type values (camera_base.h:67-84)
+CAM_FOV, CAM_POLYNOMIAL, CAM_POLYNOMIAL_TANGENTIAL, CAM_FISHEYE_POLYNOMIAL_TANGENTIAL, CAM_PINHOLE, CAM_BENCHMARK, CAM_FISHEYE_POLYNOMIAL_4 = 0, 1, 2, 3, 4, 5, 6
+CAM_SIMPLE_PINHOLE, CAM_RADIAL, CAM_SIMPLE_RADIAL, CAM_FULL_OPENCV, CAM_POLYNOMIAL_4, CAM_RADIAL_FISHEYE, CAM_SIMPLE_RADIAL_FISHEYE, CAM_THIN_PRISM = 7, 8, 9, 10, 11, 12, 13, 14
+# (camera::CameraBase::Type values, camera_base.h:67-84)
 
 
 def cam_param_count(model):

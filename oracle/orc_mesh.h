@@ -109,10 +109,19 @@ typedef Camera RasterCam;   // orc_camera.h (included before this header)
 // (never for the benchmark camera, whose radius_cutoff_squared() is +inf, :668-680) the vertex is pushed far out (x, y) *= 99.
 // The thin-prism model has no renderer program of its own in the reference (its objects report Type::kBenchmark,
 // camera_thin_prism.cc:37,47); here it gets the same snippet without the fisheye step.
+// The other models (renderer.cc:154-560): every snippet evaluates z * Distort(x/z, y/z) with the (x, y) * 99 push-out beyond the cut-off;
+// GLSL float arithmetic is driver-defined, so their individual operation orders are not restated: Camera::distort is used.
 static inline void vertex_distort(const Camera& c, V3f* p) {
-  if (c.type == kCamPinhole) return;
+  if (c.dist == kDistNone && !c.fisheye) return;
   float nx = p->x / p->z, ny = p->y / p->z;
   float r2 = nx * nx + ny * ny;
+  if (c.dist != kDistThinPrism) {
+    float dx, dy;
+    if (r2 <= c.cutoff2) c.distort(nx, ny, &dx, &dy);
+    if (r2 <= c.cutoff2 && std::isfinite(dx) && std::isfinite(dy)) { p->x = p->z * dx; p->y = p->z * dy; }
+    else { p->x = p->x * 99.0f; p->y = p->y * 99.0f; }
+    return;
+  }
   if (r2 <= c.cutoff2) {
     if (c.type == kCamBenchmark) {
       const float r = std::sqrt(r2);

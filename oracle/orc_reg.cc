@@ -681,7 +681,7 @@ void orc_reg_min_max_point_radius(orc_reg* h, const float* xyz, size_t n, double
     const Pinhole& cam = intr.model(image_scale);
     const Pinhole& cam0 = intr.model(0);                 // min_image_scale_camera = *intrinsics.model(0) (:240)
     std::vector<float> table;
-    if (cam0.type != kCamPinhole) { table.resize((size_t)2 * cam0.w * cam0.h); cam0.undistortion_lookup(table.data()); }
+    if (cam0.has_lookup()) { table.resize((size_t)2 * cam0.w * cam0.h); cam0.undistortion_lookup(table.data()); }
     float R[9]; quat_to_matrix(im.image_T_global.q, R);
     const int level = image_scale - intr.min_image_scale;
     for (size_t pi = 0; pi < n; ++pi) {

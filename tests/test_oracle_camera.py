@@ -9,8 +9,32 @@ PINHOLE = [250.0, 200.0, 319.5, 239.5]
 BENCH = [340.926, 341.124, 302.4, 201.6, 0.221184, 0.128597, 0.000531602, -0.000388873, 0.0623079, 0.20419, -0.000805024, 4.07704e-05]
 
 
+K1, K2, K3 = 0.13, -0.66, 0.64
+PT = [340.926, 341.124, 302.4, 201.6, -0.101082, 0.0703954, 0.000438661, -0.000680887]
+
+
 def cameras(orc):
-    return [(orc.CAM_PINHOLE, PINHOLE), (orc.CAM_THIN_PRISM, BENCH), (orc.CAM_BENCHMARK, BENCH)]
+    """The cameras of the reference's test_camera.cc:422-505 (one TEST per model) + the thin-prism model (the benchmark camera's inner
+    model) + Polynomial4 (FisheyePolynomial4's inner model)."""
+    return [(orc.CAM_PINHOLE, PINHOLE),
+            (orc.CAM_SIMPLE_PINHOLE, [250.0, 319.5, 239.5]),
+            (orc.CAM_RADIAL, [250.0, 319.5, 239.5, K1, -1e-2]),
+            (orc.CAM_RADIAL_FISHEYE, [250.0, 319.5, 239.5, -K1, -K2]),
+            (orc.CAM_SIMPLE_RADIAL, [450.0, 319.5, 239.5, K1]),
+            (orc.CAM_SIMPLE_RADIAL_FISHEYE, [450.0, 319.5, 239.5, K1]),
+            (orc.CAM_POLYNOMIAL, PINHOLE + [K1, K2, K3]),
+            (orc.CAM_FOV, PINHOLE + [1.0]),
+            (orc.CAM_POLYNOMIAL_TANGENTIAL, PT),
+            (orc.CAM_FULL_OPENCV, PT[:4] + [-0.101082, 0.0703954, 0.0438661, -0.0680887, -0.00101082, .1, .001, -.001]),
+            (orc.CAM_FISHEYE_POLYNOMIAL_4, PT[:4] + [0.221184, 0.128597, 0.0623079, 0.20419]),
+            (orc.CAM_POLYNOMIAL_4, PT[:4] + [0.221184, 0.128597, 0.0623079, 0.20419]),
+            (orc.CAM_FISHEYE_POLYNOMIAL_TANGENTIAL, PT),
+            (orc.CAM_THIN_PRISM, BENCH), (orc.CAM_BENCHMARK, BENCH)]
+
+
+def base_intrinsics(p, model, orc):
+    unique = model in (orc.CAM_SIMPLE_PINHOLE, orc.CAM_RADIAL, orc.CAM_RADIAL_FISHEYE, orc.CAM_SIMPLE_RADIAL, orc.CAM_SIMPLE_RADIAL_FISHEYE)
+    return (p[0], p[0], p[1], p[2]) if unique else tuple(p[:4])
 
 
 def test_parameter_counts(oracle):
@@ -18,15 +42,19 @@ def test_parameter_counts(oracle):
     assert orc.cam_param_count(orc.CAM_PINHOLE) == 4           # camera_pinhole.h ParameterCount
     assert orc.cam_param_count(orc.CAM_THIN_PRISM) == 12       # camera_thin_prism.h:52-54
     assert orc.cam_param_count(orc.CAM_BENCHMARK) == 12        # FisheyeBase::ParameterCount -> inner model's
+    for model, p in cameras(oracle):
+        assert orc.cam_param_count(model) == len(p)            # test_camera.cc:361-376 TestParameterStorage
     with pytest.raises(ValueError):
-        orc.cam_param_count(0)                                 # FOV camera: not on the path
+        orc.cam_param_count(15)
 
 
 def test_undistort_distort_image_corners(oracle):
     orc = oracle
     # test_camera.cc:40-70: Distort(Undistort(n)) == n at the four image corners, 1e-5
     for model, p in cameras(oracle):
-        fx, fy, cx, cy = p[:4]
+        if model == orc.CAM_FOV:
+            continue                                           # test_camera.cc:384-388: the corners show nothing with these parameters
+        fx, fy, cx, cy = base_intrinsics(p, model, orc)
         fxi, fyi = np.float32(1.0 / fx), np.float32(1.0 / fy)
         cxi, cyi = np.float32(-1.0 * cx / fx), np.float32(-1.0 * cy / fy)
         corners = np.array([[0, 0], [W - 1, 0], [0, H - 1], [W - 1, H - 1]], np.float32)
@@ -40,7 +68,7 @@ def test_distort_undistort(oracle):
     # test_camera.cc:123-150: Undistort(Distort(n)) == n for nine image positions, 1e-5
     rel = np.array([[0, 0], [1, 1], [0, 1], [1, 0], [.5, .5], [.1, .2], [.8, .9], [.5, .6], [.1, .9]], np.float32)
     for model, p in cameras(oracle):
-        fx, fy, cx, cy = p[:4]
+        fx, fy, cx, cy = base_intrinsics(p, model, orc)
         fxi, fyi = np.float32(1.0 / fx), np.float32(1.0 / fy)
         cxi, cyi = np.float32(-1.0 * cx / fx), np.float32(-1.0 * cy / fy)
         n = np.stack([fxi * (rel[:, 0] * W) + cxi, fyi * (rel[:, 1] * H) + cyi], 1)
@@ -56,6 +84,8 @@ def test_image_derivative_by_world(oracle):
     for model, p in cameras(oracle):
         ana = orc.cam_eval(model, W, H, p, "d_by_world", pts).reshape(-1, 2, 3)
         for i, at in enumerate(pts):
+            if model == orc.CAM_FOV and at[0] == 0 and at[1] == 0:
+                continue                                       # test_camera.cc:262-265
             num = np.zeros((2, 3), np.float32)
             for a in range(3):
                 plus, minus = at.copy(), at.copy()
