@@ -32,20 +32,31 @@ namespace b2 {
 // One camera (pyramid level) from the reference's parameter vector (GetParameters order). Cut-offs are filled in by
 // compute_cutoffs() — the constructors' InitCutoff (camera_thin_prism.cc:40,50).
 static void cam_set(Cam* c, int type, int w, int h, const float* p) {
-  c->type = type; c->w = w; c->h = h; c->fx = p[0]; c->fy = p[1]; c->cx = p[2]; c->cy = p[3];
+  CamModel m{kDistNone, 0, 0, 0};
+  cam_model(type, &m);
+  c->type = type; c->w = w; c->h = h; c->dist = m.dist; c->fisheye = m.fisheye; c->unique_focal = m.unique_focal; c->nd = m.nd;
+  const int nb = m.unique_focal ? 3 : 4;
+  if (m.unique_focal) { c->fx = c->fy = p[0]; c->cx = p[1]; c->cy = p[2]; } else { c->fx = p[0]; c->fy = p[1]; c->cx = p[2]; c->cy = p[3]; }
   c->fx_inv = (float)(1.0 / c->fx); c->fy_inv = (float)(1.0 / c->fy);            // camera_base.cc:83
   c->cx_inv = (float)(-1.0 * c->cx / c->fx); c->cy_inv = (float)(-1.0 * c->cy / c->fy);
-  for (int i = 0; i < 8; ++i) c->d[i] = type == kCamPinhole ? 0.f : p[4 + i];
+  for (int i = 0; i < 8; ++i) c->d[i] = i < m.nd ? p[nb + i] : 0.f;
+  c->two_tan = c->image_radius = 0.f;
+  if (m.dist == kDistFOV) {                                                       // camera_fisheye_fov.cc:38-43 (tan correctly rounded, see b2_camera.cuh)
+    c->two_tan = 2.0f * (float)std::tan((double)(0.5f * c->d[0]));
+    c->image_radius = (float)(M_PI / (double)(2 * c->d[0]));
+  }
   c->cutoff2 = c->inner_cutoff2 = std::numeric_limits<float>::infinity();
 }
 static void cam_get(const Cam& c, float* p) {
-  p[0] = c.fx; p[1] = c.fy; p[2] = c.cx; p[3] = c.cy;
-  if (c.type != kCamPinhole) for (int i = 0; i < 8; ++i) p[4 + i] = c.d[i];
+  const int nb = c.unique_focal ? 3 : 4;
+  if (c.unique_focal) { p[0] = c.fx; p[1] = c.cx; p[2] = c.cy; } else { p[0] = c.fx; p[1] = c.fy; p[2] = c.cx; p[3] = c.cy; }
+  for (int i = 0; i < c.nd; ++i) p[nb + i] = c.d[i];
 }
 static Cam cam_half(const Cam& s) {                                          // CameraBaseImpl::ScaledBy(0.5), camera_base_impl.h:70-89
   const float f = 0.5f;
   float p[kMaxIntrinsics] = {0}; cam_get(s, p);
-  p[0] *= f; p[1] *= f; p[2] = f * (s.cx + 0.5f) - 0.5f; p[3] = f * (s.cy + 0.5f) - 0.5f;
+  if (!s.unique_focal) { p[0] *= f; p[1] *= f; p[2] = f * (s.cx + 0.5f) - 0.5f; p[3] = f * (s.cy + 0.5f) - 0.5f; }
+  else { p[0] *= f; p[1] = f * (s.cx + 0.5f) - 0.5f; p[2] = f * (s.cy + 0.5f) - 0.5f; }
   Cam d; cam_set(&d, s.type, (int)(f * s.w + 0.5f), (int)(f * s.h + 0.5f), p);
   return d;
 }
@@ -54,6 +65,7 @@ struct IntrinsicsB {
   std::vector<Cam> models;   // [0] = original resolution
   int min_image_scale = -1;
   int np() const { return cam_param_count(models[0].type); }
+  int kni() const { return cam_kernel_ni(models[0].type); }   // width of the Jacobian rows the kernels carry (>= np, zero padded)
   const Cam& model(int image_scale) const { return models[std::max(0, image_scale - min_image_scale)]; }
   int best_available(int image_scale) const { return std::min<int>(min_image_scale + (int)models.size() - 1, std::max<int>(min_image_scale, image_scale)); }
   void build_pyramid() { for (size_t i = 1; i < models.size(); ++i) models[i] = cam_half(models[i - 1]); }
@@ -147,14 +159,33 @@ static int nvars(const b2_reg* h) { return pose_var(h, (int)h->images.size()); }
 // K16: radius cut-offs of every pyramid level of the given intrinsics (the reference re-runs InitCutoff in each camera
 // constructor: CreateUpdatedCamera + ScaledBy per level, intrinsics.cc:66-79). One batched search, one readback.
 static int compute_cutoffs(b2_reg* h, std::vector<IntrinsicsB>* intr) {
-  std::vector<Cam> cams; std::vector<int> first(1, 0); std::vector<std::pair<int, int>> where;
+  std::vector<Cam> cams; std::vector<int> first(1, 0); std::vector<std::pair<int, int>> where;      // generic search (camera_base_impl.h:410-462)
+  std::vector<Cam> rcams; std::vector<std::pair<int, int>> rwhere;                                  // RadialBase search (camera_base_impl_radial.h:143-171)
+  auto assign = [](Cam& c, float v) { if (c.fisheye) c.inner_cutoff2 = v; else c.cutoff2 = v; };     // a fisheye camera keeps +inf; its inner model carries the cut-off
   for (size_t i = 0; i < intr->size(); ++i)
     for (size_t l = 0; l < (*intr)[i].models.size(); ++l) {
-      const Cam& c = (*intr)[i].models[l];
-      if (c.type == kCamPinhole) continue;
-      cams.push_back(c); where.emplace_back((int)i, (int)l);
-      first.push_back(first.back() + 2 * (c.w + c.h));
+      Cam& c = (*intr)[i].models[l];
+      if (c.dist == kDistPolyTan || c.dist == kDistOpenCV || c.dist == kDistThinPrism) {
+        cams.push_back(c); where.emplace_back((int)i, (int)l);
+        first.push_back(first.back() + 2 * (c.w + c.h));
+      } else if (c.dist == kDistRadial2 || c.dist == kDistPoly3 || c.dist == kDistPoly4) {
+        rcams.push_back(c); rwhere.emplace_back((int)i, (int)l);
+      } else if (c.dist == kDistRadial1) {
+        if (c.d[0] < 0) assign(c, -1.f / (3 * c.d[0]));                                              // SimpleRadialCamera::InitCutoff (camera_simple_radial.cc:53-57)
+      }
     }
+  if (!rcams.empty()) {
+    const int n = (int)rcams.size();
+    B2_TRY(h->cut_cams.ensure(sizeof(Cam) * n)); B2_TRY(h->cut_out.ensure(sizeof(float) * n));
+    B2_CUDA(cudaMemcpyAsync(h->cut_cams.p, rcams.data(), sizeof(Cam) * n, cudaMemcpyHostToDevice, h->stream));
+    kr_cutoff_radial<<<divup(n, 32), 32, 0, h->stream>>>(h->cut_cams.as<Cam>(), n, h->cut_out.as<float>());
+    ++h->launches;
+    std::vector<float> out(n);
+    B2_CUDA(cudaMemcpyAsync(out.data(), h->cut_out.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    B2_CUDA(cudaGetLastError());
+    for (int k = 0; k < n; ++k) assign((*intr)[rwhere[k].first].models[rwhere[k].second], out[k]);
+  }
   if (cams.empty()) return B2_OK;
   const int ncam = (int)cams.size(), npoints = first.back();
   B2_TRY(h->cut_cams.ensure(sizeof(Cam) * ncam)); B2_TRY(h->cut_first.ensure(sizeof(int) * (ncam + 1)));
@@ -170,10 +201,7 @@ static int compute_cutoffs(b2_reg* h, std::vector<IntrinsicsB>* intr) {
   B2_CUDA(cudaMemcpyAsync(out.data(), h->cut_out.p, sizeof(float) * ncam, cudaMemcpyDeviceToHost, h->stream));
   B2_CUDA(cudaStreamSynchronize(h->stream));
   B2_CUDA(cudaGetLastError());
-  for (int k = 0; k < ncam; ++k) {
-    Cam& c = (*intr)[where[k].first].models[where[k].second];
-    if (c.type == kCamThinPrism) c.cutoff2 = out[k]; else c.inner_cutoff2 = out[k];
-  }
+  for (int k = 0; k < ncam; ++k) assign((*intr)[where[k].first].models[where[k].second], out[k]);
   return B2_OK;
 }
 
@@ -449,8 +477,8 @@ static int residual_for_state(b2_reg* h, const StateB& st, double* cost) {
   return B2_OK;
 }
 
-static void launch_jacobians(b2_reg* h, int np, ObsSet& o, const ScaleB& P, const Pose3& P3, const Levels& L, const RigDev& rig) {
-  if (np == 4)
+static void launch_jacobians(b2_reg* h, int kni, ObsSet& o, const ScaleB& P, const Pose3& P3, const Levels& L, const RigDev& rig) {
+  if (kni == 4)
     kr_jacobians<4><<<divup(o.count, 256), 256, 0, h->stream>>>(o.count, o.idx.as<unsigned int>(), o.x.as<float>(), o.y.as<float>(), o.s.as<float>(),
                                                                  P.xyz.as<float>(), P3, P.radius, L, o.inten.as<float>(), o.jK.as<float>(), o.jP.as<float>(),
                                                                  rig, o.jR.as<float>());
@@ -492,7 +520,7 @@ static int accumulate_all(b2_reg* h, std::vector<double>* H, std::vector<double>
       ObsSet& o = h->obs[im][ps];
       if (o.count == 0) continue;
       evals += o.count;
-      const int np = st.intr[I.intrinsics_id].np();
+      const int np = st.intr[I.intrinsics_id].kni();      // width of the local system's intrinsics block (zero columns beyond the model's np)
       while (h->ev_pool.size() < 3 * (nsets + 1)) { cudaEvent_t e; B2_CUDA(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
       cudaEvent_t* ev = &h->ev_pool[3 * nsets];
       ++nsets;
@@ -548,13 +576,17 @@ static int accumulate_all(b2_reg* h, std::vector<double>* H, std::vector<double>
     if (!owned(h, im)) continue;
     const int iv = intr_var(h, h->images[im].intrinsics_id), pv = pose_var(h, (int)im);
     int rv; const bool dep = rig_dev(h, st, (int)im, &rv).dependent != 0;
-    const int ni = st.intr[h->images[im].intrinsics_id].np(), nr = dep ? 6 : 0, lv = ni + nr + 6, lh = lv * (lv + 1) / 2;
-    auto g = [&](int l) { return l < ni ? iv + l : l < ni + nr ? rv + (l - ni) : pv + (l - ni - nr); };
+    const int ni = st.intr[h->images[im].intrinsics_id].kni(), ni_real = st.intr[h->images[im].intrinsics_id].np();
+    const int nr = dep ? 6 : 0, lv = ni + nr + 6, lh = lv * (lv + 1) / 2;
+    auto g = [&](int l) { return l < ni ? (l < ni_real ? iv + l : -1) : l < ni + nr ? rv + (l - ni) : pv + (l - ni - nr); };   // -1: padding column
     for (size_t ps = 0; ps < S; ++ps) {
       const double* v = r + kAccW * (im * S + ps);
       int e = 0;
-      for (int c = 0; c < lv; ++c) for (int rr = 0; rr <= c; ++rr) { (*H)[(size_t)std::max(g(c), g(rr)) * nv + std::min(g(c), g(rr))] += v[e]; ++e; }
-      for (int k = 0; k < lv; ++k) (*b)[g(k)] += v[lh + k];
+      for (int c = 0; c < lv; ++c) for (int rr = 0; rr <= c; ++rr) {
+        if (g(c) >= 0 && g(rr) >= 0) (*H)[(size_t)std::max(g(c), g(rr)) * nv + std::min(g(c), g(rr))] += v[e];
+        ++e;
+      }
+      for (int k = 0; k < lv; ++k) if (g(k) >= 0) (*b)[g(k)] += v[lh + k];
       sums->fixed_sum += v[lh + lv]; sums->nf += v[lh + lv + 1]; sums->var_sum += v[lh + lv + 2]; sums->nv += v[lh + lv + 3];
     }
   }
@@ -717,9 +749,8 @@ int b2_reg_destroy(b2_reg* h) {
 
 int b2_reg_add_intrinsics(b2_reg* h, int camera_model, int width, int height, const float* params, int num_params, int* out_id) {
   REG_ENTER(h);
-  if (camera_model == 0) camera_model = kCamPinhole;   // ABI v1 alias
   const int np = cam_param_count(camera_model);
-  if (np < 0) return set_error(B2_ERR_ARG, "camera model %d not supported (4 = PINHOLE, 14 = THIN_PRISM, 5 = BENCHMARK / thin-prism fisheye)", camera_model);
+  if (np < 0) return set_error(B2_ERR_ARG, "camera model %d is not a camera::CameraBase::Type (0..14)", camera_model);
   if (!params || num_params != np || width < 2 || height < 2) return set_error(B2_ERR_ARG, "camera model %d needs %d parameters and a size >= 2x2", camera_model, np);
   if (h->initialized) return set_error(B2_ERR_STATE, "add_intrinsics after initialize");
   IntrinsicsB in; in.models.resize(1); cam_set(&in.models[0], camera_model, width, height, params);
@@ -1070,7 +1101,7 @@ int b2_reg_min_max_point_radius(b2_reg* h, const float* xyz, size_t n, double mi
     V.occlusion_threshold = h->prm.occlusion_depth_threshold; V.max_valid_intensity = h->prm.maximum_valid_intensity;
     V.min_scaling_factor = min_scaling_factor;
     V.table = nullptr;
-    if (V.cam0.type != kCamPinhole) {
+    if (cam_has_lookup(V.cam0)) {
       const size_t px = (size_t)V.cam0.w * V.cam0.h;
       if (table_for != im.intrinsics_id) {
         B2_TRY(d_table.ensure(px * 8));
@@ -1215,16 +1246,16 @@ int b2_reg_get_point_jacobians_rig(b2_reg* h, int image_id, int ps, float* inten
   const ImageB& I = h->images[image_id];
   const Levels L = levels_of(h, I, h->intr[I.intrinsics_id]);
   begin_call(h);
-  const int np = h->intr[I.intrinsics_id].np();
+  const int np = h->intr[I.intrinsics_id].np(), kni = h->intr[I.intrinsics_id].kni();
   int rv; const RigDev rig = rig_dev(h, current_state(h), image_id, &rv);
-  launch_jacobians(h, np, o, h->pts[ps], pose3_of(I.pose), L, rig);
+  launch_jacobians(h, kni, o, h->pts[ps], pose3_of(I.pose), L, rig);
   B2_CUDA(cudaGetLastError());
   if (jR) {
     if (rig.dependent) B2_CUDA(cudaMemcpyAsync(jR, o.jR.p, o.count * 24, cudaMemcpyDeviceToHost, h->stream));
     else std::memset(jR, 0, o.count * 24);
   }
   if (inten) B2_CUDA(cudaMemcpyAsync(inten, o.inten.p, o.count * 4, cudaMemcpyDeviceToHost, h->stream));
-  if (jK) B2_CUDA(cudaMemcpyAsync(jK, o.jK.p, o.count * 4 * np, cudaMemcpyDeviceToHost, h->stream));
+  if (jK) B2_CUDA(cudaMemcpy2DAsync(jK, (size_t)np * 4, o.jK.p, (size_t)kni * 4, (size_t)np * 4, o.count, cudaMemcpyDeviceToHost, h->stream));   // rows of kni floats, the first np are the model's
   if (jP) B2_CUDA(cudaMemcpyAsync(jP, o.jP.p, o.count * 24, cudaMemcpyDeviceToHost, h->stream));
   end_call(h);
   return B2_OK;
@@ -1354,7 +1385,6 @@ int b2_reg_last_stats(b2_reg* h, b2_reg_stats* out) {
 // Stand-alone camera evaluation (the camera::CameraBase calls Path B makes), mainly for parity tests of the camera models.
 int b2_camera_eval(int camera_model, int width, int height, const float* params, int num_params, int op, const float* in, size_t n, float* out,
                    float cutoffs[2]) {
-  if (camera_model == 0) camera_model = kCamPinhole;
   const int np = cam_param_count(camera_model);
   if (np < 0 || !params || num_params != np || width < 2 || height < 2) return set_error(B2_ERR_ARG, "unsupported camera model or parameter count");
   if (op < 0 || op > 3 || (op != 0 && n != 0 && (!in || !out))) return set_error(B2_ERR_ARG, "bad op / null buffers");

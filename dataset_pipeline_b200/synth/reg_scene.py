@@ -39,19 +39,69 @@ def _thin_prism(d, x, y):
     return (x * radial + 2 * p1 * xy + p2 * (r2 + 2 * x2) + sx1 * r2, y * radial + 2 * p2 * xy + p1 * (r2 + 2 * y2) + sy1 * r2)
 
 
+# camera::CameraBase::Type -> (distortion function, fisheye wrapper, single focal length); mirrors b2_camera.cuh:cam_model
+_MODELS = {0: ("fov", False, False), 1: ("radial", False, False), 2: ("tangential", False, False), 3: ("tangential", True, False),
+           4: ("none", False, False), 5: ("thin_prism", True, False), 6: ("radial", True, False), 7: ("none", False, True),
+           8: ("radial", False, True), 9: ("radial", False, True), 10: ("opencv", False, False), 11: ("radial", False, False),
+           12: ("radial", True, True), 13: ("radial", True, True), 14: ("thin_prism", False, False)}
+
+
+def distort(camera_model, dist, x, y):
+    """Normalized -> distorted coordinates in float64 (scene generation only; the product path is the CUDA library)."""
+    kind, fisheye, _ = _MODELS[camera_model]
+    if fisheye:
+        r = np.sqrt(x * x + y * y)
+        f = np.where(r > 1e-9, np.arctan(r) / np.maximum(r, 1e-9), 1.0)
+        x, y = x * f, y * f
+    if kind == "none":
+        return x, y
+    if kind == "thin_prism":
+        return _thin_prism(dist, x, y)
+    r2 = x * x + y * y
+    if kind == "radial":
+        fac = 0.0
+        for k in reversed(list(dist)):
+            fac = r2 * (k + fac)
+        return x * (1 + fac), y * (1 + fac)
+    if kind == "tangential":
+        k1, k2, p1, p2 = dist
+        radial = 1 + r2 * (k1 + r2 * k2)
+        return x * radial + 2 * p1 * x * y + p2 * (r2 + 2 * x * x), y * radial + 2 * p2 * x * y + p1 * (r2 + 2 * y * y)
+    if kind == "opencv":
+        k1, k2, p1, p2, k3, k4, k5, k6 = dist
+        radial = (1 + r2 * (k1 + r2 * (k2 + r2 * k3))) / (1 + r2 * (k4 + r2 * (k5 + r2 * k6)))
+        return x * radial + 2 * p1 * x * y + p2 * (r2 + 2 * x * x), y * radial + 2 * p2 * x * y + p1 * (r2 + 2 * y * y)
+    omega = dist[0]                                                     # FOV
+    r = np.sqrt(r2)
+    f = np.where(r > 1e-9, np.arctan(r * 2 * math.tan(0.5 * omega)) / (np.maximum(r, 1e-9) * omega), 1.0)
+    return x * f, y * f
+
+
 def unproject(camera_model, dist, dx, dy):
     """Distorted (f-normalised) coordinates -> normalized ray coordinates (float64, damped fixed-point inversion)."""
-    if camera_model == CAM_PINHOLE:
+    if _MODELS[camera_model][0] == "none" and not _MODELS[camera_model][1]:
         return dx, dy
+    if camera_model in (CAM_BENCHMARK, CAM_THIN_PRISM):                 # (kept as it was: the committed scenes depend on it)
+        ux, uy = dx.copy(), dy.copy()
+        for _ in range(60):
+            fx_, fy_ = _thin_prism(dist, ux, uy)
+            ux = ux + 0.8 * (dx - fx_); uy = uy + 0.8 * (dy - fy_)
+        if camera_model == CAM_BENCHMARK:
+            r = np.sqrt(ux * ux + uy * uy)
+            f = np.where(r > 1e-9, np.tan(np.minimum(r, 1.5)) / np.maximum(r, 1e-9), 1.0)
+            ux, uy = ux * f, uy * f
+        return ux, uy
     ux, uy = dx.copy(), dy.copy()
-    for _ in range(60):
-        fx_, fy_ = _thin_prism(dist, ux, uy)
+    for _ in range(80):
+        fx_, fy_ = distort(camera_model, dist, ux, uy)
         ux = ux + 0.8 * (dx - fx_); uy = uy + 0.8 * (dy - fy_)
-    if camera_model == CAM_BENCHMARK:
-        r = np.sqrt(ux * ux + uy * uy)
-        f = np.where(r > 1e-9, np.tan(np.minimum(r, 1.5)) / np.maximum(r, 1e-9), 1.0)
-        ux, uy = ux * f, uy * f
     return ux, uy
+
+
+def split_params(camera_model, params):
+    """GetParameters order -> ((fx, fy, cx, cy), distortion parameters)."""
+    p = [float(v) for v in params]
+    return ((p[0], p[0], p[1], p[2]), p[3:]) if _MODELS[camera_model][2] else ((p[0], p[1], p[2], p[3]), p[4:])
 
 
 def render_image(width, height, K, camera_model, distortion, R_wc, c):
@@ -115,12 +165,17 @@ def load_rig_into(reg, scene, use_init=True):
 
 
 def make_scene(num_images=3, width=640, height=480, fx=520.0, extent=(2.4, 1.8), base_radius=0.0025, num_scales=3, seed=31,
-               perturb=(0.002, 0.002), camera_model=CAM_PINHOLE, distortion=DEFAULT_DISTORTION):
+               perturb=(0.002, 0.002), camera_model=CAM_PINHOLE, distortion=DEFAULT_DISTORTION, camera_params=None):
     """Returns dict(intr=(w,h,params), camera_model, images=[uint8 HxW], poses_gt, poses_init (qx qy qz qw tx ty tz),
-    scales=[(xyz, radius, nbr, colors)]). params = fx fy cx cy (+ k1 k2 p1 p2 k3 k4 sx1 sy1 for the distorted models)."""
+    scales=[(xyz, radius, nbr, colors)]). params = fx fy cx cy (+ k1 k2 p1 p2 k3 k4 sx1 sy1 for the thin-prism models), or camera_params
+    (the model's full GetParameters vector) for any of the 15 camera models."""
     rng = np.random.default_rng(seed)
     K = np.array([fx, fx, (width - 1) / 2.0, (height - 1) / 2.0], np.float32)
     params = K if camera_model == CAM_PINHOLE else np.concatenate([K, np.asarray(distortion, np.float32)])
+    if camera_params is not None:
+        params = np.asarray(camera_params, np.float32)
+        K4, distortion = split_params(camera_model, params)
+        K = np.array(K4, np.float32)
     images, poses_gt, poses_init = [], [], []
     for i in range(num_images):
         # camera centre above the plane, looking down (camera z axis = -world z), small tilts

@@ -231,9 +231,9 @@ int b2_ms_point_neighbors(const float* xyz, size_t n, const uint8_t* scan_indice
  * CostCalculator::ComputeCost (cost_calculator.cc:44-100), IntrinsicsAndPoseOptimizer::Apply
  * (intrinsics_and_pose_optimizer.h:48-51, .cc:48-259), OcclusionGeometry::RenderDepthMap splat path
  * (occlusion_geometry.cc:404-464) and the image / mask / intrinsics pyramids (image.cc:106-154, intrinsics.cc:45-79).
- * Scope of this ABI version: PINHOLE cameras (camera_pinhole.h), no rigs, depth residuals off (the reference default,
- * parameters.h:54); occlusion depth from splats, from a caller-supplied depth map, or none (all visible).
- * Variable layout of H/b/delta: [4 per intrinsics (fx fy cx cy) | 6 per image (translation, rotation)], ascending ids.
+ * Scope: every camera model of src/camera, camera rigs, depth residuals off (the reference default, parameters.h:54); occlusion depth
+ * from a mesh, from splats, from a caller-supplied depth map, or none (all visible).
+ * Variable layout of H/b/delta: [ParameterCount() per intrinsics | 6 per further rig camera | 6 per image (translation, rotation)], ascending ids.
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct b2_reg b2_reg;
 
@@ -272,10 +272,13 @@ int b2_camera_eval(int camera_model, int width, int height, const float* params,
 void b2_reg_default_params(b2_reg_params* p);
 int b2_reg_create(const b2_reg_params* p, b2_reg** out);
 int b2_reg_destroy(b2_reg* h);
-/* camera_model = camera::CameraBase::Type (camera_base.h:67-84): 4 PINHOLE (fx fy cx cy), 14 THIN_PRISM and 5 BENCHMARK = ETH3D's
- * THIN_PRISM_FISHEYE (fx fy cx cy k1 k2 p1 p2 k3 k4 sx1 sy1, GetParameters order); 0 is accepted as PINHOLE. num_params must
- * equal the model's ParameterCount(). COLMAP's -0.5 px shift (colmap_model.cc:833) is the caller's job. The radius cut-off
- * search of the reference's camera constructors (camera_base_impl.h:410-462) runs on the device whenever intrinsics change. */
+/* camera_model = camera::CameraBase::Type (camera_base.h:67-84), all 15 models: 0 FOV (fx fy cx cy omega), 1 POLYNOMIAL (+ k1 k2 k3),
+ * 2 POLYNOMIAL_TANGENTIAL / 3 FISHEYE_POLYNOMIAL_TANGENTIAL (+ k1 k2 p1 p2), 4 PINHOLE (fx fy cx cy), 5 BENCHMARK = ETH3D's
+ * THIN_PRISM_FISHEYE / 14 THIN_PRISM (+ k1 k2 p1 p2 k3 k4 sx1 sy1), 6 FISHEYE_POLYNOMIAL_4 / 11 POLYNOMIAL_4 (+ k1 k2 k3 k4), 10 FULL_OPENCV
+ * (+ k1 k2 p1 p2 k3 k4 k5 k6), and the single-focal-length models 7 SIMPLE_PINHOLE (f cx cy), 8 RADIAL / 12 RADIAL_FISHEYE (+ k1 k2),
+ * 9 SIMPLE_RADIAL / 13 SIMPLE_RADIAL_FISHEYE (+ k) — GetParameters order; num_params must equal the model's ParameterCount(). COLMAP's
+ * -0.5 px shift (colmap_model.cc:833) is the caller's job. The radius cut-off search of the reference's camera constructors
+ * (camera_base_impl.h:410-462, camera_base_impl_radial.h:143-171, camera_simple_radial.cc:53-57) runs on the device whenever intrinsics change. */
 int b2_reg_add_intrinsics(b2_reg* h, int camera_model, int width, int height, const float* params, int num_params, int* out_id);
 /* gray: width*height uint8 (cv::imread GRAYSCALE); mask: same size or NULL (values 0/1/2, image.h:43-47);
  * image_T_global: Sophus::SE3f::data() order qx qy qz qw tx ty tz (what io::ReadColmapImages fills, colmap_model.cc:117-124). */

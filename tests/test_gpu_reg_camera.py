@@ -164,7 +164,9 @@ def test_rejects_unknown_model_and_wrong_count():
     b2, R = _b2()
     g = b2.Registration()
     with pytest.raises(Exception):
-        g.add_intrinsics(64, 48, [50, 50, 32, 24, 0.1], camera_model=0 + 8)      # RADIAL: not supported
+        g.add_intrinsics(64, 48, [50, 50, 32, 24, 0.1], camera_model=15)         # not a camera::CameraBase::Type
+    with pytest.raises(Exception):
+        g.add_intrinsics(64, 48, [50, 50, 32, 24], camera_model=8)                # RADIAL is f cx cy k1 k2
     with pytest.raises(Exception):
         g.add_intrinsics(64, 48, [50, 50, 32, 24], camera_model=5)                # BENCHMARK needs 12
 
