@@ -124,3 +124,68 @@ def test_path_b_with_every_distortion_family(oracle, model):
     assert np.asarray(gi).size == npar
     assert rel(gp, op) < 1e-5 and rel(gi, oi) < 1e-5, (rel(gp, op), rel(gi, oi))
     assert abs(c2g - c2o) <= 1e-5 * abs(c2o)
+
+
+@pytest.mark.parametrize("model", [2, 13, 1])
+def test_mesh_occlusion_with_further_models(oracle, model):
+    """K8 / K9 with the vertex-stage distortion of the other renderer programs (opengl/renderer.cc:154-560: z * Distort(x/z, y/z), pushed
+    out by 99 beyond the cut-off): depth maps and the observation sets behind them identical to the oracle's software rasteriser."""
+    b2, R = _b2()
+    from dataset_pipeline_b200.synth import reg_scene
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from mesh_util import _grid_mesh, _box_mesh
+    sc = reg_scene.make_scene(num_images=2, width=320, height=240, camera_model=model, camera_params=SCENE_CAMERAS[model], num_scales=3, base_radius=0.004)
+    Vp, Fp = _grid_mesh(-1.3, 1.3, -1.0, 1.0, 0.0, 30)
+    Vb, Fb = _box_mesh((0.2, 0.1, 0.5), 0.15)
+    V = np.concatenate([Vp, Vb]); F = np.concatenate([Fp, Fb + len(Vp)])
+    area = 320 * 240 // 4
+    kw = dict(max_initial_image_area_in_pixels=area, mask_occlusion_boundaries=1)
+    g = b2.Registration(R.default_params(**kw)); o = oracle.Registration(oracle.reg_default_params(**kw))
+    for r in (g, o):
+        reg_scene.load_into(r, sc, splats=False)
+        r.set_mesh(V, F); r.set_image_scale(0)
+    for im in range(2):
+        dg, sg = g.render_depth(im); do, so = o.render_depth(im)
+        assert sg == so and np.array_equal(dg, do), (model, im, int((dg != do).sum()))
+        assert (do > 0).mean() > 0.5 and (do == -1).sum() > 200
+    g.CreateObservationsForAllImages(1); o.create_observations(1)
+    n = 0
+    for im in range(2):
+        for ps in range(3):
+            go, oo = g.observations(im, ps), o.observations(im, ps)
+            assert all(np.array_equal(a, b) for a, b in zip(go, oo)), (model, im, ps)
+            n += len(oo[0])
+    assert n > 10000
+
+
+@pytest.mark.parametrize("model", [7, 9, 10, 0])
+def test_min_max_point_radius_with_further_models(oracle, model):
+    """ComputeMinMaxPointRadius (multi_scale_point_cloud.cc:126-184): ImageToNormalized through the undistortion lookup (generic
+    IterativeUndistort per pixel), directly for SimplePinhole, in closed form for the FOV camera."""
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import registration as R
+    from dataset_pipeline_b200.synth import reg_scene
+    sc = reg_scene.make_scene(num_images=3, width=320, height=240, camera_model=model, camera_params=SCENE_CAMERAS[model], num_scales=1, base_radius=0.004)
+    rng = np.random.default_rng(8)
+    gx, gy = np.meshgrid(np.arange(-1.3, 1.3, 0.011), np.arange(-1.0, 1.0, 0.011), indexing="xy")
+    pts = np.stack([gx.ravel() + rng.uniform(-0.003, 0.003, gx.size), gy.ravel() + rng.uniform(-0.003, 0.003, gx.size), rng.normal(0, 2e-4, gx.size)], 1).astype(np.float32)
+    area = 320 * 240 // 64
+    g = b2.Registration(R.default_params(max_initial_image_area_in_pixels=area)); o = oracle.Registration(oracle.reg_default_params(max_initial_image_area_in_pixels=area))
+    counts = []
+    for reg in (g, o):
+        w, h, K = sc["intr"]
+        reg.add_intrinsics(w, h, K, camera_model=model)
+        for img, T in zip(sc["images"], sc["poses_gt"]):
+            reg.add_image(0, img, None, T)
+        counts.append(reg.initialize())
+        reg.set_splat_points(pts); reg.set_image_scale(0)
+    assert counts[0] == counts[1] == 4
+    msf = float(np.float32(2.0 ** (-(counts[0] - 1))))
+    lg, hg = g.ComputeMinMaxPointRadius(pts, msf); lo, ho = o.min_max_point_radius(pts, msf)
+    seen = np.isfinite(lo)
+    assert np.array_equal(np.isfinite(lg), seen) and 0.3 < seen.mean() <= 1.0
+    if model == 0:      # FOV: tan / atan of the device's double library vs glibc's, and a difference of two nearby rays (cancellation)
+        assert np.allclose(lg[seen], lo[seen], rtol=1e-3, atol=0) and np.allclose(hg[seen], ho[seen], rtol=1e-3, atol=0)
+    else:
+        assert np.array_equal(lg, lo) and np.array_equal(hg, ho)
