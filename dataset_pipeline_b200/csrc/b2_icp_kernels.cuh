@@ -285,17 +285,17 @@ __global__ void __launch_bounds__(128) k_nn_radius1(const float4* __restrict__ s
   const float ex2 = ex * ex * 0.9999f, ey2 = ey * ey * 0.9999f, ez2 = ez * ez * 0.9999f;
 
   // Own cell first; a neighbour (bit0 = x, bit1 = y, bit2 = z) is probed only if its nearest face is not already farther than the
-  // best match, which removes most of the 8 probes for matched queries.
+  // best match, which removes most of the 8 probes for matched queries. The neighbours a lane still needs are kept as a bit mask and
+  // popped in a per-lane loop: in round r every lane probes ITS r-th remaining neighbour, whichever that is, so the ~0.35 neighbour
+  // probes per query of a warp run side by side instead of one mostly idle pass per neighbour slot (measured: search 36.8 -> 33.9 ms
+  // per outer iteration at config 2).
   const unsigned int mask = (1u << log2size) - 1u;
   float best = r2;
   int best_pos = -1;
   unsigned int best_idx = 0xFFFFFFFFu;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float lb = ((c & 1) ? ex2 : 0.f) + ((c & 2) ? ey2 : 0.f) + ((c & 4) ? ez2 : 0.f);
-    if (lb > best) continue;
+  auto probe = [&](int c) {
     const int x = cx + ((c & 1) ? sx : 0), y = cy + ((c & 2) ? sy : 0), z = cz + ((c & 4) ? sz : 0);
-    if (x < 0 || x >= g.nx || y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+    if (x < 0 || x >= g.nx || y < 0 || y >= g.ny || z < 0 || z >= g.nz) return;
     const unsigned long long key = cell_key(g, x, y, z);
     unsigned int s = hash_slot(key, log2size);
     uint4 e = __ldg(reinterpret_cast<const uint4*>(table + s));
@@ -306,6 +306,20 @@ __global__ void __launch_bounds__(128) k_nn_radius1(const float4* __restrict__ s
       k = ((unsigned long long)e.y << 32) | e.x;
     }
     if (k == key) scan_cell(tgt, box1, box2, e.z, e.w, q, best, best_pos, best_idx, wk);
+  };
+  probe(0);
+  unsigned int todo = 0;
+#pragma unroll
+  for (int c = 1; c < 8; ++c) {
+    const float lb = ((c & 1) ? ex2 : 0.f) + ((c & 2) ? ey2 : 0.f) + ((c & 4) ? ez2 : 0.f);
+    if (!(lb > best)) todo |= 1u << c;
+  }
+  while (todo) {
+    const int c = __ffs(todo) - 1;
+    todo &= todo - 1u;
+    const float lb = ((c & 1) ? ex2 : 0.f) + ((c & 2) ? ey2 : 0.f) + ((c & 4) ? ez2 : 0.f);
+    if (lb > best) continue;                  // an earlier neighbour tightened the bound
+    probe(c);
   }
   if (STATS) work[j] = make_uint4(wk.points, wk.box1, wk.box2, wk.cells);
   match_pos[j] = best_pos;

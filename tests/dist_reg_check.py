@@ -1,4 +1,5 @@
-"""Launched by torchrun (one process per GPU): image-sharded Path B (b2_reg_set_comm) against the single-GPU result on rank 0.
+"""Launched by torchrun (one process per GPU): image-sharded Path B (b2_reg_set_comm), sharded normals and pair-direction-sharded ICP
+against the single-GPU results on rank 0.
 Prints DIST_REG_OK from rank 0 on success. Used by tests/test_gpu_reg_dist.py; also runnable by hand:
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/dist_reg_check.py"""
 import os
@@ -31,6 +32,26 @@ def main():
     nd, dense_d = estimate_normals_dist(pts, 12, (0.0, 0.0, 5.0), comm, device=local)
     ns = estimate_normals(pts, 12, (0.0, 0.0, 5.0))
     assert np.array_equal(np.nan_to_num(nd, nan=7.0), np.nan_to_num(ns, nan=7.0)), "sharded normals differ from the single-GPU result"
+
+    # ---- pair-direction-sharded ICP (b2_icp_config.rank / world_size / comm): poses, LM try sequence and counts as on one GPU ----
+    from dataset_pipeline_b200 import synth
+    clouds, poses, _ = synth.room_scans(3, 400, 160)
+    def run_icp(**kw):
+        g = b2.PointToPlaneICP(device=local, **kw)
+        for (xyz, nrm), T in zip(clouds, poses):
+            g.AddPointCloud(xyz, nrm, T)
+        tries = []
+        for it in range(3):
+            g.Run(0.05, it, 1, 1e-10, False)
+            tries.append((g.stats()["inner_iterations"], g.stats()["lm_tries_total"], g.stats()["num_correspondences"]))
+        return [g.GetResultGlobalTCloud(i).astype(np.float64) for i in range(3)], tries
+    pd, td = run_icp(rank=rank, world_size=world, comm=comm)
+    if rank == 0:
+        ps, ts = run_icp()
+        assert td == ts, "sharded ICP: LM sequence / correspondence counts differ: %s vs %s" % (td, ts)
+        for a, c in zip(pd, ps):
+            assert np.linalg.norm(a - c) / np.linalg.norm(c) <= 1e-6, "sharded ICP poses differ"
+        print("dist_icp_check", world, "ranks: (inner iterations, LM tries, correspondences) per outer iteration", td, flush=True)
 
     model = int(os.environ.get("B2_TEST_CAMERA", "5"))
     sc = reg_scene.make_rig_scene(num_sets=3, camera_model=model)          # 6 images: ranks own 3 each; rig sets span both ranks
