@@ -152,6 +152,7 @@ __device__ __forceinline__ float3 xform_normal(const Mat4& T, float x, float y, 
 struct GridParams {
   double ox, oy, oz;   // origin (bbox min)
   double inv;          // 1 / cell size
+  double cell;         // 1.0 / inv, precomputed (a double division per query otherwise)
   int nx, ny, nz;      // cells per axis (each < 2^21)
   int fbits;           // bits per axis of the in-cell Morton code appended to the cell key (5..8)
 };

@@ -77,6 +77,7 @@ struct b2_icp {
   int grid_acc = 0;
   unsigned long long per_cta = 0;
   int launches = 0;
+  int prev_inner_iterations = 0;        // LM iterations of the previous outer iteration (0 = none yet): gates the speculative second try
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> acc_events, nn_events;
 };
@@ -190,6 +191,7 @@ static int compute_grid(b2_icp* h, float max_dist, GridParams* g, int* key_bits)
     cell *= 2.0; g->inv = 1.0 / cell;
     g->nx = cell_of(mx[0], g->ox, g->inv) + 1; g->ny = cell_of(mx[1], g->oy, g->inv) + 1; g->nz = cell_of(mx[2], g->oz, g->inv) + 1;
   }
+  g->cell = 1.0 / g->inv;
   const unsigned long long maxkey = cell_key(*g, g->nx - 1, g->ny - 1, g->nz - 1);
   int bits = 1;
   while (bits < 64 && (maxkey >> bits) != 0ull) ++bits;
@@ -519,13 +521,18 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   h->H0 = H; h->b0 = b; h->cost0 = cost;
   double lambda = 0.1;
   const int max_inner = h->cfg.inner_max_iterations > 0 ? h->cfg.inner_max_iterations : 150;
+  // The first pass of an LM iteration carries a speculative second try only once the alignment has settled (the previous outer
+  // iteration took at most three LM iterations, i.e. it was mostly its final chain of ten rejected tries): far from convergence every
+  // iteration is accepted at its first try and the extra cost evaluation (+32 % on the pass) would be thrown away each time. The
+  // decision depends on counts the reference produces identically, never on timing, so runs stay reproducible.
+  const bool speculate_first = h->prev_inner_iterations > 0 && h->prev_inner_iterations <= 3;
   for (int it = 0; it < max_inner; ++it) {
     ++h->stats.inner_iterations;
     bool applied = false;
     int ntries = 0;
     for (int lm = 0; lm < 10 && !applied;) {
       // tries lm .. lm + nb - 1 of this iteration: damping lambda, 2 lambda, 4 lambda, ...
-      const int nb = std::min(10 - lm, 1 + (lm == 0 ? spec.first : spec.second));
+      const int nb = std::min(10 - lm, 1 + (lm == 0 ? (speculate_first ? spec.first : 0) : spec.second));
       const bool with_h = lm == 0;
       batch.assign(nb, poses);
       double lam_j = lambda;
@@ -569,6 +576,7 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
     h->tries.push_back(ntries);
     if (!applied) break;
   }
+  h->prev_inner_iterations = h->stats.inner_iterations;
   h->stats.last_cost = cost;
   h->stats.final_lambda = lambda;
   B2_CUDA(cudaEventRecord(h->ev[4], h->stream));

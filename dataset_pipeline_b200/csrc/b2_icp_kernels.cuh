@@ -174,17 +174,20 @@ __global__ void __launch_bounds__(256) k_chunk_boxes2(const Aabb* __restrict__ b
 
 struct SearchWork { unsigned int points, box1, box2, cells; };   // per-query work counters of the diagnostic K3 variant (B2_K3_WORK)
 
-// candidate test; ties on d2 go to the lower original target index so the result does not depend on the visiting order
+// candidate test; ties on d2 go to the lower original target index so the result does not depend on the visiting order.
+// (d2, index) is ONE 64-bit key, (d2 bits << 32) | index: for non-negative floats the integer order is the float order, so a single
+// unsigned compare implements "d2 < best, or d2 == best and lower index"; the initial key (r2 bits << 32) | 0 rejects d2 == r2 for every
+// index (the radius test is strict). best (float) is kept alongside for the box / face pruning tests.
 #define B2_NN_TEST(T, P)                                                                                              \
   {                                                                                                                   \
     const float ax_ = fsub(q.x, (T).x), ay_ = fsub(q.y, (T).y), az_ = fsub(q.z, (T).z);                                \
     const float d_ = fadd(fadd(fmul(ax_, ax_), fmul(ay_, ay_)), fmul(az_, az_));                                      \
-    const unsigned int i_ = __float_as_uint((T).w);                                                                   \
-    if (d_ < best || (d_ == best && best_pos >= 0 && i_ < best_idx)) { best = d_; best_pos = (int)(P); best_idx = i_; } \
+    const unsigned long long k_ = ((unsigned long long)__float_as_uint(d_) << 32) | (unsigned long long)__float_as_uint((T).w); \
+    if (k_ < best_key) { best_key = k_; best = d_; best_pos = (int)(P); }                                              \
   }
 
 __device__ __forceinline__ void scan_range(const float4* __restrict__ tgt, unsigned int b, unsigned int e, const float4& q, float& best,
-                                           int& best_pos, unsigned int& best_idx, SearchWork& wk) {
+                                           int& best_pos, unsigned long long& best_key, SearchWork& wk) {
   wk.points += e - b;
   unsigned int p = b;
   for (; p + 3 < e; p += 4) {   // four candidate loads in flight: the heavy lanes of this kernel are latency bound
@@ -198,7 +201,7 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ tgt, unsig
 }
 // candidates p, p+stride, p+2 stride, p+3 stride (those below e)
 __device__ __forceinline__ void scan_strided4(const float4* __restrict__ tgt, unsigned int p, unsigned int stride, unsigned int e, const float4& q,
-                                              float& best, int& best_pos, unsigned int& best_idx, SearchWork& wk) {
+                                              float& best, int& best_pos, unsigned long long& best_key, SearchWork& wk) {
   const unsigned int p1 = p + stride, p2 = p + 2u * stride, p3 = p + 3u * stride;
   const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + min(p1, e - 1)), t2 = __ldg(tgt + min(p2, e - 1)), t3 = __ldg(tgt + min(p3, e - 1));
   wk.points += 1u + (p1 < e) + (p2 < e) + (p3 < e);
@@ -214,16 +217,16 @@ __device__ __forceinline__ void scan_strided4(const float4* __restrict__ tgt, un
 // neighbour — ~10^3 candidates against a mean of ~20 (measured with B2_K3_WORK / tools/k3_work.py). Those lanes are latency
 // bound, so scan_range keeps four candidate loads in flight, and the launch order of the CTAs is longest-first (k_cta_cost).
 __device__ __forceinline__ void scan_cell(const float4* __restrict__ tgt, const Aabb* __restrict__ box1, const Aabb* __restrict__ box2,
-                                          unsigned int b, unsigned int e, const float4& q, float& best, int& best_pos, unsigned int& best_idx,
+                                          unsigned int b, unsigned int e, const float4& q, float& best, int& best_pos, unsigned long long& best_key,
                                           SearchWork& wk) {
   ++wk.cells;
-  if (e - b <= 48u) { scan_range(tgt, b, e, q, best, best_pos, best_idx, wk); return; }
+  if (e - b <= 48u) { scan_range(tgt, b, e, q, best, best_pos, best_key, wk); return; }
   const unsigned int last = e - 1;
   if (e - b > 2u * kChunk2) {
     // Very dense cell: a strided sample of 64 candidates first (independent loads), so that `best` is already tight when the
     // chunk boxes are tested. Sampled points are real candidates; re-visiting them later changes nothing.
     const unsigned int stride = (e - b) / 64u;
-    for (unsigned int p = b; p < e; p += 4u * stride) scan_strided4(tgt, p, stride, e, q, best, best_pos, best_idx, wk);
+    for (unsigned int p = b; p < e; p += 4u * stride) scan_strided4(tgt, p, stride, e, q, best, best_pos, best_key, wk);
   }
   for (unsigned int c2 = b / kChunk2; c2 <= last / kChunk2; ++c2) {
     ++wk.box2;
@@ -232,7 +235,7 @@ __device__ __forceinline__ void scan_cell(const float4* __restrict__ tgt, const 
     for (unsigned int c1 = c1b; c1 <= c1e; ++c1) {
       ++wk.box1;
       if (dist2_box(q.x, q.y, q.z, box1[c1]) > best) continue;
-      scan_range(tgt, max(b, c1 * kChunk1), min(e, (c1 + 1u) * kChunk1), q, best, best_pos, best_idx, wk);
+      scan_range(tgt, max(b, c1 * kChunk1), min(e, (c1 + 1u) * kChunk1), q, best, best_pos, best_key, wk);
     }
   }
 }
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(128) k_nn_radius1(const float4* __restrict__ s
   const double rx = fx - cx, ry = fy - cy, rz = fz - cz;               // position inside the cell, [0,1)
   const int sx = rx < 0.5 ? -1 : 1, sy = ry < 0.5 ? -1 : 1, sz = rz < 0.5 ? -1 : 1;
   // distance to the nearer face per axis, shrunk so that fp32 rounding of d2 can never beat the bound
-  const double cell = 1.0 / g.inv;
+  const double cell = g.cell;
   const float ex = (float)((rx < 0.5 ? rx : 1.0 - rx) * cell * 0.9999);
   const float ey = (float)((ry < 0.5 ? ry : 1.0 - ry) * cell * 0.9999);
   const float ez = (float)((rz < 0.5 ? rz : 1.0 - rz) * cell * 0.9999);
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(128) k_nn_radius1(const float4* __restrict__ s
   const unsigned int mask = (1u << log2size) - 1u;
   float best = r2;
   int best_pos = -1;
-  unsigned int best_idx = 0xFFFFFFFFu;
+  unsigned long long best_key = (unsigned long long)__float_as_uint(r2) << 32;
   auto probe = [&](int c) {
     const int x = cx + ((c & 1) ? sx : 0), y = cy + ((c & 2) ? sy : 0), z = cz + ((c & 4) ? sz : 0);
     if (x < 0 || x >= g.nx || y < 0 || y >= g.ny || z < 0 || z >= g.nz) return;
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(128) k_nn_radius1(const float4* __restrict__ s
       e = __ldg(reinterpret_cast<const uint4*>(table + s));
       k = ((unsigned long long)e.y << 32) | e.x;
     }
-    if (k == key) scan_cell(tgt, box1, box2, e.z, e.w, q, best, best_pos, best_idx, wk);
+    if (k == key) scan_cell(tgt, box1, box2, e.z, e.w, q, best, best_pos, best_key, wk);
   };
   probe(0);
   unsigned int todo = 0;
