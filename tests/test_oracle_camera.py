@@ -159,3 +159,37 @@ def test_pyramid_scaling_matches_pinhole_rule(oracle):
     half_p[2] = np.float32(0.5) * (half_p[2] + np.float32(0.5)) - np.float32(0.5); half_p[3] = np.float32(0.5) * (half_p[3] + np.float32(0.5)) - np.float32(0.5)
     half = orc.cam_eval(orc.CAM_BENCHMARK, W // 2, H // 2, half_p, "project", n)
     assert np.abs(half - ((full + 0.5) / 2 - 0.5)).max() < 1e-3
+
+
+def test_radial_and_closed_form_cutoffs(oracle):
+    """RadialBase::InitCutoff (camera_base_impl_radial.h:143-171) and SimpleRadialCamera::InitCutoff (camera_simple_radial.cc:53-57)."""
+    orc = oracle
+    # closed form: k < 0 -> -1 / (3 k) (where d(distorted r)/dr = 1 + 3 k r^2 changes sign); k >= 0 -> no cut-off
+    assert orc.cam_cutoff(orc.CAM_SIMPLE_RADIAL, W, H, [450.0, 319.5, 239.5, -0.2]) == (np.float32(-1.0) / (np.float32(3) * np.float32(-0.2)), float("inf"))
+    assert orc.cam_cutoff(orc.CAM_SIMPLE_RADIAL, W, H, [450.0, 319.5, 239.5, K1]) == (float("inf"), float("inf"))
+    own, inner = orc.cam_cutoff(orc.CAM_SIMPLE_RADIAL_FISHEYE, W, H, [450.0, 319.5, 239.5, -0.2])
+    assert own == float("inf") and inner == np.float32(-1.0) / (np.float32(3) * np.float32(-0.2))      # the fisheye camera's INNER model carries it
+    # radial search: the cut-off lies just above the undistorted radius of the farthest corner (x 1.01 on the square), or at the
+    # second solution if that is nearer; projections are finite inside and infinite outside
+    for model, p in [(orc.CAM_RADIAL, [250.0, 319.5, 239.5, K1, -1e-2]), (orc.CAM_POLYNOMIAL, PINHOLE + [K1, K2, K3]),
+                     (orc.CAM_POLYNOMIAL_4, PT[:4] + [0.221184, 0.128597, 0.0623079, 0.20419])]:
+        own, inner = orc.cam_cutoff(model, W, H, p)
+        assert np.isfinite(own) and inner == float("inf"), (model, own, inner)
+        fx, fy, cx, cy = base_intrinsics(p, model, orc)
+        corners = np.array([[0, 0], [0, H], [W, 0], [W, H]], np.float32)
+        n = np.stack([np.float32(1.0 / fx) * corners[:, 0] + np.float32(-cx / fx), np.float32(1.0 / fy) * corners[:, 1] + np.float32(-cy / fy)], 1)
+        far = n[np.argmax((n ** 2).sum(1))][None]
+        und = orc.cam_eval(model, W, H, p, "undistort", far)
+        r2 = float((und ** 2).sum())
+        if np.isfinite(r2) and np.abs(orc.cam_eval(model, W, H, p, "distort", und) - far).max() < 1e-4:
+            assert own <= 1.0101 * r2 * 1.001, (model, own, r2)
+        r_in, r_out = np.sqrt(own) * 0.999, np.sqrt(own) * 1.001
+        assert np.all(np.isfinite(orc.cam_eval(model, W, H, p, "project", [[r_in, 0]])))
+        assert np.all(np.isinf(orc.cam_eval(model, W, H, p, "project", [[r_out, 1e-4]])))
+    # the fisheye wrappers apply the inner cut-off to theta = atan(r)
+    own, inner = orc.cam_cutoff(orc.CAM_RADIAL_FISHEYE, W, H, [250.0, 319.5, 239.5, -K1, -K2])
+    assert own == float("inf") and np.isfinite(inner)
+    t_in, t_out = np.tan(min(np.sqrt(inner) * 0.999, 1.5)), np.tan(min(np.sqrt(inner) * 1.001, 1.55))
+    assert np.all(np.isfinite(orc.cam_eval(orc.CAM_RADIAL_FISHEYE, W, H, [250.0, 319.5, 239.5, -K1, -K2], "project", [[t_in, 0]])))
+    if np.sqrt(inner) * 1.001 < 1.55:
+        assert np.all(np.isinf(orc.cam_eval(orc.CAM_RADIAL_FISHEYE, W, H, [250.0, 319.5, 239.5, -K1, -K2], "project", [[t_out, 1e-4]])))
