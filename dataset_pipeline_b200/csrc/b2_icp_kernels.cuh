@@ -177,16 +177,18 @@ struct SearchWork { unsigned int points, box1, box2, cells; };   // per-query wo
 // candidate test; ties on d2 go to the lower original target index so the result does not depend on the visiting order.
 // (d2, index) is ONE 64-bit key, (d2 bits << 32) | index: for non-negative floats the integer order is the float order, so a single
 // unsigned compare implements "d2 < best, or d2 == best and lower index"; the initial key (r2 bits << 32) | 0 rejects d2 == r2 for every
-// index (the radius test is strict). best (float) is kept alongside for the box / face pruning tests.
+// index (the radius test is strict). The pruning tests read the best d2 back from the key's high word (key_d2): no second accumulator.
 #define B2_NN_TEST(T, P)                                                                                              \
   {                                                                                                                   \
     const float ax_ = fsub(q.x, (T).x), ay_ = fsub(q.y, (T).y), az_ = fsub(q.z, (T).z);                                \
     const float d_ = fadd(fadd(fmul(ax_, ax_), fmul(ay_, ay_)), fmul(az_, az_));                                      \
     const unsigned long long k_ = ((unsigned long long)__float_as_uint(d_) << 32) | (unsigned long long)__float_as_uint((T).w); \
-    if (k_ < best_key) { best_key = k_; best = d_; best_pos = (int)(P); }                                              \
+    if (k_ < best_key) { best_key = k_; best_pos = (int)(P); }                                                        \
   }
 
-__device__ __forceinline__ void scan_range(const float4* __restrict__ tgt, unsigned int b, unsigned int e, const float4& q, float& best,
+__device__ __forceinline__ float key_d2(unsigned long long key) { return __uint_as_float((unsigned int)(key >> 32)); }
+
+__device__ __forceinline__ void scan_range(const float4* __restrict__ tgt, unsigned int b, unsigned int e, const float4& q,
                                            int& best_pos, unsigned long long& best_key, SearchWork& wk) {
   wk.points += e - b;
   unsigned int p = b;
@@ -201,7 +203,7 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ tgt, unsig
 }
 // candidates p, p+stride, p+2 stride, p+3 stride (those below e)
 __device__ __forceinline__ void scan_strided4(const float4* __restrict__ tgt, unsigned int p, unsigned int stride, unsigned int e, const float4& q,
-                                              float& best, int& best_pos, unsigned long long& best_key, SearchWork& wk) {
+                                              int& best_pos, unsigned long long& best_key, SearchWork& wk) {
   const unsigned int p1 = p + stride, p2 = p + 2u * stride, p3 = p + 3u * stride;
   const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + min(p1, e - 1)), t2 = __ldg(tgt + min(p2, e - 1)), t3 = __ldg(tgt + min(p3, e - 1));
   wk.points += 1u + (p1 < e) + (p2 < e) + (p3 < e);
@@ -217,25 +219,25 @@ __device__ __forceinline__ void scan_strided4(const float4* __restrict__ tgt, un
 // neighbour — ~10^3 candidates against a mean of ~20 (measured with B2_K3_WORK / tools/k3_work.py). Those lanes are latency
 // bound, so scan_range keeps four candidate loads in flight, and the launch order of the CTAs is longest-first (k_cta_cost).
 __device__ __forceinline__ void scan_cell(const float4* __restrict__ tgt, const Aabb* __restrict__ box1, const Aabb* __restrict__ box2,
-                                          unsigned int b, unsigned int e, const float4& q, float& best, int& best_pos, unsigned long long& best_key,
+                                          unsigned int b, unsigned int e, const float4& q, int& best_pos, unsigned long long& best_key,
                                           SearchWork& wk) {
   ++wk.cells;
-  if (e - b <= 48u) { scan_range(tgt, b, e, q, best, best_pos, best_key, wk); return; }
+  if (e - b <= 48u) { scan_range(tgt, b, e, q, best_pos, best_key, wk); return; }
   const unsigned int last = e - 1;
   if (e - b > 2u * kChunk2) {
     // Very dense cell: a strided sample of 64 candidates first (independent loads), so that `best` is already tight when the
     // chunk boxes are tested. Sampled points are real candidates; re-visiting them later changes nothing.
     const unsigned int stride = (e - b) / 64u;
-    for (unsigned int p = b; p < e; p += 4u * stride) scan_strided4(tgt, p, stride, e, q, best, best_pos, best_key, wk);
+    for (unsigned int p = b; p < e; p += 4u * stride) scan_strided4(tgt, p, stride, e, q, best_pos, best_key, wk);
   }
   for (unsigned int c2 = b / kChunk2; c2 <= last / kChunk2; ++c2) {
     ++wk.box2;
-    if (e - b > 2u * kChunk2 && dist2_box(q.x, q.y, q.z, box2[c2]) > best) continue;
+    if (e - b > 2u * kChunk2 && dist2_box(q.x, q.y, q.z, box2[c2]) > key_d2(best_key)) continue;
     const unsigned int c1b = max(b / kChunk1, c2 * 32u), c1e = min(last / kChunk1, c2 * 32u + 31u);
     for (unsigned int c1 = c1b; c1 <= c1e; ++c1) {
       ++wk.box1;
-      if (dist2_box(q.x, q.y, q.z, box1[c1]) > best) continue;
-      scan_range(tgt, max(b, c1 * kChunk1), min(e, (c1 + 1u) * kChunk1), q, best, best_pos, best_key, wk);
+      if (dist2_box(q.x, q.y, q.z, box1[c1]) > key_d2(best_key)) continue;
+      scan_range(tgt, max(b, c1 * kChunk1), min(e, (c1 + 1u) * kChunk1), q, best_pos, best_key, wk);
     }
   }
 }
@@ -293,7 +295,6 @@ __global__ void __launch_bounds__(128) k_nn_radius1(const float4* __restrict__ s
   // probes per query of a warp run side by side instead of one mostly idle pass per neighbour slot (measured: search 36.8 -> 33.9 ms
   // per outer iteration at config 2).
   const unsigned int mask = (1u << log2size) - 1u;
-  float best = r2;
   int best_pos = -1;
   unsigned long long best_key = (unsigned long long)__float_as_uint(r2) << 32;
   auto probe = [&](int c) {
@@ -308,25 +309,25 @@ __global__ void __launch_bounds__(128) k_nn_radius1(const float4* __restrict__ s
       e = __ldg(reinterpret_cast<const uint4*>(table + s));
       k = ((unsigned long long)e.y << 32) | e.x;
     }
-    if (k == key) scan_cell(tgt, box1, box2, e.z, e.w, q, best, best_pos, best_key, wk);
+    if (k == key) scan_cell(tgt, box1, box2, e.z, e.w, q, best_pos, best_key, wk);
   };
   probe(0);
   unsigned int todo = 0;
 #pragma unroll
   for (int c = 1; c < 8; ++c) {
     const float lb = ((c & 1) ? ex2 : 0.f) + ((c & 2) ? ey2 : 0.f) + ((c & 4) ? ez2 : 0.f);
-    if (!(lb > best)) todo |= 1u << c;
+    if (!(lb > key_d2(best_key))) todo |= 1u << c;
   }
   while (todo) {
     const int c = __ffs(todo) - 1;
     todo &= todo - 1u;
     const float lb = ((c & 1) ? ex2 : 0.f) + ((c & 2) ? ey2 : 0.f) + ((c & 4) ? ez2 : 0.f);
-    if (lb > best) continue;                  // an earlier neighbour tightened the bound
+    if (lb > key_d2(best_key)) continue;      // an earlier neighbour tightened the bound
     probe(c);
   }
   if (STATS) work[j] = make_uint4(wk.points, wk.box1, wk.box2, wk.cells);
   match_pos[j] = best_pos;
-  match_d2[j] = best;
+  match_d2[j] = key_d2(best_key);
   flags[j] = best_pos >= 0 ? 1u : 0u;
 }
 

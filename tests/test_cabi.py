@@ -53,3 +53,21 @@ def test_fails_loudly_without_gpu(L):
     with pytest.raises(B2Error) as ei:
         PointToPlaneICP()
     assert "NO_DEVICE" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_cpp_shims_compile_and_fail_loudly(L, tmp_path):
+    """The header-only C++ shims (reference class shapes over the C ABI) compile as C++14 — the reference's standard — and, without
+    a GPU, surface the library's error as an exception instead of aborting."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    from dataset_pipeline_b200 import _lib
+    exe = str(tmp_path / "shim_check")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["g++", "-std=c++14", "-Wall", "-Werror", "-I", ROOT, "-o", exe, os.path.join(ROOT, "tests", "cpp", "shim_check.cc"),
+           "-L", libdir, "-leth3d_b200", "-Wl,-rpath," + libdir]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
