@@ -58,6 +58,7 @@ struct b2_icp {
   int nsearch = 4;
   cudaStream_t aux[kMaxSearchStreams - 1] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[kMaxSearchStreams - 1] = {};
+  std::vector<cudaEvent_t> cloud_ev;    // per impl cloud: [2i] = phase-1 count copied, [2i+1] = index ready (index / search overlap)
   DevBuf search_tmp[kMaxSearchStreams];
   std::vector<std::unique_ptr<Cloud>> movable;
   std::unique_ptr<Cloud> fixed;         // concatenated global-frame fixed cloud (may be null)
@@ -339,11 +340,6 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   B2_TRY(h->cell_counts.ensure(sizeof(unsigned int) * nc));
   B2_TRY(h->pin_counts.ensure(sizeof(unsigned long long) * (size_t)std::max(nc, 4 * nmov * nmov + 4 * nmov + 4)));
   B2_CUDA(cudaMemsetAsync(h->cell_counts.p, 0, sizeof(unsigned int) * nc, h->stream));
-  for (int i = 0; i < nc; ++i) B2_TRY(index_cloud_phase1(h, impl_cloud(h, i), g, key_bits, i));
-  B2_CUDA(cudaMemcpyAsync(h->pin_counts.p, h->cell_counts.p, sizeof(unsigned int) * nc, cudaMemcpyDeviceToHost, h->stream));
-  B2_CUDA(cudaStreamSynchronize(h->stream));
-  for (int i = 0; i < nc; ++i) { impl_cloud(h, i)->ncells = h->pin_counts.as<unsigned int>()[i]; B2_TRY(index_cloud_phase2(h, impl_cloud(h, i), g)); }
-  B2_CUDA(cudaEventRecord(h->ev[1], h->stream));
 
   // ---- pair scheduling in ik order (icp_point_to_plane.cc:208-309); ownership from the shared planner ----
   h->ndirs = 0;
@@ -361,28 +357,18 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   }
   const float r2 = (float)((double)max_dist * (double)max_dist);
 
-  // ---- K3 + compaction offsets ----
+  // ---- K3 + compaction offsets: one pair-direction on stream st ----
   unsigned long long* counts = h->pin_counts.as<unsigned long long>();
   B2_TRY(h->pin_misc.ensure(sizeof(unsigned int) * 2 * (size_t)std::max(1, h->ndirs)));
   unsigned int* tails = h->pin_misc.as<unsigned int>();
   const bool diag = getenv("B2_K3_WORK") && *getenv("B2_K3_WORK");
   const int nstreams = diag ? 1 : h->nsearch;
-  if (nstreams > 1) {
-    B2_CUDA(cudaEventRecord(h->fork_ev, h->stream));
-    for (int i = 0; i + 1 < nstreams; ++i) B2_CUDA(cudaStreamWaitEvent(h->aux[i], h->fork_ev, 0));
-  }
-  int issued = 0;
-  for (int k = 0; k < h->ndirs; ++k) {
+  for (int k = 0; k < h->ndirs; ++k) { h->dirs[k]->count = 0; tails[2 * k] = tails[2 * k + 1] = 0; }
+  auto issue_search = [&](int k, cudaStream_t st, DevBuf& cub_tmp) -> int {
     Direction* d = h->dirs[k].get();
-    d->count = 0;
-    if (!d->local) continue;
     Cloud* S = impl_cloud(h, d->src); Cloud* T = impl_cloud(h, d->tgt);
     const size_t ns = S->n;
-    tails[2 * k] = tails[2 * k + 1] = 0;
-    if (ns == 0 || T->n == 0) continue;
-    const int si = issued++ % nstreams;
-    cudaStream_t st = si == 0 ? h->stream : h->aux[si - 1];
-    DevBuf& cub_tmp = h->search_tmp[si];
+    if (ns == 0 || T->n == 0) return B2_OK;
     B2_TRY(d->match.ensure(ns * 4)); B2_TRY(d->d2.ensure(ns * 4)); B2_TRY(d->flags.ensure(ns * 4)); B2_TRY(d->offs.ensure(ns * 4));
     cudaEvent_t n0 = nullptr, n1 = nullptr;
     B2_CUDA(cudaEventCreate(&n0)); B2_CUDA(cudaEventCreate(&n1));
@@ -430,6 +416,59 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
     B2_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp, d->flags.as<unsigned int>(), d->offs.as<unsigned int>(), (long long)ns, st));
     B2_CUDA(cudaMemcpyAsync(&tails[2 * k], d->offs.as<unsigned int>() + (ns - 1), 4, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaMemcpyAsync(&tails[2 * k + 1], d->flags.as<unsigned int>() + (ns - 1), 4, cudaMemcpyDeviceToHost, st));
+    return B2_OK;
+  };
+
+  // Index build and search overlap (B2_ICP_OVERLAP=1; OFF by default): the searches of the pairs whose two clouds are indexed run on the
+  // auxiliary streams underneath the index build of the remaining clouds. Per cloud: phase 1 (keys, sort, gather, cell count) is queued
+  // two clouds ahead; the host waits for a cloud's cell count only to size its hash table (phase 2), then releases its pairs.
+  // Measured at config 2 (tools/gpu_job_r01s.sh): parity intact, but index + search 41.1 ms against 40.4 ms for the two separate phases
+  // and a slower step overall (70.3 vs 67.2 ms) — the radix-sort passes and K3 contend for L2 / issue slots instead of complementing
+  // each other, and only three streams remain for the searches. Kept as an A/B switch.
+  static const bool overlap_env = [] { const char* e = getenv("B2_ICP_OVERLAP"); return e && e[0] == '1'; }();
+  const bool overlap = overlap_env && nstreams > 1 && nc >= 3;
+  int issued = 0;
+  if (overlap) {
+    while ((int)h->cloud_ev.size() < 2 * nc) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->cloud_ev.push_back(e); }
+    unsigned int* cnt_host = reinterpret_cast<unsigned int*>(h->pin_counts.p);
+    auto queue_phase1 = [&](int i) -> int {
+      B2_TRY(index_cloud_phase1(h, impl_cloud(h, i), g, key_bits, i));
+      B2_CUDA(cudaMemcpyAsync(cnt_host + i, h->cell_counts.as<unsigned int>() + i, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+      B2_CUDA(cudaEventRecord(h->cloud_ev[2 * i], h->stream));
+      return B2_OK;
+    };
+    for (int i = 0; i < std::min(2, nc); ++i) B2_TRY(queue_phase1(i));
+    for (int i = 0; i < nc; ++i) {
+      B2_CUDA(cudaEventSynchronize(h->cloud_ev[2 * i]));
+      impl_cloud(h, i)->ncells = cnt_host[i];
+      B2_TRY(index_cloud_phase2(h, impl_cloud(h, i), g));
+      B2_CUDA(cudaEventRecord(h->cloud_ev[2 * i + 1], h->stream));
+      for (int k = 0; k < h->ndirs; ++k) {          // the pairs this cloud completes, in ik order
+        Direction* d = h->dirs[k].get();
+        if (!d->local || std::max(d->src, d->tgt) != i) continue;
+        const int si = issued++ % (nstreams - 1);
+        B2_CUDA(cudaStreamWaitEvent(h->aux[si], h->cloud_ev[2 * d->src + 1], 0));
+        B2_CUDA(cudaStreamWaitEvent(h->aux[si], h->cloud_ev[2 * d->tgt + 1], 0));
+        B2_TRY(issue_search(k, h->aux[si], h->search_tmp[si + 1]));
+      }
+      if (i + 2 < nc) B2_TRY(queue_phase1(i + 2));
+    }
+    B2_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  } else {
+    for (int i = 0; i < nc; ++i) B2_TRY(index_cloud_phase1(h, impl_cloud(h, i), g, key_bits, i));
+    B2_CUDA(cudaMemcpyAsync(h->pin_counts.p, h->cell_counts.p, sizeof(unsigned int) * nc, cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < nc; ++i) { impl_cloud(h, i)->ncells = h->pin_counts.as<unsigned int>()[i]; B2_TRY(index_cloud_phase2(h, impl_cloud(h, i), g)); }
+    B2_CUDA(cudaEventRecord(h->ev[1], h->stream));
+    if (nstreams > 1) {
+      B2_CUDA(cudaEventRecord(h->fork_ev, h->stream));
+      for (int i = 0; i + 1 < nstreams; ++i) B2_CUDA(cudaStreamWaitEvent(h->aux[i], h->fork_ev, 0));
+    }
+    for (int k = 0; k < h->ndirs; ++k) {
+      if (!h->dirs[k]->local) continue;
+      const int si = issued++ % nstreams;
+      B2_TRY(issue_search(k, si == 0 ? h->stream : h->aux[si - 1], h->search_tmp[si]));
+    }
   }
   if (nstreams > 1)
     for (int i = 0; i + 1 < nstreams; ++i) { B2_CUDA(cudaEventRecord(h->join_ev[i], h->aux[i])); B2_CUDA(cudaStreamWaitEvent(h->stream, h->join_ev[i], 0)); }
@@ -699,6 +738,7 @@ int b2_icp_destroy(b2_icp* h) {
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < b2_icp::kMaxSearchStreams - 1; ++i) { if (h->aux[i]) cudaStreamDestroy(h->aux[i]); if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]); }
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  for (cudaEvent_t e : h->cloud_ev) if (e) cudaEventDestroy(e);
   for (DevBuf& b : h->search_tmp) b.release();
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
