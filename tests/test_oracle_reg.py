@@ -82,11 +82,11 @@ def _quat_R(q):
                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
 
 
-def _make_problem(oracle, intr_params, image_T_global, point, radius):
+def _make_problem(oracle, intr_params, image_T_global, point, radius, camera_model=4):
     p = oracle.reg_default_params(point_neighbor_count=2, robust_weighting_type=2, robust_weighting_parameter=30.0,
                                   max_initial_image_area_in_pixels=80 * 60, image_scale_count_override=2)
     r = oracle.Registration(p)
-    r.add_intrinsics(40, 30, intr_params)
+    r.add_intrinsics(40, 30, intr_params, camera_model=camera_model)
     yy, xx = np.mgrid[0:30, 0:40]
     r.add_image(0, ((1 * xx + 3 * yy) % 256).astype(np.uint8), None, image_T_global)
     assert r.initialize() == 2
@@ -123,6 +123,51 @@ def test_ref_point_intensity_and_jacobians_fd(oracle):
             r2 = _make_problem(oracle, base_intr, np.concatenate([qo, to]), point, radius)
             I1, _, _ = r2.point_jacobians(0, 0, 0)
             assert abs(d[c] * jP[c] - (I1 - I0)) < 1e-3, ("pose", c)
+
+
+@pytest.mark.parametrize("model,params", [
+    (7, [40, 20, 15]),                                              # SIMPLE_PINHOLE: f cx cy
+    (9, [40, 20, 15, 0.05]),                                        # SIMPLE_RADIAL
+    (8, [40, 20, 15, 0.05, -0.01]),                                 # RADIAL
+    (13, [40, 20, 15, 0.05]),                                       # SIMPLE_RADIAL_FISHEYE
+    (1, [40, 30, 20, 15, 0.04, -0.02, 0.005]),                      # POLYNOMIAL
+    (2, [40, 30, 20, 15, -0.05, 0.02, 1e-3, -2e-3]),                # POLYNOMIAL_TANGENTIAL
+    (10, [40, 30, 20, 15, -0.05, 0.02, 4e-3, -6e-3, -1e-3, 0.05, 1e-3, -1e-3]),   # FULL_OPENCV
+    (0, [40, 30, 20, 15, 0.8]),                                     # FOV
+])
+def test_point_intensity_and_jacobians_fd_further_models(oracle, model, params):
+    """The reference's finite-difference check (test_intrinsics_and_pose_optimizer.cc:101-336) repeated for the other camera models: the
+    Jacobian by the intrinsics in each model's own parameter layout (single focal length first; distortion parameters last), by the pose
+    through each model's ImageDerivativeByWorld. Central differences; the test image is linear in the pixel coordinates."""
+    q = _from_two_vectors(np.array([0.1, 0.3, 0.785]), np.array([0.4375, 0.2458, 0.2724]))
+    q = q / np.linalg.norm(q)
+    t = np.array([0.89763, 0.789346, 0.21398])
+    R = _quat_R(q)
+    qi = np.array([-q[0], -q[1], -q[2], q[3]]); ti = -(R.T @ t)
+    image_T_global = np.concatenate([qi, ti]).astype(np.float32)
+    base = np.array(params, np.float32)
+    nbase = 3 if model in (7, 8, 9, 12, 13) else 4
+    radius = 0.036
+    for local in ((0.1, 0.23, 2.0), (0.4, 0.37, 2.1)):
+        point = (R @ np.array(local) + t).astype(np.float32)
+        r = _make_problem(oracle, base, image_T_global, point, radius, model)
+        I0, jK, jP = r.point_jacobians(0, 0, 0, np_intr=len(params))
+        assert np.abs(jK).max() > 0
+        for c in range(len(params)):
+            h = 0.25 if c < nbase else 2e-3                             # pixels for f / c, small for the distortion coefficients
+            ip, im = base.copy(), base.copy(); ip[c] += h; im[c] -= h
+            I1, _, _ = _make_problem(oracle, ip, image_T_global, point, radius, model).point_jacobians(0, 0, 0, np_intr=len(params))
+            I2, _, _ = _make_problem(oracle, im, image_T_global, point, radius, model).point_jacobians(0, 0, 0, np_intr=len(params))
+            fd = (I1 - I2) / (2 * h)
+            assert abs(jK[c] - fd) <= 2e-2 * max(1.0, abs(fd)) + 2e-3 / h * 1e-3, ("intrinsics", model, c, jK[c], fd)
+        for c in range(6):
+            d = np.zeros(6); d[c] = 0.01 if c < 3 else 0.002
+            qo, to = oracle.se3_exp_left_mul(d, image_T_global[:4], image_T_global[4:])
+            qm, tm = oracle.se3_exp_left_mul(-d, image_T_global[:4], image_T_global[4:])
+            I1, _, _ = _make_problem(oracle, base, np.concatenate([qo, to]), point, radius, model).point_jacobians(0, 0, 0, np_intr=len(params))
+            I2, _, _ = _make_problem(oracle, base, np.concatenate([qm, tm]), point, radius, model).point_jacobians(0, 0, 0, np_intr=len(params))
+            fd = (I1 - I2) / (2 * d[c])
+            assert abs(jP[c] - fd) <= 2e-2 * max(1.0, abs(fd)), ("pose", model, c, jP[c], fd)
 
 
 # ---- test_intrinsics_and_pose_optimizer.cc:338-700 (ComputePointIntensityAndJacobiansForRig) -------------------------------------
