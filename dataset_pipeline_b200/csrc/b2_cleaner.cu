@@ -404,6 +404,10 @@ extern "C" int b2_splat_create(const float* xyz, const float* normals, size_t n,
   const size_t sf = stride_bytes / 4;
   TriBvh bvh; DevBuf d_nrm, d_corners, d_added, d_radius;
   int rc = B2_OK;
+  // magnitude bound of every query of the mesh test (the points and their splat corners: a neighbour distance never exceeds the cloud's
+  // extent <= 2 sqrt(3) amax, a corner lies sqrt(2) radii from its point) -> the pruning margin of the triangle walk
+  const float amax = abs_max(xyz, n, sf);
+  const float corner_bound = amax + 1.5f * std::min(max_splat_size, 3.5f * amax) + 1e-30f;
   KnnHook hook;
   hook.stat_mode = kKnnStatLastD2;
   hook.need_idx = false;
@@ -413,7 +417,7 @@ extern "C" int b2_splat_create(const float* xyz, const float* normals, size_t n,
     if (out_radius) B2_TRY(d_radius.ensure(cnt * 4));
     if (stride_bytes == 12) B2_CUDA(cudaMemcpyAsync(d_nrm.p, normals, cnt * 12, cudaMemcpyHostToDevice, st));
     else B2_CUDA(cudaMemcpy2DAsync(d_nrm.p, 12, normals, stride_bytes, 12, cnt, cudaMemcpyHostToDevice, st));
-    kc_splats<<<bvh_div_up(cnt, 128), 128, 0, st>>>(bvh.view(abs_max(xyz, cnt, sf) * 2.f + 1.f), xyz_dev, d_nrm.as<float>(), cnt, stat_dev, max_splat_size,
+    kc_splats<<<bvh_div_up(cnt, 128), 128, 0, st>>>(bvh.view(corner_bound), xyz_dev, d_nrm.as<float>(), cnt, stat_dev, max_splat_size,
                                                     squared_distance_threshold, d_corners.as<float>(), d_added.as<unsigned char>(),
                                                     out_radius ? d_radius.as<float>() : nullptr);
     B2_CUDA(cudaGetLastError());
