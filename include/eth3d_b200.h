@@ -149,6 +149,7 @@ int b2_find_correspondences(const float* src_xyz, size_t n_src, const float* tgt
  * out_nxyz_curv: n x 4 floats (normal_x, normal_y, normal_z, curvature); NaN where fewer than 3 neighbours
  * (two_pass_normal_3d.h:100-105). *is_dense = 0 if any NaN was written. out_knn_idx (nullable): n x k neighbour
  * indices sorted by (distance, index), -1 padded. out_nxyz_curv may be NULL when out_knn_idx is given (neighbour lists only).
+ * 1 <= k <= 2048 (lists of 56 and more neighbours are searched by one warp per query instead of one thread).
  * ------------------------------------------------------------------------------------------------------------------ */
 int b2_normals_estimate(const float* xyz, size_t n, size_t stride_bytes, int k, const float viewpoint[3],
                         float* out_nxyz_curv, int32_t* out_knn_idx, int* is_dense);
