@@ -160,3 +160,39 @@ def test_splat_geometry():
         if abs(dmax - 4e-4) > 1e-5:
             assert added[i] == (dmax > 4e-4), i
     assert added[:40].all()
+
+
+def test_mesh_distance_properties():
+    """Size-independent properties of the point-mesh distance: zero on the surface (vertices, edge midpoints, centroids), symmetric under
+    a permutation of the faces and of the vertices inside a face's first edge... (the AB-edge branch is the only order-dependent one:
+    checked to a tolerance), and never larger than the distance to any vertex."""
+    verts, faces = _mesh(7)
+    rng = np.random.default_rng(9)
+    V = verts.astype(np.float64)
+    tri = faces[:-1]                                                    # without the degenerate one
+    mids = 0.5 * (V[tri[:, 0]] + V[tri[:, 1]]); cents = (V[tri[:, 0]] + V[tri[:, 1]] + V[tri[:, 2]]) / 3
+    on = np.concatenate([V[:30], mids[:60], cents[:60]]).astype(np.float32)
+    d_on = orc.mesh_squared_distance(on, verts, faces)
+    assert d_on.max() < 1e-10
+    pts = rng.uniform(-1.5, 1.5, (400, 3)).astype(np.float32)
+    d = orc.mesh_squared_distance(pts, verts, faces)
+    d_perm = orc.mesh_squared_distance(pts, verts, faces[rng.permutation(len(faces))])
+    assert np.array_equal(d, d_perm)                                    # the minimum does not depend on the face order
+    d_rot = orc.mesh_squared_distance(pts, verts, np.roll(faces, 1, axis=1))
+    assert np.allclose(d, d_rot, rtol=1e-4, atol=1e-9)                  # rotating a face's vertex order changes the rounding only
+    used = np.unique(faces)
+    d_vert = ((pts[:, None, :].astype(np.float64) - V[None, used, :]) ** 2).sum(-1).min(1)
+    assert (d <= d_vert * (1 + 1e-5) + 1e-9).all()
+
+
+def test_lsor_scale_and_order_properties():
+    """The filter is invariant under a uniform power-of-two scaling of the cloud (every distance scales exactly) and, for clouds without
+    tied distances, under a permutation of the points (the kept SET is the same)."""
+    x = _cloud(11, n=700, outliers=30)
+    keep, rem, dist = orc.lsor_filter(x, 12, 1.6)
+    k2, r2, d2 = orc.lsor_filter(x * np.float32(4.0), 12, 1.6)
+    assert np.array_equal(keep, k2) and np.array_equal(d2, dist * np.float32(4.0))
+    perm = np.random.default_rng(3).permutation(len(x))
+    kp, _, dp = orc.lsor_filter(x[perm], 12, 1.6)
+    assert set(perm[kp].tolist()) == set(keep.tolist())
+    assert np.array_equal(dp, dist[perm])
