@@ -27,7 +27,8 @@ class IcpStats(C.Structure):
                 ("passes", C.c_int32), ("kernel_launches", C.c_int32),
                 ("ms_index", C.c_float), ("ms_search", C.c_float), ("ms_pack", C.c_float), ("ms_inner", C.c_float),
                 ("ms_total", C.c_float), ("ms_accum_kernel_avg", C.c_float), ("ms_search_kernel_avg", C.c_float),
-                ("search_launches", C.c_int32), ("search_algorithmic_bytes", C.c_uint64)]
+                ("search_launches", C.c_int32), ("search_algorithmic_bytes", C.c_uint64),
+                ("ms_index_build", C.c_float), ("reserved0", C.c_int32), ("search_work", C.c_uint64 * 5)]
 
 
 class B2Error(RuntimeError):
@@ -118,6 +119,7 @@ EXPORTS = [
     "b2_reg_set_state",
     "b2_reg_variable_index",
     "b2_splat_create",
+    "b2_trim",
 ]
 
 

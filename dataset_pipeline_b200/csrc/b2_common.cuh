@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "../../include/eth3d_b200.h"
@@ -30,32 +31,47 @@ inline int set_error(int code, const char* fmt, ...) {
   } while (0)
 #define B2_TRY(expr) do { int _rc = (expr); if (_rc != B2_OK) return _rc; } while (0)
 
-// ---- grow-only device buffer, carved from the device's stream-ordered memory pool ---------------------------------
+// ---- grow-only device buffer, carved from a stream-ordered memory pool PRIVATE to this library -------------------------
 // A handle owns GBs of index / direction / record buffers; with plain cudaMalloc / cudaFree a create -> add clouds -> run -> destroy
-// cycle spent more time mapping and unmapping memory than computing. The device's default pool is told to keep what is freed
-// (release threshold = max), so every cycle after the first re-uses the same physical memory. Semantics stay those of
-// cudaMalloc / cudaFree: memory returned by ensure() is usable on any stream at once, release() waits for the device first.
+// cycle spent more time mapping and unmapping memory than computing. The library therefore allocates from its own cudaMemPool_t
+// (one per device, release threshold = max, so every cycle after the first re-uses the same physical memory). The device's DEFAULT
+// pool is left untouched: a host process that also uses cudaMallocAsync (PyTorch's allocator among them) keeps its own policy, and
+// b2_trim() hands everything this library has cached back to the driver. Semantics stay those of cudaMalloc / cudaFree: memory
+// returned by ensure() is usable on any stream at once, release() waits for the device first.
 // B2_POOL=0 restores cudaMalloc / cudaFree (A/B runs, memory debugging tools).
 inline bool pool_enabled() {
   static const bool on = [] { const char* e = std::getenv("B2_POOL"); return !(e && e[0] == '0'); }();
   return on;
 }
-inline void pool_retain(int dev) {
-  static bool done[64] = {};
-  if (dev < 0 || dev >= 64 || done[dev]) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+struct PoolTable { cudaMemPool_t pool[64]; bool made[64]; std::mutex mu; };
+inline PoolTable& pool_table() { static PoolTable t = {}; return t; }
+inline cudaError_t private_pool(int dev, cudaMemPool_t* out) {
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  PoolTable& t = pool_table();
+  std::lock_guard<std::mutex> lock(t.mu);
+  if (!t.made[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaError_t e = cudaMemPoolCreate(&t.pool[dev], &props);
+    if (e != cudaSuccess) return e;
     uint64_t keep = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    cudaMemPoolSetAttribute(t.pool[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+    t.made[dev] = true;
   }
-  done[dev] = true;
+  *out = t.pool[dev];
+  return cudaSuccess;
 }
 inline cudaError_t dev_alloc(void** p, size_t bytes) {
   if (!pool_enabled()) return cudaMalloc(p, bytes);
   int dev = 0;
   cudaGetDevice(&dev);
-  pool_retain(dev);
-  cudaError_t e = cudaMallocAsync(p, bytes, cudaStreamPerThread);
+  cudaMemPool_t pool;
+  cudaError_t e = private_pool(dev, &pool);
+  if (e != cudaSuccess) return e;
+  e = cudaMallocFromPoolAsync(p, bytes, pool, cudaStreamPerThread);
   if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
   return e;
 }
@@ -64,6 +80,13 @@ inline void dev_free(void* p) {
   if (!pool_enabled()) { cudaFree(p); return; }
   cudaDeviceSynchronize();                         // cudaFree's implicit guarantee: nothing in flight still uses the block
   cudaFreeAsync(p, cudaStreamPerThread);
+}
+// Returns the cached (unused) memory of every device's private pool to the driver.
+inline void pool_trim_all() {
+  PoolTable& t = pool_table();
+  std::lock_guard<std::mutex> lock(t.mu);
+  for (int d = 0; d < 64; ++d)
+    if (t.made[d]) { cudaStreamSynchronize(cudaStreamPerThread); cudaMemPoolTrimTo(t.pool[d], 0); }
 }
 
 struct DevBuf {

@@ -1,12 +1,18 @@
-// Host side of Path A behind the C ABI (include/eth3d_b200.h): owns device memory, builds the spatial index,
+// Host side of Path A behind the C ABI (include/eth3d_b200.h): owns device memory, builds the static per-cloud index,
 // schedules the pair-directions, runs the LM loop of PointToPlaneICPImpl::compute on top of the streaming kernels.
 //
 // Reference seams replaced (see the header for the signatures):
 //   PointToPlaneICP::AddPointCloud  /root/reference/src/icp/icp_point_to_plane.cc:109-135
 //   PointToPlaneICP::Run            :137-163        AlignMeshes :169-342
 //   PointToPlaneICPImpl::compute    /root/reference/src/icp/icp_point_to_plane_impl.h:115-293
+//
+// Index design. The reference rebuilds a kd-tree over the transformed target for every pair-direction of every outer iteration
+// (:46-51). Here a cloud is indexed ONCE, in its own frame: cell-sorted copies of its points and a hash table of the occupied cells
+// of a uniform grid of that frame. A pose update moves the grid rigidly with the cloud, so nothing is re-sorted or re-hashed; per
+// outer iteration a cloud costs one streaming pass (K1x: global-frame copies, chunk boxes, AABB). A query reaches the target's
+// grid through the inverse pose; candidate distances are evaluated on the global-frame fp32 coordinates exactly as the reference
+// does, so the results do not depend on the frame the lookup ran in (see the error budget at grid_for_cloud).
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -24,19 +30,35 @@ namespace b2 {
 struct Cloud {
   size_t n = 0;
   bool is_fixed = false;
-  DevBuf local_xyz, local_nrm;          // packed float3 (cloud frame; global frame for the fixed cloud)
+  DevBuf local_xyz, local_nrm;          // packed float3, caller's order (cloud frame; global frame for the fixed cloud)
   float T[16];                          // global_T_cloud, column-major
   float bmin[3], bmax[3];               // AABB of the global-frame cloud (this outer iteration)
-  DevBuf keys_in, keys_out, idx_in, perm, s_xyz, s_nrm, table, box1, box2;
+  // ---- static index in the cloud frame (valid for index_d / index_sigma / index_mtot) ----
+  bool have_lbox = false, indexed = false;
+  float lmin[3], lmax[3];               // AABB in the cloud frame
+  float index_d = 0.f;
+  double index_sigma = 0, index_mtot = 0, margin = 0;
+  GridParams g;
+  DevBuf l_xyz, l_nrm, perm_inv, table, occ; // cell-sorted cloud-frame rows (float4), original index -> sorted position, occupied cells (hash + bitmap)
+  bool has_occ = false;
   int log2size = 0;
   unsigned int ncells = 0;
+  // ---- per outer iteration ----
+  DevBuf s_xyz, s_nrm, box1, box2;      // global-frame rows in the sorted order + chunk boxes
 };
 
 struct Direction {
   int src = 0, tgt = 0;                 // impl cloud indices
   bool local = false;                   // searched / accumulated on this rank
-  DevBuf match, d2, flags, offs, cta_cost;
+  DevBuf key, tile_count, tile_off, order;   // per sorted query: (d2, index) key; per tile: matches, exclusive offsets; launch order
+  int order_src = -1, order_tgt = -1, order_age = 0;
+  unsigned int order_tiles = 0;
   unsigned long long count = 0, rec_begin = 0;
+};
+
+struct Scoped {                         // temporaries of a call: released on every exit path
+  DevBuf b;
+  ~Scoped() { b.release(); }
 };
 
 static inline Mat4 mat4_of(const float T[16]) { Mat4 m; std::memcpy(m.m, T, sizeof(m.m)); return m; }
@@ -49,7 +71,8 @@ using namespace b2;
 struct b2_icp {
   b2_icp_config cfg;
   int device = 0, sms = 148;
-  bool lpt_order = true;                // K3 CTAs issued longest-first (B2_K3_ORDER=grid disables, for A/B runs)
+  bool lpt_order = true;                // K3 tiles issued longest-first (B2_K3_ORDER=grid disables, for A/B runs)
+  bool work_stats = false;              // B2_K3_WORK=1: the diagnostic K3 variant that counts its work
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   // K3 runs the pair-directions of an iteration round-robin over `nsearch` streams (the handle's + auxiliaries) so that one
@@ -58,15 +81,15 @@ struct b2_icp {
   int nsearch = 4;
   cudaStream_t aux[kMaxSearchStreams - 1] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[kMaxSearchStreams - 1] = {};
-  std::vector<cudaEvent_t> cloud_ev;    // per impl cloud: [2i] = phase-1 count copied, [2i+1] = index ready (index / search overlap)
   DevBuf search_tmp[kMaxSearchStreams];
   std::vector<std::unique_ptr<Cloud>> movable;
   std::unique_ptr<Cloud> fixed;         // concatenated global-frame fixed cloud (may be null)
   std::vector<std::unique_ptr<Direction>> dirs;   // pool, reused across outer iterations
   int ndirs = 0;
   // scratch
-  DevBuf bbox_partial, cub_tmp, cell_counts, rec_a, rec_b, rec_c, segs_dev, poses_dev, partials, xpartials, segsum, xsegsum, eq_dev, scatter_m, scatter_d;
+  DevBuf bbox_partial, cub_tmp, cell_counts, rec_a, rec_b, rec_c, segs_dev, poses_dev, partials, xpartials, segsum, xsegsum, eq_dev, scatter_m, scatter_d, work_dev, totals_dev;
   PinnedBuf pin_bbox, pin_counts, pin_eq, pin_poses, pin_segs, pin_misc;
+  unsigned int tma_attr_mask = 0;       // K5 instantiations whose dynamic shared memory opt-in has been set on THIS handle's device
   // last outer iteration
   b2_icp_stats stats;
   std::vector<int32_t> tries;
@@ -78,6 +101,8 @@ struct b2_icp {
   int grid_acc = 0;
   unsigned long long per_cta = 0;
   int launches = 0;
+  float ms_index_build = 0.f;
+  unsigned long long last_init_key = 0; // "no match" key of the last search (r2 bits << 32)
   int prev_inner_iterations = 0;        // LM iterations of the previous outer iteration (0 = none yet): gates the speculative second try
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> acc_events, nn_events;
@@ -94,6 +119,7 @@ static int impl_index_of_movable(const b2_icp* h, int m) { return h->fixed ? m +
 
 static int upload_cloud(b2_icp* h, Cloud* c, const float* xyz, const float* nrm, size_t n, size_t stride_bytes, bool from_device) {
   c->n = n;
+  c->have_lbox = c->indexed = false;
   B2_TRY(c->local_xyz.ensure(std::max<size_t>(n, 1) * 12));
   B2_TRY(c->local_nrm.ensure(std::max<size_t>(n, 1) * 12));
   if (n == 0) return B2_OK;
@@ -111,45 +137,187 @@ static int upload_cloud(b2_icp* h, Cloud* c, const float* xyz, const float* nrm,
   return B2_OK;
 }
 
-// Sort one cloud into the grid and build its occupied-cell table (K1b, K1c, K2). Two-phase so that all clouds share
-// one host sync for the cell counts.
-static int index_cloud_phase1(b2_icp* h, Cloud* c, const GridParams& g, int key_bits, int slot) {
-  const size_t n = c->n;
-  if (n == 0) { c->ncells = 0; return B2_OK; }
-  B2_TRY(c->keys_in.ensure(n * 8)); B2_TRY(c->keys_out.ensure(n * 8));
-  B2_TRY(c->idx_in.ensure(n * 4)); B2_TRY(c->perm.ensure(n * 4));
-  B2_TRY(c->s_xyz.ensure(n * 16)); B2_TRY(c->s_nrm.ensure(n * 16));
-  const Mat4 T = mat4_of(c->T);
-  k_keys<<<div_up(n, 256), 256, 0, h->stream>>>(c->local_xyz.as<float>(), n, T, g, c->keys_in.as<unsigned long long>(),
-                                                c->idx_in.as<unsigned int>());
-  ++h->launches;
-  size_t tmp = 0;
-  B2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->keys_in.as<unsigned long long>(), c->keys_out.as<unsigned long long>(),
-                                          c->idx_in.as<unsigned int>(), c->perm.as<unsigned int>(), (long long)n, 0, key_bits, h->stream));
-  B2_TRY(h->cub_tmp.ensure(tmp));
-  B2_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, c->keys_in.as<unsigned long long>(), c->keys_out.as<unsigned long long>(),
-                                          c->idx_in.as<unsigned int>(), c->perm.as<unsigned int>(), (long long)n, 0, key_bits, h->stream));
-  k_apply<<<div_up(n, 256), 256, 0, h->stream>>>(c->local_xyz.as<float>(), c->local_nrm.as<float>(), n, T, c->perm.as<unsigned int>(),
-                                                 c->s_xyz.as<float4>(), c->s_nrm.as<float4>());
-  k_count_cells<<<div_up(n, 256), 256, 0, h->stream>>>(c->keys_out.as<unsigned long long>(), n, h->cell_counts.as<unsigned int>() + slot, 3 * g.fbits);
-  const unsigned int nb1 = div_up(n, kChunk1), nb2 = div_up(nb1, 32);
-  B2_TRY(c->box1.ensure(sizeof(Aabb) * nb1)); B2_TRY(c->box2.ensure(sizeof(Aabb) * nb2));
-  k_chunk_boxes1<<<div_up((size_t)nb1 * 32, 256), 256, 0, h->stream>>>(c->s_xyz.as<float4>(), n, c->box1.as<Aabb>(), nb1);
-  k_chunk_boxes2<<<div_up((size_t)nb2 * 32, 256), 256, 0, h->stream>>>(c->box1.as<Aabb>(), nb1, c->box2.as<Aabb>(), nb2);
-  h->launches += 4;
+// ---- the linear part of a pose -------------------------------------------------------------------------------------
+// sigma >= || A^-1 ||_2 for the 3x3 linear part A of a pose: cloud-frame distances are at most sigma times the global ones.
+// Rigid poses give 1 + O(1e-7); anything invertible is accepted (a similarity or shear only enlarges the cells).
+static bool invert3(const double A[9], double Ai[9]) {      // row-major
+  const double c0 = A[4] * A[8] - A[5] * A[7], c1 = A[5] * A[6] - A[3] * A[8], c2 = A[3] * A[7] - A[4] * A[6];
+  const double det = A[0] * c0 + A[1] * c1 + A[2] * c2;
+  if (!(std::fabs(det) > 1e-300) || !std::isfinite(det)) return false;
+  const double id = 1.0 / det;
+  Ai[0] = c0 * id; Ai[1] = (A[2] * A[7] - A[1] * A[8]) * id; Ai[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+  Ai[3] = c1 * id; Ai[4] = (A[0] * A[8] - A[2] * A[6]) * id; Ai[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+  Ai[6] = c2 * id; Ai[7] = (A[1] * A[6] - A[0] * A[7]) * id; Ai[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+  return true;
+}
+static void linear_part(const float T[16], double A[9]) { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) A[3 * r + c] = T[r + 4 * c]; }
+static int pose_sigma(const float T[16], double* sigma) {
+  double A[9], Ai[9];
+  linear_part(T, A);
+  if (!invert3(A, Ai)) return set_error(B2_ERR_ARG, "pose is not invertible");
+  double eta = 0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double e = -(i == j ? 1.0 : 0.0);
+      for (int k = 0; k < 3; ++k) e += A[3 * k + i] * A[3 * k + j];
+      eta += e * e;
+    }
+  eta = std::sqrt(eta);
+  if (eta < 0.25) *sigma = 1.0 / std::sqrt(1.0 - eta);            // sigma_min(A)^2 >= 1 - ||A^T A - I||
+  else { double f = 0; for (double v : Ai) f += v * v; *sigma = std::sqrt(f); }   // || . ||_2 <= || . ||_F
   return B2_OK;
 }
-static int index_cloud_phase2(b2_icp* h, Cloud* c, const GridParams& g) {
+// Largest coordinate magnitude anything on the lookup path can take: global coordinates of every cloud (bounded from its pose
+// and its cloud-frame AABB) and the cloud-frame coordinates themselves.
+static double magnitude_bound(b2_icp* h) {
+  double m = 0;
+  const int nc = num_impl_clouds(h);
+  for (int i = 0; i < nc; ++i) {
+    const Cloud* c = impl_cloud(h, i);
+    if (c->n == 0) continue;
+    double la[3];
+    for (int k = 0; k < 3; ++k) { la[k] = std::max(std::fabs((double)c->lmin[k]), std::fabs((double)c->lmax[k])); m = std::max(m, la[k]); }
+    for (int a = 0; a < 3; ++a) {
+      double gsum = std::fabs((double)c->T[12 + a]);
+      for (int k = 0; k < 3; ++k) gsum += std::fabs((double)c->T[a + 4 * k]) * la[k];
+      m = std::max(m, gsum);
+    }
+  }
+  return m;
+}
+
+// Grid of one cloud in its own frame.
+// Error budget of the lookup (why every target with fp32 d2 < r2 lies in the 2x2x2 block that k_nn_tiles searches):
+//   * d2 < r2 in the reference's fp32 arithmetic  =>  true distance of the fp32 global coordinates D <= d (1 + 2^-21);
+//   * the target's global row is fl(T l): |rounding| <= 3 * 2^-24 * M per coordinate (M = magnitude_bound);
+//   * the query is mapped by fl32(T^-1) with three FMAs: <= 7 * 2^-24 * M per coordinate, and the cell fraction is formed in
+//     fp32: <= 4 * 2^-24 * M;
+//   * cloud-frame distance <= sigma * global distance (pose_sigma).
+// Hence |cloud-frame offset per axis| <= d sigma + 32 * 2^-24 * M. margin = 64 * 2^-24 * M, the index is built for 2 M and
+// sigma (1 + 1e-4) and rebuilt should an iteration exceed either. cell = 2 (d sigma + margin) (1 + 1e-4): from a query's
+// (computed) half of its cell, the far faces of the 2x2x2 block on that side are >= cell / 2 away.
+static int grid_for_cloud(Cloud* c, float max_dist, double sigma, double mtot, int* key_bits) {
+  for (int d = 0; d < 3; ++d)
+    if (!std::isfinite(c->lmin[d]) || !std::isfinite(c->lmax[d]))
+      return set_error(B2_ERR_ARG, "non-finite point coordinates (clouds must be dense, as the reference's is_dense path assumes)");
+  c->index_sigma = sigma * (1.0 + 1e-4);
+  c->index_mtot = 2.0 * mtot;
+  c->margin = 64.0 * std::ldexp(1.0, -24) * c->index_mtot;
+  double cell = 2.0 * ((double)max_dist * c->index_sigma + c->margin) * 1.0001;
+  if (!(cell > 0.0)) cell = 1e-30;
+  GridParams& g = c->g;
+  const double ext = std::max({(double)c->lmax[0] - c->lmin[0], (double)c->lmax[1] - c->lmin[1], (double)c->lmax[2] - c->lmin[2]});
+  cell = std::max(cell, ext / 2097000.0);    // keep every axis below 2^21 cells
+  g.ox = c->lmin[0]; g.oy = c->lmin[1]; g.oz = c->lmin[2];
+  auto dims = [&] {
+    g.inv = 1.0 / cell;
+    g.nx = cell_of(c->lmax[0], g.ox, g.inv) + 1; g.ny = cell_of(c->lmax[1], g.oy, g.inv) + 1; g.nz = cell_of(c->lmax[2], g.oz, g.inv) + 1;
+  };
+  dims();
+  // keep the cell key below 2^47 so that (key << 3*kMinFineBits) fits 63 bits: enlarge the cells of enormous sparse clouds
+  while ((double)g.nx * (double)g.ny * (double)g.nz >= 140737488355328.0) { cell *= 2.0; dims(); }
+  g.cell = 1.0 / g.inv;
+  const unsigned long long maxkey = cell_key(g, g.nx - 1, g.ny - 1, g.nz - 1);
+  int bits = 1;
+  while (bits < 64 && (maxkey >> bits) != 0ull) ++bits;
+  // in-cell Morton resolution: as fine as fits 40 key bits, never below 5 bits per axis (dense cells are pruned through chunk boxes
+  // over this order)
+  g.fbits = std::max(kMinFineBits, std::min(kMaxFineBits, (40 - bits) / 3));
+  *key_bits = bits + 3 * g.fbits;
+  return B2_OK;
+}
+
+// One-time index of a cloud (K1, K2): AABB in the cloud frame -> grid -> keys -> radix sort -> cell-sorted rows, inverse
+// permutation, occupied-cell table. The sort is the only library call (cub::DeviceRadixSort) and it is off the per-iteration path.
+static int cloud_local_box(b2_icp* h, Cloud* c) {
+  if (c->have_lbox) return B2_OK;
+  for (int d = 0; d < 3; ++d) { c->lmin[d] = INFINITY; c->lmax[d] = -INFINITY; }
+  if (c->n) {
+    const int blocks = h->sms * 2;
+    B2_TRY(h->bbox_partial.ensure((size_t)blocks * 6 * sizeof(float)));
+    B2_TRY(h->pin_bbox.ensure((size_t)blocks * 6 * sizeof(float)));
+    const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    k_bbox<<<blocks, 256, 0, h->stream>>>(c->local_xyz.as<float>(), c->n, mat4_of(I), h->bbox_partial.as<float>());
+    ++h->launches;
+    B2_CUDA(cudaMemcpyAsync(h->pin_bbox.p, h->bbox_partial.p, (size_t)blocks * 6 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    const float* p = h->pin_bbox.as<float>();
+    for (int b = 0; b < blocks; ++b)
+      for (int d = 0; d < 3; ++d) { c->lmin[d] = std::min(c->lmin[d], p[b * 6 + d]); c->lmax[d] = std::max(c->lmax[d], p[b * 6 + 3 + d]); }
+  } else {
+    for (int d = 0; d < 3; ++d) c->lmin[d] = c->lmax[d] = 0.f;
+  }
+  c->have_lbox = true;
+  return B2_OK;
+}
+
+static int build_index(b2_icp* h, Cloud* c, float max_dist, double sigma, double mtot) {
   const size_t n = c->n;
-  if (n == 0) return B2_OK;
+  c->indexed = false;
+  if (n == 0) { c->ncells = 0; c->index_d = max_dist; c->index_sigma = sigma * (1.0 + 1e-4); c->index_mtot = 2.0 * mtot; c->indexed = true; return B2_OK; }
+  int key_bits = 0;
+  B2_TRY(grid_for_cloud(c, max_dist, sigma, mtot, &key_bits));
+  const GridParams& g = c->g;
+  Scoped keys_in, keys_out, idx_in, perm;
+  B2_TRY(keys_in.b.ensure(n * 8 + 16)); B2_TRY(keys_out.b.ensure(n * 8 + 16)); B2_TRY(idx_in.b.ensure(n * 4)); B2_TRY(perm.b.ensure(n * 4));
+  B2_TRY(c->l_xyz.ensure(n * 16)); B2_TRY(c->l_nrm.ensure(n * 16)); B2_TRY(c->perm_inv.ensure(n * 4));
+  B2_TRY(c->s_xyz.ensure(n * 16)); B2_TRY(c->s_nrm.ensure(n * 16));
+  k_keys<<<div_up(n, 256), 256, 0, h->stream>>>(c->local_xyz.as<float>(), n, g, keys_in.b.as<unsigned long long>(), idx_in.b.as<unsigned int>());
+  size_t tmp = 0;
+  B2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys_in.b.as<unsigned long long>(), keys_out.b.as<unsigned long long>(),
+                                          idx_in.b.as<unsigned int>(), perm.b.as<unsigned int>(), (long long)n, 0, key_bits, h->stream));
+  B2_TRY(h->cub_tmp.ensure(tmp));
+  B2_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, keys_in.b.as<unsigned long long>(), keys_out.b.as<unsigned long long>(),
+                                          idx_in.b.as<unsigned int>(), perm.b.as<unsigned int>(), (long long)n, 0, key_bits, h->stream));
+  k_gather_sorted<<<div_up(n, 256), 256, 0, h->stream>>>(c->local_xyz.as<float>(), c->local_nrm.as<float>(), n, perm.b.as<unsigned int>(),
+                                                         c->l_xyz.as<float4>(), c->l_nrm.as<float4>(), c->perm_inv.as<unsigned int>());
+  B2_TRY(h->cell_counts.ensure(sizeof(unsigned int)));
+  B2_TRY(h->pin_counts.ensure(sizeof(unsigned long long) * 8));
+  B2_CUDA(cudaMemsetAsync(h->cell_counts.p, 0, sizeof(unsigned int), h->stream));
+  k_count_cells<<<div_up(n, 256), 256, 0, h->stream>>>(keys_out.b.as<unsigned long long>(), n, h->cell_counts.as<unsigned int>(), 3 * g.fbits);
+  B2_CUDA(cudaMemcpyAsync(h->pin_counts.p, h->cell_counts.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  c->ncells = h->pin_counts.as<unsigned int>()[0];
   int lg = 4;
   while ((1ull << lg) < 2ull * c->ncells) ++lg;
   c->log2size = lg;
   B2_TRY(c->table.ensure(sizeof(HashEntry) << lg));
   B2_CUDA(cudaMemsetAsync(c->table.p, 0xFF, sizeof(HashEntry) << lg, h->stream));
-  k_hash_insert<<<div_up(n, 256), 256, 0, h->stream>>>(c->keys_out.as<unsigned long long>(), n, c->table.as<HashEntry>(), lg, 3 * g.fbits);
-  k_hash_ends<<<div_up(n, 256), 256, 0, h->stream>>>(c->keys_out.as<unsigned long long>(), n, c->table.as<HashEntry>(), lg, 3 * g.fbits);
-  h->launches += 2;
+  // one occupancy bit per grid cell while the grid is small enough (2^31 cells = 256 MB; a 10 x 8 x 3 m room at 2 cm is 4 MB)
+  const double cells_total = (double)g.nx * (double)g.ny * (double)g.nz;
+  c->has_occ = cells_total <= 2147483648.0;
+  if (c->has_occ) {
+    const size_t words = (size_t)(cells_total / 32.0) + 2;
+    B2_TRY(c->occ.ensure(words * 4));
+    B2_CUDA(cudaMemsetAsync(c->occ.p, 0, words * 4, h->stream));
+  }
+  k_hash_cells<<<div_up(n, 256), 256, 0, h->stream>>>(keys_out.b.as<unsigned long long>(), n, c->table.as<HashEntry>(), lg, 3 * g.fbits,
+                                                      c->has_occ ? c->occ.as<unsigned int>() : nullptr);
+  h->launches += 4;
+  B2_CUDA(cudaStreamSynchronize(h->stream));     // the temporaries go out of scope
+  c->index_d = max_dist;
+  c->indexed = true;
+  return B2_OK;
+}
+
+// This iteration's map into a target's grid: position relative to the grid origin = T^-1 (q - t) - o, as one fp32 3x4.
+static int search_grid(const Cloud* c, SearchGrid* sg) {
+  double A[9], Ai[9];
+  linear_part(c->T, A);
+  if (!invert3(A, Ai)) return set_error(B2_ERR_ARG, "pose is not invertible");
+  const double t[3] = {c->T[12], c->T[13], c->T[14]}, o[3] = {c->g.ox, c->g.oy, c->g.oz};
+  for (int r = 0; r < 3; ++r) {
+    for (int k = 0; k < 3; ++k) sg->m[4 * r + k] = (float)Ai[3 * r + k];
+    sg->m[4 * r + 3] = (float)(-(Ai[3 * r] * t[0] + Ai[3 * r + 1] * t[1] + Ai[3 * r + 2] * t[2]) - o[r]);
+  }
+  sg->inv = (float)c->g.inv; sg->cell = (float)c->g.cell;
+  sg->inv_sigma = (float)((1.0 - 1e-6) / c->index_sigma);
+  sg->margin = (float)c->margin;
+  sg->nx = c->g.nx; sg->ny = c->g.ny; sg->nz = c->g.nz;
+  sg->sy = c->g.nx; sg->sz = (long long)c->g.nx * (long long)c->g.ny;
+  sg->log2size = c->log2size;
+  sg->one = 1.0f;
+  sg->occ = c->has_occ ? c->occ.as<unsigned int>() : nullptr;
   return B2_OK;
 }
 
@@ -164,54 +332,16 @@ static Direction* next_direction(b2_icp* h) {
   return h->dirs[h->ndirs++].get();
 }
 
-static int compute_grid(b2_icp* h, float max_dist, GridParams* g, int* key_bits) {
-  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-  const int nc = num_impl_clouds(h);
-  for (int i = 0; i < nc; ++i) {
-    const Cloud* c = impl_cloud(h, i);
-    if (c->n == 0) continue;
-    for (int d = 0; d < 3; ++d) { mn[d] = std::min(mn[d], c->bmin[d]); mx[d] = std::max(mx[d], c->bmax[d]); }
-  }
-  if (!(mn[0] <= mx[0])) { mn[0] = mn[1] = mn[2] = 0.f; mx[0] = mx[1] = mx[2] = 0.f; }
-  for (int d = 0; d < 3; ++d)
-    if (!std::isfinite(mn[d]) || !std::isfinite(mx[d]))
-      return set_error(B2_ERR_ARG, "non-finite point coordinates (clouds must be dense, as the reference's is_dense path assumes)");
-  // cell >= 2d*(1+1e-4): any target with fp32 d2 < fl(d*d) lies in the 2x2x2 block of cells on the query's side of its cell
-  // (k_nn_radius1): the face on the far side is >= cell/2 > d away.
-  double cell = (double)max_dist * 2.0002;
-  if (!(cell > 0.0)) cell = 1e-30;
-  const double ext = std::max({(double)mx[0] - mn[0], (double)mx[1] - mn[1], (double)mx[2] - mn[2]});
-  cell = std::max(cell, ext / 2097000.0);    // keep every axis below 2^21 cells
-  g->ox = mn[0]; g->oy = mn[1]; g->oz = mn[2];
-  g->inv = 1.0 / cell;
-  g->nx = cell_of(mx[0], g->ox, g->inv) + 1;
-  g->ny = cell_of(mx[1], g->oy, g->inv) + 1;
-  g->nz = cell_of(mx[2], g->oz, g->inv) + 1;
-  // keep the cell key below 2^47 so that (key << 3*kMinFineBits) fits 63 bits: enlarge the cells of enormous sparse scenes
-  while ((double)g->nx * (double)g->ny * (double)g->nz >= 140737488355328.0) {
-    cell *= 2.0; g->inv = 1.0 / cell;
-    g->nx = cell_of(mx[0], g->ox, g->inv) + 1; g->ny = cell_of(mx[1], g->oy, g->inv) + 1; g->nz = cell_of(mx[2], g->oz, g->inv) + 1;
-  }
-  g->cell = 1.0 / g->inv;
-  const unsigned long long maxkey = cell_key(*g, g->nx - 1, g->ny - 1, g->nz - 1);
-  int bits = 1;
-  while (bits < 64 && (maxkey >> bits) != 0ull) ++bits;
-  // in-cell Morton resolution: as fine as fits 40 key bits (5 radix passes of 8 bits; measured on the bench scene, finer codes cost
-  // a sixth / seventh pass and no longer shorten the search), never below 5 bits per axis
-  g->fbits = std::max(kMinFineBits, std::min(kMaxFineBits, (40 - bits) / 3));
-  *key_bits = bits + 3 * g->fbits;
-  return B2_OK;
-}
-
 // One streaming pass (K5 + K6) at the given increments; returns [H|b|cost|extras|costs of the speculative trials] in h->pin_eq (host)
 // after the optional cross-rank reduction. trials[0] is the state the normal equations (with_h) and the cost are evaluated at;
 // trials[1..] (at most kMaxExtraTrials) are further LM trial states whose costs ride along on the same read of the records.
 template <bool WITH_H, int NX>
 static int launch_accumulate_tma(b2_icp* h, int nseg, int nc) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the > 48 KB dynamic shared memory opt-in is per device: tracked per handle (a handle is bound to one device)
+  const unsigned int bit = 1u << ((WITH_H ? 4 : 0) + NX);
+  if (!(h->tma_attr_mask & bit)) {
     B2_CUDA(cudaFuncSetAttribute(k_accumulate_tma<WITH_H, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
-    attr_set = true;
+    h->tma_attr_mask |= bit;
   }
   k_accumulate_tma<WITH_H, NX><<<h->grid_acc, kAccThreads, kTmaSmemBytes, h->stream>>>(
       h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>(), h->segs_dev.as<Segment>(), nseg, h->poses_dev.as<CloudPose>(), nc,
@@ -299,10 +429,36 @@ static int run_pass(b2_icp* h, const std::vector<std::vector<Pose>>& trials, boo
 
 static float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
 
+// Index maintenance at the start of an outer iteration: (re)build the indexes the current radius / poses are not covered by.
+static int ensure_indexes(b2_icp* h, float max_dist) {
+  const int nc = num_impl_clouds(h);
+  for (int i = 0; i < nc; ++i) B2_TRY(cloud_local_box(h, impl_cloud(h, i)));
+  const double mtot = magnitude_bound(h);
+  if (!std::isfinite(mtot)) return set_error(B2_ERR_ARG, "non-finite pose or point coordinates");
+  bool built = false;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  for (int i = 0; i < nc; ++i) {
+    Cloud* c = impl_cloud(h, i);
+    double sigma = 1.0;
+    B2_TRY(pose_sigma(c->T, &sigma));
+    if (c->indexed && c->index_d == max_dist && sigma <= c->index_sigma && mtot <= c->index_mtot) continue;
+    if (!built) { B2_CUDA(cudaEventCreate(&e0)); B2_CUDA(cudaEventCreate(&e1)); B2_CUDA(cudaEventRecord(e0, h->stream)); built = true; }
+    B2_TRY(build_index(h, c, max_dist, sigma, mtot));
+  }
+  if (built) {
+    B2_CUDA(cudaEventRecord(e1, h->stream));
+    B2_CUDA(cudaEventSynchronize(e1));
+    h->ms_index_build = elapsed(e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+  return B2_OK;
+}
+
 // AlignMeshes (icp_point_to_plane.cc:169-342).
 static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* converged, bool search_only = false, bool gate = true) {
   h->launches = 0;
   std::memset(&h->stats, 0, sizeof(h->stats));
+  h->ms_index_build = 0.f;
   h->tries.clear();
   for (auto& pr : h->acc_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   h->acc_events.clear();
@@ -311,35 +467,34 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   const int nc = num_impl_clouds(h);
   const int nmov = (int)h->movable.size();
   const int nv = 6 * (nc - 1);
+  B2_TRY(ensure_indexes(h, max_dist));
   B2_CUDA(cudaEventRecord(h->ev[0], h->stream));
 
-  // ---- K1a: bounding boxes of the global-frame clouds ----
-  const int bb_blocks = h->sms * 2;
-  B2_TRY(h->bbox_partial.ensure((size_t)nc * bb_blocks * 6 * sizeof(float)));
-  B2_TRY(h->pin_bbox.ensure((size_t)nc * bb_blocks * 6 * sizeof(float)));
+  // ---- K1x: global-frame rows, chunk boxes and bounding boxes of all clouds (one stream per cloud, one sync for all) ----
+  const int xf_blocks = h->sms * 4;
+  B2_TRY(h->bbox_partial.ensure((size_t)nc * xf_blocks * 6 * sizeof(float)));
+  B2_TRY(h->pin_bbox.ensure((size_t)nc * xf_blocks * 6 * sizeof(float)));
   for (int i = 0; i < nc; ++i) {
     Cloud* c = impl_cloud(h, i);
     if (c->n == 0) continue;
-    k_bbox<<<bb_blocks, 256, 0, h->stream>>>(c->local_xyz.as<float>(), c->n, mat4_of(c->T), h->bbox_partial.as<float>() + (size_t)i * bb_blocks * 6);
-    ++h->launches;
+    const unsigned int nb1 = div_up(c->n, kChunk1), nb2 = div_up(nb1, 32);
+    B2_TRY(c->box1.ensure(sizeof(Aabb) * nb1)); B2_TRY(c->box2.ensure(sizeof(Aabb) * nb2));
+    k_xform_sorted<<<xf_blocks, 256, 0, h->stream>>>(c->l_xyz.as<float4>(), c->l_nrm.as<float4>(), c->n, mat4_of(c->T), c->s_xyz.as<float4>(),
+                                                     c->s_nrm.as<float4>(), c->box1.as<Aabb>(), h->bbox_partial.as<float>() + (size_t)i * xf_blocks * 6);
+    k_chunk_boxes2<<<div_up((size_t)nb2 * 32, 256), 256, 0, h->stream>>>(c->box1.as<Aabb>(), nb1, c->box2.as<Aabb>(), nb2);
+    h->launches += 2;
   }
-  B2_CUDA(cudaMemcpyAsync(h->pin_bbox.p, h->bbox_partial.p, (size_t)nc * bb_blocks * 6 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaMemcpyAsync(h->pin_bbox.p, h->bbox_partial.p, (size_t)nc * xf_blocks * 6 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   B2_CUDA(cudaStreamSynchronize(h->stream));
   for (int i = 0; i < nc; ++i) {
     Cloud* c = impl_cloud(h, i);
     for (int d = 0; d < 3; ++d) { c->bmin[d] = INFINITY; c->bmax[d] = -INFINITY; }
     if (c->n == 0) continue;
-    const float* p = h->pin_bbox.as<float>() + (size_t)i * bb_blocks * 6;
-    for (int b = 0; b < bb_blocks; ++b)
+    const float* p = h->pin_bbox.as<float>() + (size_t)i * xf_blocks * 6;
+    for (int b = 0; b < xf_blocks; ++b)
       for (int d = 0; d < 3; ++d) { c->bmin[d] = std::min(c->bmin[d], p[b * 6 + d]); c->bmax[d] = std::max(c->bmax[d], p[b * 6 + 3 + d]); }
   }
-
-  // ---- K1b/K1c/K2: common grid, cell sort, occupied-cell tables ----
-  GridParams g; int key_bits = 0;
-  B2_TRY(compute_grid(h, max_dist, &g, &key_bits));
-  B2_TRY(h->cell_counts.ensure(sizeof(unsigned int) * nc));
-  B2_TRY(h->pin_counts.ensure(sizeof(unsigned long long) * (size_t)std::max(nc, 4 * nmov * nmov + 4 * nmov + 4)));
-  B2_CUDA(cudaMemsetAsync(h->cell_counts.p, 0, sizeof(unsigned int) * nc, h->stream));
+  B2_CUDA(cudaEventRecord(h->ev[1], h->stream));
 
   // ---- pair scheduling in ik order (icp_point_to_plane.cc:208-309); ownership from the shared planner ----
   h->ndirs = 0;
@@ -356,125 +511,79 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
     }
   }
   const float r2 = (float)((double)max_dist * (double)max_dist);
+  unsigned int r2_bits; std::memcpy(&r2_bits, &r2, 4);
+  const unsigned long long init_key = (unsigned long long)r2_bits << 32;
+  h->last_init_key = init_key;
 
-  // ---- K3 + compaction offsets: one pair-direction on stream st ----
-  unsigned long long* counts = h->pin_counts.as<unsigned long long>();
-  B2_TRY(h->pin_misc.ensure(sizeof(unsigned int) * 2 * (size_t)std::max(1, h->ndirs)));
-  unsigned int* tails = h->pin_misc.as<unsigned int>();
-  const bool diag = getenv("B2_K3_WORK") && *getenv("B2_K3_WORK");
-  const int nstreams = diag ? 1 : h->nsearch;
-  for (int k = 0; k < h->ndirs; ++k) { h->dirs[k]->count = 0; tails[2 * k] = tails[2 * k + 1] = 0; }
+  // ---- K3 + tile offsets: one pair-direction on stream st ----
+  B2_TRY(h->pin_misc.ensure(sizeof(unsigned int) * (size_t)std::max(1, h->ndirs)));
+  B2_TRY(h->totals_dev.ensure(sizeof(unsigned int) * (size_t)std::max(1, h->ndirs)));
+  unsigned int* totals = h->pin_misc.as<unsigned int>();
+  if (h->work_stats) { B2_TRY(h->work_dev.ensure(5 * sizeof(unsigned long long))); B2_CUDA(cudaMemsetAsync(h->work_dev.p, 0, 5 * sizeof(unsigned long long), h->stream)); }
+  const int nstreams = h->nsearch;
+  for (int k = 0; k < h->ndirs; ++k) { h->dirs[k]->count = 0; totals[k] = 0; }
+  static const bool grid_order = [] { const char* e = getenv("B2_K3_ORDER"); return e && std::string(e) == "grid"; }();
   auto issue_search = [&](int k, cudaStream_t st, DevBuf& cub_tmp) -> int {
     Direction* d = h->dirs[k].get();
     Cloud* S = impl_cloud(h, d->src); Cloud* T = impl_cloud(h, d->tgt);
     const size_t ns = S->n;
     if (ns == 0 || T->n == 0) return B2_OK;
-    B2_TRY(d->match.ensure(ns * 4)); B2_TRY(d->d2.ensure(ns * 4)); B2_TRY(d->flags.ensure(ns * 4)); B2_TRY(d->offs.ensure(ns * 4));
+    const unsigned int ntiles = div_up(ns, kTile);
+    B2_TRY(d->key.ensure(ns * 8)); B2_TRY(d->tile_count.ensure((size_t)ntiles * 4)); B2_TRY(d->tile_off.ensure((size_t)ntiles * 4));
+    SearchGrid sg;
+    B2_TRY(search_grid(T, &sg));
     cudaEvent_t n0 = nullptr, n1 = nullptr;
     B2_CUDA(cudaEventCreate(&n0)); B2_CUDA(cudaEventCreate(&n1));
     B2_CUDA(cudaEventRecord(n0, st));
-    // longest-first launch order (k_cta_cost + a 10^4..10^5-element radix sort: a few tens of microseconds per direction)
-    const unsigned int ncta = div_up(ns, 128);
+    // longest-first launch order (k_tile_cost + a 10^4..10^5-element radix sort); the geometry of a direction changes by millimetres
+    // between outer iterations, so the order is kept for eight of them
     const unsigned int* order = nullptr;
-    static const bool grid_order = [] { const char* e = getenv("B2_K3_ORDER"); return e && std::string(e) == "grid"; }();
-    if (h->lpt_order && !grid_order && ncta > 4u * (unsigned int)h->sms) {
-      B2_TRY(d->cta_cost.ensure((size_t)ncta * 16));
-      unsigned int* cc = d->cta_cost.as<unsigned int>();
-      k_cta_cost<<<div_up(ncta, 256), 256, 0, st>>>(S->s_xyz.as<float4>(), ns, T->table.as<HashEntry>(), T->log2size, g, ncta, cc, cc + ncta);
-      size_t tmp2 = 0;
-      B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp2, cc, cc + 2 * (size_t)ncta, cc + ncta, cc + 3 * (size_t)ncta, (int)ncta, 0, 32, st));
-      B2_TRY(cub_tmp.ensure(tmp2));
-      B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(cub_tmp.p, tmp2, cc, cc + 2 * (size_t)ncta, cc + ncta, cc + 3 * (size_t)ncta, (int)ncta, 0, 32, st));
-      order = cc + 3 * (size_t)ncta;
-      h->launches += 2;
+    if (h->lpt_order && !grid_order && ntiles > 4u * (unsigned int)h->sms) {
+      B2_TRY(d->order.ensure((size_t)ntiles * 16));
+      unsigned int* cc = d->order.as<unsigned int>();
+      if (d->order_src != d->src || d->order_tgt != d->tgt || d->order_tiles != ntiles || d->order_age >= 8) {
+        k_tile_cost<<<div_up(ntiles, 256), 256, 0, st>>>(S->s_xyz.as<float4>(), ns, T->table.as<HashEntry>(), sg, ntiles, cc, cc + ntiles);
+        size_t tmp2 = 0;
+        B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp2, cc, cc + 2 * (size_t)ntiles, cc + ntiles, cc + 3 * (size_t)ntiles, (int)ntiles, 0, 32, st));
+        B2_TRY(cub_tmp.ensure(tmp2));
+        B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(cub_tmp.p, tmp2, cc, cc + 2 * (size_t)ntiles, cc + ntiles, cc + 3 * (size_t)ntiles, (int)ntiles, 0, 32, st));
+        d->order_src = d->src; d->order_tgt = d->tgt; d->order_tiles = ntiles; d->order_age = 0;
+        h->launches += 2;
+      }
+      ++d->order_age;
+      order = cc + 3 * (size_t)ntiles;
     }
-    const char* work_path = getenv("B2_K3_WORK");   // diagnostic: per-query work counters of every search launch -> <path>.<k>.bin
-    if (work_path && *work_path) {
-      DevBuf wk; B2_TRY(wk.ensure(ns * 16));
-      k_nn_radius1<true><<<div_up(ns, 128), 128, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(),
-                                                                 T->box2.as<Aabb>(), T->table.as<HashEntry>(), T->log2size, g, r2,
-                                                                 d->match.as<int>(), d->d2.as<float>(), d->flags.as<unsigned int>(), wk.as<uint4>(), order);
-      std::vector<uint4> hw(ns); std::vector<float4> hq(ns);
-      B2_CUDA(cudaMemcpyAsync(hw.data(), wk.p, ns * 16, cudaMemcpyDeviceToHost, st));
-      B2_CUDA(cudaMemcpyAsync(hq.data(), S->s_xyz.p, ns * 16, cudaMemcpyDeviceToHost, st));
-      B2_CUDA(cudaStreamSynchronize(st));
-      const std::string fn = std::string(work_path) + "." + std::to_string(k) + ".bin";
-      if (FILE* f = fopen(fn.c_str(), "wb")) { fwrite(hq.data(), 16, ns, f); fwrite(hw.data(), 16, ns, f); fclose(f); }
-      wk.release();
-    } else {
-      k_nn_radius1<false><<<div_up(ns, 128), 128, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(),
-                                                                  T->box2.as<Aabb>(), T->table.as<HashEntry>(), T->log2size, g, r2,
-                                                                  d->match.as<int>(), d->d2.as<float>(), d->flags.as<unsigned int>(), nullptr, order);
-    }
+    if (h->work_stats)
+      k_nn_tiles<true><<<ntiles, kTile, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(), T->box2.as<Aabb>(),
+                                                 T->table.as<HashEntry>(), sg, r2, d->key.as<unsigned long long>(), d->tile_count.as<unsigned int>(),
+                                                 h->work_dev.as<unsigned long long>(), order);
+    else
+      k_nn_tiles<false><<<ntiles, kTile, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(), T->box2.as<Aabb>(),
+                                                  T->table.as<HashEntry>(), sg, r2, d->key.as<unsigned long long>(), d->tile_count.as<unsigned int>(),
+                                                  nullptr, order);
     B2_CUDA(cudaEventRecord(n1, st));
     h->nn_events.emplace_back(n0, n1);
     h->stats.search_algorithmic_bytes += 12ull * ns + 12ull * T->n;
-    ++h->launches;
-    size_t tmp = 0;
-    B2_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d->flags.as<unsigned int>(), d->offs.as<unsigned int>(), (long long)ns, st));
-    B2_TRY(cub_tmp.ensure(tmp));
-    B2_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp, d->flags.as<unsigned int>(), d->offs.as<unsigned int>(), (long long)ns, st));
-    B2_CUDA(cudaMemcpyAsync(&tails[2 * k], d->offs.as<unsigned int>() + (ns - 1), 4, cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaMemcpyAsync(&tails[2 * k + 1], d->flags.as<unsigned int>() + (ns - 1), 4, cudaMemcpyDeviceToHost, st));
+    k_scan_tiles<<<1, 1024, 0, st>>>(d->tile_count.as<unsigned int>(), ntiles, d->tile_off.as<unsigned int>(), h->totals_dev.as<unsigned int>() + k);
+    h->launches += 2;
+    B2_CUDA(cudaMemcpyAsync(&totals[k], h->totals_dev.as<unsigned int>() + k, 4, cudaMemcpyDeviceToHost, st));
     return B2_OK;
   };
 
-  // Index build and search overlap (B2_ICP_OVERLAP=1; OFF by default): the searches of the pairs whose two clouds are indexed run on the
-  // auxiliary streams underneath the index build of the remaining clouds. Per cloud: phase 1 (keys, sort, gather, cell count) is queued
-  // two clouds ahead; the host waits for a cloud's cell count only to size its hash table (phase 2), then releases its pairs.
-  // Measured at config 2 (tools/gpu_job_r01s.sh): parity intact, but index + search 41.1 ms against 40.4 ms for the two separate phases
-  // and a slower step overall (70.3 vs 67.2 ms) — the radix-sort passes and K3 contend for L2 / issue slots instead of complementing
-  // each other, and only three streams remain for the searches. Kept as an A/B switch.
-  static const bool overlap_env = [] { const char* e = getenv("B2_ICP_OVERLAP"); return e && e[0] == '1'; }();
-  const bool overlap = overlap_env && nstreams > 1 && nc >= 3;
   int issued = 0;
-  if (overlap) {
-    while ((int)h->cloud_ev.size() < 2 * nc) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->cloud_ev.push_back(e); }
-    unsigned int* cnt_host = reinterpret_cast<unsigned int*>(h->pin_counts.p);
-    auto queue_phase1 = [&](int i) -> int {
-      B2_TRY(index_cloud_phase1(h, impl_cloud(h, i), g, key_bits, i));
-      B2_CUDA(cudaMemcpyAsync(cnt_host + i, h->cell_counts.as<unsigned int>() + i, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
-      B2_CUDA(cudaEventRecord(h->cloud_ev[2 * i], h->stream));
-      return B2_OK;
-    };
-    for (int i = 0; i < std::min(2, nc); ++i) B2_TRY(queue_phase1(i));
-    for (int i = 0; i < nc; ++i) {
-      B2_CUDA(cudaEventSynchronize(h->cloud_ev[2 * i]));
-      impl_cloud(h, i)->ncells = cnt_host[i];
-      B2_TRY(index_cloud_phase2(h, impl_cloud(h, i), g));
-      B2_CUDA(cudaEventRecord(h->cloud_ev[2 * i + 1], h->stream));
-      for (int k = 0; k < h->ndirs; ++k) {          // the pairs this cloud completes, in ik order
-        Direction* d = h->dirs[k].get();
-        if (!d->local || std::max(d->src, d->tgt) != i) continue;
-        const int si = issued++ % (nstreams - 1);
-        B2_CUDA(cudaStreamWaitEvent(h->aux[si], h->cloud_ev[2 * d->src + 1], 0));
-        B2_CUDA(cudaStreamWaitEvent(h->aux[si], h->cloud_ev[2 * d->tgt + 1], 0));
-        B2_TRY(issue_search(k, h->aux[si], h->search_tmp[si + 1]));
-      }
-      if (i + 2 < nc) B2_TRY(queue_phase1(i + 2));
-    }
-    B2_CUDA(cudaEventRecord(h->ev[1], h->stream));
-  } else {
-    for (int i = 0; i < nc; ++i) B2_TRY(index_cloud_phase1(h, impl_cloud(h, i), g, key_bits, i));
-    B2_CUDA(cudaMemcpyAsync(h->pin_counts.p, h->cell_counts.p, sizeof(unsigned int) * nc, cudaMemcpyDeviceToHost, h->stream));
-    B2_CUDA(cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < nc; ++i) { impl_cloud(h, i)->ncells = h->pin_counts.as<unsigned int>()[i]; B2_TRY(index_cloud_phase2(h, impl_cloud(h, i), g)); }
-    B2_CUDA(cudaEventRecord(h->ev[1], h->stream));
-    if (nstreams > 1) {
-      B2_CUDA(cudaEventRecord(h->fork_ev, h->stream));
-      for (int i = 0; i + 1 < nstreams; ++i) B2_CUDA(cudaStreamWaitEvent(h->aux[i], h->fork_ev, 0));
-    }
-    for (int k = 0; k < h->ndirs; ++k) {
-      if (!h->dirs[k]->local) continue;
-      const int si = issued++ % nstreams;
-      B2_TRY(issue_search(k, si == 0 ? h->stream : h->aux[si - 1], h->search_tmp[si]));
-    }
+  if (nstreams > 1) {
+    B2_CUDA(cudaEventRecord(h->fork_ev, h->stream));
+    for (int i = 0; i + 1 < nstreams; ++i) B2_CUDA(cudaStreamWaitEvent(h->aux[i], h->fork_ev, 0));
+  }
+  for (int k = 0; k < h->ndirs; ++k) {
+    if (!h->dirs[k]->local) continue;
+    const int si = issued++ % nstreams;
+    B2_TRY(issue_search(k, si == 0 ? h->stream : h->aux[si - 1], h->search_tmp[si]));
   }
   if (nstreams > 1)
     for (int i = 0; i + 1 < nstreams; ++i) { B2_CUDA(cudaEventRecord(h->join_ev[i], h->aux[i])); B2_CUDA(cudaStreamWaitEvent(h->stream, h->join_ev[i], 0)); }
   B2_CUDA(cudaStreamSynchronize(h->stream));
   B2_CUDA(cudaEventRecord(h->ev[2], h->stream));
-  (void)counts;
 
   // ---- K4: pack local non-empty sets into one record array ----
   h->segs_host.clear(); h->seg_dir.clear();
@@ -482,7 +591,7 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   for (int k = 0; k < h->ndirs; ++k) {
     Direction* d = h->dirs[k].get();
     if (!d->local) continue;
-    d->count = (unsigned long long)tails[2 * k] + tails[2 * k + 1];
+    d->count = totals[k];
     h->stats.search_algorithmic_bytes += 8ull * d->count;
     d->rec_begin = total;
     if (d->count == 0) continue;   // empty sets are not registered (icp_point_to_plane.cc:240)
@@ -498,9 +607,10 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   for (int s = 0; s < nseg; ++s) {
     Direction* d = h->dirs[h->seg_dir[s]].get();
     Cloud* S = impl_cloud(h, d->src); Cloud* T = impl_cloud(h, d->tgt);
-    k_pack<<<div_up(S->n, 256), 256, 0, h->stream>>>(S->s_xyz.as<float4>(), S->s_nrm.as<float4>(), S->n, T->s_xyz.as<float4>(),
-                                                     T->s_nrm.as<float4>(), d->match.as<int>(), d->offs.as<unsigned int>(), d->rec_begin,
-                                                     h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>());
+    k_pack_tiles<<<div_up(S->n, kTile), kTile, 0, h->stream>>>(S->s_xyz.as<float4>(), S->s_nrm.as<float4>(), S->n, T->s_xyz.as<float4>(),
+                                                               T->s_nrm.as<float4>(), T->perm_inv.as<unsigned int>(), d->key.as<unsigned long long>(),
+                                                               d->tile_off.as<unsigned int>(), init_key, d->rec_begin, h->rec_a.as<float4>(),
+                                                               h->rec_b.as<float4>(), h->rec_c.as<float4>());
     ++h->launches;
   }
   B2_TRY(h->segs_dev.ensure(sizeof(Segment) * std::max(1, nseg)));
@@ -646,6 +756,10 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   // with several search streams the per-launch spans overlap, so the per-launch figure is the phase time over the launches
   h->stats.ms_search_kernel_avg = h->nn_events.empty() ? 0.f : (float)((h->nsearch > 1 ? (double)h->stats.ms_search : nn) / h->nn_events.size());
   h->stats.search_launches = (int)h->nn_events.size();
+  h->stats.ms_index_build = h->ms_index_build;
+  if (h->work_stats) {
+    B2_CUDA(cudaMemcpy(h->stats.search_work, h->work_dev.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
   return B2_OK;
 }
 
@@ -673,6 +787,7 @@ int b2_icp_plan_directions(int n_movable, int has_fixed, int world_size, int32_t
 
 const char* b2_last_error(void) { return last_error_ref().c_str(); }
 int b2_abi_version(void) { return B2_ABI_VERSION; }
+int b2_trim(void) { pool_trim_all(); return B2_OK; }
 
 int b2_device_info(int* device, char* name, size_t name_cap, int* sm_count, int* cc_major, int* cc_minor) {
   int count = 0;
@@ -708,6 +823,7 @@ int b2_icp_create(const b2_icp_config* cfg, b2_icp** out) {
   if (c.stream) { h->stream = (cudaStream_t)c.stream; }
   else { B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
   if (const char* e = getenv("B2_K3_STREAMS")) h->nsearch = std::max(1, std::min((int)b2_icp::kMaxSearchStreams, atoi(e)));
+  if (const char* e = getenv("B2_K3_WORK")) h->work_stats = e[0] && e[0] != '0';
   for (int i = 0; i + 1 < h->nsearch; ++i) {
     B2_CUDA(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
     B2_CUDA(cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
@@ -725,20 +841,19 @@ int b2_icp_destroy(b2_icp* h) {
   cudaStreamSynchronize(h->stream);
   auto free_cloud = [](Cloud* c) {
     if (!c) return;
-    for (DevBuf* b : {&c->local_xyz, &c->local_nrm, &c->keys_in, &c->keys_out, &c->idx_in, &c->perm, &c->s_xyz, &c->s_nrm, &c->table, &c->box1, &c->box2}) b->release();
+    for (DevBuf* b : {&c->local_xyz, &c->local_nrm, &c->l_xyz, &c->l_nrm, &c->perm_inv, &c->occ, &c->s_xyz, &c->s_nrm, &c->table, &c->box1, &c->box2}) b->release();
   };
   for (auto& c : h->movable) free_cloud(c.get());
   free_cloud(h->fixed.get());
-  for (auto& d : h->dirs) for (DevBuf* b : {&d->match, &d->d2, &d->flags, &d->offs}) b->release();
+  for (auto& d : h->dirs) for (DevBuf* b : {&d->key, &d->tile_count, &d->tile_off, &d->order}) b->release();
   for (DevBuf* b : {&h->bbox_partial, &h->cub_tmp, &h->cell_counts, &h->rec_a, &h->rec_b, &h->rec_c, &h->segs_dev, &h->poses_dev, &h->partials,
-                    &h->segsum, &h->eq_dev, &h->scatter_m, &h->scatter_d, &h->xpartials, &h->xsegsum}) b->release();
+                    &h->segsum, &h->eq_dev, &h->scatter_m, &h->scatter_d, &h->xpartials, &h->xsegsum, &h->work_dev, &h->totals_dev}) b->release();
   for (PinnedBuf* b : {&h->pin_bbox, &h->pin_counts, &h->pin_eq, &h->pin_poses, &h->pin_segs, &h->pin_misc}) b->release();
   for (auto& pr : h->acc_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto& pr : h->nn_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < b2_icp::kMaxSearchStreams - 1; ++i) { if (h->aux[i]) cudaStreamDestroy(h->aux[i]); if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]); }
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
-  for (cudaEvent_t e : h->cloud_ev) if (e) cudaEventDestroy(e);
   for (DevBuf& b : h->search_tmp) b.release();
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -754,11 +869,13 @@ static int add_cloud_impl(b2_icp* h, const float* xyz, const float* nrm, size_t 
   if (fixed) {
     // icp_point_to_plane.cc:112-127: transform to the global frame, concatenate, return -1.
     Cloud tmp;
+    struct Guard { Cloud* c; ~Guard() { c->local_xyz.release(); c->local_nrm.release(); } } tmp_guard{&tmp};
     B2_TRY(upload_cloud(h, &tmp, xyz, nrm, n, stride, from_device));
     if (!h->fixed) { h->fixed.reset(new Cloud()); h->fixed->is_fixed = true; const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}; std::memcpy(h->fixed->T, I, sizeof(I)); }
     Cloud* f = h->fixed.get();
     const size_t old = f->n, tot = old + n;
-    DevBuf nx, nn;
+    Scoped sx, sn;      // become the fixed cloud's buffers on success (swapped below), released on every error path
+    DevBuf &nx = sx.b, &nn = sn.b;
     B2_TRY(nx.ensure(std::max<size_t>(tot, 1) * 12)); B2_TRY(nn.ensure(std::max<size_t>(tot, 1) * 12));
     if (old) {
       B2_CUDA(cudaMemcpyAsync(nx.p, f->local_xyz.p, old * 12, cudaMemcpyDeviceToDevice, h->stream));
@@ -767,9 +884,8 @@ static int add_cloud_impl(b2_icp* h, const float* xyz, const float* nrm, size_t 
     if (n) k_transform<<<div_up(n, 256), 256, 0, h->stream>>>(tmp.local_xyz.as<float>(), tmp.local_nrm.as<float>(), n, mat4_of(T),
                                                              nx.as<float>() + 3 * old, nn.as<float>() + 3 * old);
     B2_CUDA(cudaStreamSynchronize(h->stream));
-    f->local_xyz.release(); f->local_nrm.release();
-    f->local_xyz = nx; f->local_nrm = nn; f->n = tot;
-    tmp.local_xyz.release(); tmp.local_nrm.release();
+    std::swap(f->local_xyz, nx); std::swap(f->local_nrm, nn);   // the old buffers leave with the Scoped temporaries
+    f->n = tot; f->have_lbox = f->indexed = false;
     if (out_id) *out_id = -1;
     return B2_OK;
   }
@@ -840,10 +956,10 @@ int b2_icp_get_pair_correspondences(b2_icp* h, int k, int32_t* iq, int32_t* im, 
   if (!h || k < 0 || k >= (int)h->segs_host.size() || !iq || !im || !dist) return set_error(B2_ERR_ARG, "bad argument");
   B2_CUDA(cudaSetDevice(h->device));
   Direction* d = h->dirs[h->seg_dir[k]].get();
-  Cloud* S = impl_cloud(h, d->src); Cloud* T = impl_cloud(h, d->tgt);
+  Cloud* S = impl_cloud(h, d->src);
   const size_t ns = S->n;
   B2_TRY(h->scatter_m.ensure(ns * 4)); B2_TRY(h->scatter_d.ensure(ns * 4));
-  k_scatter_matches<<<div_up(ns, 256), 256, 0, h->stream>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), d->match.as<int>(), d->d2.as<float>(),
+  k_scatter_matches<<<div_up(ns, 256), 256, 0, h->stream>>>(S->s_xyz.as<float4>(), ns, d->key.as<unsigned long long>(), h->last_init_key,
                                                            h->scatter_m.as<int>(), h->scatter_d.as<float>());
   std::vector<int> m(ns); std::vector<float> dd(ns);
   B2_CUDA(cudaMemcpyAsync(m.data(), h->scatter_m.p, ns * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -874,13 +990,12 @@ int b2_find_correspondences(const float* src_xyz, size_t n_src, const float* tgt
   int rc = B2_OK;
   do {
     const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-    Cloud S, T;
-    std::memcpy(S.T, I, sizeof(I)); std::memcpy(T.T, I, sizeof(I));
-    // normals are irrelevant for the search: reuse xyz as a stand-in
-    if ((rc = upload_cloud(h, &S, src_xyz, src_xyz, n_src, 12, false)) != B2_OK) break;
-    if ((rc = upload_cloud(h, &T, tgt_xyz, tgt_xyz, n_tgt, 12, false)) != B2_OK) break;
-    h->movable.emplace_back(new Cloud(S)); h->movable.emplace_back(new Cloud(T));
-    S = Cloud(); T = Cloud();
+    // the handle owns both clouds from the start, so every exit path releases them; normals are irrelevant for the search: xyz stands in
+    h->movable.emplace_back(new Cloud()); h->movable.emplace_back(new Cloud());
+    Cloud* S = h->movable[0].get(); Cloud* T = h->movable[1].get();
+    std::memcpy(S->T, I, sizeof(I)); std::memcpy(T->T, I, sizeof(I));
+    if ((rc = upload_cloud(h, S, src_xyz, src_xyz, n_src, 12, false)) != B2_OK) break;
+    if ((rc = upload_cloud(h, T, tgt_xyz, tgt_xyz, n_tgt, 12, false)) != B2_OK) break;
     if (n_src == 0 || n_tgt == 0) break;
     // run only the index + search part of an outer iteration
     bool conv;

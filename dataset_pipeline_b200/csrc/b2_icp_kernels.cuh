@@ -1,14 +1,20 @@
 // Device kernels of Path A (multi-scan point-to-plane ICP) for sm_100a.
 //
-//   K1  k_bbox / k_keys / k_apply   transform to the global frame + AABB + cell keys + sorted SoA copies
-//                                   (replaces pcl::transformPointCloudWithNormals + bbox loops, icp_point_to_plane.cc:189-205)
-//   K2  k_count_cells / k_hash_*    occupied-cell hash over the cell-sorted target (replaces the per-pair kd-tree build, :46-51)
-//   K3  k_nn_radius1                nearest target within radius per source point (replaces radiusSearch loop, :63-102)
-//   K4  k_pack                      48 B packed correspondence records (p_s,n_s,p_t,n_t), three float4 planes
-//   K5  k_accumulate                one streaming pass: cost + 6x6 S + 6-vector g per correspondence set, fp64
-//                                   (replaces compute() loops, icp_point_to_plane_impl.h:129-211 and :240-266)
-//   K6  k_finalize                  fixed-order reduction of the per-CTA partials + assembly of the normal equations
-//                                   with the reference's upper-triangle quirk (impl.h:82-113 + :226)
+// Static index, once per cloud and search radius, in the CLOUD's own frame (a rigid transform maps a uniform grid to a uniform
+// grid, so the index survives every pose update; replaces the per-pair kd-tree build, icp_point_to_plane.cc:46-51):
+//   K1  k_bbox / k_keys / k_gather_sorted   cell keys of the cloud-frame points, cell-sorted copies, inverse permutation
+//   K2  k_count_cells / k_hash_cells        occupied-cell hash table over the sorted keys
+// Per outer iteration:
+//   K1x k_xform_sorted     global-frame copies of the sorted points + chunk boxes + AABB in ONE streaming pass
+//                          (replaces pcl::transformPointCloudWithNormals + bbox loops, icp_point_to_plane.cc:189-205)
+//   K3  k_nn_tiles         nearest target within radius per source point (replaces the radiusSearch loop, :63-102):
+//                          CTA-cooperative — query tiles staged in shared memory by the bulk-copy engine, own cells per thread,
+//                          neighbour cells through a shared-memory work queue drained by full warps
+//   K4  k_scan_tiles / k_pack_tiles   48 B packed correspondence records (p_s,n_s,p_t,n_t), three float4 planes
+//   K5  k_accumulate       one streaming pass: cost + 6x6 S + 6-vector g per correspondence set, fp64
+//                          (replaces compute() loops, icp_point_to_plane_impl.h:129-211 and :240-266)
+//   K6  k_finalize         fixed-order reduction of the per-CTA partials + assembly of the normal equations
+//                          with the reference's upper-triangle quirk (impl.h:82-113 + :226)
 // All of these are HBM / gather bound integer+fp32+fp64 streaming work: no tensor cores.
 #pragma once
 #include "b2_common.cuh"
@@ -17,6 +23,30 @@ namespace b2 {
 
 static constexpr int kAccThreads = 256;
 static constexpr int kAccVals = 28;   // 21 (upper S) + 6 (g) + 1 (cost)
+
+// ---- mbarrier / bulk-copy (TMA 1-D) helpers, used by K3 (query tiles) and K5 (record tiles) ------------------------
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+  unsigned int ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned int bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 
 // ------------------------------------------------------------------------------------------------------------------
 // K1a: AABB of the transformed cloud. One partial (6 floats) per block; the host finishes the reduction.
@@ -44,31 +74,29 @@ __global__ void __launch_bounds__(256) k_bbox(const float* __restrict__ xyz, siz
   }
 }
 
-// K1b: cell key of every transformed point (+ identity permutation).
-__global__ void __launch_bounds__(256) k_keys(const float* __restrict__ xyz, size_t n, Mat4 T, GridParams g,
+// K1b: cell key of every point in the cloud frame (+ identity permutation). Cell coordinates in double, so the key of a point is
+// a function of its fp32 coordinates and the grid alone.
+__global__ void __launch_bounds__(256) k_keys(const float* __restrict__ xyz, size_t n, GridParams g,
                                               unsigned long long* __restrict__ keys, unsigned int* __restrict__ idx) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float3 p = xform_point(T, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
-  const double fx = ((double)p.x - g.ox) * g.inv, fy = ((double)p.y - g.oy) * g.inv, fz = ((double)p.z - g.oz) * g.inv;
+  const double fx = ((double)xyz[3 * i] - g.ox) * g.inv, fy = ((double)xyz[3 * i + 1] - g.oy) * g.inv, fz = ((double)xyz[3 * i + 2] - g.oz) * g.inv;
   const int cx = (int)floor(fx), cy = (int)floor(fy), cz = (int)floor(fz);
   keys[i] = (cell_key(g, cx, cy, cz) << (3 * g.fbits)) | fine_code(fx - cx, fy - cy, fz - cz, g.fbits);
   idx[i] = (unsigned int)i;
 }
 
-// K1c: cell-sorted global-frame copies: s_xyz[j] = (p, bits(original index)), s_nrm[j] = (n, 0).
-__global__ void __launch_bounds__(256) k_apply(const float* __restrict__ xyz, const float* __restrict__ nrm, size_t n, Mat4 T,
-                                               const unsigned int* __restrict__ perm, float4* __restrict__ s_xyz,
-                                               float4* __restrict__ s_nrm) {
+// K1c: cell-sorted cloud-frame copies: l_xyz[j] = (p, bits(original index)), l_nrm[j] = (n, 0), and the inverse permutation
+// (sorted position of every original index; K4 looks the matched target up through it).
+__global__ void __launch_bounds__(256) k_gather_sorted(const float* __restrict__ xyz, const float* __restrict__ nrm, size_t n,
+                                                       const unsigned int* __restrict__ perm, float4* __restrict__ l_xyz,
+                                                       float4* __restrict__ l_nrm, unsigned int* __restrict__ perm_inv) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const unsigned int i = perm[j];
-  const float3 p = xform_point(T, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]);
-  s_xyz[j] = make_float4(p.x, p.y, p.z, __uint_as_float(i));
-  if (nrm) {
-    const float3 q = xform_normal(T, nrm[3 * (size_t)i], nrm[3 * (size_t)i + 1], nrm[3 * (size_t)i + 2]);
-    s_nrm[j] = make_float4(q.x, q.y, q.z, 0.f);
-  }
+  l_xyz[j] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], __uint_as_float(i));
+  l_nrm[j] = make_float4(nrm[3 * (size_t)i], nrm[3 * (size_t)i + 1], nrm[3 * (size_t)i + 2], 0.f);
+  perm_inv[i] = (unsigned int)j;
 }
 
 // Plain transform into packed float3 arrays (fixed-cloud concatenation, icp_point_to_plane.cc:118-126).
@@ -83,80 +111,53 @@ __global__ void __launch_bounds__(256) k_transform(const float* __restrict__ xyz
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K2: occupied-cell hash table over the sorted keys. Entry = {key, begin, end} (16 B, one LDG.128 per probe).
+// K1x (every outer iteration): s_xyz[j] = (T * l_xyz[j], index), s_nrm[j] = R * l_nrm[j] in the reference's fp32 operation order,
+// the level-1 chunk box of every 32 consecutive sorted points (one warp = one chunk) and one AABB partial per block — a single
+// 64 B/point stream; nothing is sorted or hashed after the first iteration. Persistent grid (a multiple of the SM count), every
+// warp walks whole chunks.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_count_cells(const unsigned long long* __restrict__ keys, size_t n, unsigned int* __restrict__ count,
-                                                     int kFineBits) {
-  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool head = j < n && (j == 0 || (keys[j] >> kFineBits) != (keys[j - 1] >> kFineBits));
-  const unsigned int m = __ballot_sync(0xffffffffu, head);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned int)__popc(m));
-}
-
-__global__ void __launch_bounds__(256) k_hash_insert(const unsigned long long* __restrict__ keys, size_t n, HashEntry* __restrict__ table,
-                                                     int log2size, int kFineBits) {
-  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const unsigned long long key = keys[j] >> kFineBits;
-  if (j != 0 && (keys[j - 1] >> kFineBits) == key) return;
-  const unsigned int mask = (1u << log2size) - 1u;
-  unsigned int s = hash_slot(key, log2size);
-  while (true) {
-    const unsigned long long prev = atomicCAS(&table[s].key, kEmptyKey, key);
-    if (prev == kEmptyKey) { table[s].begin = (unsigned int)j; return; }
-    s = (s + 1) & mask;
-  }
-}
-
-__device__ __forceinline__ bool hash_find(const HashEntry* __restrict__ table, int log2size, unsigned long long key,
-                                          unsigned int* begin, unsigned int* end) {
-  const unsigned int mask = (1u << log2size) - 1u;
-  unsigned int s = hash_slot(key, log2size);
-  while (true) {
-    const uint4 e = __ldg(reinterpret_cast<const uint4*>(table + s));
-    const unsigned long long k = ((unsigned long long)e.y << 32) | e.x;
-    if (k == key) { *begin = e.z; *end = e.w; return true; }
-    if (k == kEmptyKey) return false;
-    s = (s + 1) & mask;
-  }
-}
-
-__global__ void __launch_bounds__(256) k_hash_ends(const unsigned long long* __restrict__ keys, size_t n, HashEntry* __restrict__ table,
-                                                   int log2size, int kFineBits) {
-  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const unsigned long long key = keys[j] >> kFineBits;
-  if (j + 1 != n && (keys[j + 1] >> kFineBits) == key) return;
-  const unsigned int mask = (1u << log2size) - 1u;
-  unsigned int s = hash_slot(key, log2size);
-  while (table[s].key != key) s = (s + 1) & mask;
-  table[s].end = (unsigned int)(j + 1);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// K3: nearest target within radius (strict d2 < r2), lowest ORIGINAL target index on exact ties.
-// d2 = ((dx*dx)+(dy*dy))+(dz*dz) in fp32 without contraction (FLANN L2_Simple order).
-// Grid cells are >= 2d wide, so every target within d of a query lies in the 2x2x2 block of cells on the query's side of
-// its own cell (per axis: the neighbour across the NEARER face; the farther face is >= cell/2 >= d away). One thread per
-// cell-sorted source point: the query's own cell is probed and scanned first, the other seven only when their nearest face
-// is not already farther than the best match (most matched queries touch 1-2 cells).
-// Neighbouring threads share cells, so probes and candidate rows are served from L1/L2. Output at the sorted source position.
-// ------------------------------------------------------------------------------------------------------------------
-// Chunk boxes over the cell-sorted points: level 1 = 32 consecutive points (one warp each), level 2 = 32 level-1 boxes.
-__global__ void __launch_bounds__(256) k_chunk_boxes1(const float4* __restrict__ s_xyz, size_t n, Aabb* __restrict__ box1, unsigned int nbox1) {
-  const unsigned int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__global__ void __launch_bounds__(256) k_xform_sorted(const float4* __restrict__ l_xyz, const float4* __restrict__ l_nrm, size_t n, Mat4 T,
+                                                      float4* __restrict__ s_xyz, float4* __restrict__ s_nrm, Aabb* __restrict__ box1,
+                                                      float* __restrict__ partial) {
+  float mnx = INFINITY, mny = INFINITY, mnz = INFINITY, mxx = -INFINITY, mxy = -INFINITY, mxz = -INFINITY;
   const int lane = threadIdx.x & 31;
-  if (c >= nbox1) return;
-  const size_t p = (size_t)c * kChunk1 + lane;
-  float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
-  if (p < n) { const float4 v = s_xyz[p]; lx = hx = v.x; ly = hy = v.y; lz = hz = v.z; }
-  for (int o = 16; o > 0; o >>= 1) {
-    lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o));
-    lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
-    hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+  const size_t nround = (n + 31) & ~(size_t)31;      // whole warps stay in the loop (the shuffles need all 32 lanes)
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += (size_t)gridDim.x * blockDim.x) {
+    float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+    if (j < n) {
+      const float4 l = __ldcs(l_xyz + j), ln = __ldcs(l_nrm + j);
+      const float3 p = xform_point(T, l.x, l.y, l.z);
+      const float3 q = xform_normal(T, ln.x, ln.y, ln.z);
+      s_xyz[j] = make_float4(p.x, p.y, p.z, l.w);
+      s_nrm[j] = make_float4(q.x, q.y, q.z, 0.f);
+      lx = hx = p.x; ly = hy = p.y; lz = hz = p.z;
+      mnx = fminf(mnx, p.x); mny = fminf(mny, p.y); mnz = fminf(mnz, p.z);
+      mxx = fmaxf(mxx, p.x); mxy = fmaxf(mxy, p.y); mxz = fmaxf(mxz, p.z);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o));
+      lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+      hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+    }
+    if (lane == 0) { Aabb b; b.lo[0] = lx; b.lo[1] = ly; b.lo[2] = lz; b.hi[0] = hx; b.hi[1] = hy; b.hi[2] = hz; box1[j >> 5] = b; }
   }
-  if (lane == 0) { Aabb b; b.lo[0] = lx; b.lo[1] = ly; b.lo[2] = lz; b.hi[0] = hx; b.hi[1] = hy; b.hi[2] = hz; box1[c] = b; }
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o)); mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
+  }
+  __shared__ float s[8][6];
+  const int w = threadIdx.x >> 5;
+  if (lane == 0) { s[w][0] = mnx; s[w][1] = mny; s[w][2] = mnz; s[w][3] = mxx; s[w][4] = mxy; s[w][5] = mxz; }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float v = s[0][threadIdx.x];
+    for (int i = 1; i < 8; ++i) v = threadIdx.x < 3 ? fminf(v, s[i][threadIdx.x]) : fmaxf(v, s[i][threadIdx.x]);
+    partial[blockIdx.x * 6 + threadIdx.x] = v;
+  }
 }
+
+// Level-2 chunk boxes: one per 32 level-1 boxes (1024 points).
 __global__ void __launch_bounds__(256) k_chunk_boxes2(const Aabb* __restrict__ box1, unsigned int nbox1, Aabb* __restrict__ box2, unsigned int nbox2) {
   const unsigned int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -172,196 +173,381 @@ __global__ void __launch_bounds__(256) k_chunk_boxes2(const Aabb* __restrict__ b
   if (lane == 0) { Aabb b; b.lo[0] = lx; b.lo[1] = ly; b.lo[2] = lz; b.hi[0] = hx; b.hi[1] = hy; b.hi[2] = hz; box2[c] = b; }
 }
 
-struct SearchWork { unsigned int points, box1, box2, cells; };   // per-query work counters of the diagnostic K3 variant (B2_K3_WORK)
+// ------------------------------------------------------------------------------------------------------------------
+// K2: occupied-cell hash table over the sorted keys. Entry = {key, begin, end} (16 B, one LDG.128 per probe).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_count_cells(const unsigned long long* __restrict__ keys, size_t n, unsigned int* __restrict__ count,
+                                                     int kFineBits) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool head = j < n && (j == 0 || (keys[j] >> kFineBits) != (keys[j - 1] >> kFineBits));
+  const int c = __syncthreads_count(head);
+  if (threadIdx.x == 0 && c) atomicAdd(count, (unsigned int)c);
+}
 
-// candidate test; ties on d2 go to the lower original target index so the result does not depend on the visiting order.
-// (d2, index) is ONE 64-bit key, (d2 bits << 32) | index: for non-negative floats the integer order is the float order, so a single
-// unsigned compare implements "d2 < best, or d2 == best and lower index"; the initial key (r2 bits << 32) | 0 rejects d2 == r2 for every
-// index (the radius test is strict). The pruning tests read the best d2 back from the key's high word (key_d2): no second accumulator.
-#define B2_NN_TEST(T, P)                                                                                              \
+// One read of the sorted keys: the first point of a cell stores `begin`, the last one stores `end`; whichever of the two arrives
+// first claims the slot (both run the same claim-or-find probe), so no second pass is needed.
+__device__ __forceinline__ unsigned int hash_claim(HashEntry* __restrict__ table, int log2size, unsigned long long key) {
+  const unsigned int mask = (1u << log2size) - 1u;
+  unsigned int s = hash_slot(key, log2size);
+  while (true) {
+    const unsigned long long prev = atomicCAS(&table[s].key, kEmptyKey, key);
+    if (prev == kEmptyKey || prev == key) return s;
+    s = (s + 1) & mask;
+  }
+}
+__global__ void __launch_bounds__(256) k_hash_cells(const unsigned long long* __restrict__ keys, size_t n, HashEntry* __restrict__ table,
+                                                    int log2size, int kFineBits, unsigned int* __restrict__ occ) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const unsigned long long key = keys[j] >> kFineBits;
+  const bool head = j == 0 || (keys[j - 1] >> kFineBits) != key;
+  const bool tail = j + 1 == n || (keys[j + 1] >> kFineBits) != key;
+  if (!head && !tail) return;
+  const unsigned int s = hash_claim(table, log2size, key);
+  if (head && occ) atomicOr(occ + (key >> 5), 1u << (unsigned int)(key & 31ull));   // dense occupancy bitmap of the grid (small grids only)
+  if (head) table[s].begin = (unsigned int)j;
+  if (tail) table[s].end = (unsigned int)(j + 1);
+}
+
+__device__ __forceinline__ bool hash_find(const HashEntry* __restrict__ table, int log2size, unsigned long long key,
+                                          unsigned int* begin, unsigned int* end) {
+  const unsigned int mask = (1u << log2size) - 1u;
+  unsigned int s = hash_slot(key, log2size);
+  while (true) {
+    const uint4 e = __ldg(reinterpret_cast<const uint4*>(table + s));
+    const unsigned long long k = ((unsigned long long)e.y << 32) | e.x;
+    if (k == key) { *begin = e.z; *end = e.w; return true; }
+    if (k == kEmptyKey) return false;      // linear probing, load factor <= 0.5: rare second probe
+    s = (s + 1) & mask;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3: nearest target within radius (strict d2 < r2), lowest ORIGINAL target index on exact ties.
+// d2 = ((dx*dx)+(dy*dy))+(dz*dz) in fp32 on the GLOBAL-frame coordinates, without contraction (FLANN L2_Simple order) — the
+// arithmetic of the reference. Only the candidate LOOKUP runs in the target cloud's frame: the query is mapped there by the
+// inverse pose (fp32 FMA), its cell and its half of the cell are read off, and the 2x2x2 block of cells on that side is
+// searched. The grid cell is >= 2 (d sigma + margin), where sigma bounds the stretch of the inverse pose and margin every fp32
+// rounding on the way (host: grid_for_cloud / search_grid), so every target whose fp32 d2 is below r2 lies in that block.
+//
+// Work decomposition (one CTA = one tile of kTile consecutive cell-sorted queries):
+//   stage  the tile's query rows are copied into shared memory by the bulk-copy engine (cp.async.bulk + mbarrier);
+//   A      one thread per query: cell lookup, scan of the query's OWN target cell (neighbouring threads share cells, so
+//          candidate rows are broadcast loads), then the neighbour cells whose nearest face is not already farther than the
+//          best match are appended to a work queue in shared memory — ~0.4 items per query instead of up to 7 mostly idle
+//          per-thread rounds;
+//   B      full warps drain the queue, one (query, neighbour cell) item per lane; results meet in a shared 64-bit key per query
+//          (atomicMin);
+//   C      key out (8 B/query) + matched count of the tile (for K4's offsets).
+// (d2, index) is ONE 64-bit key, (d2 bits << 32) | original index: for non-negative floats the integer order is the float order,
+// so min() over keys implements "d2 < best, or d2 == best and lower index" independently of the visiting order; the initial key
+// (r2 bits << 32) | 0 rejects d2 == r2 for every index (the radius test is strict) and doubles as the "no match" value.
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr int kTile = 256;          // queries per CTA
+static constexpr unsigned int kInlineCell = 64u;   // cells up to this many points are scanned without chunk boxes
+
+struct SearchGrid {              // a target cloud's static grid + this iteration's global -> cloud-frame map
+  float m[12];                   // row-major 3x4: position relative to the grid origin = m[4r..4r+2] . q + m[4r+3]
+  float inv, cell;
+  float inv_sigma, margin;       // global distance >= cloud-frame distance * inv_sigma - margin
+  int nx, ny, nz;
+  long long sy, sz;              // cell key = cz*sz + cy*sy + cx
+  int log2size;
+  float one;                     // 1.0f at run time (see B2_NN_KEY)
+  const unsigned int* occ;       // one bit per grid cell: occupied (nullptr for grids above 2^31 cells: every neighbour is probed)
+};
+__device__ __forceinline__ bool cell_occupied(const SearchGrid& g, long long key) {
+  return !g.occ || ((__ldg(g.occ + (key >> 5)) >> (unsigned int)(key & 31ll)) & 1u);
+}
+
+struct SearchWork { unsigned int points, box1, box2, cells; };   // work counters of the diagnostic K3 variant (B2_K3_WORK)
+
+// The five additions of a candidate test are issued as FMAs with a unit factor, fma(b, -1, a) = fl(a - b) and fma(a, 1, b) =
+// fl(a + b) bit for bit: FADD shares the ALU pipe with the key compare / select (ISETP, SEL), which was the binding pipe of this
+// kernel (ncu r02b: ALU 51 %, FMA 19 % of peak); as FFMA they run beside them. `one` is a run-time 1.0f so that the multiply
+// survives ptxas (a literal 1.0 is folded back into FADD).
+#define B2_NN_KEY(T)                                                                                                  \
   {                                                                                                                   \
-    const float ax_ = fsub(q.x, (T).x), ay_ = fsub(q.y, (T).y), az_ = fsub(q.z, (T).z);                                \
-    const float d_ = fadd(fadd(fmul(ax_, ax_), fmul(ay_, ay_)), fmul(az_, az_));                                      \
+    const float ax_ = __fmaf_rn((T).x, -one, q.x), ay_ = __fmaf_rn((T).y, -one, q.y), az_ = __fmaf_rn((T).z, -one, q.z);  \
+    const float d_ = __fmaf_rn(__fmaf_rn(fmul(ax_, ax_), one, fmul(ay_, ay_)), one, fmul(az_, az_));                  \
     const unsigned long long k_ = ((unsigned long long)__float_as_uint(d_) << 32) | (unsigned long long)__float_as_uint((T).w); \
-    if (k_ < best_key) { best_key = k_; best_pos = (int)(P); }                                                        \
+    best = k_ < best ? k_ : best;                                                                                     \
   }
 
 __device__ __forceinline__ float key_d2(unsigned long long key) { return __uint_as_float((unsigned int)(key >> 32)); }
 
-__device__ __forceinline__ void scan_range(const float4* __restrict__ tgt, unsigned int b, unsigned int e, const float4& q,
-                                           int& best_pos, unsigned long long& best_key, SearchWork& wk) {
+// Candidates [b,e), four loads in flight: whole groups of four first, then ONE clamped group for the remainder — it re-reads
+// candidate e-1 (testing a candidate twice changes nothing: the key minimum is idempotent), so there is no per-candidate tail loop
+// and the lanes of a warp run the same loop shape.
+__device__ __forceinline__ void scan_range(const float4* __restrict__ tgt, unsigned int b, unsigned int e, const float4& q, float one,
+                                           unsigned long long& best, SearchWork& wk) {
   wk.points += e - b;
   unsigned int p = b;
-  for (; p + 3 < e; p += 4) {   // four candidate loads in flight: the heavy lanes of this kernel are latency bound
-    const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + p + 1), t2 = __ldg(tgt + p + 2), t3 = __ldg(tgt + p + 3);
-    B2_NN_TEST(t0, p) B2_NN_TEST(t1, p + 1) B2_NN_TEST(t2, p + 2) B2_NN_TEST(t3, p + 3)
+  for (; p + 4u <= e; p += 4u) {
+    const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + p + 1u), t2 = __ldg(tgt + p + 2u), t3 = __ldg(tgt + p + 3u);
+    B2_NN_KEY(t0) B2_NN_KEY(t1) B2_NN_KEY(t2) B2_NN_KEY(t3)
   }
-  for (; p < e; ++p) {
-    const float4 t0 = __ldg(tgt + p);
-    B2_NN_TEST(t0, p)
+  if (p < e) {
+    const unsigned int last = e - 1u;
+    const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + min(p + 1u, last)), t2 = __ldg(tgt + min(p + 2u, last));
+    B2_NN_KEY(t0) B2_NN_KEY(t1) B2_NN_KEY(t2)
   }
-}
-// candidates p, p+stride, p+2 stride, p+3 stride (those below e)
-__device__ __forceinline__ void scan_strided4(const float4* __restrict__ tgt, unsigned int p, unsigned int stride, unsigned int e, const float4& q,
-                                              int& best_pos, unsigned long long& best_key, SearchWork& wk) {
-  const unsigned int p1 = p + stride, p2 = p + 2u * stride, p3 = p + 3u * stride;
-  const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + min(p1, e - 1)), t2 = __ldg(tgt + min(p2, e - 1)), t3 = __ldg(tgt + min(p3, e - 1));
-  wk.points += 1u + (p1 < e) + (p2 < e) + (p3 < e);
-  B2_NN_TEST(t0, p)
-  if (p1 < e) B2_NN_TEST(t1, p1)
-  if (p2 < e) B2_NN_TEST(t2, p2)
-  if (p3 < e) B2_NN_TEST(t3, p3)
 }
 
-// One cell's candidates [b,e). Small cells are scanned directly; dense cells (scanner-zenith clusters reach 10^4..10^5 points in
-// one cell) go through the chunk boxes so the work per query stays bounded. What remains expensive is inherent to exact search:
-// a query a few millimetres off a dense slab (range-noise outliers) has to visit every chunk whose box is nearer than its true
-// neighbour — ~10^3 candidates against a mean of ~20 (measured with B2_K3_WORK / tools/k3_work.py). Those lanes are latency
-// bound, so scan_range keeps four candidate loads in flight, and the launch order of the CTAs is longest-first (k_cta_cost).
+// One cell's candidates [b,e). Small cells are scanned directly; dense cells (near the target's scanner a 2 cm cell holds
+// 10^2..10^3 points, at its zenith 10^4..10^5) go through the chunk boxes — 32 / 1024 consecutive points of the in-cell Morton
+// order; the box bound is evaluated with the same fp32 operations as the point distance, so pruning is exact. Cells above 2048
+// points first take a strided sample of 64 candidates so that `best` is tight before the boxes are tested.
 __device__ __forceinline__ void scan_cell(const float4* __restrict__ tgt, const Aabb* __restrict__ box1, const Aabb* __restrict__ box2,
-                                          unsigned int b, unsigned int e, const float4& q, int& best_pos, unsigned long long& best_key,
+                                          unsigned int b, unsigned int e, const float4& q, float one, unsigned long long& best,
                                           SearchWork& wk) {
   ++wk.cells;
-  if (e - b <= 48u) { scan_range(tgt, b, e, q, best_pos, best_key, wk); return; }
-  const unsigned int last = e - 1;
-  if (e - b > 2u * kChunk2) {
-    // Very dense cell: a strided sample of 64 candidates first (independent loads), so that `best` is already tight when the
-    // chunk boxes are tested. Sampled points are real candidates; re-visiting them later changes nothing.
+  if (e - b <= kInlineCell) { scan_range(tgt, b, e, q, one, best, wk); return; }
+  const unsigned int last = e - 1u;
+  const bool huge = e - b > 2u * kChunk2;
+  if (huge) {
     const unsigned int stride = (e - b) / 64u;
-    for (unsigned int p = b; p < e; p += 4u * stride) scan_strided4(tgt, p, stride, e, q, best_pos, best_key, wk);
+    wk.points += 64u;
+    for (unsigned int p = b; p < b + 64u * stride; p += 4u * stride) {
+      const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + p + stride), t2 = __ldg(tgt + p + 2u * stride), t3 = __ldg(tgt + p + 3u * stride);
+      B2_NN_KEY(t0) B2_NN_KEY(t1) B2_NN_KEY(t2) B2_NN_KEY(t3)
+    }
   }
   for (unsigned int c2 = b / kChunk2; c2 <= last / kChunk2; ++c2) {
-    ++wk.box2;
-    if (e - b > 2u * kChunk2 && dist2_box(q.x, q.y, q.z, box2[c2]) > key_d2(best_key)) continue;
+    if (huge) { ++wk.box2; if (dist2_box(q.x, q.y, q.z, box2[c2]) > key_d2(best)) continue; }
     const unsigned int c1b = max(b / kChunk1, c2 * 32u), c1e = min(last / kChunk1, c2 * 32u + 31u);
     for (unsigned int c1 = c1b; c1 <= c1e; ++c1) {
       ++wk.box1;
-      if (dist2_box(q.x, q.y, q.z, box1[c1]) > key_d2(best_key)) continue;
-      scan_range(tgt, max(b, c1 * kChunk1), min(e, (c1 + 1u) * kChunk1), q, best_pos, best_key, wk);
+      if (dist2_box(q.x, q.y, q.z, box1[c1]) > key_d2(best)) continue;
+      scan_range(tgt, max(b, c1 * kChunk1), min(e, (c1 + 1u) * kChunk1), q, one, best, wk);
     }
   }
 }
 
-// Launch-order heuristic for K3: estimated cost of each 128-query CTA = target population of the cells of four of its queries.
-// The CTAs are then issued longest-first (the ids sorted by descending cost), so the expensive ones (queries inside scanner-zenith
-// clusters; with the z-major cell key they would otherwise sit at the very end of the grid and run alone) overlap with the rest.
-__global__ void __launch_bounds__(256) k_cta_cost(const float4* __restrict__ src, size_t ns, const HashEntry* __restrict__ table, int log2size,
-                                                  GridParams g, unsigned int ncta, unsigned int* __restrict__ cost, unsigned int* __restrict__ ids) {
+// Cell of a global-frame point in the target's grid: cell coordinates, the half of the cell per axis and the conservative
+// distances to the nearer faces.
+struct CellLookup { int cx, cy, cz; unsigned int upper; float ex2, ey2, ez2; };
+__device__ __forceinline__ CellLookup lookup_cell(const SearchGrid& g, const float4& q) {
+  const float lx = __fmaf_rn(g.m[0], q.x, __fmaf_rn(g.m[1], q.y, __fmaf_rn(g.m[2], q.z, g.m[3])));
+  const float ly = __fmaf_rn(g.m[4], q.x, __fmaf_rn(g.m[5], q.y, __fmaf_rn(g.m[6], q.z, g.m[7])));
+  const float lz = __fmaf_rn(g.m[8], q.x, __fmaf_rn(g.m[9], q.y, __fmaf_rn(g.m[10], q.z, g.m[11])));
+  // clamped so that the int conversion is defined; a query more than a cell outside the grid has no candidate at all
+  const float ux = fminf(fmaxf(fmul(lx, g.inv), -2.f), (float)g.nx + 1.f);
+  const float uy = fminf(fmaxf(fmul(ly, g.inv), -2.f), (float)g.ny + 1.f);
+  const float uz = fminf(fmaxf(fmul(lz, g.inv), -2.f), (float)g.nz + 1.f);
+  const float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
+  const float rx = fsub(ux, fx), ry = fsub(uy, fy), rz = fsub(uz, fz);
+  CellLookup c;
+  c.cx = (int)fx; c.cy = (int)fy; c.cz = (int)fz;
+  const bool hx = rx >= 0.5f, hy = ry >= 0.5f, hz = rz >= 0.5f;
+  c.upper = (hx ? 1u : 0u) | (hy ? 2u : 0u) | (hz ? 4u : 0u);
+  // distance to the nearer face: cloud-frame -> global (inv_sigma), minus every rounding on the way (margin), squared and shrunk so
+  // that the fp32 rounding of d2 itself can never beat the bound
+  const float ex = fmaxf(fsub(fmul(fmul(hx ? fsub(1.f, rx) : rx, g.cell), g.inv_sigma), g.margin), 0.f);
+  const float ey = fmaxf(fsub(fmul(fmul(hy ? fsub(1.f, ry) : ry, g.cell), g.inv_sigma), g.margin), 0.f);
+  const float ez = fmaxf(fsub(fmul(fmul(hz ? fsub(1.f, rz) : rz, g.cell), g.inv_sigma), g.margin), 0.f);
+  c.ex2 = fmul(fmul(ex, ex), 0.9999f); c.ey2 = fmul(fmul(ey, ey), 0.9999f); c.ez2 = fmul(fmul(ez, ez), 0.9999f);
+  return c;
+}
+
+// Launch-order heuristic for K3: estimated cost of each tile = target population of the cells of eight of its queries. The
+// tiles are then issued longest-first (ids sorted by descending cost), so the expensive ones (queries inside the target's
+// scanner-zenith clusters) overlap with the rest instead of forming the tail of the launch.
+__global__ void __launch_bounds__(256) k_tile_cost(const float4* __restrict__ src, size_t ns, const HashEntry* __restrict__ table, SearchGrid g,
+                                                   unsigned int ntiles, unsigned int* __restrict__ cost, unsigned int* __restrict__ ids) {
   const unsigned int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncta) return;
-  const unsigned int mask = (1u << log2size) - 1u;
+  if (c >= ntiles) return;
   unsigned int total = 0;
-  for (int k = 0; k < 4; ++k) {
-    const size_t j = (size_t)c * 128 + 32 * k;
+  for (int k = 0; k < 8; ++k) {
+    const size_t j = (size_t)c * kTile + 32 * k + 16;
     if (j >= ns) break;
     const float4 q = src[j];
-    const int cx = cell_of(q.x, g.ox, g.inv), cy = cell_of(q.y, g.oy, g.inv), cz = cell_of(q.z, g.oz, g.inv);
-    if (cx < 0 || cx >= g.nx || cy < 0 || cy >= g.ny || cz < 0 || cz >= g.nz) continue;
-    const unsigned long long key = cell_key(g, cx, cy, cz);
-    unsigned int s = hash_slot(key, log2size);
-    uint4 e = __ldg(reinterpret_cast<const uint4*>(table + s));
-    unsigned long long kk = ((unsigned long long)e.y << 32) | e.x;
-    while (kk != key && kk != kEmptyKey) { s = (s + 1) & mask; e = __ldg(reinterpret_cast<const uint4*>(table + s)); kk = ((unsigned long long)e.y << 32) | e.x; }
-    if (kk == key) total += e.w - e.z;
+    const CellLookup L = lookup_cell(g, q);
+    if ((unsigned int)L.cx >= (unsigned int)g.nx || (unsigned int)L.cy >= (unsigned int)g.ny || (unsigned int)L.cz >= (unsigned int)g.nz) continue;
+    unsigned int b, e;
+    if (hash_find(table, g.log2size, (unsigned long long)((long long)L.cz * g.sz + (long long)L.cy * g.sy + L.cx), &b, &e)) total += e - b;
   }
   cost[c] = total; ids[c] = c;
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(128) k_nn_radius1(const float4* __restrict__ src, size_t ns, const float4* __restrict__ tgt,
+__global__ void __launch_bounds__(kTile) k_nn_tiles(const float4* __restrict__ src, size_t ns, const float4* __restrict__ tgt,
                                                     const Aabb* __restrict__ box1, const Aabb* __restrict__ box2,
-                                                    const HashEntry* __restrict__ table, int log2size, GridParams g, float r2,
-                                                    int* __restrict__ match_pos, float* __restrict__ match_d2,
-                                                    unsigned int* __restrict__ flags, uint4* __restrict__ work,
-                                                    const unsigned int* __restrict__ order) {
-  const size_t j = (size_t)(order ? order[blockIdx.x] : blockIdx.x) * blockDim.x + threadIdx.x;
-  if (j >= ns) return;
-  const float4 q = src[j];
-  SearchWork wk = {0u, 0u, 0u, 0u};
-  const double fx = ((double)q.x - g.ox) * g.inv, fy = ((double)q.y - g.oy) * g.inv, fz = ((double)q.z - g.oz) * g.inv;
-  const int cx = (int)floor(fx), cy = (int)floor(fy), cz = (int)floor(fz);
-  const double rx = fx - cx, ry = fy - cy, rz = fz - cz;               // position inside the cell, [0,1)
-  const int sx = rx < 0.5 ? -1 : 1, sy = ry < 0.5 ? -1 : 1, sz = rz < 0.5 ? -1 : 1;
-  // distance to the nearer face per axis, shrunk so that fp32 rounding of d2 can never beat the bound
-  const double cell = g.cell;
-  const float ex = (float)((rx < 0.5 ? rx : 1.0 - rx) * cell * 0.9999);
-  const float ey = (float)((ry < 0.5 ? ry : 1.0 - ry) * cell * 0.9999);
-  const float ez = (float)((rz < 0.5 ? rz : 1.0 - rz) * cell * 0.9999);
-  const float ex2 = ex * ex * 0.9999f, ey2 = ey * ey * 0.9999f, ez2 = ez * ez * 0.9999f;
+                                                    const HashEntry* __restrict__ table, SearchGrid g, float r2,
+                                                    unsigned long long* __restrict__ out_key, unsigned int* __restrict__ tile_count,
+                                                    unsigned long long* __restrict__ work, const unsigned int* __restrict__ order) {
+  __shared__ __align__(128) float4 sq[kTile];                 // the tile's query rows (bulk copy)
+  __shared__ unsigned long long s_best[kTile];                // per query: best (d2, index) key
+  __shared__ long long s_cell[kTile];                         // per query: key of its own cell (signed: may lie just outside the grid)
+  __shared__ unsigned short s_items[kTile * 7];               // work queue: (query << 6) | (upper halves << 3) | neighbour
+  __shared__ unsigned int s_nitems;
+  __shared__ __align__(8) unsigned long long bar;
+  const unsigned int t = threadIdx.x, lane = t & 31u;
+  const unsigned int tile = order ? order[blockIdx.x] : blockIdx.x;
+  const size_t j0 = (size_t)tile * kTile;
+  const unsigned int cnt = (unsigned int)min((size_t)kTile, ns - j0);
+  if (t == 0) {
+    s_nitems = 0u;
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (t == 0) { mbar_expect_tx(&bar, cnt * 16u); bulk_g2s(sq, src + j0, cnt * 16u, &bar); }
+  mbar_wait(&bar, 0);
 
-  // Own cell first; a neighbour (bit0 = x, bit1 = y, bit2 = z) is probed only if its nearest face is not already farther than the
-  // best match, which removes most of the 8 probes for matched queries. The neighbours a lane still needs are kept as a bit mask and
-  // popped in a per-lane loop: in round r every lane probes ITS r-th remaining neighbour, whichever that is, so the ~0.35 neighbour
-  // probes per query of a warp run side by side instead of one mostly idle pass per neighbour slot (measured: search 36.8 -> 33.9 ms
-  // per outer iteration at config 2).
-  const unsigned int mask = (1u << log2size) - 1u;
-  int best_pos = -1;
-  unsigned long long best_key = (unsigned long long)__float_as_uint(r2) << 32;
-  auto probe = [&](int c) {
-    const int x = cx + ((c & 1) ? sx : 0), y = cy + ((c & 2) ? sy : 0), z = cz + ((c & 4) ? sz : 0);
-    if (x < 0 || x >= g.nx || y < 0 || y >= g.ny || z < 0 || z >= g.nz) return;
-    const unsigned long long key = cell_key(g, x, y, z);
-    unsigned int s = hash_slot(key, log2size);
-    uint4 e = __ldg(reinterpret_cast<const uint4*>(table + s));
-    unsigned long long k = ((unsigned long long)e.y << 32) | e.x;
-    while (k != key && k != kEmptyKey) {      // linear probing (rare at load factor <= 0.5)
-      s = (s + 1) & mask;
-      e = __ldg(reinterpret_cast<const uint4*>(table + s));
-      k = ((unsigned long long)e.y << 32) | e.x;
+  // ---- A: own cell per thread ----
+  const unsigned long long init = (unsigned long long)__float_as_uint(r2) << 32;
+  unsigned long long best = init;
+  long long base = 0;
+  unsigned int todo = 0u, upper = 0u;
+  SearchWork wk = {0u, 0u, 0u, 0u};
+  if (t < cnt) {
+    const float4 q = sq[t];
+    const CellLookup L = lookup_cell(g, q);
+    upper = L.upper;
+    base = (long long)L.cz * g.sz + (long long)L.cy * g.sy + L.cx;
+    const bool x0 = (unsigned int)L.cx < (unsigned int)g.nx, y0 = (unsigned int)L.cy < (unsigned int)g.ny, z0 = (unsigned int)L.cz < (unsigned int)g.nz;
+    const bool x1 = (unsigned int)(L.cx + ((upper & 1u) ? 1 : -1)) < (unsigned int)g.nx;
+    const bool y1 = (unsigned int)(L.cy + ((upper & 2u) ? 1 : -1)) < (unsigned int)g.ny;
+    const bool z1 = (unsigned int)(L.cz + ((upper & 4u) ? 1 : -1)) < (unsigned int)g.nz;
+    if (x0 && y0 && z0 && cell_occupied(g, base)) {
+      unsigned int b, e;
+      if (hash_find(table, g.log2size, (unsigned long long)base, &b, &e)) scan_cell(tgt, box1, box2, b, e, q, g.one, best, wk);
     }
-    if (k == key) scan_cell(tgt, box1, box2, e.z, e.w, q, best_pos, best_key, wk);
-  };
-  probe(0);
-  unsigned int todo = 0;
+    // neighbours worth a visit: inside the grid, nearest face not farther than the best match, and OCCUPIED (one bit per cell of
+    // the target's grid: most neighbour cells of a surface scan are empty, and an empty cell costs a full unsuccessful hash probe)
+    const float bd = key_d2(best);
 #pragma unroll
-  for (int c = 1; c < 8; ++c) {
-    const float lb = ((c & 1) ? ex2 : 0.f) + ((c & 2) ? ey2 : 0.f) + ((c & 4) ? ez2 : 0.f);
-    if (!(lb > key_d2(best_key))) todo |= 1u << c;
+    for (int c = 1; c < 8; ++c) {
+      const bool valid = ((c & 1) ? x1 : x0) && ((c & 2) ? y1 : y0) && ((c & 4) ? z1 : z0);
+      const float lb = fadd(fadd((c & 1) ? L.ex2 : 0.f, (c & 2) ? L.ey2 : 0.f), (c & 4) ? L.ez2 : 0.f);
+      if (valid && !(lb > bd)) {
+        const long long key = base + ((c & 1) ? ((upper & 1u) ? 1ll : -1ll) : 0ll) + ((c & 2) ? ((upper & 2u) ? g.sy : -g.sy) : 0ll) +
+                              ((c & 4) ? ((upper & 4u) ? g.sz : -g.sz) : 0ll);
+        if (cell_occupied(g, key)) todo |= 1u << c;
+      }
+    }
   }
-  while (todo) {
-    const int c = __ffs(todo) - 1;
-    todo &= todo - 1u;
-    const float lb = ((c & 1) ? ex2 : 0.f) + ((c & 2) ? ey2 : 0.f) + ((c & 4) ? ez2 : 0.f);
-    if (lb > key_d2(best_key)) continue;      // an earlier neighbour tightened the bound
-    probe(c);
+  {
+    // warp-aggregated append: one shared atomic per warp
+    const unsigned int mine = __popc(todo);
+    unsigned int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned int)o) incl += v; }
+    const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned int at = 0u;
+    if (lane == 31u && total) at = atomicAdd(&s_nitems, total);
+    at = __shfl_sync(0xffffffffu, at, 31) + incl - mine;
+    while (todo) {
+      const unsigned int c = __ffs(todo) - 1u;
+      todo &= todo - 1u;
+      s_items[at++] = (unsigned short)((t << 6) | (upper << 3) | c);
+    }
   }
-  if (STATS) work[j] = make_uint4(wk.points, wk.box1, wk.box2, wk.cells);
-  match_pos[j] = best_pos;
-  match_d2[j] = key_d2(best_key);
-  flags[j] = best_pos >= 0 ? 1u : 0u;
+  s_best[t] = best;
+  s_cell[t] = base;
+  __syncthreads();
+
+  // ---- B: neighbour cells, one queue item per lane ----
+  const unsigned int nitems = s_nitems;
+  for (unsigned int i = t; i < nitems; i += kTile) {
+    const unsigned int it = s_items[i], ql = it >> 6, up = (it >> 3) & 7u, c = it & 7u;
+    const float4 q = sq[ql];
+    long long key = s_cell[ql];
+    if (c & 1u) key += (up & 1u) ? 1 : -1;
+    if (c & 2u) key += (up & 2u) ? g.sy : -g.sy;
+    if (c & 4u) key += (up & 4u) ? g.sz : -g.sz;
+    unsigned int b, e;
+    if (!hash_find(table, g.log2size, (unsigned long long)key, &b, &e)) continue;
+    const unsigned long long seen = s_best[ql];     // possibly lowered by another item of this query already: a tighter start
+    unsigned long long bk = seen;
+    scan_cell(tgt, box1, box2, b, e, q, g.one, bk, wk);
+    if (bk < seen) atomicMin(&s_best[ql], bk);
+  }
+  __syncthreads();
+
+  // ---- C: results ----
+  bool matched = false;
+  if (t < cnt) {
+    best = s_best[t];
+    matched = best < init;
+    out_key[j0 + t] = best;
+  }
+  const int nm = __syncthreads_count(matched);
+  if (t == 0) tile_count[tile] = (unsigned int)nm;
+  if (STATS) {
+    // per-launch totals: candidates tested, level-1 / level-2 box tests, cells scanned, queue items
+    unsigned int v[4] = {wk.points, wk.box1, wk.box2, wk.cells};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unsigned int x = v[k];
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane == 0u && x) atomicAdd(work + k, (unsigned long long)x);
+    }
+    if (t == 0 && nitems) atomicAdd(work + 4, (unsigned long long)nitems);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // K4: packed correspondence records, three float4 planes (48 B / correspondence, fully coalesced in K5):
 //   A = (ps.x, ps.y, ps.z, ns.x)  B = (ns.y, ns.z, pt.x, pt.y)  C = (pt.z, nt.x, nt.y, nt.z)
+// Record order = ascending cell-sorted source position: the tile offsets are an exclusive scan of K3's per-tile match counts
+// (k_scan_tiles, one block), the position inside a tile comes from ballots — no per-query flag / offset arrays.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pack(const float4* __restrict__ s_xyz_src, const float4* __restrict__ s_nrm_src, size_t ns,
-                                              const float4* __restrict__ s_xyz_tgt, const float4* __restrict__ s_nrm_tgt,
-                                              const int* __restrict__ match_pos, const unsigned int* __restrict__ offs,
-                                              unsigned long long base, float4* __restrict__ ra, float4* __restrict__ rb,
-                                              float4* __restrict__ rc) {
-  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= ns) return;
-  const int p = match_pos[j];
-  if (p < 0) return;
+__global__ void __launch_bounds__(1024) k_scan_tiles(const unsigned int* __restrict__ tile_count, unsigned int ntiles,
+                                                     unsigned int* __restrict__ tile_off, unsigned int* __restrict__ total) {
+  __shared__ unsigned int s[1024];
+  const unsigned int per = (ntiles + 1023u) / 1024u, b = threadIdx.x * per, e = min(ntiles, b + per);
+  unsigned int sum = 0;
+  for (unsigned int i = b; i < e; ++i) sum += tile_count[i];
+  s[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const unsigned int v = threadIdx.x >= (unsigned int)o ? s[threadIdx.x - o] : 0u;
+    __syncthreads();
+    s[threadIdx.x] += v;
+    __syncthreads();
+  }
+  unsigned int run = s[threadIdx.x] - sum;
+  for (unsigned int i = b; i < e; ++i) { tile_off[i] = run; run += tile_count[i]; }
+  if (threadIdx.x == 1023) *total = s[1023];
+}
+
+__global__ void __launch_bounds__(kTile) k_pack_tiles(const float4* __restrict__ s_xyz_src, const float4* __restrict__ s_nrm_src, size_t ns,
+                                                      const float4* __restrict__ s_xyz_tgt, const float4* __restrict__ s_nrm_tgt,
+                                                      const unsigned int* __restrict__ perm_inv_tgt, const unsigned long long* __restrict__ key,
+                                                      const unsigned int* __restrict__ tile_off, unsigned long long init_key,
+                                                      unsigned long long base, float4* __restrict__ ra, float4* __restrict__ rb,
+                                                      float4* __restrict__ rc) {
+  __shared__ unsigned int warp_sum[kTile / 32];
+  const size_t j = (size_t)blockIdx.x * kTile + threadIdx.x;
+  const unsigned int lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const unsigned long long k = j < ns ? key[j] : init_key;
+  const bool matched = k < init_key;
+  const unsigned int m = __ballot_sync(0xffffffffu, matched);
+  if (lane == 0u) warp_sum[w] = __popc(m);
+  __syncthreads();
+  if (!matched) return;
+  unsigned int before = __popc(m & ((1u << lane) - 1u));
+  for (unsigned int i = 0; i < w; ++i) before += warp_sum[i];
+  const unsigned int p = perm_inv_tgt[(unsigned int)k];
   const float4 ps = s_xyz_src[j], nsr = s_nrm_src[j];
   const float4 pt = __ldg(s_xyz_tgt + p), nt = __ldg(s_nrm_tgt + p);
-  const unsigned long long o = base + offs[j];
+  const unsigned long long o = base + tile_off[blockIdx.x] + before;
   ra[o] = make_float4(ps.x, ps.y, ps.z, nsr.x);
   rb[o] = make_float4(nsr.y, nsr.z, pt.x, pt.y);
   rc[o] = make_float4(pt.z, nt.x, nt.y, nt.z);
 }
 
 // Correspondence list in the caller's (original) indexing, scattered to the original query index.
-__global__ void __launch_bounds__(256) k_scatter_matches(const float4* __restrict__ s_xyz_src, size_t ns, const float4* __restrict__ s_xyz_tgt,
-                                                         const int* __restrict__ match_pos, const float* __restrict__ match_d2,
-                                                         int* __restrict__ out_match, float* __restrict__ out_d2) {
+__global__ void __launch_bounds__(256) k_scatter_matches(const float4* __restrict__ s_xyz_src, size_t ns, const unsigned long long* __restrict__ key,
+                                                         unsigned long long init_key, int* __restrict__ out_match, float* __restrict__ out_d2) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= ns) return;
   const unsigned int qi = __float_as_uint(s_xyz_src[j].w);
-  const int p = match_pos[j];
-  out_match[qi] = p >= 0 ? (int)__float_as_uint(__ldg(s_xyz_tgt + p).w) : -1;
-  out_d2[qi] = match_d2[j];
+  const unsigned long long k = key[j];
+  out_match[qi] = k < init_key ? (int)(unsigned int)k : -1;
+  out_d2[qi] = key_d2(k);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -537,28 +723,6 @@ static constexpr int kMaxExtraTrials = 3;
 static constexpr int kTmaStages = 4;
 static constexpr int kTmaTile = 2 * kAccThreads;                   // records per tile: two per consumer thread
 static constexpr size_t kTmaSmemBytes = (size_t)kTmaStages * 3 * kTmaTile * 16;
-
-__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
-  unsigned int ok;
-  do {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned int bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 // Walks the tile sequence of one CTA: tiles never straddle a segment ("correspondence set") boundary.
 struct TileCursor {

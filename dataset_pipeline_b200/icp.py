@@ -136,7 +136,9 @@ class PointToPlaneICP:
     def stats(self):
         s = _lib.IcpStats()
         _lib.check(_lib.lib().b2_icp_last_stats(self._h, C.byref(s)))
-        return {k: getattr(s, k) for k, _ in _lib.IcpStats._fields_}
+        out = {k: getattr(s, k) for k, _ in _lib.IcpStats._fields_}
+        out["search_work"] = [int(v) for v in s.search_work]
+        return out
 
     def tries(self):
         buf = np.zeros(256, np.int32)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 1
+#define B2_ABI_VERSION 2
 
 enum {
   B2_OK = 0,
@@ -39,6 +39,10 @@ const char* b2_last_error(void);
 int b2_abi_version(void);
 /* Device index the library runs on, name, SM count. B2_ERR_NO_DEVICE when there is none. */
 int b2_device_info(int* device, char* name, size_t name_cap, int* sm_count, int* cc_major, int* cc_minor);
+/* Device memory comes from a memory pool private to this library (one per device) that keeps what handles release, so that
+ * create / destroy cycles do not re-map memory. b2_trim() returns everything the pools hold unused to the driver (call it after
+ * destroying handles when the host process needs the memory back). */
+int b2_trim(void);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Path A — multi-scan point-to-plane ICP.
@@ -88,11 +92,14 @@ typedef struct b2_icp_stats {
   int32_t passes;               /* streaming passes over the packed correspondences (this outer iteration) */
   int32_t kernel_launches;      /* kernels of this library launched (this outer iteration) */
   /* device time (ms, CUDA events on the handle's stream) of the last outer iteration */
-  float ms_index, ms_search, ms_pack, ms_inner, ms_total;
+  float ms_index, ms_search, ms_pack, ms_inner, ms_total;   /* ms_index = the per-iteration part (global-frame rows, boxes, AABBs) */
   float ms_accum_kernel_avg;    /* average duration of one accumulate-pass kernel (K5) */
   float ms_search_kernel_avg;   /* average duration of one correspondence-search kernel (K3), one pair-direction */
   int32_t search_launches;      /* pair-directions searched on this rank */
   uint64_t search_algorithmic_bytes; /* sum over those launches of 12*Q + 8*Q_matched + 12*T */
+  float ms_index_build;         /* one-time static index builds that fell into this outer iteration (0 once every cloud is indexed) */
+  int32_t reserved0;
+  uint64_t search_work[5];      /* B2_K3_WORK=1 only: candidates tested, level-1 box tests, level-2 box tests, cells scanned, queue items */
 } b2_icp_stats;
 
 void b2_icp_default_config(b2_icp_config* cfg);

@@ -28,7 +28,7 @@ def test_header_symbols_exported(L):
 
 
 def test_abi_version(L):
-    assert L.b2_abi_version() == 1
+    assert L.b2_abi_version() == 2
 
 
 def test_product_path_does_not_touch_oracle():
