@@ -7,11 +7,15 @@
 //   PointToPlaneICPImpl::compute    /root/reference/src/icp/icp_point_to_plane_impl.h:115-293
 //
 // Index design. The reference rebuilds a kd-tree over the transformed target for every pair-direction of every outer iteration
-// (:46-51). Here a cloud is indexed ONCE, in its own frame: cell-sorted copies of its points and a hash table of the occupied cells
-// of a uniform grid of that frame. A pose update moves the grid rigidly with the cloud, so nothing is re-sorted or re-hashed; per
-// outer iteration a cloud costs one streaming pass (K1x: global-frame copies, chunk boxes, AABB). A query reaches the target's
-// grid through the inverse pose; candidate distances are evaluated on the global-frame fp32 coordinates exactly as the reference
-// does, so the results do not depend on the frame the lookup ran in (see the error budget at grid_for_cloud).
+// (:46-51). Here a cloud is indexed ONCE: cell-sorted copies of its points and a hash table (+ bitmap) of the occupied cells of a
+// uniform grid that is attached to the cloud. The grid is laid out in the cloud's "index frame" = the global frame as it was when
+// the cloud was indexed (x' = F l, F = the pose at that time, frozen), with its origin on the lattice of multiples of the cell
+// size — so the grids of all clouds of a handle coincide when they are built and drift apart only by what ICP moves the poses
+// (millimetres), and the cell-sorted queries of one cloud walk the cells of another in order. A pose update moves the grid rigidly
+// with its cloud, so nothing is re-sorted or re-hashed; per outer iteration a cloud costs one streaming pass (K1x: global-frame
+// copies, chunk boxes, AABB). A query reaches a target's grid through F T^-1; candidate distances are evaluated on the global-frame
+// fp32 coordinates exactly as the reference does, so the results do not depend on the frame the lookup ran in (see the error
+// budget at grid_for_cloud).
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -36,6 +40,7 @@ struct Cloud {
   // ---- static index in the cloud frame (valid for index_d / index_sigma / index_mtot) ----
   bool have_lbox = false, indexed = false;
   float lmin[3], lmax[3];               // AABB in the cloud frame
+  double F[12];                         // index frame (row-major 3x4): the pose at index time, frozen; grid coordinates = F l
   float index_d = 0.f;
   double index_sigma = 0, index_mtot = 0, margin = 0;
   GridParams g;
@@ -138,8 +143,9 @@ static int upload_cloud(b2_icp* h, Cloud* c, const float* xyz, const float* nrm,
 }
 
 // ---- the linear part of a pose -------------------------------------------------------------------------------------
-// sigma >= || A^-1 ||_2 for the 3x3 linear part A of a pose: cloud-frame distances are at most sigma times the global ones.
-// Rigid poses give 1 + O(1e-7); anything invertible is accepted (a similarity or shear only enlarges the cells).
+// sigma >= || B ||_2 for the linear part B of the map from the global frame into a cloud's index frame: index-frame distances are at
+// most sigma times the global ones (and global ones at least 1 / sigma times the index-frame ones). While poses stay rigid B is a
+// rotation and sigma = 1 + O(1e-7); anything invertible is accepted (a pose that starts to scale or shear only enlarges the cells).
 static bool invert3(const double A[9], double Ai[9]) {      // row-major
   const double c0 = A[4] * A[8] - A[5] * A[7], c1 = A[5] * A[6] - A[3] * A[8], c2 = A[3] * A[7] - A[4] * A[6];
   const double det = A[0] * c0 + A[1] * c1 + A[2] * c2;
@@ -151,20 +157,28 @@ static bool invert3(const double A[9], double Ai[9]) {      // row-major
   return true;
 }
 static void linear_part(const float T[16], double A[9]) { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) A[3 * r + c] = T[r + 4 * c]; }
-static int pose_sigma(const float T[16], double* sigma) {
-  double A[9], Ai[9];
+// B = F_lin A^-1 maps global offsets to index-frame offsets (F_lin = linear part of the frozen index frame, nullptr = A itself, i.e.
+// the index is about to be built at this pose and B = I up to rounding).
+static int pose_sigma(const float T[16], const double* F, double* sigma) {
+  double A[9], Ai[9], B[9];
   linear_part(T, A);
   if (!invert3(A, Ai)) return set_error(B2_ERR_ARG, "pose is not invertible");
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k) {
+      double v = 0;
+      for (int m = 0; m < 3; ++m) v += (F ? F[4 * r + m] : A[3 * r + m]) * Ai[3 * m + k];
+      B[3 * r + k] = v;
+    }
   double eta = 0;
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) {
       double e = -(i == j ? 1.0 : 0.0);
-      for (int k = 0; k < 3; ++k) e += A[3 * k + i] * A[3 * k + j];
+      for (int k = 0; k < 3; ++k) e += B[3 * k + i] * B[3 * k + j];
       eta += e * e;
     }
   eta = std::sqrt(eta);
-  if (eta < 0.25) *sigma = 1.0 / std::sqrt(1.0 - eta);            // sigma_min(A)^2 >= 1 - ||A^T A - I||
-  else { double f = 0; for (double v : Ai) f += v * v; *sigma = std::sqrt(f); }   // || . ||_2 <= || . ||_F
+  if (eta < 0.25) *sigma = std::sqrt(1.0 + eta);                 // sigma_max(B)^2 <= 1 + ||B^T B - I||
+  else { double f = 0; for (double v : B) f += v * v; *sigma = std::sqrt(f); }   // || . ||_2 <= || . ||_F
   return B2_OK;
 }
 // Largest coordinate magnitude anything on the lookup path can take: global coordinates of every cloud (bounded from its pose
@@ -186,19 +200,19 @@ static double magnitude_bound(b2_icp* h) {
   return m;
 }
 
-// Grid of one cloud in its own frame.
+// Grid of one cloud in its index frame (the global frame as it was when the cloud was indexed).
 // Error budget of the lookup (why every target with fp32 d2 < r2 lies in the 2x2x2 block that k_nn_tiles searches):
 //   * d2 < r2 in the reference's fp32 arithmetic  =>  true distance of the fp32 global coordinates D <= d (1 + 2^-21);
 //   * the target's global row is fl(T l): |rounding| <= 3 * 2^-24 * M per coordinate (M = magnitude_bound);
-//   * the query is mapped by fl32(T^-1) with three FMAs: <= 7 * 2^-24 * M per coordinate, and the cell fraction is formed in
+//   * the query is mapped by fl32(F T^-1) with three FMAs: <= 7 * 2^-24 * M per coordinate, and the cell fraction is formed in
 //     fp32: <= 4 * 2^-24 * M;
-//   * cloud-frame distance <= sigma * global distance (pose_sigma).
-// Hence |cloud-frame offset per axis| <= d sigma + 32 * 2^-24 * M. margin = 64 * 2^-24 * M, the index is built for 2 M and
+//   * index-frame distance <= sigma * global distance (pose_sigma).
+// Hence |index-frame offset per axis| <= d sigma + 32 * 2^-24 * M. margin = 64 * 2^-24 * M, the index is built for 2 M and
 // sigma (1 + 1e-4) and rebuilt should an iteration exceed either. cell = 2 (d sigma + margin) (1 + 1e-4): from a query's
 // (computed) half of its cell, the far faces of the 2x2x2 block on that side are >= cell / 2 away.
-static int grid_for_cloud(Cloud* c, float max_dist, double sigma, double mtot, int* key_bits) {
+static int grid_for_cloud(Cloud* c, const float fmin[3], const float fmax[3], float max_dist, double sigma, double mtot, int* key_bits) {
   for (int d = 0; d < 3; ++d)
-    if (!std::isfinite(c->lmin[d]) || !std::isfinite(c->lmax[d]))
+    if (!std::isfinite(fmin[d]) || !std::isfinite(fmax[d]))
       return set_error(B2_ERR_ARG, "non-finite point coordinates (clouds must be dense, as the reference's is_dense path assumes)");
   c->index_sigma = sigma * (1.0 + 1e-4);
   c->index_mtot = 2.0 * mtot;
@@ -206,12 +220,16 @@ static int grid_for_cloud(Cloud* c, float max_dist, double sigma, double mtot, i
   double cell = 2.0 * ((double)max_dist * c->index_sigma + c->margin) * 1.0001;
   if (!(cell > 0.0)) cell = 1e-30;
   GridParams& g = c->g;
-  const double ext = std::max({(double)c->lmax[0] - c->lmin[0], (double)c->lmax[1] - c->lmin[1], (double)c->lmax[2] - c->lmin[2]});
-  cell = std::max(cell, ext / 2097000.0);    // keep every axis below 2^21 cells
-  g.ox = c->lmin[0]; g.oy = c->lmin[1]; g.oz = c->lmin[2];
+  // the box was measured on fp32 positions, the keys use double ones: pad by the margin (it bounds that difference many times over)
+  const double lo[3] = {fmin[0] - c->margin, fmin[1] - c->margin, fmin[2] - c->margin};
+  const double hi[3] = {fmax[0] + c->margin, fmax[1] + c->margin, fmax[2] + c->margin};
+  const double ext = std::max({hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]});
+  cell = std::max(cell, ext / 2096000.0);    // keep every axis below 2^21 cells
   auto dims = [&] {
     g.inv = 1.0 / cell;
-    g.nx = cell_of(c->lmax[0], g.ox, g.inv) + 1; g.ny = cell_of(c->lmax[1], g.oy, g.inv) + 1; g.nz = cell_of(c->lmax[2], g.oz, g.inv) + 1;
+    // origin on the lattice of multiples of the cell size: clouds indexed with the same radius and magnitude bound share one lattice
+    g.ox = std::floor(lo[0] / cell) * cell; g.oy = std::floor(lo[1] / cell) * cell; g.oz = std::floor(lo[2] / cell) * cell;
+    g.nx = (int)std::floor((hi[0] - g.ox) * g.inv) + 2; g.ny = (int)std::floor((hi[1] - g.oy) * g.inv) + 2; g.nz = (int)std::floor((hi[2] - g.oz) * g.inv) + 2;
   };
   dims();
   // keep the cell key below 2^47 so that (key << 3*kMinFineBits) fits 63 bits: enlarge the cells of enormous sparse clouds
@@ -220,9 +238,9 @@ static int grid_for_cloud(Cloud* c, float max_dist, double sigma, double mtot, i
   const unsigned long long maxkey = cell_key(g, g.nx - 1, g.ny - 1, g.nz - 1);
   int bits = 1;
   while (bits < 64 && (maxkey >> bits) != 0ull) ++bits;
-  // in-cell Morton resolution: as fine as fits 40 key bits, never below 5 bits per axis (dense cells are pruned through chunk boxes
-  // over this order)
-  g.fbits = std::max(kMinFineBits, std::min(kMaxFineBits, (40 - bits) / 3));
+  // in-cell Morton resolution: as fine as fits 42 key bits, never below 5 bits per axis (dense cells are pruned through chunk boxes
+  // over this order; the sort runs once per cloud, so a sixth radix pass is affordable)
+  g.fbits = std::max(kMinFineBits, std::min(kMaxFineBits, (42 - bits) / 3));
   *key_bits = bits + 3 * g.fbits;
   return B2_OK;
 }
@@ -255,14 +273,30 @@ static int build_index(b2_icp* h, Cloud* c, float max_dist, double sigma, double
   const size_t n = c->n;
   c->indexed = false;
   if (n == 0) { c->ncells = 0; c->index_d = max_dist; c->index_sigma = sigma * (1.0 + 1e-4); c->index_mtot = 2.0 * mtot; c->indexed = true; return B2_OK; }
+  // freeze the index frame at the current pose and measure the cloud's box in it
+  for (int r = 0; r < 3; ++r) { for (int k = 0; k < 3; ++k) c->F[4 * r + k] = c->T[r + 4 * k]; c->F[4 * r + 3] = c->T[12 + r]; }
+  float fmin[3] = {INFINITY, INFINITY, INFINITY}, fmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+  {
+    const int blocks = h->sms * 2;
+    B2_TRY(h->bbox_partial.ensure((size_t)blocks * 6 * sizeof(float)));
+    B2_TRY(h->pin_bbox.ensure((size_t)blocks * 6 * sizeof(float)));
+    k_bbox<<<blocks, 256, 0, h->stream>>>(c->local_xyz.as<float>(), n, mat4_of(c->T), h->bbox_partial.as<float>());
+    ++h->launches;
+    B2_CUDA(cudaMemcpyAsync(h->pin_bbox.p, h->bbox_partial.p, (size_t)blocks * 6 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    const float* p = h->pin_bbox.as<float>();
+    for (int b = 0; b < blocks; ++b)
+      for (int d = 0; d < 3; ++d) { fmin[d] = std::min(fmin[d], p[b * 6 + d]); fmax[d] = std::max(fmax[d], p[b * 6 + 3 + d]); }
+  }
   int key_bits = 0;
-  B2_TRY(grid_for_cloud(c, max_dist, sigma, mtot, &key_bits));
+  B2_TRY(grid_for_cloud(c, fmin, fmax, max_dist, sigma, mtot, &key_bits));
   const GridParams& g = c->g;
+  IndexFrame F; std::memcpy(F.f, c->F, sizeof(F.f));
   Scoped keys_in, keys_out, idx_in, perm;
   B2_TRY(keys_in.b.ensure(n * 8 + 16)); B2_TRY(keys_out.b.ensure(n * 8 + 16)); B2_TRY(idx_in.b.ensure(n * 4)); B2_TRY(perm.b.ensure(n * 4));
   B2_TRY(c->l_xyz.ensure(n * 16)); B2_TRY(c->l_nrm.ensure(n * 16)); B2_TRY(c->perm_inv.ensure(n * 4));
   B2_TRY(c->s_xyz.ensure(n * 16)); B2_TRY(c->s_nrm.ensure(n * 16));
-  k_keys<<<div_up(n, 256), 256, 0, h->stream>>>(c->local_xyz.as<float>(), n, g, keys_in.b.as<unsigned long long>(), idx_in.b.as<unsigned int>());
+  k_keys<<<div_up(n, 256), 256, 0, h->stream>>>(c->local_xyz.as<float>(), n, F, g, keys_in.b.as<unsigned long long>(), idx_in.b.as<unsigned int>());
   size_t tmp = 0;
   B2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys_in.b.as<unsigned long long>(), keys_out.b.as<unsigned long long>(),
                                           idx_in.b.as<unsigned int>(), perm.b.as<unsigned int>(), (long long)n, 0, key_bits, h->stream));
@@ -300,15 +334,16 @@ static int build_index(b2_icp* h, Cloud* c, float max_dist, double sigma, double
   return B2_OK;
 }
 
-// This iteration's map into a target's grid: position relative to the grid origin = T^-1 (q - t) - o, as one fp32 3x4.
+// This iteration's map into a target's grid: position relative to the grid origin = F T^-1 (q - t) - o, as one fp32 3x4.
 static int search_grid(const Cloud* c, SearchGrid* sg) {
   double A[9], Ai[9];
   linear_part(c->T, A);
   if (!invert3(A, Ai)) return set_error(B2_ERR_ARG, "pose is not invertible");
   const double t[3] = {c->T[12], c->T[13], c->T[14]}, o[3] = {c->g.ox, c->g.oy, c->g.oz};
   for (int r = 0; r < 3; ++r) {
-    for (int k = 0; k < 3; ++k) sg->m[4 * r + k] = (float)Ai[3 * r + k];
-    sg->m[4 * r + 3] = (float)(-(Ai[3 * r] * t[0] + Ai[3 * r + 1] * t[1] + Ai[3 * r + 2] * t[2]) - o[r]);
+    double B[3];
+    for (int k = 0; k < 3; ++k) { B[k] = c->F[4 * r] * Ai[k] + c->F[4 * r + 1] * Ai[3 + k] + c->F[4 * r + 2] * Ai[6 + k]; sg->m[4 * r + k] = (float)B[k]; }
+    sg->m[4 * r + 3] = (float)(c->F[4 * r + 3] - (B[0] * t[0] + B[1] * t[1] + B[2] * t[2]) - o[r]);
   }
   sg->inv = (float)c->g.inv; sg->cell = (float)c->g.cell;
   sg->inv_sigma = (float)((1.0 - 1e-6) / c->index_sigma);
@@ -440,8 +475,9 @@ static int ensure_indexes(b2_icp* h, float max_dist) {
   for (int i = 0; i < nc; ++i) {
     Cloud* c = impl_cloud(h, i);
     double sigma = 1.0;
-    B2_TRY(pose_sigma(c->T, &sigma));
+    if (c->indexed) B2_TRY(pose_sigma(c->T, c->F, &sigma));
     if (c->indexed && c->index_d == max_dist && sigma <= c->index_sigma && mtot <= c->index_mtot) continue;
+    B2_TRY(pose_sigma(c->T, nullptr, &sigma));                    // (re)built at the current pose: B = I up to rounding
     if (!built) { B2_CUDA(cudaEventCreate(&e0)); B2_CUDA(cudaEventCreate(&e1)); B2_CUDA(cudaEventRecord(e0, h->stream)); built = true; }
     B2_TRY(build_index(h, c, max_dist, sigma, mtot));
   }

