@@ -5,7 +5,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libeth3d_b200.so")
+LIB_PATH = os.environ.get("B2_LIB_PATH") or os.path.join(_HERE, "_build", "libeth3d_b200.so")   # (override: A/B builds of the library)
 _lib = None
 
 B2_OK = 0
@@ -28,7 +28,7 @@ class IcpStats(C.Structure):
                 ("ms_index", C.c_float), ("ms_search", C.c_float), ("ms_pack", C.c_float), ("ms_inner", C.c_float),
                 ("ms_total", C.c_float), ("ms_accum_kernel_avg", C.c_float), ("ms_search_kernel_avg", C.c_float),
                 ("search_launches", C.c_int32), ("search_algorithmic_bytes", C.c_uint64),
-                ("ms_index_build", C.c_float), ("reserved0", C.c_int32), ("search_work", C.c_uint64 * 5)]
+                ("ms_index_build", C.c_float), ("sparse_grids", C.c_int32), ("search_work", C.c_uint64 * 5)]
 
 
 class B2Error(RuntimeError):

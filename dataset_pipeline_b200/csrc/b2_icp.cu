@@ -44,8 +44,9 @@ struct Cloud {
   float index_d = 0.f;
   double index_sigma = 0, index_mtot = 0, margin = 0;
   GridParams g;
-  DevBuf l_xyz, l_nrm, perm_inv, table, occ; // cell-sorted cloud-frame rows (float4), original index -> sorted position, occupied cells (hash + bitmap)
-  bool has_occ = false;
+  DevBuf l_xyz, l_nrm, perm_inv;        // cell-sorted cloud-frame rows (float4), original index -> sorted position
+  bool dense = false;                   // layout of the occupied-cell index (k_nn_tiles<., DENSE>)
+  DevBuf rb, starts, table;             // DENSE: rank bitmap + cell starts; sparse: hash table of the occupied cells
   int log2size = 0;
   unsigned int ncells = 0;
   // ---- per outer iteration ----
@@ -312,21 +313,34 @@ static int build_index(b2_icp* h, Cloud* c, float max_dist, double sigma, double
   B2_CUDA(cudaMemcpyAsync(h->pin_counts.p, h->cell_counts.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
   B2_CUDA(cudaStreamSynchronize(h->stream));
   c->ncells = h->pin_counts.as<unsigned int>()[0];
-  int lg = 4;
-  while ((1ull << lg) < 2ull * c->ncells) ++lg;
-  c->log2size = lg;
-  B2_TRY(c->table.ensure(sizeof(HashEntry) << lg));
-  B2_CUDA(cudaMemsetAsync(c->table.p, 0xFF, sizeof(HashEntry) << lg, h->stream));
-  // one occupancy bit per grid cell while the grid is small enough (2^31 cells = 256 MB; a 10 x 8 x 3 m room at 2 cm is 4 MB)
+  // layout of the occupied-cell index: rank bitmap while the grid has at most 2^31 cells (8 B per 32 cells: 512 MB at the limit,
+  // 7.5 MB for a 10 x 8 x 3 m room at 2 cm), hash table of the occupied cells beyond
   const double cells_total = (double)g.nx * (double)g.ny * (double)g.nz;
-  c->has_occ = cells_total <= 2147483648.0;
-  if (c->has_occ) {
-    const size_t words = (size_t)(cells_total / 32.0) + 2;
-    B2_TRY(c->occ.ensure(words * 4));
-    B2_CUDA(cudaMemsetAsync(c->occ.p, 0, words * 4, h->stream));
+  c->dense = cells_total <= 2147483648.0;
+  if (c->dense) {
+    const size_t nwords = (size_t)(cells_total / 32.0) + 2;
+    const unsigned int nblocks = div_up(nwords, kWordsPerBlock);
+    Scoped block_sum, block_off;
+    B2_TRY(c->rb.ensure(nwords * 8)); B2_TRY(c->starts.ensure(((size_t)c->ncells + 2) * 4));
+    B2_TRY(block_sum.b.ensure((size_t)nblocks * 4)); B2_TRY(block_off.b.ensure((size_t)nblocks * 4 + 4));
+    B2_CUDA(cudaMemsetAsync(c->rb.p, 0, nwords * 8, h->stream));
+    k_mark_cells<<<div_up(n, 256), 256, 0, h->stream>>>(keys_out.b.as<unsigned long long>(), n, 3 * g.fbits, c->rb.as<uint2>());
+    k_word_counts<<<nblocks, 256, 0, h->stream>>>(c->rb.as<uint2>(), nwords, block_sum.b.as<unsigned int>());
+    k_scan_tiles<<<1, 1024, 0, h->stream>>>(block_sum.b.as<unsigned int>(), nblocks, block_off.b.as<unsigned int>(), block_off.b.as<unsigned int>() + nblocks);
+    k_word_prefix<<<nblocks, 256, 0, h->stream>>>(c->rb.as<uint2>(), nwords, block_off.b.as<unsigned int>());
+    k_cell_starts<<<div_up(n, 256), 256, 0, h->stream>>>(keys_out.b.as<unsigned long long>(), n, 3 * g.fbits, c->rb.as<uint2>(),
+                                                         c->starts.as<unsigned int>(), c->ncells);
+    h->launches += 5;
+    B2_CUDA(cudaStreamSynchronize(h->stream));   // block_sum / block_off go out of scope
+  } else {
+    int lg = 4;
+    while ((1ull << lg) < 2ull * c->ncells) ++lg;
+    c->log2size = lg;
+    B2_TRY(c->table.ensure(sizeof(HashEntry) << lg));
+    B2_CUDA(cudaMemsetAsync(c->table.p, 0xFF, sizeof(HashEntry) << lg, h->stream));
+    k_hash_cells<<<div_up(n, 256), 256, 0, h->stream>>>(keys_out.b.as<unsigned long long>(), n, c->table.as<HashEntry>(), lg, 3 * g.fbits);
+    ++h->launches;
   }
-  k_hash_cells<<<div_up(n, 256), 256, 0, h->stream>>>(keys_out.b.as<unsigned long long>(), n, c->table.as<HashEntry>(), lg, 3 * g.fbits,
-                                                      c->has_occ ? c->occ.as<unsigned int>() : nullptr);
   h->launches += 4;
   B2_CUDA(cudaStreamSynchronize(h->stream));     // the temporaries go out of scope
   c->index_d = max_dist;
@@ -352,7 +366,9 @@ static int search_grid(const Cloud* c, SearchGrid* sg) {
   sg->sy = c->g.nx; sg->sz = (long long)c->g.nx * (long long)c->g.ny;
   sg->log2size = c->log2size;
   sg->one = 1.0f;
-  sg->occ = c->has_occ ? c->occ.as<unsigned int>() : nullptr;
+  sg->occ = nullptr;
+  sg->rb = c->dense ? c->rb.as<uint2>() : nullptr;
+  sg->starts = c->dense ? c->starts.as<unsigned int>() : nullptr;
   return B2_OK;
 }
 
@@ -578,7 +594,8 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
       B2_TRY(d->order.ensure((size_t)ntiles * 16));
       unsigned int* cc = d->order.as<unsigned int>();
       if (d->order_src != d->src || d->order_tgt != d->tgt || d->order_tiles != ntiles || d->order_age >= 8) {
-        k_tile_cost<<<div_up(ntiles, 256), 256, 0, st>>>(S->s_xyz.as<float4>(), ns, T->table.as<HashEntry>(), sg, ntiles, cc, cc + ntiles);
+        if (T->dense) k_tile_cost<true><<<div_up(ntiles, 256), 256, 0, st>>>(S->s_xyz.as<float4>(), ns, T->table.as<HashEntry>(), sg, ntiles, cc, cc + ntiles);
+        else k_tile_cost<false><<<div_up(ntiles, 256), 256, 0, st>>>(S->s_xyz.as<float4>(), ns, T->table.as<HashEntry>(), sg, ntiles, cc, cc + ntiles);
         size_t tmp2 = 0;
         B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp2, cc, cc + 2 * (size_t)ntiles, cc + ntiles, cc + 3 * (size_t)ntiles, (int)ntiles, 0, 32, st));
         B2_TRY(cub_tmp.ensure(tmp2));
@@ -589,14 +606,14 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
       ++d->order_age;
       order = cc + 3 * (size_t)ntiles;
     }
-    if (h->work_stats)
-      k_nn_tiles<true><<<ntiles, kTile, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(), T->box2.as<Aabb>(),
-                                                 T->table.as<HashEntry>(), sg, r2, d->key.as<unsigned long long>(), d->tile_count.as<unsigned int>(),
-                                                 h->work_dev.as<unsigned long long>(), order);
-    else
-      k_nn_tiles<false><<<ntiles, kTile, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(), T->box2.as<Aabb>(),
-                                                  T->table.as<HashEntry>(), sg, r2, d->key.as<unsigned long long>(), d->tile_count.as<unsigned int>(),
-                                                  nullptr, order);
+    B2_CUDA(cudaMemsetAsync(d->tile_count.p, 0, (size_t)ntiles * 4, st));
+#define B2_LAUNCH_NN(STATS, DENSE)                                                                                                  \
+  k_nn_tiles<STATS, DENSE><<<ntiles, kTile, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(), T->box2.as<Aabb>(),  \
+                                                     T->table.as<HashEntry>(), sg, r2, d->key.as<unsigned long long>(),                 \
+                                                     d->tile_count.as<unsigned int>(), h->work_stats ? h->work_dev.as<unsigned long long>() : nullptr, order)
+    if (h->work_stats) { if (T->dense) B2_LAUNCH_NN(true, true); else B2_LAUNCH_NN(true, false); }
+    else { if (T->dense) B2_LAUNCH_NN(false, true); else B2_LAUNCH_NN(false, false); }
+#undef B2_LAUNCH_NN
     B2_CUDA(cudaEventRecord(n1, st));
     h->nn_events.emplace_back(n0, n1);
     h->stats.search_algorithmic_bytes += 12ull * ns + 12ull * T->n;
@@ -793,6 +810,7 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   h->stats.ms_search_kernel_avg = h->nn_events.empty() ? 0.f : (float)((h->nsearch > 1 ? (double)h->stats.ms_search : nn) / h->nn_events.size());
   h->stats.search_launches = (int)h->nn_events.size();
   h->stats.ms_index_build = h->ms_index_build;
+  for (int i = 0; i < nc; ++i) if (impl_cloud(h, i)->n && !impl_cloud(h, i)->dense) ++h->stats.sparse_grids;
   if (h->work_stats) {
     B2_CUDA(cudaMemcpy(h->stats.search_work, h->work_dev.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   }
@@ -877,7 +895,7 @@ int b2_icp_destroy(b2_icp* h) {
   cudaStreamSynchronize(h->stream);
   auto free_cloud = [](Cloud* c) {
     if (!c) return;
-    for (DevBuf* b : {&c->local_xyz, &c->local_nrm, &c->l_xyz, &c->l_nrm, &c->perm_inv, &c->occ, &c->s_xyz, &c->s_nrm, &c->table, &c->box1, &c->box2}) b->release();
+    for (DevBuf* b : {&c->local_xyz, &c->local_nrm, &c->l_xyz, &c->l_nrm, &c->perm_inv, &c->rb, &c->starts, &c->s_xyz, &c->s_nrm, &c->table, &c->box1, &c->box2}) b->release();
   };
   for (auto& c : h->movable) free_cloud(c.get());
   free_cloud(h->fixed.get());

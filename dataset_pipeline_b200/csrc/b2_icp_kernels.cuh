@@ -17,6 +17,8 @@
 //                          with the reference's upper-triangle quirk (impl.h:82-113 + :226)
 // All of these are HBM / gather bound integer+fp32+fp64 streaming work: no tensor cores.
 #pragma once
+#include <type_traits>
+
 #include "b2_common.cuh"
 
 namespace b2 {
@@ -202,7 +204,7 @@ __device__ __forceinline__ unsigned int hash_claim(HashEntry* __restrict__ table
   }
 }
 __global__ void __launch_bounds__(256) k_hash_cells(const unsigned long long* __restrict__ keys, size_t n, HashEntry* __restrict__ table,
-                                                    int log2size, int kFineBits, unsigned int* __restrict__ occ) {
+                                                    int log2size, int kFineBits) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const unsigned long long key = keys[j] >> kFineBits;
@@ -210,7 +212,6 @@ __global__ void __launch_bounds__(256) k_hash_cells(const unsigned long long* __
   const bool tail = j + 1 == n || (keys[j + 1] >> kFineBits) != key;
   if (!head && !tail) return;
   const unsigned int s = hash_claim(table, log2size, key);
-  if (head && occ) atomicOr(occ + (key >> 5), 1u << (unsigned int)(key & 31ull));   // dense occupancy bitmap of the grid (small grids only)
   if (head) table[s].begin = (unsigned int)j;
   if (tail) table[s].end = (unsigned int)(j + 1);
 }
@@ -249,10 +250,23 @@ __device__ __forceinline__ bool hash_find(const HashEntry* __restrict__ table, i
 // so min() over keys implements "d2 < best, or d2 == best and lower index" independently of the visiting order; the initial key
 // (r2 bits << 32) | 0 rejects d2 == r2 for every index (the radius test is strict) and doubles as the "no match" value.
 // ------------------------------------------------------------------------------------------------------------------
-static constexpr int kTile = 256;          // queries per CTA
-static constexpr unsigned int kInlineCell = 64u;   // cells up to this many points are scanned without chunk boxes
-static constexpr unsigned int kCoopCell = 256u;    // cells above this many points are scanned by a whole warp (scan_cell_warp)
-static constexpr unsigned int kDenseCap = 384u;    // dense-cell queue entries per tile (overflow: the thread scans the cell itself)
+// (the B2_K3_* macros exist for A/B builds: tools/k3_variants.sh)
+#ifndef B2_K3_TILE
+#define B2_K3_TILE 256
+#endif
+#ifndef B2_K3_INLINE
+#define B2_K3_INLINE 64
+#endif
+#ifndef B2_K3_COOP
+#define B2_K3_COOP 256
+#endif
+#ifndef B2_K3_MINB
+#define B2_K3_MINB 7
+#endif
+static constexpr int kTile = B2_K3_TILE;   // queries per CTA
+static constexpr unsigned int kInlineCell = B2_K3_INLINE;   // cells up to this many points are scanned without chunk boxes
+static constexpr unsigned int kCoopCell = B2_K3_COOP;       // cells above this many points are scanned by a whole warp (scan_cell_warp)
+static constexpr unsigned int kDenseCap = 48u;     // dense-cell queue entries per warp (overflow: the thread scans the cell itself)
 
 struct SearchGrid {              // a target cloud's static grid + this iteration's global -> cloud-frame map
   float m[12];                   // row-major 3x4: position relative to the grid origin = m[4r..4r+2] . q + m[4r+3]
@@ -262,7 +276,9 @@ struct SearchGrid {              // a target cloud's static grid + this iteratio
   long long sy, sz;              // cell key = cz*sz + cy*sy + cx
   int log2size;
   float one;                     // 1.0f at run time (see B2_NN_KEY)
-  const unsigned int* occ;       // one bit per grid cell: occupied (nullptr for grids above 2^31 cells: every neighbour is probed)
+  const unsigned int* occ;       // sparse layout: unused (nullptr: every neighbour is probed in the hash table)
+  const uint2* rb;               // DENSE layout: rank bitmap, {occupancy bits, occupied cells before this word} per 32 cells
+  const unsigned int* starts;    // DENSE layout: first sorted point of every occupied cell, + the total
 };
 __device__ __forceinline__ bool cell_occupied(const SearchGrid& g, long long key) {
   return !g.occ || ((__ldg(g.occ + (key >> 5)) >> (unsigned int)(key & 31ll)) & 1u);
@@ -409,9 +425,33 @@ __device__ __forceinline__ CellLookup lookup_cell(const SearchGrid& g, const flo
   return c;
 }
 
+// Cell lookup. Two index layouts, chosen per cloud when it is indexed:
+//   DENSE  (grids up to 2^31 cells — a 10 x 8 x 3 m room at 2 cm has 3 * 10^7): a rank bitmap over the grid, one {bits, prefix}
+//          pair per 32 cells; an occupied cell's rank = prefix + popc(bits below it) indexes `starts` (first point of every occupied
+//          cell in sorted order, + the total). One 8 B load answers "occupied?" and "where?"; no probing, 32-bit cell keys; ~10 MB
+//          for a 10 M-point room scan, so the whole index stays in L2.
+//   sparse (anything larger): open-addressing hash of the occupied cells, 64-bit keys.
+__device__ __forceinline__ bool dense_rank(const SearchGrid& g, int key, unsigned int* rank) {
+  const uint2 w = __ldg(g.rb + (key >> 5));
+  const unsigned int bit = 1u << (key & 31);
+  *rank = w.y + __popc(w.x & (bit - 1u));
+  return (w.x & bit) != 0u;
+}
+template <bool DENSE>
+__device__ __forceinline__ bool find_cell(const SearchGrid& g, const HashEntry* __restrict__ table, long long key, unsigned int* b, unsigned int* e) {
+  if (DENSE) {
+    unsigned int rank;
+    if (!dense_rank(g, (int)key, &rank)) return false;
+    *b = __ldg(g.starts + rank); *e = __ldg(g.starts + rank + 1);
+    return true;
+  }
+  return hash_find(table, g.log2size, (unsigned long long)key, b, e);
+}
+
 // Launch-order heuristic for K3: estimated cost of each tile = target population of the cells of eight of its queries. The
 // tiles are then issued longest-first (ids sorted by descending cost), so the expensive ones (queries inside the target's
 // scanner-zenith clusters) overlap with the rest instead of forming the tail of the launch.
+template <bool DENSE>
 __global__ void __launch_bounds__(256) k_tile_cost(const float4* __restrict__ src, size_t ns, const HashEntry* __restrict__ table, SearchGrid g,
                                                    unsigned int ntiles, unsigned int* __restrict__ cost, unsigned int* __restrict__ ids) {
   const unsigned int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -424,153 +464,186 @@ __global__ void __launch_bounds__(256) k_tile_cost(const float4* __restrict__ sr
     const CellLookup L = lookup_cell(g, q);
     if ((unsigned int)L.cx >= (unsigned int)g.nx || (unsigned int)L.cy >= (unsigned int)g.ny || (unsigned int)L.cz >= (unsigned int)g.nz) continue;
     unsigned int b, e;
-    if (hash_find(table, g.log2size, (unsigned long long)((long long)L.cz * g.sz + (long long)L.cy * g.sy + L.cx), &b, &e)) total += e - b;
+    if (find_cell<DENSE>(g, table, (long long)L.cz * g.sz + (long long)L.cy * g.sy + L.cx, &b, &e)) total += e - b;
   }
   cost[c] = total; ids[c] = c;
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(kTile) k_nn_tiles(const float4* __restrict__ src, size_t ns, const float4* __restrict__ tgt,
+// Per-warp working set in shared memory (a CTA is kTile / 32 independent warps; nothing in K3 synchronises the CTA).
+template <typename key_t>
+struct __align__(128) WarpTile {
+  float4 q[32];                            // the warp's 32 query rows (its own bulk copy)
+  unsigned long long best[32];             // per query: best (d2, index) key
+  key_t item_cell[32 * 7];                 // work queue of (query, neighbour cell): DENSE: the cell's rank; sparse: the cell's key
+  uint2 dense_range[kDenseCap];            // dense-cell queue: candidate range [x, y) ...
+  unsigned char item_q[32 * 7];
+  unsigned char dense_q[kDenseCap];        // ... and the query it belongs to
+  unsigned long long bar;
+};
+
+template <bool STATS, bool DENSE>
+__global__ void __launch_bounds__(kTile, B2_K3_MINB) k_nn_tiles(const float4* __restrict__ src, size_t ns, const float4* __restrict__ tgt,
                                                     const Aabb* __restrict__ box1, const Aabb* __restrict__ box2,
                                                     const HashEntry* __restrict__ table, SearchGrid g, float r2,
                                                     unsigned long long* __restrict__ out_key, unsigned int* __restrict__ tile_count,
                                                     unsigned long long* __restrict__ work, const unsigned int* __restrict__ order) {
-  __shared__ __align__(128) float4 sq[kTile];                 // the tile's query rows (bulk copy)
-  __shared__ unsigned long long s_best[kTile];                // per query: best (d2, index) key
-  __shared__ long long s_cell[kTile];                         // per query: key of its own cell (signed: may lie just outside the grid)
-  __shared__ unsigned short s_items[kTile * 7];               // work queue: (query << 6) | (upper halves << 3) | neighbour
-  __shared__ unsigned int s_nitems, s_ndense;
-  __shared__ uint2 s_dense_range[kDenseCap];                  // dense-cell queue: candidate range [x, y) ...
-  __shared__ unsigned char s_dense_q[kDenseCap];              // ... and the query it belongs to
-  __shared__ __align__(8) unsigned long long bar;
-  const unsigned int t = threadIdx.x, lane = t & 31u;
+  typedef typename std::conditional<DENSE, int, long long>::type key_t;   // cell key: 32 bits suffice for a dense grid
+  __shared__ WarpTile<key_t> s_warp[kTile / 32];
+  const unsigned int lane = threadIdx.x & 31u;
+  WarpTile<key_t>& W = s_warp[threadIdx.x >> 5];
   const unsigned int tile = order ? order[blockIdx.x] : blockIdx.x;
-  const size_t j0 = (size_t)tile * kTile;
-  const unsigned int cnt = (unsigned int)min((size_t)kTile, ns - j0);
-  if (t == 0) {
-    s_nitems = 0u; s_ndense = 0u;
-    mbar_init(&bar, 1);
+  const size_t j0 = (size_t)tile * kTile + (threadIdx.x & ~31u);          // this warp's first query
+  if (j0 >= ns) return;                                                   // (whole warp)
+  const unsigned int cnt = (unsigned int)min((size_t)32, ns - j0);
+  if (lane == 0) {
+    mbar_init(&W.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&W.bar, cnt * 16u);
+    bulk_g2s(W.q, src + j0, cnt * 16u, &W.bar);
   }
-  __syncthreads();
-  if (t == 0) { mbar_expect_tx(&bar, cnt * 16u); bulk_g2s(sq, src + j0, cnt * 16u, &bar); }
-  mbar_wait(&bar, 0);
+  __syncwarp();
+  mbar_wait(&W.bar, 0);
 
   // ---- A: own cell per thread ----
   const unsigned long long init = (unsigned long long)__float_as_uint(r2) << 32;
   unsigned long long best = init;
-  long long base = 0;
-  unsigned int todo = 0u, upper = 0u;
+  key_t base = 0, dxk = 0, dyk = 0, dzk = 0;
+  unsigned int todo = 0u;
+  bool own_dense = false;
+  uint2 own_range = make_uint2(0u, 0u);
   SearchWork wk = {0u, 0u, 0u, 0u};
-  if (t < cnt) {
-    const float4 q = sq[t];
+  if (lane < cnt) {
+    const float4 q = W.q[lane];
     const CellLookup L = lookup_cell(g, q);
-    upper = L.upper;
-    base = (long long)L.cz * g.sz + (long long)L.cy * g.sy + L.cx;
+    const unsigned int upper = L.upper;
+    base = (key_t)((key_t)L.cz * (key_t)g.sz + (key_t)L.cy * (key_t)g.sy + (key_t)L.cx);
+    dxk = (upper & 1u) ? (key_t)1 : (key_t)-1;
+    dyk = (upper & 2u) ? (key_t)g.sy : (key_t)-g.sy;
+    dzk = (upper & 4u) ? (key_t)g.sz : (key_t)-g.sz;
     const bool x0 = (unsigned int)L.cx < (unsigned int)g.nx, y0 = (unsigned int)L.cy < (unsigned int)g.ny, z0 = (unsigned int)L.cz < (unsigned int)g.nz;
     const bool x1 = (unsigned int)(L.cx + ((upper & 1u) ? 1 : -1)) < (unsigned int)g.nx;
     const bool y1 = (unsigned int)(L.cy + ((upper & 2u) ? 1 : -1)) < (unsigned int)g.ny;
     const bool z1 = (unsigned int)(L.cz + ((upper & 4u) ? 1 : -1)) < (unsigned int)g.nz;
-    if (x0 && y0 && z0 && cell_occupied(g, base)) {
+    if (x0 && y0 && z0) {
       unsigned int b, e;
-      if (hash_find(table, g.log2size, (unsigned long long)base, &b, &e)) {
-        bool queued = false;
+      if (find_cell<DENSE>(g, table, base, &b, &e)) {
         if (e - b > kCoopCell) {
-          // dense own cell: a whole warp scans it later; 16 strided candidates now, so that the neighbours are still pruned
-          const unsigned int slot = atomicAdd(&s_ndense, 1u);
-          if (slot < kDenseCap) {
-            s_dense_range[slot] = make_uint2(b, e); s_dense_q[slot] = (unsigned char)t; queued = true;
-            const unsigned int stride = (e - b) / 16u;
-            for (unsigned int p = b; p < b + 16u * stride; p += 4u * stride) {
-              const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + p + stride), t2 = __ldg(tgt + p + 2u * stride), t3 = __ldg(tgt + p + 3u * stride);
-              const float one = g.one;
-              B2_NN_KEY(t0) B2_NN_KEY(t1) B2_NN_KEY(t2) B2_NN_KEY(t3)
-            }
+          // dense own cell: the whole warp scans it in phase B2; 16 strided candidates now, so that the neighbours are still pruned
+          own_dense = true; own_range = make_uint2(b, e);
+          const unsigned int stride = (e - b) / 16u;
+          for (unsigned int p = b; p < b + 16u * stride; p += 4u * stride) {
+            const float4 t0 = __ldg(tgt + p), t1 = __ldg(tgt + p + stride), t2 = __ldg(tgt + p + 2u * stride), t3 = __ldg(tgt + p + 3u * stride);
+            const float one = g.one;
+            B2_NN_KEY(t0) B2_NN_KEY(t1) B2_NN_KEY(t2) B2_NN_KEY(t3)
           }
+        } else {
+          scan_cell(tgt, box1, box2, b, e, q, g.one, best, wk);
         }
-        if (!queued) scan_cell(tgt, box1, box2, b, e, q, g.one, best, wk);
       }
     }
-    // neighbours worth a visit: inside the grid, nearest face not farther than the best match, and OCCUPIED (one bit per cell of
-    // the target's grid: most neighbour cells of a surface scan are empty, and an empty cell costs a full unsuccessful hash probe)
+    // neighbours worth a visit: inside the grid, nearest face not farther than the best match, and OCCUPIED (most neighbour cells
+    // of a surface scan are empty; the test is one bitmap word)
     const float bd = key_d2(best);
 #pragma unroll
     for (int c = 1; c < 8; ++c) {
       const bool valid = ((c & 1) ? x1 : x0) && ((c & 2) ? y1 : y0) && ((c & 4) ? z1 : z0);
       const float lb = fadd(fadd((c & 1) ? L.ex2 : 0.f, (c & 2) ? L.ey2 : 0.f), (c & 4) ? L.ez2 : 0.f);
       if (valid && !(lb > bd)) {
-        const long long key = base + ((c & 1) ? ((upper & 1u) ? 1ll : -1ll) : 0ll) + ((c & 2) ? ((upper & 2u) ? g.sy : -g.sy) : 0ll) +
-                              ((c & 4) ? ((upper & 4u) ? g.sz : -g.sz) : 0ll);
-        if (cell_occupied(g, key)) todo |= 1u << c;
+        const key_t key = base + ((c & 1) ? dxk : (key_t)0) + ((c & 2) ? dyk : (key_t)0) + ((c & 4) ? dzk : (key_t)0);
+        bool occ = true;
+        if (DENSE) { const uint2 w = __ldg(g.rb + ((int)key >> 5)); occ = (w.x >> ((int)key & 31)) & 1u; }
+        if (occ) todo |= 1u << c;
       }
     }
   }
+  // queue slots by prefix sums over the warp: no atomics, the queues are private to the warp
+  unsigned int ndense;
   {
-    // warp-aggregated append: one shared atomic per warp
+    const unsigned int dm = __ballot_sync(0xffffffffu, own_dense);
+    ndense = __popc(dm);                                                // <= 32 < kDenseCap
+    if (own_dense) { const unsigned int slot = __popc(dm & ((1u << lane) - 1u)); W.dense_range[slot] = own_range; W.dense_q[slot] = (unsigned char)lane; }
+  }
+  unsigned int nitems;
+  {
     const unsigned int mine = __popc(todo);
     unsigned int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned int)o) incl += v; }
-    const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
-    unsigned int at = 0u;
-    if (lane == 31u && total) at = atomicAdd(&s_nitems, total);
-    at = __shfl_sync(0xffffffffu, at, 31) + incl - mine;
+    nitems = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned int at = incl - mine;
     while (todo) {
       const unsigned int c = __ffs(todo) - 1u;
       todo &= todo - 1u;
-      s_items[at++] = (unsigned short)((t << 6) | (upper << 3) | c);
+      const key_t key = base + ((c & 1u) ? dxk : (key_t)0) + ((c & 2u) ? dyk : (key_t)0) + ((c & 4u) ? dzk : (key_t)0);
+      if (DENSE) { unsigned int rank; dense_rank(g, (int)key, &rank); W.item_cell[at] = (key_t)rank; }   // (the word is in L1 from the test above)
+      else W.item_cell[at] = key;
+      W.item_q[at] = (unsigned char)lane;
+      ++at;
     }
   }
-  s_best[t] = best;
-  s_cell[t] = base;
-  __syncthreads();
+  W.best[lane] = best;
+  __syncwarp();
 
   // ---- B: neighbour cells, one queue item per lane ----
-  const unsigned int nitems = s_nitems;
-  for (unsigned int i = t; i < nitems; i += kTile) {
-    const unsigned int it = s_items[i], ql = it >> 6, up = (it >> 3) & 7u, c = it & 7u;
-    const float4 q = sq[ql];
-    long long key = s_cell[ql];
-    if (c & 1u) key += (up & 1u) ? 1 : -1;
-    if (c & 2u) key += (up & 2u) ? g.sy : -g.sy;
-    if (c & 4u) key += (up & 4u) ? g.sz : -g.sz;
-    unsigned int b, e;
-    if (!hash_find(table, g.log2size, (unsigned long long)key, &b, &e)) continue;
-    if (e - b > kCoopCell) {
-      const unsigned int slot = atomicAdd(&s_ndense, 1u);
-      if (slot < kDenseCap) { s_dense_range[slot] = make_uint2(b, e); s_dense_q[slot] = (unsigned char)ql; continue; }
+  for (unsigned int i0 = 0; i0 < nitems; i0 += 32u) {
+    const unsigned int i = i0 + lane;
+    bool dense_item = false;
+    uint2 range = make_uint2(0u, 0u);
+    unsigned int ql = 0;
+    if (i < nitems) {
+      ql = W.item_q[i];
+      const key_t cell = W.item_cell[i];
+      unsigned int b = 0, e = 0;
+      bool found = true;
+      if (DENSE) { b = __ldg(g.starts + (unsigned int)cell); e = __ldg(g.starts + (unsigned int)cell + 1u); }
+      else found = hash_find(table, g.log2size, (unsigned long long)cell, &b, &e);
+      if (found) {
+        if (e - b > kCoopCell) { dense_item = true; range = make_uint2(b, e); }
+        else {
+          const float4 q = W.q[ql];
+          const unsigned long long seen = W.best[ql];     // possibly lowered by another item of this query already: a tighter start
+          unsigned long long bk = seen;
+          scan_cell(tgt, box1, box2, b, e, q, g.one, bk, wk);
+          if (bk < seen) atomicMin(&W.best[ql], bk);
+        }
+      }
     }
-    const unsigned long long seen = s_best[ql];     // possibly lowered by another item of this query already: a tighter start
-    unsigned long long bk = seen;
-    scan_cell(tgt, box1, box2, b, e, q, g.one, bk, wk);
-    if (bk < seen) atomicMin(&s_best[ql], bk);
+    const unsigned int dm = __ballot_sync(0xffffffffu, dense_item);
+    if (dense_item) {
+      const unsigned int slot = ndense + __popc(dm & ((1u << lane) - 1u));
+      if (slot < kDenseCap) { W.dense_range[slot] = range; W.dense_q[slot] = (unsigned char)ql; }
+      else {                                             // queue full: this lane walks the cell itself
+        const float4 q = W.q[ql];
+        const unsigned long long seen = W.best[ql];
+        unsigned long long bk = seen;
+        scan_cell(tgt, box1, box2, range.x, range.y, q, g.one, bk, wk);
+        if (bk < seen) atomicMin(&W.best[ql], bk);
+      }
+    }
+    ndense = min(ndense + __popc(dm), kDenseCap);
   }
-  __syncthreads();
+  __syncwarp();
 
-  // ---- B2: dense cells, one queue entry per WARP ----
-  const unsigned int ndense = min(s_ndense, kDenseCap);
-  if (ndense) {
-    for (unsigned int i = t >> 5; i < ndense; i += kTile / 32) {
-      const uint2 r = s_dense_range[i];
-      const unsigned int ql = s_dense_q[i];
-      const float4 q = sq[ql];
-      const unsigned long long seen = s_best[ql];
-      const unsigned long long bk = scan_cell_warp(tgt, box1, box2, r.x, r.y, q, g.one, seen, lane, wk);
-      if (lane == 0u && bk < seen) atomicMin(&s_best[ql], bk);
-      if (lane == 0u) ++wk.cells;
-    }
-    __syncthreads();
+  // ---- B2: dense cells, the whole warp on one queue entry at a time ----
+  for (unsigned int i = 0; i < ndense; ++i) {
+    const uint2 r = W.dense_range[i];
+    const unsigned int ql = W.dense_q[i];
+    const float4 q = W.q[ql];
+    const unsigned long long seen = W.best[ql];
+    const unsigned long long bk = scan_cell_warp(tgt, box1, box2, r.x, r.y, q, g.one, seen, lane, wk);
+    if (lane == 0u) { if (bk < seen) W.best[ql] = bk; ++wk.cells; }
+    __syncwarp();
   }
 
   // ---- C: results ----
   bool matched = false;
-  if (t < cnt) {
-    best = s_best[t];
+  if (lane < cnt) {
+    best = W.best[lane];
     matched = best < init;
-    out_key[j0 + t] = best;
+    out_key[j0 + lane] = best;
   }
-  const int nm = __syncthreads_count(matched);
-  if (t == 0) tile_count[tile] = (unsigned int)nm;
+  const unsigned int mm = __ballot_sync(0xffffffffu, matched);
+  if (lane == 0u && mm) atomicAdd(tile_count + tile, (unsigned int)__popc(mm));   // (zeroed by the host before the launch)
   if (STATS) {
     // per-launch totals: candidates tested, level-1 / level-2 box tests, cells scanned, queue items
     unsigned int v[4] = {wk.points, wk.box1, wk.box2, wk.cells};
@@ -580,8 +653,57 @@ __global__ void __launch_bounds__(kTile) k_nn_tiles(const float4* __restrict__ s
       for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
       if (lane == 0u && x) atomicAdd(work + k, (unsigned long long)x);
     }
-    if (t == 0 && nitems) atomicAdd(work + 4, (unsigned long long)nitems);
+    if (lane == 0u && nitems) atomicAdd(work + 4, (unsigned long long)nitems);
   }
+}
+
+// ---- one-time construction of the rank bitmap (DENSE layout) ----
+__global__ void __launch_bounds__(256) k_mark_cells(const unsigned long long* __restrict__ keys, size_t n, int kFineBits, uint2* __restrict__ rb) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const unsigned long long key = keys[j] >> kFineBits;
+  if (j != 0 && (keys[j - 1] >> kFineBits) == key) return;
+  atomicOr(&rb[key >> 5].x, 1u << (unsigned int)(key & 31ull));
+}
+static constexpr unsigned int kWordsPerBlock = 2048;   // bitmap words per block of the two-level prefix
+__global__ void __launch_bounds__(256) k_word_counts(const uint2* __restrict__ rb, size_t nwords, unsigned int* __restrict__ block_sum) {
+  __shared__ unsigned int s[8];
+  const size_t w0 = (size_t)blockIdx.x * kWordsPerBlock;
+  unsigned int c = 0;
+  for (unsigned int i = threadIdx.x; i < kWordsPerBlock; i += 256) if (w0 + i < nwords) c += __popc(rb[w0 + i].x);
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { unsigned int v = 0; for (int i = 0; i < 8; ++i) v += s[i]; block_sum[blockIdx.x] = v; }
+}
+__global__ void __launch_bounds__(256) k_word_prefix(uint2* __restrict__ rb, size_t nwords, const unsigned int* __restrict__ block_off) {
+  // block-wide exclusive scan of the 2048 word counts of this block (8 consecutive words per thread), + the block's offset
+  __shared__ unsigned int s[256];
+  const size_t w0 = (size_t)blockIdx.x * kWordsPerBlock + (size_t)threadIdx.x * 8;
+  unsigned int c[8], sum = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i] = w0 + i < nwords ? __popc(rb[w0 + i].x) : 0u; sum += c[i]; }
+  s[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    const unsigned int v = threadIdx.x >= (unsigned int)o ? s[threadIdx.x - o] : 0u;
+    __syncthreads();
+    s[threadIdx.x] += v;
+    __syncthreads();
+  }
+  unsigned int run = block_off[blockIdx.x] + s[threadIdx.x] - sum;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { if (w0 + i < nwords) rb[w0 + i].y = run; run += c[i]; }
+}
+__global__ void __launch_bounds__(256) k_cell_starts(const unsigned long long* __restrict__ keys, size_t n, int kFineBits, const uint2* __restrict__ rb,
+                                                     unsigned int* __restrict__ starts, unsigned int ncells) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  if (j == 0) starts[ncells] = (unsigned int)n;
+  const unsigned long long key = keys[j] >> kFineBits;
+  if (j != 0 && (keys[j - 1] >> kFineBits) == key) return;
+  const uint2 w = rb[key >> 5];
+  starts[w.y + __popc(w.x & ((1u << (unsigned int)(key & 31ull)) - 1u))] = (unsigned int)j;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -98,7 +98,7 @@ typedef struct b2_icp_stats {
   int32_t search_launches;      /* pair-directions searched on this rank */
   uint64_t search_algorithmic_bytes; /* sum over those launches of 12*Q + 8*Q_matched + 12*T */
   float ms_index_build;         /* one-time static index builds that fell into this outer iteration (0 once every cloud is indexed) */
-  int32_t reserved0;
+  int32_t sparse_grids;         /* clouds whose occupied-cell index uses the hash layout (grid above 2^31 cells) instead of the rank bitmap */
   uint64_t search_work[5];      /* B2_K3_WORK=1 only: candidates tested, level-1 box tests, level-2 box tests, cells scanned, queue items */
 } b2_icp_stats;
 

@@ -178,3 +178,21 @@ def test_index_survives_pose_updates_and_radius_change(b2, oracle, monkeypatch):
         for (s, t, q1, m1, d1), (_, _, q2, m2, d2) in zip(g.pairs(), o.pairs()):
             assert np.array_equal(q1, q2) and np.array_equal(m1, m2) and np.array_equal(d1, d2), "iteration %d pair %d->%d" % (it, s, t)
     assert builds == [True, False, False, True, False, True]
+
+
+def test_sparse_grid_uses_the_hash_layout(b2, oracle, monkeypatch):
+    """A 30 m cube at d = 0.01 is 3.4 * 10^9 grid cells: above the rank-bitmap limit, so the occupied cells are hashed. Same bar."""
+    rng = np.random.default_rng(21)
+    tgt = rng.uniform(0, 30, (200000, 3)).astype(np.float32)
+    tgt[:20000] = (np.array([11.0, 7.0, 23.0]) + rng.normal(0, 0.05, (20000, 3))).astype(np.float32)      # a dense blob too
+    src = np.concatenate([tgt[rng.choice(len(tgt), 100000, replace=False)] + rng.normal(0, 0.003, (100000, 3)),
+                          rng.uniform(0, 30, (50000, 3))]).astype(np.float32)
+    Rs, Rt = _rot(0.1, 0.2, -0.3), _rot(-0.2, 0.05, 0.4)
+    ts, tt = np.array([1.0, 2.0, 3.0]), np.array([-2.0, 0.5, 1.5])
+    src_l = ((src.astype(np.float64) - ts) @ Rs).astype(np.float32)
+    tgt_l = ((tgt.astype(np.float64) - tt) @ Rt).astype(np.float32)
+    st, seen = _search_both_ways(b2, oracle, [(src_l, _unit(rng, len(src))), (tgt_l, _unit(rng, len(tgt)))], [_pose(Rs, ts), _pose(Rt, tt)],
+                                 0.01, monkeypatch)
+    assert (0, 1) in seen and (1, 0) in seen
+    assert st["sparse_grids"] == 2
+    assert st["num_correspondences"] > 50000
