@@ -6,6 +6,15 @@
 
 A step = one ICP outer iteration = one `icp.Run(d, it, 1, thr)` as issued by icp_scan_aligner.cc:343 (global-frame transform,
 all pair-direction correspondence searches, the complete inner LM loop of PointToPlaneICPImpl::compute, pose composition).
+
+Which iteration. Both arms time the SAME, fully specified step: an outer iteration started from `--state` (default "gt": the
+scanner poses of the synthetic scene, i.e. the refinement iterations an alignment spends most of its outer loop in; the poses
+move, Run() does not report convergence). The B200 arm puts the poses back to that state before every timed step; the reference
+arm executes that one iteration for real, once, on the full 8 x 10M scans (steps: 1) — its serial accumulate / cost loops take
+minutes per outer iteration, and an iteration started from the 5 mm / 0.1 deg perturbed poses ("start", dozens of LM iterations)
+would take it the better part of an hour. The B200 arm additionally reports, under "extra", the whole alignment from the
+perturbed start (iterations 0..k until Run() reports convergence: per-iteration LM counts and times) and the post-convergence
+iteration.
 Prints ONE JSON line (rank 0). Data: synthetic room scans (dataset_pipeline_b200/synth), inputs far larger than L2.
 """
 import argparse
@@ -14,7 +23,6 @@ import math
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -25,6 +33,7 @@ sys.path.insert(0, ROOT)
 METRIC = "ICP iterations/sec (8x10M-pt scans, point-to-plane, d=0.01)"
 UNIT = "iterations/s"
 CACHE = os.environ.get("B2_SYNTH_CACHE", "/tmp/b2_synth_cache")
+THR = 1e-10
 
 
 def parse():
@@ -37,10 +46,21 @@ def parse():
     ap.add_argument("--scan-w", type=int, default=5000)
     ap.add_argument("--scan-h", type=int, default=2000)
     ap.add_argument("--d", type=float, default=0.01)
+    ap.add_argument("--state", default="gt", choices=["gt", "start", "trajectory"],
+                    help="pose state every timed step starts from: gt = the scene's scanner poses; start = the perturbed poses; "
+                         "trajectory = free-running from the perturbed poses, back to them whenever Run() reports convergence")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the untimed alignment-from-start report")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the ImageRegistrator (Path B) numbers")
     return ap.parse_args()
+
+
+def workload(args):
+    return {"workload": "ICPScanAligner %dx%dM-pt synthetic room scans, point-to-plane, d=%g, 1 outer iteration per step, every step started from state '%s'"
+                        % (args.scans, args.scan_w * args.scan_h // 1000000, args.d, args.state),
+            "scans": args.scans, "points_per_scan": args.scan_w * args.scan_h, "state": args.state}
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -69,102 +89,91 @@ def load_scan(i, W, H):
 
 
 def scene_poses(nscans):
+    """(perturbed start poses, ground-truth poses) of the config-2 scene."""
     from dataset_pipeline_b200 import synth
     gts = []
     for i in range(nscans):
         T = np.eye(4); T[:3, :3] = synth.rot_xyz(0, 0, 0.35 * i); T[:3, 3] = synth.SCANNER_POSITIONS[i]
         gts.append(T)
-    return synth.perturbed_poses(gts), gts
+    return synth.perturbed_poses(gts), [T.astype(np.float32) for T in gts]
+
+
+def state_poses(args):
+    start, gt = scene_poses(max(2, args.scans))
+    return gt if args.state == "gt" else start
 
 
 # --------------------------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port timed on a bounded sample, scaled to the metric's unit
+# CPU arm: the oracle port (reference algorithm and parallel structure: OpenMP over pair-directions only, serial accumulate /
+# cost loops) executing REAL outer iterations
 # --------------------------------------------------------------------------------------------------------------------
-def cpu_sample(args, counts=None):
-    """Times the reference algorithm (oracle port, reference's parallel structure: OpenMP over pair-directions only, serial
-    accumulate / cost loops) on a bounded sample of the workload and scales to one full outer iteration.
-
-    Sample: scans 0 and 1 at FULL size. (a) global-frame transform of one full scan; (b) P concurrent single-thread probes,
-    each = kd-tree build over a full 10M target + nearest-within-radius for every `stride`-th source point (P = host cores,
-    as OpenMP would run P pair-directions at once); (c) the oracle ICP on the two scans with the source stride and the inner LM
-    loop capped, for the per-correspondence accumulate / cost pass rates.
-    Full iteration = 8 transforms + 56 (build + N queries) / min(P,56) + C * (n_acc * r_acc + n_cost * r_cost).
-    C, n_acc, n_cost come from the B200 run of the same workload when given (`counts`), else from the sample itself
-    (match fraction of the probes; LM counts of the capped run = a LOWER bound on the CPU time)."""
+def cpu_iteration(args, scan_ids, poses):
+    """One real outer iteration of the oracle on the given scans (full size) from `poses`. Returns (seconds, stats, cores)."""
     from oracle import oracle as orc
     orc.build()
-    W, H = args.scan_w, args.scan_h
-    ensure_scans([0, 1], W, H)
-    poses, _ = scene_poses(max(2, args.scans))
-    a_xyz, a_nrm = load_scan(0, W, H); b_xyz, b_nrm = load_scan(1, W, H)
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    n_pts = a_xyz.shape[0]
-    stride = max(1, n_pts // 400000)
-    gb, _ = orc.transform_cloud(b_xyz, b_nrm, poses[1])     # first call also pays one-time costs: not timed
+    icp = orc.PointToPlaneICP(use_kdtree=True)
+    for i in scan_ids:
+        xyz, nrm = load_scan(i, args.scan_w, args.scan_h)
+        icp.AddPointCloud(xyz, nrm, poses[i])
+        del xyz, nrm
     t0 = time.perf_counter()
-    ga, _ = orc.transform_cloud(a_xyz, a_nrm, poses[0])
-    t_transform_pp = (time.perf_counter() - t0) / n_pts
-    P = max(1, min(cores, 56))
-    res = [None] * P
-
-    def probe(k):
-        src, tgt = (ga, gb) if k % 2 == 0 else (gb, ga)
-        off = (k // 2) % stride
-        res[k] = orc.time_search(src[off::stride], tgt, args.d)
-
-    th = [threading.Thread(target=probe, args=(k,)) for k in range(P)]
-    tw = time.perf_counter()
-    [t.start() for t in th]; [t.join() for t in th]
-    probe_wall = time.perf_counter() - tw
-    nq = math.ceil(n_pts / stride)
-    t_build = float(np.mean([r[0] for r in res])); t_q = float(np.mean([r[1] for r in res])) / nq
-    frac = float(np.mean([r[2] for r in res])) / nq
-    del ga, gb
-    icp = orc.PointToPlaneICP(use_kdtree=True, inner_max_iterations=3)
-    icp.set_query_stride(stride)
-    icp.AddPointCloud(a_xyz, a_nrm, poses[0]); icp.AddPointCloud(b_xyz, b_nrm, poses[1])
-    icp.Run(args.d, 0, 1, 1e-10, False)
+    icp.Run(args.d, 0, 1, THR, False)
+    dt = time.perf_counter() - t0
     st = icp.stats()
+    st["tries"] = [int(v) for v in icp.tries()]
+    return dt, st, cores
+
+
+def cpu_baseline_sample(args, counts):
+    """cpu_baseline of the B200 line: a bounded sample = one REAL outer iteration of the oracle on scans 0 and 1 at full size from the
+    same state (2 of the 56 pair-directions, the complete LM loop on their correspondences), scaled to the full step with the measured
+    rates: search time x 56 / 2 over the cores OpenMP can use (it parallelises over pair-directions only), LM time x (passes x C) of the
+    full step as counted by the B200 run of the identical step."""
+    ensure_scans([0, 1], args.scan_w, args.scan_h)
+    poses = state_poses(args)
+    dt, st, cores = cpu_iteration(args, [0, 1], poses)
+    ndirs = args.scans * (args.scans - 1)
     C_s = max(1, st["num_correspondences"])
     r_acc = st["t_acc"] / (C_s * max(1, st["inner_iterations"]))
     r_cost = st["t_cost"] / (C_s * max(1, st["lm_tries_total"]))
-    ndirs = args.scans * (args.scans - 1)
-    if counts:
-        C, n_acc, n_cost, src = counts["C"], counts["n_acc"], counts["n_cost"], "B200 run"
-    else:
-        C, n_acc, n_cost, src = frac * ndirs * n_pts, st["inner_iterations"], st["lm_tries_total"], "sample (LM capped at 3: lower bound)"
-    t_full = args.scans * n_pts * t_transform_pp + ndirs * (t_build + n_pts * t_q) / min(P, ndirs) + C * (n_acc * r_acc + n_cost * r_cost)
-    sample = ("scans 0,1 at full size (%d pts): %d concurrent 1-thread probes (kd-tree build over the full target + every %d-th source "
-              "point, d=%g) + oracle ICP on the pair (source stride %d, LM capped at 3) ; rates: transform %.1f ns/pt, build %.2f s, "
-              "query %.2f us, accumulate %.1f ns/corr/pass, cost %.1f ns/corr/pass ; scaled with C=%.3g, n_acc=%d, n_cost=%d from %s"
-              % (n_pts, P, stride, args.d, stride, t_transform_pp * 1e9, t_build, t_q * 1e6, r_acc * 1e9, r_cost * 1e9, C, n_acc, n_cost, src))
-    return {"value": 1.0 / t_full, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-            "seconds_per_iteration": t_full, "probe_wall_s": probe_wall}
+    t_search_dir = st["t_search"]                 # the two directions ran concurrently: wall time of one
+    t_full = (st["t_transform"] / 2.0) * args.scans + t_search_dir * math.ceil(ndirs / min(cores, ndirs)) + \
+        counts["C"] * (counts["n_acc"] * r_acc + counts["n_cost"] * r_cost)
+    sample = ("one real oracle outer iteration on scans 0,1 at full size (%d pts each) from state '%s': %.1f s wall (search %.1f s, LM loop %.1f s: "
+              "%d LM iterations, %d tries, %d correspondences; accumulate %.1f ns/corr/pass, cost %.1f ns/corr/pass); scaled to 8 scans: 56 directions over "
+              "%d cores + C=%.3g x (%d accumulate + %d cost passes) as counted by the B200 run of the same step"
+              % (args.scan_w * args.scan_h, args.state, dt, st["t_search"], st["t_inner"], st["inner_iterations"], st["lm_tries_total"], C_s,
+                 r_acc * 1e9, r_cost * 1e9, cores, counts["C"], counts["n_acc"], counts["n_cost"]))
+    return {"value": 1.0 / t_full, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds_per_iteration_scaled": t_full,
+            "sample_seconds": dt}
 
 
 def run_reference(args):
+    """--impl reference: ONE real outer iteration of the reference algorithm (oracle port: the reference itself needs PCL / FLANN / Eigen
+    and cannot be built here) on the full 8 x 10M scans from the same state as the B200 arm. steps = 1 whatever --steps says: the serial
+    accumulate / cost loops of PointToPlaneICPImpl::compute make one iteration take minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    for s in range(args.warmup + args.steps):
-        r = cpu_sample(args)
-        if s >= args.warmup or args.warmup + args.steps <= 2:
-            vals.append(r)
-        if s == 0 and r["probe_wall_s"] > 60:      # keep the whole run within minutes on slow hosts
-            vals = [r]
-            break
-    v = float(np.mean([x["value"] for x in vals]))
-    last = vals[-1]
-    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-           "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 residuals, f64 accumulation",
-           "data": "synthetic",
-           "config": {"workload": "ICPScanAligner 8x10M-pt synthetic room scans, point-to-plane, d=0.01, 1 outer iteration per step",
-                      "scans": args.scans, "points_per_scan": args.scan_w * args.scan_h, "note": "CPU oracle port of the reference algorithm, bounded sample scaled to one full iteration"},
-           "cpu_baseline": {k: last[k] for k in ("unit", "cores", "kind", "sample")},
+    ensure_scans(range(args.scans), args.scan_w, args.scan_h)
+    poses = state_poses(args)
+    dt, st, cores = cpu_iteration(args, list(range(args.scans)), poses)
+    v = 1.0 / dt
+    cfg = workload(args)
+    cfg.update({"correspondences": st["num_correspondences"], "inner_iterations": st["inner_iterations"], "lm_tries": st["lm_tries_total"],
+                "lm_tries_per_iteration": st["tries"],
+                "seconds": {"transform": st["t_transform"], "search": st["t_search"], "inner": st["t_inner"], "accumulate_passes": st["t_acc"],
+                            "cost_passes": st["t_cost"]},
+                "note": "one full outer iteration executed for real (not sampled, not scaled); --steps/--warmup are not repeated because one step takes minutes"})
+    sample = "the full step: one real outer iteration on all %d scans (%d pts each), %d pair-directions, complete LM loop" % (
+        args.scans, args.scan_w * args.scan_h, args.scans * (args.scans - 1))
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+           "ms_per_step": 1000.0 * dt, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32 residuals/Jacobians, f64 accumulation", "data": "synthetic", "config": cfg,
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    out["cpu_baseline"]["value"] = v
     print(json.dumps(out))
 
 
@@ -184,7 +193,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -213,6 +222,41 @@ class ClockSampler:
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def hist(values):
+    out = {}
+    for v in values:
+        out[str(int(v))] = out.get(str(int(v)), 0) + 1
+    return out
+
+
+def parity_check(args, g, poses, stride=89):
+    """Bit-exact comparison of one pair-direction of the full-size run with the oracle's kd-tree search (FindCorrespondencesFast,
+    icp_point_to_plane.cc:42-105) on every `stride`-th query: the oracle transforms scans 0 and 1 with the poses the search ran at,
+    builds its kd-tree over ALL of scan 1 and answers the sampled queries of scan 0."""
+    from oracle import oracle as orc
+    orc.build()
+    k = None
+    for i, (s, t, c) in enumerate(g.pairs(with_lists=False)):
+        if (s, t) == (0, 1):
+            k = i
+    if k is None:
+        return {"checked": False, "why": "pair 0->1 not searched on this rank"}
+    _, _, q, m, d2 = g.pair_correspondences(k)
+    W, H = args.scan_w, args.scan_h
+    a_xyz, a_nrm = load_scan(0, W, H); b_xyz, b_nrm = load_scan(1, W, H)
+    ga, _ = orc.transform_cloud(a_xyz, a_nrm, poses[0]); gb, _ = orc.transform_cloud(b_xyz, b_nrm, poses[1])
+    sel = np.arange(0, ga.shape[0], stride)
+    t0 = time.perf_counter()
+    qo, mo, do = orc.find_correspondences(ga[sel], gb, args.d, use_kdtree=True)
+    t_or = time.perf_counter() - t0
+    keep = (q % stride) == 0
+    qg, mg, dg = q[keep] // stride, m[keep], d2[keep]
+    ok = bool(np.array_equal(qg, qo) and np.array_equal(mg, mo) and np.array_equal(dg, do))
+    return {"checked": True, "bit_exact": ok, "pair": "scan 0 -> scan 1", "queries_checked": int(sel.size), "matches_checked": int(qo.size),
+            "gpu_matches_of_pair": int(q.size), "against": "oracle kd-tree over all %d target points (oracle/orc_icp.cc: find_correspondences)" % gb.shape[0],
+            "oracle_seconds": t_or}
 
 
 def run_b200(args):
@@ -251,7 +295,8 @@ def run_b200(args):
         px.numpy()[:] = xyz; pn.numpy()[:] = nrm
         clouds.append((px, pn))
     t_gen = time.perf_counter() - t_gen
-    poses, _ = scene_poses(NS)
+    start_poses, gt_poses = scene_poses(NS)
+    base_poses = gt_poses if args.state == "gt" else start_poses
     npts = sum(c[0].shape[0] for c in clouds)
     stream = torch.cuda.Stream()          # a real (non-null) stream shared by torch events, NCCL ordering and the library
     torch.cuda.set_stream(stream)
@@ -271,26 +316,57 @@ def run_b200(args):
         dist.broadcast(idt, 0)
         comm = b2.Comm(rank, world, bytes(idt.cpu().numpy().tobytes()), device=local)
 
-    def make(start_poses=None):
+    def make(poses):
         g = b2.PointToPlaneICP(device=local, rank=rank, world_size=world, allreduce=allreduce if (world > 1 and comm is None) else None,
-                               stream=stream.cuda_stream, comm=comm)
-        for (px, pn), T in zip(clouds, start_poses if start_poses is not None else poses):
+                               stream=stream.cuda_stream, comm=comm, index_distance_hint=args.d, shard_uploads=comm is not None)
+        g.upload_ms = []
+        for (px, pn), T in zip(clouds, poses):
+            t = time.perf_counter()
             g.AddPointCloud(px.numpy(), pn.numpy(), T)
+            g.upload_ms.append(round(1e3 * (time.perf_counter() - t), 2))
         return g
 
-    thr = 1e-10
-    g = make()
+    def set_poses(g, poses):
+        for i, T in enumerate(poses):
+            g.SetGlobalTCloud(i, T)
+
+    def brief(st):
+        return {"inner_iterations": st["inner_iterations"], "lm_tries": st["lm_tries_total"], "passes": st["passes"], "ms": round(st["ms_total"], 3)}
+
+    g = make(start_poses)
+    # ---- untimed: the whole alignment from the perturbed start (also the warm-up of allocations and of the static index) ----
+    extra = None
+    if not args.no_extra:
+        traj = []
+        conv = False
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for it in range(40):
+            conv = g.Run(args.d, it, 1, THR, False)
+            traj.append(brief(g.stats()))
+            if conv:
+                break
+        torch.cuda.synchronize(); t_traj = time.perf_counter() - t0
+        g.Run(args.d, len(traj), 1, THR, False)           # one more at the converged state
+        extra = {"alignment_from_perturbed_start": {"outer_iterations_until_converged": len(traj), "converged": bool(conv), "seconds": t_traj,
+                                                    "iterations_per_s": len(traj) / t_traj, "per_iteration": traj},
+                 "converged_iteration": brief(g.stats())}
     for it in range(args.warmup):
-        g.Run(args.d, it, 1, thr, False)
+        set_poses(g, base_poses)
+        g.Run(args.d, it, 1, THR, False)
     sampler = ClockSampler(local) if rank == 0 else None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    set_poses(g, base_poses)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    step_stats = []
-    for it in range(args.warmup, args.warmup + args.steps):
-        g.Run(args.d, it, 1, thr, False)
+    step_stats, step_poses = [], []
+    conv = False
+    for it in range(args.steps):
+        if args.state != "trajectory" or conv or it == 0:
+            set_poses(g, base_poses)                       # host-side: eight 4x4 matrices
+        step_poses.append([g.GetResultGlobalTCloud(i) for i in range(NS)])
+        conv = g.Run(args.d, it, 1, THR, False)
         step_stats.append(g.stats())
     e1.record(stream)
     torch.cuda.synchronize()
@@ -303,30 +379,36 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = args.steps / (ms / 1000.0)
-    final_poses = [g.GetResultGlobalTCloud(i) for i in range(NS)]
+
+    # ---- parity of the timed path at full size: one pair-direction of the LAST timed step against the oracle ----
+    parity = None
+    if not args.no_parity and rank == 0:
+        parity = parity_check(args, g, step_poses[-1])
     g.close()
     del g
 
     # ---- end to end through the public API with HOST buffers: create, 8 x AddPointCloud (H2D from pinned memory), Run, read poses ----
     e2e = None
     if not args.no_e2e:
-        k_e2e = max(1, min(args.steps, 3))
-        times = []
+        k_e2e = args.steps
+        times, parts = [], None
         for s in range(1 + k_e2e):
+            poses_s = step_poses[(s - 1) % len(step_poses)] if s else step_poses[0]
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            ge = make(final_poses)          # the same kind of iteration as the timed ones: the alignment state after warm-up + steps
+            ge = make(poses_s)
             t1 = time.perf_counter()
-            ge.Run(args.d, args.warmup + args.steps, 1, thr, False)
+            ge.Run(args.d, 0, 1, THR, False)
             t2 = time.perf_counter()
             _ = [ge.GetResultGlobalTCloud(i) for i in range(NS)]
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             st_e = ge.stats()
             ge.close()
-            parts = {"create_and_upload_ms": 1e3 * (t1 - t0), "run_ms": 1e3 * (t2 - t1), "run_device_ms": st_e["ms_total"], "destroy_ms": 1e3 * (time.perf_counter() - t0 - dt),
+            parts = {"create_and_upload_ms": 1e3 * (t1 - t0), "add_cloud_ms": ge.upload_ms, "run_ms": 1e3 * (t2 - t1), "run_device_ms": st_e["ms_total"], "index_build_ms": st_e["ms_index_build"],
+                     "destroy_ms": 1e3 * (time.perf_counter() - t0 - dt),
                      "run_phases_ms": {k: st_e["ms_" + k] for k in ("index", "search", "pack", "inner")}, "passes": st_e["passes"]}
             if world > 1:
                 t = torch.tensor([dt], device="cuda", dtype=torch.float64)
@@ -335,73 +417,81 @@ def run_b200(args):
             if s >= 1:
                 times.append(dt)
         nv = 6 * (NS - 1)
-        d2h = st_e["passes"] * (nv * nv + nv + 6) * 8 + NS * 2 * 148 * 6 * 4 + 8 * NS * (NS - 1) + 4 * NS
-        e2e = {"value": len(times) / sum(times), "unit": UNIT, "h2d_bytes_per_step": int(npts * 24), "d2h_bytes_per_step": int(d2h),
-               "steps": len(times), "last_step_breakdown": parts, "h2d_gb_per_s_in_upload": npts * 24 / 1e9 / max(parts["create_and_upload_ms"] * 1e-3, 1e-9), "note": "each step: b2_icp_create + 8 x b2_icp_add_cloud from pinned host memory (poses = the state the timed iterations ended in) + b2_icp_run(1 iteration) + b2_icp_get_pose + destroy"}
+        d2h = st_e["passes"] * (nv * nv + nv + 6) * 8 + NS * 4 * 148 * 6 * 4 + 4 * NS * (NS - 1) + 4 * NS
+        h2d = npts * 24 if comm is None else sum(c[0].shape[0] * 24 for i, c in enumerate(clouds) if i % world == rank)   # rank 0's share when sharded
+        e2e = {"value": len(times) / sum(times), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "step_ms": [round(1e3 * v, 2) for v in times],
+               "steps": len(times), "last_step_breakdown": parts, "h2d_gb_per_s_in_upload": npts * 24 / 1e9 / max(parts["create_and_upload_ms"] * 1e-3, 1e-9),
+               "note": "each step: b2_icp_create + 8 x b2_icp_add_cloud from pinned host memory (static index built behind the uploads) + b2_icp_run(1 iteration from the "
+                       "same poses as the corresponding timed step) + b2_icp_get_pose + destroy"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_accumulate: 48 algorithmic bytes per correspondence per pass) ----
+    # ---- rooflines (SURVEY.md §8d byte counts) ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    acc_ms = float(np.mean([s["ms_accum_kernel_avg"] for s in step_stats]))
-    recs = float(np.mean([s["local_correspondences"] for s in step_stats]))
-    achieved = (48.0 * recs / (acc_ms * 1e-3)) / 1e9 if acc_ms > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "accumulate_traffic.json")
-    if os.path.exists(tp):
-        try:
-            tj = json.load(open(tp))      # ncu capture (profiles/): DRAM bytes over algorithmic bytes of that capture, applied to this launch
-            traffic = tj["dram_over_algorithmic"] * 48.0 * recs if "dram_over_algorithmic" in tj else tj.get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
     src = "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
     mean = lambda k: float(np.mean([s[k] for s in step_stats]))
-    roof_acc = {"bound": "hbm", "kernel": "k_accumulate_tma<WITH_H, NX> (K5, 48 B/correspondence/pass; a pass evaluates up to 4 LM tries on one read of the records)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": src,
-                "algorithmic_bytes_per_launch": 48.0 * recs, "avg_launch_ms": acc_ms,
-                "share_of_step": mean("passes") * acc_ms / (ms / args.steps)}
+    step_ms = ms / args.steps
+
+    def traffic_of(name, algorithmic):
+        tp = os.path.join(ROOT, "profiles", name)
+        try:
+            tj = json.load(open(tp))          # ncu capture (profiles/): DRAM bytes over algorithmic bytes of that capture, applied to this launch
+            return tj["dram_over_algorithmic"] * algorithmic if "dram_over_algorithmic" in tj else tj.get("dram_bytes_per_launch")
+        except Exception:
+            return None
+
+    acc_ms = mean("ms_accum_kernel_avg"); recs = mean("local_correspondences")
+    achieved = (48.0 * recs / (acc_ms * 1e-3)) / 1e9 if acc_ms > 0 else 0.0
+    roof_acc = {"bound": "hbm", "kernel": "k_accumulate_tma<WITH_H, NX> (K5, 48 B/correspondence/pass; a pass evaluates up to 4 LM tries on one read of the records)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic_of("accumulate_traffic.json", 48.0 * recs),
+                "peak_source": src, "algorithmic_bytes_per_launch": 48.0 * recs, "avg_launch_ms": acc_ms, "share_of_step": mean("passes") * acc_ms / step_ms}
     nn_ms = mean("ms_search_kernel_avg"); nn_launches = max(1.0, mean("search_launches"))
     nn_bytes = mean("search_algorithmic_bytes") / nn_launches
     nn_ach = (nn_bytes / (nn_ms * 1e-3)) / 1e9 if nn_ms > 0 else 0.0
-    nn_traffic = None
-    tp = os.path.join(ROOT, "profiles", "search_traffic.json")
-    if os.path.exists(tp):
-        try:
-            tj = json.load(open(tp))
-            nn_traffic = tj["dram_over_algorithmic"] * nn_bytes if "dram_over_algorithmic" in tj else tj.get("dram_bytes_per_launch")
-        except Exception:
-            nn_traffic = None
-    roof_nn = {"bound": "hbm", "kernel": "k_nn_radius1 (K3, 12Q+8Qm+12T B/pair-direction; gather/L2-latency bound in practice)", "achieved": nn_ach,
-               "peak": peak, "unit": "GB/s", "frac": nn_ach / peak if peak else None, "traffic": nn_traffic, "peak_source": src,
-               "algorithmic_bytes_per_launch": nn_bytes, "avg_launch_ms": nn_ms, "share_of_step": nn_launches * nn_ms / (ms / args.steps)}
+    roof_nn = {"bound": "hbm", "kernel": "k_nn_tiles (K3, 12Q+8Qm+12T B/pair-direction; instruction-issue / gather-latency bound in practice)", "achieved": nn_ach,
+               "peak": peak, "unit": "GB/s", "frac": nn_ach / peak if peak else None, "traffic": traffic_of("search_traffic.json", nn_bytes), "peak_source": src,
+               "algorithmic_bytes_per_launch": nn_bytes, "avg_launch_ms": nn_ms, "share_of_step": nn_launches * nn_ms / step_ms,
+               "note": "launches of the pair-directions overlap on 4 streams: avg_launch_ms = search phase / launches"}
     # the dominant kernel of the step is the one the roofline key describes; the other is kept alongside
     roofline, roofline2 = (roof_nn, roof_acc) if roof_nn["share_of_step"] >= roof_acc["share_of_step"] else (roof_acc, roof_nn)
+    cfg = workload(args)
+    cfg.update({"parallelism": "pair-directions sharded over %d GPU(s), 1 allreduce of the normal equations per pass" % world,
+                "l2": "inputs larger than L2 (%.1f GB of scans, %.1f GB of packed records per pass)" % (npts * 24 / 1e9, 48.0 * recs / 1e9),
+                "correspondences": mean("num_correspondences"), "inner_iterations": mean("inner_iterations"), "lm_tries": mean("lm_tries_total"),
+                "passes_per_step": mean("passes"),
+                "per_step": {"inner_iterations": hist(s["inner_iterations"] for s in step_stats), "passes": hist(s["passes"] for s in step_stats)},
+                "lm": "reference semantics (tries evaluated in order); up to 4 tries ride on one streaming pass",
+                "ms_breakdown": {"index": mean("ms_index"), "search": mean("ms_search"), "pack": mean("ms_pack"), "inner": mean("ms_inner")},
+                "input_generation_s": t_gen})
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "f32 residuals/Jacobians, f64 accumulation", "data": "synthetic",
-           "config": {"workload": "ICPScanAligner 8x10M-pt synthetic room scans, point-to-plane, d=0.01, 1 outer iteration per step",
-                      "scans": NS, "points_per_scan": int(npts // NS), "parallelism": "pair-directions sharded over %d GPU(s), 1 allreduce of the normal equations per pass" % world,
-                      "l2": "inputs larger than L2 (%.1f GB of scans, %.1f GB of packed records per pass)" % (npts * 24 / 1e9, 48.0 * recs / 1e9),
-                      "correspondences": mean("num_correspondences"), "inner_iterations": mean("inner_iterations"), "lm_tries": mean("lm_tries_total"),
-                      "passes_per_step": mean("passes"), "lm": "reference semantics (tries evaluated in order); up to 4 tries ride on one streaming pass",
-                      "ms_breakdown": {"index": mean("ms_index"), "search": mean("ms_search"), "pack": mean("ms_pack"), "inner": mean("ms_inner")},
-                      "input_generation_s": t_gen},
+           "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32 residuals/Jacobians, f64 accumulation", "data": "synthetic", "config": cfg,
            "gpu_launches": int(sum(s["kernel_launches"] for s in step_stats)),
            "clocks": clocks, "roofline": roofline, "roofline_second_kernel": roofline2}
     if e2e:
         out["e2e"] = e2e
+    if parity:
+        out["parity_checked"] = parity
+    if extra:
+        out["extra"] = extra
     if world == 1 and not args.no_cpu_baseline:
-        counts = {"C": mean("num_correspondences"), "n_acc": int(round(mean("inner_iterations"))), "n_cost": int(round(mean("lm_tries_total")))}
-        cb = cpu_sample(args, counts)
+        counts = {"C": mean("num_correspondences"), "n_acc": int(round(mean("inner_iterations"))) + 1, "n_cost": int(round(mean("lm_tries_total")))}
+        cb = cpu_baseline_sample(args, counts)
         out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if not args.no_secondary:
+        try:
+            import bench_reg
+            out["secondary"] = bench_reg.secondary_line(world, rank)
+        except Exception as e:      # the ICP line must not be lost to the secondary benchmark
+            out["secondary"] = {"error": repr(e)}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(out))

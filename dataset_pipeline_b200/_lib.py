@@ -17,7 +17,7 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void
 class IcpConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("inner_max_iterations", C.c_int32), ("keep_correspondences", C.c_int32),
                 ("rank", C.c_int32), ("world_size", C.c_int32), ("allreduce", ALLREDUCE_FN), ("allreduce_user", C.c_void_p),
-                ("stream", C.c_void_p), ("comm", C.c_void_p)]
+                ("stream", C.c_void_p), ("comm", C.c_void_p), ("index_distance_hint", C.c_float), ("shard_uploads", C.c_int32)]
 
 
 class IcpStats(C.Structure):
@@ -50,6 +50,7 @@ EXPORTS = [
     "b2_camera_eval",
     "b2_comm_allreduce",
     "b2_comm_allreduce_f64",
+    "b2_comm_broadcast",
     "b2_comm_create",
     "b2_comm_destroy",
     "b2_comm_info",

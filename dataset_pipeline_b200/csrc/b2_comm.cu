@@ -14,13 +14,14 @@ namespace b2 {
 
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
-enum { kNcclSuccess = 0, kNcclSum = 0, kNcclInt32 = 2, kNcclFloat32 = 7, kNcclFloat64 = 8 };
+enum { kNcclSuccess = 0, kNcclSum = 0, kNcclUint8 = 1, kNcclInt32 = 2, kNcclFloat32 = 7, kNcclFloat64 = 8 };
 
 struct NcclApi {
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
 };
@@ -36,6 +37,7 @@ static NcclApi& nccl() {
     api.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(lib, "ncclCommInitRank");
     api.CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
     api.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    api.Broadcast = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclBroadcast");
     api.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
     api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce;
   });
@@ -100,6 +102,18 @@ int b2_comm_allreduce(b2_comm* c, void* buf_dev, size_t count, int dtype, void* 
   if (count == 0) return B2_OK;
   const int rc = nccl().AllReduce(buf_dev, buf_dev, count, t, kNcclSum, c->comm, (cudaStream_t)stream);
   if (rc != kNcclSuccess) return set_error(B2_ERR_COMM, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
+  return B2_OK;
+}
+
+// In-place broadcast of `bytes` bytes from rank `root` on `stream` (the sharded upload of b2_icp_add_cloud: the owner's copy of a scan
+// reaches the other GPUs over NVLink instead of every process pushing every scan through PCIe).
+int b2_comm_broadcast(b2_comm* c, void* buf_dev, size_t bytes, int root, void* stream) {
+  if (!c || (!buf_dev && bytes)) return set_error(B2_ERR_ARG, "null");
+  if (root < 0 || root >= c->world) return set_error(B2_ERR_ARG, "bad root %d", root);
+  if (!nccl().Broadcast) return set_error(B2_ERR_COMM, "ncclBroadcast not found in libnccl");
+  if (bytes == 0) return B2_OK;
+  const int rc = nccl().Broadcast(buf_dev, buf_dev, bytes, kNcclUint8, root, c->comm, (cudaStream_t)stream);
+  if (rc != kNcclSuccess) return set_error(B2_ERR_COMM, "ncclBroadcast failed: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
   return B2_OK;
 }
 

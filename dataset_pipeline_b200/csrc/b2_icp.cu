@@ -79,8 +79,9 @@ struct b2_icp {
   int device = 0, sms = 148;
   bool lpt_order = true;                // K3 tiles issued longest-first (B2_K3_ORDER=grid disables, for A/B runs)
   bool work_stats = false;              // B2_K3_WORK=1: the diagnostic K3 variant that counts its work
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;   // copy_stream: uploads of b2_icp_add_cloud (so that an index build can run beside them)
   bool own_stream = false;
+  b2::Cloud* pending_index = nullptr;   // index_distance_hint: the cloud whose index is built behind the next upload
   // K3 runs the pair-directions of an iteration round-robin over `nsearch` streams (the handle's + auxiliaries) so that one
   // direction's tail overlaps the next direction's head; each stream has its own CUB scratch.
   static constexpr int kMaxSearchStreams = 8;
@@ -123,24 +124,37 @@ static Cloud* impl_cloud(b2_icp* h, int idx) {
 }
 static int impl_index_of_movable(const b2_icp* h, int m) { return h->fixed ? m + 1 : m; }
 
-static int upload_cloud(b2_icp* h, Cloud* c, const float* xyz, const float* nrm, size_t n, size_t stride_bytes, bool from_device) {
+static int build_pending_index(b2_icp* h);
+// owner >= 0: sharded upload (cfg.shard_uploads) — only rank `owner` reads the caller's buffers, everyone else receives the cloud
+// by ncclBroadcast on the copy stream.
+static int upload_cloud(b2_icp* h, Cloud* c, const float* xyz, const float* nrm, size_t n, size_t stride_bytes, bool from_device, int owner = -1) {
   c->n = n;
   c->have_lbox = c->indexed = false;
   B2_TRY(c->local_xyz.ensure(std::max<size_t>(n, 1) * 12));
   B2_TRY(c->local_nrm.ensure(std::max<size_t>(n, 1) * 12));
-  if (n == 0) return B2_OK;
-  if (from_device) {
-    B2_CUDA(cudaMemcpyAsync(c->local_xyz.p, xyz, n * 12, cudaMemcpyDeviceToDevice, h->stream));
-    B2_CUDA(cudaMemcpyAsync(c->local_nrm.p, nrm, n * 12, cudaMemcpyDeviceToDevice, h->stream));
-  } else if (stride_bytes == 12) {
-    B2_CUDA(cudaMemcpyAsync(c->local_xyz.p, xyz, n * 12, cudaMemcpyHostToDevice, h->stream));
-    B2_CUDA(cudaMemcpyAsync(c->local_nrm.p, nrm, n * 12, cudaMemcpyHostToDevice, h->stream));
-  } else {
-    B2_CUDA(cudaMemcpy2DAsync(c->local_xyz.p, 12, xyz, stride_bytes, 12, n, cudaMemcpyHostToDevice, h->stream));
-    B2_CUDA(cudaMemcpy2DAsync(c->local_nrm.p, 12, nrm, stride_bytes, 12, n, cudaMemcpyHostToDevice, h->stream));
+  if (n) {
+    cudaStream_t cs = h->copy_stream;
+    if (owner >= 0 && owner != h->cfg.rank) {
+      // nothing to read on this rank
+    } else if (from_device) {
+      B2_CUDA(cudaMemcpyAsync(c->local_xyz.p, xyz, n * 12, cudaMemcpyDeviceToDevice, cs));
+      B2_CUDA(cudaMemcpyAsync(c->local_nrm.p, nrm, n * 12, cudaMemcpyDeviceToDevice, cs));
+    } else if (stride_bytes == 12) {
+      B2_CUDA(cudaMemcpyAsync(c->local_xyz.p, xyz, n * 12, cudaMemcpyHostToDevice, cs));
+      B2_CUDA(cudaMemcpyAsync(c->local_nrm.p, nrm, n * 12, cudaMemcpyHostToDevice, cs));
+    } else {
+      B2_CUDA(cudaMemcpy2DAsync(c->local_xyz.p, 12, xyz, stride_bytes, 12, n, cudaMemcpyHostToDevice, cs));
+      B2_CUDA(cudaMemcpy2DAsync(c->local_nrm.p, 12, nrm, stride_bytes, 12, n, cudaMemcpyHostToDevice, cs));
+    }
+    if (owner >= 0) {
+      B2_TRY(b2_comm_broadcast(h->cfg.comm, c->local_xyz.p, n * 12, owner, (void*)cs));
+      B2_TRY(b2_comm_broadcast(h->cfg.comm, c->local_nrm.p, n * 12, owner, (void*)cs));
+    }
   }
-  B2_CUDA(cudaStreamSynchronize(h->stream));   // the caller may free / reuse its buffers after return
-  return B2_OK;
+  // while this cloud's bytes are on the wire: the search index of the previously added cloud (index_distance_hint)
+  const int rc = build_pending_index(h);
+  if (n) B2_CUDA(cudaStreamSynchronize(h->copy_stream));   // the caller may free / reuse its buffers after return
+  return rc;
 }
 
 // ---- the linear part of a pose -------------------------------------------------------------------------------------
@@ -216,7 +230,9 @@ static int grid_for_cloud(Cloud* c, const float fmin[3], const float fmax[3], fl
     if (!std::isfinite(fmin[d]) || !std::isfinite(fmax[d]))
       return set_error(B2_ERR_ARG, "non-finite point coordinates (clouds must be dense, as the reference's is_dense path assumes)");
   c->index_sigma = sigma * (1.0 + 1e-4);
-  c->index_mtot = 2.0 * mtot;
+  // magnitude classes are powers of two, so that clouds indexed at different times (index_distance_hint) still get the same margin,
+  // hence the same cell size and the same lattice
+  c->index_mtot = std::ldexp(1.0, (int)std::ceil(std::log2(std::max(2.0 * mtot, 1e-30))));
   c->margin = 64.0 * std::ldexp(1.0, -24) * c->index_mtot;
   double cell = 2.0 * ((double)max_dist * c->index_sigma + c->margin) * 1.0001;
   if (!(cell > 0.0)) cell = 1e-30;
@@ -273,7 +289,7 @@ static int cloud_local_box(b2_icp* h, Cloud* c) {
 static int build_index(b2_icp* h, Cloud* c, float max_dist, double sigma, double mtot) {
   const size_t n = c->n;
   c->indexed = false;
-  if (n == 0) { c->ncells = 0; c->index_d = max_dist; c->index_sigma = sigma * (1.0 + 1e-4); c->index_mtot = 2.0 * mtot; c->indexed = true; return B2_OK; }
+  if (n == 0) { c->ncells = 0; c->index_d = max_dist; c->index_sigma = sigma * (1.0 + 1e-4); c->index_mtot = 4.0 * mtot; c->indexed = true; return B2_OK; }
   // freeze the index frame at the current pose and measure the cloud's box in it
   for (int r = 0; r < 3; ++r) { for (int k = 0; k < 3; ++k) c->F[4 * r + k] = c->T[r + 4 * k]; c->F[4 * r + 3] = c->T[12 + r]; }
   float fmin[3] = {INFINITY, INFINITY, INFINITY}, fmax[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -480,9 +496,30 @@ static int run_pass(b2_icp* h, const std::vector<std::vector<Pose>>& trials, boo
 
 static float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
 
+// index_distance_hint: the cloud added last is indexed now — the caller is b2_icp_add_cloud with the NEXT cloud's copy in flight (or
+// ensure_indexes for the last one). Only this cloud's own magnitude is known yet; should a later cloud raise the handle's bound above
+// the class chosen here, ensure_indexes rebuilds.
+static int build_pending_index(b2_icp* h) {
+  Cloud* c = h->pending_index;
+  h->pending_index = nullptr;
+  if (!c || !(h->cfg.index_distance_hint > 0.f) || c->indexed) return B2_OK;
+  B2_TRY(cloud_local_box(h, c));
+  double m = 0, sigma = 1.0;
+  for (int k = 0; k < 3; ++k) m = std::max({m, std::fabs((double)c->lmin[k]), std::fabs((double)c->lmax[k])});
+  for (int a = 0; a < 3; ++a) {
+    double gsum = std::fabs((double)c->T[12 + a]);
+    for (int k = 0; k < 3; ++k) gsum += std::fabs((double)c->T[a + 4 * k]) * std::max(std::fabs((double)c->lmin[k]), std::fabs((double)c->lmax[k]));
+    m = std::max(m, gsum);
+  }
+  if (!std::isfinite(m)) return B2_OK;           // reported by b2_icp_run
+  B2_TRY(pose_sigma(c->T, nullptr, &sigma));
+  return build_index(h, c, h->cfg.index_distance_hint, sigma, m);
+}
+
 // Index maintenance at the start of an outer iteration: (re)build the indexes the current radius / poses are not covered by.
 static int ensure_indexes(b2_icp* h, float max_dist) {
   const int nc = num_impl_clouds(h);
+  h->pending_index = nullptr;                    // whatever is still pending is built below, with the handle's full magnitude bound
   for (int i = 0; i < nc; ++i) B2_TRY(cloud_local_box(h, impl_cloud(h, i)));
   const double mtot = magnitude_bound(h);
   if (!std::isfinite(mtot)) return set_error(B2_ERR_ARG, "non-finite pose or point coordinates");
@@ -870,12 +907,14 @@ int b2_icp_create(const b2_icp_config* cfg, b2_icp** out) {
   if (cfg) c = *cfg;
   if (c.world_size < 1) c.world_size = 1;
   if (c.world_size > 1 && !c.allreduce && !c.comm) return set_error(B2_ERR_ARG, "world_size > 1 needs a b2_comm or an allreduce hook");
+  if (c.shard_uploads && !c.comm) return set_error(B2_ERR_ARG, "shard_uploads needs a b2_comm");
   if (c.rank < 0 || c.rank >= c.world_size) return set_error(B2_ERR_ARG, "rank %d out of range", c.rank);
   std::unique_ptr<b2_icp> h(new b2_icp());
   h->cfg = c;
   B2_TRY(select_device(c.device, &h->device, &h->sms));
   if (c.stream) { h->stream = (cudaStream_t)c.stream; }
   else { B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  B2_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   if (const char* e = getenv("B2_K3_STREAMS")) h->nsearch = std::max(1, std::min((int)b2_icp::kMaxSearchStreams, atoi(e)));
   if (const char* e = getenv("B2_K3_WORK")) h->work_stats = e[0] && e[0] != '0';
   for (int i = 0; i + 1 < h->nsearch; ++i) {
@@ -909,6 +948,7 @@ int b2_icp_destroy(b2_icp* h) {
   for (int i = 0; i < b2_icp::kMaxSearchStreams - 1; ++i) { if (h->aux[i]) cudaStreamDestroy(h->aux[i]); if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]); }
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   for (DevBuf& b : h->search_tmp) b.release();
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return B2_OK;
@@ -916,7 +956,9 @@ int b2_icp_destroy(b2_icp* h) {
 
 static int add_cloud_impl(b2_icp* h, const float* xyz, const float* nrm, size_t n, size_t stride, const float T[16], int fixed, int* out_id,
                           bool from_device) {
-  if (!h || !T || (n > 0 && (!xyz || !nrm))) return set_error(B2_ERR_ARG, "null argument");
+  if (!h || !T) return set_error(B2_ERR_ARG, "null argument");
+  const int owner = (!fixed && h->cfg.shard_uploads && h->cfg.comm && h->cfg.world_size > 1) ? (int)(h->movable.size() % (size_t)h->cfg.world_size) : -1;
+  if (n > 0 && (!xyz || !nrm) && (owner < 0 || owner == h->cfg.rank)) return set_error(B2_ERR_ARG, "null argument");
   if (!from_device && stride < 12) return set_error(B2_ERR_ARG, "stride_bytes must be >= 12");
   if (n >= (1ull << 31)) return set_error(B2_ERR_ARG, "clouds above 2^31 points are not supported (pcl::Correspondence indices are int)");
   B2_CUDA(cudaSetDevice(h->device));
@@ -945,7 +987,8 @@ static int add_cloud_impl(b2_icp* h, const float* xyz, const float* nrm, size_t 
   }
   std::unique_ptr<Cloud> c(new Cloud());
   std::memcpy(c->T, T, sizeof(float) * 16);
-  B2_TRY(upload_cloud(h, c.get(), xyz, nrm, n, stride, from_device));
+  B2_TRY(upload_cloud(h, c.get(), xyz, nrm, n, stride, from_device, owner));
+  h->pending_index = c.get();
   h->movable.push_back(std::move(c));
   if (out_id) *out_id = (int)h->movable.size() - 1;
   return B2_OK;

@@ -49,7 +49,7 @@ class Comm:
 
 class PointToPlaneICP:
     def __init__(self, device=-1, inner_max_iterations=150, keep_correspondences=False, rank=0, world_size=1,
-                 allreduce=None, stream=None, comm=None):
+                 allreduce=None, stream=None, comm=None, index_distance_hint=0.0, shard_uploads=False):
         L = _lib.lib()
         cfg = _lib.IcpConfig()
         L.b2_icp_default_config(C.byref(cfg))
@@ -57,6 +57,8 @@ class PointToPlaneICP:
         cfg.inner_max_iterations = inner_max_iterations
         cfg.keep_correspondences = int(keep_correspondences)
         cfg.rank, cfg.world_size = rank, world_size
+        cfg.index_distance_hint = float(index_distance_hint)
+        cfg.shard_uploads = int(bool(shard_uploads))
         self._cb = None
         if allreduce is not None:
             # allreduce(ptr:int, count:int, stream:int) -> None ; wrapped into the C hook
@@ -161,6 +163,14 @@ class PointToPlaneICP:
                 out.append((s.value, t.value, c.value))
             k += 1
         return out
+
+    def pair_correspondences(self, k):
+        """(src_impl_index, tgt_impl_index, q, m, d2) of the k-th non-empty correspondence set of the last outer iteration."""
+        s, t, c = C.c_int32(), C.c_int32(), C.c_uint64()
+        _lib.check(_lib.lib().b2_icp_get_pair_info(self._h, k, C.byref(s), C.byref(t), C.byref(c)))
+        q = np.zeros(c.value, np.int32); m = np.zeros(c.value, np.int32); d2 = np.zeros(c.value, np.float32)
+        _lib.check(_lib.lib().b2_icp_get_pair_correspondences(self._h, k, _i(q), _i(m), _f(d2)))
+        return s.value, t.value, q, m, d2
 
     def normal_equations(self):
         nv = C.c_int32(0)

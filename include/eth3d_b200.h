@@ -67,6 +67,7 @@ int b2_comm_destroy(b2_comm* c);
 int b2_comm_allreduce_f64(b2_comm* c, double* buf_dev, size_t count, void* stream);   /* in-place sum, ordered on stream */
 enum { B2_F64 = 0, B2_F32 = 1, B2_I32 = 2 };
 int b2_comm_allreduce(b2_comm* c, void* buf_dev, size_t count, int dtype /* B2_F64 | B2_F32 | B2_I32 */, void* stream);   /* in-place sum */
+int b2_comm_broadcast(b2_comm* c, void* buf_dev, size_t bytes, int root, void* stream);   /* in place, from rank `root` */
 int b2_comm_info(b2_comm* c, int* rank, int* world_size);
 
 typedef struct b2_icp_config {
@@ -79,6 +80,14 @@ typedef struct b2_icp_config {
   void* allreduce_user;
   void* stream;                 /* cudaStream_t to run on; NULL = a stream owned by the handle */
   b2_comm* comm;                /* library-owned NCCL communicator (preferred): ncclAllReduce(sum, double) on the handle's stream */
+  float index_distance_hint;    /* > 0: the max_correspondence_distance b2_icp_run will be called with (ICPScanAligner knows it from
+                                   its flags before it adds a cloud). b2_icp_add_cloud then builds a cloud's search index while the
+                                   NEXT cloud's host-to-device copy is in flight instead of inside the first b2_icp_run. 0 = no hint.
+                                   A wrong hint costs a rebuild, never correctness. */
+  int32_t shard_uploads;        /* != 0 (needs `comm`): b2_icp_add_cloud becomes COLLECTIVE — every rank calls it for every movable cloud
+                                   in the same order with the same n; only rank (cloud_id % world_size) reads its host buffers and
+                                   copies them to its GPU, the other ranks receive the cloud by ncclBroadcast over NVLink (their
+                                   xyz / normals arguments are ignored and may be NULL). Fixed clouds are uploaded by every rank. */
 } b2_icp_config;
 
 typedef struct b2_icp_stats {
