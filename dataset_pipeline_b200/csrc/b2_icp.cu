@@ -51,6 +51,7 @@ struct Cloud {
   unsigned int ncells = 0;
   // ---- per outer iteration ----
   DevBuf s_xyz, s_nrm, box1, box2;      // global-frame rows in the sorted order + chunk boxes
+  cudaEvent_t ready_ev = nullptr;       // sharded upload: the cloud's bytes have arrived on this rank (recorded on the broadcast stream)
 };
 
 struct Direction {
@@ -80,6 +81,7 @@ struct b2_icp {
   bool lpt_order = true;                // K3 tiles issued longest-first (B2_K3_ORDER=grid disables, for A/B runs)
   bool work_stats = false;              // B2_K3_WORK=1: the diagnostic K3 variant that counts its work
   cudaStream_t stream = nullptr, copy_stream = nullptr;   // copy_stream: uploads of b2_icp_add_cloud (so that an index build can run beside them)
+  cudaStream_t bcast_stream = nullptr;  // sharded uploads: the NCCL broadcasts, ordered behind the owner's copy by an event
   bool own_stream = false;
   b2::Cloud* pending_index = nullptr;   // index_distance_hint: the cloud whose index is built behind the next upload
   // K3 runs the pair-directions of an iteration round-robin over `nsearch` streams (the handle's + auxiliaries) so that one
@@ -147,13 +149,18 @@ static int upload_cloud(b2_icp* h, Cloud* c, const float* xyz, const float* nrm,
       B2_CUDA(cudaMemcpy2DAsync(c->local_nrm.p, 12, nrm, stride_bytes, 12, n, cudaMemcpyHostToDevice, cs));
     }
     if (owner >= 0) {
-      B2_TRY(b2_comm_broadcast(h->cfg.comm, c->local_xyz.p, n * 12, owner, (void*)cs));
-      B2_TRY(b2_comm_broadcast(h->cfg.comm, c->local_nrm.p, n * 12, owner, (void*)cs));
+      // The broadcasts run on their own stream: behind this cloud's copy on the owner, behind nothing on the other ranks — whose
+      // call returns at once, so that THEIR next upload (a cloud they own) crosses PCIe at the same time as this one.
+      if (!c->ready_ev) B2_CUDA(cudaEventCreateWithFlags(&c->ready_ev, cudaEventDisableTiming));
+      if (owner == h->cfg.rank) { B2_CUDA(cudaEventRecord(c->ready_ev, cs)); B2_CUDA(cudaStreamWaitEvent(h->bcast_stream, c->ready_ev, 0)); }
+      B2_TRY(b2_comm_broadcast(h->cfg.comm, c->local_xyz.p, n * 12, owner, (void*)h->bcast_stream));
+      B2_TRY(b2_comm_broadcast(h->cfg.comm, c->local_nrm.p, n * 12, owner, (void*)h->bcast_stream));
+      B2_CUDA(cudaEventRecord(c->ready_ev, h->bcast_stream));
     }
   }
   // while this cloud's bytes are on the wire: the search index of the previously added cloud (index_distance_hint)
   const int rc = build_pending_index(h);
-  if (n) B2_CUDA(cudaStreamSynchronize(h->copy_stream));   // the caller may free / reuse its buffers after return
+  if (n && (owner < 0 || owner == h->cfg.rank)) B2_CUDA(cudaStreamSynchronize(h->copy_stream));   // the caller may free / reuse its buffers after return
   return rc;
 }
 
@@ -265,6 +272,10 @@ static int grid_for_cloud(Cloud* c, const float fmin[3], const float fmax[3], fl
 // One-time index of a cloud (K1, K2): AABB in the cloud frame -> grid -> keys -> radix sort -> cell-sorted rows, inverse
 // permutation, occupied-cell table. The sort is the only library call (cub::DeviceRadixSort) and it is off the per-iteration path.
 static int cloud_local_box(b2_icp* h, Cloud* c) {
+  if (c->ready_ev) {       // sharded upload: everything that touches the cloud comes after this point
+    B2_CUDA(cudaEventSynchronize(c->ready_ev));
+    cudaEventDestroy(c->ready_ev); c->ready_ev = nullptr;
+  }
   if (c->have_lbox) return B2_OK;
   for (int d = 0; d < 3; ++d) { c->lmin[d] = INFINITY; c->lmax[d] = -INFINITY; }
   if (c->n) {
@@ -915,6 +926,7 @@ int b2_icp_create(const b2_icp_config* cfg, b2_icp** out) {
   if (c.stream) { h->stream = (cudaStream_t)c.stream; }
   else { B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
   B2_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  B2_CUDA(cudaStreamCreateWithFlags(&h->bcast_stream, cudaStreamNonBlocking));
   if (const char* e = getenv("B2_K3_STREAMS")) h->nsearch = std::max(1, std::min((int)b2_icp::kMaxSearchStreams, atoi(e)));
   if (const char* e = getenv("B2_K3_WORK")) h->work_stats = e[0] && e[0] != '0';
   for (int i = 0; i + 1 < h->nsearch; ++i) {
@@ -934,6 +946,7 @@ int b2_icp_destroy(b2_icp* h) {
   cudaStreamSynchronize(h->stream);
   auto free_cloud = [](Cloud* c) {
     if (!c) return;
+    if (c->ready_ev) { cudaEventSynchronize(c->ready_ev); cudaEventDestroy(c->ready_ev); c->ready_ev = nullptr; }
     for (DevBuf* b : {&c->local_xyz, &c->local_nrm, &c->l_xyz, &c->l_nrm, &c->perm_inv, &c->rb, &c->starts, &c->s_xyz, &c->s_nrm, &c->table, &c->box1, &c->box2}) b->release();
   };
   for (auto& c : h->movable) free_cloud(c.get());
@@ -949,6 +962,7 @@ int b2_icp_destroy(b2_icp* h) {
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   for (DevBuf& b : h->search_tmp) b.release();
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->bcast_stream) { cudaStreamSynchronize(h->bcast_stream); cudaStreamDestroy(h->bcast_stream); }
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return B2_OK;

@@ -226,6 +226,7 @@ static Levels levels_of(const b2_reg* h, const ImageB& im, const IntrinsicsB& in
   L.nlevels = (int)in.models.size(); L.min_image_scale = in.min_image_scale;
   for (int l = 0; l < L.nlevels; ++l) {
     L.cam[l] = in.models[l];
+    L.iw[l] = im.lw[l];
     L.img[l] = im.img[l].as<unsigned char>();
     L.mask[l] = im.has_mask ? im.mask[l].as<unsigned char>() : nullptr;
   }
@@ -861,6 +862,54 @@ int b2_reg_set_comm(b2_reg* h, b2_comm* comm) {
   return B2_OK;
 }
 
+// One pyramid level (image.cc:106-154). Masks: OR of the 2x2 block (the last row / column of an odd parent is ignored, :139-150).
+// Images: cv::resize INTER_AREA with dsize given — integer 2x2 mean when both parents are even, the general area filter otherwise
+// (OpenCV resize.cpp computeResizeAreaTab / resizeArea_, restated; pinned against cv2 in tests/test_oracle_reg.py and, on the device,
+// tests/test_gpu_reg.py). The level is zero-padded by one row past its last pixel (Levels::iw).
+static void area_taps(int ssize, int dsize, double scale, std::vector<AreaTapDev>* taps, std::vector<int>* ofs) {
+  taps->clear(); ofs->assign(1, 0);
+  for (int dx = 0; dx < dsize; ++dx) {
+    const double fsx1 = dx * scale, fsx2 = fsx1 + scale, cell = std::min(scale, ssize - fsx1);
+    int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+    sx2 = std::min(sx2, ssize - 1); sx1 = std::min(sx1, sx2);
+    if (sx1 - fsx1 > 1e-3) taps->push_back({sx1 - 1, (float)((sx1 - fsx1) / cell)});
+    for (int sx = sx1; sx < sx2; ++sx) taps->push_back({sx, float(1.0 / cell)});
+    if (fsx2 - sx2 > 1e-3) taps->push_back({sx2, (float)(std::min(std::min(fsx2 - sx2, 1.), cell) / cell)});
+    ofs->push_back((int)taps->size());
+  }
+}
+static int pyr_down_level(b2_reg* h, const DevBuf& src, int sw, int sh, DevBuf* dst, int dw, int dh, bool is_mask) {
+  const size_t px = (size_t)dw * dh, pad = (size_t)dw + 2;
+  B2_TRY(dst->ensure(px + pad));
+  B2_CUDA(cudaMemsetAsync((unsigned char*)dst->p + px, 0, pad, h->stream));
+  dim3 g(divup(dw, 256), dh);
+  const double scale_x = 1. / ((double)dw / sw), scale_y = 1. / ((double)dh / sh);
+  if (is_mask || (scale_x == 2.0 && scale_y == 2.0)) {
+    kr_pyr_down<<<g, 256, 0, h->stream>>>(src.as<unsigned char>(), sw, dst->as<unsigned char>(), dw, dh, is_mask ? 1 : 0);
+    ++h->launches;
+    return B2_OK;
+  }
+  std::vector<AreaTapDev> xt, yt; std::vector<int> xo, yo;
+  area_taps(sw, dw, scale_x, &xt, &xo); area_taps(sh, dh, scale_y, &yt, &yo);
+  DevBuf tabs;       // [xt | yt | xofs | yofs]
+  const size_t b_xt = xt.size() * sizeof(AreaTapDev), b_yt = yt.size() * sizeof(AreaTapDev), b_xo = xo.size() * 4, b_yo = yo.size() * 4;
+  B2_TRY(tabs.ensure(b_xt + b_yt + b_xo + b_yo));
+  unsigned char* t = (unsigned char*)tabs.p;
+  cudaError_t e = cudaMemcpyAsync(t, xt.data(), b_xt, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(t + b_xt, yt.data(), b_yt, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(t + b_xt + b_yt, xo.data(), b_xo, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(t + b_xt + b_yt + b_xo, yo.data(), b_yo, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    kr_pyr_area<<<g, 256, 0, h->stream>>>(src.as<unsigned char>(), sw, dst->as<unsigned char>(), dw, dh, (const AreaTapDev*)t,
+                                          (const int*)(t + b_xt + b_yt), (const AreaTapDev*)(t + b_xt), (const int*)(t + b_xt + b_yt + b_xo));
+    ++h->launches;
+    e = cudaStreamSynchronize(h->stream);      // the pageable host tables and `tabs` go out of scope
+  }
+  tabs.release();
+  if (e != cudaSuccess) return set_error(B2_ERR_CUDA, "pyramid level failed: %s", cudaGetErrorString(e));
+  return B2_OK;
+}
+
 int b2_reg_initialize(b2_reg* h, int* image_scale_count) {
   REG_ENTER(h);
   if (h->intr.empty() || h->images.empty()) return set_error(B2_ERR_STATE, "initialize needs at least one intrinsics and one image");
@@ -891,35 +940,23 @@ int b2_reg_initialize(b2_reg* h, int* image_scale_count) {
     im.lw.assign(levels, 0); im.lh.assign(levels, 0);
     im.lw[0] = in.models[0].w; im.lh[0] = in.models[0].h;
     for (size_t l = 1; l < levels; ++l) {
-      if ((im.lw[l - 1] & 1) || (im.lh[l - 1] & 1))
-        return set_error(B2_ERR_ARG, "pyramid level %zu has odd size %dx%d: cv::resize INTER_AREA is only reproduced for even sizes (use sizes divisible by 2^(levels-1))",
-                         l - 1, im.lw[l - 1], im.lh[l - 1]);
+      // image.cc:115-118: dsize = (int(0.5 cols), int(0.5 rows)); the camera level may be one pixel larger (see Levels::iw)
       im.lw[l] = (int)(0.5 * im.lw[l - 1]); im.lh[l] = (int)(0.5 * im.lh[l - 1]);
-      if (im.lw[l] != in.models[l].w || im.lh[l] != in.models[l].h)
-        return set_error(B2_ERR_ARG, "image pyramid level %zu (%dx%d) and camera pyramid (%dx%d) disagree", l, im.lw[l], im.lh[l], in.models[l].w, in.models[l].h);
-      const size_t px = (size_t)im.lw[l] * im.lh[l];
-      B2_TRY(im.img[l].ensure(px));
-      dim3 g(divup(im.lw[l], 256), im.lh[l]);
-      kr_pyr_down<<<g, 256, 0, h->stream>>>(im.img[l - 1].as<unsigned char>(), im.lw[l - 1], im.img[l].as<unsigned char>(), im.lw[l], im.lh[l], 0);
-      ++h->launches;
-      if (im.has_mask) {
-        B2_TRY(im.mask[l].ensure(px));
-        kr_pyr_down<<<g, 256, 0, h->stream>>>(im.mask[l - 1].as<unsigned char>(), im.lw[l - 1], im.mask[l].as<unsigned char>(), im.lw[l], im.lh[l], 1);
-        ++h->launches;
-      }
+      if (im.lw[l] < 1 || im.lh[l] < 1) return set_error(B2_ERR_ARG, "image pyramid level %zu is empty (%dx%d parent)", l, im.lw[l - 1], im.lh[l - 1]);
+      B2_TRY(pyr_down_level(h, im.img[l - 1], im.lw[l - 1], im.lh[l - 1], &im.img[l], im.lw[l], im.lh[l], false));
+      if (im.has_mask) B2_TRY(pyr_down_level(h, im.mask[l - 1], im.lw[l - 1], im.lh[l - 1], &im.mask[l], im.lw[l], im.lh[l], true));
     }
   }
   for (auto& kv : h->cam_masks) {                                         // camera-mask pyramids (image.cc:62-72 + BuildMaskPyramid)
     const IntrinsicsB& in = h->intr[kv.first];
     std::vector<DevBuf>& pyr = kv.second;
     pyr.resize(in.models.size());
+    int w = in.models[0].w, hh = in.models[0].h;
     for (size_t l = 1; l < in.models.size(); ++l) {
-      const Cam &a = in.models[l - 1], &b = in.models[l];
-      if ((int)(0.5 * a.w) != b.w || (int)(0.5 * a.h) != b.h) return set_error(B2_ERR_ARG, "camera mask pyramid level %zu disagrees with the camera pyramid", l);
-      B2_TRY(pyr[l].ensure((size_t)b.w * b.h));
-      dim3 g(divup(b.w, 256), b.h);
-      kr_pyr_down<<<g, 256, 0, h->stream>>>(pyr[l - 1].as<unsigned char>(), a.w, pyr[l].as<unsigned char>(), b.w, b.h, 1);
-      ++h->launches;
+      const int dw = (int)(0.5 * w), dh = (int)(0.5 * hh);                // the sizes of the image pyramid, not of the camera pyramid
+      if (dw < 1 || dh < 1) return set_error(B2_ERR_ARG, "camera mask pyramid level %zu is empty", l);
+      B2_TRY(pyr_down_level(h, pyr[l - 1], w, hh, &pyr[l], dw, dh, true));
+      w = dw; hh = dh;
     }
   }
   B2_CUDA(cudaGetLastError());
@@ -1097,7 +1134,7 @@ int b2_reg_min_max_point_radius(b2_reg* h, const float* xyz, size_t n, double mi
     RadiusParams V;
     V.P = pose3_of(im.pose); V.cam = in.model(best); V.cam0 = in.model(0); V.image_scale = best; V.min_image_scale = in.min_image_scale;
     V.level = best - in.min_image_scale;
-    V.depth = depth; V.mask = L.mask[V.level]; V.cmask = L.cmask[V.level]; V.img = L.img[V.level];
+    V.depth = depth; V.mask = L.mask[V.level]; V.cmask = L.cmask[V.level]; V.img = L.img[V.level]; V.iw = L.iw[V.level];
     V.occlusion_threshold = h->prm.occlusion_depth_threshold; V.max_valid_intensity = h->prm.maximum_valid_intensity;
     V.min_scaling_factor = min_scaling_factor;
     V.table = nullptr;

@@ -28,6 +28,11 @@ struct Levels {
   const unsigned char* img[kMaxLevels];
   const unsigned char* mask[kMaxLevels];   // null = no mask at that level
   const unsigned char* cmask[kMaxLevels];  // camera mask of the intrinsics (intrinsics.h:104), null = none
+  // Row pitch of img / mask / cmask at each level. Not always cam[l].w: the image pyramid TRUNCATES the halved size (image.cc:116),
+  // the camera pyramid ROUNDS it (camera_base_impl.h:72), and the reference's bounds tests use the camera's size — so below an
+  // odd-sized parent the last column tapped lies one past the image row and the (unchecked) cv::Mat access reads the first pixel of
+  // the next row. Indexing with the image's own pitch reproduces exactly that; the buffers are zero-padded past their last pixel.
+  int iw[kMaxLevels];
   int nlevels, min_image_scale;
 };
 
@@ -76,9 +81,9 @@ __device__ __forceinline__ void bilinear_d(const unsigned char* __restrict__ im,
 }
 // interpolate_trilinear.h:44-87: image0 = smaller level, image1 = twice the size.
 __device__ __forceinline__ float trilinear(const Levels& L, int small_level, float x0, float y0, float z) {
-  const float v0 = bilinear(L.img[small_level], L.cam[small_level].w, x0, y0);
+  const float v0 = bilinear(L.img[small_level], L.iw[small_level], x0, y0);
   const float x1 = 2 * (x0 + 0.5f) - 0.5f, y1 = 2 * (y0 + 0.5f) - 0.5f;
-  const float v1 = bilinear(L.img[small_level - 1], L.cam[small_level - 1].w, x1, y1);
+  const float v1 = bilinear(L.img[small_level - 1], L.iw[small_level - 1], x1, y1);
   return (1 - z) * v0 + z * v1;
 }
 
@@ -89,6 +94,27 @@ __global__ void __launch_bounds__(256) kr_pyr_down(const unsigned char* __restri
   if (x >= dw || y >= dh) return;
   const unsigned char* r0 = src + (size_t)(2 * y) * sw + 2 * x; const unsigned char* r1 = r0 + sw;
   dst[(size_t)y * dw + x] = is_mask ? (unsigned char)(r0[0] | r0[1] | r1[0] | r1[1]) : (unsigned char)((r0[0] + r0[1] + r1[0] + r1[1] + 2) >> 2);
+}
+
+// General cv::resize INTER_AREA (the parent is odd in x or y, so a scale is not the integer 2): per axis a table of (source index, alpha)
+// taps with fractional coverage at the cell borders, `ofs[d] .. ofs[d+1]` the taps of destination index d. One thread per destination
+// pixel runs OpenCV's loop nest for that pixel in the same order (resizeArea_: per source row buf = sum S * alpha over the x taps, then
+// sum (+)= beta * buf), fp32 without contraction, saturate_cast<uchar> = round half to even. Tables: host, area_taps() in b2_reg.cu.
+struct AreaTapDev { int si; float alpha; };
+__global__ void __launch_bounds__(256) kr_pyr_area(const unsigned char* __restrict__ src, int sw, unsigned char* __restrict__ dst, int dw, int dh,
+                                                   const AreaTapDev* __restrict__ xt, const int* __restrict__ xofs,
+                                                   const AreaTapDev* __restrict__ yt, const int* __restrict__ yofs) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= dw || y >= dh) return;
+  const int xb = xofs[x], xe = xofs[x + 1], yb = yofs[y], ye = yofs[y + 1];
+  float sum = 0.f;
+  for (int j = yb; j < ye; ++j) {
+    const unsigned char* S = src + (size_t)yt[j].si * sw;
+    float buf = 0.f;
+    for (int k = xb; k < xe; ++k) buf = buf + (float)__ldg(S + xt[k].si) * xt[k].alpha;
+    sum = j == yb ? yt[j].alpha * buf : sum + yt[j].alpha * buf;
+  }
+  dst[(size_t)y * dw + x] = (unsigned char)min(255, max(0, __float2int_rn(sum)));
 }
 
 __global__ void __launch_bounds__(256) kr_fill_u32(unsigned int* __restrict__ p, size_t n, unsigned int v) {
@@ -315,9 +341,10 @@ __global__ void __launch_bounds__(256) kr_visibility(const float* __restrict__ x
           bool keep = true;
           if (V.check_masks) {
             const int level = small - L.min_image_scale;
-            if (L.mask[level] != nullptr && __ldg(L.mask[level] + (size_t)jiy * ic.w + jix) != 0) keep = false;
-            else if (L.cmask[level] != nullptr && __ldg(L.cmask[level] + (size_t)jiy * ic.w + jix) != 0) keep = false;
-            else if ((float)__ldg(L.img[level] + (size_t)jiy * ic.w + jix) > V.max_valid_intensity) keep = false;
+            const size_t jpix = (size_t)jiy * L.iw[level] + jix;
+            if (L.mask[level] != nullptr && __ldg(L.mask[level] + jpix) != 0) keep = false;
+            else if (L.cmask[level] != nullptr && __ldg(L.cmask[level] + jpix) != 0) keep = false;
+            else if ((float)__ldg(L.img[level] + jpix) > V.max_valid_intensity) keep = false;
           }
           if (keep) { ok = 1; rx_ = jx; ry_ = jy; rs_ = observation_scale; }
         }
@@ -331,7 +358,7 @@ __global__ void __launch_bounds__(256) kr_visibility(const float* __restrict__ x
 // (visibility_estimator.cc:296-364): one thread per point, one launch per image (images in sequence on one stream, so the per-point
 // min / max need no atomics). cam0 / table: the camera of image scale `min_image_scale` and its undistortion lookup (null for pinhole).
 struct RadiusParams {
-  Pose3 P; Cam cam; Cam cam0; int image_scale, min_image_scale, level;
+  Pose3 P; Cam cam; Cam cam0; int image_scale, min_image_scale, level, iw;   // iw: row pitch of mask / cmask / img (Levels::iw)
   const float* depth; const unsigned char* mask; const unsigned char* cmask; const unsigned char* img;
   const float2* table;
   float occlusion_threshold, max_valid_intensity; double min_scaling_factor;
@@ -346,7 +373,7 @@ __global__ void __launch_bounds__(256) kr_min_max_radius(const float* __restrict
   const int ix = f2i_x86(ixx + 0.5f), iy = f2i_x86(ixy + 0.5f);
   if (!(ixx + 0.5f >= 0 && ixy + 0.5f >= 0 && ix >= 0 && iy >= 0 && ix < V.cam.w && iy < V.cam.h &&
         (V.depth == nullptr || __ldg(V.depth + (size_t)iy * V.cam.w + ix) + V.occlusion_threshold >= pz))) return;
-  const size_t pix = (size_t)iy * V.cam.w + ix;
+  const size_t pix = (size_t)iy * V.iw + ix;
   if (V.mask != nullptr && __ldg(V.mask + pix) != 0) return;
   if (V.cmask != nullptr && __ldg(V.cmask + pix) != 0) return;
   if ((float)__ldg(V.img + pix) > V.max_valid_intensity) return;
@@ -467,9 +494,9 @@ __global__ void __launch_bounds__(256) kr_jacobians(size_t count, const unsigned
   const int sl = smaller - L.min_image_scale;
   const float z = 1 - (s - (int)s);
   float v0, d0x, d0y, v1, d1x, d1y;
-  bilinear_d(L.img[sl], L.cam[sl].w, x0, y0, &v0, &d0x, &d0y);
+  bilinear_d(L.img[sl], L.iw[sl], x0, y0, &v0, &d0x, &d0y);
   const float x1 = 2 * (x0 + 0.5f) - 0.5f, y1 = 2 * (y0 + 0.5f) - 0.5f;
-  bilinear_d(L.img[sl - 1], L.cam[sl - 1].w, x1, y1, &v1, &d1x, &d1y);
+  bilinear_d(L.img[sl - 1], L.iw[sl - 1], x1, y1, &v1, &d1x, &d1y);
   inten[i] = (1 - z) * v0 + z * v1;
   float ji0 = (1 - z) * d0x + z * 2 * d1x;
   float ji1 = (1 - z) * d0y + z * 2 * d1y;

@@ -37,7 +37,15 @@ namespace orc {
 
 typedef Camera Pinhole;   // historical name: one pyramid level of a camera model (orc_camera.h)
 
-struct Img8 { int w = 0, h = 0; std::vector<uint8_t> d; uint8_t at(int y, int x) const { return d[(size_t)y * w + x]; } };
+// Row-major u8 image with pitch w, addressed like cv::Mat_<uint8_t>::operator()(row, col) in a release build: no bounds check, so a
+// column index == w reads the first pixel of the next row. That matters: for odd-sized pyramid parents the reference's image level is
+// one column narrower than its camera level (image.cc:116 truncates, camera_base_impl.h:72 rounds) while the bounds tests use the
+// camera's size (visibility_estimator.cc:479), so the last interpolation column reads across the row end. Past the last pixel the
+// reference reads unallocated memory; defined here (and in the CUDA path) as 0.
+struct Img8 {
+  int w = 0, h = 0; std::vector<uint8_t> d;
+  uint8_t at(int y, int x) const { const size_t i = (size_t)y * w + x; return i < d.size() ? d[i] : (uint8_t)0; }
+};
 struct ImgF { int w = 0, h = 0; std::vector<float> d; float at(int y, int x) const { return d[(size_t)y * w + x]; } };
 
 // interpolate_bilinear.h:36-74
@@ -148,16 +156,55 @@ namespace orc {
 static int K(const orc_reg* h) { return h->prm.point_neighbor_count; }
 
 // ---- pyramids ----
-static bool build_image_pyramid(std::vector<Img8>& pyr) {   // image.cc:106-131, even parents only
-  for (size_t i = 1; i < pyr.size(); ++i) {
-    const Img8& s = pyr[i - 1];
-    Img8& d = pyr[i];
-    d.w = (int)(0.5 * s.w); d.h = (int)(0.5 * s.h);
-    if ((s.w & 1) || (s.h & 1)) return false;
-    d.d.resize((size_t)d.w * d.h);
+// cv::resize(src, dst, dsize = (int(0.5 cols), int(0.5 rows)), 0.5, 0.5, INTER_AREA) as image.cc:115-118 calls it. OpenCV (imgproc
+// resize.cpp; not vendored: restated from its published algorithm, pinned against cv2 in tests/test_oracle_reg.py):
+//   scale = 1 / ((double)dsize / ssize) per axis (dsize wins over fx, fy); both scales == 2 -> integer 2x2 mean (a+b+c+d+2)>>2;
+//   otherwise the general area filter: per axis a table of (dst, src, alpha) with fractional coverage at the cell borders
+//   (computeResizeAreaTab), float accumulation in table order, beta * row sums, saturate_cast<uchar> = round half to even.
+struct AreaTap { int di, si; float alpha; };
+static std::vector<AreaTap> resize_area_tab(int ssize, int dsize, double scale) {
+  std::vector<AreaTap> tab;
+  for (int dx = 0; dx < dsize; ++dx) {
+    const double fsx1 = dx * scale, fsx2 = fsx1 + scale, cell = std::min(scale, ssize - fsx1);
+    int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+    sx2 = std::min(sx2, ssize - 1); sx1 = std::min(sx1, sx2);
+    if (sx1 - fsx1 > 1e-3) tab.push_back({dx, sx1 - 1, (float)((sx1 - fsx1) / cell)});
+    for (int sx = sx1; sx < sx2; ++sx) tab.push_back({dx, sx, float(1.0 / cell)});
+    if (fsx2 - sx2 > 1e-3) tab.push_back({dx, sx2, (float)(std::min(std::min(fsx2 - sx2, 1.), cell) / cell)});
+  }
+  return tab;
+}
+static void resize_area_half(const Img8& s, Img8& d) {
+  d.w = (int)(0.5 * s.w); d.h = (int)(0.5 * s.h);
+  d.d.assign((size_t)d.w * d.h, 0);
+  if (d.w == 0 || d.h == 0) return;
+  const double scale_x = 1. / ((double)d.w / s.w), scale_y = 1. / ((double)d.h / s.h);
+  if (scale_x == 2.0 && scale_y == 2.0) {
     for (int y = 0; y < d.h; ++y) for (int x = 0; x < d.w; ++x)
       d.d[(size_t)y * d.w + x] = (uint8_t)((s.at(2 * y, 2 * x) + s.at(2 * y, 2 * x + 1) + s.at(2 * y + 1, 2 * x) + s.at(2 * y + 1, 2 * x + 1) + 2) >> 2);
+    return;
   }
+  const std::vector<AreaTap> xt = resize_area_tab(s.w, d.w, scale_x), yt = resize_area_tab(s.h, d.h, scale_y);
+  std::vector<float> buf(d.w), sum(d.w, 0.f);
+  auto flush = [&](int dy) {
+    for (int x = 0; x < d.w; ++x) { const long r = lrintf(sum[x]); d.d[(size_t)dy * d.w + x] = (uint8_t)std::min(255l, std::max(0l, r)); }
+  };
+  int prev = -1;
+  for (const AreaTap& ty : yt) {
+    std::fill(buf.begin(), buf.end(), 0.f);
+    for (const AreaTap& tx : xt) buf[tx.di] += s.at(ty.si, tx.si) * tx.alpha;
+    if (ty.di != prev) {
+      if (prev >= 0) flush(prev);
+      for (int x = 0; x < d.w; ++x) sum[x] = ty.alpha * buf[x];
+      prev = ty.di;
+    } else {
+      for (int x = 0; x < d.w; ++x) sum[x] += ty.alpha * buf[x];
+    }
+  }
+  if (prev >= 0) flush(prev);
+}
+static bool build_image_pyramid(std::vector<Img8>& pyr) {   // image.cc:106-131
+  for (size_t i = 1; i < pyr.size(); ++i) resize_area_half(pyr[i - 1], pyr[i]);
   return true;
 }
 static void build_mask_pyramid(std::vector<Img8>& pyr) {    // image.cc:133-154

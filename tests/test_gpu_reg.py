@@ -187,8 +187,12 @@ def test_reg_error_paths():
         r.initialize()                                                  # nothing added yet
     r.add_intrinsics(70, 50, [50, 50, 32, 24])
     r.add_image(0, np.zeros((50, 70), np.uint8), None, [0, 0, 0, 1, 0, 0, 0])
+    assert r.initialize() == 3                                          # 70x50 -> 35x25 -> 17x12: odd parents are fine (image.cc:115-118)
+    r2 = b2.Registration(registration.default_params(image_scale_count_override=4))
+    r2.add_intrinsics(6, 5, [5, 5, 3, 2])
+    r2.add_image(0, np.zeros((5, 6), np.uint8), None, [0, 0, 0, 1, 0, 0, 0])
     with pytest.raises(B2Error):
-        r.initialize()                                                  # 70x50 -> 35x25 -> odd parent for a 3rd level
+        r2.initialize()                                                 # 6x5 -> 3x2 -> 1x1 -> empty: the reference's "Resizing failed"
 
 
 from mesh_util import _box_mesh, _grid_mesh  # noqa: E402
@@ -288,3 +292,42 @@ def test_camera_mask(oracle, scene):
     g.add_intrinsics(w, h, K)
     with pytest.raises(Exception):
         g.set_camera_mask(3, cmask)
+
+
+def test_odd_sized_pyramid_levels(oracle):
+    """750x500 images: the pyramid is 750x500 -> 375x250 -> 187x125 while the camera pyramid ends at 188x125 (image.cc:116 truncates,
+    camera_base_impl.h:72 rounds) — the shape of BASELINE config 4's 6000x4000 images at levels 4 -> 5. The 375 -> 187 level goes
+    through cv::resize's general INTER_AREA path (fractional coverage); the oracle's is pinned against cv2 (tests/test_oracle_reg.py).
+    Everything downstream must agree: observations bit-exact, intensities / cost / normal equations as for even sizes."""
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import registration
+    from dataset_pipeline_b200.synth import reg_scene
+    scene = reg_scene.make_scene(num_images=2, width=750, height=500, fx=610.0, base_radius=0.002, extent=(3.2, 2.4))   # the plane overfills the images
+    w, h, K = scene["intr"]
+    mask = np.zeros((h, w), np.uint8); mask[60:140, 500:700] = 1; mask[401:499, 3:90] = 1
+    g = b2.Registration(registration.default_params()); o = oracle.Registration(oracle.reg_default_params())
+    for r in (g, o):
+        r.add_intrinsics(w, h, K)
+        r.add_image(0, scene["images"][0], mask, scene["poses_init"][0])
+        r.add_image(0, scene["images"][1], None, scene["poses_init"][1])
+        assert r.initialize() == 3
+        for xyz, radius, nbr, colors in scene["scales"]:
+            r.add_point_scale(xyz, float(radius), nbr, colors)
+        r.set_splat_points(scene["scales"][0][0])
+    for s in (1, 0):
+        g.set_image_scale(s); o.set_image_scale(s)
+        g.CreateObservationsForAllImages(1); o.create_observations(1)
+        assert _obs_equal(g, o, 2, 3) > 20000
+        I, jK, jP = g.point_jacobians(1, 1)
+        for k in np.linspace(0, len(I) - 1, 400).astype(int):
+            Io, jKo, jPo = o.point_jacobians(1, 1, int(k))
+            assert abs(I[k] - Io) <= 1e-5 * max(1, abs(Io))
+            assert np.allclose(jK[k], jKo, rtol=1e-5, atol=1e-5) and np.allclose(jP[k], jPo, rtol=1e-5, atol=1e-4)
+        g.ColorOptimizerApply(); o.color_update()
+        cg, sg = g.ComputeCost(); co, so = o.cost()
+        assert sg[1] == so[1] and sg[3] == so[3] and abs(cg - co) <= 1e-9 * co
+        Hg, bg, _, _ = g.accumulate(); Ho, bo, _, _ = o.accumulate()
+        assert rel(Hg, Ho) <= 1e-5 and rel(bg, bo) <= 1e-5
+    # the coarsest observations really tap the 187-wide level up to its last column and beyond (camera width 188, border 1)
+    xs = np.concatenate([o.observations(im, 1)[1] for im in range(2)])
+    assert xs.max() > 185.5

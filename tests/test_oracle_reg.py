@@ -59,10 +59,17 @@ def test_robust_weighting(oracle):
 def test_image_pyramid_matches_opencv_inter_area(oracle):
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(0)
-    for (h, w) in ((30, 40), (240, 320), (64, 2)):
+    # even parents (integer 2x2 mean) and odd ones (general area filter with fractional coverage, image.cc:115-118 with dsize truncated):
+    # 375x250 -> 187x125 is level 4 -> 5 of BASELINE config 4's 6000x4000 images
+    for (h, w) in ((30, 40), (240, 320), (64, 2), (250, 375), (251, 375), (7, 11), (13, 13), (375, 750), (999, 1501), (5, 6), (6, 5), (3, 3),
+                   (125, 187), (62, 93), (250, 377)):
         img = rng.integers(0, 256, (h, w), dtype=np.uint8)
         ref = cv2.resize(img, (int(0.5 * w), int(0.5 * h)), fx=0.5, fy=0.5, interpolation=cv2.INTER_AREA)
-        assert np.array_equal(oracle.image_pyramid_level(img), ref)
+        assert np.array_equal(oracle.image_pyramid_level(img), ref), (h, w)
+    # smooth content too (rounding ties are likelier than on noise)
+    yy, xx = np.mgrid[0:251, 0:375]
+    img = ((np.sin(xx / 9.0) * np.cos(yy / 7.0) * 0.5 + 0.5) * 255).astype(np.uint8)
+    assert np.array_equal(oracle.image_pyramid_level(img), cv2.resize(img, (187, 125), fx=0.5, fy=0.5, interpolation=cv2.INTER_AREA))
 
 
 # ---- test_intrinsics_and_pose_optimizer.cc:101-336 -------------------------------------------------------------------
