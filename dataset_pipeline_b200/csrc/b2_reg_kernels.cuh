@@ -158,13 +158,16 @@ struct ClippedTri { float x[4], y[4], z[4]; int n; };   // camera-space polygon 
 __device__ __forceinline__ ClippedTri clip_triangle(const float* __restrict__ v, const unsigned int* __restrict__ f, size_t fi, const Pose3& P,
                                                     const Cam& cam, float min_depth) {
   float px[3], py[3], pz[3];
+  bool finite = true;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const size_t vi = f[3 * fi + k];
     rigid(P, v[3 * vi], v[3 * vi + 1], v[3 * vi + 2], &px[k], &py[k], &pz[k]);
-    cam_vertex_distort(cam, &px[k], &py[k], pz[k]);      // the renderer's vertex stage; clipping follows it, as in GL
+    finite = finite && isfinite(px[k]) && isfinite(py[k]) && isfinite(pz[k]);
+    if (finite) cam_vertex_distort(cam, &px[k], &py[k], pz[k]);      // the renderer's vertex stage; clipping follows it, as in GL
   }
   ClippedTri c; c.n = 0;
+  if (!finite) return c;      // a triangle with a non-finite vertex draws nothing (test_renderer.cc:77-82,204-206)
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int k2 = (k + 1) % 3;

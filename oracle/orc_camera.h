@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <vector>
 
 #include "orc_math.h"
 
@@ -468,16 +469,21 @@ struct Camera {
   }
   float generic_cutoff() const {
     const float kIncreaseFactor = 1.01f, inf = std::numeric_limits<float>::infinity();
+    // border pixels in the reference's order (camera_base_impl.h:418-447); the two results are a max and a min over them, so the pixels
+    // can be searched in parallel (test infrastructure: the search is 100 starts x 100 iterations per pixel)
+    std::vector<float> bx_, by_;
+    for (int x = 0; x < w; ++x) { bx_.push_back((float)x); by_.push_back(0.f); bx_.push_back((float)x); by_.push_back((float)(h - 1)); }
+    for (int y = 0; y < h; ++y) { bx_.push_back(0.f); by_.push_back((float)y); bx_.push_back((float)(w - 1)); by_.push_back((float)y); }
     float min_candidate = 0, max_candidate = inf;
-    auto test = [&](float px, float py) {
+    const long n = (long)bx_.size();
+#pragma omp parallel for schedule(dynamic, 16) reduction(max : min_candidate) reduction(min : max_candidate)
+    for (long i = 0; i < n; ++i) {
       float bx, by, s2; bool sa;
-      if (undistort_from_inside(fx_inv * px + cx_inv, fy_inv * py + cy_inv, &bx, &by, &s2, &sa)) {
+      if (undistort_from_inside(fx_inv * bx_[i] + cx_inv, fy_inv * by_[i] + cy_inv, &bx, &by, &s2, &sa)) {
         min_candidate = std::max(bx * bx + by * by, min_candidate);
         if (sa) max_candidate = std::min(s2, max_candidate);
       }
-    };
-    for (int x = 0; x < w; ++x) { test((float)x, 0.f); test((float)x, (float)(h - 1)); }
-    for (int y = 0; y < h; ++y) { test(0.f, (float)y); test((float)(w - 1), (float)y); }
+    }
     return std::min(min_candidate * kIncreaseFactor, max_candidate);
   }
 

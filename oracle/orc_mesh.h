@@ -178,7 +178,15 @@ static void raster_mesh(const OccMesh& m, const RasterCam& c, const float R[9], 
   const M3f& M = *reinterpret_cast<const M3f*>(R);
   for (size_t fi = 0; fi < m.f.size() / 3; ++fi) {
     V3f p[3];
-    for (int k = 0; k < 3; ++k) { const V3f r = mul(M, v3(&m.v[3 * m.f[3 * fi + k]])); p[k] = V3f{r.x + t.x, r.y + t.y, r.z + t.z}; vertex_distort(c, &p[k]); }
+    bool finite = true;
+    for (int k = 0; k < 3; ++k) {
+      const V3f r = mul(M, v3(&m.v[3 * m.f[3 * fi + k]])); p[k] = V3f{r.x + t.x, r.y + t.y, r.z + t.z};
+      finite = finite && std::isfinite(p[k].x) && std::isfinite(p[k].y) && std::isfinite(p[k].z);
+      if (finite) vertex_distort(c, &p[k]);
+    }
+    // a triangle with a non-finite vertex draws nothing: the reference's renderer test feeds such vertices (pixels that cannot be
+    // undistorted get x = y = depth * inf, test_renderer.cc:77-82) and requires depth 0 at their pixels (:204-206)
+    if (!finite) continue;
     // clip against z >= min_depth (after the vertex stage, as GL clips)
     V3f poly[4]; int np = 0;
     for (int k = 0; k < 3; ++k) {

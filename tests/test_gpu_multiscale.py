@@ -181,3 +181,30 @@ def test_compute_multi_res_point_cloud_pipeline(oracle):
         for a in range(1, 5):
             assert np.array_equal(got[a][k], ref[a][k]), (k, a)
         assert len(ref[1][k]) >= 52
+
+
+# ---- the reference's own tests (src/opt/test/test_multi_scale_point_cloud.cc) through the C ABI ---------------------------------
+def test_reference_merge_close_points_through_the_abi():
+    from dataset_pipeline_b200 import multiscale as MS
+    from tests.test_oracle_multiscale import check_ref_merge, ref_merge_inputs
+    xyz, colors, scans, max_radius = ref_merge_inputs()
+    check_ref_merge(xyz, colors, scans, max_radius, *MS.MergeClosePoints(1.0, 2, xyz, colors, scans, max_radius))
+
+
+def test_reference_preprocess_scans():
+    """test_multi_scale_point_cloud.cc:109-151 (host glue of the tool, mirrored in dataset_pipeline_b200/multiscale.py)."""
+    from dataset_pipeline_b200 import multiscale as MS
+    scans = [(np.array([[1, 2, 3]], np.float32), np.array([[5, 5, 5]], np.uint8)), (np.array([[7, 8, 9]], np.float32), np.array([[11, 11, 11]], np.uint8))]
+    pts, cols, idx = MS.PreprocessScans(scans)
+    assert len(pts) == len(cols) == len(idx) == 2
+    for i in range(2):
+        k = int(idx[i])
+        assert k in (0, 1) and np.allclose(pts[i], scans[k][0][0], rtol=5e-7) and np.isclose(cols[i], (5, 11)[k], rtol=5e-7)
+
+
+def test_reference_create_multi_scale_point_cloud_through_the_abi():
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import multiscale as MS
+    from dataset_pipeline_b200 import registration as R
+    from tests.test_oracle_multiscale import ref_create_inputs, run_ref_create
+    run_ref_create(b2.Registration(R.default_params(image_scale_count_override=3)), MS.CreateMultiScalePointCloud, ref_create_inputs())

@@ -331,3 +331,48 @@ def test_odd_sized_pyramid_levels(oracle):
     # the coarsest observations really tap the 187-wide level up to its last column and beyond (camera width 188, border 1)
     xs = np.concatenate([o.observations(im, 1)[1] for im in range(2)])
     assert xs.max() > 185.5
+
+
+@pytest.mark.parametrize("key", ["identical", "small_offset"])
+def test_reference_simple_two_frame_alignment_through_the_abi(oracle, key):
+    """The reference's end-to-end test (test_alignment.cc:50-84 + test_alignment_util.cc:134-330, data = its test_data/ as a fixture):
+    depth image -> coloured point cloud -> ComputeMultiResPointCloud -> RunOnCurrentScale over the image scales; translation error
+    <= 1e-2 of the scene depth, rotation error <= 1 degree. Also: the same iteration counts and optimum cost as the oracle's run."""
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import multiscale as MS
+    from dataset_pipeline_b200 import registration as R
+    from tests import ref_alignment as RA
+    info = RA.load_pair(key)
+    est, log = RA.process_one_pair(info, lambda **kw: b2.Registration(R.default_params(**kw)), MS.ComputeMultiResPointCloud,
+                                   lambda reg, it, thr, no: reg.RunOnCurrentScale(it, thr, no), lambda reg: reg.get_state()[1])
+    terr, ang = RA.error_metrics(info, est)
+    assert terr <= RA.TRANSLATION_THRESHOLD and ang <= RA.ROTATION_THRESHOLD_DEG, (terr, ang, log)
+    esto, logo = RA.process_one_pair(info, lambda **kw: oracle.Registration(oracle.reg_default_params(**kw)), oracle.ms_compute_multi_res_point_cloud,
+                                     lambda reg, it, thr, no: reg.run_on_current_scale(it, thr, no), lambda reg: reg.get_state()[1])
+    assert [(s, it, conv) for s, it, _, conv in log] == [(s, it, conv) for s, it, _, conv in logo]
+    for (_, _, cg, _), (_, _, co, _) in zip(log, logo):
+        assert abs(cg - co) <= 1e-5 * max(co, 1e-12)
+    assert np.abs(est - esto).max() <= 1e-4
+
+
+@pytest.mark.parametrize("idx", range(13))
+def test_reference_renderer_pixel_accuracy_through_the_abi(oracle, idx):
+    """The reference's renderer test (test_renderer.cc:43-315, thirteen camera models) against the CUDA depth pass (K8): the depth at
+    every 20th pixel equals its mesh vertex's depth within 5e-2 and the vertex reprojects onto the pixel within 1e-2 px; triangles with
+    vertices that cannot be undistorted draw nothing. Also bit-exact against the oracle's rasteriser."""
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import registration as R
+    from tests import ref_renderer as RR
+    from tests.test_oracle_reg import _render_ref_mesh
+    name, model, params = RR.cameras(oracle)[idx]
+    verts, faces, gw = RR.build_mesh(oracle, model, params)
+    kw = dict(image_scale_count_override=1, min_occlusion_depth=0.1, max_occlusion_depth=20.1, mask_occlusion_boundaries=0)
+    depth = _render_ref_mesh(b2.Registration(R.default_params(**kw)), model, params, verts, faces)
+    project = lambda n: R.camera_eval(model, 640, 480, params, "project", n)[0]
+    frac = RR.check(oracle, model, params, depth, verts, gw, project)
+    assert frac > 0.9, (name, frac)
+    ref = _render_ref_mesh(oracle.Registration(oracle.reg_default_params(**kw)), model, params, verts, faces)
+    same = depth == ref
+    # fisheye vertex stage: device atanf vs the oracle's correctly rounded one can move a vertex by an ulp, i.e. flip single edge pixels
+    assert same.mean() > (0.9995 if model in (oracle.CAM_BENCHMARK, oracle.CAM_FISHEYE_POLYNOMIAL_4, oracle.CAM_FISHEYE_POLYNOMIAL_TANGENTIAL,
+                                               oracle.CAM_RADIAL_FISHEYE, oracle.CAM_SIMPLE_RADIAL_FISHEYE, oracle.CAM_FOV) else 0.99999), (name, same.mean())

@@ -88,3 +88,71 @@ def test_create_scale_loop_structure(oracle):
     # merged points of one scale are at least the merge distance apart from every EARLIER centre's neighbourhood: centres of a scale
     # cannot be closer than... (they are averages, so only a weak sanity bound is asserted) and there are fewer of them at coarser scales
     assert len(scales[-1][1]) < len(scales[0][1])
+
+
+# ---- the reference's own tests: src/opt/test/test_multi_scale_point_cloud.cc ----------------------------------------------------
+def ref_merge_inputs():
+    """test_multi_scale_point_cloud.cc:37-70: three points in a row that merge (the middle one from another scan) + one far point."""
+    xyz = np.array([[0.1, 0, 0], [0.5, 0, 0], [0.9, 0, 0], [0.5, 0, 2]], np.float32)
+    colors = np.array([0, 44, 2, 99], np.float32)
+    scans = np.array([0, 1, 0, 1], np.uint8)
+    max_radius = np.array([13, 12, 11, 47], np.float32)
+    return xyz, colors, scans, max_radius
+
+
+def check_ref_merge(xyz, colors, scans, max_radius, ox, oc, os_, om):
+    """The assertions of test_multi_scale_point_cloud.cc:81-107 (EXPECT_FLOAT_EQ = 4 ulp)."""
+    assert len(ox) == len(oc) == len(os_) == 2
+    seen = set()
+    for i in range(2):
+        if os_[i] == 0:          # the merged first three input points; colour = mean over the winning scan's points only
+            assert np.allclose(ox[i], [0.5, 0, 0], rtol=5e-7, atol=1e-7) and np.isclose(oc[i], 1, rtol=5e-7) and np.isclose(om[i], 13, rtol=5e-7)
+        elif os_[i] == 1:        # the single far point of scan 1, untouched
+            assert np.array_equal(ox[i], xyz[3]) and oc[i] == colors[3] and om[i] == max_radius[3]
+        else:
+            raise AssertionError("invalid scan index %d" % os_[i])
+        seen.add(int(os_[i]))
+    assert seen == {0, 1}
+
+
+def test_reference_merge_close_points(oracle):
+    xyz, colors, scans, max_radius = ref_merge_inputs()
+    check_ref_merge(xyz, colors, scans, max_radius, *oracle.ms_merge_close_points(xyz, colors, scans, max_radius, 2, 1.0))
+
+
+def ref_create_inputs():
+    """test_multi_scale_point_cloud.cc:164-214: one 640x480 pinhole camera (fx = 640, fy = 480) in the default pose, a constant image,
+    one point in front of the camera and one behind it; minimum scaling factor 2^-2, 3 image scales."""
+    w, h = 640, 480
+    return dict(w=w, h=h, K=np.array([w, h, w / 2 - 0.5, h / 2 - 0.5], np.float32), image=np.full((h, w), 100, np.uint8),
+                pose=np.array([0, 0, 0, 1, 0, 0, 0], np.float32), points=np.array([[0, 0, 2], [0, 0, -2]], np.float32),
+                colors=np.array([12, 33], np.float32), scans=np.zeros(2, np.uint8), min_scaling_factor=float(np.float32(2.0 ** -2)))
+
+
+def run_ref_create(reg, create, ci):
+    """CreateMultiScalePointCloud on the reference test's input, then the test's assertions (:241-289)."""
+    reg.add_intrinsics(ci["w"], ci["h"], ci["K"])
+    reg.add_image(0, ci["image"], None, ci["pose"])
+    assert reg.initialize() == 3
+    reg.set_splat_points(ci["points"])
+    mmr = getattr(reg, "min_max_point_radius", None) or reg.ComputeMinMaxPointRadius
+    lo, hi = mmr(ci["points"], ci["min_scaling_factor"])
+    scales = create(ci["points"], ci["colors"], ci["scans"], lo, hi, 1)
+    assert len(scales) == 2                                   # the point in front of the camera, at 2 scales
+    for radius, xyz, col, si in scales:
+        assert len(xyz) == len(col) == len(si) == 1
+        assert col[0] == 12 and si[0] == 0 and np.array_equal(xyz[0], ci["points"][0])
+        reg.add_point_scale(xyz, float(radius), np.zeros((1, 5), np.uint64), col)
+    reg.set_image_scale(0)
+    (getattr(reg, "create_observations", None) or reg.CreateObservationsForAllImages)(0)
+    got = []
+    for ps in range(2):
+        idx, x, y, s, nb = reg.observations(0, ps)
+        assert len(idx) == 1, "wrong number of observations on point scale %d" % ps
+        got.append(float(s[0]))
+    assert any(0 <= s < 1 for s in got) and any(1 <= s < 2 for s in got)
+
+
+def test_reference_create_multi_scale_point_cloud(oracle):
+    ci = ref_create_inputs()
+    run_ref_create(oracle.Registration(oracle.reg_default_params(image_scale_count_override=3)), oracle.ms_create, ci)

@@ -244,3 +244,37 @@ def test_ref_point_intensity_and_jacobians_for_rig_fd(oracle):
             qo, to = oracle.se3_exp_left_mul(d, image_T_rig[:4].astype(np.float32), image_T_rig[4:].astype(np.float32))
             I1 = _make_rig_problem(oracle, base_intr, rig_T_global, np.concatenate([qo, to]), point, radius).point_jacobians_rig(1, 0, 0)[0]
             assert abs(d[c] * jR[c] - (I1 - I0)) < 1e-3, ("extrinsics", c)
+
+
+# ---- test_alignment.cc:50-84 (TestPairAlignment = TEST(Alignment, SimpleTwoFrame)) on the oracle ---------------------------------
+@pytest.mark.parametrize("key", ["identical", "small_offset"])
+def test_reference_simple_two_frame_alignment(oracle, key):
+    from tests import ref_alignment as RA
+    info = RA.load_pair(key)
+    est, log = RA.process_one_pair(
+        info, lambda **kw: oracle.Registration(oracle.reg_default_params(**kw)), oracle.ms_compute_multi_res_point_cloud,
+        lambda reg, it, thr, no: reg.run_on_current_scale(it, thr, no), lambda reg: reg.get_state()[1])
+    terr, ang = RA.error_metrics(info, est)
+    assert terr <= RA.TRANSLATION_THRESHOLD and ang <= RA.ROTATION_THRESHOLD_DEG, (terr, ang, log)
+
+
+# ---- test_renderer.cc:43-315 (depth assertions) on the oracle's software rasteriser ----------------------------------------------
+def _render_ref_mesh(reg, model, params, verts, faces):
+    reg.add_intrinsics(640, 480, params, camera_model=model)
+    reg.add_image(0, np.zeros((480, 640), np.uint8), None, np.array([0, 0, 0, 1, 0, 0, 0], np.float32))
+    assert reg.initialize() == 1
+    reg.set_mesh(verts, faces)
+    reg.set_image_scale(0)
+    return reg.render_depth(0)[0]
+
+
+@pytest.mark.parametrize("idx", range(13))
+def test_reference_renderer_pixel_accuracy(oracle, idx):
+    from tests import ref_renderer as RR
+    name, model, params = RR.cameras(oracle)[idx]
+    verts, faces, gw = RR.build_mesh(oracle, model, params)
+    reg = oracle.Registration(oracle.reg_default_params(image_scale_count_override=1, min_occlusion_depth=0.1, max_occlusion_depth=20.1,
+                                                        mask_occlusion_boundaries=0))
+    depth = _render_ref_mesh(reg, model, params, verts, faces)
+    frac = RR.check(oracle, model, params, depth, verts, gw, lambda n: oracle.cam_eval(model, 640, 480, params, "project", n))
+    assert frac > 0.9, (name, frac)
