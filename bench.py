@@ -424,6 +424,16 @@ def run_b200(args):
                "note": "each step: b2_icp_create + 8 x b2_icp_add_cloud from pinned host memory (static index built behind the uploads) + b2_icp_run(1 iteration from the "
                        "same poses as the corresponding timed step) + b2_icp_get_pose + destroy"}
 
+    # ---- the other half of BASELINE.json's metric: ImageRegistrator residual-evaluations/s (config 4; images sharded over the ranks) ----
+    secondary = None
+    if not args.no_secondary:
+        try:
+            import bench_reg
+            torch.cuda.set_stream(torch.cuda.default_stream())
+            secondary = bench_reg.secondary_line(world, rank, comm, local, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+        except Exception as e:      # the ICP line must not be lost to the secondary benchmark
+            secondary = {"error": repr(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -486,12 +496,8 @@ def run_b200(args):
         counts = {"C": mean("num_correspondences"), "n_acc": int(round(mean("inner_iterations"))) + 1, "n_cost": int(round(mean("lm_tries_total")))}
         cb = cpu_baseline_sample(args, counts)
         out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    if not args.no_secondary:
-        try:
-            import bench_reg
-            out["secondary"] = bench_reg.secondary_line(world, rank)
-        except Exception as e:      # the ICP line must not be lost to the secondary benchmark
-            out["secondary"] = {"error": repr(e)}
+    if secondary is not None:
+        out["secondary"] = secondary
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(out))

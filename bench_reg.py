@@ -1,12 +1,19 @@
 #!/usr/bin/env python
-"""Secondary benchmark (Path B, BASELINE.json configs[3]): ImageRegistrator residual-evaluations/s.
+"""Path B benchmark (BASELINE.json configs[3] / [4]): ImageRegistrator residual-evaluations/s.
 
-A residual evaluation = one (image, point scale, observation) through AccumulateHAndBAndResidualsForObservations pass 1+2
-(SURVEY.md §8d), i.e. one observation through kr_jacobians + kr_accumulate inside b2_reg_accumulate. The primary driver contract
-is bench.py (ICP); this script prints one JSON line with the same style of keys for BASELINE.md.
+Workload: N pinhole views (default 20 x 6000x4000, fx = fy = 4400) of the config-2 room — the scene the ICP
+benchmark scans — rendered by ray casting with a multi-octave albedo; the scan = three of the 10M-point room scans merged (30M points,
+coloured with the same albedo), turned into the multi-resolution point cloud by ComputeMultiResPointCloud on the device; the occlusion
+geometry = the room tessellated at 2 cm (1.8M triangles: depth pass K8 + boundary masking K9 per image). Initial state = ground truth
+perturbed by U(+-2 mm), U(+-0.05 deg), fx, fy +-0.1 %.
 
-Workload: N images (default 20 x 3008x2000, pinhole) of a textured plane rendered analytically on the GPU (harness only), a
-multi-resolution point cloud of grids on that plane (~default 30 M points), no occlusion geometry (all visible).
+A step = one iteration of Optimizer::RunOnCurrentScale at the finest image scale from that state (optimizer.cc:49-182):
+CreateObservationsForAllImages (depth maps, visibility, scale selection) + ColorOptimizer::Apply + IntrinsicsAndPoseOptimizer::Apply
+(accumulate H, b + LM tries). A residual evaluation = one (image, point scale, observation) through pass 1+2 of
+AccumulateHAndBAndResidualsForObservations (K11 + K12). value = residual evaluations per second of whole steps.
+
+    python bench_reg.py [--images 20 --width 6000 --height 4000 --steps 3 --warmup 1]      # one JSON line
+bench.py calls secondary_line() and puts the result under "secondary" of its own line (image-sharded under torchrun).
 """
 import argparse
 import json
@@ -20,191 +27,246 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "ImageRegistrator residual-evaluations/sec"
+UNIT = "residual-evaluations/s"
+FX = 4400.0 / 6000.0          # focal length as a fraction of the image width (fx = fy = 4400 at 6000 x 4000)
 
-def build_scene(num_images, width, height, target_points, seed=31, camera_model=4, owns=lambda i: True):
+
+def build_scene(num_images, width, height, scan_wh, device, need_image):
+    """-> dict(intr, params_init, images [uint8 HxW or None], poses_gt, poses_init, mesh (v, f), scans [(xyz global f32, rgb u8)])."""
     import torch
-    from dataset_pipeline_b200.synth import reg_scene as rs
-    dev = torch.device("cuda")
-    fx = 0.8125 * width
+    import bench as B
+    from dataset_pipeline_b200.synth import room_views as rv
+    fx = FX * width
     K = np.array([fx, fx, (width - 1) / 2.0, (height - 1) / 2.0], np.float32)
-    dist_p = rs.DEFAULT_DISTORTION
-    params = K if camera_model == rs.CAM_PINHOLE else np.concatenate([K, np.asarray(dist_p, np.float32)])
-    rng = np.random.default_rng(seed)
-    images, poses_gt, poses_init = [], [], []
-    yy, xx = torch.meshgrid(torch.arange(height, device=dev, dtype=torch.float64), torch.arange(width, device=dev, dtype=torch.float64), indexing="ij")
-
-    def tex(x, y):
-        v = (torch.sin(7.0 * x) * torch.cos(5.0 * y) + 0.6 * torch.sin(19.0 * x + 1.3) * torch.sin(23.0 * y + 0.4) + 0.35 * torch.cos(41.0 * x - 29.0 * y)
-             + 0.25 * torch.sin(83.0 * x + 61.0 * y) + 0.2 * torch.sin(211.0 * x - 173.0 * y) + 0.15 * torch.cos(431.0 * x + 389.0 * y))
-        return 120.0 + 40.0 * v
-
-    # pixel -> normalized ray coordinates (numerical inverse of the distortion for the non-pinhole models; harness only)
-    ncx = (xx - float(K[2])) / float(K[0]); ncy = (yy - float(K[3])) / float(K[1])
-    if camera_model != rs.CAM_PINHOLE:
-        k1, k2, p1, p2, k3, k4, sx1, sy1 = [float(v) for v in dist_p]
-        ux, uy = ncx.clone(), ncy.clone()
-        for _ in range(60):
-            x2, xy, y2 = ux * ux, ux * uy, uy * uy
-            r2 = x2 + y2
-            rad = 1 + r2 * (k1 + r2 * (k2 + r2 * (k3 + r2 * k4)))
-            fx_ = ux * rad + 2 * p1 * xy + p2 * (r2 + 2 * x2) + sx1 * r2
-            fy_ = uy * rad + 2 * p2 * xy + p1 * (r2 + 2 * y2) + sy1 * r2
-            ux = ux + 0.8 * (ncx - fx_); uy = uy + 0.8 * (ncy - fy_)
-        if camera_model == rs.CAM_BENCHMARK:
-            r = torch.sqrt(ux * ux + uy * uy)
-            f = torch.where(r > 1e-9, torch.tan(torch.clamp(r, max=1.5)) / torch.clamp(r, min=1e-9), torch.ones_like(r))
-            ux, uy = ux * f, uy * f
-        ncx, ncy = ux, uy
-    for i in range(num_images):
-        c = np.array([0.25 * math.cos(2.1 * i), 0.2 * math.sin(1.7 * i), 2.0 + 0.1 * math.sin(i)])
-        R_wc = rs.rot(math.pi + 0.08 * math.sin(1.3 * i), 0.07 * math.cos(0.9 * i), 0.3 * i)
-        R_cw = R_wc.T; t_cw = -R_cw @ c
-        poses_gt.append(np.concatenate([rs.quat_from_R(R_cw), t_cw]).astype(np.float32))
-        dR = rs.rot(*(rng.uniform(-0.0005, 0.0005, 3))); dt = rng.uniform(-0.001, 0.001, 3)
-        poses_init.append(np.concatenate([rs.quat_from_R(dR @ R_cw), dR @ t_cw + dt]).astype(np.float32))
-        if not owns(i):
-            images.append(None)
-            continue
-        Rt = torch.tensor(R_wc, device=dev)
-        dcx = ncx; dcy = ncy
-        dwx = Rt[0, 0] * dcx + Rt[0, 1] * dcy + Rt[0, 2]; dwy = Rt[1, 0] * dcx + Rt[1, 1] * dcy + Rt[1, 2]; dwz = Rt[2, 0] * dcx + Rt[2, 1] * dcy + Rt[2, 2]
-        s = -c[2] / dwz
-        img = torch.clamp(torch.round(tex(c[0] + dwx * s, c[1] + dwy * s)), 0, 255).to(torch.uint8).cpu().numpy()
-        images.append(img)
-    # multi-resolution grids: scale k has radius r0 * 2^k; pixel footprint of scale 0 ~ 0.6 px at the finest image scale
-    extent = (3.6, 2.6)
-    nscales = 6
-    # total points = sum_k (extent area / (2 r0 2^k)^2) = A/(4 r0^2) * 4/3
-    r0 = math.sqrt(extent[0] * extent[1] / (3.0 * target_points))
-    scales = []
-    for k in range(nscales):
-        radius = r0 * 2 ** k; step = 2 * radius
-        nx = int(extent[0] / step); ny = int(extent[1] / step)
-        if nx < 8 or ny < 8:
-            break
-        gx, gy = np.meshgrid(np.arange(nx, dtype=np.int64), np.arange(ny, dtype=np.int64), indexing="xy")
-        x = ((gx.ravel() - (nx - 1) / 2.0) * step).astype(np.float32); y = ((gy.ravel() - (ny - 1) / 2.0) * step).astype(np.float32)
-        xyz = np.stack([x, y, np.zeros_like(x)], 1)
-        def nb(dx, dy):
-            return (np.clip(gy + dy, 0, ny - 1) * nx + np.clip(gx + dx, 0, nx - 1)).ravel()
-        idx = (gy * nx + gx).ravel()
-        nbr = np.stack([nb(1, 0), nb(-1, 0), nb(0, 1), nb(0, -1), nb(1, 1)], 1)
-        alt = np.stack([nb(-2, 0), nb(2, 0), nb(0, -2), nb(0, 2), nb(-1, -1)], 1)
-        nbr = np.where(nbr == idx[:, None], alt, nbr).astype(np.uint64)
-        colors = tex(torch.tensor(x, device=dev, dtype=torch.float64), torch.tensor(y, device=dev, dtype=torch.float64)).float().cpu().numpy()
-        scales.append((xyz, np.float32(radius), nbr, colors))
-    return {"intr": (width, height, params), "camera_model": camera_model, "images": images, "poses_gt": poses_gt, "poses_init": poses_init, "scales": scales}
+    Rs, cs, gt, init = rv.view_poses(num_images)
+    images = [rv.render_view(width, height, fx, fx, float(K[2]), float(K[3]), Rs[i], cs[i], device, seed=31 + i).cpu().numpy() if need_image(i) else None
+              for i in range(num_images)]
+    rng = np.random.default_rng(32)
+    K_init = K.copy(); K_init[:2] *= (1.0 + rng.uniform(-1e-3, 1e-3, 2)).astype(np.float32)
+    W, H = scan_wh
+    B.ensure_scans(range(3), W, H)
+    _, gts = B.scene_poses(8)
+    scans = []
+    for i in range(3):
+        xyz, _ = B.load_scan(i, W, H)
+        T = gts[i].astype(np.float64)
+        g = (xyz.astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+        scans.append((g, rv.point_colors(g, device)))
+    torch.cuda.synchronize()
+    return {"intr": (width, height, K), "K_init": K_init, "images": images, "poses_gt": gt, "poses_init": init, "mesh": rv.room_mesh(0.02), "scans": scans}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--images", type=int, default=20)
-    ap.add_argument("--width", type=int, default=3008)
-    ap.add_argument("--height", type=int, default=2000)
-    ap.add_argument("--points", type=float, default=30e6)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--camera", default="pinhole", choices=["pinhole", "thin_prism", "benchmark"])
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--profile", action="store_true", help="finest image scale only; cudaProfilerStart/Stop around one CreateObservations + ColorOptimizer + accumulate "
-                    "(for `ncu --profile-from-start off`); prints no benchmark value")
-    a = ap.parse_args()
+def load(reg, sc, use_images):
+    w, h, _ = sc["intr"]
+    reg.add_intrinsics(w, h, sc["K_init"])
+    for img, T in zip(use_images, sc["poses_init"]):
+        reg.add_image(0, img, None, T)
+    count = reg.initialize()
+    reg.set_mesh(*sc["mesh"])
+    return count
+
+
+def secondary_line(world=1, rank=0, comm=None, local=0, num_images=20, width=6000, height=4000, scan_wh=(5000, 2000), steps=3, warmup=1,
+                   cpu_baseline=True, e2e=True):
+    """The Path B numbers as a dict (rank 0; other ranks take part and return None)."""
     import torch
-    if not torch.cuda.is_available():
-        raise SystemExit("bench_reg.py: no CUDA device — no CPU fallback")
     import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import multiscale as MS
     from dataset_pipeline_b200 import registration as R
-    from dataset_pipeline_b200.synth import reg_scene
-    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    comm = None
-    if world > 1:      # one process per GPU (torchrun); images dealt round-robin, the library's own NCCL communicator for the sums
-        import torch.distributed as dist
-        from dataset_pipeline_b200.icp import Comm
-        dist.init_process_group("gloo")
-        ids = [Comm.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, 0)
-        comm = Comm(rank, world, ids[0], device=local)
-    model = {"pinhole": 4, "thin_prism": 14, "benchmark": 5}[a.camera]
+    dev = torch.device("cuda", local)
+    owns = lambda i: i % world == rank
     t0 = time.perf_counter()
-    sc = build_scene(a.images, a.width, a.height, a.points, camera_model=model, owns=lambda i: i % world == rank)
-    t_gen = time.perf_counter() - t0
-    npts = sum(s[0].shape[0] for s in sc["scales"])
-    g = b2.Registration(R.default_params(device=local))
-    if comm is not None:
-        g.set_comm(comm)
-    nsc = reg_scene.load_into(g, sc, splats=False)
-    if a.profile:
-        g.set_image_scale(0)
-        g.CreateObservationsForAllImages(1); g.ColorOptimizerApply(); g.accumulate()
-        torch.cuda.synchronize()
-        torch.cuda.profiler.start()
-        g.CreateObservationsForAllImages(1); g.ColorOptimizerApply(); g.accumulate()
-        torch.cuda.synchronize()
-        torch.cuda.profiler.stop()
-        print(json.dumps({"profile": True, "stats": g.stats()}))
-        return
-    res = {}
-    for scale in (nsc - 2, 0):
-        g.set_image_scale(scale)
+    # the multi-resolution point cloud needs every image (ComputeMinMaxPointRadius): with several ranks each one builds it on a
+    # handle of its own that holds all images, then keeps only its share in the sharded handle (set-up, untimed)
+    sc = build_scene(num_images, width, height, scan_wh, dev, (lambda i: True))
+    t_scene = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    setup = b2.Registration(R.default_params(device=local))
+    count = load(setup, sc, sc["images"])
+    radii, pts, cols, sidx, nbrs = MS.ComputeMultiResPointCloud(setup, sc["scans"], count)
+    if world > 1:
+        setup.close(); del setup
+    t_multires = time.perf_counter() - t0
+    npts = int(sum(len(p) for p in pts))
+
+    def make():
+        if world == 1 and make.first is not None:
+            g, make.first = make.first, None
+        else:
+            g = b2.Registration(R.default_params(device=local))
+            if comm is not None:
+                g.set_comm(comm)
+            load(g, sc, [img if owns(i) else None for i, img in enumerate(sc["images"])])
+        for r, p, c, nb in zip(radii, pts, cols, nbrs):
+            g.add_point_scale(p, float(r), nb, c)
+        return g
+    make.first = setup if world == 1 else None
+
+    g = make()
+    state0 = g.get_state()
+    g.set_image_scale(0)
+
+    def step(g):
+        g.set_state(*state0)
         g.CreateObservationsForAllImages(1)
-        st_obs = g.stats()
+        ms_obs = g.stats()["ms_last_call"]; nobs = g.stats()["observations"]
         g.ColorOptimizerApply()
-        for _ in range(a.warmup):
-            g.accumulate()
-        torch.cuda.synchronize()
-        t = time.perf_counter()
-        ms_j = ms_a = 0.0
-        for _ in range(a.steps):
-            g.accumulate()
-            s = g.stats(); ms_j += s["ms_jacobian_kernel"]; ms_a += s["ms_accumulate_kernel"]
-        dt = (time.perf_counter() - t) / a.steps
-        if world > 1:   # the step time of the job is the slowest rank's
-            tt = torch.tensor([dt, ms_j, ms_a], dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); dt, ms_j, ms_a = [float(v) for v in tt]
-        evals = g.stats()["residual_evaluations"]
-        full = sum(int(g.observations(im, ps)[4].sum()) for im in range(min(2, a.images)) for ps in range(len(sc["scales"])))
-        res[scale] = {"image_scale": scale, "observations": st_obs["observations"], "ms_create_observations": st_obs["ms_last_call"],
-                      "residual_evaluations": evals, "s_per_accumulate": dt, "evals_per_s": evals / dt,
-                      "ms_jacobian_kernels": ms_j / a.steps, "ms_accumulate_kernels": ms_a / a.steps, "fully_observed_first2_images": full}
-    # one LM step + cost at the finest scale (end to end through the ABI)
-    t = time.perf_counter(); ap_ = g.IntrinsicsAndPoseOptimizerApply(64.0); torch.cuda.synchronize(); t_apply = time.perf_counter() - t
+        ms_col = g.stats()["ms_last_call"]
+        ap = g.IntrinsicsAndPoseOptimizerApply(64.0)
+        st = g.stats()
+        return {"observations": int(nobs), "ms_create_observations": ms_obs, "ms_color": ms_col, "ms_apply": st["ms_last_call"], "lm_tries": int(ap[3]),
+                "applied": bool(ap[0])}
+
+    def accumulate_only(g):
+        g.accumulate()
+        st = g.stats()
+        return int(st["residual_evaluations"]), float(st["ms_jacobian_kernel"]), float(st["ms_accumulate_kernel"]), float(st["ms_last_call"])
+
+    for _ in range(warmup):
+        step(g)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    parts = [step(g) for _ in range(steps)]
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / steps
+    # the accumulate pass alone (K11 + K12), at the state the last step left the observations in
+    g.set_state(*state0); g.CreateObservationsForAllImages(1); g.ColorOptimizerApply()
+    acc = [accumulate_only(g) for _ in range(max(2, steps))][1:]
+    evals = acc[-1][0]; ms_j = float(np.mean([a[1] for a in acc])); ms_a = float(np.mean([a[2] for a in acc])); ms_acc_call = float(np.mean([a[3] for a in acc]))
+    if world > 1:
+        tt = torch.tensor([dt, ms_j, ms_a, ms_acc_call], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt, ms_j, ms_a, ms_acc_call = [float(v) for v in tt]
+        te = torch.tensor([float(evals)], dtype=torch.float64, device=dev); dist.all_reduce(te, op=dist.ReduceOp.SUM); evals_local, evals = evals, int(te.item())
+    else:
+        evals_local = evals
+    g.close()
+
+    e2e_out = None
+    if e2e:
+        times = []
+        for s in range(2):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev); t0 = time.perf_counter()
+            ge = make(); ge.set_image_scale(0)
+            step(ge); _ = ge.get_state()
+            torch.cuda.synchronize(dev); d = time.perf_counter() - t0
+            ge.close()
+            if world > 1:
+                tt = torch.tensor([d], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); d = float(tt.item())
+            times.append(d)
+        h2d = sum(img.size for i, img in enumerate(sc["images"]) if owns(i)) + sum(p.nbytes + nb.nbytes + c.nbytes for p, nb, c in zip(pts, nbrs, cols)) \
+            + sc["mesh"][0].nbytes + sc["mesh"][1].nbytes
+        e2e_out = {"value": evals / times[-1], "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(8 * (124 * 124 + 124 + 8) * 8 + 7 * 4 * num_images),
+                   "seconds": times, "note": "b2_reg_create + intrinsics + images (host u8) + initialize (pyramids) + mesh + point scales (host arrays) + one optimizer "
+                                             "iteration + b2_reg_get_state + destroy; second of two runs"}
+    if rank != 0:
+        return None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    fin = res[0]
-    # K11 80 B/observation (pinhole K=4; 112 B with 12 intrinsics), K12 304 B/fully observed observation
-    bpo = 80.0 if model == 4 else 112.0
-    ach_j = bpo * (fin["residual_evaluations"] / world) / (fin["ms_jacobian_kernels"] * 1e-3) / 1e9 if fin["ms_jacobian_kernels"] else 0
-    if rank != 0:
-        if comm is not None:
-            dist.barrier(); comm.close(); dist.destroy_process_group()
-        return
-    out = {"metric": "ImageRegistrator residual-evaluations/sec", "value": fin["evals_per_s"], "unit": "residual-evaluations/s", "n_gpus": world,
-           "steps": a.steps, "warmup": a.warmup, "higher_is_better": True, "data": "synthetic", "dtype": "u8 images, f32 residuals/Jacobians, f64 accumulation",
-           "scaling": "strong", "config": {"workload": "%d " % a.images + a.camera + " views %dx%d vs %.1fM-pt multi-resolution scan (%d scales), no occlusion geometry" % (a.width, a.height, npts / 1e6, len(sc["scales"])),
-                      "image_scale_count": nsc, "scene_generation_s": t_gen},
-           "per_scale": res, "lm_apply": {"applied": ap_[0], "tries": ap_[3], "seconds": t_apply},
-           "roofline": {"bound": "hbm", "kernel": "kr_jacobians (K11, %d B/observation)" % int(bpo), "achieved": ach_j, "peak": peak, "unit": "GB/s", "frac": ach_j / peak,
-                        "traffic": None}}
-    if not a.no_cpu_baseline:
-        from oracle import oracle as orc
-        o = orc.Registration()
-        sub = dict(sc); sub["images"] = sc["images"][:1]; sub["poses_init"] = sc["poses_init"][:1]; sub["poses_gt"] = sc["poses_gt"][:1]
-        reg_scene.load_into(o, sub, splats=False)
-        o.set_image_scale(0)
-        t = time.perf_counter(); o.create_observations(1); t_obs = time.perf_counter() - t
-        o.color_update()
-        t = time.perf_counter(); o.accumulate(); t_acc = time.perf_counter() - t
-        n_o = sum(len(o.observations(0, ps)[0]) for ps in range(len(sc["scales"])))
-        out["cpu_baseline"] = {"value": n_o / t_acc, "unit": "residual-evaluations/s", "cores": 1, "kind": "port",
-                               "sample": "oracle (serial, as the reference) on image 0 of the same workload at the finest image scale: %d observations, accumulate %.1f s, create_observations %.1f s" % (n_o, t_acc, t_obs)}
-    print(json.dumps(out))
-    if comm is not None:
-        dist.barrier(); comm.close(); dist.destroy_process_group()
+    ach_j = 80.0 * evals_local / (ms_j * 1e-3) / 1e9 if ms_j > 0 else 0.0          # SURVEY §8d: K11 80 B / observation (pinhole, 4 intrinsics)
+    ach_a = 304.0 * evals_local / (ms_a * 1e-3) / 1e9 if ms_a > 0 else 0.0         # K12 304 B / fully observed observation (upper bound: all counted)
+
+    def traffic(name, algorithmic):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return tj["dram_over_algorithmic"] * algorithmic
+        except Exception:
+            return None
+    out = {"metric": METRIC, "value": evals / dt, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt,
+           "higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "u8 images, f32 residuals/Jacobians, f64 accumulation",
+           "config": {"workload": "ImageRegistrator: %d pinhole views %dx%d of the config-2 room vs %.1fM-pt multi-resolution scan (%d scales, from 3 x %.0fM-pt scans) + "
+                                  "occlusion mesh (%d triangles); 1 optimizer iteration at image scale 0 per step" % (
+                                      num_images, width, height, npts / 1e6, len(pts), scan_wh[0] * scan_wh[1] / 1e6, len(sc["mesh"][1])),
+                      "image_scale_count": count, "points_per_scale": [int(len(p)) for p in pts], "parallelism": "images sharded over %d GPU(s)" % world,
+                      "l2": "inputs larger than L2 (%.2f GB of image pyramids, %.2f GB of points / neighbours / descriptors)" % (
+                          num_images * width * height * 4 / 3 / 1e9, sum(p.nbytes + nb.nbytes / 2 + 2 * c.nbytes * 5 for p, nb, c in zip(pts, nbrs, cols)) / 1e9),
+                      "scene_generation_s": t_scene, "multires_build_s": t_multires},
+           "per_step": parts, "residual_evaluations_per_step": evals,
+           "accumulate_only": {"ms": ms_acc_call, "evals_per_s": evals / (ms_acc_call * 1e-3) if ms_acc_call else None, "ms_jacobian_kernels": ms_j, "ms_accumulate_kernels": ms_a},
+           "roofline": {"bound": "hbm", "kernel": "kr_jacobians (K11, 80 B/observation: xyz, observation, 8 u8 taps, I + 10 Jacobian floats)", "achieved": ach_j, "peak": peak,
+                        "unit": "GB/s", "frac": ach_j / peak, "traffic": traffic("reg_jacobians_traffic.json", 80.0 * evals_local),
+                        "algorithmic_bytes_per_launch_set": 80.0 * evals_local, "kernel_ms_per_accumulate": ms_j},
+           "roofline_second_kernel": {"bound": "hbm", "kernel": "kr_residual_weights + kr_accumulate_weighted (K12, 304 B/observation)", "achieved": ach_a, "peak": peak,
+                                      "unit": "GB/s", "frac": ach_a / peak, "traffic": traffic("reg_accumulate_traffic.json", 304.0 * evals_local),
+                                      "kernel_ms_per_accumulate": ms_a}}
+    if e2e_out:
+        out["e2e"] = e2e_out
+    if cpu_baseline:
+        out["cpu_baseline"] = cpu_sample(sc, radii, pts, cols, nbrs, evals)
+    return out
+
+
+def cpu_sample(sc, radii, pts, cols, nbrs, evals_full, views=(0, 1)):
+    """The oracle (serial, as the reference) on a bounded sample: one outward- and one inward-looking view of the same workload at full
+    resolution with the same occlusion mesh and point cloud — depth maps, observations, colour update, accumulate. Scaled by evaluations."""
+    from oracle import oracle as orc
+    orc.build()
+    o = orc.Registration(orc.reg_default_params())
+    w, h, _ = sc["intr"]
+    o.add_intrinsics(w, h, sc["K_init"])
+    for i in views:
+        o.add_image(0, sc["images"][i], None, sc["poses_init"][i])
+    o.initialize()
+    o.set_mesh(*sc["mesh"])
+    for r, p, c, nb in zip(radii, pts, cols, nbrs):
+        o.add_point_scale(p, float(r), nb, c)
+    o.set_image_scale(0)
+    t0 = time.perf_counter(); o.create_observations(1); t_obs = time.perf_counter() - t0
+    t0 = time.perf_counter(); o.color_update(); t_col = time.perf_counter() - t0
+    t0 = time.perf_counter(); o.accumulate(); t_acc = time.perf_counter() - t0
+    n_o = int(sum(len(o.observations(i, ps)[0]) for i in range(len(views)) for ps in range(len(pts))))
+    t_all = t_obs + t_col + t_acc
+    return {"value": n_o / t_all, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle (serial, as the reference's Path B) on views %s of the same workload at full resolution, same mesh and point cloud: %d residual evaluations; "
+                      "depth maps + observations %.1f s, colour update %.1f s, accumulate %.1f s (one LM try's cost evaluation not included: a lower bound of the "
+                      "reference's time per iteration)" % (list(views), n_o, t_obs, t_col, t_acc)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--images", type=int, default=20)
+    ap.add_argument("--width", type=int, default=6000)
+    ap.add_argument("--height", type=int, default=4000)
+    ap.add_argument("--scan-w", type=int, default=5000)
+    ap.add_argument("--scan-h", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench_reg.py: no CUDA device — no CPU fallback")
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    comm = None
+    if world > 1:
+        import datetime
+        import torch.distributed as dist
+        import dataset_pipeline_b200 as b2
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=600))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(b2.Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        comm = b2.Comm(rank, world, bytes(idt.cpu().numpy().tobytes()), device=local)
+    out = secondary_line(world, rank, comm, local, a.images, a.width, a.height, (a.scan_w, a.scan_h), a.steps, a.warmup, not a.no_cpu_baseline and world == 1,
+                         not a.no_e2e)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
 
 
 if __name__ == "__main__":
