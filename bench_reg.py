@@ -129,11 +129,15 @@ def secondary_line(world=1, rank=0, comm=None, local=0, num_images=20, width=600
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    profile = os.environ.get("B2_BENCH_PROFILE") == "1"      # ncu --profile-from-start off: only the timed steps are captured
+    if profile:
+        torch.cuda.profiler.start()
     t0 = time.perf_counter()
     parts = [step(g) for _ in range(steps)]
     torch.cuda.synchronize(dev)
     dt = (time.perf_counter() - t0) / steps
+    if profile:
+        torch.cuda.profiler.stop()
     # the accumulate pass alone (K11 + K12), at the state the last step left the observations in
     g.set_state(*state0); g.CreateObservationsForAllImages(1); g.ColorOptimizerApply()
     acc = [accumulate_only(g) for _ in range(max(2, steps))][1:]

@@ -113,7 +113,7 @@ struct b2_reg {
   std::map<int, std::vector<DevBuf>> cam_masks;      // camera-mask pyramids by intrinsics id (not part of the optimised state)
   std::vector<ScaleB> pts;
   DevBuf splats; size_t nsplats = 0;
-  DevBuf mesh_v, mesh_f, mesh_fn, mesh_edges, big_list, big_count, depth_masked; size_t mesh_nv = 0, mesh_nf = 0, mesh_ne = 0;
+  DevBuf mesh_v, mesh_f, mesh_fn, mesh_edges, big_list, big_count, warp_list, splat_queue, depth_masked; size_t mesh_nv = 0, mesh_nf = 0, mesh_ne = 0;
   int image_scale_count = 0, current_image_scale = 0;
   bool initialized = false;
   b2_comm* comm = nullptr; int rank = 0, world = 1;     // multi-GPU: images dealt round-robin, sums allreduced (b2_reg_set_comm)
@@ -255,28 +255,36 @@ static int render_depth(b2_reg* h, const ImageB& im, const IntrinsicsB& in, cons
     // mesh path (occlusion_geometry.cc:211-270): K8 depth pass + K9 boundary masking
     const size_t px = (size_t)cam.w * cam.h;
     B2_TRY(h->depth.ensure(px * 4)); B2_TRY(h->depth_masked.ensure(px * 4));
-    B2_TRY(h->big_list.ensure(std::max<size_t>(h->mesh_nf, 1) * 4)); B2_TRY(h->big_count.ensure(4));
+    B2_TRY(h->big_list.ensure(std::max<size_t>(h->mesh_nf, 1) * 4)); B2_TRY(h->big_count.ensure(16));
+    B2_TRY(h->warp_list.ensure(std::max<size_t>(h->mesh_nf, 1) * 4));
     const Pose3 P3 = pose3_of(pose);
     kr_fill_u32<<<divup(px, 256), 256, 0, h->stream>>>(h->depth.as<unsigned int>(), px, 0x7f800000u);
-    B2_CUDA(cudaMemsetAsync(h->big_count.p, 0, 4, h->stream));
+    B2_CUDA(cudaMemsetAsync(h->big_count.p, 0, 16, h->stream));       // [0] block queue, [1] warp queue, [2] splat queue
+    unsigned int* counts = h->big_count.as<unsigned int>();
     kr_raster_small<<<divup(h->mesh_nf, 128), 128, 0, h->stream>>>(h->mesh_v.as<float>(), h->mesh_f.as<unsigned int>(), h->mesh_nf, P3, cam,
                                                                    h->prm.min_occlusion_depth, h->prm.max_occlusion_depth, h->depth.as<unsigned int>(),
-                                                                   h->big_list.as<unsigned int>(), h->big_count.as<unsigned int>());
+                                                                   h->big_list.as<unsigned int>(), counts, h->warp_list.as<unsigned int>(), counts + 1);
+    kr_raster_warp<<<h->sms * 8, 256, 0, h->stream>>>(h->mesh_v.as<float>(), h->mesh_f.as<unsigned int>(), P3, cam, h->prm.min_occlusion_depth,
+                                                      h->prm.max_occlusion_depth, h->depth.as<unsigned int>(), h->warp_list.as<unsigned int>(), counts + 1);
     kr_raster_big<<<h->sms * 4, 256, 0, h->stream>>>(h->mesh_v.as<float>(), h->mesh_f.as<unsigned int>(), P3, cam, h->prm.min_occlusion_depth,
                                                      h->prm.max_occlusion_depth, h->depth.as<unsigned int>(), h->big_list.as<unsigned int>(),
                                                      h->big_count.as<unsigned int>());
     const bool mask = h->prm.mask_occlusion_boundaries != 0 && h->mesh_ne > 0;
     kr_depth_background<<<divup(px, 256), 256, 0, h->stream>>>(h->depth.as<float>(), mask ? h->depth_masked.as<float>() : nullptr, px);
-    h->launches += 4;
+    h->launches += 5;
     if (mask) {
       // image position = global_T_image.translation() = inv(q) * (-t)   (sophus se3.hpp:208-211)
       Pose inv; inv.q[0] = -pose.q[0]; inv.q[1] = -pose.q[1]; inv.q[2] = -pose.q[2]; inv.q[3] = pose.q[3];
       Pose neg; neg.t[0] = pose.t[0] * -1.f; neg.t[1] = pose.t[1] * -1.f; neg.t[2] = pose.t[2] * -1.f;
       const Pose ip = pose_mul(inv, neg);     // ip.t = 0 + inv.q (x) (-t)
+      const unsigned int splat_cap = 4u << 20;                     // 4M splats (80 MB); beyond that the edge threads draw themselves
+      B2_TRY(h->splat_queue.ensure((size_t)splat_cap * sizeof(EdgeSplat)));
       kr_mask_edges<<<divup(h->mesh_ne, 128), 128, 0, h->stream>>>(h->mesh_edges.as<MeshEdgeDev>(), h->mesh_ne, h->mesh_v.as<float>(), h->mesh_fn.as<float>(),
                                                                    P3, ip.t[0], ip.t[1], ip.t[2], cam, h->prm.splat_radius, h->depth.as<float>(),
-                                                                   h->depth_masked.as<float>());
-      ++h->launches;
+                                                                   h->depth_masked.as<float>(), h->splat_queue.as<EdgeSplat>(), counts + 2, splat_cap);
+      kr_draw_splats<<<h->sms * 8, 256, 0, h->stream>>>(h->splat_queue.as<EdgeSplat>(), counts + 2, splat_cap, cam.w, h->depth.as<float>(),
+                                                        h->depth_masked.as<float>());
+      h->launches += 2;
       *out = h->depth_masked.as<float>();
     } else {
       *out = h->depth.as<float>();
@@ -736,7 +744,7 @@ int b2_reg_destroy(b2_reg* h) {
   for (auto& o : h->trial) free_set(o);
   for (auto& im : h->images) { for (auto& b : im.img) b.release(); for (auto& b : im.mask) b.release(); im.given_depth.release(); }
   for (auto& P : h->pts) for (DevBuf* b : {&P.xyz, &P.nbr, &P.fixed_desc, &P.var_desc, &P.obs_count}) b->release();
-  for (DevBuf* b : {&h->mesh_v, &h->mesh_f, &h->mesh_fn, &h->mesh_edges, &h->big_list, &h->big_count, &h->depth_masked}) b->release();
+  for (DevBuf* b : {&h->mesh_v, &h->mesh_f, &h->mesh_fn, &h->mesh_edges, &h->big_list, &h->big_count, &h->warp_list, &h->splat_queue, &h->depth_masked}) b->release();
   for (DevBuf* b : {&h->splats, &h->flags, &h->offs, &h->cx, &h->cy, &h->cs, &h->cub_tmp, &h->depth, &h->partials, &h->results}) b->release();
   for (DevBuf* b : {&h->cut_cams, &h->cut_first, &h->cut_starts, &h->cut_points, &h->cut_out, &h->xchg, &h->w_nj, &h->w_ws, &h->w_wr, &h->w_part}) b->release();
   for (auto& kv : h->cam_masks) for (auto& b : kv.second) b.release();

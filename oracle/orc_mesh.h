@@ -155,6 +155,7 @@ static inline void raster_triangle(const RasterCam& c, const V3f& a, const V3f& 
   const int iy0 = std::max(0, (int)std::floor(miny - 0.5)), iy1 = std::min(c.h - 1, (int)std::ceil(maxy - 0.5));
   auto owns = [](double dx, double dy) { return dy < 0.0 || (dy == 0.0 && dx > 0.0); };
   const bool o0 = owns(x2 - x1, y2 - y1), o1 = owns(x0 - x2, y0 - y2), o2 = owns(x1 - x0, y1 - y0);
+  const double iz0 = 1.0 / z0, iz1 = 1.0 / z1, iz2 = 1.0 / z2;
   for (int iy = iy0; iy <= iy1; ++iy) {
     const double py = iy + 0.5;
     for (int ix = ix0; ix <= ix1; ++ix) {
@@ -163,8 +164,8 @@ static inline void raster_triangle(const RasterCam& c, const V3f& a, const V3f& 
       const double w1 = (x0 - x2) * (py - y2) - (y0 - y2) * (px - x2);
       const double w2 = (x1 - x0) * (py - y0) - (y1 - y0) * (px - x0);
       if (!((w0 > 0.0 || (w0 == 0.0 && o0)) && (w1 > 0.0 || (w1 == 0.0 && o1)) && (w2 > 0.0 || (w2 == 0.0 && o2)))) continue;
-      const double inv = (w0 / area) / z0 + (w1 / area) / z1 + (w2 / area) / z2;
-      const float z = (float)(1.0 / inv);
+      // perspective-correct depth 1 / sum(lambda_i / z_i), lambda_i = w_i / area, as ONE division per pixel: area / sum(w_i * (1 / z_i))
+      const float z = (float)(area / (w0 * iz0 + w1 * iz1 + w2 * iz2));
       if (!(z <= max_depth)) continue;
       float& d = depth[(size_t)iy * c.w + ix];
       if (z < d) d = z;

@@ -24,6 +24,9 @@ while [ $# -gt 0 ]; do
       [ -f ${O}_k3.ncu-rep ] && ncu -i ${O}_k3.ncu-rep --page source --csv > ${O}_k3.source.csv 2>/dev/null ;;
     ncu_k5) timeout 400 ncu --set full --clock-control none -k regex:'k_accumulate_tma' --launch-skip 8 -c 3 -f -o ${O}_k5 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-parity > ${O}_ncu_k5.log 2>&1; stamp $S $?
       [ -f ${O}_k5.ncu-rep ] && ncu -i ${O}_k5.ncu-rep --page raw --csv > ${O}_k5.raw.csv 2>/dev/null ;;
+    ncu_reg_launches) B2_BENCH_PROFILE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file ${O}_reg_launches.csv python bench_reg.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > ${O}_reg_launches.log 2>&1; stamp $S $? ;;
+    ncu_reg_full) B2_BENCH_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none -k regex:'kr_jacobians|kr_accumulate_weighted|kr_residual_weights|kr_visibility|kr_raster_small|kr_mask_edges' -c 12 -f -o ${O}_reg python bench_reg.py --images 2 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > ${O}_ncu_reg.log 2>&1; stamp $S $?
+      [ -f ${O}_reg.ncu-rep ] && ncu -i ${O}_reg.ncu-rep --page raw --csv > ${O}_reg.raw.csv 2>/dev/null ;;
     *) echo "unknown stage $S" ;;
   esac
 done
