@@ -71,6 +71,7 @@ EXPORTS = [
     "b2_icp_plan_directions",
     "b2_icp_run",
     "b2_icp_set_pose",
+    "b2_icp_upload_owner",
     "b2_last_error",
     "b2_lsor_filter",
     "b2_mesh_squared_distance",

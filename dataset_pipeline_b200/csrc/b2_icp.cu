@@ -887,6 +887,8 @@ int b2_icp_plan_directions(int n_movable, int has_fixed, int world_size, int32_t
   return n <= cap ? B2_OK : set_error(B2_ERR_ARG, "capacity %d too small for %d directions", cap, n);
 }
 
+int b2_icp_upload_owner(int cloud_id, int world_size) { return world_size > 0 && cloud_id >= 0 ? cloud_id % world_size : -1; }
+
 const char* b2_last_error(void) { return last_error_ref().c_str(); }
 int b2_abi_version(void) { return B2_ABI_VERSION; }
 int b2_trim(void) { pool_trim_all(); return B2_OK; }
@@ -971,7 +973,7 @@ int b2_icp_destroy(b2_icp* h) {
 static int add_cloud_impl(b2_icp* h, const float* xyz, const float* nrm, size_t n, size_t stride, const float T[16], int fixed, int* out_id,
                           bool from_device) {
   if (!h || !T) return set_error(B2_ERR_ARG, "null argument");
-  const int owner = (!fixed && h->cfg.shard_uploads && h->cfg.comm && h->cfg.world_size > 1) ? (int)(h->movable.size() % (size_t)h->cfg.world_size) : -1;
+  const int owner = (!fixed && h->cfg.shard_uploads && h->cfg.comm && h->cfg.world_size > 1) ? b2_icp_upload_owner((int)h->movable.size(), h->cfg.world_size) : -1;
   if (n > 0 && (!xyz || !nrm) && (owner < 0 || owner == h->cfg.rank)) return set_error(B2_ERR_ARG, "null argument");
   if (!from_device && stride < 12) return set_error(B2_ERR_ARG, "stride_bytes must be >= 12");
   if (n >= (1ull << 31)) return set_error(B2_ERR_ARG, "clouds above 2^31 points are not supported (pcl::Correspondence indices are int)");

@@ -199,3 +199,8 @@ def plan_directions(n_movable, has_fixed=False, world_size=1):
     c = C.c_int32(0)
     _lib.check(_lib.lib().b2_icp_plan_directions(n_movable, int(has_fixed), world_size, _i(s), _i(t), _i(o), cap, C.byref(c)))
     return [(int(s[k]), int(t[k]), int(o[k])) for k in range(c.value)]
+
+
+def upload_owner(cloud_id, world_size):
+    """Rank that uploads movable cloud `cloud_id` under shard_uploads (host-only call, no GPU needed)."""
+    return int(_lib.lib().b2_icp_upload_owner(int(cloud_id), int(world_size)))

@@ -152,6 +152,10 @@ int b2_icp_get_normal_equations(b2_icp* h, double* H, double* b, double* cost, i
 int b2_icp_plan_directions(int n_movable, int has_fixed, int world_size, int32_t* src_impl, int32_t* tgt_impl, int32_t* owner,
                            int cap, int* count);
 
+/* Pure host function: the rank whose host buffers are read for movable cloud `cloud_id` (0-based, in AddPointCloud order) when
+ * cfg.shard_uploads is set; the other ranks receive the cloud by broadcast. -1 for bad arguments. */
+int b2_icp_upload_owner(int cloud_id, int world_size);
+
 /* Stand-alone correspondence search = FindCorrespondencesFast (icp_point_to_plane.cc:42-105) on two point sets that
  * are already in a common frame. Outputs sized for n_src; *count receives the number of correspondences. */
 int b2_find_correspondences(const float* src_xyz, size_t n_src, const float* tgt_xyz, size_t n_tgt,

@@ -161,3 +161,32 @@ def test_two_rank_registration_exchange_reproduces_single_rank_system(oracle):
         assert p.exitcode == 0
     assert ret["owners"] == [0, 1, 0, 1]
     assert ret["H"] < 1e-12 and ret["b"] < 1e-12 and ret["sums"] < 1e-12, dict(ret)
+
+
+# ---- sharded upload (cfg.shard_uploads): who reads its host buffers, who receives -------------------------------------------------
+def _upload_rank(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dataset_pipeline_b200.icp import upload_owner
+    rng = np.random.default_rng(5)                      # every rank could read every cloud; only the owner does
+    clouds = [rng.normal(size=(1000 + 17 * i, 3)).astype(np.float32) for i in range(5)]
+    got, read = [], 0
+    for i, c in enumerate(clouds):                      # the protocol of b2_icp_add_cloud: same order, same n on every rank
+        owner = upload_owner(i, world)
+        buf = torch.from_numpy(c.copy()) if owner == rank else torch.zeros(c.shape, dtype=torch.float32)
+        read += c.nbytes if owner == rank else 0
+        dist.broadcast(buf, src=owner)
+        got.append(buf.numpy())
+    ret[rank] = (all(np.array_equal(a, b) for a, b in zip(got, clouds)), read, sum(c.nbytes for c in clouds))
+    dist.destroy_process_group()
+
+
+def test_sharded_upload_protocol_delivers_every_cloud_once():
+    from dataset_pipeline_b200.icp import upload_owner
+    assert [upload_owner(i, 3) for i in range(7)] == [0, 1, 2, 0, 1, 2, 0] and upload_owner(2, 1) == 0 and upload_owner(-1, 2) == -1
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_upload_rank, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret[r][0] for r in range(world))                                   # every rank ends up with every cloud
+    assert sum(ret[r][1] for r in range(world)) == ret[0][2]                      # each byte crossed a host link exactly once
+    assert max(ret[r][1] for r in range(world)) < 0.7 * ret[0][2]

@@ -210,3 +210,29 @@ def test_deterministic_repeat(b2, room3):
         res.append([g.GetResultGlobalTCloud(i) for i in range(3)] + [g.stats()["last_cost"]])
     for a, b in zip(res[0], res[1]):
         assert np.array_equal(a, b)
+
+
+def _tries_equal_one_iteration(b2, oracle, clouds, poses, d, fixed_first=False):
+    g, o, ids = _setup_pair(b2, oracle, clouds, poses, fixed_first=fixed_first)
+    g.Run(d, 0, 1, 1e-10, False); o.Run(d, 0, 1, 1e-10, False)
+    assert np.array_equal(g.tries(), o.tries()), (g.tries(), o.tries())
+    sg, so = g.stats(), o.stats()
+    assert sg["inner_iterations"] == so["inner_iterations"] and sg["lm_tries_total"] == so["lm_tries_total"]
+    return sg
+
+
+def test_lm_try_sequences_on_several_scenes(b2, oracle, room3):
+    """K5 builds H from one symmetric S per correspondence set (the source-pose Jacobian is the negated target-pose one) where the
+    reference evaluates both forms in fp32; the accept / reject sequence of the LM loop must nevertheless be the reference's. Checked on
+    scenes of different conditioning: three room scans, a fixed cloud, the config-1 relief pair, the reference's rank-deficient plane
+    (test_icp.cc:111-172) and its 20 identical clouds (:39-109, 114 variables)."""
+    from dataset_pipeline_b200 import synth
+    clouds, poses, _ = room3
+    assert _tries_equal_one_iteration(b2, oracle, clouds, poses, 0.05)["inner_iterations"] > 3
+    _tries_equal_one_iteration(b2, oracle, clouds, poses, 0.05, fixed_first=True)
+    rc, rp = synth.relief_scans()
+    _tries_equal_one_iteration(b2, oracle, rc, rp, 0.01)
+    pts, nrm, pp = rti.plane_with_single_point_inputs()
+    _tries_equal_one_iteration(b2, oracle, [(pts, nrm), (pts, nrm)], pp, 1.5)
+    pts, nrm, pp = rti.identical_cloud_alignment_inputs()
+    _tries_equal_one_iteration(b2, oracle, [(pts, nrm)] * 6, pp[:6], float(np.float32(0.15) * np.float32(math.sqrt(3))))
