@@ -57,6 +57,27 @@ def main():
            "config": {"workload": "room scan %dx%d rays from one position, kNN=%d, viewpoint = scan origin" % (a.scan_w, a.scan_h, a.k),
                       "points": n, "generation_s": t_gen, "h2d_bytes": n * 12, "d2h_bytes": n * 16,
                       "normals_agree_with_analytic_on_flat_surfaces": agree}}
+    # roofline of the device portion of the call (Morton sort + BVH + kn_knn_normals): SURVEY §8d counts 12 (k + 1) + 16 B per point.
+    # The call's H2D / D2H legs are timed separately on the same pinned buffers and taken off the call time.
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    dev_in = torch.empty(xyz.shape, dtype=torch.float32, device="cuda"); host_out = torch.empty((n, 4), dtype=torch.float32, pin_memory=True)
+    dev_out = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize(); t = time.perf_counter()
+    for _ in range(3):
+        dev_in.copy_(pinned, non_blocking=True); host_out.copy_(dev_out, non_blocking=True); torch.cuda.synchronize()
+    t_copy = (time.perf_counter() - t) / 3
+    t_dev = max(dt - t_copy, 1e-9)
+    alg = (12.0 * (a.k + 1) + 16.0) * n
+    res["roofline"] = {"bound": "hbm", "kernel": "device portion of b2_normals_estimate (Morton sort, implicit BVH, kn_knn_normals: exact kNN + two-pass covariance + eigenvector)",
+                       "achieved": alg / t_dev / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / t_dev / 1e9 / peak, "traffic": None,
+                       "algorithmic_bytes_per_call": alg, "device_seconds": t_dev, "copy_seconds": t_copy,
+                       "note": "gather / traversal-latency bound (8 of 32 lanes active in the per-thread BVH walk, profiles/r01d_k7_knn_normals_ncu.txt), not bandwidth bound"}
+    res["e2e"] = {"value": n / dt, "unit": "points/s", "h2d_bytes_per_step": int(n * 12), "d2h_bytes_per_step": int(n * 16)}
     if not a.no_cpu_baseline:
         from oracle import oracle as orc
         w = int((a.cpu_points * 2) ** 0.5); h = w // 2

@@ -145,9 +145,7 @@ def secondary_line(world=1, rank=0, comm=None, local=0, num_images=20, width=600
     if world > 1:
         tt = torch.tensor([dt, ms_j, ms_a, ms_acc_call], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt, ms_j, ms_a, ms_acc_call = [float(v) for v in tt]
-        te = torch.tensor([float(evals)], dtype=torch.float64, device=dev); dist.all_reduce(te, op=dist.ReduceOp.SUM); evals_local, evals = evals, int(te.item())
-    else:
-        evals_local = evals
+    evals_local = evals / world          # (the library's counters are already summed over the ranks; images are dealt round-robin)
     g.close()
 
     e2e_out = None

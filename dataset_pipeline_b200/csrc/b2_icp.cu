@@ -63,9 +63,18 @@ struct Direction {
   unsigned long long count = 0, rec_begin = 0;
 };
 
-struct Scoped {                         // temporaries of a call: released on every exit path
+// Temporaries of a call, released on every exit path. With a stream: a stream-ORDERED free (every use of the buffer was queued on that
+// stream), which does not wait for the device — a device-wide wait here would also wait for a peer's upload that is still being broadcast
+// into another cloud (sharded uploads), serialising what the broadcast stream exists to overlap.
+struct Scoped {
   DevBuf b;
-  ~Scoped() { b.release(); }
+  cudaStream_t stream = nullptr;
+  Scoped() {}
+  explicit Scoped(cudaStream_t s) : stream(s) {}
+  ~Scoped() {
+    if (b.p && stream && pool_enabled()) { cudaFreeAsync(b.p, stream); b.p = nullptr; b.cap = 0; }
+    else b.release();
+  }
 };
 
 static inline Mat4 mat4_of(const float T[16]) { Mat4 m; std::memcpy(m.m, T, sizeof(m.m)); return m; }
@@ -83,7 +92,7 @@ struct b2_icp {
   cudaStream_t stream = nullptr, copy_stream = nullptr;   // copy_stream: uploads of b2_icp_add_cloud (so that an index build can run beside them)
   cudaStream_t bcast_stream = nullptr;  // sharded uploads: the NCCL broadcasts, ordered behind the owner's copy by an event
   bool own_stream = false;
-  b2::Cloud* pending_index = nullptr;   // index_distance_hint: the cloud whose index is built behind the next upload
+  std::vector<b2::Cloud*> pending_index;   // index_distance_hint: clouds whose index is built behind the following uploads
   // K3 runs the pair-directions of an iteration round-robin over `nsearch` streams (the handle's + auxiliaries) so that one
   // direction's tail overlaps the next direction's head; each stream has its own CUB scratch.
   static constexpr int kMaxSearchStreams = 8;
@@ -320,7 +329,7 @@ static int build_index(b2_icp* h, Cloud* c, float max_dist, double sigma, double
   B2_TRY(grid_for_cloud(c, fmin, fmax, max_dist, sigma, mtot, &key_bits));
   const GridParams& g = c->g;
   IndexFrame F; std::memcpy(F.f, c->F, sizeof(F.f));
-  Scoped keys_in, keys_out, idx_in, perm;
+  Scoped keys_in(h->stream), keys_out(h->stream), idx_in(h->stream), perm(h->stream);
   B2_TRY(keys_in.b.ensure(n * 8 + 16)); B2_TRY(keys_out.b.ensure(n * 8 + 16)); B2_TRY(idx_in.b.ensure(n * 4)); B2_TRY(perm.b.ensure(n * 4));
   B2_TRY(c->l_xyz.ensure(n * 16)); B2_TRY(c->l_nrm.ensure(n * 16)); B2_TRY(c->perm_inv.ensure(n * 4));
   B2_TRY(c->s_xyz.ensure(n * 16)); B2_TRY(c->s_nrm.ensure(n * 16));
@@ -347,7 +356,7 @@ static int build_index(b2_icp* h, Cloud* c, float max_dist, double sigma, double
   if (c->dense) {
     const size_t nwords = (size_t)(cells_total / 32.0) + 2;
     const unsigned int nblocks = div_up(nwords, kWordsPerBlock);
-    Scoped block_sum, block_off;
+    Scoped block_sum(h->stream), block_off(h->stream);
     B2_TRY(c->rb.ensure(nwords * 8)); B2_TRY(c->starts.ensure(((size_t)c->ncells + 2) * 4));
     B2_TRY(block_sum.b.ensure((size_t)nblocks * 4)); B2_TRY(block_off.b.ensure((size_t)nblocks * 4 + 4));
     B2_CUDA(cudaMemsetAsync(c->rb.p, 0, nwords * 8, h->stream));
@@ -358,7 +367,6 @@ static int build_index(b2_icp* h, Cloud* c, float max_dist, double sigma, double
     k_cell_starts<<<div_up(n, 256), 256, 0, h->stream>>>(keys_out.b.as<unsigned long long>(), n, 3 * g.fbits, c->rb.as<uint2>(),
                                                          c->starts.as<unsigned int>(), c->ncells);
     h->launches += 5;
-    B2_CUDA(cudaStreamSynchronize(h->stream));   // block_sum / block_off go out of scope
   } else {
     int lg = 4;
     while ((1ull << lg) < 2ull * c->ncells) ++lg;
@@ -369,7 +377,6 @@ static int build_index(b2_icp* h, Cloud* c, float max_dist, double sigma, double
     ++h->launches;
   }
   h->launches += 4;
-  B2_CUDA(cudaStreamSynchronize(h->stream));     // the temporaries go out of scope
   c->index_d = max_dist;
   c->indexed = true;
   return B2_OK;
@@ -507,30 +514,37 @@ static int run_pass(b2_icp* h, const std::vector<std::vector<Pose>>& trials, boo
 
 static float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
 
-// index_distance_hint: the cloud added last is indexed now — the caller is b2_icp_add_cloud with the NEXT cloud's copy in flight (or
-// ensure_indexes for the last one). Only this cloud's own magnitude is known yet; should a later cloud raise the handle's bound above
-// the class chosen here, ensure_indexes rebuilds.
+// index_distance_hint: the clouds added so far are indexed now — the caller is b2_icp_add_cloud with the NEXT cloud's copy in flight.
+// Only a cloud's own magnitude is known yet; should a later cloud raise the handle's bound above the class chosen here, ensure_indexes
+// rebuilds.
 static int build_pending_index(b2_icp* h) {
-  Cloud* c = h->pending_index;
-  h->pending_index = nullptr;
-  if (!c || !(h->cfg.index_distance_hint > 0.f) || c->indexed) return B2_OK;
-  B2_TRY(cloud_local_box(h, c));
-  double m = 0, sigma = 1.0;
-  for (int k = 0; k < 3; ++k) m = std::max({m, std::fabs((double)c->lmin[k]), std::fabs((double)c->lmax[k])});
-  for (int a = 0; a < 3; ++a) {
-    double gsum = std::fabs((double)c->T[12 + a]);
-    for (int k = 0; k < 3; ++k) gsum += std::fabs((double)c->T[a + 4 * k]) * std::max(std::fabs((double)c->lmin[k]), std::fabs((double)c->lmax[k]));
-    m = std::max(m, gsum);
+  if (!(h->cfg.index_distance_hint > 0.f)) { h->pending_index.clear(); return B2_OK; }
+  while (!h->pending_index.empty()) {
+    Cloud* c = h->pending_index.front();
+    // sharded uploads: a cloud another rank owns is indexed only once its bytes are here — waiting for them would delay THIS rank's
+    // own upload (the next call), and with it every other rank (b2_icp_run builds whatever is still pending)
+    if (c->ready_ev && cudaEventQuery(c->ready_ev) != cudaSuccess) break;
+    h->pending_index.erase(h->pending_index.begin());
+    if (c->indexed) continue;
+    B2_TRY(cloud_local_box(h, c));
+    double m = 0, sigma = 1.0;
+    for (int k = 0; k < 3; ++k) m = std::max({m, std::fabs((double)c->lmin[k]), std::fabs((double)c->lmax[k])});
+    for (int a = 0; a < 3; ++a) {
+      double gsum = std::fabs((double)c->T[12 + a]);
+      for (int k = 0; k < 3; ++k) gsum += std::fabs((double)c->T[a + 4 * k]) * std::max(std::fabs((double)c->lmin[k]), std::fabs((double)c->lmax[k]));
+      m = std::max(m, gsum);
+    }
+    if (!std::isfinite(m)) continue;             // reported by b2_icp_run
+    B2_TRY(pose_sigma(c->T, nullptr, &sigma));
+    B2_TRY(build_index(h, c, h->cfg.index_distance_hint, sigma, m));
   }
-  if (!std::isfinite(m)) return B2_OK;           // reported by b2_icp_run
-  B2_TRY(pose_sigma(c->T, nullptr, &sigma));
-  return build_index(h, c, h->cfg.index_distance_hint, sigma, m);
+  return B2_OK;
 }
 
 // Index maintenance at the start of an outer iteration: (re)build the indexes the current radius / poses are not covered by.
 static int ensure_indexes(b2_icp* h, float max_dist) {
   const int nc = num_impl_clouds(h);
-  h->pending_index = nullptr;                    // whatever is still pending is built below, with the handle's full magnitude bound
+  h->pending_index.clear();                      // whatever is still pending is built below, with the handle's full magnitude bound
   for (int i = 0; i < nc; ++i) B2_TRY(cloud_local_box(h, impl_cloud(h, i)));
   const double mtot = magnitude_bound(h);
   if (!std::isfinite(mtot)) return set_error(B2_ERR_ARG, "non-finite pose or point coordinates");
@@ -1004,7 +1018,7 @@ static int add_cloud_impl(b2_icp* h, const float* xyz, const float* nrm, size_t 
   std::unique_ptr<Cloud> c(new Cloud());
   std::memcpy(c->T, T, sizeof(float) * 16);
   B2_TRY(upload_cloud(h, c.get(), xyz, nrm, n, stride, from_device, owner));
-  h->pending_index = c.get();
+  h->pending_index.push_back(c.get());
   h->movable.push_back(std::move(c));
   if (out_id) *out_id = (int)h->movable.size() - 1;
   return B2_OK;

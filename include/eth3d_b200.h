@@ -328,7 +328,11 @@ int b2_reg_variable_index(b2_reg* h, int kind, int id, int* out_index);
  * residual sums of every cost evaluation. Call before b2_reg_add_image; comm = NULL returns to single-GPU operation. */
 int b2_reg_set_comm(b2_reg* h, b2_comm* comm);
 int b2_reg_image_owner(int image_id, int world_size);
-/* Problem::InitializeImages + LoadImages pyramids. *image_scale_count receives Problem::image_scale_count(). */
+/* Problem::InitializeImages + LoadImages pyramids (image.cc:106-154, intrinsics.cc:45-50). *image_scale_count receives
+ * Problem::image_scale_count(). Any image size: a level with even parents is cv::resize INTER_AREA's integer 2x2 mean, one with an odd
+ * parent its general area filter (fractional coverage), both bit-identical to OpenCV; image / mask levels TRUNCATE the halved size
+ * (image.cc:116,137) while camera levels ROUND it (camera_base_impl.h:72), as in the reference. B2_ERR_ARG when a level would be empty
+ * (the reference: LOG(FATAL) "Resizing failed"). */
 int b2_reg_initialize(b2_reg* h, int* image_scale_count);
 /* One scale of the multi-resolution point cloud (problem.h points()/point_radius()/neighbor indices) + grey colours from which the
  * fixed descriptors are derived (problem.cc:550-572). neighbor_indices: n * point_neighbor_count. */
