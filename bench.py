@@ -409,7 +409,8 @@ def run_b200(args):
             ge.close()
             parts = {"create_and_upload_ms": 1e3 * (t1 - t0), "add_cloud_ms": ge.upload_ms, "run_ms": 1e3 * (t2 - t1), "run_device_ms": st_e["ms_total"], "index_build_ms": st_e["ms_index_build"],
                      "destroy_ms": 1e3 * (time.perf_counter() - t0 - dt),
-                     "run_phases_ms": {k: st_e["ms_" + k] for k in ("index", "search", "pack", "inner")}, "passes": st_e["passes"]}
+                     "run_phases_ms": {k: st_e["ms_" + k] for k in ("index", "search", "pack", "inner")}, "passes": st_e["passes"],
+                     "searches_done_behind_uploads": st_e["searches_ahead"], "searches_in_run": st_e["search_launches"]}
             if world > 1:
                 t = torch.tensor([dt], device="cuda", dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -421,8 +422,9 @@ def run_b200(args):
         h2d = npts * 24 if comm is None else sum(c[0].shape[0] * 24 for i, c in enumerate(clouds) if i % world == rank)   # rank 0's share when sharded
         e2e = {"value": len(times) / sum(times), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "step_ms": [round(1e3 * v, 2) for v in times],
                "steps": len(times), "last_step_breakdown": parts, "h2d_gb_per_s_in_upload": npts * 24 / 1e9 / max(parts["create_and_upload_ms"] * 1e-3, 1e-9),
-               "note": "each step: b2_icp_create + 8 x b2_icp_add_cloud from pinned host memory (static index built behind the uploads) + b2_icp_run(1 iteration from the "
-                       "same poses as the corresponding timed step) + b2_icp_get_pose + destroy"}
+               "note": "each step: b2_icp_create + 8 x b2_icp_add_cloud from pinned host memory (static index built, and on one GPU the pair-directions among the clouds "
+                       "already resident searched, behind the uploads that follow) + b2_icp_run(1 iteration from the same poses as the corresponding timed step) + "
+                       "b2_icp_get_pose + destroy; all of it inside the timed region"}
 
     # ---- the other half of BASELINE.json's metric: ImageRegistrator residual-evaluations/s (config 4; images sharded over the ranks) ----
     secondary = None

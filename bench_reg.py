@@ -57,13 +57,18 @@ def build_scene(num_images, width, height, scan_wh, device, need_image):
     return {"intr": (width, height, K), "K_init": K_init, "images": images, "poses_gt": gt, "poses_init": init, "mesh": rv.room_mesh(0.02), "scans": scans}
 
 
-def load(reg, sc, use_images):
+def load(reg, sc, use_images, parts=None):
     w, h, _ = sc["intr"]
+    t0 = time.perf_counter()
     reg.add_intrinsics(w, h, sc["K_init"])
     for img, T in zip(use_images, sc["poses_init"]):
         reg.add_image(0, img, None, T)
+    t1 = time.perf_counter()
     count = reg.initialize()
+    t2 = time.perf_counter()
     reg.set_mesh(*sc["mesh"])
+    if parts is not None:
+        parts.update({"add_images_ms": 1e3 * (t1 - t0), "initialize_ms": 1e3 * (t2 - t1), "set_mesh_ms": 1e3 * (time.perf_counter() - t2)})
     return count
 
 
@@ -94,13 +99,18 @@ def secondary_line(world=1, rank=0, comm=None, local=0, num_images=20, width=600
         if world == 1 and make.first is not None:
             g, make.first = make.first, None
         else:
+            t0 = time.perf_counter()
             g = b2.Registration(R.default_params(device=local))
             if comm is not None:
                 g.set_comm(comm)
-            load(g, sc, [img if owns(i) else None for i, img in enumerate(sc["images"])])
+            make.parts = {"create_ms": 1e3 * (time.perf_counter() - t0)}
+            load(g, sc, [img if owns(i) else None for i, img in enumerate(sc["images"])], make.parts)
+        t0 = time.perf_counter()
         for r, p, c, nb in zip(radii, pts, cols, nbrs):
             g.add_point_scale(p, float(r), nb, c)
+        make.parts["add_point_scales_ms"] = 1e3 * (time.perf_counter() - t0)
         return g
+    make.parts = {}
     make.first = setup if world == 1 else None
 
     g = make()
@@ -156,16 +166,19 @@ def secondary_line(world=1, rank=0, comm=None, local=0, num_images=20, width=600
                 dist.barrier()
             torch.cuda.synchronize(dev); t0 = time.perf_counter()
             ge = make(); ge.set_image_scale(0)
+            t1 = time.perf_counter()
             step(ge); _ = ge.get_state()
             torch.cuda.synchronize(dev); d = time.perf_counter() - t0
+            e2e_parts = dict(make.parts); e2e_parts["iteration_ms"] = 1e3 * (t0 + d - t1)
             ge.close()
+            e2e_parts["destroy_ms"] = 1e3 * (time.perf_counter() - t0 - d)
             if world > 1:
                 tt = torch.tensor([d], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); d = float(tt.item())
             times.append(d)
         h2d = sum(img.size for i, img in enumerate(sc["images"]) if owns(i)) + sum(p.nbytes + nb.nbytes + c.nbytes for p, nb, c in zip(pts, nbrs, cols)) \
             + sc["mesh"][0].nbytes + sc["mesh"][1].nbytes
         e2e_out = {"value": evals / times[-1], "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(8 * (124 * 124 + 124 + 8) * 8 + 7 * 4 * num_images),
-                   "seconds": times, "note": "b2_reg_create + intrinsics + images (host u8) + initialize (pyramids) + mesh + point scales (host arrays) + one optimizer "
+                   "seconds": times, "last_run_breakdown": {k: round(v, 2) for k, v in e2e_parts.items()}, "note": "b2_reg_create + intrinsics + images (host u8) + initialize (pyramids) + mesh + point scales (host arrays) + one optimizer "
                                              "iteration + b2_reg_get_state + destroy; second of two runs"}
     if rank != 0:
         return None

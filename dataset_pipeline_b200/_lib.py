@@ -17,7 +17,8 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void
 class IcpConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("inner_max_iterations", C.c_int32), ("keep_correspondences", C.c_int32),
                 ("rank", C.c_int32), ("world_size", C.c_int32), ("allreduce", ALLREDUCE_FN), ("allreduce_user", C.c_void_p),
-                ("stream", C.c_void_p), ("comm", C.c_void_p), ("index_distance_hint", C.c_float), ("shard_uploads", C.c_int32)]
+                ("stream", C.c_void_p), ("comm", C.c_void_p), ("index_distance_hint", C.c_float), ("shard_uploads", C.c_int32),
+                ("search_ahead", C.c_int32)]
 
 
 class IcpStats(C.Structure):
@@ -28,7 +29,8 @@ class IcpStats(C.Structure):
                 ("ms_index", C.c_float), ("ms_search", C.c_float), ("ms_pack", C.c_float), ("ms_inner", C.c_float),
                 ("ms_total", C.c_float), ("ms_accum_kernel_avg", C.c_float), ("ms_search_kernel_avg", C.c_float),
                 ("search_launches", C.c_int32), ("search_algorithmic_bytes", C.c_uint64),
-                ("ms_index_build", C.c_float), ("sparse_grids", C.c_int32), ("search_work", C.c_uint64 * 5)]
+                ("ms_index_build", C.c_float), ("sparse_grids", C.c_int32), ("search_work", C.c_uint64 * 5),
+                ("searches_ahead", C.c_int32)]
 
 
 class B2Error(RuntimeError):

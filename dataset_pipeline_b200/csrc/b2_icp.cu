@@ -51,6 +51,10 @@ struct Cloud {
   unsigned int ncells = 0;
   // ---- per outer iteration ----
   DevBuf s_xyz, s_nrm, box1, box2;      // global-frame rows in the sorted order + chunk boxes
+  unsigned int index_epoch = 0;         // bumped by every index build (the sorted order of the rows changes with it)
+  bool rows_ahead = false;              // search_ahead: s_xyz / boxes hold the rows at pose rows_T of index build rows_epoch
+  float rows_T[16];
+  unsigned int rows_epoch = 0;
   cudaEvent_t ready_ev = nullptr;       // sharded upload: the cloud's bytes have arrived on this rank (recorded on the broadcast stream)
 };
 
@@ -61,6 +65,18 @@ struct Direction {
   int order_src = -1, order_tgt = -1, order_age = 0;
   unsigned int order_tiles = 0;
   unsigned long long count = 0, rec_begin = 0;
+  int ahead_slot = -1;                  // >= 0: this iteration's search was done ahead of b2_icp_run (slot of its match count)
+};
+
+// A pair-direction searched ahead of b2_icp_run (cfg.search_ahead): its result is adopted by the first outer iteration if, by then,
+// neither pose nor either index has changed and the radius is the hinted one; otherwise it is dropped and the search runs as usual.
+struct Ahead {
+  Cloud* S = nullptr; Cloud* T = nullptr;
+  float Ts[16], Tt[16];
+  unsigned int s_epoch = 0, t_epoch = 0;
+  float r2 = 0.f;
+  int slot = 0;
+  Direction d;
 };
 
 // Temporaries of a call, released on every exit path. With a stream: a stream-ORDERED free (every use of the buffer was queued on that
@@ -93,6 +109,14 @@ struct b2_icp {
   cudaStream_t bcast_stream = nullptr;  // sharded uploads: the NCCL broadcasts, ordered behind the owner's copy by an event
   bool own_stream = false;
   std::vector<b2::Cloud*> pending_index;   // index_distance_hint: clouds whose index is built behind the following uploads
+  // search_ahead: pair-directions among the clouds indexed so far, searched on the auxiliary streams behind the following uploads
+  static constexpr int kMaxAhead = 4096;
+  std::vector<std::unique_ptr<b2::Ahead>> ahead;
+  std::vector<b2::Cloud*> ahead_clouds;
+  DevBuf ahead_totals_dev, ahead_bbox;
+  PinnedBuf ahead_totals_pin;
+  cudaEvent_t ahead_ev = nullptr;
+  int ahead_rr = 0;
   // K3 runs the pair-directions of an iteration round-robin over `nsearch` streams (the handle's + auxiliaries) so that one
   // direction's tail overlaps the next direction's head; each stream has its own CUB scratch.
   static constexpr int kMaxSearchStreams = 8;
@@ -309,6 +333,11 @@ static int cloud_local_box(b2_icp* h, Cloud* c) {
 static int build_index(b2_icp* h, Cloud* c, float max_dist, double sigma, double mtot) {
   const size_t n = c->n;
   c->indexed = false;
+  ++c->index_epoch;
+  if (c->rows_ahead) {     // searches issued ahead of b2_icp_run may still be reading the index this call rewrites
+    for (int i = 0; i + 1 < h->nsearch; ++i) B2_CUDA(cudaStreamSynchronize(h->aux[i]));
+    c->rows_ahead = false;
+  }
   if (n == 0) { c->ncells = 0; c->index_d = max_dist; c->index_sigma = sigma * (1.0 + 1e-4); c->index_mtot = 4.0 * mtot; c->indexed = true; return B2_OK; }
   // freeze the index frame at the current pose and measure the cloud's box in it
   for (int r = 0; r < 3; ++r) { for (int k = 0; k < 3; ++k) c->F[4 * r + k] = c->T[r + 4 * k]; c->F[4 * r + 3] = c->T[12 + r]; }
@@ -514,6 +543,131 @@ static int run_pass(b2_icp* h, const std::vector<std::vector<Pose>>& trials, boo
 
 static float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
 
+// K3 + tile offsets of one pair-direction on stream st; the match count lands in *total_host (pinned) once st has drained.
+static int launch_search(b2_icp* h, Direction* d, Cloud* S, Cloud* T, float r2, cudaStream_t st, DevBuf& cub_tmp, unsigned int* total_dev,
+                         unsigned int* total_host, bool timed) {
+  static const bool grid_order = [] { const char* e = getenv("B2_K3_ORDER"); return e && std::string(e) == "grid"; }();
+  const size_t ns = S->n;
+  const unsigned int ntiles = div_up(ns, kTile);
+  B2_TRY(d->key.ensure(ns * 8)); B2_TRY(d->tile_count.ensure((size_t)ntiles * 4)); B2_TRY(d->tile_off.ensure((size_t)ntiles * 4));
+  SearchGrid sg;
+  B2_TRY(search_grid(T, &sg));
+  cudaEvent_t n0 = nullptr, n1 = nullptr;
+  if (timed) { B2_CUDA(cudaEventCreate(&n0)); B2_CUDA(cudaEventCreate(&n1)); B2_CUDA(cudaEventRecord(n0, st)); }
+  // longest-first launch order (k_tile_cost + a 10^4..10^5-element radix sort); the geometry of a direction changes by millimetres
+  // between outer iterations, so the order is kept for eight of them
+  const unsigned int* order = nullptr;
+  if (h->lpt_order && !grid_order && ntiles > 4u * (unsigned int)h->sms) {
+    B2_TRY(d->order.ensure((size_t)ntiles * 16));
+    unsigned int* cc = d->order.as<unsigned int>();
+    if (d->order_src != d->src || d->order_tgt != d->tgt || d->order_tiles != ntiles || d->order_age >= 8) {
+      if (T->dense) k_tile_cost<true><<<div_up(ntiles, 256), 256, 0, st>>>(S->s_xyz.as<float4>(), ns, T->table.as<HashEntry>(), sg, ntiles, cc, cc + ntiles);
+      else k_tile_cost<false><<<div_up(ntiles, 256), 256, 0, st>>>(S->s_xyz.as<float4>(), ns, T->table.as<HashEntry>(), sg, ntiles, cc, cc + ntiles);
+      size_t tmp2 = 0;
+      B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp2, cc, cc + 2 * (size_t)ntiles, cc + ntiles, cc + 3 * (size_t)ntiles, (int)ntiles, 0, 32, st));
+      B2_TRY(cub_tmp.ensure(tmp2));
+      B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(cub_tmp.p, tmp2, cc, cc + 2 * (size_t)ntiles, cc + ntiles, cc + 3 * (size_t)ntiles, (int)ntiles, 0, 32, st));
+      d->order_src = d->src; d->order_tgt = d->tgt; d->order_tiles = ntiles; d->order_age = 0;
+      h->launches += 2;
+    }
+    ++d->order_age;
+    order = cc + 3 * (size_t)ntiles;
+  }
+  B2_CUDA(cudaMemsetAsync(d->tile_count.p, 0, (size_t)ntiles * 4, st));
+#define B2_LAUNCH_NN(STATS, DENSE)                                                                                                  \
+  k_nn_tiles<STATS, DENSE><<<ntiles, kTile, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(), T->box2.as<Aabb>(),  \
+                                                     T->table.as<HashEntry>(), sg, r2, d->key.as<unsigned long long>(),                 \
+                                                     d->tile_count.as<unsigned int>(), h->work_stats ? h->work_dev.as<unsigned long long>() : nullptr, order)
+  if (h->work_stats) { if (T->dense) B2_LAUNCH_NN(true, true); else B2_LAUNCH_NN(true, false); }
+  else { if (T->dense) B2_LAUNCH_NN(false, true); else B2_LAUNCH_NN(false, false); }
+#undef B2_LAUNCH_NN
+  if (timed) {
+    B2_CUDA(cudaEventRecord(n1, st));
+    h->nn_events.emplace_back(n0, n1);
+    h->stats.search_algorithmic_bytes += 12ull * ns + 12ull * T->n;
+  }
+  k_scan_tiles<<<1, 1024, 0, st>>>(d->tile_count.as<unsigned int>(), ntiles, d->tile_off.as<unsigned int>(), total_dev);
+  h->launches += 2;
+  B2_CUDA(cudaMemcpyAsync(total_host, total_dev, 4, cudaMemcpyDeviceToHost, st));
+  return B2_OK;
+}
+
+// The global-frame rows, chunk boxes and per-block bounding boxes of one cloud at its current pose (K1x).
+static int launch_rows(b2_icp* h, Cloud* c, float* bbox_partial, int xf_blocks) {
+  const unsigned int nb1 = div_up(c->n, kChunk1), nb2 = div_up(nb1, 32);
+  B2_TRY(c->box1.ensure(sizeof(Aabb) * nb1)); B2_TRY(c->box2.ensure(sizeof(Aabb) * nb2));
+  k_xform_sorted<<<xf_blocks, 256, 0, h->stream>>>(c->l_xyz.as<float4>(), c->l_nrm.as<float4>(), c->n, mat4_of(c->T), c->s_xyz.as<float4>(),
+                                                   c->s_nrm.as<float4>(), c->box1.as<Aabb>(), bbox_partial);
+  k_chunk_boxes2<<<div_up((size_t)nb2 * 32, 256), 256, 0, h->stream>>>(c->box1.as<Aabb>(), nb1, c->box2.as<Aabb>(), nb2);
+  h->launches += 2;
+  return B2_OK;
+}
+
+static void release_direction(Direction* d) { for (DevBuf* b : {&d->key, &d->tile_count, &d->tile_off, &d->order}) b->release(); }
+
+// Drops every search done ahead of b2_icp_run (their streams are drained first: the buffers go back to the pool).
+static void drop_ahead(b2_icp* h) {
+  if (h->ahead.empty() && h->ahead_clouds.empty()) return;
+  for (int i = 0; i + 1 < h->nsearch; ++i) cudaStreamSynchronize(h->aux[i]);
+  for (auto& a : h->ahead) release_direction(&a->d);
+  h->ahead.clear();
+  for (Cloud* c : h->ahead_clouds) c->rows_ahead = false;
+  h->ahead_clouds.clear();
+}
+
+static bool rows_current(const Cloud* c) {
+  return c->rows_ahead && c->indexed && c->rows_epoch == c->index_epoch && std::memcmp(c->rows_T, c->T, sizeof(c->T)) == 0;
+}
+
+static Ahead* find_ahead(b2_icp* h, const Cloud* S, const Cloud* T, float r2) {
+  if (h->work_stats) return nullptr;
+  for (auto& a : h->ahead)
+    if (a->S == S && a->T == T && a->d.key.p && a->r2 == r2 && a->s_epoch == S->index_epoch && a->t_epoch == T->index_epoch && S->indexed && T->indexed &&
+        std::memcmp(a->Ts, S->T, sizeof(a->Ts)) == 0 && std::memcmp(a->Tt, T->T, sizeof(a->Tt)) == 0)
+      return a.get();
+  return nullptr;
+}
+
+// cfg.search_ahead: cloud c has just been indexed (behind the upload of the cloud after it). Its global-frame rows are written at the
+// pose it was added with, and the pair-directions between c and every cloud prepared the same way before it are searched on the
+// auxiliary streams: while the remaining clouds cross PCIe the GPU is otherwise idle, and a first outer iteration that is called with
+// the hinted radius and unchanged poses finds these searches done (align_once adopts them; bit-identical, it is the same kernel on
+// the same rows). One rank only: with several, which rank owns a direction is not known before the last cloud has been added.
+static int search_ahead_for(b2_icp* h, Cloud* c) {
+  if (!h->cfg.search_ahead || h->cfg.world_size > 1 || h->work_stats || h->nsearch < 2 || c->n == 0 || !c->indexed) return B2_OK;
+  const float hint = h->cfg.index_distance_hint;
+  const float r2 = (float)((double)hint * (double)hint);
+  const int xf_blocks = h->sms * 4;
+  B2_TRY(h->ahead_bbox.ensure((size_t)xf_blocks * 6 * sizeof(float)));
+  B2_TRY(launch_rows(h, c, h->ahead_bbox.as<float>(), xf_blocks));
+  c->rows_ahead = true; c->rows_epoch = c->index_epoch; std::memcpy(c->rows_T, c->T, sizeof(c->T));
+  if (!h->ahead_ev) B2_CUDA(cudaEventCreateWithFlags(&h->ahead_ev, cudaEventDisableTiming));
+  B2_CUDA(cudaEventRecord(h->ahead_ev, h->stream));
+  const int naux = h->nsearch - 1;
+  for (int i = 0; i < naux; ++i) B2_CUDA(cudaStreamWaitEvent(h->aux[i], h->ahead_ev, 0));
+  B2_TRY(h->ahead_totals_dev.ensure(sizeof(unsigned int) * b2_icp::kMaxAhead));
+  B2_TRY(h->ahead_totals_pin.ensure(sizeof(unsigned int) * b2_icp::kMaxAhead));
+  for (Cloud* o : h->ahead_clouds) {
+    if (o == c || o->n == 0 || !rows_current(o)) continue;
+    for (int dir = 0; dir < 2; ++dir) {
+      if ((int)h->ahead.size() >= b2_icp::kMaxAhead) break;
+      Cloud* S = dir == 0 ? o : c; Cloud* T = dir == 0 ? c : o;
+      std::unique_ptr<Ahead> a(new Ahead());
+      a->S = S; a->T = T; a->s_epoch = S->index_epoch; a->t_epoch = T->index_epoch; a->r2 = r2; a->slot = (int)h->ahead.size();
+      std::memcpy(a->Ts, S->T, sizeof(a->Ts)); std::memcpy(a->Tt, T->T, sizeof(a->Tt));
+      a->d.src = -2; a->d.tgt = -2;
+      h->ahead_totals_pin.as<unsigned int>()[a->slot] = 0;
+      const int si = h->ahead_rr++ % naux;
+      const int rc = launch_search(h, &a->d, S, T, r2, h->aux[si], h->search_tmp[si + 1], h->ahead_totals_dev.as<unsigned int>() + a->slot,
+                                   h->ahead_totals_pin.as<unsigned int>() + a->slot, false);
+      if (rc != B2_OK) { cudaStreamSynchronize(h->aux[si]); release_direction(&a->d); return rc; }
+      h->ahead.push_back(std::move(a));
+    }
+  }
+  h->ahead_clouds.push_back(c);
+  return B2_OK;
+}
+
 // index_distance_hint: the clouds added so far are indexed now — the caller is b2_icp_add_cloud with the NEXT cloud's copy in flight.
 // Only a cloud's own magnitude is known yet; should a later cloud raise the handle's bound above the class chosen here, ensure_indexes
 // rebuilds.
@@ -537,6 +691,7 @@ static int build_pending_index(b2_icp* h) {
     if (!std::isfinite(m)) continue;             // reported by b2_icp_run
     B2_TRY(pose_sigma(c->T, nullptr, &sigma));
     B2_TRY(build_index(h, c, h->cfg.index_distance_hint, sigma, m));
+    B2_TRY(search_ahead_for(h, c));
   }
   return B2_OK;
 }
@@ -585,18 +740,15 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   B2_CUDA(cudaEventRecord(h->ev[0], h->stream));
 
   // ---- K1x: global-frame rows, chunk boxes and bounding boxes of all clouds (one stream per cloud, one sync for all) ----
+  if (!h->ahead.empty())     // the rows are rewritten below (with the same values where a search done ahead is still reading them)
+    for (int i = 0; i + 1 < h->nsearch; ++i) { B2_CUDA(cudaEventRecord(h->join_ev[i], h->aux[i])); B2_CUDA(cudaStreamWaitEvent(h->stream, h->join_ev[i], 0)); }
   const int xf_blocks = h->sms * 4;
   B2_TRY(h->bbox_partial.ensure((size_t)nc * xf_blocks * 6 * sizeof(float)));
   B2_TRY(h->pin_bbox.ensure((size_t)nc * xf_blocks * 6 * sizeof(float)));
   for (int i = 0; i < nc; ++i) {
     Cloud* c = impl_cloud(h, i);
     if (c->n == 0) continue;
-    const unsigned int nb1 = div_up(c->n, kChunk1), nb2 = div_up(nb1, 32);
-    B2_TRY(c->box1.ensure(sizeof(Aabb) * nb1)); B2_TRY(c->box2.ensure(sizeof(Aabb) * nb2));
-    k_xform_sorted<<<xf_blocks, 256, 0, h->stream>>>(c->l_xyz.as<float4>(), c->l_nrm.as<float4>(), c->n, mat4_of(c->T), c->s_xyz.as<float4>(),
-                                                     c->s_nrm.as<float4>(), c->box1.as<Aabb>(), h->bbox_partial.as<float>() + (size_t)i * xf_blocks * 6);
-    k_chunk_boxes2<<<div_up((size_t)nb2 * 32, 256), 256, 0, h->stream>>>(c->box1.as<Aabb>(), nb1, c->box2.as<Aabb>(), nb2);
-    h->launches += 2;
+    B2_TRY(launch_rows(h, c, h->bbox_partial.as<float>() + (size_t)i * xf_blocks * 6, xf_blocks));
   }
   B2_CUDA(cudaMemcpyAsync(h->pin_bbox.p, h->bbox_partial.p, (size_t)nc * xf_blocks * 6 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   B2_CUDA(cudaStreamSynchronize(h->stream));
@@ -636,53 +788,21 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   if (h->work_stats) { B2_TRY(h->work_dev.ensure(5 * sizeof(unsigned long long))); B2_CUDA(cudaMemsetAsync(h->work_dev.p, 0, 5 * sizeof(unsigned long long), h->stream)); }
   const int nstreams = h->nsearch;
   for (int k = 0; k < h->ndirs; ++k) { h->dirs[k]->count = 0; totals[k] = 0; }
-  static const bool grid_order = [] { const char* e = getenv("B2_K3_ORDER"); return e && std::string(e) == "grid"; }();
+  std::vector<std::pair<int, int>> adopted;      // (direction, slot): searched ahead of this call
   auto issue_search = [&](int k, cudaStream_t st, DevBuf& cub_tmp) -> int {
     Direction* d = h->dirs[k].get();
     Cloud* S = impl_cloud(h, d->src); Cloud* T = impl_cloud(h, d->tgt);
-    const size_t ns = S->n;
-    if (ns == 0 || T->n == 0) return B2_OK;
-    const unsigned int ntiles = div_up(ns, kTile);
-    B2_TRY(d->key.ensure(ns * 8)); B2_TRY(d->tile_count.ensure((size_t)ntiles * 4)); B2_TRY(d->tile_off.ensure((size_t)ntiles * 4));
-    SearchGrid sg;
-    B2_TRY(search_grid(T, &sg));
-    cudaEvent_t n0 = nullptr, n1 = nullptr;
-    B2_CUDA(cudaEventCreate(&n0)); B2_CUDA(cudaEventCreate(&n1));
-    B2_CUDA(cudaEventRecord(n0, st));
-    // longest-first launch order (k_tile_cost + a 10^4..10^5-element radix sort); the geometry of a direction changes by millimetres
-    // between outer iterations, so the order is kept for eight of them
-    const unsigned int* order = nullptr;
-    if (h->lpt_order && !grid_order && ntiles > 4u * (unsigned int)h->sms) {
-      B2_TRY(d->order.ensure((size_t)ntiles * 16));
-      unsigned int* cc = d->order.as<unsigned int>();
-      if (d->order_src != d->src || d->order_tgt != d->tgt || d->order_tiles != ntiles || d->order_age >= 8) {
-        if (T->dense) k_tile_cost<true><<<div_up(ntiles, 256), 256, 0, st>>>(S->s_xyz.as<float4>(), ns, T->table.as<HashEntry>(), sg, ntiles, cc, cc + ntiles);
-        else k_tile_cost<false><<<div_up(ntiles, 256), 256, 0, st>>>(S->s_xyz.as<float4>(), ns, T->table.as<HashEntry>(), sg, ntiles, cc, cc + ntiles);
-        size_t tmp2 = 0;
-        B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp2, cc, cc + 2 * (size_t)ntiles, cc + ntiles, cc + 3 * (size_t)ntiles, (int)ntiles, 0, 32, st));
-        B2_TRY(cub_tmp.ensure(tmp2));
-        B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(cub_tmp.p, tmp2, cc, cc + 2 * (size_t)ntiles, cc + ntiles, cc + 3 * (size_t)ntiles, (int)ntiles, 0, 32, st));
-        d->order_src = d->src; d->order_tgt = d->tgt; d->order_tiles = ntiles; d->order_age = 0;
-        h->launches += 2;
-      }
-      ++d->order_age;
-      order = cc + 3 * (size_t)ntiles;
+    d->ahead_slot = -1;
+    if (S->n == 0 || T->n == 0) return B2_OK;
+    if (Ahead* a = find_ahead(h, S, T, r2)) {
+      std::swap(d->key, a->d.key); std::swap(d->tile_count, a->d.tile_count); std::swap(d->tile_off, a->d.tile_off); std::swap(d->order, a->d.order);
+      d->order_src = d->src; d->order_tgt = d->tgt; d->order_tiles = a->d.order_tiles; d->order_age = a->d.order_age;
+      d->ahead_slot = a->slot;
+      adopted.emplace_back(k, a->slot);
+      ++h->stats.searches_ahead;
+      return B2_OK;
     }
-    B2_CUDA(cudaMemsetAsync(d->tile_count.p, 0, (size_t)ntiles * 4, st));
-#define B2_LAUNCH_NN(STATS, DENSE)                                                                                                  \
-  k_nn_tiles<STATS, DENSE><<<ntiles, kTile, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(), T->box2.as<Aabb>(),  \
-                                                     T->table.as<HashEntry>(), sg, r2, d->key.as<unsigned long long>(),                 \
-                                                     d->tile_count.as<unsigned int>(), h->work_stats ? h->work_dev.as<unsigned long long>() : nullptr, order)
-    if (h->work_stats) { if (T->dense) B2_LAUNCH_NN(true, true); else B2_LAUNCH_NN(true, false); }
-    else { if (T->dense) B2_LAUNCH_NN(false, true); else B2_LAUNCH_NN(false, false); }
-#undef B2_LAUNCH_NN
-    B2_CUDA(cudaEventRecord(n1, st));
-    h->nn_events.emplace_back(n0, n1);
-    h->stats.search_algorithmic_bytes += 12ull * ns + 12ull * T->n;
-    k_scan_tiles<<<1, 1024, 0, st>>>(d->tile_count.as<unsigned int>(), ntiles, d->tile_off.as<unsigned int>(), h->totals_dev.as<unsigned int>() + k);
-    h->launches += 2;
-    B2_CUDA(cudaMemcpyAsync(&totals[k], h->totals_dev.as<unsigned int>() + k, 4, cudaMemcpyDeviceToHost, st));
-    return B2_OK;
+    return launch_search(h, d, S, T, r2, st, cub_tmp, h->totals_dev.as<unsigned int>() + k, &totals[k], true);
   };
 
   int issued = 0;
@@ -699,6 +819,11 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
     for (int i = 0; i + 1 < nstreams; ++i) { B2_CUDA(cudaEventRecord(h->join_ev[i], h->aux[i])); B2_CUDA(cudaStreamWaitEvent(h->stream, h->join_ev[i], 0)); }
   B2_CUDA(cudaStreamSynchronize(h->stream));
   B2_CUDA(cudaEventRecord(h->ev[2], h->stream));
+  if (!h->ahead.empty() || !h->ahead_clouds.empty()) {
+    for (int i = 0; i + 1 < h->nsearch; ++i) B2_CUDA(cudaStreamSynchronize(h->aux[i]));     // (also drained when nothing was launched above)
+    for (auto& ks : adopted) totals[ks.first] = h->ahead_totals_pin.as<unsigned int>()[ks.second];
+    drop_ahead(h);           // whatever was not adopted is stale by now
+  }
 
   // ---- K4: pack local non-empty sets into one record array ----
   h->segs_host.clear(); h->seg_dir.clear();
@@ -707,7 +832,7 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
     Direction* d = h->dirs[k].get();
     if (!d->local) continue;
     d->count = totals[k];
-    h->stats.search_algorithmic_bytes += 8ull * d->count;
+    if (d->ahead_slot < 0) h->stats.search_algorithmic_bytes += 8ull * d->count;
     d->rec_begin = total;
     if (d->count == 0) continue;   // empty sets are not registered (icp_point_to_plane.cc:240)
     h->segs_host.push_back(Segment{total, total + d->count, d->src, d->tgt});
@@ -924,7 +1049,7 @@ int b2_device_info(int* device, char* name, size_t name_cap, int* sm_count, int*
 void b2_icp_default_config(b2_icp_config* cfg) {
   if (!cfg) return;
   std::memset(cfg, 0, sizeof(*cfg));
-  cfg->device = -1; cfg->inner_max_iterations = 150; cfg->world_size = 1;
+  cfg->device = -1; cfg->inner_max_iterations = 150; cfg->world_size = 1; cfg->search_ahead = 1;
 }
 
 int b2_icp_create(const b2_icp_config* cfg, b2_icp** out) {
@@ -967,7 +1092,11 @@ int b2_icp_destroy(b2_icp* h) {
   };
   for (auto& c : h->movable) free_cloud(c.get());
   free_cloud(h->fixed.get());
-  for (auto& d : h->dirs) for (DevBuf* b : {&d->key, &d->tile_count, &d->tile_off, &d->order}) b->release();
+  drop_ahead(h);
+  for (DevBuf* b : {&h->ahead_totals_dev, &h->ahead_bbox}) b->release();
+  h->ahead_totals_pin.release();
+  if (h->ahead_ev) cudaEventDestroy(h->ahead_ev);
+  for (auto& d : h->dirs) release_direction(d.get());
   for (DevBuf* b : {&h->bbox_partial, &h->cub_tmp, &h->cell_counts, &h->rec_a, &h->rec_b, &h->rec_c, &h->segs_dev, &h->poses_dev, &h->partials,
                     &h->segsum, &h->eq_dev, &h->scatter_m, &h->scatter_d, &h->xpartials, &h->xsegsum, &h->work_dev, &h->totals_dev}) b->release();
   for (PinnedBuf* b : {&h->pin_bbox, &h->pin_counts, &h->pin_eq, &h->pin_poses, &h->pin_segs, &h->pin_misc}) b->release();

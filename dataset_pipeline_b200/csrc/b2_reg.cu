@@ -25,6 +25,7 @@
 
 #include "b2_common.cuh"
 #include "b2_hostmath.h"
+#include "b2_mesh_edges.h"
 #include "b2_reg_kernels.cuh"
 
 namespace b2 {
@@ -979,16 +980,26 @@ int b2_reg_add_point_scale(b2_reg* h, const float* xyz, size_t n, float radius, 
   if (n && (!xyz || !nbr || !colors)) return set_error(B2_ERR_ARG, "null argument");
   if (n >= (1ull << 31)) return set_error(B2_ERR_ARG, "point scales above 2^31 points are not supported");
   const int k = K(h);
+  // 64-bit caller indices -> 32-bit device indices, range-checked; a few host threads (the 15.8 M-point cloud of the benchmark has
+  // 7.9 * 10^7 of them) into an uninitialised buffer
+  std::unique_ptr<unsigned int[]> nb32(new unsigned int[std::max<size_t>(n * k, 1)]);
+  const int threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  std::vector<char> bad((size_t)threads, 0);
+  host_parallel_ranges(n * k, threads, [&](int part, size_t i0, size_t i1) {
+    unsigned int* out = nb32.get();
+    bool any = false;
+    for (size_t i = i0; i < i1; ++i) { any |= nbr[i] >= n; out[i] = (unsigned int)nbr[i]; }
+    bad[(size_t)part] = any;
+  });
+  for (char b : bad) if (b) return set_error(B2_ERR_ARG, "neighbour index out of range");
   ScaleB P; P.n = n; P.radius = radius;
   const size_t m = std::max<size_t>(n, 1);
   B2_TRY(P.xyz.ensure(m * 12)); B2_TRY(P.nbr.ensure(m * k * 4)); B2_TRY(P.fixed_desc.ensure(m * k * 4)); B2_TRY(P.var_desc.ensure(m * k * 4));
   B2_TRY(P.obs_count.ensure(m * 4));
   if (n) {
-    std::vector<unsigned int> nb32(n * k);
-    for (size_t i = 0; i < n * k; ++i) { if (nbr[i] >= n) return set_error(B2_ERR_ARG, "neighbour index out of range"); nb32[i] = (unsigned int)nbr[i]; }
     DevBuf col; B2_TRY(col.ensure(n * 4));
     B2_CUDA(cudaMemcpyAsync(P.xyz.p, xyz, n * 12, cudaMemcpyHostToDevice, h->stream));
-    B2_CUDA(cudaMemcpyAsync(P.nbr.p, nb32.data(), n * k * 4, cudaMemcpyHostToDevice, h->stream));
+    B2_CUDA(cudaMemcpyAsync(P.nbr.p, nb32.get(), n * k * 4, cudaMemcpyHostToDevice, h->stream));
     B2_CUDA(cudaMemcpyAsync(col.p, colors, n * 4, cudaMemcpyHostToDevice, h->stream));
     B2_CUDA(cudaMemsetAsync(P.fixed_desc.p, 0, n * k * 4, h->stream));
     B2_CUDA(cudaMemsetAsync(P.var_desc.p, 0, n * k * 4, h->stream));
@@ -1012,60 +1023,10 @@ int b2_reg_set_mesh(b2_reg* h, const float* vertices, size_t nv, const uint32_t*
   for (size_t i = 0; i < 3 * nf; ++i) if (faces[i] >= nv) return set_error(B2_ERR_ARG, "face index out of range");
   h->mesh_nv = nv; h->mesh_nf = nf; h->mesh_ne = 0;
   if (nf == 0) return B2_OK;
-  auto P = [&](uint32_t i, int c) { return vertices[3 * (size_t)i + c]; };
-  auto nrm3 = [](float* a) { const float n = std::sqrt(a[0] * a[0] + (a[1] * a[1] + a[2] * a[2])); a[0] /= n; a[1] /= n; a[2] /= n; };
-  auto dot3f = [](const float* a, const float* b) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); };
-  std::vector<float> fn(3 * nf);
-  typedef std::pair<uint32_t, uint32_t> Key;
-  std::map<Key, std::vector<std::pair<uint32_t, bool>>> half_edges;
-  for (size_t fi = 0; fi < nf; ++fi) {
-    const uint32_t* t = faces + 3 * fi;
-    const float a[3] = {P(t[1], 0) - P(t[0], 0), P(t[1], 1) - P(t[0], 1), P(t[1], 2) - P(t[0], 2)};
-    const float b[3] = {P(t[2], 0) - P(t[0], 0), P(t[2], 1) - P(t[0], 1), P(t[2], 2) - P(t[0], 2)};
-    float n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
-    nrm3(n);
-    fn[3 * fi] = n[0]; fn[3 * fi + 1] = n[1]; fn[3 * fi + 2] = n[2];
-    for (int k = 0; k < 3; ++k) {
-      uint32_t u = t[k], w = t[(k + 1) % 3];
-      const bool swapped = u > w;
-      if (swapped) std::swap(u, w);
-      half_edges[Key(u, w)].push_back(std::make_pair((uint32_t)fi, swapped));
-    }
-  }
-  std::vector<MeshEdgeDev> edges;
-  for (const auto& kv : half_edges) {
-    const auto& fl = kv.second;
-    MeshEdgeDev e; e.v1 = kv.first.first; e.v2 = kv.first.second; e.f1 = fl[0].first; e.f2 = 0; e.flags = 0;
-    if (fl.size() == 1) { e.flags = 1; edges.push_back(e); continue; }
-    const float ed[3] = {P(e.v2, 0) - P(e.v1, 0), P(e.v2, 1) - P(e.v1, 1), P(e.v2, 2) - P(e.v1, 2)};
-    float s1 = fl[0].second ? -1.f : 1.f, s2 = fl[1].second ? -1.f : 1.f;
-    const float n1v[3] = {fn[3 * e.f1] * s1, fn[3 * e.f1 + 1] * s1, fn[3 * e.f1 + 2] * s1};
-    const uint32_t face2 = fl[1].first;
-    const float n2v[3] = {fn[3 * face2] * s2, fn[3 * face2 + 1] * s2, fn[3 * face2 + 2] * s2};
-    e.f2 = face2;
-    bool opposite = s1 * s2 > 0;
-    float bx[3] = {n1v[0], n1v[1], n1v[2]}; nrm3(bx);
-    float by[3] = {bx[1] * ed[2] - bx[2] * ed[1], bx[2] * ed[0] - bx[0] * ed[2], bx[0] * ed[1] - bx[1] * ed[0]}; nrm3(by);
-    float n1x = 1.f, n1y = 0.f, n2x = dot3f(bx, n2v), n2y = dot3f(by, n2v);
-    if (n2x < 0 && std::fabs(n2y) < 1e-4f) continue;                      // coplanar pair: not an edge (:571-575)
-    bool keep = true;
-    if (fl.size() > 2) {
-      const float c12 = n2y;
-      for (size_t k = 2; k < fl.size(); ++k) {
-        const uint32_t f3 = fl[k].first; const float s3 = fl[k].second ? -1.f : 1.f;
-        const float cn[3] = {fn[3 * f3] * s3, fn[3 * f3 + 1] * s3, fn[3 * f3 + 2] * s3};
-        const float n3x = dot3f(bx, cn), n3y = dot3f(by, cn);
-        const float c13 = n1x * n3y - n1y * n3x, c23 = n2x * n3y - n2y * n3x;
-        const bool sign1 = c13 * c12 > 0, sign2 = c23 * c12 < 0;
-        if (sign1 && !sign2) { n2x = n3x; n2y = n3y; e.f2 = f3; s2 = s3; opposite = s1 * s3 != 1; }
-        else if (sign2 && !sign1) { n1x = n3x; n1y = n3y; e.f1 = f3; s1 = s3; opposite = s3 * s2 != 1; }
-        else if (!sign2) { keep = false; break; }                          // `!sign2 && !sign2` in the reference (:633)
-      }
-    }
-    if (!keep) continue;
-    e.flags = opposite ? 2u : 0u;
-    edges.push_back(e);
-  }
+  static_assert(sizeof(MeshEdgeHost) == sizeof(MeshEdgeDev), "host and device edge records must have one layout");
+  std::vector<float> fn;
+  std::vector<MeshEdgeHost> edges;
+  build_mesh_edges(vertices, nv, faces, nf, &fn, &edges);
   h->mesh_ne = edges.size();
   B2_TRY(h->mesh_v.ensure(nv * 12)); B2_TRY(h->mesh_f.ensure(nf * 12)); B2_TRY(h->mesh_fn.ensure(nf * 12));
   B2_TRY(h->mesh_edges.ensure(std::max<size_t>(edges.size(), 1) * sizeof(MeshEdgeDev)));

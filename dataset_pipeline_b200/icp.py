@@ -49,7 +49,7 @@ class Comm:
 
 class PointToPlaneICP:
     def __init__(self, device=-1, inner_max_iterations=150, keep_correspondences=False, rank=0, world_size=1,
-                 allreduce=None, stream=None, comm=None, index_distance_hint=0.0, shard_uploads=False):
+                 allreduce=None, stream=None, comm=None, index_distance_hint=0.0, shard_uploads=False, search_ahead=True):
         L = _lib.lib()
         cfg = _lib.IcpConfig()
         L.b2_icp_default_config(C.byref(cfg))
@@ -59,6 +59,7 @@ class PointToPlaneICP:
         cfg.rank, cfg.world_size = rank, world_size
         cfg.index_distance_hint = float(index_distance_hint)
         cfg.shard_uploads = int(bool(shard_uploads))
+        cfg.search_ahead = int(bool(search_ahead))
         self._cb = None
         if allreduce is not None:
             # allreduce(ptr:int, count:int, stream:int) -> None ; wrapped into the C hook

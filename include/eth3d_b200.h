@@ -88,6 +88,11 @@ typedef struct b2_icp_config {
                                    in the same order with the same n; only rank (cloud_id % world_size) reads its host buffers and
                                    copies them to its GPU, the other ranks receive the cloud by ncclBroadcast over NVLink (their
                                    xyz / normals arguments are ignored and may be NULL). Fixed clouds are uploaded by every rank. */
+  int32_t search_ahead;         /* != 0 (the default of b2_icp_default_config; needs index_distance_hint, one rank): b2_icp_add_cloud also
+                                   searches the pair-directions among the clouds added so far, at the hinted radius and the poses they
+                                   were added with, on auxiliary streams behind the uploads that follow. The first b2_icp_run adopts
+                                   those results if radius, poses and indexes are still the same, and searches as usual otherwise:
+                                   results never differ, only when the work happens. */
 } b2_icp_config;
 
 typedef struct b2_icp_stats {
@@ -109,6 +114,8 @@ typedef struct b2_icp_stats {
   float ms_index_build;         /* one-time static index builds that fell into this outer iteration (0 once every cloud is indexed) */
   int32_t sparse_grids;         /* clouds whose occupied-cell index uses the hash layout (grid above 2^31 cells) instead of the rank bitmap */
   uint64_t search_work[5];      /* B2_K3_WORK=1 only: candidates tested, level-1 box tests, level-2 box tests, cells scanned, queue items */
+  int32_t searches_ahead;       /* pair-directions of this outer iteration whose search had been done behind the uploads (search_ahead);
+                                   they are not in search_launches / ms_search / search_algorithmic_bytes */
 } b2_icp_stats;
 
 void b2_icp_default_config(b2_icp_config* cfg);

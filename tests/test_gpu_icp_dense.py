@@ -196,3 +196,82 @@ def test_sparse_grid_uses_the_hash_layout(b2, oracle, monkeypatch):
     assert (0, 1) in seen and (1, 0) in seen
     assert st["sparse_grids"] == 2
     assert st["num_correspondences"] > 50000
+
+
+def _run_handle(b2, clouds, poses, d, iterations=2, move=None, **kw):
+    g = b2.PointToPlaneICP(keep_correspondences=True, **kw)
+    for (xyz, nrm), T in zip(clouds, poses):
+        g.AddPointCloud(xyz, nrm, T)
+    if move is not None:
+        g.SetGlobalTCloud(*move)
+    out = []
+    for it in range(iterations):
+        g.Run(d, it, 1, 1e-10, False)
+        st = g.stats()
+        out.append((st, g.pairs(), [g.GetResultGlobalTCloud(i) for i in range(len(clouds))], g.tries()))
+    g.close()
+    return out
+
+
+def _same_iterations(a, b, exact=True):
+    """exact: everything bit for bit (same index grids, hence the same record order and the same fp64 summation order).
+    not exact: the lists bit for bit, the fp64 sums to rounding (the grids — and with them the order of the records — may differ)."""
+    for it, ((sa, pa, Ta, ta), (sb, pb, Tb, tb)) in enumerate(zip(a, b)):
+        assert [(s, t) for s, t, *_ in pa] == [(s, t) for s, t, *_ in pb]
+        if exact or it == 0:
+            for (s, t, q1, m1, d1), (_, _, q2, m2, d2) in zip(pa, pb):
+                assert np.array_equal(q1, q2) and np.array_equal(m1, m2) and np.array_equal(d1, d2), "iteration %d pair %d->%d" % (it, s, t)
+        for k in ("num_correspondences", "num_pairs", "inner_iterations", "lm_tries_total"):
+            if exact or it == 0:
+                assert sa[k] == sb[k], (it, k, sa[k], sb[k])
+        for k in ("first_cost", "last_cost"):
+            if exact:
+                assert sa[k] == sb[k], (it, k, sa[k], sb[k])
+            elif it == 0:
+                assert abs(sa[k] - sb[k]) <= 1e-11 * abs(sa[k]), (it, k, sa[k], sb[k])
+        if exact:
+            assert list(ta) == list(tb)
+            for A, B in zip(Ta, Tb):
+                assert np.array_equal(A, B)
+
+
+def test_searches_done_behind_the_uploads_are_the_same_searches(b2, oracle):
+    """search_ahead (index_distance_hint given): the pair-directions among the clouds indexed while later clouds upload are searched at
+    add time and adopted by the first Run. Lists, costs, LM decisions and poses are bit-identical to a handle that searches inside Run,
+    and the adoption is dropped — not trusted — when a pose or the radius is not what it was searched with."""
+    from dataset_pipeline_b200 import synth
+    clouds, poses, _ = synth.room_scans(4, 400, 300)
+    d = 0.02
+    plain = _run_handle(b2, clouds, poses, d)
+    assert plain[0][0]["searches_ahead"] == 0 and plain[0][0]["search_launches"] == 12
+    # same handle configuration (hint: the indexes are built at AddPointCloud), searching inside Run: the bit-for-bit baseline
+    off = _run_handle(b2, clouds, poses, d, index_distance_hint=d, search_ahead=False)
+    assert off[0][0]["searches_ahead"] == 0 and off[0][0]["search_launches"] == 12
+    ahead = _run_handle(b2, clouds, poses, d, index_distance_hint=d)
+    # clouds 0..2 are indexed behind the uploads of clouds 1..3; cloud 3 is indexed by Run: 6 of the 12 directions were done ahead
+    assert ahead[0][0]["searches_ahead"] == 6 and ahead[0][0]["search_launches"] == 6
+    assert ahead[1][0]["searches_ahead"] == 0 and ahead[1][0]["search_launches"] == 12
+    _same_iterations(off, ahead)
+    # without a hint the index grids may be laid out differently (they are sized from all clouds' magnitudes instead of each cloud's
+    # own), which reorders the records of a set: same lists, sums equal to rounding
+    _same_iterations(plain, ahead, exact=False)
+    # against the oracle too (first iteration's lists)
+    o = oracle.PointToPlaneICP(use_kdtree=True)
+    for (xyz, nrm), T in zip(clouds, poses):
+        o.AddPointCloud(xyz, nrm, T)
+    o.Run(d, 0, 1, 1e-10, False)
+    for (s, t, q1, m1, d1), (_, _, q2, m2, d2) in zip(ahead[0][1], o.pairs()):
+        assert np.array_equal(q1, q2) and np.array_equal(m1, m2) and np.array_equal(d1, d2), "pair %d->%d" % (s, t)
+
+    # a pose changed between AddPointCloud and Run: the directions of that cloud are searched again, the others are adopted
+    T1 = poses[1].copy(); T1[:3, 3] += np.array([0.004, -0.003, 0.002], np.float32)
+    moved_off = _run_handle(b2, clouds, poses, d, move=(1, T1), index_distance_hint=d, search_ahead=False)
+    moved_ahead = _run_handle(b2, clouds, poses, d, move=(1, T1), index_distance_hint=d)
+    assert moved_ahead[0][0]["searches_ahead"] == 2 and moved_ahead[0][0]["search_launches"] == 10
+    _same_iterations(moved_off, moved_ahead)
+
+    # Run called with another radius than the hint: nothing is adopted (and the indexes are rebuilt for the new radius)
+    other_off = _run_handle(b2, clouds, poses, 0.012, index_distance_hint=d, search_ahead=False)
+    other_ahead = _run_handle(b2, clouds, poses, 0.012, index_distance_hint=d)
+    assert other_ahead[0][0]["searches_ahead"] == 0 and other_ahead[0][0]["search_launches"] == 12
+    _same_iterations(other_off, other_ahead)
