@@ -167,9 +167,10 @@ def secondary_line(world=1, rank=0, comm=None, local=0, num_images=20, width=600
             torch.cuda.synchronize(dev); t0 = time.perf_counter()
             ge = make(); ge.set_image_scale(0)
             t1 = time.perf_counter()
-            step(ge); _ = ge.get_state()
+            st_e = step(ge); _ = ge.get_state()
             torch.cuda.synchronize(dev); d = time.perf_counter() - t0
             e2e_parts = dict(make.parts); e2e_parts["iteration_ms"] = 1e3 * (t0 + d - t1)
+            e2e_parts.update({"iteration_device_" + k: st_e[k] for k in ("ms_create_observations", "ms_color", "ms_apply")})
             ge.close()
             e2e_parts["destroy_ms"] = 1e3 * (time.perf_counter() - t0 - d)
             if world > 1:

@@ -30,7 +30,7 @@ class IcpStats(C.Structure):
                 ("ms_total", C.c_float), ("ms_accum_kernel_avg", C.c_float), ("ms_search_kernel_avg", C.c_float),
                 ("search_launches", C.c_int32), ("search_algorithmic_bytes", C.c_uint64),
                 ("ms_index_build", C.c_float), ("sparse_grids", C.c_int32), ("search_work", C.c_uint64 * 5),
-                ("searches_ahead", C.c_int32)]
+                ("searches_ahead", C.c_int32), ("packs_overlapped", C.c_int32)]
 
 
 class B2Error(RuntimeError):
@@ -72,6 +72,7 @@ EXPORTS = [
     "b2_icp_last_stats",
     "b2_icp_plan_directions",
     "b2_icp_run",
+    "b2_icp_set_option",
     "b2_icp_set_pose",
     "b2_icp_upload_owner",
     "b2_last_error",
@@ -154,6 +155,7 @@ def lib():
     L.b2_icp_get_pose.argtypes = [vp, C.c_int, fp]
     L.b2_icp_set_pose.argtypes = [vp, C.c_int, fp]
     L.b2_icp_last_stats.argtypes = [vp, C.POINTER(IcpStats)]
+    L.b2_icp_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     L.b2_icp_get_lm_tries.argtypes = [vp, ip, C.c_int, ip]
     L.b2_icp_get_pair_info.argtypes = [vp, C.c_int, ip, ip, C.POINTER(C.c_uint64)]
     L.b2_icp_get_pair_correspondences.argtypes = [vp, C.c_int, ip, ip, fp]

@@ -117,6 +117,17 @@ struct b2_icp {
   PinnedBuf ahead_totals_pin;
   cudaEvent_t ahead_ev = nullptr;
   int ahead_rr = 0;
+  // K4 overlapped with K3: a set is packed on pack_stream as soon as its search has finished, at a device-side running offset
+  // Off by default: measured on config 2 (r02D) the step took 51.35 ms with it and 51.49 ms without — K3 needs its occupancy and K4
+  // its threads in flight, they take SM slots from each other one for one — and sizing the record arrays for the worst case made
+  // create / destroy of a handle slower. Kept as an option (B2_PACK=overlap | overlap_nosize, b2_icp_set_option "pack_overlap").
+  bool pack_overlap = false;
+  bool pack_presize = true;             // overlap_nosize: no worst-case sizing of the record arrays in the first iteration (tests)
+  cudaStream_t pack_stream = nullptr;
+  cudaEvent_t pack_join_ev = nullptr;
+  std::vector<cudaEvent_t> done_ev;     // search of the i-th issued set finished
+  DevBuf chain_dev;                     // [sets + 1] running offsets + overflow flag
+  PinnedBuf pin_chain;
   // K3 runs the pair-directions of an iteration round-robin over `nsearch` streams (the handle's + auxiliaries) so that one
   // direction's tail overlaps the next direction's head; each stream has its own CUB scratch.
   static constexpr int kMaxSearchStreams = 8;
@@ -459,7 +470,7 @@ static int launch_accumulate_tma(b2_icp* h, int nseg, int nc) {
   }
   k_accumulate_tma<WITH_H, NX><<<h->grid_acc, kAccThreads, kTmaSmemBytes, h->stream>>>(
       h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>(), h->segs_dev.as<Segment>(), nseg, h->poses_dev.as<CloudPose>(), nc,
-      h->total_records, h->per_cta, h->partials.as<double>(), h->xpartials.as<double>());
+      h->total_records, h->per_cta, h->partials.as<double>(), h->xpartials.as<double>(), 1.0f, -0.0f);
   return B2_OK;
 }
 
@@ -789,6 +800,8 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   const int nstreams = h->nsearch;
   for (int k = 0; k < h->ndirs; ++k) { h->dirs[k]->count = 0; totals[k] = 0; }
   std::vector<std::pair<int, int>> adopted;      // (direction, slot): searched ahead of this call
+  bool launched = false;
+  int adopted_slot = -1;
   auto issue_search = [&](int k, cudaStream_t st, DevBuf& cub_tmp) -> int {
     Direction* d = h->dirs[k].get();
     Cloud* S = impl_cloud(h, d->src); Cloud* T = impl_cloud(h, d->tgt);
@@ -799,24 +812,80 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
       d->order_src = d->src; d->order_tgt = d->tgt; d->order_tiles = a->d.order_tiles; d->order_age = a->d.order_age;
       d->ahead_slot = a->slot;
       adopted.emplace_back(k, a->slot);
+      adopted_slot = a->slot;
       ++h->stats.searches_ahead;
       return B2_OK;
     }
+    launched = true;
     return launch_search(h, d, S, T, r2, st, cub_tmp, h->totals_dev.as<unsigned int>() + k, &totals[k], true);
   };
 
+  // ---- optional (pack_overlap): K4 behind K3 — a set is packed (on pack_stream) as soon as its search has finished, while later sets
+  // are still being searched. A set's first record
+  // is a running offset kept on the device (PackChain); the host learns the counts at the one synchronisation below, as before, and
+  // derives the same offsets for the segment table. Needs record arrays that are already large enough: sized from the previous
+  // iteration, or — first iteration — for the worst case (every query matched) when that is a small part of the free memory.
+  int nlocal = 0;
+  unsigned long long worst = 0;
+  for (int k = 0; k < h->ndirs; ++k)
+    if (h->dirs[k]->local) { ++nlocal; const Cloud* S = impl_cloud(h, h->dirs[k]->src); if (impl_cloud(h, h->dirs[k]->tgt)->n) worst += S->n; }
+  bool chain = h->pack_overlap && !search_only && !h->work_stats && nlocal > 0;
+  if (chain && h->pack_presize && h->rec_a.cap == 0 && worst > 0) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (double)worst * 48.0 * 1.2 < 0.25 * (double)free_b) {
+      B2_TRY(h->rec_a.ensure(worst * 16)); B2_TRY(h->rec_b.ensure(worst * 16)); B2_TRY(h->rec_c.ensure(worst * 16));
+    }
+  }
+  const unsigned long long rec_cap = std::min({h->rec_a.cap, h->rec_b.cap, h->rec_c.cap}) / 16;
+  chain = chain && rec_cap > 0;
+  unsigned long long* chain_base = nullptr;
+  unsigned int* chain_overflow = nullptr;
+  int chain_pos = 0;
+  if (chain) {
+    const size_t bytes = ((size_t)nlocal + 2) * sizeof(unsigned long long);
+    B2_TRY(h->chain_dev.ensure(bytes)); B2_TRY(h->pin_chain.ensure(sizeof(unsigned int)));
+    B2_CUDA(cudaMemsetAsync(h->chain_dev.p, 0, bytes, h->stream));
+    chain_base = h->chain_dev.as<unsigned long long>();
+    chain_overflow = reinterpret_cast<unsigned int*>(chain_base + nlocal + 1);
+    *h->pin_chain.as<unsigned int>() = 1u;         // pessimistic until the flag has been read back
+    while ((int)h->done_ev.size() < nlocal) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->done_ev.push_back(e); }
+  }
+
   int issued = 0;
-  if (nstreams > 1) {
+  if (nstreams > 1 || chain) {
     B2_CUDA(cudaEventRecord(h->fork_ev, h->stream));
     for (int i = 0; i + 1 < nstreams; ++i) B2_CUDA(cudaStreamWaitEvent(h->aux[i], h->fork_ev, 0));
+    if (chain) B2_CUDA(cudaStreamWaitEvent(h->pack_stream, h->fork_ev, 0));
   }
   for (int k = 0; k < h->ndirs; ++k) {
     if (!h->dirs[k]->local) continue;
     const int si = issued++ % nstreams;
-    B2_TRY(issue_search(k, si == 0 ? h->stream : h->aux[si - 1], h->search_tmp[si]));
+    cudaStream_t st = si == 0 ? h->stream : h->aux[si - 1];
+    launched = false; adopted_slot = -1;
+    B2_TRY(issue_search(k, st, h->search_tmp[si]));
+    if (chain && (launched || adopted_slot >= 0)) {
+      Direction* d = h->dirs[k].get();
+      Cloud* S = impl_cloud(h, d->src); Cloud* T = impl_cloud(h, d->tgt);
+      if (launched) {
+        B2_CUDA(cudaEventRecord(h->done_ev[chain_pos], st));
+        B2_CUDA(cudaStreamWaitEvent(h->pack_stream, h->done_ev[chain_pos], 0));
+      }   // (a set searched ahead of this call is complete: this call's work was queued behind the auxiliary streams above)
+      const unsigned int* set_total = launched ? h->totals_dev.as<unsigned int>() + k : h->ahead_totals_dev.as<unsigned int>() + adopted_slot;
+      const PackChain pc = {chain_base, set_total, chain_overflow, rec_cap, chain_pos};
+      k_pack_tiles<<<div_up(S->n, kTile), kTile, 0, h->pack_stream>>>(S->s_xyz.as<float4>(), S->s_nrm.as<float4>(), S->n, T->s_xyz.as<float4>(),
+                                                                      T->s_nrm.as<float4>(), T->perm_inv.as<unsigned int>(),
+                                                                      d->key.as<unsigned long long>(), d->tile_off.as<unsigned int>(), init_key, 0ull, pc,
+                                                                      h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>());
+      ++h->launches; ++chain_pos;
+    }
   }
   if (nstreams > 1)
     for (int i = 0; i + 1 < nstreams; ++i) { B2_CUDA(cudaEventRecord(h->join_ev[i], h->aux[i])); B2_CUDA(cudaStreamWaitEvent(h->stream, h->join_ev[i], 0)); }
+  if (chain) {
+    B2_CUDA(cudaMemcpyAsync(h->pin_chain.p, chain_overflow, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->pack_stream));
+    B2_CUDA(cudaEventRecord(h->pack_join_ev, h->pack_stream));
+    B2_CUDA(cudaStreamWaitEvent(h->stream, h->pack_join_ev, 0));
+  }
   B2_CUDA(cudaStreamSynchronize(h->stream));
   B2_CUDA(cudaEventRecord(h->ev[2], h->stream));
   if (!h->ahead.empty() || !h->ahead_clouds.empty()) {
@@ -844,12 +913,16 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   if (search_only) { *converged = false; h->stats.kernel_launches = h->launches; return B2_OK; }
   B2_TRY(h->rec_a.ensure(std::max<unsigned long long>(total, 1) * 16)); B2_TRY(h->rec_b.ensure(std::max<unsigned long long>(total, 1) * 16));
   B2_TRY(h->rec_c.ensure(std::max<unsigned long long>(total, 1) * 16));
-  for (int s = 0; s < nseg; ++s) {
+  // (the device-side offsets of an overlapped pack are the prefix sums computed above: same counts, same set order)
+  const bool packed = chain && *h->pin_chain.as<unsigned int>() == 0u;
+  h->stats.packs_overlapped = packed ? chain_pos : 0;
+  for (int s = 0; s < nseg && !packed; ++s) {
     Direction* d = h->dirs[h->seg_dir[s]].get();
     Cloud* S = impl_cloud(h, d->src); Cloud* T = impl_cloud(h, d->tgt);
+    const PackChain none = {nullptr, nullptr, nullptr, 0ull, 0};
     k_pack_tiles<<<div_up(S->n, kTile), kTile, 0, h->stream>>>(S->s_xyz.as<float4>(), S->s_nrm.as<float4>(), S->n, T->s_xyz.as<float4>(),
                                                                T->s_nrm.as<float4>(), T->perm_inv.as<unsigned int>(), d->key.as<unsigned long long>(),
-                                                               d->tile_off.as<unsigned int>(), init_key, d->rec_begin, h->rec_a.as<float4>(),
+                                                               d->tile_off.as<unsigned int>(), init_key, d->rec_begin, none, h->rec_a.as<float4>(),
                                                                h->rec_b.as<float4>(), h->rec_c.as<float4>());
     ++h->launches;
   }
@@ -1075,6 +1148,13 @@ int b2_icp_create(const b2_icp_config* cfg, b2_icp** out) {
     B2_CUDA(cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
   }
   B2_CUDA(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+  {
+    int least = 0, greatest = 0;
+    B2_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    B2_CUDA(cudaStreamCreateWithPriority(&h->pack_stream, cudaStreamNonBlocking, greatest));   // its short kernels slot in between K3's tiles
+    B2_CUDA(cudaEventCreateWithFlags(&h->pack_join_ev, cudaEventDisableTiming));
+    if (const char* e = getenv("B2_PACK")) { const std::string v(e); h->pack_overlap = v == "overlap" || v == "overlap_nosize"; h->pack_presize = v != "overlap_nosize"; }
+  }
   for (auto& e : h->ev) B2_CUDA(cudaEventCreate(&e));
   std::memset(&h->stats, 0, sizeof(h->stats));
   *out = h.release();
@@ -1093,6 +1173,10 @@ int b2_icp_destroy(b2_icp* h) {
   for (auto& c : h->movable) free_cloud(c.get());
   free_cloud(h->fixed.get());
   drop_ahead(h);
+  if (h->pack_stream) { cudaStreamSynchronize(h->pack_stream); cudaStreamDestroy(h->pack_stream); }
+  if (h->pack_join_ev) cudaEventDestroy(h->pack_join_ev);
+  for (cudaEvent_t e : h->done_ev) cudaEventDestroy(e);
+  h->chain_dev.release(); h->pin_chain.release();
   for (DevBuf* b : {&h->ahead_totals_dev, &h->ahead_bbox}) b->release();
   h->ahead_totals_pin.release();
   if (h->ahead_ev) cudaEventDestroy(h->ahead_ev);
@@ -1186,6 +1270,15 @@ int b2_icp_get_pose(b2_icp* h, int id, float T[16]) {
 int b2_icp_set_pose(b2_icp* h, int id, const float T[16]) {
   if (!h || !T || id < 0 || id >= (int)h->movable.size()) return set_error(B2_ERR_ARG, "bad cloud id %d", id);
   std::memcpy(h->movable[id]->T, T, sizeof(float) * 16);
+  return B2_OK;
+}
+
+int b2_icp_set_option(b2_icp* h, const char* name, int value) {
+  if (!h || !name) return set_error(B2_ERR_ARG, "null argument");
+  const std::string n(name);
+  if (n == "pack_overlap") h->pack_overlap = value != 0;
+  else if (n == "lpt_order") h->lpt_order = value != 0;
+  else return set_error(B2_ERR_ARG, "unknown option '%s'", name);
   return B2_OK;
 }
 

@@ -294,9 +294,21 @@ struct SearchWork { unsigned int points, box1, box2, cells; };   // work counter
   {                                                                                                                   \
     const float ax_ = __fmaf_rn((T).x, -one, q.x), ay_ = __fmaf_rn((T).y, -one, q.y), az_ = __fmaf_rn((T).z, -one, q.z);  \
     const float d_ = __fmaf_rn(__fmaf_rn(fmul(ax_, ax_), one, fmul(ay_, ay_)), one, fmul(az_, az_));                  \
-    const unsigned long long k_ = ((unsigned long long)__float_as_uint(d_) << 32) | (unsigned long long)__float_as_uint((T).w); \
+    B2_NN_MIN(d_, (T).w)                                                                                              \
+  }
+// The 64-bit key minimum. Default: unsigned compare + selects (ISETP, ISETP.EX, 2 SEL on the ALU pipe). B2_K3_DMIN: the same minimum
+// taken as an fp64 one (DSETP.MIN + 2 selects): for a finite non-negative d2 the key's bit pattern is a finite non-negative double
+// whose order is the order of the bit patterns, and a NaN d2 loses either way.
+#ifdef B2_K3_DMIN
+#define B2_NN_MIN(D, W)                                                                                               \
+  best = (unsigned long long)__double_as_longlong(fmin(__longlong_as_double((long long)best), __hiloint2double(__float_as_int(D), __float_as_int(W))));
+#else
+#define B2_NN_MIN(D, W)                                                                                               \
+  {                                                                                                                   \
+    const unsigned long long k_ = ((unsigned long long)__float_as_uint(D) << 32) | (unsigned long long)__float_as_uint(W); \
     best = k_ < best ? k_ : best;                                                                                     \
   }
+#endif
 
 __device__ __forceinline__ float key_d2(unsigned long long key) { return __uint_as_float((unsigned int)(key >> 32)); }
 
@@ -731,13 +743,25 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const unsigned int* __restr
   if (threadIdx.x == 1023) *total = s[1023];
 }
 
+// Where a set's records start: either the host's value (`base`, chain == nullptr) or — when the sets are packed while later sets are
+// still being searched — a device-side running offset: set number `pos` of the iteration starts at chain->base[pos] and publishes
+// chain->base[pos + 1] = its start + its match count (the packs of an iteration run in set order on one stream). A set that would not
+// fit into the record arrays raises chain->overflow and writes nothing; the host then packs the classic way.
+struct PackChain { unsigned long long* base; const unsigned int* total; unsigned int* overflow; unsigned long long cap; int pos; };
+
 __global__ void __launch_bounds__(kTile) k_pack_tiles(const float4* __restrict__ s_xyz_src, const float4* __restrict__ s_nrm_src, size_t ns,
                                                       const float4* __restrict__ s_xyz_tgt, const float4* __restrict__ s_nrm_tgt,
                                                       const unsigned int* __restrict__ perm_inv_tgt, const unsigned long long* __restrict__ key,
                                                       const unsigned int* __restrict__ tile_off, unsigned long long init_key,
-                                                      unsigned long long base, float4* __restrict__ ra, float4* __restrict__ rb,
+                                                      unsigned long long base, PackChain chain, float4* __restrict__ ra, float4* __restrict__ rb,
                                                       float4* __restrict__ rc) {
   __shared__ unsigned int warp_sum[kTile / 32];
+  if (chain.base) {                                   // (block-uniform)
+    base = chain.base[chain.pos];
+    const unsigned long long end = base + (unsigned long long)*chain.total;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { chain.base[chain.pos + 1] = end; if (end > chain.cap) *chain.overflow = 1u; }
+    if (end > chain.cap) return;
+  }
   const size_t j = (size_t)blockIdx.x * kTile + threadIdx.x;
   const unsigned int lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
   const unsigned long long k = j < ns ? key[j] : init_key;
@@ -752,9 +776,10 @@ __global__ void __launch_bounds__(kTile) k_pack_tiles(const float4* __restrict__
   const float4 ps = s_xyz_src[j], nsr = s_nrm_src[j];
   const float4 pt = __ldg(s_xyz_tgt + p), nt = __ldg(s_nrm_tgt + p);
   const unsigned long long o = base + tile_off[blockIdx.x] + before;
-  ra[o] = make_float4(ps.x, ps.y, ps.z, nsr.x);
-  rb[o] = make_float4(nsr.y, nsr.z, pt.x, pt.y);
-  rc[o] = make_float4(pt.z, nt.x, nt.y, nt.z);
+  // source and target components interleaved (see "Record layout" at K5): the packed fp32 path reads its operand pairs as they lie
+  ra[o] = make_float4(ps.x, pt.x, ps.y, pt.y);
+  rb[o] = make_float4(ps.z, pt.z, nsr.x, nt.x);
+  rc[o] = make_float4(nsr.y, nt.y, nsr.z, nt.z);
 }
 
 // Correspondence list in the caller's (original) indexing, scattered to the original query index.
@@ -790,20 +815,30 @@ __device__ __forceinline__ void load_pose(const CloudPose* __restrict__ P, int i
   for (int k = 0; k < 3; ++k) t[k] = __ldg(&P[i].t[k]);
 }
 
+// Record layout (three float4 planes, 48 B): a = (ps.x, pt.x, ps.y, pt.y), b = (ps.z, pt.z, ns.x, nt.x), c = (ns.y, nt.y, ns.z, nt.z) —
+// the source and target value of every component side by side, which is how the packed path below consumes them.
+struct RecordFields { float psx, psy, psz, nsx, nsy, nsz, ptx, pty, ptz, ntx, nty, ntz; };
+__device__ __forceinline__ RecordFields record_fields(const float4 a, const float4 b, const float4 c) {
+  RecordFields f;
+  f.psx = a.x; f.ptx = a.y; f.psy = a.z; f.pty = a.w; f.psz = b.x; f.ptz = b.y; f.nsx = b.z; f.ntx = b.w; f.nsy = c.x; f.nty = c.y; f.nsz = c.z; f.ntz = c.w;
+  return f;
+}
+
 __device__ __forceinline__ void accumulate_record(const float4 a, const float4 b, const float4 c, const float Rs[9], const float ts[3],
                                                   const float Rt[9], const float tt[3], double acc[kAccVals]) {
-  const float psx = fadd(sum3(fmul(Rs[0], a.x), fmul(Rs[1], a.y), fmul(Rs[2], a.z)), ts[0]);
-  const float psy = fadd(sum3(fmul(Rs[3], a.x), fmul(Rs[4], a.y), fmul(Rs[5], a.z)), ts[1]);
-  const float psz = fadd(sum3(fmul(Rs[6], a.x), fmul(Rs[7], a.y), fmul(Rs[8], a.z)), ts[2]);
-  const float nsx = sum3(fmul(Rs[0], a.w), fmul(Rs[1], b.x), fmul(Rs[2], b.y));
-  const float nsy = sum3(fmul(Rs[3], a.w), fmul(Rs[4], b.x), fmul(Rs[5], b.y));
-  const float nsz = sum3(fmul(Rs[6], a.w), fmul(Rs[7], b.x), fmul(Rs[8], b.y));
-  const float ptx = fadd(sum3(fmul(Rt[0], b.z), fmul(Rt[1], b.w), fmul(Rt[2], c.x)), tt[0]);
-  const float pty = fadd(sum3(fmul(Rt[3], b.z), fmul(Rt[4], b.w), fmul(Rt[5], c.x)), tt[1]);
-  const float ptz = fadd(sum3(fmul(Rt[6], b.z), fmul(Rt[7], b.w), fmul(Rt[8], c.x)), tt[2]);
-  const float ntx = sum3(fmul(Rt[0], c.y), fmul(Rt[1], c.z), fmul(Rt[2], c.w));
-  const float nty = sum3(fmul(Rt[3], c.y), fmul(Rt[4], c.z), fmul(Rt[5], c.w));
-  const float ntz = sum3(fmul(Rt[6], c.y), fmul(Rt[7], c.z), fmul(Rt[8], c.w));
+  const RecordFields f = record_fields(a, b, c);
+  const float psx = fadd(sum3(fmul(Rs[0], f.psx), fmul(Rs[1], f.psy), fmul(Rs[2], f.psz)), ts[0]);
+  const float psy = fadd(sum3(fmul(Rs[3], f.psx), fmul(Rs[4], f.psy), fmul(Rs[5], f.psz)), ts[1]);
+  const float psz = fadd(sum3(fmul(Rs[6], f.psx), fmul(Rs[7], f.psy), fmul(Rs[8], f.psz)), ts[2]);
+  const float nsx = sum3(fmul(Rs[0], f.nsx), fmul(Rs[1], f.nsy), fmul(Rs[2], f.nsz));
+  const float nsy = sum3(fmul(Rs[3], f.nsx), fmul(Rs[4], f.nsy), fmul(Rs[5], f.nsz));
+  const float nsz = sum3(fmul(Rs[6], f.nsx), fmul(Rs[7], f.nsy), fmul(Rs[8], f.nsz));
+  const float ptx = fadd(sum3(fmul(Rt[0], f.ptx), fmul(Rt[1], f.pty), fmul(Rt[2], f.ptz)), tt[0]);
+  const float pty = fadd(sum3(fmul(Rt[3], f.ptx), fmul(Rt[4], f.pty), fmul(Rt[5], f.ptz)), tt[1]);
+  const float ptz = fadd(sum3(fmul(Rt[6], f.ptx), fmul(Rt[7], f.pty), fmul(Rt[8], f.ptz)), tt[2]);
+  const float ntx = sum3(fmul(Rt[0], f.ntx), fmul(Rt[1], f.nty), fmul(Rt[2], f.ntz));
+  const float nty = sum3(fmul(Rt[3], f.ntx), fmul(Rt[4], f.nty), fmul(Rt[5], f.ntz));
+  const float ntz = sum3(fmul(Rt[6], f.ntx), fmul(Rt[7], f.nty), fmul(Rt[8], f.ntz));
 
   const float r1 = dot3(nsx, nsy, nsz, fsub(ptx, psx), fsub(pty, psy), fsub(ptz, psz));
   const float r2 = dot3(ntx, nty, ntz, fsub(psx, ptx), fsub(psy, pty), fsub(psz, ptz));
@@ -834,22 +869,61 @@ __device__ __forceinline__ void accumulate_record(const float4 a, const float4 b
 
 __device__ __forceinline__ void cost_record(const float4 a, const float4 b, const float4 c, const float Rs[9], const float ts[3],
                                             const float Rt[9], const float tt[3], double* cost) {
-  const float psx = fadd(sum3(fmul(Rs[0], a.x), fmul(Rs[1], a.y), fmul(Rs[2], a.z)), ts[0]);
-  const float psy = fadd(sum3(fmul(Rs[3], a.x), fmul(Rs[4], a.y), fmul(Rs[5], a.z)), ts[1]);
-  const float psz = fadd(sum3(fmul(Rs[6], a.x), fmul(Rs[7], a.y), fmul(Rs[8], a.z)), ts[2]);
-  const float nsx = sum3(fmul(Rs[0], a.w), fmul(Rs[1], b.x), fmul(Rs[2], b.y));
-  const float nsy = sum3(fmul(Rs[3], a.w), fmul(Rs[4], b.x), fmul(Rs[5], b.y));
-  const float nsz = sum3(fmul(Rs[6], a.w), fmul(Rs[7], b.x), fmul(Rs[8], b.y));
-  const float ptx = fadd(sum3(fmul(Rt[0], b.z), fmul(Rt[1], b.w), fmul(Rt[2], c.x)), tt[0]);
-  const float pty = fadd(sum3(fmul(Rt[3], b.z), fmul(Rt[4], b.w), fmul(Rt[5], c.x)), tt[1]);
-  const float ptz = fadd(sum3(fmul(Rt[6], b.z), fmul(Rt[7], b.w), fmul(Rt[8], c.x)), tt[2]);
-  const float ntx = sum3(fmul(Rt[0], c.y), fmul(Rt[1], c.z), fmul(Rt[2], c.w));
-  const float nty = sum3(fmul(Rt[3], c.y), fmul(Rt[4], c.z), fmul(Rt[5], c.w));
-  const float ntz = sum3(fmul(Rt[6], c.y), fmul(Rt[7], c.z), fmul(Rt[8], c.w));
+  const RecordFields f = record_fields(a, b, c);
+  const float psx = fadd(sum3(fmul(Rs[0], f.psx), fmul(Rs[1], f.psy), fmul(Rs[2], f.psz)), ts[0]);
+  const float psy = fadd(sum3(fmul(Rs[3], f.psx), fmul(Rs[4], f.psy), fmul(Rs[5], f.psz)), ts[1]);
+  const float psz = fadd(sum3(fmul(Rs[6], f.psx), fmul(Rs[7], f.psy), fmul(Rs[8], f.psz)), ts[2]);
+  const float nsx = sum3(fmul(Rs[0], f.nsx), fmul(Rs[1], f.nsy), fmul(Rs[2], f.nsz));
+  const float nsy = sum3(fmul(Rs[3], f.nsx), fmul(Rs[4], f.nsy), fmul(Rs[5], f.nsz));
+  const float nsz = sum3(fmul(Rs[6], f.nsx), fmul(Rs[7], f.nsy), fmul(Rs[8], f.nsz));
+  const float ptx = fadd(sum3(fmul(Rt[0], f.ptx), fmul(Rt[1], f.pty), fmul(Rt[2], f.ptz)), tt[0]);
+  const float pty = fadd(sum3(fmul(Rt[3], f.ptx), fmul(Rt[4], f.pty), fmul(Rt[5], f.ptz)), tt[1]);
+  const float ptz = fadd(sum3(fmul(Rt[6], f.ptx), fmul(Rt[7], f.pty), fmul(Rt[8], f.ptz)), tt[2]);
+  const float ntx = sum3(fmul(Rt[0], f.ntx), fmul(Rt[1], f.nty), fmul(Rt[2], f.ntz));
+  const float nty = sum3(fmul(Rt[3], f.ntx), fmul(Rt[4], f.nty), fmul(Rt[5], f.ntz));
+  const float ntz = sum3(fmul(Rt[6], f.ntx), fmul(Rt[7], f.nty), fmul(Rt[8], f.ntz));
   const float r1 = dot3(nsx, nsy, nsz, fsub(ptx, psx), fsub(pty, psy), fsub(ptz, psz));
   const float r2 = dot3(ntx, nty, ntz, fsub(psx, ptx), fsub(psy, pty), fsub(psz, ptz));
   *cost += (double)fmul(r1, r1);
   *cost += (double)fmul(r2, r2);
+}
+
+// ---- the cost of a record with packed fp32 (sm_100 FFMA2: one instruction, two IEEE-rn results) ----------------------------------
+// Lane 0 carries the source side of a quantity, lane 1 the target side: (ps_k, pt_k) = (Rs, Rt)(row k) . (p_s0, p_t0) + (ts_k, tt_k),
+// (ns_k, nt_k) likewise; then d = pt - ps (scalar), (r1, -r2) = (ns, nt) . d — the reference's r2 = nt . (ps - pt) is exactly the negative,
+// products and round-to-nearest sums being sign-symmetric — and (r1^2, r2^2). Every lane performs the operations of cost_record in
+// cost_record's order, each rounded once, so the two functions return the same bits; the instruction count per record and trial
+// drops from ~96 to ~46, which is what bounds a pass that evaluates four LM tries (ncu r02D: 76 % issue-active, 63 % FMA pipe).
+// ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even under -fmad=false, so products and sums are written as FMAs that cannot be
+// contracted any further: a * b = fma(a, b, -0), a + b = fma(a, 1, b), with 1 and -0 passed at run time so that they are not folded back.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+struct PackedOps {
+  f32x2 one, nzero;
+  __device__ __forceinline__ f32x2 mul(f32x2 a, f32x2 b) const { return fma2(a, b, nzero); }
+  __device__ __forceinline__ f32x2 add(f32x2 a, f32x2 b) const { return fma2(a, one, b); }
+  __device__ __forceinline__ f32x2 sum3(f32x2 a, f32x2 b, f32x2 c) const { return add(a, add(b, c)); }
+};
+// P: 12 pairs of one trial — (Rs[k], Rt[k]) for k = 0..8, then (ts[k], tt[k]) for k = 0..2.
+__device__ __forceinline__ void cost_record_packed(const float4 a, const float4 b, const float4 c, const f32x2 P[12], const PackedOps& K, double* cost) {
+  const f32x2 x0 = pk2(a.x, a.y), x1 = pk2(a.z, a.w), x2 = pk2(b.x, b.y);      // (ps0, pt0) by component: adjacent in the record
+  const f32x2 n0 = pk2(b.z, b.w), n1 = pk2(c.x, c.y), n2 = pk2(c.z, c.w);      // (ns0, nt0)
+  f32x2 p[3], n[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    p[r] = K.add(K.sum3(K.mul(P[3 * r], x0), K.mul(P[3 * r + 1], x1), K.mul(P[3 * r + 2], x2)), P[9 + r]);
+    n[r] = K.sum3(K.mul(P[3 * r], n0), K.mul(P[3 * r + 1], n1), K.mul(P[3 * r + 2], n2));
+  }
+  float d[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) { float ps, pt; upk2(p[r], ps, pt); d[r] = fsub(pt, ps); }
+  const f32x2 rr = K.sum3(K.mul(n[0], pk2(d[0], d[0])), K.mul(n[1], pk2(d[1], d[1])), K.mul(n[2], pk2(d[2], d[2])));
+  float q1, q2;
+  upk2(K.mul(rr, rr), q1, q2);
+  *cost += (double)q1;
+  *cost += (double)q2;
 }
 
 // Block-wide fixed-tree reduction of NV doubles per thread; result valid in threads [0,NV) of the block.
@@ -958,13 +1032,17 @@ __global__ void __launch_bounds__(kAccThreads, 2)
 k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, const float4* __restrict__ rc,
                  const Segment* __restrict__ segs, int nseg, const CloudPose* __restrict__ poses /* [1 + NX][nclouds] */, int nclouds,
                  unsigned long long total, unsigned long long per_cta, double* __restrict__ partials /* [nseg][gridDim.x][kAccVals] */,
-                 double* __restrict__ xpartials /* [nseg][gridDim.x][kMaxExtraTrials] */) {
+                 double* __restrict__ xpartials /* [nseg][gridDim.x][kMaxExtraTrials] */, float one, float nzero /* 1.0f, -0.0f */) {
   constexpr int NV = WITH_H ? kAccVals : 1;
   constexpr int NXS = NX > 0 ? NX : 1;
+  constexpr int kFirstPacked = WITH_H ? 1 : 0;                   // trial 0 goes through the packed cost path unless it carries H
+  constexpr bool kAnyPacked = NX > 0 || !WITH_H;
   extern __shared__ __align__(128) unsigned char tile_smem[];
   __shared__ double red[kAccThreads / 32][NV];
   __shared__ double xred[kAccThreads / 32][NXS];
-  __shared__ __align__(16) float xpose[NXS][24];                 // per extra trial: source pose (R, t), target pose (R, t)
+  // per trial (0 = the pass's own state, 1.. = the speculative ones): the 12 (source, target) pairs of cost_record_packed
+  __shared__ __align__(16) float ppose[1 + NXS][24];
+  const PackedOps K = {pk2(one, one), pk2(nzero, nzero)};
   __shared__ __align__(8) unsigned long long full_bar[kTmaStages], empty_bar[kTmaStages];
   const unsigned long long r_begin = (unsigned long long)blockIdx.x * per_cta;
   const unsigned long long r_end = min(total, r_begin + per_cta);
@@ -1008,12 +1086,12 @@ k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, c
     double xacc[NXS];
 #pragma unroll
     for (int j = 0; j < NXS; ++j) xacc[j] = 0.0;
-    if (NX > 0) {   // (the reductions at the end of the previous segment separate its readers from this write)
-      if ((int)threadIdx.x < NX * 24) {
+    if (kAnyPacked) {   // (the reductions at the end of the previous segment separate its readers from this write)
+      if ((int)threadIdx.x < (1 + NX) * 24 && (int)threadIdx.x >= kFirstPacked * 24) {
         const int j = threadIdx.x / 24, w = threadIdx.x % 24;
-        const CloudPose* P = poses + (size_t)(1 + j) * nclouds + (w < 12 ? sg.src : sg.tgt);
-        const int q = w % 12;
-        xpose[j][w] = q < 9 ? __ldg(&P->R[q]) : __ldg(&P->t[q - 9]);
+        const CloudPose* P = poses + (size_t)j * nclouds + ((w & 1) ? sg.tgt : sg.src);
+        const int q = w >> 1;
+        ppose[j][w] = q < 9 ? __ldg(&P->R[q]) : __ldg(&P->t[q - 9]);
       }
       __syncthreads();
     }
@@ -1028,17 +1106,20 @@ k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, c
       if (m1) { a1 = st[kAccThreads + threadIdx.x]; b1 = st[kTmaTile + kAccThreads + threadIdx.x]; c1 = st[2 * kTmaTile + kAccThreads + threadIdx.x]; }
       __syncwarp();
       if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[s]);     // this warp's values are in registers: one arrival per warp
-      if (m0) { if (WITH_H) accumulate_record(a0, b0, c0, Rs, ts, Rt, tt, acc); else cost_record(a0, b0, c0, Rs, ts, Rt, tt, &acc[0]); }
-      if (m1) { if (WITH_H) accumulate_record(a1, b1, c1, Rs, ts, Rt, tt, acc); else cost_record(a1, b1, c1, Rs, ts, Rt, tt, &acc[0]); }
-      if (NX > 0) {
+      if (WITH_H) {
+        if (m0) accumulate_record(a0, b0, c0, Rs, ts, Rt, tt, acc);
+        if (m1) accumulate_record(a1, b1, c1, Rs, ts, Rt, tt, acc);
+      }
+      if (kAnyPacked) {
 #pragma unroll
-        for (int j = 0; j < NX; ++j) {
-          float P[24];
-          const float4* xp = reinterpret_cast<const float4*>(xpose[j]);
+        for (int j = kFirstPacked; j <= NX; ++j) {
+          f32x2 P[12];
+          const ulonglong2* pp = reinterpret_cast<const ulonglong2*>(ppose[j]);
 #pragma unroll
-          for (int q = 0; q < 6; ++q) { const float4 v = xp[q]; P[4 * q] = v.x; P[4 * q + 1] = v.y; P[4 * q + 2] = v.z; P[4 * q + 3] = v.w; }
-          if (m0) cost_record(a0, b0, c0, P, P + 9, P + 12, P + 21, &xacc[j]);
-          if (m1) cost_record(a1, b1, c1, P, P + 9, P + 12, P + 21, &xacc[j]);
+          for (int q = 0; q < 6; ++q) { const ulonglong2 v = pp[q]; P[2 * q] = v.x; P[2 * q + 1] = v.y; }
+          double* sum = j == 0 ? &acc[0] : &xacc[j > 0 ? j - 1 : 0];
+          if (m0) cost_record_packed(a0, b0, c0, P, K, sum);
+          if (m1) cost_record_packed(a1, b1, c1, P, K, sum);
         }
       }
     }

@@ -136,6 +136,10 @@ class PointToPlaneICP:
     def SetGlobalTCloud(self, cloud_index, T):
         _lib.check(_lib.lib().b2_icp_set_pose(self._h, cloud_index, _f(_colmajor(T))))
 
+    def set_option(self, name, value):
+        """Scheduling switches for A/B measurements ("pack_overlap", "lpt_order"); results never depend on them."""
+        _lib.check(_lib.lib().b2_icp_set_option(self._h, name.encode(), int(value)))
+
     def stats(self):
         s = _lib.IcpStats()
         _lib.check(_lib.lib().b2_icp_last_stats(self._h, C.byref(s)))

@@ -116,6 +116,8 @@ typedef struct b2_icp_stats {
   uint64_t search_work[5];      /* B2_K3_WORK=1 only: candidates tested, level-1 box tests, level-2 box tests, cells scanned, queue items */
   int32_t searches_ahead;       /* pair-directions of this outer iteration whose search had been done behind the uploads (search_ahead);
                                    they are not in search_launches / ms_search / search_algorithmic_bytes */
+  int32_t packs_overlapped;     /* correspondence sets of this outer iteration that were packed while later sets were still being
+                                   searched (their time is inside ms_search; ms_pack is what remained after the last search) */
 } b2_icp_stats;
 
 void b2_icp_default_config(b2_icp_config* cfg);
@@ -141,6 +143,10 @@ int b2_icp_run(b2_icp* h, float max_correspondence_distance, int initial_iterati
 int b2_icp_get_pose(b2_icp* h, int cloud_id, float global_T_cloud[16]);
 /* Not in the reference API: overwrite a pose (parity tests feed both implementations identical poses). */
 int b2_icp_set_pose(b2_icp* h, int cloud_id, const float global_T_cloud[16]);
+
+/* Not in the reference API: scheduling switches for A/B measurements (results never depend on them). Names: "pack_overlap" (1: sets are
+   packed while later sets are searched; 0: after all searches), "lpt_order" (1: K3 tiles issued longest-first). */
+int b2_icp_set_option(b2_icp* h, const char* name, int value);
 
 /* Introspection for parity dumps (state of the LAST outer iteration). */
 int b2_icp_last_stats(b2_icp* h, b2_icp_stats* out);

@@ -1,6 +1,7 @@
 """Parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
 Bar: correspondence lists bit-exact; normal equations and poses within 1e-5 relative Frobenius."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -236,3 +237,42 @@ def test_lm_try_sequences_on_several_scenes(b2, oracle, room3):
     _tries_equal_one_iteration(b2, oracle, [(pts, nrm), (pts, nrm)], pp, 1.5)
     pts, nrm, pp = rti.identical_cloud_alignment_inputs()
     _tries_equal_one_iteration(b2, oracle, [(pts, nrm)] * 6, pp[:6], float(np.float32(0.15) * np.float32(math.sqrt(3))))
+
+
+def test_packed_fp32_cost_path_returns_the_bits_of_the_scalar_one():
+    """K5 evaluates the LM tries' costs with packed fp32 (FFMA2, two IEEE-rn lanes per instruction) on records staged by the bulk-copy
+    engine; B2_K5=ldg runs the register-staged kernel with the scalar arithmetic and one try per pass. Costs, accept / reject sequence
+    and poses must agree bit for bit over a whole alignment (each process reads the switch once, hence the subprocesses)."""
+    import json
+    import subprocess
+    import sys
+    code = r'''
+import json, sys, numpy as np
+sys.path.insert(0, %r)
+import dataset_pipeline_b200 as b2
+from dataset_pipeline_b200 import synth
+clouds, poses, _ = synth.room_scans(4, 300, 200)
+g = b2.PointToPlaneICP()
+for (xyz, nrm), T in zip(clouds, poses):
+    g.AddPointCloud(xyz, nrm, T)
+out = []
+for it in range(6):
+    g.Run(0.03, it, 1, 1e-10, False)
+    st = g.stats()
+    out.append({"first": float(st["first_cost"]).hex(), "last": float(st["last_cost"]).hex(), "tries": [int(v) for v in g.tries()],
+                "lambda": float(st["final_lambda"]).hex(), "n": int(st["num_correspondences"]),
+                "poses": [g.GetResultGlobalTCloud(i).astype(np.float32).tobytes().hex() for i in range(4)]})
+print("RESULT " + json.dumps(out))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runs = []
+    for mode in (None, "ldg"):
+        env = dict(os.environ)
+        env.pop("B2_K5", None)
+        if mode:
+            env["B2_K5"] = mode
+        p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1]
+        runs.append(json.loads(line[len("RESULT "):]))
+    assert len(runs[0]) == 6 and sum(len(r["tries"]) for r in runs[0]) > 6
+    assert runs[0] == runs[1]

@@ -275,3 +275,45 @@ def test_searches_done_behind_the_uploads_are_the_same_searches(b2, oracle):
     other_ahead = _run_handle(b2, clouds, poses, 0.012, index_distance_hint=d)
     assert other_ahead[0][0]["searches_ahead"] == 0 and other_ahead[0][0]["search_launches"] == 12
     _same_iterations(other_off, other_ahead)
+
+
+def test_sets_packed_behind_the_searches_and_the_overflow_fallback(b2, oracle, monkeypatch):
+    """K4 overlapped with K3 (optional, B2_PACK=overlap): sets are packed on their own stream at device-side running offsets while later sets are searched. Same
+    records in the same places as the serial pack (costs, LM decisions, poses bit for bit, lists against the oracle), and when a
+    set does not fit the record arrays of the previous iteration the whole iteration is packed the serial way."""
+    from dataset_pipeline_b200 import synth
+    clouds, poses, _ = synth.room_scans(3, 400, 300)
+    radii = [0.01, 0.01, 0.05, 0.05]
+
+    def run(mode):
+        if mode is None:
+            monkeypatch.delenv("B2_PACK", raising=False)
+        else:
+            monkeypatch.setenv("B2_PACK", mode)
+        g = b2.PointToPlaneICP(keep_correspondences=True)
+        for (xyz, nrm), T in zip(clouds, poses):
+            g.AddPointCloud(xyz, nrm, T)
+        out = []
+        for it, d in enumerate(radii):
+            for i in range(3):
+                g.SetGlobalTCloud(i, poses[i])          # every iteration from the same poses: the same sets every time
+            g.Run(d, it, 1, 1e-10, False)
+            out.append((g.stats(), g.pairs(), [g.GetResultGlobalTCloud(i) for i in range(3)], g.tries()))
+        g.close()
+        return out
+
+    serial, overlapped, nosize = run(None), run("overlap"), run("overlap_nosize")
+    assert [o[0]["packs_overlapped"] for o in serial] == [0, 0, 0, 0]
+    assert [o[0]["packs_overlapped"] for o in overlapped] == [6, 6, 6, 6]       # record arrays sized for the worst case up front
+    # without the up-front sizing: first iteration serial (no arrays yet), second overlapped, third overflows (five times the
+    # radius, several times the matches) and falls back, fourth overlapped again
+    assert [o[0]["packs_overlapped"] for o in nosize] == [0, 6, 0, 6]
+    assert nosize[2][0]["num_correspondences"] > 1.2 * nosize[1][0]["num_correspondences"]
+    _same_iterations(serial, overlapped)
+    _same_iterations(serial, nosize)
+    o = oracle.PointToPlaneICP(use_kdtree=True)
+    for (xyz, nrm), T in zip(clouds, poses):
+        o.AddPointCloud(xyz, nrm, T)
+    o.Run(radii[0], 0, 1, 1e-10, False)
+    for (s, t, q1, m1, d1), (_, _, q2, m2, d2) in zip(overlapped[0][1], o.pairs()):
+        assert np.array_equal(q1, q2) and np.array_equal(m1, m2) and np.array_equal(d1, d2), "pair %d->%d" % (s, t)

@@ -12,6 +12,7 @@ import dataset_pipeline_b200 as b2
 B.ensure_scans(range(a.scans), 5000, 2000)
 poses, _ = B.scene_poses(8)
 g = b2.PointToPlaneICP(inner_max_iterations=1)
+g.set_option("pack_overlap", int(os.environ.get("K3_BENCH_PACK_OVERLAP", "0")))      # 0: ms_search is K3 alone
 for i in range(a.scans):
     xyz, nrm = B.load_scan(i, 5000, 2000)
     g.AddPointCloud(xyz, nrm, poses[i])

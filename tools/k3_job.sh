@@ -1,7 +1,5 @@
-for v in base minb8 minb7 tile128 inl32 inl128 coop128 coop1024; do
-  B2_LIB_PATH=$PWD/dataset_pipeline_b200/_build/variants/libeth3d_b200_$v.so timeout 120 python tools/k3_bench.py 2>/dev/null | tail -1
+# K3 A/B runs on one box: tools/k3_job.sh <variant> ...   (variants built by tools/k3_variants.sh; "default" = the in-tree library)
+for v in "$@"; do
+  if [ "$v" = default ]; then timeout 160 python tools/k3_bench.py 2>/dev/null | tail -1
+  else B2_LIB_PATH=$PWD/dataset_pipeline_b200/_build/variants/libeth3d_b200_$v.so timeout 160 python tools/k3_bench.py 2>/dev/null | tail -1; fi
 done
-B2_K3_ORDER=grid timeout 120 python tools/k3_bench.py 2>/dev/null | tail -1
-B2_K3_STREAMS=1 timeout 120 python tools/k3_bench.py 2>/dev/null | tail -1
-B2_K3_STREAMS=2 timeout 120 python tools/k3_bench.py 2>/dev/null | tail -1
-B2_K3_STREAMS=8 timeout 120 python tools/k3_bench.py 2>/dev/null | tail -1
