@@ -96,7 +96,11 @@ struct DevBuf {
     if (bytes <= cap) return B2_OK;
     if (p) dev_free(p);
     p = nullptr; cap = 0;
-    const size_t want = bytes + bytes / 8 + 256;   // slack so small growth does not re-allocate
+    size_t want = bytes + bytes / 8 + 256;         // slack so small growth does not re-allocate
+    // large buffers in 32 MB steps: a create -> run -> destroy cycle whose counts differ a little from the previous one's (record
+    // arrays follow the number of correspondences) then asks the pool for the sizes it has cached instead of for new physical memory
+    constexpr size_t kStep = (size_t)32 << 20;
+    if (want > kStep) want = (want + kStep - 1) / kStep * kStep;
     cudaError_t e = dev_alloc(&p, want);
     if (e != cudaSuccess) return set_error(B2_ERR_ALLOC, "device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
     cap = want;
