@@ -47,6 +47,8 @@ struct Cloud {
   DevBuf l_xyz, l_nrm, perm_inv;        // cell-sorted cloud-frame rows (float4), original index -> sorted position
   bool dense = false;                   // layout of the occupied-cell index (k_nn_tiles<., DENSE>)
   DevBuf rb, starts, table;             // DENSE: rank bitmap + cell starts; sparse: hash table of the occupied cells
+  DevBuf corner;                        // DENSE, lattices up to 2^29 corners: the corner map of the DUAL lookup (1 B per corner)
+  bool dual = false;
   int log2size = 0;
   unsigned int ncells = 0;
   // ---- per outer iteration ----
@@ -393,6 +395,7 @@ static int build_index(b2_icp* h, Cloud* c, float max_dist, double sigma, double
   // 7.5 MB for a 10 x 8 x 3 m room at 2 cm), hash table of the occupied cells beyond
   const double cells_total = (double)g.nx * (double)g.ny * (double)g.nz;
   c->dense = cells_total <= 2147483648.0;
+  c->dual = false;
   if (c->dense) {
     const size_t nwords = (size_t)(cells_total / 32.0) + 2;
     const unsigned int nblocks = div_up(nwords, kWordsPerBlock);
@@ -407,6 +410,15 @@ static int build_index(b2_icp* h, Cloud* c, float max_dist, double sigma, double
     k_cell_starts<<<div_up(n, 256), 256, 0, h->stream>>>(keys_out.b.as<unsigned long long>(), n, 3 * g.fbits, c->rb.as<uint2>(),
                                                          c->starts.as<unsigned int>(), c->ncells);
     h->launches += 5;
+    // corner map (30 MB for a 10 x 8 x 3 m room at 2 cm; skipped for lattices above 2^29 corners, the search then tests the bitmap)
+    const double corners = ((double)g.nx + 1.0) * ((double)g.ny + 1.0) * ((double)g.nz + 1.0);
+    static const bool dual_off = [] { const char* e = getenv("B2_K3_DUAL"); return e && e[0] == '0'; }();
+    c->dual = !dual_off && corners <= 536870912.0;
+    if (c->dual) {
+      B2_TRY(c->corner.ensure((size_t)corners));
+      k_corner_occupancy<<<div_up((size_t)corners, 256), 256, 0, h->stream>>>(c->rb.as<uint2>(), g.nx, g.ny, g.nz, c->corner.as<unsigned char>());
+      ++h->launches;
+    }
   } else {
     int lg = 4;
     while ((1ull << lg) < 2ull * c->ncells) ++lg;
@@ -441,6 +453,7 @@ static int search_grid(const Cloud* c, SearchGrid* sg) {
   sg->log2size = c->log2size;
   sg->one = 1.0f;
   sg->occ = nullptr;
+  sg->corner = (c->dense && c->dual) ? c->corner.as<unsigned char>() : nullptr;
   sg->rb = c->dense ? c->rb.as<uint2>() : nullptr;
   sg->starts = c->dense ? c->starts.as<unsigned int>() : nullptr;
   return B2_OK;
@@ -585,12 +598,13 @@ static int launch_search(b2_icp* h, Direction* d, Cloud* S, Cloud* T, float r2, 
     order = cc + 3 * (size_t)ntiles;
   }
   B2_CUDA(cudaMemsetAsync(d->tile_count.p, 0, (size_t)ntiles * 4, st));
-#define B2_LAUNCH_NN(STATS, DENSE)                                                                                                  \
-  k_nn_tiles<STATS, DENSE><<<ntiles, kTile, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(), T->box2.as<Aabb>(),  \
+#define B2_LAUNCH_NN(STATS, DENSE, DUAL)                                                                                            \
+  k_nn_tiles<STATS, DENSE, DUAL><<<ntiles, kTile, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(), T->box2.as<Aabb>(),  \
                                                      T->table.as<HashEntry>(), sg, r2, d->key.as<unsigned long long>(),                 \
                                                      d->tile_count.as<unsigned int>(), h->work_stats ? h->work_dev.as<unsigned long long>() : nullptr, order)
-  if (h->work_stats) { if (T->dense) B2_LAUNCH_NN(true, true); else B2_LAUNCH_NN(true, false); }
-  else { if (T->dense) B2_LAUNCH_NN(false, true); else B2_LAUNCH_NN(false, false); }
+  const bool dual = T->dense && T->dual;
+  if (h->work_stats) { if (dual) B2_LAUNCH_NN(true, true, true); else if (T->dense) B2_LAUNCH_NN(true, true, false); else B2_LAUNCH_NN(true, false, false); }
+  else { if (dual) B2_LAUNCH_NN(false, true, true); else if (T->dense) B2_LAUNCH_NN(false, true, false); else B2_LAUNCH_NN(false, false, false); }
 #undef B2_LAUNCH_NN
   if (timed) {
     B2_CUDA(cudaEventRecord(n1, st));
@@ -1168,7 +1182,7 @@ int b2_icp_destroy(b2_icp* h) {
   auto free_cloud = [](Cloud* c) {
     if (!c) return;
     if (c->ready_ev) { cudaEventSynchronize(c->ready_ev); cudaEventDestroy(c->ready_ev); c->ready_ev = nullptr; }
-    for (DevBuf* b : {&c->local_xyz, &c->local_nrm, &c->l_xyz, &c->l_nrm, &c->perm_inv, &c->rb, &c->starts, &c->s_xyz, &c->s_nrm, &c->table, &c->box1, &c->box2}) b->release();
+    for (DevBuf* b : {&c->local_xyz, &c->local_nrm, &c->l_xyz, &c->l_nrm, &c->perm_inv, &c->rb, &c->starts, &c->corner, &c->s_xyz, &c->s_nrm, &c->table, &c->box1, &c->box2}) b->release();
   };
   for (auto& c : h->movable) free_cloud(c.get());
   free_cloud(h->fixed.get());

@@ -277,6 +277,7 @@ struct SearchGrid {              // a target cloud's static grid + this iteratio
   int log2size;
   float one;                     // 1.0f at run time (see B2_NN_KEY)
   const unsigned int* occ;       // sparse layout: unused (nullptr: every neighbour is probed in the hash table)
+  const unsigned char* corner;   // DUAL: per lattice corner, the occupancy of its 8 adjacent cells (bit dx + 2 dy + 4 dz, d = 1: the cell on the upper side)
   const uint2* rb;               // DENSE layout: rank bitmap, {occupancy bits, occupied cells before this word} per 32 cells
   const unsigned int* starts;    // DENSE layout: first sorted point of every occupied cell, + the total
 };
@@ -493,7 +494,7 @@ struct __align__(128) WarpTile {
   unsigned long long bar;
 };
 
-template <bool STATS, bool DENSE>
+template <bool STATS, bool DENSE, bool DUAL>
 __global__ void __launch_bounds__(kTile, B2_K3_MINB) k_nn_tiles(const float4* __restrict__ src, size_t ns, const float4* __restrict__ tgt,
                                                     const Aabb* __restrict__ box1, const Aabb* __restrict__ box2,
                                                     const HashEntry* __restrict__ table, SearchGrid g, float r2,
@@ -536,7 +537,23 @@ __global__ void __launch_bounds__(kTile, B2_K3_MINB) k_nn_tiles(const float4* __
     const bool x1 = (unsigned int)(L.cx + ((upper & 1u) ? 1 : -1)) < (unsigned int)g.nx;
     const bool y1 = (unsigned int)(L.cy + ((upper & 2u) ? 1 : -1)) < (unsigned int)g.ny;
     const bool z1 = (unsigned int)(L.cz + ((upper & 4u) ? 1 : -1)) < (unsigned int)g.nz;
-    if (x0 && y0 && z0) {
+    // DUAL: the 2x2x2 block of cells a query can have matches in is the set of cells around ONE lattice corner — the corner of its cell
+    // on the side of the octant it lies in. One byte of the corner map says which of the eight are inside the grid and occupied; it
+    // replaces seven bitmap lookups (key, word load, bit test) and all range checks. Bit j of occ8, after the permutation: the cell
+    // reached from the query's own by stepping along the axes in j (bit 0 = its own cell).
+    unsigned int occ8 = 0u;
+    if (DUAL) {
+      const int kx = L.cx + (int)(upper & 1u), ky = L.cy + (int)((upper >> 1) & 1u), kz = L.cz + (int)((upper >> 2) & 1u);
+      if ((unsigned int)kx <= (unsigned int)g.nx && (unsigned int)ky <= (unsigned int)g.ny && (unsigned int)kz <= (unsigned int)g.nz) {
+        unsigned int m = __ldg(g.corner + ((size_t)kz * (size_t)(g.ny + 1) + (size_t)ky) * (size_t)(g.nx + 1) + (size_t)kx);
+        // the query's own cell is the corner's cell number (~upper & 7); bit j of the result = bit (j ^ own) of m
+        if (!(upper & 1u)) m = ((m & 0x55u) << 1) | ((m >> 1) & 0x55u);
+        if (!(upper & 2u)) m = ((m & 0x33u) << 2) | ((m >> 2) & 0x33u);
+        if (!(upper & 4u)) m = ((m & 0x0fu) << 4) | (m >> 4);
+        occ8 = m;
+      }
+    }
+    if (DUAL ? (occ8 & 1u) != 0u : (x0 && y0 && z0)) {
       unsigned int b, e;
       if (find_cell<DENSE>(g, table, base, &b, &e)) {
         if (e - b > kCoopCell) {
@@ -558,8 +575,9 @@ __global__ void __launch_bounds__(kTile, B2_K3_MINB) k_nn_tiles(const float4* __
     const float bd = key_d2(best);
 #pragma unroll
     for (int c = 1; c < 8; ++c) {
-      const bool valid = ((c & 1) ? x1 : x0) && ((c & 2) ? y1 : y0) && ((c & 4) ? z1 : z0);
       const float lb = fadd(fadd((c & 1) ? L.ex2 : 0.f, (c & 2) ? L.ey2 : 0.f), (c & 4) ? L.ez2 : 0.f);
+      if (DUAL) { if (((occ8 >> c) & 1u) && !(lb > bd)) todo |= 1u << c; continue; }
+      const bool valid = ((c & 1) ? x1 : x0) && ((c & 2) ? y1 : y0) && ((c & 4) ? z1 : z0);
       if (valid && !(lb > bd)) {
         const key_t key = base + ((c & 1) ? dxk : (key_t)0) + ((c & 2) ? dyk : (key_t)0) + ((c & 4) ? dzk : (key_t)0);
         bool occ = true;
@@ -676,6 +694,25 @@ __global__ void __launch_bounds__(256) k_mark_cells(const unsigned long long* __
   const unsigned long long key = keys[j] >> kFineBits;
   if (j != 0 && (keys[j - 1] >> kFineBits) == key) return;
   atomicOr(&rb[key >> 5].x, 1u << (unsigned int)(key & 31ull));
+}
+// The corner map of the DUAL lookup: thread per lattice corner (kx, ky, kz) in [0, nx] x [0, ny] x [0, nz]; cell (kx-1+dx, ky-1+dy, kz-1+dz).
+__global__ void __launch_bounds__(256) k_corner_occupancy(const uint2* __restrict__ rb, int nx, int ny, int nz, unsigned char* __restrict__ corner) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)(nx + 1) * (size_t)(ny + 1) * (size_t)(nz + 1);
+  if (i >= total) return;
+  const int kx = (int)(i % (size_t)(nx + 1));
+  const size_t t = i / (size_t)(nx + 1);
+  const int ky = (int)(t % (size_t)(ny + 1)), kz = (int)(t / (size_t)(ny + 1));
+  unsigned int m = 0u;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    const int x = kx - 1 + (d & 1), y = ky - 1 + ((d >> 1) & 1), z = kz - 1 + (d >> 2);
+    if ((unsigned int)x < (unsigned int)nx && (unsigned int)y < (unsigned int)ny && (unsigned int)z < (unsigned int)nz) {
+      const long long key = ((long long)z * ny + y) * nx + x;
+      m |= ((__ldg(&rb[key >> 5].x) >> (unsigned int)(key & 31ll)) & 1u) << d;
+    }
+  }
+  corner[i] = (unsigned char)m;
 }
 static constexpr unsigned int kWordsPerBlock = 2048;   // bitmap words per block of the two-level prefix
 __global__ void __launch_bounds__(256) k_word_counts(const uint2* __restrict__ rb, size_t nwords, unsigned int* __restrict__ block_sum) {
