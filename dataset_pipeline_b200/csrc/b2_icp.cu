@@ -598,10 +598,14 @@ static int launch_search(b2_icp* h, Direction* d, Cloud* S, Cloud* T, float r2, 
     order = cc + 3 * (size_t)ntiles;
   }
   B2_CUDA(cudaMemsetAsync(d->tile_count.p, 0, (size_t)ntiles * 4, st));
+  // persistent CTAs (as many as are resident at once) unless B2_K3_PERSIST=0; the longest-first order is what balances them
+  // (B2_K3_PERSIST=n: 1/n of the resident CTA slots per launch, so that n launches of different streams share the GPU)
+  static const int persist = [] { const char* e = getenv("B2_K3_PERSIST"); return e ? std::max(0, atoi(e)) : 1; }();
+  const unsigned int nn_grid = persist > 0 && order ? std::min(ntiles, (unsigned int)std::max(1, h->sms * B2_K3_MINB / persist)) : ntiles;
 #define B2_LAUNCH_NN(STATS, DENSE, DUAL)                                                                                            \
-  k_nn_tiles<STATS, DENSE, DUAL><<<ntiles, kTile, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(), T->box2.as<Aabb>(),  \
+  k_nn_tiles<STATS, DENSE, DUAL><<<nn_grid, kTile, 0, st>>>(S->s_xyz.as<float4>(), ns, T->s_xyz.as<float4>(), T->box1.as<Aabb>(), T->box2.as<Aabb>(),  \
                                                      T->table.as<HashEntry>(), sg, r2, d->key.as<unsigned long long>(),                 \
-                                                     d->tile_count.as<unsigned int>(), h->work_stats ? h->work_dev.as<unsigned long long>() : nullptr, order)
+                                                     d->tile_count.as<unsigned int>(), h->work_stats ? h->work_dev.as<unsigned long long>() : nullptr, order, ntiles)
   const bool dual = T->dense && T->dual;
   if (h->work_stats) { if (dual) B2_LAUNCH_NN(true, true, true); else if (T->dense) B2_LAUNCH_NN(true, true, false); else B2_LAUNCH_NN(true, false, false); }
   else { if (dual) B2_LAUNCH_NN(false, true, true); else if (T->dense) B2_LAUNCH_NN(false, true, false); else B2_LAUNCH_NN(false, false, false); }

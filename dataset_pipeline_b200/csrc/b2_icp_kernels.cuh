@@ -485,13 +485,13 @@ __global__ void __launch_bounds__(256) k_tile_cost(const float4* __restrict__ sr
 // Per-warp working set in shared memory (a CTA is kTile / 32 independent warps; nothing in K3 synchronises the CTA).
 template <typename key_t>
 struct __align__(128) WarpTile {
-  float4 q[32];                            // the warp's 32 query rows (its own bulk copy)
+  float4 q[2][32];                         // the warp's 32 query rows (its own bulk copy), double-buffered across the tiles of a persistent CTA
   unsigned long long best[32];             // per query: best (d2, index) key
   key_t item_cell[32 * 7];                 // work queue of (query, neighbour cell): DENSE: the cell's rank; sparse: the cell's key
   uint2 dense_range[kDenseCap];            // dense-cell queue: candidate range [x, y) ...
   unsigned char item_q[32 * 7];
   unsigned char dense_q[kDenseCap];        // ... and the query it belongs to
-  unsigned long long bar;
+  unsigned long long bar[2];
 };
 
 template <bool STATS, bool DENSE, bool DUAL>
@@ -499,34 +499,54 @@ __global__ void __launch_bounds__(kTile, B2_K3_MINB) k_nn_tiles(const float4* __
                                                     const Aabb* __restrict__ box1, const Aabb* __restrict__ box2,
                                                     const HashEntry* __restrict__ table, SearchGrid g, float r2,
                                                     unsigned long long* __restrict__ out_key, unsigned int* __restrict__ tile_count,
-                                                    unsigned long long* __restrict__ work, const unsigned int* __restrict__ order) {
+                                                    unsigned long long* __restrict__ work, const unsigned int* __restrict__ order,
+                                                    unsigned int ntiles) {
   typedef typename std::conditional<DENSE, int, long long>::type key_t;   // cell key: 32 bits suffice for a dense grid
   __shared__ WarpTile<key_t> s_warp[kTile / 32];
   const unsigned int lane = threadIdx.x & 31u;
   WarpTile<key_t>& W = s_warp[threadIdx.x >> 5];
-  const unsigned int tile = order ? order[blockIdx.x] : blockIdx.x;
-  const size_t j0 = (size_t)tile * kTile + (threadIdx.x & ~31u);          // this warp's first query
-  if (j0 >= ns) return;                                                   // (whole warp)
-  const unsigned int cnt = (unsigned int)min((size_t)32, ns - j0);
+  // Persistent CTAs: CTA b works through tiles order[b], order[b + grid], ... (with the longest-first order every CTA receives an equal
+  // share of long and short tiles, so all of them finish together instead of leaving the launch's tail to a few long tiles), and each
+  // warp has the query rows of its NEXT tile copied into the other half of its buffer while it works on the current one. With
+  // grid == ntiles this is the one-tile-per-CTA kernel.
+  const unsigned int wofs = threadIdx.x & ~31u;
   if (lane == 0) {
-    mbar_init(&W.bar, 1);
+    mbar_init(&W.bar[0], 1); mbar_init(&W.bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(&W.bar, cnt * 16u);
-    bulk_g2s(W.q, src + j0, cnt * 16u, &W.bar);
   }
   __syncwarp();
-  mbar_wait(&W.bar, 0);
+  auto stage = [&](unsigned int t, unsigned int buf) {                    // lane 0: start the copy of this warp's rows of tile number t
+    const size_t j = (size_t)(order ? order[t] : t) * kTile + wofs;
+    if (j < ns) {
+      const unsigned int c = (unsigned int)min((size_t)32, ns - j);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // the rows read from this half are overwritten by the copy engine
+      mbar_expect_tx(&W.bar[buf], c * 16u);
+      bulk_g2s(W.q[buf], src + j, c * 16u, &W.bar[buf]);
+    }
+  };
+  if (lane == 0 && blockIdx.x < ntiles) stage(blockIdx.x, 0u);
+  const unsigned long long init = (unsigned long long)__float_as_uint(r2) << 32;
+  SearchWork wk = {0u, 0u, 0u, 0u};
+  unsigned int total_items = 0u, phases = 0u, it = 0u;
+  for (unsigned int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+  const unsigned int buf = it & 1u;
+  const unsigned int tile = order ? order[t] : t;
+  const size_t j0 = (size_t)tile * kTile + wofs;                          // this warp's first query
+  if (lane == 0 && t + gridDim.x < ntiles) stage(t + gridDim.x, buf ^ 1u);
+  if (j0 >= ns) continue;                                                 // (whole warp; nothing was staged for it)
+  const unsigned int cnt = (unsigned int)min((size_t)32, ns - j0);
+  mbar_wait(&W.bar[buf], (phases >> buf) & 1u);
+  phases ^= 1u << buf;
+  const float4* __restrict__ Wq = W.q[buf];
 
   // ---- A: own cell per thread ----
-  const unsigned long long init = (unsigned long long)__float_as_uint(r2) << 32;
   unsigned long long best = init;
   key_t base = 0, dxk = 0, dyk = 0, dzk = 0;
   unsigned int todo = 0u;
   bool own_dense = false;
   uint2 own_range = make_uint2(0u, 0u);
-  SearchWork wk = {0u, 0u, 0u, 0u};
   if (lane < cnt) {
-    const float4 q = W.q[lane];
+    const float4 q = Wq[lane];
     const CellLookup L = lookup_cell(g, q);
     const unsigned int upper = L.upper;
     base = (key_t)((key_t)L.cz * (key_t)g.sz + (key_t)L.cy * (key_t)g.sy + (key_t)L.cx);
@@ -630,7 +650,7 @@ __global__ void __launch_bounds__(kTile, B2_K3_MINB) k_nn_tiles(const float4* __
       if (found) {
         if (e - b > kCoopCell) { dense_item = true; range = make_uint2(b, e); }
         else {
-          const float4 q = W.q[ql];
+          const float4 q = Wq[ql];
           const unsigned long long seen = W.best[ql];     // possibly lowered by another item of this query already: a tighter start
           unsigned long long bk = seen;
           scan_cell(tgt, box1, box2, b, e, q, g.one, bk, wk);
@@ -643,7 +663,7 @@ __global__ void __launch_bounds__(kTile, B2_K3_MINB) k_nn_tiles(const float4* __
       const unsigned int slot = ndense + __popc(dm & ((1u << lane) - 1u));
       if (slot < kDenseCap) { W.dense_range[slot] = range; W.dense_q[slot] = (unsigned char)ql; }
       else {                                             // queue full: this lane walks the cell itself
-        const float4 q = W.q[ql];
+        const float4 q = Wq[ql];
         const unsigned long long seen = W.best[ql];
         unsigned long long bk = seen;
         scan_cell(tgt, box1, box2, range.x, range.y, q, g.one, bk, wk);
@@ -658,7 +678,7 @@ __global__ void __launch_bounds__(kTile, B2_K3_MINB) k_nn_tiles(const float4* __
   for (unsigned int i = 0; i < ndense; ++i) {
     const uint2 r = W.dense_range[i];
     const unsigned int ql = W.dense_q[i];
-    const float4 q = W.q[ql];
+    const float4 q = Wq[ql];
     const unsigned long long seen = W.best[ql];
     const unsigned long long bk = scan_cell_warp(tgt, box1, box2, r.x, r.y, q, g.one, seen, lane, wk);
     if (lane == 0u) { if (bk < seen) W.best[ql] = bk; ++wk.cells; }
@@ -674,6 +694,9 @@ __global__ void __launch_bounds__(kTile, B2_K3_MINB) k_nn_tiles(const float4* __
   }
   const unsigned int mm = __ballot_sync(0xffffffffu, matched);
   if (lane == 0u && mm) atomicAdd(tile_count + tile, (unsigned int)__popc(mm));   // (zeroed by the host before the launch)
+  if (STATS) total_items += nitems;
+  __syncwarp();                                                           // the queues and W.best are reused by the next tile
+  }
   if (STATS) {
     // per-launch totals: candidates tested, level-1 / level-2 box tests, cells scanned, queue items
     unsigned int v[4] = {wk.points, wk.box1, wk.box2, wk.cells};
@@ -683,7 +706,7 @@ __global__ void __launch_bounds__(kTile, B2_K3_MINB) k_nn_tiles(const float4* __
       for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
       if (lane == 0u && x) atomicAdd(work + k, (unsigned long long)x);
     }
-    if (lane == 0u && nitems) atomicAdd(work + 4, (unsigned long long)nitems);
+    if (lane == 0u && total_items) atomicAdd(work + 4, (unsigned long long)total_items);
   }
 }
 

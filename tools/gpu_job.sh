@@ -29,6 +29,7 @@ while [ $# -gt 0 ]; do
     k3_variants) V=$1; shift; bash tools/k3_job.sh $(echo $V | tr , ' ') > ${O}_k3_variants.txt 2>&1; stamp $S $?; cat ${O}_k3_variants.txt ;;
     dmin_parity) B2_LIB_PATH=$PWD/dataset_pipeline_b200/_build/variants/libeth3d_b200_dmin.so timeout 600 python -m pytest tests/test_gpu_icp_dense.py tests/test_gpu_icp.py -x -q -m gpu > ${O}_dmin_parity.log 2>&1; stamp $S $?; tail -3 ${O}_dmin_parity.log ;;
     k3_dual_ab) (timeout 200 python tools/k3_bench.py 2>/dev/null | tail -1; B2_K3_DUAL=0 timeout 200 python tools/k3_bench.py 2>/dev/null | tail -1) > ${O}_k3_dual_ab.txt; stamp $S $?; cat ${O}_k3_dual_ab.txt ;;
+    k3_persist_ab) (for v in 1 2 4 0; do B2_K3_PERSIST=$v timeout 200 python tools/k3_bench.py 2>/dev/null | tail -1; done; B2_K3_PERSIST=1 B2_K3_STREAMS=1 timeout 200 python tools/k3_bench.py 2>/dev/null | tail -1) > ${O}_k3_persist_ab.txt; stamp $S $?; cat ${O}_k3_persist_ab.txt ;;
     micro) ./dataset_pipeline_b200/_build/micro/ffma2_bench > ${O}_micro.txt 2>&1; stamp $S $?; cat ${O}_micro.txt ;;
     ncu_reg_launches) B2_BENCH_PROFILE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file ${O}_reg_launches.csv python bench_reg.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > ${O}_reg_launches.log 2>&1; stamp $S $? ;;
     ncu_reg_full) B2_BENCH_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none -k regex:'kr_jacobians|kr_accumulate_weighted|kr_residual_weights|kr_visibility|kr_raster_small|kr_mask_edges' -c 12 -f -o ${O}_reg python bench_reg.py --images 2 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > ${O}_ncu_reg.log 2>&1; stamp $S $?
