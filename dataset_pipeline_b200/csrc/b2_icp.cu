@@ -478,10 +478,10 @@ static int launch_accumulate_tma(b2_icp* h, int nseg, int nc) {
   // the > 48 KB dynamic shared memory opt-in is per device: tracked per handle (a handle is bound to one device)
   const unsigned int bit = 1u << ((WITH_H ? 4 : 0) + NX);
   if (!(h->tma_attr_mask & bit)) {
-    B2_CUDA(cudaFuncSetAttribute(k_accumulate_tma<WITH_H, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
+    B2_CUDA(cudaFuncSetAttribute(k_accumulate_tma<WITH_H, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes(WITH_H)));
     h->tma_attr_mask |= bit;
   }
-  k_accumulate_tma<WITH_H, NX><<<h->grid_acc, kAccThreads, kTmaSmemBytes, h->stream>>>(
+  k_accumulate_tma<WITH_H, NX><<<h->grid_acc, kAccThreads, tma_smem_bytes(WITH_H), h->stream>>>(
       h->rec_a.as<float4>(), h->rec_b.as<float4>(), h->rec_c.as<float4>(), h->segs_dev.as<Segment>(), nseg, h->poses_dev.as<CloudPose>(), nc,
       h->total_records, h->per_cta, h->partials.as<double>(), h->xpartials.as<double>(), 1.0f, -0.0f);
   return B2_OK;
@@ -959,7 +959,10 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   }
 
   // ---- streaming-pass geometry ----
-  h->grid_acc = h->sms * 2;
+  // record ranges (= CTAs of a pass; the partition fixes the summation order, so it is the same for every kind of pass): 6 per SM — three
+  // waves of the passes that carry the normal equations (2 CTAs of 128 registers per SM), two waves of the cost-only passes (3 per SM)
+  static const int ranges_per_sm = [] { const char* e = getenv("B2_K5_RANGES_PER_SM"); return e ? std::max(1, std::min(16, atoi(e))) : 6; }();
+  h->grid_acc = h->sms * ranges_per_sm;
   unsigned long long per = (total + h->grid_acc - 1) / (unsigned long long)h->grid_acc;
   per = std::max<unsigned long long>(kAccThreads, (per + kAccThreads - 1) / kAccThreads * kAccThreads);
   h->per_cta = per;

@@ -1074,7 +1074,10 @@ k_accumulate(const float4* __restrict__ ra, const float4* __restrict__ rb, const
 static constexpr int kMaxExtraTrials = 3;
 static constexpr int kTmaStages = 4;
 static constexpr int kTmaTile = 2 * kAccThreads;                   // records per tile: two per consumer thread
-static constexpr size_t kTmaSmemBytes = (size_t)kTmaStages * 3 * kTmaTile * 16;
+// Passes without the normal equations need a third of the registers (no 28 fp64 accumulators): with three stages (72 KB) instead of four
+// three of their CTAs fit an SM (24 warps instead of 16) — they are bound by fp32 latency / issue, not by bytes in flight.
+__host__ __device__ constexpr int tma_stages(bool with_h) { return with_h ? kTmaStages : 3; }
+__host__ __device__ constexpr size_t tma_smem_bytes(bool with_h) { return (size_t)tma_stages(with_h) * 3 * kTmaTile * 16; }
 
 // Walks the tile sequence of one CTA: tiles never straddle a segment ("correspondence set") boundary.
 struct TileCursor {
@@ -1088,13 +1091,14 @@ struct TileCursor {
 };
 
 template <bool WITH_H, int NX>
-__global__ void __launch_bounds__(kAccThreads, 2)
+__global__ void __launch_bounds__(kAccThreads, WITH_H ? 2 : 3)
 k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, const float4* __restrict__ rc,
                  const Segment* __restrict__ segs, int nseg, const CloudPose* __restrict__ poses /* [1 + NX][nclouds] */, int nclouds,
                  unsigned long long total, unsigned long long per_cta, double* __restrict__ partials /* [nseg][gridDim.x][kAccVals] */,
                  double* __restrict__ xpartials /* [nseg][gridDim.x][kMaxExtraTrials] */, float one, float nzero /* 1.0f, -0.0f */) {
   constexpr int NV = WITH_H ? kAccVals : 1;
   constexpr int NXS = NX > 0 ? NX : 1;
+  constexpr int kStages = tma_stages(WITH_H);
   constexpr int kFirstPacked = WITH_H ? 1 : 0;                   // trial 0 goes through the packed cost path unless it carries H
   constexpr bool kAnyPacked = NX > 0 || !WITH_H;
   extern __shared__ __align__(128) unsigned char tile_smem[];
@@ -1103,12 +1107,12 @@ k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, c
   // per trial (0 = the pass's own state, 1.. = the speculative ones): the 12 (source, target) pairs of cost_record_packed
   __shared__ __align__(16) float ppose[1 + NXS][24];
   const PackedOps K = {pk2(one, one), pk2(nzero, nzero)};
-  __shared__ __align__(8) unsigned long long full_bar[kTmaStages], empty_bar[kTmaStages];
+  __shared__ __align__(8) unsigned long long full_bar[kStages], empty_bar[kStages];
   const unsigned long long r_begin = (unsigned long long)blockIdx.x * per_cta;
   const unsigned long long r_end = min(total, r_begin + per_cta);
   if (r_begin >= r_end) return;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTmaStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kAccThreads / 32); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kAccThreads / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -1116,11 +1120,11 @@ k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, c
   while (lo < hi) { const int mid = (lo + hi) >> 1; if (segs[mid].end > r_begin) hi = mid; else lo = mid + 1; }
   float4* const sa = reinterpret_cast<float4*>(tile_smem);       // stage s: planes at sa + (3*s + p) * kTmaTile
 
-  // Thread 0 doubles as the producer: it keeps kTmaStages-1 tiles in flight ahead of the tile being consumed.
+  // Thread 0 doubles as the producer: it keeps kStages-1 tiles in flight ahead of the tile being consumed.
   TileCursor prod{r_begin, 0, r_end, lo}; unsigned int pit = 0;
   auto produce = [&]() {
-    const unsigned int s = pit % kTmaStages, cnt = prod.count();
-    if (pit >= (unsigned int)kTmaStages) mbar_wait(&empty_bar[s], ((pit / kTmaStages) - 1) & 1);
+    const unsigned int s = pit % kStages, cnt = prod.count();
+    if (pit >= (unsigned int)kStages) mbar_wait(&empty_bar[s], ((pit / kStages) - 1) & 1);
     mbar_expect_tx(&full_bar[s], 3u * cnt * 16u);
     bulk_g2s(sa + (3 * s + 0) * kTmaTile, ra + prod.r, cnt * 16u, &full_bar[s]);
     bulk_g2s(sa + (3 * s + 1) * kTmaTile, rb + prod.r, cnt * 16u, &full_bar[s]);
@@ -1129,7 +1133,7 @@ k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, c
   };
   if (threadIdx.x == 0) {
     prod.settle(segs);
-    for (int k = 0; k < kTmaStages - 1 && prod.valid(); ++k) produce();
+    for (int k = 0; k < kStages - 1 && prod.valid(); ++k) produce();
   }
 
   unsigned long long r0 = r_begin; int seg = lo; unsigned int it = 0;
@@ -1157,8 +1161,8 @@ k_accumulate_tma(const float4* __restrict__ ra, const float4* __restrict__ rb, c
     }
     for (unsigned long long r = r0; r < e; r += kTmaTile, ++it) {
       if (threadIdx.x == 0 && prod.valid()) produce();            // refill the stage released one tile ago
-      const unsigned int s = it % kTmaStages, cnt = (unsigned int)min((unsigned long long)kTmaTile, e - r);
-      mbar_wait(&full_bar[s], (it / kTmaStages) & 1);
+      const unsigned int s = it % kStages, cnt = (unsigned int)min((unsigned long long)kTmaTile, e - r);
+      mbar_wait(&full_bar[s], (it / kStages) & 1);
       float4 a0, b0, c0, a1, b1, c1;
       const bool m0 = threadIdx.x < cnt, m1 = threadIdx.x + kAccThreads < cnt;
       const float4* st = sa + (3 * s) * kTmaTile;
