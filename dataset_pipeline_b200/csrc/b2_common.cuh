@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <utility>
+#include <vector>
 #include <string>
 
 #include "../../include/eth3d_b200.h"
@@ -82,7 +84,9 @@ inline void dev_free(void* p) {
   cudaFreeAsync(p, cudaStreamPerThread);
 }
 // Returns the cached (unused) memory of every device's private pool to the driver.
+inline void pinned_cache_trim();
 inline void pool_trim_all() {
+  pinned_cache_trim();
   PoolTable& t = pool_table();
   std::lock_guard<std::mutex> lock(t.mu);
   for (int d = 0; d < 64; ++d)
@@ -110,19 +114,50 @@ struct DevBuf {
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Page-locked host buffers. cudaMallocHost / cudaFreeHost take 0.1 .. 10+ ms each (page locking, and they synchronise with the device);
+// a handle needs eight small ones, so a create -> run -> destroy cycle returns them to a process-wide free list instead (power-of-two
+// size classes from 4 KB; at most 64 cached blocks; pool_trim_all() / b2_trim() frees them).
+struct PinnedCache {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> free_list;
+};
+inline PinnedCache& pinned_cache() { static PinnedCache c; return c; }
+inline size_t pinned_class(size_t bytes) { size_t c = 4096; while (c < bytes) c <<= 1; return c; }
+inline void pinned_cache_trim() {
+  PinnedCache& c = pinned_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  for (auto& b : c.free_list) cudaFreeHost(b.first);
+  c.free_list.clear();
+}
 struct PinnedBuf {
   void* p = nullptr;
   size_t cap = 0;
   int ensure(size_t bytes) {
     if (bytes <= cap) return B2_OK;
-    if (p) cudaFreeHost(p);
-    p = nullptr; cap = 0;
-    cudaError_t e = cudaMallocHost(&p, bytes);
-    if (e != cudaSuccess) return set_error(B2_ERR_ALLOC, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
-    cap = bytes;
+    release();
+    const size_t want = pinned_class(bytes);
+    {
+      PinnedCache& c = pinned_cache();
+      std::lock_guard<std::mutex> lock(c.mu);
+      for (size_t i = 0; i < c.free_list.size(); ++i)
+        if (c.free_list[i].second == want) { p = c.free_list[i].first; cap = want; c.free_list.erase(c.free_list.begin() + i); return B2_OK; }
+    }
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) { p = nullptr; return set_error(B2_ERR_ALLOC, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e)); }
+    cap = want;
     return B2_OK;
   }
-  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  void release() {
+    if (!p) return;
+    PinnedCache& c = pinned_cache();
+    bool kept = false;
+    {
+      std::lock_guard<std::mutex> lock(c.mu);
+      if (c.free_list.size() < 64 && cap <= ((size_t)64 << 20)) { c.free_list.emplace_back(p, cap); kept = true; }
+    }
+    if (!kept) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+  }
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
