@@ -171,14 +171,16 @@ inline int select_device(int requested, int* out_dev, int* out_sms) {
   int dev = requested;
   if (dev < 0) { B2_CUDA(cudaGetDevice(&dev)); }
   if (dev >= count) return set_error(B2_ERR_ARG, "device %d out of range (%d devices)", dev, count);
-  cudaDeviceProp prop;
-  B2_CUDA(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10)
-    return set_error(B2_ERR_NO_DEVICE, "device %d (%s) is sm_%d%d; this library is built for sm_100a only", dev,
-                     prop.name, prop.major, prop.minor);
+  // (single attributes: cudaGetDeviceProperties fills ~100 fields and takes milliseconds, on every handle creation)
+  int major = 0, minor = 0, sms = 0;
+  B2_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  B2_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (major != 10)
+    return set_error(B2_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, major, minor);
   B2_CUDA(cudaSetDevice(dev));
   *out_dev = dev;
-  *out_sms = prop.multiProcessorCount;
+  *out_sms = sms;
   return B2_OK;
 }
 
