@@ -859,6 +859,12 @@ static int align_once(b2_icp* h, float max_dist, float thr, int print, bool* con
   unsigned long long* chain_base = nullptr;
   unsigned int* chain_overflow = nullptr;
   int chain_pos = 0;
+  if (chain && !h->pack_stream) {
+    int least = 0, greatest = 0;
+    B2_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    B2_CUDA(cudaStreamCreateWithPriority(&h->pack_stream, cudaStreamNonBlocking, greatest));   // its short kernels slot in between K3's tiles
+    B2_CUDA(cudaEventCreateWithFlags(&h->pack_join_ev, cudaEventDisableTiming));
+  }
   if (chain) {
     const size_t bytes = ((size_t)nlocal + 2) * sizeof(unsigned long long);
     B2_TRY(h->chain_dev.ensure(bytes)); B2_TRY(h->pin_chain.ensure(sizeof(unsigned int)));
@@ -1169,11 +1175,7 @@ int b2_icp_create(const b2_icp_config* cfg, b2_icp** out) {
     B2_CUDA(cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
   }
   B2_CUDA(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
-  {
-    int least = 0, greatest = 0;
-    B2_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    B2_CUDA(cudaStreamCreateWithPriority(&h->pack_stream, cudaStreamNonBlocking, greatest));   // its short kernels slot in between K3's tiles
-    B2_CUDA(cudaEventCreateWithFlags(&h->pack_join_ev, cudaEventDisableTiming));
+  {   // (the pack stream itself is created on first use: a stream of another priority is a new channel for the driver, tens of ms)
     if (const char* e = getenv("B2_PACK")) { const std::string v(e); h->pack_overlap = v == "overlap" || v == "overlap_nosize"; h->pack_presize = v != "overlap_nosize"; }
   }
   for (auto& e : h->ev) B2_CUDA(cudaEventCreate(&e));
