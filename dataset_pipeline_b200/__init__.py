@@ -9,4 +9,5 @@ from .icp import Comm, PointToPlaneICP, find_correspondences  # noqa: F401
 from .normals import NormalEstimationTwoPassOMP, estimate_normals, estimate_normals_radius  # noqa: F401
 from .registration import Registration  # noqa: F401
 from .multiscale import CreateMultiScalePointCloud, DeterminePointNeighbors, MergeClosePoints  # noqa: F401
+from .scan_aligner import align_scans, scale_schedule  # noqa: F401
 from .cleaner import LocalStatisticalOutlierRemoval, clean_point_cloud, create_splats, mesh_squared_distance  # noqa: F401
