@@ -379,3 +379,19 @@ def test_reference_renderer_pixel_accuracy_through_the_abi(oracle, idx):
     # fisheye vertex stage: device atanf vs the oracle's correctly rounded one can move a vertex by an ulp, i.e. flip single edge pixels
     assert same.mean() > (0.9995 if model in (oracle.CAM_BENCHMARK, oracle.CAM_FISHEYE_POLYNOMIAL_4, oracle.CAM_FISHEYE_POLYNOMIAL_TANGENTIAL,
                                                oracle.CAM_RADIAL_FISHEYE, oracle.CAM_SIMPLE_RADIAL_FISHEYE, oracle.CAM_FOV) else 0.99999), (name, same.mean())
+
+
+@pytest.mark.skipif(not os.environ.get("B2_TEST_FOURFRAME"), reason="opt-in (B2_TEST_FOURFRAME=1): written after this round's GPU budget was spent, "
+                    "green on the oracle (tests/test_oracle_reg.py::test_reference_four_frame_alignment), not yet run on hardware")
+@pytest.mark.parametrize("fixed,variable,rig", [(True, False, False), (True, True, False), (True, False, True), (True, True, True)])
+def test_reference_four_frame_alignment_through_the_abi(fixed, variable, rig):
+    """test_alignment.cc:86-634 through the C ABI (see tests/ref_alignment4.py)."""
+    import dataset_pipeline_b200 as b2
+    from dataset_pipeline_b200 import multiscale as MS
+    from dataset_pipeline_b200 import registration as R
+    from tests import ref_alignment4 as R4
+    worst, flow, log = R4.run_four_frame(
+        lambda **kw: b2.Registration(R.default_params(**kw)),
+        lambda reg, scans, count, fw: MS.ComputeMultiResPointCloud(reg, scans, count, fw, 5, 25, 0),
+        lambda reg, it, thr, no: reg.RunOnCurrentScale(it, thr, no), lambda reg: reg.get_state(), fixed, variable, rig)
+    assert worst <= R4.TEST_THRESHOLD and flow <= R4.FLOW_THRESHOLD, (worst, flow, log)

@@ -258,6 +258,24 @@ def test_reference_simple_two_frame_alignment(oracle, key):
     assert terr <= RA.TRANSLATION_THRESHOLD and ang <= RA.ROTATION_THRESHOLD_DEG, (terr, ang, log)
 
 
+# ---- test_alignment.cc:86-634 (Test4FrameAlignment = the four active FourFrame_* tests) on the oracle -------------------------------
+@pytest.mark.parametrize("name,fixed,variable,rig", [("FourFrame_FixedColorsOnly", True, False, False),
+                                                     ("FourFrame_FixedAndVariableColors", True, True, False),
+                                                     ("FourFrame_FixedColorsOnly_Rig", True, False, True),
+                                                     ("FourFrame_FixedAndVariableColors_Rig", True, True, True)])
+def test_reference_four_frame_alignment(oracle, name, fixed, variable, rig):
+    """Multi-resolution cloud from the rendered views, Tukey weights, splat occlusion, (rig extrinsics,) RunOnCurrentScale over the image
+    scales from a perturbed start; the reference's pass criteria (test_alignment.cc:541, :592). FourFrame_DepthResidualVerification
+    needs the depth-residual branch (not built); the other FourFrame tests are commented out in the reference."""
+    from tests import ref_alignment4 as R4
+    worst, flow, log = R4.run_four_frame(
+        lambda **kw: oracle.Registration(oracle.reg_default_params(**kw)),
+        lambda reg, scans, count, fw: oracle.ms_compute_multi_res_point_cloud(reg, scans, count, fw, 5, 25, 0),
+        lambda reg, it, thr, no: reg.run_on_current_scale(it, thr, no), lambda reg: reg.get_state(), fixed, variable, rig)
+    assert worst <= R4.TEST_THRESHOLD and flow <= R4.FLOW_THRESHOLD, (name, worst, flow, log)
+    assert [s for s, *_ in log] == [1, 0]                     # 256 -> 128 -> 64 px pyramid, optimised at scales 1 and 0
+
+
 # ---- test_renderer.cc:43-315 (depth assertions) on the oracle's software rasteriser ----------------------------------------------
 def _render_ref_mesh(reg, model, params, verts, faces):
     reg.add_intrinsics(640, 480, params, camera_model=model)
