@@ -3,15 +3,18 @@
 // Static index, once per cloud and search radius, in the CLOUD's own frame (a rigid transform maps a uniform grid to a uniform
 // grid, so the index survives every pose update; replaces the per-pair kd-tree build, icp_point_to_plane.cc:46-51):
 //   K1  k_bbox / k_keys / k_gather_sorted   cell keys of the cloud-frame points, cell-sorted copies, inverse permutation
-//   K2  k_count_cells / k_hash_cells        occupied-cell hash table over the sorted keys
+//   K2  k_mark_cells / k_word_counts / k_word_prefix / k_cell_starts / k_corner_occupancy   (grids up to 2^31 cells) rank bitmap,
+//       first point of every occupied cell, one occupancy byte per lattice corner;  k_hash_cells: occupied-cell hash beyond
 // Per outer iteration:
 //   K1x k_xform_sorted     global-frame copies of the sorted points + chunk boxes + AABB in ONE streaming pass
 //                          (replaces pcl::transformPointCloudWithNormals + bbox loops, icp_point_to_plane.cc:189-205)
-//   K3  k_nn_tiles         nearest target within radius per source point (replaces the radiusSearch loop, :63-102):
-//                          CTA-cooperative — query tiles staged in shared memory by the bulk-copy engine, own cells per thread,
-//                          neighbour cells through a shared-memory work queue drained by full warps
-//   K4  k_scan_tiles / k_pack_tiles   48 B packed correspondence records (p_s,n_s,p_t,n_t), three float4 planes
-//   K5  k_accumulate       one streaming pass: cost + 6x6 S + 6-vector g per correspondence set, fp64
+//   K3  k_nn_tiles         nearest target within radius per source point (replaces the radiusSearch loop, :63-102): persistent CTAs
+//                          over the longest-first tile order, warp-autonomous tiles of 32 queries staged (and prefetched) in shared
+//                          memory by the bulk-copy engine, own cell per lane, occupied neighbour cells (corner map) through a per-warp
+//                          work queue, dense cells by the whole warp
+//   K4  k_scan_tiles / k_pack_tiles   48 B packed correspondence records, three float4 planes with source / target values interleaved
+//   K5  k_accumulate_tma   one streaming pass over bulk-copied record tiles: cost + 6x6 S + 6-vector g per correspondence set in fp64,
+//                          plus the costs of up to three further LM tries in packed fp32 (FFMA2); k_accumulate = register-staged variant
 //                          (replaces compute() loops, icp_point_to_plane_impl.h:129-211 and :240-266)
 //   K6  k_finalize         fixed-order reduction of the per-CTA partials + assembly of the normal equations
 //                          with the reference's upper-triangle quirk (impl.h:82-113 + :226)
